@@ -1,0 +1,182 @@
+/* rsrgan_b200 -- C ABI of the B200-native (sm_100a) RSRGAN GAN-training hot path.
+ *
+ * The reference (wangkenpu/rsrgan) has no FFI: its hot path is inline TensorFlow-1 ops.
+ * Each entry point below replaces one group of those TF call sites (cited as
+ * reference file:line, paths relative to the reference root) and is what a ctypes / cffi /
+ * pybind stub on the reference side would bind.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     immediately; nothing synchronises, allocates persistent memory or throws;
+ *   - return value: 0 = ok, > 0 = cudaError_t, < 0 = argument / shape error (RSR_E_*);
+ *   - 16-bit tensors ("h16") hold IEEE fp16 or bf16 according to the handle's dtype;
+ *   - internal sequence tensors are TIME-major: row index = t * B + b;
+ *   - there is no CPU fallback: without an sm_100 device every compute call fails.
+ */
+#ifndef RSRGAN_B200_H_
+#define RSRGAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSR_E_ARG (-1)      /* null / misaligned pointer, non-positive size           */
+#define RSR_E_SHAPE (-2)    /* shape the kernels do not support (see each function)  */
+#define RSR_E_NODEV (-3)    /* no sm_100 device / driver entry point missing         */
+#define RSR_E_RESIDENT (-4) /* persistent kernel would not be co-resident            */
+
+#define RSR_DTYPE_F16 0
+#define RSR_DTYPE_BF16 1
+
+/* activations of tf.contrib.layers.fully_connected call sites */
+#define RSR_ACT_NONE 0
+#define RSR_ACT_RELU 1  /* models/discriminator_dnn.py:61-90, models/dnn.py:79-110 */
+#define RSR_ACT_LRELU 2 /* utils/ops.py:120-121 leakyrelu(alpha=0.3), models/lstm.py:82-87 */
+#define RSR_ACT_CLIP 3  /* models/discriminator_dnn.py:93 clip_by_value(-0.5, 1.5) */
+
+typedef struct rsr_handle rsr_handle;
+
+/* library / handle ------------------------------------------------------------------ */
+int rsr_version(void);
+/* Creates the per-rank handle (tensor-map cache, barrier workspace). dtype = RSR_DTYPE_*. */
+int rsr_create(rsr_handle** out, int device, int dtype);
+int rsr_destroy(rsr_handle* h);
+int rsr_num_sms(rsr_handle* h);
+
+/* GEMM with fused epilogue on the tcgen05 tensor cores ------------------------------- */
+/* D[M,N] = epi(alpha * A[M,K] * B[K,N]) ; A and B are h16 operands fed by TMA.
+ *   a_mn = 0: A stored row-major [M, lda] (K contiguous);  a_mn = 1: A stored [K, lda] (M contiguous)
+ *   b_mn = 0: B stored [N, ldb] (K contiguous);             b_mn = 1: B stored row-major [K, ldb] (N contiguous)
+ * epi(v): v += bias[n]; v += resid[m,n]; v = act(v); v *= act'(dact_src[m,n]) ; v += beta*out32_old
+ * Replaces tf.contrib.layers.fully_connected (models/lstm.py:82-87,121-124,
+ * models/discriminator_dnn.py:61-93, models/discriminator_lstm.py:100-104), the input half of
+ * LSTMCell's _Linear (models/lstm.py:90-96) hoisted over all frames, and their gradients. */
+typedef struct rsr_gemm_args {
+    int M, N, K;
+    const void* A; int lda; int a_mn;
+    const void* B; int ldb; int b_mn;
+    float alpha, beta;
+    const float* bias;            /* [N] or NULL */
+    const float* resid; int ldr;  /* fp32 [M, ldr] or NULL */
+    int act;                      /* RSR_ACT_* applied to the value */
+    const void* dact_src; int ldd; int dact; /* h16 [M, ldd]: multiply by derivative of RSR_ACT_{RELU,LRELU} at that OUTPUT value */
+    float* out32; int ldc32;      /* fp32 output or NULL */
+    void* out16; int ldc16;       /* h16 output or NULL  */
+    int tile_n;                   /* 0 = auto */
+} rsr_gemm_args;
+int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a);
+
+/* input staging ---------------------------------------------------------------------- */
+/* x fp32 batch-major (B, T, D) -> h16 time-major [T*B, ld16] (and optional fp32 copy [T*B, ld32]):
+ *   v = (x - mean[d]) * istd[d]   (mean/istd NULL = identity; io_funcs/make_tfrecords.py:84-87)
+ *   v += noise[b, d]              (noise NULL = none; utils/ops.py:19-30 draws ONE (B,1,D) vector
+ *                                  per utterance, broadcast over time; models/discriminator_lstm.py:60)
+ * time_major_in != 0: x is already [T*B, ldx] fp32 time-major (used for G outputs fed to D). */
+int rsr_stage_input(rsr_handle* h, void* stream, const float* x, int ldx, int time_major_in,
+                    int B, int T, int D, const float* mean, const float* istd, const float* noise,
+                    void* out16, int ld16, float* out32, int ld32);
+/* fp32 time-major [T*B, ld] -> fp32 batch-major (B, T, D), optional decode CMVN y*std+mean
+ * (scripts/train_gan_rnn_placeholder.py:286-287). */
+int rsr_unstage_output(rsr_handle* h, void* stream, const float* y_tm, int ld, int B, int T, int D,
+                       const float* mean, const float* std, float* out_bm);
+/* CMVN on flat (N, D) matrices: out = (x - mean) / std, io_funcs/make_tfrecords.py:84-87;
+ * inverse: out = y * std + mean, scripts/train_gan_rnn_placeholder.py:286-287. */
+int rsr_cmvn_apply(rsr_handle* h, void* stream, const float* x, const float* mean, const float* std,
+                   long long N, int D, float* out);
+int rsr_cmvn_invert(rsr_handle* h, void* stream, const float* y, const float* mean, const float* std,
+                    long long N, int D, float* out);
+
+/* LSTMP (tf.contrib.rnn.LSTMCell(use_peepholes, num_proj, forget_bias=1) under
+ * tf.nn.dynamic_rnn(sequence_length)) ------------------------------------------------- */
+/* Call sites: models/lstm.py:89-112, models/res_lstm_l.py:86-138, models/discriminator_lstm.py:70-91;
+ * gate math: models/BNLSTMCell.py:176-213 (order i, j, f, o).
+ *
+ * The recurrence is run in the algebraically folded form
+ *     z_t = Zx_t + mt_{t-1} * Wc ,  Wc = W_proj * K_h   (C x 4C),  out_t = mt_t * W_proj
+ * so one persistent kernel does every time step with Wc resident in shared memory and the
+ * projection becomes a batched GEMM outside the loop.  Columns of every 4C-wide tensor are in
+ * PACKED gate order: col = (cell/32)*128 + gate*32 + cell%32, gate in (i, j, f, o); Cp = C padded
+ * to a multiple of 256 with zero weights (padded cells stay exactly 0).
+ *
+ *   zx      fp32 [T*B, 4Cp]   x_t * K_x + bias, packed columns (from rsr_gemm)
+ *   wcT     h16  [4Cp, Cp]    Wc transposed, packed rows (forward MMA A operand)
+ *   w_i,w_f,w_o fp32 [Cp]     peepholes
+ *   lengths int32 [B]         frames t >= lengths[b] are frozen: mt written as 0
+ *   mt_seq  h16  [(T+1)*B, Cp] slot 0 must be zero on entry; slot t+1 receives mt_t
+ *   save    fp32 [T*B, 5, Cp]  (i, f, o, tanh j, c_new) for the backward pass, or NULL
+ */
+int rsr_lstmp_rec_fwd(rsr_handle* h, void* stream, int B, int T, int Cp, const float* zx,
+                      const void* wcT, const float* w_i, const float* w_f, const float* w_o,
+                      float forget_bias, const int* lengths, void* mt_seq, float* save);
+/*   dmt     fp32 [T*B, Cp]    on entry dOut_t * W_proj^T (from rsr_gemm); the kernel adds the
+ *                              recurrent term dz_{t+1} * Wc^T in place (atomics), time-reversed
+ *   wc      h16  [Cp, 4Cp]    Wc, packed columns (backward MMA A operand)
+ *   dz16    h16  [T*B, 4Cp]   gate pre-activation gradients, packed columns (output)
+ *   dbias   fp32 [4Cp] packed, dw_i, dw_f, dw_o fp32 [Cp]: ACCUMULATED into (caller zeroes)
+ */
+int rsr_lstmp_rec_bwd(rsr_handle* h, void* stream, int B, int T, int Cp, float* dmt,
+                      const void* wc, const float* w_i, const float* w_f, const float* w_o,
+                      const int* lengths, const float* save, void* dz16,
+                      float* dbias, float* dw_i, float* dw_f, float* dw_o);
+
+/* losses (models/gan_rnn_placeholder.py:244-260; same formulas models/gan.py:200-208) ---- */
+/* All means run over EVERY element including padded frames (zero-padding of
+ * io_funcs/tfrecords_dataset.py:149-152 is part of the mean).
+ *   d_rl_logit / d_fk_logit : fp32, element i at [i * ld_logit] (D(labels), D(G(x))); either may be NULL
+ *   clip != 0 : the values are PRE-clip outputs of discriminator_dnn; the kernel applies
+ *               clip_by_value(-0.5, 1.5) (models/discriminator_dnn.py:93) and zeroes the gradient outside
+ *   g, y      : fp32 [n_frames, ldg|ldy] generator output and labels (same row order); both or neither
+ *   losses[0..3] += d_rl_loss, d_fk_loss, g_adv_loss, g_mse_loss  (caller zeroes; atomics)
+ *       d_rl = mean((D(y)-d_real)^2)  d_fk = mean((D(g)-d_fake)^2)  g_adv = mean((D(g)-d_real)^2)
+ *       g_mse = 0.5 * D_out * mean((g-y)^2)
+ *   gradients (each may be NULL), h16 element i at [i * ld_grad], times the static loss scale gscale:
+ *       d_rl_grad = 2 (D(y)-d_real)/n   d_fk_grad = 2 (D(g)-d_fake)/n   g_adv_grad = 2 (D(g)-d_real)/n
+ *   dg_mse fp32 [n_frames, lddg] = gscale * lambda * (g - y) / n_frames     (d(lambda*g_mse)/dg) */
+int rsr_lsgan_mse_losses(rsr_handle* h, void* stream, const float* d_rl_logit, const float* d_fk_logit,
+                         int ld_logit, long long n_logit, int clip, const float* g, int ldg,
+                         const float* y, int ldy, long long n_frames, int D_out, float d_real,
+                         float d_fake, float lambda, float gscale, float* losses, void* d_rl_grad,
+                         void* d_fk_grad, void* g_adv_grad, int ld_grad, float* dg_mse, int lddg);
+
+/* column sums: out[n] (+)= sum_m X16[m, n]  (bias gradients) */
+int rsr_colsum16(rsr_handle* h, void* stream, const void* x16, int ld, long long M, int N,
+                 float* out, int accumulate);
+int rsr_colsum32(rsr_handle* h, void* stream, const float* x32, int ld, long long M, int N,
+                 float* out, int accumulate);
+
+/* update (models/gan_rnn_placeholder.py:144-150,177-189; utils/ops.py:343-376) ---------- */
+/* One flat fp32 parameter buffer per network; every tensor (TF variable) is a segment padded to a
+ * multiple of 1024 elements, seg_id[k] = segment of the k-th 1024-element block (device int32).
+ * Gradients arrive summed over ranks (ncclAllReduce replaces utils/ops.py:343-376
+ * average_gradients) and multiplied by the static loss scale: gmul = 1 / (world_size * loss_scale).
+ *   pass 1  rsr_seg_sumsq : sumsq[s] = sum over segment s of (gmul*g)^2        (zeroed inside)
+ *   pass 2  ghat = gmul*g * max_norm / max(sqrt(sumsq[s]), max_norm)           (tf.clip_by_norm per tensor, :177-182)
+ *           SGD : theta -= lr * ghat                                            (:144)
+ *           Adam: m = b1 m + (1-b1) ghat ; v = b2 v + (1-b2) ghat^2 ;
+ *                 theta -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)       (:147, TF-1 form)
+ *           EMA : ema -= (1 - decay) * (ema - theta_new)                        (:149-150,185-189; ema NULL = skip)
+ *           theta16 = h16(theta_new)      operand copy for the tensor cores (NULL = skip)
+ * hyper (device fp32[8]): [0]=lr [1]=beta1 [2]=beta2 [3]=eps [4]=beta1_power [5]=beta2_power
+ * [6]=lr_t scratch.  Learning rates live on the device so a captured CUDA graph stays valid when
+ * the host decays them (scripts/train_gan_rnn_placeholder.py:525-533).  The Adam call advances
+ * the beta powers exactly as TF's _finish does (initialise [4]=beta1, [5]=beta2). */
+int rsr_seg_sumsq(rsr_handle* h, void* stream, const float* grad, float gmul, const int* seg_id,
+                  long long n_elems, int n_seg, float* sumsq);
+int rsr_clip_sgd_ema(rsr_handle* h, void* stream, const float* grad, float gmul, const int* seg_id,
+                     const float* sumsq, float max_norm, const float* hyper, float ema_decay,
+                     long long n_elems, float* theta, float* ema, void* theta16);
+int rsr_clip_adam_ema(rsr_handle* h, void* stream, const float* grad, float gmul, const int* seg_id,
+                      const float* sumsq, float max_norm, float* hyper, float ema_decay,
+                      long long n_elems, float* theta, float* m, float* v, float* ema, void* theta16);
+
+/* misc ---------------------------------------------------------------------------------- */
+int rsr_cast16(rsr_handle* h, void* stream, const float* x, long long n, void* out16);
+int rsr_fill32(rsr_handle* h, void* stream, float* x, long long n, float v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSRGAN_B200_H_ */

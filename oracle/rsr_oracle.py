@@ -1,0 +1,586 @@
+"""CPU oracle for the RSRGAN GAN-training hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a numpy restatement of the reference math (wangkenpu/rsrgan) for
+the path `models/gan_rnn_placeholder.py` drives.  It is the *checker*: only
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / reference
+leg may import it.  Nothing under `rsrgan_b200/` imports it and the product has
+no CPU fallback.
+
+PARITY UNPINNED: all arithmetic of the reference lives in TensorFlow 1.4.0
+(unvendored, not installable here: no python2, no `tensorflow`, no network), and
+the reference ships no golden vectors for this path.  The
+oracle is therefore pinned only by (i) an independent torch-autograd float64
+implementation of the same forward (`oracle/torch_ref.py`; must agree to
+1e-9), (ii) finite-difference gradient checks, (iii) torch.nn.LSTM(proj_size)
+cross-check with peepholes zeroed and gates re-ordered, and (iv) for the Kaldi
+ark reader the reference's own `io_funcs/kaldi_io.py`, which does import here
+(fixtures under tests/golden/ made by `oracle/make_golden.py`).
+
+Every function cites the reference file:line it follows (paths relative to the
+reference root).  Default dtype is float64; pass float32 arrays to get a
+float32 run of the same statement.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+
+# --------------------------------------------------------------------------
+# elementary pieces
+# --------------------------------------------------------------------------
+
+
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def leakyrelu(x, alpha=0.3):
+    """utils/ops.py:120-121  tf.maximum(x, alpha*x)."""
+    return np.maximum(x, alpha * x)
+
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_CLIP = 0, 1, 2, 3
+
+
+def act_fwd(u, act):
+    if act == ACT_NONE:
+        return u
+    if act == ACT_RELU:
+        return np.maximum(u, 0.0)
+    if act == ACT_LRELU:
+        return leakyrelu(u)
+    if act == ACT_CLIP:  # discriminator_dnn.py:93 clip_by_value(y, -0.5, 1.5)
+        return np.clip(u, -0.5, 1.5)
+    raise ValueError(act)
+
+
+def act_bwd(u, dy, act):
+    if act == ACT_NONE:
+        return dy
+    if act == ACT_RELU:
+        return dy * (u > 0)
+    if act == ACT_LRELU:
+        # maximum(u, .3u): slope 1 for u>0, .3 for u<0 (u==0: TF splits; measure-zero)
+        return dy * np.where(u > 0, 1.0, 0.3)
+    if act == ACT_CLIP:  # TF clip_by_value gradient: pass inside [lo, hi]
+        return dy * ((u >= -0.5) & (u <= 1.5))
+    raise ValueError(act)
+
+
+def linear_fwd(x, W, b, act=ACT_NONE):
+    """tf.contrib.layers.fully_connected over the last axis
+    (lstm.py:82-87,121-124; discriminator_dnn.py:61-93; discriminator_lstm.py:100-104)."""
+    u = x @ W + b
+    return act_fwd(u, act), (x, W, u, act)
+
+
+def linear_bwd(dy, cache):
+    x, W, u, act = cache
+    du = act_bwd(u, dy, act)
+    x2 = x.reshape(-1, x.shape[-1])
+    du2 = du.reshape(-1, du.shape[-1])
+    dW = x2.T @ du2
+    db = du2.sum(0)
+    dx = du @ W.T
+    return dx, dW, db
+
+
+# --------------------------------------------------------------------------
+# LSTMP cell with peepholes == tf.contrib.rnn.LSTMCell(use_peepholes=True,
+# num_proj=P, forget_bias=1.0) under tf.nn.dynamic_rnn(sequence_length=...)
+# call sites lstm.py:89-112, res_lstm_l.py:86-138, discriminator_lstm.py:70-91;
+# in-repo statement of the same gate math: models/BNLSTMCell.py:160-216
+# (gate order i, j, f, o at :176-179; peepholes/forget_bias at :191-192,203;
+# bias-free projection at :207-213).
+# --------------------------------------------------------------------------
+
+
+def lstmp_fwd(x, lengths, K, b, w_i, w_f, w_o, W_p, forget_bias=1.0):
+    """x (B,T,I) batch-major; K ((I+P),4C) with rows [inputs ; m_prev];
+    returns out (B,T,P) (zero past lengths[b]) and a cache for lstmp_bwd."""
+    B, T, I = x.shape
+    C = w_i.shape[0]
+    P = W_p.shape[1]
+    dt = x.dtype
+    c = np.zeros((B, C), dt)
+    m = np.zeros((B, P), dt)
+    out = np.zeros((B, T, P), dt)
+    steps = []
+    lengths = np.asarray(lengths).astype(np.int64)
+    for t in range(T):
+        act = (t < lengths)[:, None]
+        xin = np.concatenate([x[:, t], m], axis=1)
+        z = xin @ K + b
+        zi, zj, zf, zo = z[:, :C], z[:, C:2 * C], z[:, 2 * C:3 * C], z[:, 3 * C:]
+        ig = sigmoid(zi + w_i * c)
+        fg = sigmoid(zf + forget_bias + w_f * c)
+        jg = np.tanh(zj)
+        c_new = fg * c + ig * jg
+        og = sigmoid(zo + w_o * c_new)
+        tc = np.tanh(c_new)
+        mt = og * tc
+        m_new = mt @ W_p
+        steps.append((xin, c, ig, fg, jg, og, tc, c_new, mt, act))
+        out[:, t] = np.where(act, m_new, 0.0)
+        c = np.where(act, c_new, c)
+        m = np.where(act, m_new, m)
+    cache = (x.shape, K, w_i, w_f, w_o, W_p, steps)
+    return out, cache
+
+
+def lstmp_bwd(dout, cache):
+    (B, T, I), K, w_i, w_f, w_o, W_p, steps = cache
+    C = w_i.shape[0]
+    P = W_p.shape[1]
+    dt = dout.dtype
+    dx = np.zeros((B, T, I), dt)
+    dK = np.zeros_like(K)
+    db = np.zeros(4 * C, dt)
+    dw_i = np.zeros(C, dt)
+    dw_f = np.zeros(C, dt)
+    dw_o = np.zeros(C, dt)
+    dW_p = np.zeros_like(W_p)
+    dm_next = np.zeros((B, P), dt)
+    dc_next = np.zeros((B, C), dt)
+    for t in range(T - 1, -1, -1):
+        xin, c_prev, ig, fg, jg, og, tc, c_new, mt, act = steps[t]
+        a = act.astype(dt)
+        dm = (dout[:, t] + dm_next) * a          # active rows only
+        dmt = dm @ W_p.T
+        dW_p += mt.T @ dm
+        do_pre = dmt * tc * og * (1 - og)
+        dc = (dc_next * a) + dmt * og * (1 - tc * tc) + do_pre * w_o
+        dw_o += (do_pre * c_new).sum(0)
+        df_pre = dc * c_prev * fg * (1 - fg)
+        di_pre = dc * jg * ig * (1 - ig)
+        dzj = dc * ig * (1 - jg * jg)
+        dc_prev = dc * fg + df_pre * w_f + di_pre * w_i
+        dw_f += (df_pre * c_prev).sum(0)
+        dw_i += (di_pre * c_prev).sum(0)
+        dz = np.concatenate([di_pre, dzj, df_pre, do_pre], axis=1)
+        db += dz.sum(0)
+        dK += xin.T @ dz
+        dxin = dz @ K.T
+        dx[:, t] = dxin[:, :I]
+        # frozen rows pass their state gradient straight through
+        dm_next = dxin[:, I:] + dm_next * (1 - a)
+        dc_next = dc_prev + dc_next * (1 - a)
+    return dx, dict(kernel=dK, bias=db, w_i_diag=dw_i, w_f_diag=dw_f,
+                    w_o_diag=dw_o, proj=dW_p)
+
+
+# --------------------------------------------------------------------------
+# parameter containers (names follow SURVEY.md App. B == TF-1.4 variable names)
+# --------------------------------------------------------------------------
+
+
+def _cell_names(prefix):
+    return [prefix + s for s in ("kernel", "bias", "w_f_diag", "w_i_diag",
+                                 "w_o_diag", "projection/kernel")]
+
+
+def xavier(rng, shape, dtype=np.float64):
+    """tf.contrib.layers.xavier_initializer(): U(+-sqrt(6/(fan_in+fan_out)))."""
+    if len(shape) == 1:
+        fan_in = fan_out = shape[0]
+    else:
+        fan_in, fan_out = shape[0], shape[1]
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, size=shape).astype(dtype)
+
+
+def _init_cell(p, rng, prefix, I, C, P, dtype):
+    p[prefix + "kernel"] = xavier(rng, (I + P, 4 * C), dtype)
+    p[prefix + "bias"] = np.zeros(4 * C, dtype)
+    p[prefix + "w_f_diag"] = xavier(rng, (C,), dtype)
+    p[prefix + "w_i_diag"] = xavier(rng, (C,), dtype)
+    p[prefix + "w_o_diag"] = xavier(rng, (C,), dtype)
+    p[prefix + "projection/kernel"] = xavier(rng, (C, P), dtype)
+
+
+def init_g_lstm(rng, in_dim=257, out_dim=40, cell=760, proj=280, layers=3,
+                dtype=np.float64):
+    """models/lstm.py:43-45,82-124 (ref-native sizes are the defaults)."""
+    p = OrderedDict()
+    p["g_model/fully_connected/weights"] = xavier(rng, (in_dim, proj), dtype)
+    p["g_model/fully_connected/biases"] = np.zeros(proj, dtype)
+    for l in range(layers):
+        _init_cell(p, rng, "g_model/rnn/multi_rnn_cell/cell_%d/lstm_cell/" % l,
+                   proj, cell, proj, dtype)
+    p["g_model/fully_connected_1/weights"] = xavier(rng, (proj, out_dim), dtype)
+    p["g_model/fully_connected_1/biases"] = np.zeros(out_dim, dtype)
+    return p
+
+
+def init_g_res_lstm_l(rng, in_dim=257, out_dim=40, cell=760, layers=4,
+                      dtype=np.float64):
+    """models/res_lstm_l.py:43-45,101-138,187-194 (proj == in_dim == 257)."""
+    p = OrderedDict()
+    for l in range(1, layers + 1):
+        _init_cell(p, rng, "g_model/lstm_cell_%d/rnn/lstm_cell/" % l,
+                   in_dim, cell, in_dim, dtype)
+    p["g_model/forward_out/fully_connected/weights"] = xavier(rng, (in_dim, out_dim), dtype)
+    p["g_model/forward_out/fully_connected/biases"] = np.zeros(out_dim, dtype)
+    return p
+
+
+def init_d_lstm(rng, in_dim=40, cell=256, proj=40, layers=2, dtype=np.float64):
+    """models/discriminator_lstm.py:26-28,70-104."""
+    p = OrderedDict()
+    for l in range(layers):
+        _init_cell(p, rng, "d_model/rnn/multi_rnn_cell/cell_%d/lstm_cell/" % l,
+                   in_dim if l == 0 else proj, cell, proj, dtype)
+    p["d_model/fully_connected/weights"] = xavier(rng, (proj, 1), dtype)
+    p["d_model/fully_connected/biases"] = np.zeros(1, dtype)
+    return p
+
+
+def init_d_dnn(rng, in_dim=40, units=1024, hidden=3, dtype=np.float64):
+    """models/discriminator_dnn.py:23-27,61-93: truncN(0, sqrt(2/units)) hidden
+    weights (truncation at 2 sigma), xavier output layer, zero biases."""
+    p = OrderedDict()
+    std = math.sqrt(2.0 / units)
+
+    def truncn(shape):
+        v = rng.standard_normal(size=shape)
+        bad = np.abs(v) > 2
+        while bad.any():
+            v[bad] = rng.standard_normal(size=int(bad.sum()))
+            bad = np.abs(v) > 2
+        return (v * std).astype(dtype)
+
+    dims = [in_dim] + [units] * (hidden + 1)
+    for l in range(hidden + 1):
+        name = "d_model/fully_connected" + ("" if l == 0 else "_%d" % l)
+        p[name + "/weights"] = truncn((dims[l], dims[l + 1]))
+        p[name + "/biases"] = np.zeros(dims[l + 1], dtype)
+    name = "d_model/fully_connected_%d" % (hidden + 1)
+    p[name + "/weights"] = xavier(rng, (units, 1), dtype)
+    p[name + "/biases"] = np.zeros(1, dtype)
+    return p
+
+
+# --------------------------------------------------------------------------
+# networks: forward returns (y, cache); backward returns (dx, grads-dict)
+# --------------------------------------------------------------------------
+
+
+def _cell_params(p, prefix):
+    return (p[prefix + "kernel"], p[prefix + "bias"], p[prefix + "w_i_diag"],
+            p[prefix + "w_f_diag"], p[prefix + "w_o_diag"], p[prefix + "projection/kernel"])
+
+
+def _cell_grads(g, prefix, cg):
+    g[prefix + "kernel"] = cg["kernel"]
+    g[prefix + "bias"] = cg["bias"]
+    g[prefix + "w_f_diag"] = cg["w_f_diag"]
+    g[prefix + "w_i_diag"] = cg["w_i_diag"]
+    g[prefix + "w_o_diag"] = cg["w_o_diag"]
+    g[prefix + "projection/kernel"] = cg["proj"]
+
+
+def _cell_prefixes(p, scope):
+    pre = sorted({k[:-len("kernel")] for k in p
+                  if k.startswith(scope) and k.endswith("lstm_cell/kernel")})
+    return pre
+
+
+def g_lstm_fwd(p, x, lengths):
+    """models/lstm.py:82-124: FC(leakyrelu .3) -> stacked LSTMP -> FC(linear).
+    MultiRNNCell per-timestep stacking == layer-after-layer over the sequence."""
+    caches = []
+    h, c0 = linear_fwd(x, p["g_model/fully_connected/weights"],
+                       p["g_model/fully_connected/biases"], ACT_LRELU)
+    caches.append(c0)
+    for pre in _cell_prefixes(p, "g_model/rnn/"):
+        h, cc = lstmp_fwd(h, lengths, *_cell_params(p, pre))
+        caches.append(cc)
+    y, c1 = linear_fwd(h, p["g_model/fully_connected_1/weights"],
+                       p["g_model/fully_connected_1/biases"], ACT_NONE)
+    caches.append(c1)
+    return y, caches
+
+
+def g_lstm_bwd(p, dy, caches):
+    g = OrderedDict()
+    dh, dW, db = linear_bwd(dy, caches[-1])
+    g["g_model/fully_connected_1/weights"] = dW
+    g["g_model/fully_connected_1/biases"] = db
+    pres = _cell_prefixes(p, "g_model/rnn/")
+    for l in range(len(pres) - 1, -1, -1):
+        dh, cg = lstmp_bwd(dh, caches[1 + l])
+        _cell_grads(g, pres[l], cg)
+    dx, dW, db = linear_bwd(dh, caches[0])
+    g["g_model/fully_connected/weights"] = dW
+    g["g_model/fully_connected/biases"] = db
+    return dx, g
+
+
+def g_res_lstm_l_fwd(p, x, lengths, residual=True):
+    """models/res_lstm_l.py:101-138,187-194: x_{l+1} = LSTMP_l(x_l) + x_l,
+    y = FC(out_L + x_L).  residual=False is models/res_lstm_base.py:111-131,190."""
+    caches = []
+    xin = x
+    pres = _cell_prefixes(p, "g_model/lstm_cell_")
+    for pre in pres:
+        o, cc = lstmp_fwd(xin, lengths, *_cell_params(p, pre))
+        caches.append(cc)
+        xin = o + xin if residual else o
+    y, c1 = linear_fwd(xin, p["g_model/forward_out/fully_connected/weights"],
+                       p["g_model/forward_out/fully_connected/biases"], ACT_NONE)
+    caches.append(c1)
+    return y, caches
+
+
+def g_res_lstm_l_bwd(p, dy, caches, residual=True):
+    g = OrderedDict()
+    dxin, dW, db = linear_bwd(dy, caches[-1])
+    g["g_model/forward_out/fully_connected/weights"] = dW
+    g["g_model/forward_out/fully_connected/biases"] = db
+    pres = _cell_prefixes(p, "g_model/lstm_cell_")
+    for l in range(len(pres) - 1, -1, -1):
+        dprev, cg = lstmp_bwd(dxin, caches[l])
+        _cell_grads(g, pres[l], cg)
+        dxin = dprev + dxin if residual else dprev
+    return dxin, g
+
+
+def d_lstm_fwd(p, x, lengths, noise=None):
+    """models/discriminator_lstm.py:60-104.  `noise` is the (B,1,D) draw of
+    utils/ops.py:19-30 (already scaled by disc_noise_std); None == std 0."""
+    caches = []
+    h = x if noise is None else x + noise
+    for pre in _cell_prefixes(p, "d_model/rnn/"):
+        h, cc = lstmp_fwd(h, lengths, *_cell_params(p, pre))
+        caches.append(cc)
+    y, c1 = linear_fwd(h, p["d_model/fully_connected/weights"],
+                       p["d_model/fully_connected/biases"], ACT_NONE)
+    caches.append(c1)
+    return y, caches
+
+
+def d_lstm_bwd(p, dy, caches):
+    g = OrderedDict()
+    dh, dW, db = linear_bwd(dy, caches[-1])
+    g["d_model/fully_connected/weights"] = dW
+    g["d_model/fully_connected/biases"] = db
+    pres = _cell_prefixes(p, "d_model/rnn/")
+    for l in range(len(pres) - 1, -1, -1):
+        dh, cg = lstmp_bwd(dh, caches[l])
+        _cell_grads(g, pres[l], cg)
+    return dh, g
+
+
+def _dnn_names(p):
+    names = sorted({k.rsplit("/", 1)[0] for k in p if k.startswith("d_model/fully_connected")},
+                   key=lambda s: int(s.split("_")[-1]) if s[-1].isdigit() else 0)
+    return names
+
+
+def d_dnn_fwd(p, x, lengths=None, noise=None):
+    """models/discriminator_dnn.py:61-93 applied per frame (fully_connected
+    broadcasts over leading dims; SURVEY App. C-15 adapter: lengths ignored)."""
+    caches = []
+    h = x
+    names = _dnn_names(p)
+    for n in names[:-1]:
+        h, c = linear_fwd(h, p[n + "/weights"], p[n + "/biases"], ACT_RELU)
+        caches.append(c)
+    y, c = linear_fwd(h, p[names[-1] + "/weights"], p[names[-1] + "/biases"], ACT_CLIP)
+    caches.append(c)
+    return y, caches
+
+
+def d_dnn_bwd(p, dy, caches):
+    g = OrderedDict()
+    names = _dnn_names(p)
+    dh = dy
+    for n, c in zip(reversed(names), reversed(caches)):
+        dh, dW, db = linear_bwd(dh, c)
+        g[n + "/weights"] = dW
+        g[n + "/biases"] = db
+    return dh, g
+
+
+GENERATORS = {
+    "lstm": (g_lstm_fwd, g_lstm_bwd),
+    "res_lstm_l": (g_res_lstm_l_fwd, g_res_lstm_l_bwd),
+    "res_lstm_base": (lambda p, x, l: g_res_lstm_l_fwd(p, x, l, False),
+                      lambda p, dy, c: g_res_lstm_l_bwd(p, dy, c, False)),
+}
+DISCRIMINATORS = {
+    "lstm": (d_lstm_fwd, d_lstm_bwd),
+    "dnn": (d_dnn_fwd, d_dnn_bwd),
+}
+
+# --------------------------------------------------------------------------
+# losses  (models/gan_rnn_placeholder.py:244-260; same formulas models/gan.py:200-208)
+# --------------------------------------------------------------------------
+
+
+def lsgan_mse_losses(d_rl_logits, d_fk_logits, g, y, d_real=1.0, d_fake=0.0,
+                     mse_lambda=10.0, output_dim=40):
+    """All means are over every element including padded frames (App. C-1)."""
+    d_rl = np.mean((d_rl_logits - d_real) ** 2)
+    d_fk = np.mean((d_fk_logits - d_fake) ** 2)
+    g_adv = np.mean((d_fk_logits - d_real) ** 2)
+    g_mse = 0.5 * np.mean((g - y) ** 2) * output_dim
+    return dict(d_rl_loss=d_rl, d_fk_loss=d_fk, d_loss=d_rl + d_fk,
+                g_adv_loss=g_adv, g_mse_loss=g_mse, g_l2_loss=0.0,
+                g_loss=g_adv + mse_lambda * g_mse)
+
+
+def l2_loss_g(p, l2_scale):
+    """gan_rnn_placeholder.py:253-258: l2_scale * sum(0.5*||v||^2) over G vars
+    whose name does not contain "bias"."""
+    return l2_scale * sum(0.5 * float((v * v).sum()) for k, v in p.items() if "bias" not in k)
+
+
+# --------------------------------------------------------------------------
+# update rules  (gan_rnn_placeholder.py:144-150,177-189)
+# --------------------------------------------------------------------------
+
+
+def average_gradients(tower_grads):
+    """utils/ops.py:343-376: per-variable mean over towers."""
+    out = OrderedDict()
+    for k in tower_grads[0]:
+        out[k] = np.mean(np.stack([tg[k] for tg in tower_grads], 0), 0)
+    return out
+
+
+def clip_by_norm(g, max_norm=15.0):
+    """tf.clip_by_norm per tensor: g * max_norm / max(||g||, max_norm)."""
+    n = math.sqrt(float((g.astype(np.float64) ** 2).sum()))
+    return g * (max_norm / max(n, max_norm))
+
+
+def sgd_update(p, g, lr):
+    return OrderedDict((k, p[k] - lr * g[k]) for k in p)
+
+
+def adam_update_tf(p, g, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """tf.train.AdamOptimizer: lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
+    theta -= lr_t * m / (sqrt(v) + eps)   (eps on the un-corrected sqrt(v))."""
+    t = t + 1
+    lr_t = lr * math.sqrt(1 - beta2 ** t) / (1 - beta1 ** t)
+    pn, mn, vn = OrderedDict(), OrderedDict(), OrderedDict()
+    for k in p:
+        mn[k] = beta1 * m[k] + (1 - beta1) * g[k]
+        vn[k] = beta2 * v[k] + (1 - beta2) * g[k] * g[k]
+        pn[k] = p[k] - lr_t * mn[k] / (np.sqrt(vn[k]) + eps)
+    return pn, mn, vn, t
+
+
+def ema_update(shadow, p, decay=0.9999):
+    """tf.train.ExponentialMovingAverage(0.9999).apply without num_updates,
+    evaluated on the post-update weights (the tf.group has no ordering; we fix
+    'after')."""
+    return OrderedDict((k, shadow[k] - (1 - decay) * (shadow[k] - p[k])) for k in p)
+
+
+def exponential_decay(iteration, num_jobs, num_iters, init_lr, multiply_jobs=True):
+    """utils/ops.py:378-391."""
+    final = 0.0001 * init_lr
+    if iteration + 1 >= num_iters:
+        cur = final
+    else:
+        cur = init_lr * math.exp(iteration * math.log(final / init_lr) / num_iters)
+    return num_jobs * cur if multiply_jobs else cur
+
+
+# --------------------------------------------------------------------------
+# CMVN  (io_funcs/convert_cmvn_to_numpy.py:29-47; make_tfrecords.py:84-87;
+#        scripts/train_gan_rnn_placeholder.py:286-287)
+# --------------------------------------------------------------------------
+
+
+def cmvn_from_stats(stats):
+    """Kaldi global stats (2, D+1): row0 = sums | count, row1 = sumsq | 0."""
+    n = stats[0][-1]
+    s = stats[:, :-1]
+    mean = s[0] / n
+    std = np.sqrt(s[1] / n - mean ** 2)
+    return mean, std
+
+
+def cmvn_apply(x, mean, std):
+    """(x-mean)/std in float64, stored as float32."""
+    return ((x.astype(np.float64) - mean) / std).astype(np.float32)
+
+
+def cmvn_invert(y, mean, std):
+    """y*std+mean (decode), written to ark as float32 (kaldi_io.py:269)."""
+    return (y * std + mean).astype(np.float32)
+
+
+# --------------------------------------------------------------------------
+# one D update / one G update  (gan_rnn_placeholder.py:169-189,
+# train_gan_rnn_placeholder.py:72-101)
+# --------------------------------------------------------------------------
+
+
+class GanState(object):
+    """Weights + optimizer state of one GAN (all towers share it)."""
+
+    def __init__(self, g_params, d_params, g_type="lstm", d_type="lstm"):
+        self.g, self.d = g_params, d_params
+        self.g_type, self.d_type = g_type, d_type
+        z = lambda p: OrderedDict((k, np.zeros_like(v)) for k, v in p.items())
+        self.adam_m, self.adam_v, self.adam_t = z(g_params), z(g_params), 0
+        self.g_ema = OrderedDict((k, v.copy()) for k, v in g_params.items())
+        self.d_ema = OrderedDict((k, v.copy()) for k, v in d_params.items())
+
+
+def tower_losses_and_grads(st, x, y, lengths, which, noise_rl=None, noise_fk=None,
+                           mse_lambda=10.0, d_real=1.0, d_fake=0.0, l2_scale=0.0):
+    """One tower of build_model_single_gpu (gan_rnn_placeholder.py:191-298) plus
+    compute_gradients wrt d_vars (which='d') or g_vars (which='g')."""
+    gf, gb = GENERATORS[st.g_type]
+    df, db_ = DISCRIMINATORS[st.d_type]
+    g_out, gc = gf(st.g, x, lengths)
+    lr_, crl = df(st.d, y, lengths, noise_rl)
+    lf_, cfk = df(st.d, g_out, lengths, noise_fk)
+    losses = lsgan_mse_losses(lr_, lf_, g_out, y, d_real, d_fake, mse_lambda, y.shape[-1])
+    if l2_scale > 0.0:
+        losses["g_l2_loss"] = l2_loss_g(st.g, l2_scale)
+        losses["g_loss"] += losses["g_l2_loss"]
+    n_logit = lr_.size
+    if which == "d":
+        _, g_rl = db_(st.d, 2.0 * (lr_ - d_real) / n_logit, crl)
+        _, g_fk = db_(st.d, 2.0 * (lf_ - d_fake) / n_logit, cfk)
+        grads = OrderedDict((k, g_rl[k] + g_fk[k]) for k in st.d)
+    else:
+        dg_adv, _ = db_(st.d, 2.0 * (lf_ - d_real) / n_logit, cfk)
+        dg = dg_adv + mse_lambda * 0.5 * y.shape[-1] * 2.0 * (g_out - y) / g_out.size
+        _, gg = gb(st.g, dg, gc)
+        grads = OrderedDict((k, gg[k]) for k in st.g)
+        if l2_scale > 0.0:
+            for k in grads:
+                if "bias" not in k:
+                    grads[k] = grads[k] + l2_scale * st.g[k]
+    return losses, grads, g_out
+
+
+def d_step(st, towers, lr_d, max_norm=15.0, ema_decay=0.9999, **kw):
+    """towers: list of dicts(x, y, lengths, noise_rl, noise_fk). SGD on theta_D."""
+    res = [tower_losses_and_grads(st, t["x"], t["y"], t["lengths"], "d",
+                                  t.get("noise_rl"), t.get("noise_fk"), **kw) for t in towers]
+    avg = average_gradients([r[1] for r in res])
+    clipped = OrderedDict((k, clip_by_norm(v, max_norm)) for k, v in avg.items())
+    st.d = sgd_update(st.d, clipped, lr_d)
+    st.d_ema = ema_update(st.d_ema, st.d, ema_decay)
+    return [r[0] for r in res], clipped
+
+
+def g_step(st, towers, lr_g, max_norm=15.0, ema_decay=0.9999, **kw):
+    res = [tower_losses_and_grads(st, t["x"], t["y"], t["lengths"], "g",
+                                  t.get("noise_rl"), t.get("noise_fk"), **kw) for t in towers]
+    avg = average_gradients([r[1] for r in res])
+    clipped = OrderedDict((k, clip_by_norm(v, max_norm)) for k, v in avg.items())
+    st.g, st.adam_m, st.adam_v, st.adam_t = adam_update_tf(
+        st.g, clipped, st.adam_m, st.adam_v, st.adam_t, lr_g)
+    st.g_ema = ema_update(st.g_ema, st.g, ema_decay)
+    return [r[0] for r in res], clipped

@@ -1,0 +1,87 @@
+"""ctypes binding of the C-ABI library `librsrgan_sm100.so` (include/rsrgan_b200.h).
+
+There is no fallback: if the shared library is missing (not built) importing the
+compute entry points raises, and `Handle()` raises when no sm_100 device exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librsrgan_sm100.so")
+
+RSR_DTYPE_F16, RSR_DTYPE_BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_CLIP = 0, 1, 2, 3
+ERRORS = {-1: "RSR_E_ARG", -2: "RSR_E_SHAPE", -3: "RSR_E_NODEV", -4: "RSR_E_RESIDENT"}
+
+vp, ci, cf, cll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("M", ci), ("N", ci), ("K", ci),
+                ("A", vp), ("lda", ci), ("a_mn", ci),
+                ("B", vp), ("ldb", ci), ("b_mn", ci),
+                ("alpha", cf), ("beta", cf),
+                ("bias", vp),
+                ("resid", vp), ("ldr", ci),
+                ("act", ci),
+                ("dact_src", vp), ("ldd", ci), ("dact", ci),
+                ("out32", vp), ("ldc32", ci),
+                ("out16", vp), ("ldc16", ci),
+                ("tile_n", ci)]
+
+
+# name -> argtypes (every symbol include/rsrgan_b200.h declares)
+SIGNATURES = {
+    "rsr_version": [],
+    "rsr_create": [C.POINTER(vp), ci, ci],
+    "rsr_destroy": [vp],
+    "rsr_num_sms": [vp],
+    "rsr_gemm": [vp, vp, C.POINTER(GemmArgs)],
+    "rsr_stage_input": [vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, ci, vp, ci],
+    "rsr_unstage_output": [vp, vp, vp, ci, ci, ci, ci, vp, vp, vp],
+    "rsr_cmvn_apply": [vp, vp, vp, vp, vp, cll, ci, vp],
+    "rsr_cmvn_invert": [vp, vp, vp, vp, vp, cll, ci, vp],
+    "rsr_lstmp_rec_fwd": [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, cf, vp, vp, vp],
+    "rsr_lstmp_rec_bwd": [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "rsr_lsgan_mse_losses": [vp, vp, vp, vp, ci, cll, ci, vp, ci, vp, ci, cll, ci, cf, cf, cf, cf,
+                             vp, vp, vp, vp, ci, vp, ci],
+    "rsr_colsum16": [vp, vp, vp, ci, cll, ci, vp, ci],
+    "rsr_colsum32": [vp, vp, vp, ci, cll, ci, vp, ci],
+    "rsr_seg_sumsq": [vp, vp, vp, cf, vp, cll, ci, vp],
+    "rsr_clip_sgd_ema": [vp, vp, vp, cf, vp, vp, cf, vp, cf, cll, vp, vp, vp],
+    "rsr_clip_adam_ema": [vp, vp, vp, cf, vp, vp, cf, vp, cf, cll, vp, vp, vp, vp, vp],
+    "rsr_cast16": [vp, vp, vp, cll, vp],
+    "rsr_fill32": [vp, vp, vp, cll, cf],
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "rsrgan_b200: %s not found -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = ci
+        _lib = lib
+    return _lib
+
+
+class RsrError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        if rc < 0:
+            raise RsrError("%s failed: %s" % (what, ERRORS.get(rc, rc)))
+        raise RsrError("%s failed: cudaError %d" % (what, rc))

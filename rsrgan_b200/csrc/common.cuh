@@ -1,0 +1,202 @@
+// Shared device helpers for the sm_100a kernels: mbarrier, TMA, tcgen05/TMEM
+// PTX wrappers, UMMA descriptor builders, 16-bit conversion, warp reductions.
+// Everything here targets sm_100a only (nvcc -gencode arch=compute_100a,code=sm_100a).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace rsr {
+
+// ---------------------------------------------------------------------------
+// 16-bit storage type: the library runs either fp16 or bf16 operands into the
+// tensor cores (always fp32 accumulate). `bf` is a warp-uniform runtime flag.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint16_t f2h(float x, int bf) {
+    if (bf) return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+    return __half_as_ushort(__float2half_rn(x));
+}
+__device__ __forceinline__ float h2f(uint16_t v, int bf) {
+    if (bf) return __bfloat162float(__ushort_as_bfloat16(v));
+    return __half2float(__ushort_as_half(v));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, int bf) {
+    return (uint32_t)f2h(a, bf) | ((uint32_t)f2h(b, bf) << 16);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// tanh through the same exp: abs error ~1e-7, no MUFU.TANH (2^-11 rel error is too coarse
+// for the 1e-3 RMS parity bar after T recurrent steps).
+__device__ __forceinline__ float tanhf_(float x) {
+    float ax = fabsf(x);
+    float e = __expf(-2.0f * ax);
+    float r = __fdividef(1.0f - e, 1.0f + e);
+    return copysignf(r, x);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// shared-memory address + mbarrier
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) { }
+}
+// generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// generic-proxy global writes (acquired from other CTAs) -> ordered before async-proxy (TMA) reads
+__device__ __forceinline__ void fence_proxy_async_all() {
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor) 2-D tile load, completion on an mbarrier
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"((uint64_t)m), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// tcgen05 / TMEM
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {   // same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 or bf16 operands per idesc), issued by ONE thread
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 16 consecutive fp32 columns: thread <-> TMEM lane (= accumulator row), v[j] <-> column j
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------------------
+// UMMA descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp in CUTLASS 3.9/4.x)
+//
+// Shared-memory matrix descriptor, 128-byte swizzle, 16-bit elements:
+//   K-major  operand tile [rows][64 k] : one row = 128 B, 8 rows = one 1024 B swizzle atom,
+//            SBO = 1024 B between 8-row groups, LBO unused (1). Advance 16 k = +32 B.
+//   MN-major operand tile [k][64 mn]   : one k-row = 64 mn elements = 128 B, 8 k-rows = 1024 B
+//            atom, SBO = 1024 B between 8-k groups, LBO = bytes between 64-wide mn blocks.
+//            Advance 16 k = +2048 B.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor for kind::f16, fp32 accumulate.
+__host__ __device__ __forceinline__ uint32_t umma_idesc(int M, int N, int bf, int a_mn_major, int b_mn_major) {
+    uint32_t d = 0;
+    d |= 1u << 4;                       // c_format = F32
+    d |= (uint32_t)(bf ? 1 : 0) << 7;   // a_format: 0 = F16, 1 = BF16
+    d |= (uint32_t)(bf ? 1 : 0) << 10;  // b_format
+    d |= (uint32_t)(a_mn_major ? 1 : 0) << 15;
+    d |= (uint32_t)(b_mn_major ? 1 : 0) << 16;
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+
+// byte offset of element (row r, 16-bit column c in [0,64)) inside a K-major SW128 tile whose
+// rows are 128 B: 16-byte chunk index XOR (r mod 8).
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+    return (uint32_t)(r * 128 + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1)));
+}
+
+// ---------------------------------------------------------------------------
+// cross-CTA flag helpers (group barriers of the persistent recurrent kernels)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) {   // fire-and-forget L2 atomic
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+}  // namespace rsr

@@ -1,0 +1,388 @@
+// HBM-bound kernels of the GAN step: input staging (CMVN + noise + time-major 16-bit
+// conversion), LSGAN / MSE losses with their gradients (warp-shuffle reductions), bias-gradient
+// column sums, and the fused clip_by_norm + SGD|Adam + EMA + 16-bit re-pack sweep.
+// All are coalesced, vectorised where the layout allows, and sized in multiples of the SM count.
+#include "common.cuh"
+#include "handle.h"
+
+using namespace rsr;
+
+namespace {
+
+inline int grid_for(long long work_items, int threads, int num_sms, int per_sm = 8) {
+    long long blocks = (work_items + threads - 1) / threads;
+    long long cap = (long long)num_sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------------
+// staging: (B,T,D) fp32 batch-major -> [T*B, ld] time-major, 16-bit (+ fp32 copy)
+// ---------------------------------------------------------------------------------------
+__global__ void stage_input_kernel(const float* __restrict__ x, int ldx, int time_major_in, int B, int T, int D,
+                                   const float* __restrict__ mean, const float* __restrict__ istd,
+                                   const float* __restrict__ noise, uint16_t* __restrict__ out16, int ld16,
+                                   float* __restrict__ out32, int ld32, int bf) {
+    const long long total = (long long)B * T * D;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        const long long r = i / D;          // output row = t*B + b
+        const int b = (int)(r % B);
+        const int t = (int)(r / B);
+        float v = time_major_in ? x[r * ldx + d] : x[((long long)b * T + t) * ldx + d];
+        if (mean) v = (v - mean[d]) * istd[d];
+        if (noise) v += noise[(long long)b * D + d];
+        if (out16) out16[r * ld16 + d] = f2h(v, bf);
+        if (out32) out32[r * ld32 + d] = v;
+    }
+}
+
+__global__ void unstage_output_kernel(const float* __restrict__ y, int ld, int B, int T, int D,
+                                      const float* __restrict__ mean, const float* __restrict__ std,
+                                      float* __restrict__ out) {
+    const long long total = (long long)B * T * D;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        const long long r = i / D;          // batch-major output row = b*T + t
+        const int t = (int)(r % T);
+        const int b = (int)(r / T);
+        float v = y[((long long)t * B + b) * ld + d];
+        if (mean) v = v * std[d] + mean[d];
+        out[i] = v;
+    }
+}
+
+// CMVN on (N, D) fp32: mode 0: (x - mean) / std ; mode 1: y * std + mean
+__global__ void cmvn_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                            const float* __restrict__ std, long long n, int D, int mode, float* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        const float v = x[i];
+        out[i] = mode ? fmaf(v, std[d], mean[d]) : (v - mean[d]) / std[d];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// LSGAN + MSE losses and gradients
+// ---------------------------------------------------------------------------------------
+struct LossParams {
+    const float* rl; const float* fk; int ldl; long long n_logit; int clip;
+    const float* g; int ldg; const float* y; int ldy; long long n_frames; int D;
+    float d_real, d_fake, lambda, gscale;
+    float* losses;
+    uint16_t* d_rl_grad; uint16_t* d_fk_grad; uint16_t* g_adv_grad; int ldgrad;
+    float* dg_mse; int lddg;
+    int bf;
+};
+
+__device__ __forceinline__ void block_atomic_add(float v, float* dst, float* sh) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float s = lane < (blockDim.x >> 5) ? sh[lane] : 0.0f;
+        s = warp_sum(s);
+        if (lane == 0) atomicAdd(dst, s);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) lsgan_mse_kernel(const LossParams p) {
+    __shared__ float sh[8];
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    float s_rl = 0.f, s_fk = 0.f, s_adv = 0.f, s_mse = 0.f;
+    const float inv_nl = p.n_logit > 0 ? 1.0f / (float)p.n_logit : 0.f;
+    for (long long i = tid; i < p.n_logit; i += nth) {
+        if (p.rl) {
+            const float u = p.rl[i * p.ldl];
+            const float l = p.clip ? fminf(fmaxf(u, -0.5f), 1.5f) : u;
+            const float in = (!p.clip || (u >= -0.5f && u <= 1.5f)) ? 1.f : 0.f;
+            const float e = l - p.d_real;
+            s_rl += e * e;
+            if (p.d_rl_grad) p.d_rl_grad[i * p.ldgrad] = f2h(p.gscale * 2.f * e * inv_nl * in, p.bf);
+        }
+        if (p.fk) {
+            const float u = p.fk[i * p.ldl];
+            const float l = p.clip ? fminf(fmaxf(u, -0.5f), 1.5f) : u;
+            const float in = (!p.clip || (u >= -0.5f && u <= 1.5f)) ? 1.f : 0.f;
+            const float ef = l - p.d_fake, er = l - p.d_real;
+            s_fk += ef * ef;
+            s_adv += er * er;
+            if (p.d_fk_grad) p.d_fk_grad[i * p.ldgrad] = f2h(p.gscale * 2.f * ef * inv_nl * in, p.bf);
+            if (p.g_adv_grad) p.g_adv_grad[i * p.ldgrad] = f2h(p.gscale * 2.f * er * inv_nl * in, p.bf);
+        }
+    }
+    if (p.g && p.y) {
+        // g_mse = 0.5 * D * mean((g-y)^2)  ->  d/dg = lambda * 0.5 * D * 2 (g-y) / (n_frames*D) = lambda (g-y)/n_frames
+        const long long total = p.n_frames * p.D;
+        const float cg = p.gscale * p.lambda / (float)p.n_frames;
+        for (long long i = tid; i < total; i += nth) {
+            const int d = (int)(i % p.D);
+            const long long r = i / p.D;
+            const float e = p.g[r * p.ldg + d] - p.y[r * p.ldy + d];
+            s_mse += e * e;
+            if (p.dg_mse) p.dg_mse[r * p.lddg + d] = cg * e;
+        }
+    }
+    if (p.rl) block_atomic_add(s_rl * inv_nl, p.losses + 0, sh);
+    if (p.fk) { block_atomic_add(s_fk * inv_nl, p.losses + 1, sh); block_atomic_add(s_adv * inv_nl, p.losses + 2, sh); }
+    if (p.g && p.y) block_atomic_add(s_mse * 0.5f / (float)p.n_frames, p.losses + 3, sh);
+}
+
+// ---------------------------------------------------------------------------------------
+// column sums (bias gradients): out[n] (+)= sum_m x[m, n]
+// block = 32 x 8 threads handles 32 columns over a slab of rows; atomics combine slabs.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int ld, long long M, int N,
+                                                     float* __restrict__ out, int bf, long long rows_per_block) {
+    __shared__ float sh[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    const long long r0 = blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block; if (r1 > M) r1 = M;
+    float s = 0.f;
+    if (n < N) {
+        for (long long r = r0 + ty; r < r1; r += 8) {
+            if constexpr (sizeof(T) == 2) s += h2f(x[r * ld + n], bf);
+            else s += x[r * ld + n];
+        }
+    }
+    sh[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][tx];
+        atomicAdd(out + n, t);
+    }
+}
+
+__global__ void fill32_kernel(float* x, long long n, float v) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = v;
+}
+__global__ void cast16_kernel(const float* __restrict__ x, long long n, uint16_t* __restrict__ o, int bf) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = f2h(x[i], bf);
+}
+
+// ---------------------------------------------------------------------------------------
+// update sweep. One block = 1024 contiguous elements of exactly one segment (tensor).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) seg_sumsq_kernel(const float* __restrict__ g, float gmul,
+                                                        const int* __restrict__ seg_id, float* __restrict__ sumsq) {
+    __shared__ float sh[8];
+    const long long base = (long long)blockIdx.x * 1024 + threadIdx.x * 4;
+    const float4 q = *reinterpret_cast<const float4*>(g + base);
+    const float a = q.x * gmul, b = q.y * gmul, c = q.z * gmul, d = q.w * gmul;
+    float s = a * a + b * b + c * c + d * d;
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < 8 ? sh[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0 && t != 0.f) atomicAdd(sumsq + seg_id[blockIdx.x], t);
+    }
+}
+
+// hyper (device, fp32): [0]=lr  [1]=beta1  [2]=beta2  [3]=eps  [4]=beta1_power  [5]=beta2_power  [6]=lr_t
+__global__ void adam_tick_kernel(float* hyper) {
+    // tf.train.AdamOptimizer keeps beta{1,2}_power as fp32 variables; lr_t is formed from the
+    // powers BEFORE they are multiplied (powers start at beta1/beta2).
+    const float b1p = hyper[4], b2p = hyper[5];
+    hyper[6] = hyper[0] * sqrtf(1.f - b2p) / (1.f - b1p);
+}
+__global__ void adam_tock_kernel(float* hyper) {
+    hyper[4] *= hyper[1];
+    hyper[5] *= hyper[2];
+}
+
+template <int ADAM>
+__global__ void __launch_bounds__(256) clip_update_kernel(const float* __restrict__ g, float gmul,
+                                                          const int* __restrict__ seg_id,
+                                                          const float* __restrict__ sumsq, float max_norm,
+                                                          const float* __restrict__ hyper, float ema_decay,
+                                                          float* __restrict__ theta, float* __restrict__ m,
+                                                          float* __restrict__ v, float* __restrict__ ema,
+                                                          uint16_t* __restrict__ theta16, int bf) {
+    const long long base = (long long)blockIdx.x * 1024 + threadIdx.x * 4;
+    const float nrm = sqrtf(sumsq[seg_id[blockIdx.x]]);
+    const float sc = gmul * (max_norm / fmaxf(nrm, max_norm));   // tf.clip_by_norm: g * clip / max(norm, clip)
+    const float4 gq = *reinterpret_cast<const float4*>(g + base);
+    float4 th = *reinterpret_cast<const float4*>(theta + base);
+    float gg[4] = {gq.x * sc, gq.y * sc, gq.z * sc, gq.w * sc};
+    float tt[4] = {th.x, th.y, th.z, th.w};
+    if (ADAM) {
+        const float b1 = hyper[1], b2 = hyper[2], eps = hyper[3], lr_t = hyper[6];
+        float4 mq = *reinterpret_cast<const float4*>(m + base);
+        float4 vq = *reinterpret_cast<const float4*>(v + base);
+        float mm[4] = {mq.x, mq.y, mq.z, mq.w}, vv[4] = {vq.x, vq.y, vq.z, vq.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            mm[k] = b1 * mm[k] + (1.f - b1) * gg[k];
+            vv[k] = b2 * vv[k] + (1.f - b2) * gg[k] * gg[k];
+            tt[k] -= lr_t * mm[k] / (sqrtf(vv[k]) + eps);
+        }
+        *reinterpret_cast<float4*>(m + base) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+        *reinterpret_cast<float4*>(v + base) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    } else {
+        const float lr = hyper[0];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tt[k] -= lr * gg[k];
+    }
+    *reinterpret_cast<float4*>(theta + base) = make_float4(tt[0], tt[1], tt[2], tt[3]);
+    if (ema) {
+        float4 eq = *reinterpret_cast<const float4*>(ema + base);
+        float ee[4] = {eq.x, eq.y, eq.z, eq.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ee[k] -= (1.f - ema_decay) * (ee[k] - tt[k]);
+        *reinterpret_cast<float4*>(ema + base) = make_float4(ee[0], ee[1], ee[2], ee[3]);
+    }
+    if (theta16) {
+        uint2 o;
+        o.x = pack2(tt[0], tt[1], bf);
+        o.y = pack2(tt[2], tt[3], bf);
+        *reinterpret_cast<uint2*>(theta16 + base) = o;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" int rsr_stage_input(rsr_handle* h, void* stream, const float* x, int ldx, int time_major_in,
+                               int B, int T, int D, const float* mean, const float* istd, const float* noise,
+                               void* out16, int ld16, float* out32, int ld32) {
+    if (!h || !x || B <= 0 || T <= 0 || D <= 0 || (!out16 && !out32)) return RSR_E_ARG;
+    if ((mean == nullptr) != (istd == nullptr)) return RSR_E_ARG;
+    if ((out16 && ld16 < D) || (out32 && ld32 < D) || ldx < D) return RSR_E_SHAPE;
+    const long long total = (long long)B * T * D;
+    stage_input_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, time_major_in, B, T, D, mean, istd, noise, (uint16_t*)out16, ld16, out32, ld32,
+        h->dtype == RSR_DTYPE_BF16);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_unstage_output(rsr_handle* h, void* stream, const float* y_tm, int ld, int B, int T, int D,
+                                  const float* mean, const float* std, float* out_bm) {
+    if (!h || !y_tm || !out_bm || B <= 0 || T <= 0 || D <= 0 || ld < D) return RSR_E_ARG;
+    if ((mean == nullptr) != (std == nullptr)) return RSR_E_ARG;
+    const long long total = (long long)B * T * D;
+    unstage_output_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        y_tm, ld, B, T, D, mean, std, out_bm);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+static int cmvn_launch(rsr_handle* h, void* stream, const float* x, const float* mean, const float* std,
+                       long long N, int D, float* out, int mode) {
+    if (!h || !x || !mean || !std || !out || N < 0 || D <= 0) return RSR_E_ARG;
+    if (N == 0) return 0;
+    const long long total = N * D;
+    cmvn_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(x, mean, std, total, D, mode, out);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int rsr_cmvn_apply(rsr_handle* h, void* stream, const float* x, const float* mean, const float* std,
+                              long long N, int D, float* out) { return cmvn_launch(h, stream, x, mean, std, N, D, out, 0); }
+extern "C" int rsr_cmvn_invert(rsr_handle* h, void* stream, const float* y, const float* mean, const float* std,
+                               long long N, int D, float* out) { return cmvn_launch(h, stream, y, mean, std, N, D, out, 1); }
+
+extern "C" int rsr_lsgan_mse_losses(rsr_handle* h, void* stream, const float* d_rl_logit, const float* d_fk_logit,
+                                    int ld_logit, long long n_logit, int clip, const float* g, int ldg,
+                                    const float* y, int ldy, long long n_frames, int D_out, float d_real,
+                                    float d_fake, float lambda, float gscale, float* losses, void* d_rl_grad,
+                                    void* d_fk_grad, void* g_adv_grad, int ld_grad, float* dg_mse, int lddg) {
+    if (!h || !losses) return RSR_E_ARG;
+    if ((d_rl_logit || d_fk_logit) && (n_logit <= 0 || ld_logit <= 0)) return RSR_E_ARG;
+    if ((g != nullptr) != (y != nullptr)) return RSR_E_ARG;
+    if (g && (n_frames <= 0 || D_out <= 0 || ldg < D_out || ldy < D_out)) return RSR_E_ARG;
+    if ((d_rl_grad || d_fk_grad || g_adv_grad) && ld_grad <= 0) return RSR_E_ARG;
+    LossParams p;
+    p.rl = d_rl_logit; p.fk = d_fk_logit; p.ldl = ld_logit; p.n_logit = (d_rl_logit || d_fk_logit) ? n_logit : 0; p.clip = clip;
+    p.g = g; p.ldg = ldg; p.y = y; p.ldy = ldy; p.n_frames = n_frames; p.D = D_out;
+    p.d_real = d_real; p.d_fake = d_fake; p.lambda = lambda; p.gscale = gscale; p.losses = losses;
+    p.d_rl_grad = (uint16_t*)d_rl_grad; p.d_fk_grad = (uint16_t*)d_fk_grad; p.g_adv_grad = (uint16_t*)g_adv_grad;
+    p.ldgrad = ld_grad; p.dg_mse = dg_mse; p.lddg = lddg; p.bf = h->dtype == RSR_DTYPE_BF16;
+    long long work = p.n_logit;
+    if (g && n_frames * D_out > work) work = n_frames * D_out;
+    lsgan_mse_kernel<<<grid_for(work, 256, h->num_sms, 4), 256, 0, (cudaStream_t)stream>>>(p);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T>
+static int colsum_launch(rsr_handle* h, void* stream, const T* x, int ld, long long M, int N, float* out, int accumulate) {
+    if (!h || !x || !out || M <= 0 || N <= 0 || ld < N) return RSR_E_ARG;
+    if (!accumulate) RSR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, (cudaStream_t)stream));
+    const int gx = (N + 31) / 32;
+    long long gy = (2LL * h->num_sms + gx - 1) / gx;
+    if (gy > (M + 63) / 64) gy = (M + 63) / 64;
+    if (gy < 1) gy = 1;
+    const long long rpb = (M + gy - 1) / gy;
+    colsum_kernel<T><<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(x, ld, M, N, out, h->dtype == RSR_DTYPE_BF16, rpb);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int rsr_colsum16(rsr_handle* h, void* stream, const void* x16, int ld, long long M, int N, float* out, int accumulate) {
+    return colsum_launch<uint16_t>(h, stream, (const uint16_t*)x16, ld, M, N, out, accumulate);
+}
+extern "C" int rsr_colsum32(rsr_handle* h, void* stream, const float* x32, int ld, long long M, int N, float* out, int accumulate) {
+    return colsum_launch<float>(h, stream, x32, ld, M, N, out, accumulate);
+}
+
+extern "C" int rsr_seg_sumsq(rsr_handle* h, void* stream, const float* grad, float gmul, const int* seg_id,
+                             long long n_elems, int n_seg, float* sumsq) {
+    if (!h || !grad || !seg_id || !sumsq || n_elems <= 0 || (n_elems & 1023) || n_seg <= 0) return RSR_E_ARG;
+    RSR_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * n_seg, (cudaStream_t)stream));
+    seg_sumsq_kernel<<<(unsigned)(n_elems / 1024), 256, 0, (cudaStream_t)stream>>>(grad, gmul, seg_id, sumsq);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_clip_sgd_ema(rsr_handle* h, void* stream, const float* grad, float gmul, const int* seg_id,
+                                const float* sumsq, float max_norm, const float* hyper, float ema_decay,
+                                long long n_elems, float* theta, float* ema, void* theta16) {
+    if (!h || !grad || !seg_id || !sumsq || !hyper || !theta || n_elems <= 0 || (n_elems & 1023)) return RSR_E_ARG;
+    clip_update_kernel<0><<<(unsigned)(n_elems / 1024), 256, 0, (cudaStream_t)stream>>>(
+        grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, nullptr, nullptr, ema, (uint16_t*)theta16,
+        h->dtype == RSR_DTYPE_BF16);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_clip_adam_ema(rsr_handle* h, void* stream, const float* grad, float gmul, const int* seg_id,
+                                 const float* sumsq, float max_norm, float* hyper, float ema_decay,
+                                 long long n_elems, float* theta, float* m, float* v, float* ema, void* theta16) {
+    if (!h || !grad || !seg_id || !sumsq || !hyper || !theta || !m || !v || n_elems <= 0 || (n_elems & 1023)) return RSR_E_ARG;
+    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper);
+    clip_update_kernel<1><<<(unsigned)(n_elems / 1024), 256, 0, (cudaStream_t)stream>>>(
+        grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, m, v, ema, (uint16_t*)theta16,
+        h->dtype == RSR_DTYPE_BF16);
+    adam_tock_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_cast16(rsr_handle* h, void* stream, const float* x, long long n, void* out16) {
+    if (!h || !x || !out16 || n < 0) return RSR_E_ARG;
+    if (n == 0) return 0;
+    cast16_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(x, n, (uint16_t*)out16, h->dtype == RSR_DTYPE_BF16);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int rsr_fill32(rsr_handle* h, void* stream, float* x, long long n, float v) {
+    if (!h || !x || n < 0) return RSR_E_ARG;
+    if (n == 0) return 0;
+    fill32_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(x, n, v);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,56 @@
+// Per-rank library handle: device info, driver entry point for TMA descriptor
+// encoding, a cache of encoded tensor maps, and the small device workspace the
+// persistent recurrent kernels use for their group barriers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+
+#include "../../include/rsrgan_b200.h"
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TmapKey {
+    const void* ptr; uint64_t d0, d1, stride1; uint32_t b0, b1;
+    bool operator==(const TmapKey& o) const {
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride1 == o.stride1 && b0 == o.b0 && b1 == o.b1;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
+        h ^= k.d0 + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h ^= k.d1 + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h ^= k.stride1 + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h ^= ((uint64_t)k.b0 << 32 | k.b1) + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        return (size_t)h;
+    }
+};
+
+struct rsr_handle {
+    int device = 0;
+    int dtype = RSR_DTYPE_F16;   // 16-bit operand type
+    int num_sms = 0;
+    int max_smem = 0;
+    PFN_encodeTiled encode = nullptr;
+    std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> tmaps;
+    std::mutex mu;
+    unsigned int* flags = nullptr;   // device: group-barrier counters, RSR_FLAG_WORDS words
+    int flag_cursor = 0;
+};
+
+#define RSR_FLAG_WORDS 4096
+
+// 2-D tensor map over a 16-bit row-major matrix [d1 rows, d0 cols] with row pitch `ld` elements,
+// box [b1 rows, b0 cols], 128-byte swizzle (b0 * 2 bytes must be 128).
+int rsr_get_tmap(rsr_handle* h, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld,
+                 uint32_t b0, uint32_t b1, CUtensorMap* out);
+
+#define RSR_CHECK_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+#define RSR_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)

@@ -1,0 +1,440 @@
+// Persistent LSTMP (LSTM with peepholes + projection) recurrence kernels for sm_100a.
+//
+// Reference semantics: tf.contrib.rnn.LSTMCell(use_peepholes=True, num_proj=P, forget_bias=1.0)
+// under tf.nn.dynamic_rnn(sequence_length=lengths, zero initial state) -- call sites
+// models/lstm.py:89-112, models/res_lstm_l.py:86-138, models/discriminator_lstm.py:70-91; the
+// gate math (order i, j, f, o; peepholes; bias-free projection) is restated in the reference at
+// models/BNLSTMCell.py:176-213.
+//
+// B200 design.  The recurrence is folded: with mt_t = o (.) tanh(c_t) (the pre-projection
+// output) and Wc = W_proj K_h (C x 4C),
+//        z_t = Zx_t + mt_{t-1} Wc                 (Zx = X K_x + b hoisted into one big GEMM)
+//        out_t = mt_t W_proj                      (hoisted into one big GEMM after the loop)
+// so a time step is ONE dependent matmul.  The forward kernel keeps its slice of Wc resident in
+// shared memory for all T steps (weight-stationary), computes the four gate pre-activations of
+// 32 cells x NB utterances per CTA as one tcgen05 tile (swap-AB: 128 gate rows = UMMA M,
+// utterances = UMMA N, K = C) whose B operand (mt_{t-1}) arrives by TMA, adds Zx, and applies
+// the sigmoid/tanh/peephole/cell update in registers.  CTAs that share an utterance slice form
+// a group that exchanges mt_t through L2 and synchronises with one release/acquire counter per
+// step; different utterance slices never synchronise.  The backward kernel runs the reversed
+// recurrence dmt_{t-1} += dz_t Wc^T the same way, split 2-D (gate-column slices x output-row
+// slices) so that every CTA's Wc slab fits in shared memory; partial sums meet in L2 via
+// coalesced red.global.add.f32.
+#include "common.cuh"
+#include "handle.h"
+
+using namespace rsr;
+
+namespace {
+
+// =========================================================================================
+// forward
+// =========================================================================================
+struct FwdParams {
+    int B, T, Cp, bf;
+    float forget_bias;
+    const float* zx;            // [T*B, 4Cp] packed gate columns
+    const float* w_i; const float* w_f; const float* w_o;   // [Cp]
+    const int* lengths;         // [B]
+    uint16_t* mt_seq;           // [(T+1)*B, Cp]
+    float* save;                // [T*B, 5, Cp] or null
+    unsigned int* flags;        // one counter per utterance group
+};
+
+template <int NB>
+__global__ void __launch_bounds__(128, 1)
+lstmp_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmM,
+                     const FwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KB = p.Cp / 64;                 // 64-wide K sub-tiles
+    const int G = p.Cp / 32;                  // CTAs per utterance group
+    const int j = blockIdx.x % G;             // cell block: cells [32j, 32j+32)
+    const int grp = blockIdx.x / G;
+    const int b0 = grp * NB;
+
+    const uint32_t sA = base;                                // KB x [128 x 64] 16-bit, SW128
+    const uint32_t sB = sA + (uint32_t)KB * 16384u;          // KB x [NB x 64]
+    const uint32_t sX = sB + (uint32_t)KB * NB * 128u;       // float xchg[4][32][NB+1]
+    const uint32_t sBar = sX + 4u * 32u * (NB + 1) * 4u;
+    const uint32_t barA = (sBar + 7u) & ~7u, barB = barA + 8, barM = barA + 16, tslot = barA + 24;
+    float* xchg = reinterpret_cast<float*>(smem_raw + (sX - smem_u32(smem_raw)));
+
+    constexpr uint32_t TCOLS = NB < 32 ? 32 : NB;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmM);
+        mbar_init(barA, 1); mbar_init(barB, 1); mbar_init(barM, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tslot, TCOLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
+
+    if (tid == 0) {   // weight slab: resident for the whole sequence
+        mbar_expect_tx(barA, (uint32_t)KB * 16384u);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * 16384u, &tmW, barA, kb * 64, 128 * j);
+    }
+
+    // phase-2 ownership: thread <-> (cell cl, utterances n = q*NQ .. q*NQ+NQ-1)
+    constexpr int NQ = NB / 4;
+    const int cl = lane, q = warp;
+    const int cell = 32 * j + cl;
+    const float wi = p.w_i[cell], wf = p.w_f[cell], wo = p.w_o[cell];
+    float creg[NQ];
+    int len[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        creg[i] = 0.f;
+        const int b = b0 + q * NQ + i;
+        len[i] = b < p.B ? p.lengths[b] : 0;
+    }
+    const uint32_t idesc = umma_idesc(128, NB, p.bf, 0, 0);
+    const size_t zx_ld = (size_t)4 * p.Cp;
+    unsigned int* flag = p.flags + grp;
+
+    for (int t = 0; t < p.T; ++t) {
+        // Zx for gate row `tid` (independent of the recurrence: issue early)
+        float zxv[NB];
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const int b = b0 + n;
+            zxv[n] = b < p.B ? __ldg(p.zx + ((size_t)t * p.B + b) * zx_ld + 128 * j + tid) : 0.f;
+        }
+        if (tid == 0) {
+            if (t > 0) {
+                const unsigned int want = (unsigned int)G * (unsigned int)t;
+                while (ld_acquire(flag) < want) { }
+            }
+            fence_proxy_async_all();
+            mbar_expect_tx(barB, (uint32_t)KB * NB * 128u);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * NB * 128u, &tmM, barB, kb * 64, t * p.B + b0);
+            if (t == 0) mbar_wait(barA, 0);
+            mbar_wait(barB, (uint32_t)(t & 1));
+            tc_fence_after();
+            for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t da = umma_desc_sw128(sA + kb * 16384u + k * 32u, 16, 1024);
+                    const uint64_t db = umma_desc_sw128(sB + kb * NB * 128u + k * 32u, 16, 1024);
+                    tc_mma_f16(tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+                }
+            }
+            tc_commit(barM);
+        }
+        __syncwarp();
+        mbar_wait(barM, (uint32_t)(t & 1));
+        tc_fence_after();
+        float acc[NB];
+        if constexpr (NB == 16) tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), acc);
+        else tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), acc);
+        // warp w holds gate w (i, j, f, o) of cells 32j + lane
+#pragma unroll
+        for (int n = 0; n < NB; ++n) xchg[(warp * 32 + lane) * (NB + 1) + n] = acc[n] + zxv[n];
+        tc_fence_before();
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            const int n = q * NQ + i;
+            const int b = b0 + n;
+            const float zi = xchg[(0 * 32 + cl) * (NB + 1) + n];
+            const float zj = xchg[(1 * 32 + cl) * (NB + 1) + n];
+            const float zf = xchg[(2 * 32 + cl) * (NB + 1) + n];
+            const float zo = xchg[(3 * 32 + cl) * (NB + 1) + n];
+            const float cp = creg[i];
+            const float ig = sigmoidf_(zi + wi * cp);
+            const float fg = sigmoidf_(zf + p.forget_bias + wf * cp);
+            const float jg = tanhf_(zj);
+            const float cn = fg * cp + ig * jg;
+            const float og = sigmoidf_(zo + wo * cn);
+            const float mt = og * tanhf_(cn);
+            const bool active = t < len[i];
+            if (b < p.B) {
+                const size_t row = (size_t)t * p.B + b;
+                if (p.save) {
+                    float* s = p.save + row * 5 * p.Cp + cell;
+                    s[0] = ig; s[p.Cp] = fg; s[2 * (size_t)p.Cp] = og; s[3 * (size_t)p.Cp] = jg; s[4 * (size_t)p.Cp] = cn;
+                }
+                p.mt_seq[(row + p.B) * p.Cp + cell] = f2h(active ? mt : 0.f, p.bf);
+            }
+            if (active) creg[i] = cn;
+        }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); red_release_add(flag, 1u); }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+// =========================================================================================
+// backward
+// =========================================================================================
+struct BwdParams {
+    int B, T, Cp, bf;
+    float* dmt;                 // [T*B, Cp] in: dOut W_p^T ; kernel adds recurrent term
+    const float* w_i; const float* w_f; const float* w_o;
+    const int* lengths;
+    const float* save;          // [T*B, 5, Cp]
+    uint16_t* dz16;             // [T*B, 4Cp] packed
+    float* dbias; float* dw_i; float* dw_f; float* dw_o;
+    unsigned int* flags;
+};
+
+// CTA (ks, ms): gate-column slice ks = 64 cells (256 packed gate columns), output rows
+// [256 ms, 256 ms + 256) as two UMMA M=128 tiles.
+template <int NB>
+__global__ void __launch_bounds__(128, 1)
+lstmp_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const BwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KS = p.Cp / 64, MS = p.Cp / 256;
+    const int per_grp = KS * MS;
+    const int grp = blockIdx.x / per_grp;
+    const int rem = blockIdx.x % per_grp;
+    const int ks = rem / MS, ms = rem % MS;
+    const int b0 = grp * NB;
+
+    const uint32_t sA = base;                       // 2 m-tiles x 4 k-subtiles x [128 x 64]
+    const uint32_t sB = sA + 8u * 16384u;           // 4 k-subtiles x [NB x 64]
+    const uint32_t sBar = sB + 4u * NB * 128u;
+    const uint32_t barA = sBar, barM = sBar + 8, tslot = sBar + 16;
+    uint8_t* sB_ptr = base_ptr + 8 * 16384;
+
+    constexpr uint32_t TCOLS = 2 * NB < 32 ? 32 : 2 * NB;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmW);
+        mbar_init(barA, 1); mbar_init(barM, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tslot, TCOLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
+
+    if (tid == 0) {
+        mbar_expect_tx(barA, 8u * 16384u);
+        for (int mt = 0; mt < 2; ++mt)
+            for (int kb = 0; kb < 4; ++kb)
+                tma_load_2d(sA + (mt * 4 + kb) * 16384u, &tmW, barA, 256 * ks + 64 * kb, 256 * ms + 128 * mt);
+    }
+
+    // gate-backward ownership: thread <-> (cell c of the slice, utterances n = half, half+2, ...)
+    constexpr int NH = NB / 2;
+    const int c = tid & 63, half = tid >> 6;
+    const int cell = 64 * ks + c;
+    const int jl = c >> 5, c32 = c & 31;
+    const float wi = p.w_i[cell], wf = p.w_f[cell], wo = p.w_o[cell];
+    float dcar[NH];
+    int len[NH];
+#pragma unroll
+    for (int i = 0; i < NH; ++i) {
+        dcar[i] = 0.f;
+        const int b = b0 + half + 2 * i;
+        len[i] = b < p.B ? p.lengths[b] : 0;
+    }
+    float a_dwi = 0.f, a_dwf = 0.f, a_dwo = 0.f, a_db[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint32_t idesc = umma_idesc(128, NB, p.bf, 0, 0);
+    unsigned int* flag = p.flags + grp;
+    const size_t Cp = (size_t)p.Cp;
+    if (tid == 0) mbar_wait(barA, 0);      // weight slab landed (also guarantees no TMA is in flight at exit)
+
+    for (int step = 0; step < p.T; ++step) {
+        const int t = p.T - 1 - step;
+        // saved forward activations do not depend on the recurrence: load before the group wait
+        float s_i[NH], s_f[NH], s_o[NH], s_j[NH], s_c[NH], s_cp[NH];
+#pragma unroll
+        for (int i = 0; i < NH; ++i) {
+            const int b = b0 + half + 2 * i;
+            if (b < p.B) {
+                const float* s = p.save + ((size_t)t * p.B + b) * 5 * Cp + cell;
+                s_i[i] = __ldg(s); s_f[i] = __ldg(s + Cp); s_o[i] = __ldg(s + 2 * Cp); s_j[i] = __ldg(s + 3 * Cp);
+                s_c[i] = __ldg(s + 4 * Cp);
+                s_cp[i] = t > 0 ? __ldg(s - (size_t)p.B * 5 * Cp + 4 * Cp) : 0.f;
+            } else {
+                s_i[i] = s_f[i] = s_o[i] = s_j[i] = s_c[i] = s_cp[i] = 0.f;
+            }
+        }
+        if (step > 0) {
+            if (tid == 0) {
+                const unsigned int want = (unsigned int)per_grp * (unsigned int)step;
+                while (ld_acquire(flag) < want) { }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < NH; ++i) {
+            const int n = half + 2 * i;
+            const int b = b0 + n;
+            float dz_i = 0.f, dz_j = 0.f, dz_f = 0.f, dz_o = 0.f;
+            const bool active = (b < p.B) && (t < len[i]);
+            if (active) {
+                const size_t row = (size_t)t * p.B + b;
+                const float dm = __ldcg(p.dmt + row * Cp + cell);      // L2: other CTAs' atomics landed there
+                const float tc = tanhf_(s_c[i]);
+                dz_o = dm * tc * s_o[i] * (1.f - s_o[i]);
+                const float dc = dcar[i] + dm * s_o[i] * (1.f - tc * tc) + dz_o * wo;
+                dz_f = dc * s_cp[i] * s_f[i] * (1.f - s_f[i]);
+                dz_i = dc * s_j[i] * s_i[i] * (1.f - s_i[i]);
+                dz_j = dc * s_i[i] * (1.f - s_j[i] * s_j[i]);
+                dcar[i] = dc * s_f[i] + dz_f * wf + dz_i * wi;
+                a_dwo += dz_o * s_c[i]; a_dwf += dz_f * s_cp[i]; a_dwi += dz_i * s_cp[i];
+                a_db[0] += dz_i; a_db[1] += dz_j; a_db[2] += dz_f; a_db[3] += dz_o;
+            } else {
+                dcar[i] = 0.f;
+            }
+            const uint16_t h_i = f2h(dz_i, p.bf), h_j = f2h(dz_j, p.bf), h_f = f2h(dz_f, p.bf), h_o = f2h(dz_o, p.bf);
+            // B operand tile (K-major, SW128): row n, local packed column jl*128 + g*32 + c32
+            const int cb = (jl * 2) * NB * 128;
+            *reinterpret_cast<uint16_t*>(sB_ptr + cb + sw128_off(n, c32)) = h_i;                       // g = 0
+            *reinterpret_cast<uint16_t*>(sB_ptr + cb + sw128_off(n, 32 + c32)) = h_j;                  // g = 1
+            *reinterpret_cast<uint16_t*>(sB_ptr + cb + NB * 128 + sw128_off(n, c32)) = h_f;            // g = 2
+            *reinterpret_cast<uint16_t*>(sB_ptr + cb + NB * 128 + sw128_off(n, 32 + c32)) = h_o;       // g = 3
+            if (ms == 0 && b < p.B) {
+                uint16_t* d = p.dz16 + ((size_t)t * p.B + b) * 4 * Cp + 256 * ks + jl * 128 + c32;
+                d[0] = h_i; d[32] = h_j; d[64] = h_f; d[96] = h_o;
+            }
+        }
+        if (t == 0) break;                     // no earlier step to feed
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int mt = 0; mt < 2; ++mt) {
+                for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t da = umma_desc_sw128(sA + (mt * 4 + kb) * 16384u + k * 32u, 16, 1024);
+                        const uint64_t db = umma_desc_sw128(sB + kb * NB * 128u + k * 32u, 16, 1024);
+                        tc_mma_f16(tmem + (uint32_t)(mt * NB), da, db, idesc, (kb | k) ? 1u : 0u);
+                    }
+                }
+            }
+            tc_commit(barM);
+        }
+        __syncwarp();
+        mbar_wait(barM, (uint32_t)(step & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            float acc[NB];
+            if constexpr (NB == 16) tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NB), acc);
+            else tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NB), acc);
+            const int crow = 256 * ms + 128 * mt + warp * 32 + lane;
+#pragma unroll
+            for (int n = 0; n < NB; ++n) {
+                const int b = b0 + n;
+                if (b < p.B) red_add_f32(p.dmt + ((size_t)(t - 1) * p.B + b) * Cp + crow, acc[n]);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) { __threadfence(); red_release_add(flag, 1u); }
+    }
+    if (ms == 0) {
+        atomicAdd(p.dw_i + cell, a_dwi); atomicAdd(p.dw_f + cell, a_dwf); atomicAdd(p.dw_o + cell, a_dwo);
+        float* db = p.dbias + 256 * ks + jl * 128 + c32;
+        atomicAdd(db, a_db[0]); atomicAdd(db + 32, a_db[1]); atomicAdd(db + 64, a_db[2]); atomicAdd(db + 96, a_db[3]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+size_t fwd_smem(int Cp, int nb) {
+    const int KB = Cp / 64;
+    return 1024 + (size_t)KB * 16384 + (size_t)KB * nb * 128 + 4 * 32 * (nb + 1) * 4 + 64;
+}
+size_t bwd_smem(int nb) { return 1024 + 8 * 16384 + (size_t)4 * nb * 128 + 64; }
+
+// smallest utterance slice whose grid is co-resident (1 CTA / SM) and whose smem fits
+int pick_nb(int B, int ctas_per_group, int num_sms, int max_smem, int Cp, bool fwd) {
+    for (int nb = 16; nb <= 32; nb *= 2) {
+        const int groups = (B + nb - 1) / nb;
+        const size_t smem = fwd ? fwd_smem(Cp, nb) : bwd_smem(nb);
+        if (groups * ctas_per_group <= num_sms && (int)smem <= max_smem) return nb;
+    }
+    return 0;
+}
+
+unsigned int* take_flags(rsr_handle* h, int n) {
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->flag_cursor + n > RSR_FLAG_WORDS) h->flag_cursor = 0;
+    unsigned int* f = h->flags + h->flag_cursor;
+    h->flag_cursor += n;
+    return f;
+}
+
+}  // namespace
+
+extern "C" int rsr_lstmp_rec_fwd(rsr_handle* h, void* stream, int B, int T, int Cp, const float* zx,
+                                 const void* wcT, const float* w_i, const float* w_f, const float* w_o,
+                                 float forget_bias, const int* lengths, void* mt_seq, float* save) {
+    if (!h || !zx || !wcT || !w_i || !w_f || !w_o || !lengths || !mt_seq) return RSR_E_ARG;
+    if (B <= 0 || T <= 0 || Cp <= 0 || (Cp & 255)) return RSR_E_SHAPE;
+    const int G = Cp / 32;
+    const int nb = pick_nb(B, G, h->num_sms, h->max_smem, Cp, true);
+    if (!nb) return RSR_E_RESIDENT;
+    const int groups = (B + nb - 1) / nb;
+    const size_t smem = fwd_smem(Cp, nb);
+    CUtensorMap tmW, tmM;
+    int rc = rsr_get_tmap(h, wcT, (uint64_t)Cp, (uint64_t)4 * Cp, (uint64_t)Cp, 64, 128, &tmW);
+    if (rc) return rc;
+    rc = rsr_get_tmap(h, mt_seq, (uint64_t)Cp, (uint64_t)(T + 1) * B, (uint64_t)Cp, 64, (uint32_t)nb, &tmM);
+    if (rc) return rc;
+    FwdParams p;
+    p.B = B; p.T = T; p.Cp = Cp; p.bf = h->dtype == RSR_DTYPE_BF16; p.forget_bias = forget_bias;
+    p.zx = zx; p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths;
+    p.mt_seq = (uint16_t*)mt_seq; p.save = save;
+    p.flags = take_flags(h, groups);
+    RSR_CHECK_CUDA(cudaMemsetAsync(p.flags, 0, sizeof(unsigned int) * groups, (cudaStream_t)stream));
+    if (nb == 16) {
+        RSR_CHECK_CUDA(cudaFuncSetAttribute(lstmp_rec_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        lstmp_rec_fwd_kernel<16><<<groups * G, 128, smem, (cudaStream_t)stream>>>(tmW, tmM, p);
+    } else {
+        RSR_CHECK_CUDA(cudaFuncSetAttribute(lstmp_rec_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        lstmp_rec_fwd_kernel<32><<<groups * G, 128, smem, (cudaStream_t)stream>>>(tmW, tmM, p);
+    }
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_lstmp_rec_bwd(rsr_handle* h, void* stream, int B, int T, int Cp, float* dmt,
+                                 const void* wc, const float* w_i, const float* w_f, const float* w_o,
+                                 const int* lengths, const float* save, void* dz16,
+                                 float* dbias, float* dw_i, float* dw_f, float* dw_o) {
+    if (!h || !dmt || !wc || !w_i || !w_f || !w_o || !lengths || !save || !dz16 || !dbias || !dw_i || !dw_f || !dw_o)
+        return RSR_E_ARG;
+    if (B <= 0 || T <= 0 || Cp <= 0 || (Cp & 255)) return RSR_E_SHAPE;
+    const int per_grp = (Cp / 64) * (Cp / 256);
+    const int nb = pick_nb(B, per_grp, h->num_sms, h->max_smem, Cp, false);
+    if (!nb) return RSR_E_RESIDENT;
+    const int groups = (B + nb - 1) / nb;
+    const size_t smem = bwd_smem(nb);
+    CUtensorMap tmW;
+    int rc = rsr_get_tmap(h, wc, (uint64_t)4 * Cp, (uint64_t)Cp, (uint64_t)4 * Cp, 64, 128, &tmW);
+    if (rc) return rc;
+    BwdParams p;
+    p.B = B; p.T = T; p.Cp = Cp; p.bf = h->dtype == RSR_DTYPE_BF16;
+    p.dmt = dmt; p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths; p.save = save;
+    p.dz16 = (uint16_t*)dz16; p.dbias = dbias; p.dw_i = dw_i; p.dw_f = dw_f; p.dw_o = dw_o;
+    p.flags = take_flags(h, groups);
+    RSR_CHECK_CUDA(cudaMemsetAsync(p.flags, 0, sizeof(unsigned int) * groups, (cudaStream_t)stream));
+    if (nb == 16) {
+        RSR_CHECK_CUDA(cudaFuncSetAttribute(lstmp_rec_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        lstmp_rec_bwd_kernel<16><<<groups * per_grp, 128, smem, (cudaStream_t)stream>>>(tmW, p);
+    } else {
+        RSR_CHECK_CUDA(cudaFuncSetAttribute(lstmp_rec_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        lstmp_rec_bwd_kernel<32><<<groups * per_grp, 128, smem, (cudaStream_t)stream>>>(tmW, p);
+    }
+    RSR_LAUNCH_CHECK();
+    return 0;
+}

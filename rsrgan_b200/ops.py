@@ -1,0 +1,155 @@
+"""Thin Python wrappers over the C ABI (include/rsrgan_b200.h).
+
+torch is only the allocator / stream owner here: every function takes CUDA
+tensors, passes raw device pointers + the current torch stream to the library
+and returns immediately (asynchronous).  No function has a CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_CLIP, ACT_LRELU, ACT_NONE, ACT_RELU, GemmArgs, check  # noqa: F401
+
+H16 = {0: torch.float16, 1: torch.bfloat16}
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Handle(object):
+    """Per-rank library handle (rsr_create / rsr_destroy)."""
+
+    def __init__(self, device=0, dtype="f16"):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.RsrError("rsrgan_b200 needs an sm_100 GPU; there is no CPU fallback")
+        self.dtype_id = {"f16": _lib.RSR_DTYPE_F16, "fp16": _lib.RSR_DTYPE_F16,
+                         "bf16": _lib.RSR_DTYPE_BF16}[dtype]
+        self.h16 = H16[self.dtype_id]
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        h = C.c_void_p()
+        check(self.lib.rsr_create(C.byref(h), device, self.dtype_id), "rsr_create")
+        self.h = h
+        self.num_sms = self.lib.rsr_num_sms(self.h)
+        self.launches = 0          # number of library calls that launch >= 1 kernel (bench accounting)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rsr_destroy(self.h)
+            self.h = None
+
+    # ------------------------------------------------------------------ GEMM
+    def gemm(self, A, B, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, bias=None,
+             resid=None, act=ACT_NONE, dact_src=None, dact=ACT_NONE, out32=None, out16=None,
+             tile_n=0, lda=None, ldb=None):
+        """D[M,N] = epi(alpha * A B).  A/B are 2-D h16 tensors (or views with a row stride);
+        see rsr_gemm in the header for operand major-ness."""
+        a = GemmArgs()
+        a.M, a.N, a.K = M, N, K
+        a.A, a.lda, a.a_mn = _p(A), (lda if lda is not None else A.stride(0)), int(a_mn)
+        a.B, a.ldb, a.b_mn = _p(B), (ldb if ldb is not None else B.stride(0)), int(b_mn)
+        a.alpha, a.beta = alpha, beta
+        a.bias = _p(bias)
+        a.resid, a.ldr = _p(resid), (resid.stride(0) if resid is not None else 0)
+        a.act = act
+        a.dact_src, a.ldd, a.dact = _p(dact_src), (dact_src.stride(0) if dact_src is not None else 0), dact
+        a.out32, a.ldc32 = _p(out32), (out32.stride(0) if out32 is not None else 0)
+        a.out16, a.ldc16 = _p(out16), (out16.stride(0) if out16 is not None else 0)
+        a.tile_n = tile_n
+        check(self.lib.rsr_gemm(self.h, _stream(), C.byref(a)), "rsr_gemm")
+        self.launches += 1
+
+    # --------------------------------------------------------------- staging
+    def stage_input(self, x, B, T, D, out16=None, out32=None, mean=None, istd=None, noise=None,
+                    time_major_in=False, ldx=None):
+        check(self.lib.rsr_stage_input(
+            self.h, _stream(), _p(x), ldx if ldx is not None else (x.stride(0) if time_major_in else D),
+            int(time_major_in), B, T, D, _p(mean), _p(istd), _p(noise),
+            _p(out16), out16.stride(0) if out16 is not None else 0,
+            _p(out32), out32.stride(0) if out32 is not None else 0), "rsr_stage_input")
+        self.launches += 1
+
+    def unstage_output(self, y_tm, B, T, D, out_bm, mean=None, std=None):
+        check(self.lib.rsr_unstage_output(self.h, _stream(), _p(y_tm), y_tm.stride(0), B, T, D,
+                                          _p(mean), _p(std), _p(out_bm)), "rsr_unstage_output")
+        self.launches += 1
+
+    def cmvn_apply(self, x, mean, std, out):
+        n, d = x.shape
+        check(self.lib.rsr_cmvn_apply(self.h, _stream(), _p(x), _p(mean), _p(std), n, d, _p(out)), "rsr_cmvn_apply")
+        self.launches += 1
+
+    def cmvn_invert(self, y, mean, std, out):
+        n, d = y.shape
+        check(self.lib.rsr_cmvn_invert(self.h, _stream(), _p(y), _p(mean), _p(std), n, d, _p(out)), "rsr_cmvn_invert")
+        self.launches += 1
+
+    # ----------------------------------------------------------------- LSTMP
+    def lstmp_rec_fwd(self, B, T, Cp, zx, wcT, w_i, w_f, w_o, lengths, mt_seq, save, forget_bias=1.0):
+        check(self.lib.rsr_lstmp_rec_fwd(self.h, _stream(), B, T, Cp, _p(zx), _p(wcT), _p(w_i), _p(w_f),
+                                         _p(w_o), forget_bias, _p(lengths), _p(mt_seq), _p(save)),
+              "rsr_lstmp_rec_fwd")
+        self.launches += 1
+
+    def lstmp_rec_bwd(self, B, T, Cp, dmt, wc, w_i, w_f, w_o, lengths, save, dz16, dbias, dw_i, dw_f, dw_o):
+        check(self.lib.rsr_lstmp_rec_bwd(self.h, _stream(), B, T, Cp, _p(dmt), _p(wc), _p(w_i), _p(w_f),
+                                         _p(w_o), _p(lengths), _p(save), _p(dz16), _p(dbias), _p(dw_i),
+                                         _p(dw_f), _p(dw_o)), "rsr_lstmp_rec_bwd")
+        self.launches += 1
+
+    # ---------------------------------------------------------------- losses
+    def lsgan_mse_losses(self, losses, rl=None, fk=None, ld_logit=1, n_logit=0, clip=False, g=None, y=None,
+                         n_frames=0, d_out=0, d_real=1.0, d_fake=0.0, lam=0.0, gscale=1.0,
+                         d_rl_grad=None, d_fk_grad=None, g_adv_grad=None, ld_grad=1, dg_mse=None):
+        check(self.lib.rsr_lsgan_mse_losses(
+            self.h, _stream(), _p(rl), _p(fk), ld_logit, n_logit, int(clip),
+            _p(g), g.stride(0) if g is not None else 0, _p(y), y.stride(0) if y is not None else 0,
+            n_frames, d_out, d_real, d_fake, lam, gscale, _p(losses), _p(d_rl_grad), _p(d_fk_grad),
+            _p(g_adv_grad), ld_grad, _p(dg_mse), dg_mse.stride(0) if dg_mse is not None else 0),
+            "rsr_lsgan_mse_losses")
+        self.launches += 1
+
+    def colsum16(self, x16, M, N, out, accumulate=False, ld=None):
+        check(self.lib.rsr_colsum16(self.h, _stream(), _p(x16), ld if ld is not None else x16.stride(0),
+                                    M, N, _p(out), int(accumulate)), "rsr_colsum16")
+        self.launches += 1
+
+    def colsum32(self, x32, M, N, out, accumulate=False, ld=None):
+        check(self.lib.rsr_colsum32(self.h, _stream(), _p(x32), ld if ld is not None else x32.stride(0),
+                                    M, N, _p(out), int(accumulate)), "rsr_colsum32")
+        self.launches += 1
+
+    # ---------------------------------------------------------------- update
+    def seg_sumsq(self, grad, gmul, seg_id, n_seg, sumsq):
+        check(self.lib.rsr_seg_sumsq(self.h, _stream(), _p(grad), gmul, _p(seg_id), grad.numel(), n_seg,
+                                     _p(sumsq)), "rsr_seg_sumsq")
+        self.launches += 1
+
+    def clip_sgd_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, ema, theta16):
+        check(self.lib.rsr_clip_sgd_ema(self.h, _stream(), _p(grad), gmul, _p(seg_id), _p(sumsq), max_norm,
+                                        _p(hyper), ema_decay, theta.numel(), _p(theta), _p(ema), _p(theta16)),
+              "rsr_clip_sgd_ema")
+        self.launches += 1
+
+    def clip_adam_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, m, v, ema, theta16):
+        check(self.lib.rsr_clip_adam_ema(self.h, _stream(), _p(grad), gmul, _p(seg_id), _p(sumsq), max_norm,
+                                         _p(hyper), ema_decay, theta.numel(), _p(theta), _p(m), _p(v), _p(ema),
+                                         _p(theta16)), "rsr_clip_adam_ema")
+        self.launches += 1
+
+    def cast16(self, x, out16):
+        check(self.lib.rsr_cast16(self.h, _stream(), _p(x), x.numel(), _p(out16)), "rsr_cast16")
+        self.launches += 1
+
+    def fill32(self, x, v):
+        check(self.lib.rsr_fill32(self.h, _stream(), _p(x), x.numel(), v), "rsr_fill32")
+        self.launches += 1
