@@ -50,7 +50,7 @@ int rsr_num_sms(rsr_handle* h);
 /* D[M,N] = epi(alpha * A[M,K] * B[K,N]) ; A and B are h16 operands fed by TMA.
  *   a_mn = 0: A stored row-major [M, lda] (K contiguous);  a_mn = 1: A stored [K, lda] (M contiguous)
  *   b_mn = 0: B stored [N, ldb] (K contiguous);             b_mn = 1: B stored row-major [K, ldb] (N contiguous)
- * epi(v): v += bias[n]; v += resid[m,n]; v = act(v); v *= act'(dact_src[m,n]) ; v += beta*out32_old
+ * epi(v): v += bias[n]; v += resid[m,n]; v = act(v); v *= act'(dact_src[m,n]) ; out16 = h16(v) ; out32 = v + beta*out32_old
  * Replaces tf.contrib.layers.fully_connected (models/lstm.py:82-87,121-124,
  * models/discriminator_dnn.py:61-93, models/discriminator_lstm.py:100-104), the input half of
  * LSTMCell's _Linear (models/lstm.py:90-96) hoisted over all frames, and their gradients. */

@@ -69,8 +69,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// Every spin in the library is bounded: a wait that cannot complete (bad tensor map, a group of
+// the persistent kernels that is not co-resident) traps -- the launch fails with an error the host
+// sees at the next synchronisation -- instead of hanging the device.
+#ifndef RSR_SPIN_LIMIT_NS
+#define RSR_SPIN_LIMIT_NS 2000000000ull   // 2 s
+#endif
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) { }
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = global_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0 && global_ns() - t0 > RSR_SPIN_LIMIT_NS) __trap();
+    }
 }
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -197,6 +213,15 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+// wait until *p >= want (monotonic step counter of a CTA group); bounded, see mbar_wait
+__device__ __forceinline__ void spin_until_ge(const unsigned int* p, unsigned int want) {
+    if (ld_acquire(p) >= want) return;
+    const uint64_t t0 = global_ns();
+    uint32_t spins = 0;
+    while (ld_acquire(p) < want) {
+        if ((++spins & 1023u) == 0 && global_ns() - t0 > RSR_SPIN_LIMIT_NS) __trap();
+    }
 }
 
 }  // namespace rsr

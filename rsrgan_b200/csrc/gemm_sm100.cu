@@ -196,22 +196,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (n + j < p.N) v[j] *= act_grad_from_out(h2f(d[j], p.bf), p.dact);
             }
         }
-        if (p.out32) {
+        if (p.out32) {   // fp32 output carries the beta accumulation; the 16-bit output below does not
             float* o = p.out32 + (size_t)row * p.ldc32 + n;
             if (full) {
-                if (p.beta != 0.0f) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
+                for (int j = 0; j < 16; j += 4) {
+                    float4 w = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    if (p.beta != 0.0f) {
                         const float4 q = *reinterpret_cast<const float4*>(o + j);
-                        v[j] += p.beta * q.x; v[j + 1] += p.beta * q.y; v[j + 2] += p.beta * q.z; v[j + 3] += p.beta * q.w;
+                        w.x += p.beta * q.x; w.y += p.beta * q.y; w.z += p.beta * q.z; w.w += p.beta * q.w;
                     }
+                    *reinterpret_cast<float4*>(o + j) = w;
                 }
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
                 for (int j = 0; j < 16; ++j)
-                    if (n + j < p.N) { if (p.beta != 0.0f) v[j] += p.beta * o[j]; o[j] = v[j]; }
+                    if (n + j < p.N) o[j] = p.beta != 0.0f ? v[j] + p.beta * o[j] : v[j];
             }
         }
         if (p.out16) {

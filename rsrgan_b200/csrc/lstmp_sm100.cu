@@ -108,7 +108,7 @@ lstmp_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         if (tid == 0) {
             if (t > 0) {
                 const unsigned int want = (unsigned int)G * (unsigned int)t;
-                while (ld_acquire(flag) < want) { }
+                spin_until_ge(flag, want);
             }
             fence_proxy_async_all();
             mbar_expect_tx(barB, (uint32_t)KB * NB * 128u);
@@ -266,7 +266,7 @@ lstmp_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const BwdParams p)
         if (step > 0) {
             if (tid == 0) {
                 const unsigned int want = (unsigned int)per_grp * (unsigned int)step;
-                while (ld_acquire(flag) < want) { }
+                spin_until_ge(flag, want);
             }
             __syncthreads();
         }

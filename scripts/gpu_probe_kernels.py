@@ -210,7 +210,7 @@ def probe_elt(h):
     hy2 = torch.tensor([0.05, 0, 0, 0, 0, 0, 0, 0], dtype=torch.float32, device=dev)
     h.seg_sumsq(d_grad, 1.0 / 8.0, d_seg, 3, sumsq)
     h.clip_sgd_ema(d_grad, 1.0 / 8.0, d_seg, sumsq, 15.0, hy2, 0.9999, d_theta2, d_ema2, None)
-    ref = np.concatenate([theta[:3072] - 0.05 * O.clip_by_norm(grad[:3072].astype(np.float64)), theta[3072:] - 0.05 * grad[3072:]])
+    ref = np.concatenate([theta[a:b] - 0.05 * O.clip_by_norm(grad[a:b].astype(np.float64)) for a, b in ((0, 3072), (3072, 4096), (4096, 6144))])
     print("sgd theta: maxabs %.3e" % rel(d_theta2.cpu().numpy(), ref)[0])
 
 
