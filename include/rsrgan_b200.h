@@ -172,6 +172,16 @@ int rsr_clip_adam_ema(rsr_handle* h, void* stream, const float* grad, float gmul
                       const float* sumsq, float max_norm, float* hyper, float ema_decay,
                       long long n_elems, float* theta, float* m, float* v, float* ema, void* theta16);
 
+/* L2 regulariser of G (models/gan_rnn_placeholder.py:253-258): grad += scale * theta on every
+ * 1024-block whose segment has seg_flag != 0 (tensors whose name does not contain "bias"). */
+int rsr_l2_grad(rsr_handle* h, void* stream, float* grad, const float* theta, const int* seg_id,
+                const int* seg_flag, float scale, long long n_elems);
+
+/* residual connection x_{l+1} = out_l + x_l (models/res_lstm_l.py:116,127,138,187):
+ * out32 = a + b, out16 = h16(a + b); n multiple of 4; either output may be NULL. */
+int rsr_add_cast(rsr_handle* h, void* stream, const float* a, const float* b, long long n,
+                 float* out32, void* out16);
+
 /* misc ---------------------------------------------------------------------------------- */
 int rsr_cast16(rsr_handle* h, void* stream, const float* x, long long n, void* out16);
 int rsr_fill32(rsr_handle* h, void* stream, float* x, long long n, float v);

@@ -171,6 +171,34 @@ __global__ void cast16_kernel(const float* __restrict__ x, long long n, uint16_t
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = f2h(x[i], bf);
 }
 
+// residual add: out32 = a + b, out16 = h16(a + b)   (models/res_lstm_l.py:116,127,138,187)
+__global__ void add_cast_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4,
+                                float* __restrict__ o32, uint16_t* __restrict__ o16, int bf) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 x = reinterpret_cast<const float4*>(a)[i];
+        const float4 y = reinterpret_cast<const float4*>(b)[i];
+        const float4 v = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+        if (o32) reinterpret_cast<float4*>(o32)[i] = v;
+        if (o16) {
+            uint2 o; o.x = pack2(v.x, v.y, bf); o.y = pack2(v.z, v.w, bf);
+            reinterpret_cast<uint2*>(o16)[i] = o;
+        }
+    }
+}
+
+// L2 regulariser gradient on the flat buffer: grad += scale * theta on the 1024-blocks whose
+// segment is flagged (non-bias tensors; models/gan_rnn_placeholder.py:253-258)
+__global__ void __launch_bounds__(256) l2_grad_kernel(float* __restrict__ g, const float* __restrict__ theta,
+                                                      const int* __restrict__ seg_id, const int* __restrict__ seg_flag,
+                                                      float scale) {
+    if (!seg_flag[seg_id[blockIdx.x]]) return;
+    const long long base = (long long)blockIdx.x * 1024 + threadIdx.x * 4;
+    float4 q = *reinterpret_cast<float4*>(g + base);
+    const float4 t = *reinterpret_cast<const float4*>(theta + base);
+    q.x += scale * t.x; q.y += scale * t.y; q.z += scale * t.z; q.w += scale * t.w;
+    *reinterpret_cast<float4*>(g + base) = q;
+}
+
 // ---------------------------------------------------------------------------------------
 // update sweep. One block = 1024 contiguous elements of exactly one segment (tensor).
 // ---------------------------------------------------------------------------------------
@@ -368,6 +396,25 @@ extern "C" int rsr_clip_adam_ema(rsr_handle* h, void* stream, const float* grad,
         grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, m, v, ema, (uint16_t*)theta16,
         h->dtype == RSR_DTYPE_BF16);
     adam_tock_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_add_cast(rsr_handle* h, void* stream, const float* a, const float* b, long long n,
+                            float* out32, void* out16) {
+    if (!h || !a || !b || (!out32 && !out16) || n < 0 || (n & 3)) return RSR_E_ARG;
+    if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)out32) & 15 || ((uintptr_t)out16 & 7)) return RSR_E_ARG;
+    if (n == 0) return 0;
+    add_cast_kernel<<<grid_for(n / 4, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        a, b, n / 4, out32, (uint16_t*)out16, h->dtype == RSR_DTYPE_BF16);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_l2_grad(rsr_handle* h, void* stream, float* grad, const float* theta, const int* seg_id,
+                           const int* seg_flag, float scale, long long n_elems) {
+    if (!h || !grad || !theta || !seg_id || !seg_flag || n_elems <= 0 || (n_elems & 1023)) return RSR_E_ARG;
+    l2_grad_kernel<<<(unsigned)(n_elems / 1024), 256, 0, (cudaStream_t)stream>>>(grad, theta, seg_id, seg_flag, scale);
     RSR_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,402 @@
+"""GAN_RNN -- host-side mirror of the reference trainer object.
+
+Reference: models/gan_rnn_placeholder.py:63-317 (class GAN_RNN), driven by
+scripts/train_gan_rnn_placeholder.py:48-201.  Same constructor signature and attribute names
+(`.inputs/.labels/.lengths` feed names, `.d_real/.d_fake`, `.g_learning_rate/.d_learning_rate`,
+`.disc_noise_std`, `.mse_lambda`, `.disc_updates/.gen_updates`, `.save/.load`), but instead of
+`sess.run([model.d_opt, ...], feed_dict)` the caller invokes
+
+    d_step(inputs, labels, lengths)   ==  sess.run([d_opt, d_rl_losses, d_fk_losses, d_losses])   (train...py:76-82)
+    g_step(inputs, labels, lengths)   ==  sess.run([g_opt, g_adv_losses, g_mse_losses, ...])     (train...py:95-101)
+    eval_losses(...)                  ==  the two loss-only sess.run of eval_one_iteration          (train...py:154-172)
+    generate(inputs, lengths)         ==  sess.run(model.g_outputs)                                 (train...py:277-281)
+
+One process drives ONE GPU; the reference's in-graph towers (gan_rnn_placeholder.py:152-175)
+become ranks of torch.distributed and `average_gradients` (utils/ops.py:343-376) becomes one
+NCCL all-reduce of the flat gradient buffer per update, with the 1/num_gpu folded into the
+clip+optimizer kernel.  All arithmetic runs in librsrgan_sm100.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import math
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import nets, ops
+
+F32 = torch.float32
+
+LOSS_NAMES = ("d_rl_loss", "d_fk_loss", "d_loss", "g_adv_loss", "g_mse_loss", "g_l2_loss", "g_loss")
+
+
+def _arg(args, name, default):
+    return getattr(args, name, default) if args is not None else default
+
+
+class Model(object):
+    """models/gan_rnn_placeholder.py:20-60 -- save / load with the TF Saver conventions
+    (files <save_dir>/<name>-<step>, a `checkpoint` index naming the latest, max_to_keep=10).
+    The container is torch.save of {TF variable name -> array}; see DESIGN.md for TF-ckpt interop."""
+
+    def __init__(self, name="BaseModel"):
+        self.name = name
+
+    def _ckpt_path(self, save_dir, step):
+        return os.path.join(save_dir, "%s-%d.pt" % (self.name, step))
+
+    def save(self, save_dir, step):
+        os.makedirs(save_dir, exist_ok=True)
+        path = self._ckpt_path(save_dir, step)
+        torch.save(self.state_dict(), path)
+        index = os.path.join(save_dir, "checkpoint")
+        kept = []
+        if os.path.exists(index):
+            with open(index) as f:
+                kept = [l.strip() for l in f if l.strip()]
+        base = os.path.basename(path)
+        kept = [k for k in kept if k != base] + [base]
+        while len(kept) > 10:                       # tf.train.Saver(max_to_keep=10), :32
+            old = kept.pop(0)
+            try:
+                os.remove(os.path.join(save_dir, old))
+            except OSError:
+                pass
+        with open(index, "w") as f:
+            f.write("\n".join(kept) + "\n")
+        return path
+
+    def load(self, save_dir, model_file=None, moving_average=False):
+        if not os.path.exists(save_dir):
+            print("[!] Checkpoints path does not exist...")
+            return False
+        print("[*] Reading checkpoints...")
+        if model_file is None:
+            index = os.path.join(save_dir, "checkpoint")
+            if not os.path.exists(index):
+                return False
+            with open(index) as f:
+                kept = [l.strip() for l in f if l.strip()]
+            if not kept:
+                return False
+            ckpt_name = kept[-1]
+        else:
+            ckpt_name = model_file
+        sd = torch.load(os.path.join(save_dir, ckpt_name), map_location="cpu", weights_only=False)
+        self.load_state_dict(sd, moving_average=moving_average)
+        print("[*] Read {}".format(ckpt_name))
+        return True
+
+
+class GAN_RNN(Model):
+    """Generative Adversarial Network for speech dereverberation (257-d LPS -> 40-d MFCC)."""
+
+    def __init__(self, sess, args, devices, cross_validation=False, infer=False, name="GAN_RNN",
+                 handle=None, share=None):
+        super(GAN_RNN, self).__init__(name)
+        self.sess = sess                                   # unused (no TF session); kept for the call signature
+        self.cross_validation = cross_validation
+        self.infer = infer
+        self.MOVING_AVERAGE_DECAY = 0.9999                 # :69
+        self.max_grad_norm = 15                            # :70
+        self.keep_prob = 1.0 if cross_validation else _arg(args, "keep_prob", 1.0)
+        self.batch_norm = _arg(args, "batch_norm", False)
+        if self.batch_norm or self.keep_prob < 1.0:
+            # contrib batch_norm(renorm) / DropoutWrapper (models/lstm.py:61-67,99-102): off in the
+            # shipped driver (run_gan_rnn_placeholder.sh:131); not part of the B200 hot path yet.
+            raise NotImplementedError("batch_norm / dropout are not implemented (SURVEY.md section 8f)")
+        self.batch_size = _arg(args, "batch_size", 8)
+        self.devices = devices
+        self.num_gpu = _arg(args, "num_gpu", 1)
+        self.save_dir = _arg(args, "save_dir", "exp/gan_rnn")
+        self.l2_scale = _arg(args, "l2_scale", 0.0)
+        self.input_dim = _arg(args, "input_dim", 257)
+        self.output_dim = _arg(args, "output_dim", 40)
+        self.left_context = _arg(args, "left_context", 0)
+        self.right_context = _arg(args, "right_context", 0)
+        self.inputs, self.labels, self.lengths = "inputs", "labels", "lengths"   # feed names (:94-104)
+        self.g_disturb_weights = False
+        self.d_clip_weights = False
+        self.disc_updates = _arg(args, "disc_updates", 1)
+        self.gen_updates = _arg(args, "gen_updates", 2)
+        self.mse_lambda = float(_arg(args, "init_mse_weight", 1.0))
+        self.disc_noise_std = float(_arg(args, "init_disc_noise_std", 0.0))
+        self.d_real, self.d_fake = 1.0, 0.0                # :122-123
+        self.g_type = _arg(args, "g_type", "lstm")
+        self.d_type = _arg(args, "d_type", "lstm")        # reference hard-wires discriminator_lstm (:117)
+
+        self.world = 1
+        self.dist = None
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.dist = torch.distributed
+            self.world = torch.distributed.get_world_size()
+
+        if share is not None:
+            # train and CV models share weights (scripts/train_gan_rnn_placeholder.py:431-437) but own their
+            # scalars
+            self.h, self.G, self.D = share.h, share.G, share.D
+        else:
+            dev = 0
+            if devices:
+                d0 = str(devices[0])
+                dev = int(d0.split(":")[-1]) if ":" in d0 else 0
+            self.h = handle if handle is not None else ops.Handle(dev, _arg(args, "dtype", "f16"))
+            in_dim = self.input_dim * (self.left_context + 1 + self.right_context)
+            gk = dict(in_dim=in_dim, out_dim=self.output_dim)
+            for k_arg, k in (("g_cell", "cell"), ("g_proj", "proj"), ("g_layers", "layers"), ("g_units", "units")):
+                v = _arg(args, k_arg, None)
+                if v is not None:
+                    gk[k] = v
+            if self.g_type in ("res_lstm_l", "res_lstm_base"):
+                gk.pop("proj", None)
+                gk.pop("units", None)
+            self.G = nets.Generator(self.h, self.g_type, **gk)
+            self.D = None
+            if not infer:
+                dk = dict(in_dim=self.output_dim)
+                for k_arg, k in (("d_cell", "cell"), ("d_proj", "proj"), ("d_layers", "layers"), ("d_units", "units")):
+                    v = _arg(args, k_arg, None)
+                    if v is not None:
+                        dk[k] = v
+                self.D = nets.Discriminator(self.h, self.d_type, **dk)
+            self.init_weights(_arg(args, "seed", 1234))
+        self.g_learning_rate = float(_arg(args, "g_learning_rate", 0.0003))
+        self.d_learning_rate = float(_arg(args, "d_learning_rate", 0.001))
+        dev = self.h.device
+        self._losses = torch.zeros(8, dtype=F32, device=dev)
+        self._l2 = torch.zeros(1, dtype=F32, device=dev)
+        self._pin = {}
+        self.g_outputs = None
+        self.summaries = None
+        self.writer = None
+
+    # ------------------------------------------------------------------ scalars on device
+    @property
+    def g_learning_rate(self):
+        return self._g_lr
+
+    @g_learning_rate.setter
+    def g_learning_rate(self, v):
+        self._g_lr = float(v)
+        if not self.cross_validation:
+            self.G.P.set_lr(v)
+
+    @property
+    def d_learning_rate(self):
+        return self._d_lr
+
+    @d_learning_rate.setter
+    def d_learning_rate(self, v):
+        self._d_lr = float(v)
+        if self.D is not None and not self.cross_validation:
+            self.D.P.set_lr(v)
+
+    # ------------------------------------------------------------------ weights
+    def init_weights(self, seed=1234):
+        """xavier_initializer() / zeros / truncated-normal as the reference builds its variables
+        (models/lstm.py:86,92; models/discriminator_dnn.py:26-27).  Host numpy RNG, then one upload."""
+        rng = np.random.default_rng(seed)
+
+        def init(net):
+            p = OrderedDict()
+            for s in net.P.segs.values():
+                if "bias" in s.name:
+                    p[s.name] = np.zeros(s.tf_shape, np.float32)
+                elif self.d_type == "dnn" and s.name.startswith("d_model") and s.tf_shape[-1] != 1:
+                    std = math.sqrt(2.0 / s.tf_shape[1])
+                    v = rng.standard_normal(s.tf_shape)
+                    bad = np.abs(v) > 2
+                    while bad.any():
+                        v[bad] = rng.standard_normal(int(bad.sum()))
+                        bad = np.abs(v) > 2
+                    p[s.name] = (v * std).astype(np.float32)
+                else:
+                    fi, fo = (s.tf_shape[0], s.tf_shape[0]) if len(s.tf_shape) == 1 else s.tf_shape
+                    lim = math.sqrt(6.0 / (fi + fo))
+                    p[s.name] = rng.uniform(-lim, lim, s.tf_shape).astype(np.float32)
+            net.load_tf(p)
+
+        init(self.G)
+        if self.D is not None:
+            init(self.D)
+
+    def load_params(self, g_params=None, d_params=None):
+        """dicts TF-variable-name -> array (TF layout)."""
+        if g_params is not None:
+            self.G.load_tf(g_params)
+        if d_params is not None:
+            self.D.load_tf(d_params)
+
+    def state_dict(self):
+        sd = OrderedDict(G=self.G.P.state_dict())
+        if self.D is not None:
+            sd["D"] = self.D.P.state_dict()
+        sd["scalars"] = dict(mse_lambda=self.mse_lambda, disc_noise_std=self.disc_noise_std,
+                             d_learning_rate=self.d_learning_rate, g_learning_rate=self.g_learning_rate,
+                             d_real=self.d_real, d_fake=self.d_fake)
+        return sd
+
+    def load_state_dict(self, sd, moving_average=False):
+        for net, key in ((self.G, "G"), (self.D, "D")):
+            if net is None or key not in sd:
+                continue
+            net.P.load_state_dict(sd[key])
+            if moving_average:                              # :47-53 restore the EMA shadows as the weights
+                net.P.theta.copy_(net.P.ema)
+            net.P.refresh16()
+            net.refresh()
+        for k, v in sd.get("scalars", {}).items():
+            setattr(self, k, v)
+
+    # ------------------------------------------------------------------ feeding
+    def _to_dev(self, name, a, dtype):
+        """host numpy / torch -> device tensor through a pinned staging buffer (async H2D)."""
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a.to(dtype).contiguous()
+        t = torch.as_tensor(np.ascontiguousarray(a)) if not isinstance(a, torch.Tensor) else a.contiguous()
+        t = t.to(dtype)
+        if self.h.device.type != "cuda":                   # host-logic tests drive a test double on CPU tensors
+            return t.clone()
+        key = (name, tuple(t.shape), dtype)
+        if key not in self._pin:
+            self._pin[key] = (torch.empty(t.shape, dtype=dtype, pin_memory=True),
+                              torch.empty(t.shape, dtype=dtype, device=self.h.device))
+        pin, dev = self._pin[key]
+        pin.copy_(t)
+        dev.copy_(pin, non_blocking=True)
+        return dev
+
+    def _feed(self, inputs, labels, lengths):
+        x = self._to_dev("x", inputs, F32)
+        B, T = int(x.shape[0]), int(x.shape[1])
+        # lengths are fed as float32 and cast to int32 (gan_rnn_placeholder.py:102-104)
+        ln = self._to_dev("len", lengths, torch.int32)
+        y_tm = None
+        if labels is not None:
+            y = self._to_dev("y", labels, F32)
+            y_tm = self.G.ws.get(("feed", "y_tm", B), T * B, self.output_dim, F32)
+            self.h.stage_input(y, B, T, self.output_dim, out32=y_tm)
+        return x, y_tm, ln, B, T
+
+    def _noise(self, B, given, slot="rl"):
+        if self.d_type != "lstm":
+            return None                                    # discriminator_dnn has no noise layer
+        if given is not None:
+            return self._to_dev("noise_" + slot, np.asarray(given, np.float32).reshape(B, -1), F32)
+        if self.disc_noise_std <= 0.0:
+            return None
+        # utils/ops.py:19-30: tf.random_normal of shape (B, 1, D) -- one draw per utterance
+        return torch.randn(B, self.output_dim, dtype=F32, device=self.h.device) * self.disc_noise_std
+
+    def _gscale(self, rows):
+        """static loss scale keeping 16-bit gradient tensors in range (fp16 operands)"""
+        if self.h.dtype_id == ops._lib.RSR_DTYPE_BF16:
+            return 1.0
+        return float(2.0 ** round(math.log2(max(rows / max(self.mse_lambda, 1.0), 1.0))))
+
+    # ------------------------------------------------------------------ updates
+    def _update(self, net, gscale, adam):
+        P, h = net.P, self.h
+        if self.world > 1:
+            self.dist.all_reduce(P.grad)                   # utils/ops.py:343-376 average_gradients (sum here, 1/N below)
+        gmul = 1.0 / (self.world * gscale)
+        h.seg_sumsq(P.grad, gmul, P.seg_id, len(P.segs), P.sumsq)
+        if adam:
+            h.clip_adam_ema(P.grad, gmul, P.seg_id, P.sumsq, float(self.max_grad_norm), P.hyper,
+                            self.MOVING_AVERAGE_DECAY, P.theta, P.m, P.v, P.ema, P.theta16)
+        else:
+            h.clip_sgd_ema(P.grad, gmul, P.seg_id, P.sumsq, float(self.max_grad_norm), P.hyper,
+                           self.MOVING_AVERAGE_DECAY, P.theta, P.ema, P.theta16)
+        net.refresh()
+
+    def _loss_dict(self, vals, which):
+        d_rl, d_fk, g_adv, g_mse, g_l2 = (float(v) for v in vals[:5])
+        out = OrderedDict()
+        if which in ("d", "both"):
+            out.update(d_rl_loss=d_rl, d_fk_loss=d_fk, d_loss=d_rl + d_fk)
+        if which in ("g", "both"):
+            out.update(g_adv_loss=g_adv, g_mse_loss=g_mse, g_l2_loss=g_l2,
+                       g_loss=g_adv + self.mse_lambda * g_mse + g_l2)
+        return out
+
+    def _l2_loss(self):
+        """l2_scale * sum_{non-bias} 0.5 ||v||^2   (gan_rnn_placeholder.py:253-258)"""
+        if self.l2_scale <= 0.0 or self.cross_validation:
+            self._losses[4:5].zero_()
+            return
+        P = self.G.P
+        self.h.seg_sumsq(P.theta, 1.0, P.seg_id, len(P.segs), P.sumsq)
+        self._losses[4:5] = 0.5 * self.l2_scale * (P.sumsq * P.seg_l2.to(F32)).sum()
+
+    def d_step(self, inputs, labels, lengths, noise_rl=None, noise_fk=None, sync=True):
+        """One discriminator update: L_D = mean((D(y)-d_real)^2) + mean((D(G(x))-d_fake)^2),
+        gradients wrt theta_D only, tower mean, per-tensor clip 15, SGD(lr_d), EMA."""
+        x, y_tm, ln, B, T = self._feed(inputs, labels, lengths)
+        h, G, D, rows = self.h, self.G, self.D, T * B
+        gs = self._gscale(rows)
+        g32 = G.fwd(x, B, T, ln, train=False)
+        lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=self._noise(B, noise_rl))
+        lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"))
+        d_rl16 = D.ws.get(("loss", "d_rl16"), rows, 8, h.h16)
+        d_fk16 = D.ws.get(("loss", "d_fk16"), rows, 8, h.h16)
+        self._losses.zero_()
+        h.lsgan_mse_losses(self._losses, rl=lg_rl, fk=lg_fk, ld_logit=lg_rl.stride(0), n_logit=rows, clip=D.clip,
+                           g=g32, y=y_tm, n_frames=rows, d_out=self.output_dim, d_real=self.d_real,
+                           d_fake=self.d_fake, lam=self.mse_lambda, gscale=gs, d_rl_grad=d_rl16,
+                           d_fk_grad=d_fk16, ld_grad=8)
+        h.fill32(D.P.grad, 0.0)
+        D.bwd("rl", d_rl16)
+        D.bwd("fk", d_fk16)
+        self._update(D, gs, adam=False)
+        return self._loss_dict(self._losses.tolist(), "d") if sync else self._losses
+
+    def g_step(self, inputs, labels, lengths, noise_fk=None, sync=True):
+        """One generator update: L_G = mean((D(G(x))-d_real)^2) + lambda*0.5*40*mean((G(x)-y)^2) [+ l2],
+        gradients wrt theta_G only (through D, D frozen), tower mean, clip 15, Adam(lr_g), EMA."""
+        x, y_tm, ln, B, T = self._feed(inputs, labels, lengths)
+        h, G, D, rows = self.h, self.G, self.D, T * B
+        gs = self._gscale(rows)
+        g32 = G.fwd(x, B, T, ln, train=True)
+        lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"))
+        g_adv16 = D.ws.get(("loss", "g_adv16"), rows, 8, h.h16)
+        dg32 = D.ws.get(("loss", "dg32"), rows, g32.shape[1], F32)
+        self._losses.zero_()
+        h.lsgan_mse_losses(self._losses, fk=lg_fk, ld_logit=lg_fk.stride(0), n_logit=rows, clip=D.clip,
+                           g=g32, y=y_tm, n_frames=rows, d_out=self.output_dim, d_real=self.d_real,
+                           d_fake=self.d_fake, lam=self.mse_lambda, gscale=gs, g_adv_grad=g_adv16,
+                           ld_grad=8, dg_mse=dg32)
+        dg16 = D.bwd("fk", g_adv16, want_dw=False, want_dx=True, resid32=dg32)
+        h.fill32(G.P.grad, 0.0)
+        G.bwd(dg16)
+        self._l2_loss()
+        if self.l2_scale > 0.0:
+            h.l2_grad(G.P.grad, G.P.theta, G.P.seg_id, G.P.seg_l2, self.l2_scale * gs)
+        self._update(G, gs, adam=True)
+        return self._loss_dict(self._losses.tolist(), "g") if sync else self._losses
+
+    def eval_losses(self, inputs, labels, lengths, noise_rl=None, noise_fk=None, sync=True):
+        """Loss-only pass of eval_one_iteration (scripts/train_gan_rnn_placeholder.py:154-172)."""
+        x, y_tm, ln, B, T = self._feed(inputs, labels, lengths)
+        h, G, D, rows = self.h, self.G, self.D, T * B
+        g32 = G.fwd(x, B, T, ln, train=False)
+        lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=self._noise(B, noise_rl), train=False)
+        lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"), train=False)
+        self._losses.zero_()
+        h.lsgan_mse_losses(self._losses, rl=lg_rl, fk=lg_fk, ld_logit=lg_rl.stride(0), n_logit=rows, clip=D.clip,
+                           g=g32, y=y_tm, n_frames=rows, d_out=self.output_dim, d_real=self.d_real,
+                           d_fake=self.d_fake, lam=self.mse_lambda, gscale=1.0)
+        return self._loss_dict(self._losses.tolist(), "both") if sync else self._losses
+
+    def generate(self, inputs, lengths, mean=None, std=None):
+        """G(inputs) as a (B, T, output_dim) fp32 device tensor; with mean/std the decode-time inverse
+        CMVN y*std+mean (scripts/train_gan_rnn_placeholder.py:286-287) is fused into the un-staging."""
+        x, _, ln, B, T = self._feed(inputs, None, lengths)
+        y32 = self.G.fwd(x, B, T, ln, train=False)
+        out = torch.empty(B, T, self.output_dim, dtype=F32, device=self.h.device)
+        m = None if mean is None else self._to_dev("cm_mean", mean, F32)
+        s = None if std is None else self._to_dev("cm_std", std, F32)
+        self.h.unstage_output(y32, B, T, self.output_dim, out, mean=m, std=s)
+        self.g_outputs = out
+        return out

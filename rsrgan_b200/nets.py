@@ -1,0 +1,366 @@
+"""Network definitions of the GAN hot path, expressed as sequences of C-ABI kernel calls.
+
+Mirrors the reference's L2 layer:
+  * generators  `lstm` (models/lstm.py:41-129), `res_lstm_l` (models/res_lstm_l.py:41-199),
+    `res_lstm_base` (models/res_lstm_base.py:111-131,190) and the frame-level `dnn`
+    (models/dnn.py:32-114);
+  * discriminators `discriminator_lstm` (models/discriminator_lstm.py:24-110) and
+    `discriminator_dnn` (models/discriminator_dnn.py:21-98, applied per frame).
+The reference hard-codes the layer sizes inside those files; here they are constructor
+arguments whose defaults are the reference values.
+
+Every activation lives time-major ([T*B, ld] rows = t*B + b) in zero-padded 16-bit buffers
+(fp32 copies only where a residual or a loss needs them).  torch is the allocator only; all
+arithmetic is done by librsrgan_sm100.so (ops.Handle).  No function here has a CPU path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import packing, params
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU
+
+F32 = torch.float32
+
+
+class Workspace(object):
+    """Named device buffers, zero-filled at allocation, grown on demand (rows only)."""
+
+    def __init__(self, handle):
+        self.h = handle
+        self.bufs = {}
+
+    def get(self, key, rows, cols, dtype):
+        t = self.bufs.get(key)
+        if t is None or t.shape[0] < rows or t.shape[1] != cols or t.dtype != dtype:
+            t = torch.zeros(rows, cols, dtype=dtype, device=self.h.device)
+            self.bufs[key] = t
+        return t[:rows]
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
+class FC(object):
+    """tf.contrib.layers.fully_connected over the last axis (models/lstm.py:82-87,121-124;
+    models/discriminator_dnn.py:61-93; models/discriminator_lstm.py:100-104; models/dnn.py:79-110)."""
+
+    def __init__(self, net, scope, n_in, n_out, act):
+        self.net, self.scope, self.n_in, self.n_out, self.act = net, scope, n_in, n_out, act
+        self.inp, self.outp = packing.round_up(n_in, 8), packing.round_up(n_out, 8)
+        self.wname, self.bname = scope + "/weights", scope + "/biases"
+
+    def segs(self):
+        return [params.fc_w(self.wname, self.n_in, self.n_out), params.fc_b(self.bname, self.n_out)]
+
+    def refresh(self):
+        pass
+
+    def fwd(self, ctx, x16, rows, want16=True, want32=False):
+        net, h = self.net, self.net.h
+        y16 = net.ws.get((ctx, self.scope, "y16"), rows, self.outp, h.h16) if want16 else None
+        y32 = net.ws.get((ctx, self.scope, "y32"), rows, self.outp, F32) if want32 else None
+        h.gemm(x16, net.P.view(self.wname, "theta16"), rows, self.outp, self.inp, b_mn=True,
+               bias=net.P.view(self.bname), act=self.act, out16=y16, out32=y32)
+        return y16, y32
+
+    def bwd(self, ctx, x16, dy16, rows, want_dw=True, want_dx=True, prev_y16=None, prev_act=ACT_NONE,
+            resid32=None, want32=False):
+        """dy16: gradient wrt this layer's PRE-activation.  Returns the gradient wrt the input,
+        multiplied by prev_act'(prev_y16) when the producer of x16 was an activated FC."""
+        net, h = self.net, self.net.h
+        if want_dw:
+            h.gemm(x16, dy16, self.inp, self.outp, rows, a_mn=True, b_mn=True, beta=1.0,
+                   out32=net.P.view(self.wname, "grad"))
+            h.colsum16(dy16, rows, self.outp, net.P.view(self.bname, "grad"), accumulate=True)
+        if not want_dx:
+            return None, None
+        dx16 = net.ws.get((ctx, self.scope, "dx16"), rows, self.inp, h.h16)
+        dx32 = net.ws.get((ctx, self.scope, "dx32"), rows, self.inp, F32) if want32 else None
+        h.gemm(dy16, net.P.view(self.wname, "theta16"), rows, self.inp, self.outp, resid=resid32,
+               dact_src=prev_y16, dact=prev_act, out16=dx16, out32=dx32)
+        return dx16, dx32
+
+
+class LSTMP(object):
+    """tf.contrib.rnn.LSTMCell(C, use_peepholes=True, num_proj=P, forget_bias=1.0) under
+    tf.nn.dynamic_rnn(sequence_length) -- models/lstm.py:89-112, models/res_lstm_l.py:86-138,
+    models/discriminator_lstm.py:70-91.  Three kernels: hoisted input GEMM (X K_x + b), the
+    persistent recurrence with Wc = W_proj K_h resident on chip, hoisted projection GEMM."""
+
+    def __init__(self, net, prefix, I, C, P):
+        self.net, self.prefix, self.I, self.C, self.P = net, prefix, I, C, P
+        self.Ip, self.Pp, self.Cp = packing.round_up(I, 8), packing.round_up(P, 8), packing.cell_pad(C)
+        h = net.h
+        self.wc16 = torch.zeros(self.Cp, 4 * self.Cp, dtype=h.h16, device=h.device)    # Wc   (backward operand)
+        self.wcT16 = torch.zeros(4 * self.Cp, self.Cp, dtype=h.h16, device=h.device)   # Wc^T (forward operand)
+        self.scratch = torch.zeros(7 * self.Cp, dtype=F32, device=h.device)            # sink for unwanted db/dw
+
+    def segs(self):
+        return params.lstm_cell(self.prefix, self.I, self.C, self.P)
+
+    def _w(self, buf="theta16"):
+        P = self.net.P
+        K = P.view(self.prefix + "kernel", buf)
+        return K[:self.Ip], K[self.Ip:], P.view(self.prefix + "projection/kernel", buf)
+
+    def refresh(self):
+        """Wc = W_proj K_h after every weight update (fp32 accumulate, rounded once to 16 bit)."""
+        h = self.net.h
+        _, Kh16, Wp16 = self._w()
+        h.gemm(Wp16, Kh16, self.Cp, 4 * self.Cp, self.Pp, b_mn=True, out16=self.wc16)
+        h.gemm(Kh16, Wp16, 4 * self.Cp, self.Cp, self.Pp, a_mn=True, out16=self.wcT16)
+
+    def fwd(self, ctx, x16, B, T, lengths, save=True, want32=False):
+        """x16 [T*B, Ip] -> out_seq16 [(T+1)*B, Pp] (slot 0 = zero initial state; rows B.. are
+        the outputs) and optionally out32 [T*B, Pp]."""
+        net, h, P = self.net, self.net.h, self.net.P
+        rows, Cp = T * B, self.Cp
+        key = (ctx, self.prefix, B)
+        Kx16, _, Wp16 = self._w()
+        zx = net.ws.get((ctx, "zx", Cp, B), rows, 4 * Cp, F32)            # shared by layers of equal width
+        mt = net.ws.get(key + ("mt",), rows + B, Cp, h.h16)
+        out = net.ws.get(key + ("out",), rows + B, self.Pp, h.h16)
+        sv = net.ws.get(key + ("save",), rows, 5 * Cp, F32) if save else None
+        o32 = net.ws.get(key + ("o32",), rows, self.Pp, F32) if want32 else None
+        h.gemm(x16, Kx16, rows, 4 * Cp, self.Ip, b_mn=True, bias=P.view(self.prefix + "bias"), out32=zx)
+        h.lstmp_rec_fwd(B, T, Cp, zx, self.wcT16, P.view(self.prefix + "w_i_diag"),
+                        P.view(self.prefix + "w_f_diag"), P.view(self.prefix + "w_o_diag"), lengths, mt, sv)
+        h.gemm(mt[B:], Wp16, rows, self.Pp, Cp, b_mn=True, out16=out[B:], out32=o32)
+        return out, o32
+
+    def bwd(self, ctx, x16, dout16, dout32, B, T, lengths, want_dw=True, want_dx=True, prev_y16=None,
+            prev_act=ACT_NONE, resid32=None, want32=False):
+        """dout16/dout32: gradient wrt the layer output [T*B, Pp] (dout32 needed iff want_dw)."""
+        net, h, P = self.net, self.net.h, self.net.P
+        rows, Cp = T * B, self.Cp
+        key = (ctx, self.prefix, B)
+        Kx16, Kh16, Wp16 = self._w()
+        mt = net.ws.get(key + ("mt",), rows + B, Cp, h.h16)
+        out = net.ws.get(key + ("out",), rows + B, self.Pp, h.h16)
+        sv = net.ws.get(key + ("save",), rows, 5 * Cp, F32)
+        dmt = net.ws.get((ctx, "dmt", Cp, B), rows, Cp, F32)
+        dz = net.ws.get((ctx, "dz", Cp, B), rows + B, 4 * Cp, h.h16)
+        dz[rows:].zero_()                                  # dz_{T} = 0 (no step after the last one)
+        # dmt = dOut W_proj^T ; the recurrence kernel adds dz_{t+1} Wc^T
+        h.gemm(dout16, Wp16, rows, Cp, self.Pp, out32=dmt)
+        if want_dw:
+            gb = P.view(self.prefix + "bias", "grad")
+            gi, gf, go = (P.view(self.prefix + n, "grad") for n in ("w_i_diag", "w_f_diag", "w_o_diag"))
+        else:
+            s = self.scratch
+            gb, gi, gf, go = s[:4 * Cp], s[4 * Cp:5 * Cp], s[5 * Cp:6 * Cp], s[6 * Cp:]
+        h.lstmp_rec_bwd(B, T, Cp, dmt, self.wc16, P.view(self.prefix + "w_i_diag"),
+                        P.view(self.prefix + "w_f_diag"), P.view(self.prefix + "w_o_diag"), lengths, sv,
+                        dz, gb, gi, gf, go)
+        if want_dw:
+            gK = P.view(self.prefix + "kernel", "grad")
+            # dK = [x_t , m_{t-1}]^T dz_t  (two row blocks of the TF kernel)
+            h.gemm(x16, dz, self.Ip, 4 * Cp, rows, a_mn=True, b_mn=True, beta=1.0, out32=gK[:self.Ip])
+            h.gemm(out, dz, self.Pp, 4 * Cp, rows, a_mn=True, b_mn=True, beta=1.0, out32=gK[self.Ip:])
+            # dW_proj = mt_t^T (dOut_t + dz_{t+1} K_h^T)
+            dmtot = net.ws.get((ctx, "dmtot", self.Pp, B), rows, self.Pp, h.h16)
+            h.gemm(dz[B:], Kh16, rows, self.Pp, 4 * Cp, resid=dout32, out16=dmtot)
+            h.gemm(mt[B:], dmtot, Cp, self.Pp, rows, a_mn=True, b_mn=True, beta=1.0,
+                   out32=P.view(self.prefix + "projection/kernel", "grad"))
+        if not want_dx:
+            return None, None
+        dx16 = net.ws.get(key + ("dx16",), rows, self.Ip, h.h16)
+        dx32 = net.ws.get(key + ("dx32",), rows, self.Ip, F32) if want32 else None
+        h.gemm(dz, Kx16, rows, self.Ip, 4 * Cp, resid=resid32, dact_src=prev_y16, dact=prev_act,
+               out16=dx16, out32=dx32)
+        return dx16, dx32
+
+
+class Net(object):
+    """Common part: parameter store, workspace, weight-derived operands."""
+
+    def __init__(self, handle, layers_fn, adam):
+        self.h = handle
+        self.ws = Workspace(handle)
+        self.layers = layers_fn(self)
+        segs = []
+        for l in self.layers:
+            segs += l.segs()
+        self.P = params.ParamStore(handle, segs, adam)
+
+    def load_tf(self, p):
+        self.P.load_tf(p)
+        self.P.ema.copy_(self.P.theta)
+        self.refresh()
+
+    def refresh(self):
+        for l in self.layers:
+            l.refresh()
+
+
+class Generator(Net):
+    def __init__(self, handle, g_type="lstm", in_dim=257, out_dim=40, cell=760, proj=280, layers=None,
+                 units=1024):
+        self.g_type, self.in_dim, self.out_dim = g_type, in_dim, out_dim
+        if g_type == "lstm":
+            # models/lstm.py:43-45: cell 760, projection 280, 3 layers
+            L = 3 if layers is None else layers
+
+            def mk(net):
+                ls = [FC(net, "g_model/fully_connected", in_dim, proj, ACT_LRELU)]
+                ls += [LSTMP(net, "g_model/rnn/multi_rnn_cell/cell_%d/lstm_cell/" % i, proj, cell, proj)
+                       for i in range(L)]
+                return ls + [FC(net, "g_model/fully_connected_1", proj, out_dim, ACT_NONE)]
+        elif g_type in ("res_lstm_l", "res_lstm_base"):
+            # models/res_lstm_l.py:101-138: four LSTMP(760 -> in_dim) layers (the `lstm_num_layer = 3` at :45 is unused)
+            L = 4 if layers is None else layers
+
+            def mk(net):
+                ls = [LSTMP(net, "g_model/lstm_cell_%d/rnn/lstm_cell/" % (i + 1), in_dim, cell, in_dim)
+                      for i in range(L)]
+                return ls + [FC(net, "g_model/forward_out/fully_connected", in_dim, out_dim, ACT_NONE)]
+        elif g_type == "dnn":
+            # models/dnn.py:34-35,79-110: in -> 1024 x (1+3) ReLU -> out
+            L = 3 if layers is None else layers
+
+            def mk(net):
+                dims = [in_dim] + [units] * (L + 1)
+                ls = [FC(net, "g_model/fully_connected" + ("" if i == 0 else "_%d" % i), dims[i], dims[i + 1],
+                         ACT_RELU) for i in range(L + 1)]
+                return ls + [FC(net, "g_model/fully_connected_%d" % (L + 1), units, out_dim, ACT_NONE)]
+        else:
+            raise ValueError("Unrecognized G type {}".format(g_type))   # models/gan_rnn_placeholder.py:131-132
+        super(Generator, self).__init__(handle, mk, adam=True)
+        self.residual = g_type == "res_lstm_l"
+
+    def fwd(self, x, B, T, lengths, train=True, x_time_major=False):
+        """x fp32 (B, T, in_dim) batch-major on the device -> y32 [T*B, out_pad] time-major fp32."""
+        h, ws, rows = self.h, self.ws, T * B
+        ip = packing.round_up(self.in_dim, 8)
+        res = self.g_type in ("res_lstm_l", "res_lstm_base")
+        x16 = ws.get(("g", "x16", B), rows, ip, h.h16)
+        x32 = ws.get(("g", "x32", B), rows, ip, F32) if self.residual else None
+        h.stage_input(x, B, T, self.in_dim, out16=x16, out32=x32, time_major_in=x_time_major)
+        self._B, self._T, self._len = B, T, lengths
+        if self.g_type == "dnn":
+            a = x16
+            self._acts = [x16]
+            for l in self.layers[:-1]:
+                a, _ = l.fwd("g", a, rows)
+                self._acts.append(a)
+            _, y32 = self.layers[-1].fwd("g", a, rows, want16=False, want32=True)
+            return y32
+        if not res:
+            h0, _ = self.layers[0].fwd("g", x16, rows)
+            self._acts = [x16, h0]
+            a = h0
+            for l in self.layers[1:-1]:
+                seq, _ = l.fwd("g", a, B, T, lengths, save=train)
+                a = seq[B:]
+                self._acts.append(a)
+            _, y32 = self.layers[-1].fwd("g", a, rows, want16=False, want32=True)
+            return y32
+        a16, a32 = x16, x32
+        self._acts = [x16]
+        for i, l in enumerate(self.layers[:-1]):
+            seq, o32 = l.fwd("g", a16, B, T, lengths, save=train, want32=self.residual)
+            if self.residual:                      # x_{l+1} = out_l + x_l   (models/res_lstm_l.py:116,127,138,187)
+                n16 = ws.get(("g", "xr16", i, B), rows, ip, h.h16)
+                n32 = ws.get(("g", "xr32", i, B), rows, ip, F32)
+                h.add_cast(o32, a32, rows * ip, out32=n32, out16=n16)
+                a16, a32 = n16, n32
+            else:
+                a16 = seq[B:]
+            self._acts.append(a16)
+        _, y32 = self.layers[-1].fwd("g", a16, rows, want16=False, want32=True)
+        return y32
+
+    def bwd(self, dy16):
+        """dy16 [T*B, out_pad]: (scaled) gradient wrt the generator output.  Accumulates into P.grad."""
+        B, T, lengths, rows = self._B, self._T, self._len, self._T * self._B
+        acts, Ls = self._acts, self.layers
+        if self.g_type == "dnn":
+            d = dy16
+            for i in range(len(Ls) - 1, -1, -1):
+                d, _ = Ls[i].bwd("g", acts[i], d, rows, want_dx=i > 0, prev_y16=acts[i] if i > 0 else None,
+                                 prev_act=ACT_RELU)
+            return
+        if self.g_type == "lstm":
+            d16, d32 = Ls[-1].bwd("g", acts[-1], dy16, rows, want32=True)
+            for i in range(len(Ls) - 2, 0, -1):
+                first = i == 1
+                d16, d32 = Ls[i].bwd("g", acts[i], d16, d32, B, T, lengths, prev_y16=acts[1] if first else None,
+                                     prev_act=ACT_LRELU if first else ACT_NONE, want32=not first)
+            Ls[0].bwd("g", acts[0], d16, rows, want_dx=False)
+            return
+        d16, d32 = Ls[-1].bwd("g", acts[-1], dy16, rows, want32=True)
+        for i in range(len(Ls) - 2, -1, -1):
+            d16, d32 = Ls[i].bwd("g", acts[i], d16, d32, B, T, lengths, want_dx=i > 0,
+                                 resid32=d32 if self.residual else None, want32=True)
+
+
+class Discriminator(Net):
+    def __init__(self, handle, d_type="lstm", in_dim=40, cell=256, proj=40, layers=None, units=1024):
+        self.d_type, self.in_dim = d_type, in_dim
+        if d_type == "lstm":
+            # models/discriminator_lstm.py:26-28: cell 256, projection 40, 2 layers, FC -> 1 (no clip, :105)
+            L = 2 if layers is None else layers
+
+            def mk(net):
+                ls = [LSTMP(net, "d_model/rnn/multi_rnn_cell/cell_%d/lstm_cell/" % i, in_dim if i == 0 else proj,
+                            cell, proj) for i in range(L)]
+                return ls + [FC(net, "d_model/fully_connected", proj, 1, ACT_NONE)]
+        elif d_type == "dnn":
+            # models/discriminator_dnn.py:23-24,61-93: 1024 x (1+3) ReLU -> 1, clip_by_value(-0.5, 1.5)
+            # (the clip and its gradient mask are applied by rsr_lsgan_mse_losses, clip=1)
+            L = 3 if layers is None else layers
+
+            def mk(net):
+                dims = [in_dim] + [units] * (L + 1)
+                ls = [FC(net, "d_model/fully_connected" + ("" if i == 0 else "_%d" % i), dims[i], dims[i + 1],
+                         ACT_RELU) for i in range(L + 1)]
+                return ls + [FC(net, "d_model/fully_connected_%d" % (L + 1), units, 1, ACT_NONE)]
+        else:
+            raise ValueError("Unrecognized D type {}".format(d_type))
+        super(Discriminator, self).__init__(handle, mk, adam=False)
+        self.clip = d_type == "dnn"
+        self._ctx = {}
+
+    def fwd(self, ctx, x32_tm, B, T, lengths, noise=None, train=True):
+        """x32_tm fp32 [T*B, ld] time-major (labels or generator output); noise fp32 (B, in_dim) or None
+        (utils/ops.py:19-30: ONE draw per utterance broadcast over time).  Returns logits32 [T*B, 8]
+        (column 0; pre-clip for the DNN discriminator)."""
+        h, ws, rows = self.h, self.ws, T * B
+        ip = packing.round_up(self.in_dim, 8)
+        x16 = ws.get((ctx, "x16", B), rows, ip, h.h16)
+        h.stage_input(x32_tm, B, T, self.in_dim, out16=x16, noise=noise, time_major_in=True)
+        acts = [x16]
+        a = x16
+        if self.d_type == "lstm":
+            for l in self.layers[:-1]:
+                seq, _ = l.fwd(ctx, a, B, T, lengths, save=train)
+                a = seq[B:]
+                acts.append(a)
+        else:
+            for l in self.layers[:-1]:
+                a, _ = l.fwd(ctx, a, rows)
+                acts.append(a)
+        _, logits = self.layers[-1].fwd(ctx, a, rows, want16=False, want32=True)
+        self._ctx[ctx] = (acts, B, T, lengths)
+        return logits
+
+    def bwd(self, ctx, dlogit16, want_dw=True, want_dx=False, resid32=None):
+        """dlogit16 [T*B, 8] (column 0).  want_dx: returns d/d(input) (+ resid32) as 16-bit [T*B, in_pad]."""
+        acts, B, T, lengths = self._ctx[ctx]
+        rows, Ls = T * B, self.layers
+        if self.d_type == "lstm":
+            d16, d32 = Ls[-1].bwd(ctx, acts[-1], dlogit16, rows, want_dw=want_dw, want32=want_dw)
+            for i in range(len(Ls) - 2, -1, -1):
+                last = i == 0
+                d16, d32 = Ls[i].bwd(ctx, acts[i], d16, d32, B, T, lengths, want_dw=want_dw,
+                                     want_dx=(not last) or want_dx, resid32=resid32 if last else None,
+                                     want32=want_dw and not last)
+            return d16
+        d = dlogit16
+        for i in range(len(Ls) - 1, -1, -1):
+            last = i == 0
+            d, _ = Ls[i].bwd(ctx, acts[i], d, rows, want_dw=want_dw, want_dx=(not last) or want_dx,
+                             prev_y16=None if last else acts[i], prev_act=ACT_RELU,
+                             resid32=resid32 if last else None)
+        return d

@@ -40,7 +40,33 @@ class Handle(object):
         check(self.lib.rsr_create(C.byref(h), device, self.dtype_id), "rsr_create")
         self.h = h
         self.num_sms = self.lib.rsr_num_sms(self.h)
-        self.launches = 0          # number of library calls that launch >= 1 kernel (bench accounting)
+        self.launches = 0          # kernels of librsrgan_sm100.so launched so far (bench accounting)
+        self.timing = None         # list of (name, start event, end event) while profiling, else None
+
+    def _call(self, name, n_kernels, *args):
+        """One C-ABI call on torch's current stream.  With `self.timing` set (bench.py's kernel-share
+        pass) the call is bracketed by CUDA events on that stream; elapsed times are read by
+        `timing_summary()` after a synchronize."""
+        fn = getattr(self.lib, name)
+        if self.timing is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            self.timing.append((name, e0, e1))
+        else:
+            rc = fn(*args)
+        check(rc, name)
+        self.launches += n_kernels
+
+    def timing_summary(self):
+        """{call name: (count, total ms)} of the calls recorded since `self.timing = []`."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.timing or []:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + e0.elapsed_time(e1))
+        return out
 
     def close(self):
         if getattr(self, "h", None):
@@ -71,85 +97,75 @@ class Handle(object):
     # --------------------------------------------------------------- staging
     def stage_input(self, x, B, T, D, out16=None, out32=None, mean=None, istd=None, noise=None,
                     time_major_in=False, ldx=None):
-        check(self.lib.rsr_stage_input(
+        self._call("rsr_stage_input", 1, 
             self.h, _stream(), _p(x), ldx if ldx is not None else (x.stride(0) if time_major_in else D),
             int(time_major_in), B, T, D, _p(mean), _p(istd), _p(noise),
             _p(out16), out16.stride(0) if out16 is not None else 0,
-            _p(out32), out32.stride(0) if out32 is not None else 0), "rsr_stage_input")
-        self.launches += 1
+            _p(out32), out32.stride(0) if out32 is not None else 0)
 
     def unstage_output(self, y_tm, B, T, D, out_bm, mean=None, std=None):
-        check(self.lib.rsr_unstage_output(self.h, _stream(), _p(y_tm), y_tm.stride(0), B, T, D,
-                                          _p(mean), _p(std), _p(out_bm)), "rsr_unstage_output")
-        self.launches += 1
+        self._call("rsr_unstage_output", 1, self.h, _stream(), _p(y_tm), y_tm.stride(0), B, T, D,
+                                          _p(mean), _p(std), _p(out_bm))
 
     def cmvn_apply(self, x, mean, std, out):
         n, d = x.shape
-        check(self.lib.rsr_cmvn_apply(self.h, _stream(), _p(x), _p(mean), _p(std), n, d, _p(out)), "rsr_cmvn_apply")
-        self.launches += 1
+        self._call("rsr_cmvn_apply", 1, self.h, _stream(), _p(x), _p(mean), _p(std), n, d, _p(out))
 
     def cmvn_invert(self, y, mean, std, out):
         n, d = y.shape
-        check(self.lib.rsr_cmvn_invert(self.h, _stream(), _p(y), _p(mean), _p(std), n, d, _p(out)), "rsr_cmvn_invert")
-        self.launches += 1
+        self._call("rsr_cmvn_invert", 1, self.h, _stream(), _p(y), _p(mean), _p(std), n, d, _p(out))
 
     # ----------------------------------------------------------------- LSTMP
     def lstmp_rec_fwd(self, B, T, Cp, zx, wcT, w_i, w_f, w_o, lengths, mt_seq, save, forget_bias=1.0):
-        check(self.lib.rsr_lstmp_rec_fwd(self.h, _stream(), B, T, Cp, _p(zx), _p(wcT), _p(w_i), _p(w_f),
-                                         _p(w_o), forget_bias, _p(lengths), _p(mt_seq), _p(save)),
-              "rsr_lstmp_rec_fwd")
-        self.launches += 1
+        self._call("rsr_lstmp_rec_fwd", 1, self.h, _stream(), B, T, Cp, _p(zx), _p(wcT), _p(w_i), _p(w_f),
+                                         _p(w_o), forget_bias, _p(lengths), _p(mt_seq), _p(save))
 
     def lstmp_rec_bwd(self, B, T, Cp, dmt, wc, w_i, w_f, w_o, lengths, save, dz16, dbias, dw_i, dw_f, dw_o):
-        check(self.lib.rsr_lstmp_rec_bwd(self.h, _stream(), B, T, Cp, _p(dmt), _p(wc), _p(w_i), _p(w_f),
+        self._call("rsr_lstmp_rec_bwd", 1, self.h, _stream(), B, T, Cp, _p(dmt), _p(wc), _p(w_i), _p(w_f),
                                          _p(w_o), _p(lengths), _p(save), _p(dz16), _p(dbias), _p(dw_i),
-                                         _p(dw_f), _p(dw_o)), "rsr_lstmp_rec_bwd")
-        self.launches += 1
+                                         _p(dw_f), _p(dw_o))
 
     # ---------------------------------------------------------------- losses
     def lsgan_mse_losses(self, losses, rl=None, fk=None, ld_logit=1, n_logit=0, clip=False, g=None, y=None,
                          n_frames=0, d_out=0, d_real=1.0, d_fake=0.0, lam=0.0, gscale=1.0,
                          d_rl_grad=None, d_fk_grad=None, g_adv_grad=None, ld_grad=1, dg_mse=None):
-        check(self.lib.rsr_lsgan_mse_losses(
+        self._call("rsr_lsgan_mse_losses", 1, 
             self.h, _stream(), _p(rl), _p(fk), ld_logit, n_logit, int(clip),
             _p(g), g.stride(0) if g is not None else 0, _p(y), y.stride(0) if y is not None else 0,
             n_frames, d_out, d_real, d_fake, lam, gscale, _p(losses), _p(d_rl_grad), _p(d_fk_grad),
-            _p(g_adv_grad), ld_grad, _p(dg_mse), dg_mse.stride(0) if dg_mse is not None else 0),
-            "rsr_lsgan_mse_losses")
-        self.launches += 1
+            _p(g_adv_grad), ld_grad, _p(dg_mse), dg_mse.stride(0) if dg_mse is not None else 0)
 
     def colsum16(self, x16, M, N, out, accumulate=False, ld=None):
-        check(self.lib.rsr_colsum16(self.h, _stream(), _p(x16), ld if ld is not None else x16.stride(0),
-                                    M, N, _p(out), int(accumulate)), "rsr_colsum16")
-        self.launches += 1
+        self._call("rsr_colsum16", 1, self.h, _stream(), _p(x16), ld if ld is not None else x16.stride(0),
+                                    M, N, _p(out), int(accumulate))
 
     def colsum32(self, x32, M, N, out, accumulate=False, ld=None):
-        check(self.lib.rsr_colsum32(self.h, _stream(), _p(x32), ld if ld is not None else x32.stride(0),
-                                    M, N, _p(out), int(accumulate)), "rsr_colsum32")
-        self.launches += 1
+        self._call("rsr_colsum32", 1, self.h, _stream(), _p(x32), ld if ld is not None else x32.stride(0),
+                                    M, N, _p(out), int(accumulate))
 
     # ---------------------------------------------------------------- update
     def seg_sumsq(self, grad, gmul, seg_id, n_seg, sumsq):
-        check(self.lib.rsr_seg_sumsq(self.h, _stream(), _p(grad), gmul, _p(seg_id), grad.numel(), n_seg,
-                                     _p(sumsq)), "rsr_seg_sumsq")
-        self.launches += 1
+        self._call("rsr_seg_sumsq", 1, self.h, _stream(), _p(grad), gmul, _p(seg_id), grad.numel(), n_seg,
+                                     _p(sumsq))
 
     def clip_sgd_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, ema, theta16):
-        check(self.lib.rsr_clip_sgd_ema(self.h, _stream(), _p(grad), gmul, _p(seg_id), _p(sumsq), max_norm,
-                                        _p(hyper), ema_decay, theta.numel(), _p(theta), _p(ema), _p(theta16)),
-              "rsr_clip_sgd_ema")
-        self.launches += 1
+        self._call("rsr_clip_sgd_ema", 1, self.h, _stream(), _p(grad), gmul, _p(seg_id), _p(sumsq), max_norm,
+                                        _p(hyper), ema_decay, theta.numel(), _p(theta), _p(ema), _p(theta16))
 
     def clip_adam_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, m, v, ema, theta16):
-        check(self.lib.rsr_clip_adam_ema(self.h, _stream(), _p(grad), gmul, _p(seg_id), _p(sumsq), max_norm,
+        self._call("rsr_clip_adam_ema", 3, self.h, _stream(), _p(grad), gmul, _p(seg_id), _p(sumsq), max_norm,
                                          _p(hyper), ema_decay, theta.numel(), _p(theta), _p(m), _p(v), _p(ema),
-                                         _p(theta16)), "rsr_clip_adam_ema")
-        self.launches += 1
+                                         _p(theta16))
+
+    def l2_grad(self, grad, theta, seg_id, seg_flag, scale):
+        self._call("rsr_l2_grad", 1, self.h, _stream(), _p(grad), _p(theta), _p(seg_id), _p(seg_flag), scale,
+                                   grad.numel())
+
+    def add_cast(self, a, b, n, out32=None, out16=None):
+        self._call("rsr_add_cast", 1, self.h, _stream(), _p(a), _p(b), n, _p(out32), _p(out16))
 
     def cast16(self, x, out16):
-        check(self.lib.rsr_cast16(self.h, _stream(), _p(x), x.numel(), _p(out16)), "rsr_cast16")
-        self.launches += 1
+        self._call("rsr_cast16", 1, self.h, _stream(), _p(x), x.numel(), _p(out16))
 
     def fill32(self, x, v):
-        check(self.lib.rsr_fill32(self.h, _stream(), _p(x), x.numel(), v), "rsr_fill32")
-        self.launches += 1
+        self._call("rsr_fill32", 1, self.h, _stream(), _p(x), x.numel(), v)

@@ -1,0 +1,171 @@
+"""Flat parameter storage of one network (generator or discriminator).
+
+Every TF-1.4 variable of the reference (names in SURVEY.md App. B) is one *segment* of a
+flat fp32 device buffer, stored in the layout the kernels consume (zero-padded, LSTM gate
+columns packed -- see packing.py) and padded to a multiple of 1024 elements so that the
+fused update sweep (rsr_seg_sumsq / rsr_clip_*_ema) handles whole blocks of one tensor.
+Five parallel buffers share the segment table: theta, grad, ema (tf.train.ExponentialMovingAverage
+shadows, models/gan_rnn_placeholder.py:149-150), Adam m / v (models/gan_rnn_placeholder.py:147)
+and theta16, the 16-bit operand copy the tensor cores read, which the update kernel refreshes.
+
+Padding invariant: padded elements are exactly zero in theta and receive exactly zero
+gradients (padded activations are zero), so they stay zero under SGD and Adam.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import packing
+
+BLOCK = 1024
+
+
+class Seg(object):
+    __slots__ = ("name", "kind", "tf_shape", "dev_shape", "off", "size", "meta", "index")
+
+    def __init__(self, name, kind, tf_shape, dev_shape, meta=None):
+        self.name, self.kind, self.tf_shape, self.dev_shape = name, kind, tuple(tf_shape), tuple(dev_shape)
+        self.meta = meta or {}
+        self.off = self.size = self.index = 0
+
+
+def fc_w(name, n_in, n_out):
+    return Seg(name, "fc_w", (n_in, n_out), (packing.round_up(n_in, 8), packing.round_up(n_out, 8)))
+
+
+def fc_b(name, n_out):
+    return Seg(name, "vec", (n_out,), (packing.round_up(n_out, 8),))
+
+
+def lstm_cell(prefix, I, C, P):
+    """The six variables of one tf.contrib.rnn.LSTMCell(use_peepholes, num_proj) in TF creation order."""
+    Ip, Pp, Cp = packing.round_up(I, 8), packing.round_up(P, 8), packing.cell_pad(C)
+    meta = dict(I=I, C=C, P=P, Ip=Ip, Pp=Pp, Cp=Cp)
+    return [
+        Seg(prefix + "kernel", "lstm_kernel", (I + P, 4 * C), (Ip + Pp, 4 * Cp), meta),
+        Seg(prefix + "bias", "lstm_bias", (4 * C,), (4 * Cp,), meta),
+        Seg(prefix + "w_f_diag", "peep", (C,), (Cp,), meta),
+        Seg(prefix + "w_i_diag", "peep", (C,), (Cp,), meta),
+        Seg(prefix + "w_o_diag", "peep", (C,), (Cp,), meta),
+        Seg(prefix + "projection/kernel", "proj", (C, P), (Cp, Pp), meta),
+    ]
+
+
+def to_dev_layout(seg, a):
+    """numpy array in TF layout -> numpy array in device layout (zero padded / gate packed)."""
+    a = np.asarray(a)
+    assert a.shape == seg.tf_shape, (seg.name, a.shape, seg.tf_shape)
+    out = np.zeros(seg.dev_shape, dtype=np.float32)
+    if seg.kind == "fc_w":
+        out[:a.shape[0], :a.shape[1]] = a
+    elif seg.kind in ("vec", "peep"):
+        out[:a.shape[0]] = a
+    elif seg.kind == "lstm_bias":
+        out[:] = packing.pack_cols(a, seg.meta["C"])
+    elif seg.kind == "proj":
+        out[:a.shape[0], :a.shape[1]] = a
+    elif seg.kind == "lstm_kernel":
+        m = seg.meta
+        p = packing.pack_cols(a, m["C"])
+        out[:m["I"]] = p[:m["I"]]
+        out[m["Ip"]:m["Ip"] + m["P"]] = p[m["I"]:]
+    else:
+        raise ValueError(seg.kind)
+    return out
+
+
+def from_dev_layout(seg, d):
+    d = np.asarray(d).reshape(seg.dev_shape)
+    if seg.kind == "fc_w":
+        return d[:seg.tf_shape[0], :seg.tf_shape[1]].copy()
+    if seg.kind in ("vec", "peep"):
+        return d[:seg.tf_shape[0]].copy()
+    if seg.kind == "lstm_bias":
+        return packing.unpack_cols(d, seg.meta["C"])
+    if seg.kind == "proj":
+        return d[:seg.tf_shape[0], :seg.tf_shape[1]].copy()
+    if seg.kind == "lstm_kernel":
+        m = seg.meta
+        u = packing.unpack_cols(d, m["C"])
+        return np.concatenate([u[:m["I"]], u[m["Ip"]:m["Ip"] + m["P"]]], 0)
+    raise ValueError(seg.kind)
+
+
+class ParamStore(object):
+    def __init__(self, handle, segs, adam):
+        self.h = handle
+        self.segs = OrderedDict()
+        off = 0
+        for i, s in enumerate(segs):
+            n = int(np.prod(s.dev_shape))
+            s.off, s.size, s.index = off, packing.round_up(n, BLOCK), i
+            off += s.size
+            assert s.name not in self.segs, s.name
+            self.segs[s.name] = s
+        self.n = off
+        dev = handle.device
+        z = lambda: torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.theta, self.grad, self.ema = z(), z(), z()
+        self.m, self.v = (z(), z()) if adam else (None, None)
+        self.theta16 = torch.zeros(self.n, dtype=handle.h16, device=dev)
+        seg_id = np.concatenate([np.full(s.size // BLOCK, s.index, np.int32) for s in self.segs.values()])
+        self.seg_id = torch.tensor(seg_id, device=dev)
+        # L2 regulariser covers variables whose name does not contain "bias" (gan_rnn_placeholder.py:254)
+        self.seg_l2 = torch.tensor(np.array([0 if "bias" in s.name else 1 for s in self.segs.values()], np.int32),
+                                   device=dev)
+        self.sumsq = torch.zeros(len(self.segs), dtype=torch.float32, device=dev)
+        # device-resident hyper-parameters, see rsr_clip_adam_ema in include/rsrgan_b200.h
+        self.hyper = torch.tensor([0.0, 0.9, 0.999, 1e-8, 0.9, 0.999, 0.0, 0.0], dtype=torch.float32, device=dev)
+        self.adam = adam
+
+    # -- views ---------------------------------------------------------------------------
+    def view(self, name, buf="theta"):
+        s = self.segs[name]
+        n = int(np.prod(s.dev_shape))
+        return getattr(self, buf)[s.off:s.off + n].view(*s.dev_shape)
+
+    def n_params(self):
+        return sum(int(np.prod(s.tf_shape)) for s in self.segs.values())
+
+    # -- host <-> device -----------------------------------------------------------------
+    def load_tf(self, params, buf="theta"):
+        """params: dict TF-variable-name -> numpy array in TF layout."""
+        flat = np.zeros(self.n, np.float32)
+        for s in self.segs.values():
+            d = to_dev_layout(s, params[s.name])
+            flat[s.off:s.off + d.size] = d.reshape(-1)
+        t = torch.from_numpy(flat).to(self.h.device)
+        getattr(self, buf).copy_(t)
+        if buf == "theta":
+            self.refresh16()
+
+    def export_tf(self, buf="theta", dtype=np.float32):
+        flat = getattr(self, buf).detach().float().cpu().numpy()
+        out = OrderedDict()
+        for s in self.segs.values():
+            n = int(np.prod(s.dev_shape))
+            out[s.name] = from_dev_layout(s, flat[s.off:s.off + n]).astype(dtype)
+        return out
+
+    def refresh16(self):
+        self.h.cast16(self.theta, self.theta16)
+
+    def set_lr(self, lr):
+        self.hyper[0:1].fill_(float(lr))
+
+    def state_dict(self):
+        d = OrderedDict()
+        for buf in ("theta", "ema", "m", "v"):
+            if getattr(self, buf) is not None:
+                d[buf] = self.export_tf(buf)
+        d["hyper"] = self.hyper.cpu().numpy()
+        return d
+
+    def load_state_dict(self, d):
+        for buf in ("theta", "ema", "m", "v"):
+            if buf in d and getattr(self, buf) is not None:
+                self.load_tf(d[buf], buf)
+        self.hyper.copy_(torch.tensor(np.asarray(d["hyper"], np.float32)))

@@ -1,0 +1,249 @@
+"""TEST DOUBLE of rsrgan_b200.ops.Handle: emulates every C-ABI call with torch CPU ops so that the
+HOST logic (network wiring, parameter packing, update schedule, data-parallel all-reduce over gloo,
+trainer / CLI) can be exercised by the `-m "not gpu"` suite in a container without a GPU.
+
+It lives under tests/ and is injected through GAN_RNN(handle=...).  Nothing under rsrgan_b200/
+imports it: the product path only ever talks to librsrgan_sm100.so and fails loudly without it.
+The emulation follows the contracts written in include/rsrgan_b200.h (operand major-ness, packed
+gate columns, time-major rows, loss scaling), not the CUDA code.
+"""
+from __future__ import annotations
+
+import torch
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_CLIP = 0, 1, 2, 3
+
+
+def _act(v, act):
+    if act == ACT_RELU:
+        return torch.clamp_min(v, 0.0)
+    if act == ACT_LRELU:
+        return torch.maximum(v, 0.3 * v)
+    if act == ACT_CLIP:
+        return torch.clamp(v, -0.5, 1.5)
+    return v
+
+
+def _dact(y, act):
+    if act == ACT_RELU:
+        return (y > 0).to(torch.float32)
+    if act == ACT_LRELU:
+        return torch.where(y > 0, torch.ones_like(y), torch.full_like(y, 0.3))
+    return torch.ones_like(y)
+
+
+class FakeHandle(object):
+    def __init__(self, dtype="f16"):
+        self.dtype_id = {"f16": 0, "bf16": 1}[dtype]
+        self.h16 = torch.float16 if self.dtype_id == 0 else torch.bfloat16
+        self.device = torch.device("cpu")
+        self.num_sms = 148
+        self.launches = 0
+
+    def close(self):
+        pass
+
+    # ------------------------------------------------------------------ GEMM
+    def gemm(self, A, B, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, bias=None, resid=None,
+             act=ACT_NONE, dact_src=None, dact=ACT_NONE, out32=None, out16=None, tile_n=0, lda=None, ldb=None):
+        self.launches += 1
+        Ae = (A[:K, :M].t() if a_mn else A[:M, :K]).float()
+        Be = (B[:K, :N] if b_mn else B[:N, :K].t()).float()
+        v = alpha * (Ae @ Be)
+        if bias is not None:
+            v = v + bias[:N]
+        if resid is not None:
+            v = v + resid[:M, :N]
+        v = _act(v, act)
+        if dact_src is not None:
+            v = v * _dact(dact_src[:M, :N].float(), dact)
+        if out16 is not None:
+            out16[:M, :N] = v.to(self.h16)
+        if out32 is not None:
+            out32[:M, :N] = v + (beta * out32[:M, :N] if beta != 0.0 else 0.0)
+
+    # --------------------------------------------------------------- staging
+    def stage_input(self, x, B, T, D, out16=None, out32=None, mean=None, istd=None, noise=None,
+                    time_major_in=False, ldx=None):
+        self.launches += 1
+        if time_major_in:
+            v = x[:T * B, :D].float().reshape(T, B, D)
+        else:
+            v = x.reshape(B, T, -1)[:, :, :D].float().permute(1, 0, 2)
+        if mean is not None:
+            v = (v - mean) * istd
+        if noise is not None:
+            v = v + noise.reshape(1, B, D)
+        v = v.reshape(T * B, D)
+        if out16 is not None:
+            out16[:, :D] = v.to(self.h16)
+        if out32 is not None:
+            out32[:, :D] = v
+
+    def unstage_output(self, y_tm, B, T, D, out_bm, mean=None, std=None):
+        self.launches += 1
+        v = y_tm[:T * B, :D].reshape(T, B, D).permute(1, 0, 2)
+        if mean is not None:
+            v = v * std + mean
+        out_bm.copy_(v)
+
+    def cmvn_apply(self, x, mean, std, out):
+        self.launches += 1
+        out.copy_((x - mean) / std)
+
+    def cmvn_invert(self, y, mean, std, out):
+        self.launches += 1
+        out.copy_(y * std + mean)
+
+    # ----------------------------------------------------------------- LSTMP
+    @staticmethod
+    def _gates(z, Cp):
+        """packed [.., 4Cp] -> [.., 4, Cp]  (col = (cell/32)*128 + gate*32 + cell%32)"""
+        s = z.shape[:-1]
+        return z.reshape(*s, Cp // 32, 4, 32).transpose(-3, -2).reshape(*s, 4, Cp)
+
+    @staticmethod
+    def _pack(g, Cp):
+        s = g.shape[:-2]
+        return g.reshape(*s, 4, Cp // 32, 32).transpose(-3, -2).reshape(*s, 4 * Cp)
+
+    def lstmp_rec_fwd(self, B, T, Cp, zx, wcT, w_i, w_f, w_o, lengths, mt_seq, save, forget_bias=1.0):
+        self.launches += 1
+        c = torch.zeros(B, Cp)
+        W = wcT.float().t()                                  # [Cp, 4Cp] packed columns
+        for t in range(T):
+            mprev = mt_seq[t * B:(t + 1) * B].float()
+            z = self._gates(zx[t * B:(t + 1) * B] + mprev @ W, Cp)
+            ig = torch.sigmoid(z[:, 0] + w_i * c)
+            fg = torch.sigmoid(z[:, 2] + forget_bias + w_f * c)
+            jg = torch.tanh(z[:, 1])
+            cn = fg * c + ig * jg
+            og = torch.sigmoid(z[:, 3] + w_o * cn)
+            mt = og * torch.tanh(cn)
+            act = (t < lengths).reshape(B, 1)
+            if save is not None:
+                save[t * B:(t + 1) * B] = torch.cat([ig, fg, og, jg, cn], 1)
+            mt_seq[(t + 1) * B:(t + 2) * B] = torch.where(act, mt, torch.zeros_like(mt)).to(self.h16)
+            c = torch.where(act, cn, c)
+
+    def lstmp_rec_bwd(self, B, T, Cp, dmt, wc, w_i, w_f, w_o, lengths, save, dz16, dbias, dw_i, dw_f, dw_o):
+        self.launches += 1
+        W = wc.float()                                       # [Cp, 4Cp]
+        dcar = torch.zeros(B, Cp)
+        for t in range(T - 1, -1, -1):
+            sv = save[t * B:(t + 1) * B].reshape(B, 5, Cp)
+            ig, fg, og, jg, cn = (sv[:, k] for k in range(5))
+            cp = save[(t - 1) * B:t * B].reshape(B, 5, Cp)[:, 4] if t > 0 else torch.zeros(B, Cp)
+            a = (t < lengths).reshape(B, 1).float()
+            dm = dmt[t * B:(t + 1) * B]
+            tc = torch.tanh(cn)
+            dzo = dm * tc * og * (1 - og)
+            dc = dcar + dm * og * (1 - tc * tc) + dzo * w_o
+            dzf = dc * cp * fg * (1 - fg)
+            dzi = dc * jg * ig * (1 - ig)
+            dzj = dc * ig * (1 - jg * jg)
+            dzi, dzj, dzf, dzo = dzi * a, dzj * a, dzf * a, dzo * a
+            dcar = (dc * fg + dzf * w_f + dzi * w_i) * a
+            dw_o += (dzo * cn).sum(0)
+            dw_f += (dzf * cp).sum(0)
+            dw_i += (dzi * cp).sum(0)
+            dz = self._pack(torch.stack([dzi, dzj, dzf, dzo], 1), Cp)
+            dbias += dz.sum(0)
+            dzh = dz.to(self.h16)
+            dz16[t * B:(t + 1) * B] = dzh
+            if t > 0:
+                dmt[(t - 1) * B:t * B] += dzh.float() @ W.t()
+
+    # ---------------------------------------------------------------- losses
+    def lsgan_mse_losses(self, losses, rl=None, fk=None, ld_logit=1, n_logit=0, clip=False, g=None, y=None,
+                         n_frames=0, d_out=0, d_real=1.0, d_fake=0.0, lam=0.0, gscale=1.0,
+                         d_rl_grad=None, d_fk_grad=None, g_adv_grad=None, ld_grad=1, dg_mse=None):
+        self.launches += 1
+
+        def prep(u):
+            u = u[:n_logit, 0]
+            if clip:
+                return torch.clamp(u, -0.5, 1.5), ((u >= -0.5) & (u <= 1.5)).float()
+            return u, torch.ones_like(u)
+
+        if rl is not None:
+            l, m = prep(rl)
+            losses[0] += ((l - d_real) ** 2).mean()
+            if d_rl_grad is not None:
+                d_rl_grad[:n_logit, 0] = (gscale * 2 * (l - d_real) / n_logit * m).to(self.h16)
+        if fk is not None:
+            l, m = prep(fk)
+            losses[1] += ((l - d_fake) ** 2).mean()
+            losses[2] += ((l - d_real) ** 2).mean()
+            if d_fk_grad is not None:
+                d_fk_grad[:n_logit, 0] = (gscale * 2 * (l - d_fake) / n_logit * m).to(self.h16)
+            if g_adv_grad is not None:
+                g_adv_grad[:n_logit, 0] = (gscale * 2 * (l - d_real) / n_logit * m).to(self.h16)
+        if g is not None:
+            e = g[:n_frames, :d_out] - y[:n_frames, :d_out]
+            losses[3] += 0.5 * d_out * (e ** 2).mean()
+            if dg_mse is not None:
+                dg_mse[:n_frames, :d_out] = gscale * lam * e / n_frames
+
+    def colsum16(self, x16, M, N, out, accumulate=False, ld=None):
+        self.launches += 1
+        s = x16[:M, :N].float().sum(0)
+        out[:N] = out[:N] + s if accumulate else s
+
+    colsum32 = colsum16
+
+    # ---------------------------------------------------------------- update
+    def seg_sumsq(self, grad, gmul, seg_id, n_seg, sumsq):
+        self.launches += 1
+        b = ((grad * gmul) ** 2).reshape(-1, 1024).sum(1)
+        sumsq.zero_()
+        sumsq.index_add_(0, seg_id.long(), b)
+
+    def _clipped(self, grad, gmul, seg_id, sumsq, max_norm):
+        nrm = torch.sqrt(sumsq)[seg_id.long()]
+        sc = gmul * (max_norm / torch.clamp_min(nrm, max_norm))
+        return (grad.reshape(-1, 1024) * sc[:, None]).reshape(-1)
+
+    def clip_sgd_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, ema, theta16):
+        self.launches += 1
+        theta -= hyper[0] * self._clipped(grad, gmul, seg_id, sumsq, max_norm)
+        if ema is not None:
+            ema -= (1 - ema_decay) * (ema - theta)
+        if theta16 is not None:
+            theta16.copy_(theta.to(self.h16))
+
+    def clip_adam_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, m, v, ema, theta16):
+        self.launches += 1
+        g = self._clipped(grad, gmul, seg_id, sumsq, max_norm)
+        lr, b1, b2, eps, b1p, b2p = (float(hyper[i]) for i in range(6))
+        lr_t = lr * (1 - b2p) ** 0.5 / (1 - b1p)
+        m.mul_(b1).add_((1 - b1) * g)
+        v.mul_(b2).add_((1 - b2) * g * g)
+        theta -= lr_t * m / (torch.sqrt(v) + eps)
+        hyper[4] *= b1
+        hyper[5] *= b2
+        if ema is not None:
+            ema -= (1 - ema_decay) * (ema - theta)
+        if theta16 is not None:
+            theta16.copy_(theta.to(self.h16))
+
+    def l2_grad(self, grad, theta, seg_id, seg_flag, scale):
+        self.launches += 1
+        f = seg_flag[seg_id.long()].float()
+        grad += (theta.reshape(-1, 1024) * (scale * f)[:, None]).reshape(-1)
+
+    def add_cast(self, a, b, n, out32=None, out16=None):
+        self.launches += 1
+        v = a.reshape(-1)[:n] + b.reshape(-1)[:n]
+        if out32 is not None:
+            out32.reshape(-1)[:n] = v
+        if out16 is not None:
+            out16.reshape(-1)[:n] = v.to(self.h16)
+
+    def cast16(self, x, out16):
+        self.launches += 1
+        out16.copy_(x.to(self.h16))
+
+    def fill32(self, x, v):
+        self.launches += 1
+        x.fill_(v)
