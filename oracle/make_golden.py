@@ -1,0 +1,94 @@
+"""Writes tests/golden/gan_*.npz: seeded inputs + weights of small GANs and what the float64 oracle
+(oracle/rsr_oracle.py) computes for them -- generator output, the seven losses, raw D / G
+gradients and the generator output after one batch schedule (1 D + 2 G updates).
+
+PARITY UNPINNED (see rsr_oracle.py header): the reference's TF-1.4 graph cannot be executed here,
+so these vectors pin the *oracle*; they are cross-checked by the independent torch-autograd
+statement (oracle/torch_ref.py) in tests/test_oracle.py.
+
+    python -m oracle.make_golden
+"""
+from __future__ import annotations
+
+import os
+from collections import OrderedDict
+
+import numpy as np
+
+from . import rsr_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+CASES = {
+    # name: (g_type, d_type, sizes, B, T)
+    "gan_lstm_dlstm": ("lstm", "lstm", dict(g_cell=64, g_proj=32, g_layers=2, d_cell=32), 3, 7),
+    "gan_res_ddnn": ("res_lstm_l", "dnn", dict(g_cell=40, g_layers=2, d_units=64), 2, 5),
+}
+
+
+def build(name):
+    g_type, d_type, sz, B, T = CASES[name]
+    rng = np.random.default_rng(sum(map(ord, name)))
+    if g_type == "lstm":
+        gp = O.init_g_lstm(rng, cell=sz["g_cell"], proj=sz["g_proj"], layers=sz["g_layers"])
+    else:
+        gp = O.init_g_res_lstm_l(rng, cell=sz["g_cell"], layers=sz["g_layers"])
+    dp = O.init_d_lstm(rng, cell=sz["d_cell"]) if d_type == "lstm" else O.init_d_dnn(rng, units=sz["d_units"])
+    # non-zero biases so that they are exercised
+    for p in (gp, dp):
+        for k in p:
+            if "bias" in k:
+                p[k] = rng.standard_normal(p[k].shape) * 0.1
+    x = rng.standard_normal((B, T, 257))
+    y = rng.standard_normal((B, T, 40))
+    lengths = rng.integers(max(T // 2, 1), T + 1, size=B)
+    lengths[0] = T
+    n_rl = rng.standard_normal((B, 1, 40)) * 0.05 if d_type == "lstm" else None
+    n_fk = rng.standard_normal((B, 1, 40)) * 0.05 if d_type == "lstm" else None
+    return g_type, d_type, sz, gp, dp, x, y, lengths, n_rl, n_fk
+
+
+def compute(name):
+    g_type, d_type, sz, gp, dp, x, y, lengths, n_rl, n_fk = build(name)
+    st = O.GanState(OrderedDict(gp), OrderedDict(dp), g_type, d_type)
+    out = OrderedDict(x=x.astype(np.float32), y=y.astype(np.float32), lengths=lengths.astype(np.int32))
+    if n_rl is not None:
+        out["noise_rl"], out["noise_fk"] = n_rl.astype(np.float32), n_fk.astype(np.float32)
+    for k, v in gp.items():
+        out["G/" + k] = v.astype(np.float32)
+    for k, v in dp.items():
+        out["D/" + k] = v.astype(np.float32)
+    # the oracle runs on the float32-rounded inputs/weights the device will also see
+    st.g = OrderedDict((k, out["G/" + k].astype(np.float64)) for k in gp)
+    st.d = OrderedDict((k, out["D/" + k].astype(np.float64)) for k in dp)
+    x64, y64 = out["x"].astype(np.float64), out["y"].astype(np.float64)
+    nr = out["noise_rl"].astype(np.float64) if n_rl is not None else None
+    nf = out["noise_fk"].astype(np.float64) if n_fk is not None else None
+    L, dgr, g_out = O.tower_losses_and_grads(st, x64, y64, lengths, "d", nr, nf)
+    _, ggr, _ = O.tower_losses_and_grads(st, x64, y64, lengths, "g", nr, nf)
+    out["g_out"] = g_out
+    for k in ("d_rl_loss", "d_fk_loss", "d_loss", "g_adv_loss", "g_mse_loss", "g_loss"):
+        out["loss/" + k] = np.float64(L[k])
+    for k, v in dgr.items():
+        out["dgrad/" + k] = v.astype(np.float32)
+    for k, v in ggr.items():
+        out["ggrad/" + k] = v.astype(np.float32)
+    tower = dict(x=x64, y=y64, lengths=lengths, noise_rl=nr, noise_fk=nf)
+    O.d_step(st, [tower], 1e-3)
+    O.g_step(st, [tower], 8e-5)
+    O.g_step(st, [tower], 8e-5)
+    gf, _ = O.GENERATORS[g_type]
+    out["g_out_after"], _ = gf(st.g, x64, lengths)
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name in CASES:
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **compute(name))
+        print("wrote", name, os.path.getsize(os.path.join(OUT, name + ".npz")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

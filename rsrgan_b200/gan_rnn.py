@@ -264,8 +264,11 @@ class GAN_RNN(Model):
             self._pin[key] = (torch.empty(t.shape, dtype=dtype, pin_memory=True),
                               torch.empty(t.shape, dtype=dtype, device=self.h.device))
         pin, dev = self._pin[key]
-        pin.copy_(t)
-        dev.copy_(pin, non_blocking=True)
+        if t.is_pinned():                                  # caller already staged the batch in pinned memory
+            dev.copy_(t, non_blocking=True)
+        else:
+            pin.copy_(t)
+            dev.copy_(pin, non_blocking=True)
         return dev
 
     def _feed(self, inputs, labels, lengths):
@@ -330,10 +333,10 @@ class GAN_RNN(Model):
         self.h.seg_sumsq(P.theta, 1.0, P.seg_id, len(P.segs), P.sumsq)
         self._losses[4:5] = 0.5 * self.l2_scale * (P.sumsq * P.seg_l2.to(F32)).sum()
 
-    def d_step(self, inputs, labels, lengths, noise_rl=None, noise_fk=None, sync=True):
+    def d_step(self, inputs, labels, lengths, noise_rl=None, noise_fk=None, sync=True, _feed=None):
         """One discriminator update: L_D = mean((D(y)-d_real)^2) + mean((D(G(x))-d_fake)^2),
         gradients wrt theta_D only, tower mean, per-tensor clip 15, SGD(lr_d), EMA."""
-        x, y_tm, ln, B, T = self._feed(inputs, labels, lengths)
+        x, y_tm, ln, B, T = _feed if _feed is not None else self._feed(inputs, labels, lengths)
         h, G, D, rows = self.h, self.G, self.D, T * B
         gs = self._gscale(rows)
         g32 = G.fwd(x, B, T, ln, train=False)
@@ -352,10 +355,10 @@ class GAN_RNN(Model):
         self._update(D, gs, adam=False)
         return self._loss_dict(self._losses.tolist(), "d") if sync else self._losses
 
-    def g_step(self, inputs, labels, lengths, noise_fk=None, sync=True):
+    def g_step(self, inputs, labels, lengths, noise_fk=None, sync=True, _feed=None):
         """One generator update: L_G = mean((D(G(x))-d_real)^2) + lambda*0.5*40*mean((G(x)-y)^2) [+ l2],
         gradients wrt theta_G only (through D, D frozen), tower mean, clip 15, Adam(lr_g), EMA."""
-        x, y_tm, ln, B, T = self._feed(inputs, labels, lengths)
+        x, y_tm, ln, B, T = _feed if _feed is not None else self._feed(inputs, labels, lengths)
         h, G, D, rows = self.h, self.G, self.D, T * B
         gs = self._gscale(rows)
         g32 = G.fwd(x, B, T, ln, train=True)
@@ -375,6 +378,26 @@ class GAN_RNN(Model):
             h.l2_grad(G.P.grad, G.P.theta, G.P.seg_id, G.P.seg_l2, self.l2_scale * gs)
         self._update(G, gs, adam=True)
         return self._loss_dict(self._losses.tolist(), "g") if sync else self._losses
+
+    def train_batch(self, inputs, labels, lengths, sync=True):
+        """The per-batch schedule of train_one_iteration (scripts/train_gan_rnn_placeholder.py:72-101):
+        disc_updates x D update then gen_updates x G update on the SAME minibatch, which is fed to the
+        device once.  Returns the losses of the last D and the last G update."""
+        x, y_tm, ln, B, T = self._feed(inputs, labels, lengths)
+        feed = (x, y_tm, ln, B, T)
+        out = OrderedDict()
+        for _ in range(self.disc_updates):
+            d = self.d_step(None, None, None, sync=False, _feed=feed)
+        d_vals = d[:2].clone() if self.disc_updates else None
+        for _ in range(self.gen_updates):
+            g = self.g_step(None, None, None, sync=False, _feed=feed)
+        if not sync:
+            return d_vals, g
+        if d_vals is not None:
+            out.update(self._loss_dict(d_vals.tolist() + [0.0] * 3, "d"))
+        if self.gen_updates:
+            out.update(self._loss_dict(g.tolist(), "g"))
+        return out
 
     def eval_losses(self, inputs, labels, lengths, noise_rl=None, noise_fk=None, sync=True):
         """Loss-only pass of eval_one_iteration (scripts/train_gan_rnn_placeholder.py:154-172)."""

@@ -99,6 +99,12 @@ class LSTMP(object):
     def segs(self):
         return params.lstm_cell(self.prefix, self.I, self.C, self.P)
 
+    def rec_flops(self, B, T):
+        """ALGORITHMIC flops of the recurrent half per sequence: m_{t-1} K_h plus the
+        projection, 2*B*(P*4C + C*P) per step -- the unfolded reference form, not the folded
+        B x C x 4C product the kernel executes."""
+        return 2.0 * B * T * (self.P * 4 * self.C + self.C * self.P)
+
     def _w(self, buf="theta16"):
         P = self.net.P
         K = P.view(self.prefix + "kernel", buf)
@@ -125,7 +131,8 @@ class LSTMP(object):
         o32 = net.ws.get(key + ("o32",), rows, self.Pp, F32) if want32 else None
         h.gemm(x16, Kx16, rows, 4 * Cp, self.Ip, b_mn=True, bias=P.view(self.prefix + "bias"), out32=zx)
         h.lstmp_rec_fwd(B, T, Cp, zx, self.wcT16, P.view(self.prefix + "w_i_diag"),
-                        P.view(self.prefix + "w_f_diag"), P.view(self.prefix + "w_o_diag"), lengths, mt, sv)
+                        P.view(self.prefix + "w_f_diag"), P.view(self.prefix + "w_o_diag"), lengths, mt, sv,
+                        work=self.rec_flops(B, T))
         h.gemm(mt[B:], Wp16, rows, self.Pp, Cp, b_mn=True, out16=out[B:], out32=o32)
         return out, o32
 
@@ -152,7 +159,7 @@ class LSTMP(object):
             gb, gi, gf, go = s[:4 * Cp], s[4 * Cp:5 * Cp], s[5 * Cp:6 * Cp], s[6 * Cp:]
         h.lstmp_rec_bwd(B, T, Cp, dmt, self.wc16, P.view(self.prefix + "w_i_diag"),
                         P.view(self.prefix + "w_f_diag"), P.view(self.prefix + "w_o_diag"), lengths, sv,
-                        dz, gb, gi, gf, go)
+                        dz, gb, gi, gf, go, work=self.rec_flops(B, T))
         if want_dw:
             gK = P.view(self.prefix + "kernel", "grad")
             # dK = [x_t , m_{t-1}]^T dz_t  (two row blocks of the TF kernel)

@@ -43,7 +43,7 @@ class Handle(object):
         self.launches = 0          # kernels of librsrgan_sm100.so launched so far (bench accounting)
         self.timing = None         # list of (name, start event, end event) while profiling, else None
 
-    def _call(self, name, n_kernels, *args):
+    def _call(self, name, n_kernels, *args, work=0.0):
         """One C-ABI call on torch's current stream.  With `self.timing` set (bench.py's kernel-share
         pass) the call is bracketed by CUDA events on that stream; elapsed times are read by
         `timing_summary()` after a synchronize."""
@@ -53,19 +53,19 @@ class Handle(object):
             e0.record()
             rc = fn(*args)
             e1.record()
-            self.timing.append((name, e0, e1))
+            self.timing.append((name, e0, e1, work))
         else:
             rc = fn(*args)
         check(rc, name)
         self.launches += n_kernels
 
     def timing_summary(self):
-        """{call name: (count, total ms)} of the calls recorded since `self.timing = []`."""
+        """{call name: (count, total ms, total algorithmic flops)} since `self.timing = []`."""
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1 in self.timing or []:
-            c, t = out.get(name, (0, 0.0))
-            out[name] = (c + 1, t + e0.elapsed_time(e1))
+        for name, e0, e1, work in self.timing or []:
+            c, t, w = out.get(name, (0, 0.0, 0.0))
+            out[name] = (c + 1, t + e0.elapsed_time(e1), w + work)
         return out
 
     def close(self):
@@ -91,8 +91,7 @@ class Handle(object):
         a.out32, a.ldc32 = _p(out32), (out32.stride(0) if out32 is not None else 0)
         a.out16, a.ldc16 = _p(out16), (out16.stride(0) if out16 is not None else 0)
         a.tile_n = tile_n
-        check(self.lib.rsr_gemm(self.h, _stream(), C.byref(a)), "rsr_gemm")
-        self.launches += 1
+        self._call("rsr_gemm", 1, self.h, _stream(), C.byref(a), work=2.0 * M * N * K)
 
     # --------------------------------------------------------------- staging
     def stage_input(self, x, B, T, D, out16=None, out32=None, mean=None, istd=None, noise=None,
@@ -116,14 +115,15 @@ class Handle(object):
         self._call("rsr_cmvn_invert", 1, self.h, _stream(), _p(y), _p(mean), _p(std), n, d, _p(out))
 
     # ----------------------------------------------------------------- LSTMP
-    def lstmp_rec_fwd(self, B, T, Cp, zx, wcT, w_i, w_f, w_o, lengths, mt_seq, save, forget_bias=1.0):
+    def lstmp_rec_fwd(self, B, T, Cp, zx, wcT, w_i, w_f, w_o, lengths, mt_seq, save, forget_bias=1.0, work=0.0):
         self._call("rsr_lstmp_rec_fwd", 1, self.h, _stream(), B, T, Cp, _p(zx), _p(wcT), _p(w_i), _p(w_f),
-                                         _p(w_o), forget_bias, _p(lengths), _p(mt_seq), _p(save))
+                                         _p(w_o), forget_bias, _p(lengths), _p(mt_seq), _p(save), work=work)
 
-    def lstmp_rec_bwd(self, B, T, Cp, dmt, wc, w_i, w_f, w_o, lengths, save, dz16, dbias, dw_i, dw_f, dw_o):
+    def lstmp_rec_bwd(self, B, T, Cp, dmt, wc, w_i, w_f, w_o, lengths, save, dz16, dbias, dw_i, dw_f, dw_o,
+                      work=0.0):
         self._call("rsr_lstmp_rec_bwd", 1, self.h, _stream(), B, T, Cp, _p(dmt), _p(wc), _p(w_i), _p(w_f),
                                          _p(w_o), _p(lengths), _p(save), _p(dz16), _p(dbias), _p(dw_i),
-                                         _p(dw_f), _p(dw_o))
+                                         _p(dw_f), _p(dw_o), work=work)
 
     # ---------------------------------------------------------------- losses
     def lsgan_mse_losses(self, losses, rl=None, fk=None, ld_logit=1, n_logit=0, clip=False, g=None, y=None,

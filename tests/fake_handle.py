@@ -107,7 +107,7 @@ class FakeHandle(object):
         s = g.shape[:-2]
         return g.reshape(*s, 4, Cp // 32, 32).transpose(-3, -2).reshape(*s, 4 * Cp)
 
-    def lstmp_rec_fwd(self, B, T, Cp, zx, wcT, w_i, w_f, w_o, lengths, mt_seq, save, forget_bias=1.0):
+    def lstmp_rec_fwd(self, B, T, Cp, zx, wcT, w_i, w_f, w_o, lengths, mt_seq, save, forget_bias=1.0, work=0.0):
         self.launches += 1
         c = torch.zeros(B, Cp)
         W = wcT.float().t()                                  # [Cp, 4Cp] packed columns
@@ -126,7 +126,7 @@ class FakeHandle(object):
             mt_seq[(t + 1) * B:(t + 2) * B] = torch.where(act, mt, torch.zeros_like(mt)).to(self.h16)
             c = torch.where(act, cn, c)
 
-    def lstmp_rec_bwd(self, B, T, Cp, dmt, wc, w_i, w_f, w_o, lengths, save, dz16, dbias, dw_i, dw_f, dw_o):
+    def lstmp_rec_bwd(self, B, T, Cp, dmt, wc, w_i, w_f, w_o, lengths, save, dz16, dbias, dw_i, dw_f, dw_o, work=0.0):
         self.launches += 1
         W = wc.float()                                       # [Cp, 4Cp]
         dcar = torch.zeros(B, Cp)

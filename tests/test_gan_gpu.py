@@ -1,0 +1,155 @@
+"""End-to-end parity of the CUDA GAN step (GAN_RNN over librsrgan_sm100.so) with the oracle and the
+committed golden vectors, plus size-independent properties at BASELINE.json's full batch size.
+
+Tolerances (fp16 tensor-core operands, fp32 accumulate / cell state; north_star bar: generator
+output within 1e-3 RMS of the reference):
+    generator output  : absolute RMS < 1e-3  AND relative RMS < 3e-3
+    losses            : relative 2e-3
+    raw gradients     : relative RMS 5e-2 per tensor (16-bit backprop), weight deltas likewise
+"""
+import os
+from argparse import Namespace
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rsr_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def make_model(g_type, d_type, B, **kw):
+    from rsrgan_b200.gan_rnn import GAN_RNN
+    a = dict(g_type=g_type, d_type=d_type, batch_size=B, init_mse_weight=10.0, init_disc_noise_std=0.05,
+             g_learning_rate=8e-5, d_learning_rate=1e-3, l2_scale=0.0, seed=3, dtype="f16")
+    a.update(kw)
+    return GAN_RNN(None, Namespace(**a), ["/gpu:0"])
+
+
+def rms(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    d = float(np.sqrt(((a - b) ** 2).mean()))
+    return d, d / (float(np.sqrt((b ** 2).mean())) + 1e-30)
+
+
+def load_gold(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    gp = OrderedDict((k[2:], z[k]) for k in z.files if k.startswith("G/"))
+    dp = OrderedDict((k[2:], z[k]) for k in z.files if k.startswith("D/"))
+    return z, gp, dp
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("gan_lstm_dlstm", dict(g_type="lstm", d_type="lstm", g_cell=64, g_proj=32, g_layers=2, d_cell=32)),
+    ("gan_res_ddnn", dict(g_type="res_lstm_l", d_type="dnn", g_cell=40, g_layers=2, d_units=64)),
+])
+def test_golden_vectors(name, kw):
+    z, gp, dp = load_gold(name)
+    B, T = z["x"].shape[:2]
+    kw = dict(kw)
+    m = make_model(kw.pop("g_type"), kw.pop("d_type"), B, **kw)
+    m.load_params(gp, dp)
+    nz = dict(noise_rl=z["noise_rl"], noise_fk=z["noise_fk"]) if "noise_rl" in z.files else {}
+    a, r = rms(m.generate(z["x"], z["lengths"]).cpu().numpy(), z["g_out"])
+    assert a < 1e-3 and r < 3e-3, (a, r)
+    ev = m.eval_losses(z["x"], z["y"], z["lengths"], **nz)
+    for k in ("d_rl_loss", "d_fk_loss", "d_loss", "g_adv_loss", "g_mse_loss", "g_loss"):
+        assert ev[k] == pytest.approx(float(z["loss/" + k]), rel=2e-3, abs=1e-5), k
+    m.d_learning_rate, m.g_learning_rate = 0.0, 0.0
+    gs = m._gscale(B * T)
+    m.d_step(z["x"], z["y"], z["lengths"], **nz)
+    dg = m.D.P.export_tf("grad")
+    for k in dp:
+        assert rms(dg[k] / gs, z["dgrad/" + k])[1] < 5e-2, k
+    m.g_step(z["x"], z["y"], z["lengths"], noise_fk=nz.get("noise_fk"))
+    gg = m.G.P.export_tf("grad")
+    for k in gp:
+        assert rms(gg[k] / gs, z["ggrad/" + k])[1] < 5e-2, k
+    # the whole batch schedule with the reference learning rates
+    m.load_params(gp, dp)
+    m.G.P.m.zero_(); m.G.P.v.zero_(); m.G.P.hyper[4:6] = torch.tensor([0.9, 0.999], device=m.h.device)
+    m.d_learning_rate, m.g_learning_rate = 1e-3, 8e-5
+    m.d_step(z["x"], z["y"], z["lengths"], **nz)
+    m.g_step(z["x"], z["y"], z["lengths"], noise_fk=nz.get("noise_fk"))
+    m.g_step(z["x"], z["y"], z["lengths"], noise_fk=nz.get("noise_fk"))
+    a, r = rms(m.generate(z["x"], z["lengths"]).cpu().numpy(), z["g_out_after"])
+    assert a < 1e-3 and r < 5e-3, (a, r)
+
+
+@pytest.mark.parametrize("g_type,d_type,B,T", [
+    ("lstm", "lstm", 8, 30),              # reference-native sizes: models/lstm.py:43-45 + discriminator_lstm.py:26-28
+    ("res_lstm_l", "lstm", 8, 24),        # what run_gan_rnn_placeholder.sh:124 trains
+    ("res_lstm_base", "dnn", 4, 12),
+])
+def test_reference_native_sizes_against_oracle(g_type, d_type, B, T):
+    m = make_model(g_type, d_type, B)
+    rng = np.random.default_rng(B * T)
+    x, y = rng.standard_normal((B, T, 257)).astype(np.float32), rng.standard_normal((B, T, 40)).astype(np.float32)
+    lengths = rng.integers(T // 2, T + 1, size=B)
+    lengths[0] = T
+    n_rl, n_fk = (rng.standard_normal((B, 1, 40)) * 0.05).astype(np.float32), (rng.standard_normal((B, 1, 40)) * 0.05).astype(np.float32)
+    st = O.GanState(OrderedDict((k, v.astype(np.float64)) for k, v in m.G.P.export_tf().items()),
+                    OrderedDict((k, v.astype(np.float64)) for k, v in m.D.P.export_tf().items()), g_type, d_type)
+    gf, _ = O.GENERATORS[g_type]
+    g_ref, _ = gf(st.g, x.astype(np.float64), lengths)
+    a, r = rms(m.generate(x, lengths).cpu().numpy(), g_ref)
+    assert a < 1e-3 and r < 3e-3, (a, r)
+    lstm_d = d_type == "lstm"
+    tower = dict(x=x.astype(np.float64), y=y.astype(np.float64), lengths=lengths,
+                 noise_rl=n_rl.astype(np.float64) if lstm_d else None, noise_fk=n_fk.astype(np.float64) if lstm_d else None)
+    d0 = m.D.P.export_tf()
+    ours = m.d_step(x, y, lengths, noise_rl=n_rl, noise_fk=n_fk)
+    ref_losses, _ = O.d_step(st, [tower], 1e-3)
+    assert ours["d_loss"] == pytest.approx(ref_losses[0]["d_loss"], rel=2e-3)
+    d1 = m.D.P.export_tf()
+    for k in d0:
+        assert rms(d1[k] - d0[k], st.d[k] - d0[k].astype(np.float64))[1] < 5e-2, k
+    ours = m.g_step(x, y, lengths, noise_fk=n_fk)
+    ref_losses, _ = O.g_step(st, [tower], 8e-5)
+    assert ours["g_loss"] == pytest.approx(ref_losses[0]["g_loss"], rel=2e-3)
+    g_ref, _ = gf(st.g, x.astype(np.float64), lengths)
+    a, r = rms(m.generate(x, lengths).cpu().numpy(), g_ref)
+    assert a < 1e-3 and r < 5e-3, (a, r)
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE.json configs[1] (B=128 x T=100, 2xLSTMP-512/256 G + DNN D): properties that need no oracle run."""
+    B, T = 128, 100
+    m = make_model("lstm", "dnn", B, g_cell=512, g_proj=256, g_layers=2)
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal((B, T, 257)).astype(np.float32), rng.standard_normal((B, T, 40)).astype(np.float32)
+    lengths = rng.integers(T // 2, T + 1, size=B)
+    g1 = m.generate(x, lengths).cpu().numpy()
+    b_out = m.G.P.export_tf()["g_model/fully_connected_1/biases"]
+    # (1) padded frames: dynamic_rnn zero output -> y = b_out exactly; (2) causality + batch independence:
+    #     utterance b, frames < t depend only on x[b, :t]
+    for b in (0, 17, 127):
+        assert np.allclose(g1[b, lengths[b]:], b_out, atol=1e-6)
+    x2 = x.copy()
+    x2[5, 60:] += 1.0
+    x2[9] *= -1.0
+    g2 = m.generate(x2, lengths).cpu().numpy()
+    keep = [b for b in range(B) if b not in (5, 9)]
+    assert np.array_equal(g1[keep], g2[keep])
+    assert np.array_equal(g1[5, :60], g2[5, :60]) and not np.array_equal(g1[5, 60:lengths[5]], g2[5, 60:lengths[5]])
+    # (3) determinism of the whole schedule (D-DNN has no noise): two models, same seed, same batch -> same bits
+    m2 = make_model("lstm", "dnn", B, g_cell=512, g_proj=256, g_layers=2)
+    o1, o2 = m.train_batch(x, y, lengths), m2.train_batch(x, y, lengths)
+    assert o1["g_mse_loss"] == pytest.approx(o2["g_mse_loss"], rel=1e-5)
+    # (4) loss identities: d_loss = d_rl + d_fk, g_loss = g_adv + lambda g_mse ; a G step lowers g_mse on the same batch
+    assert o1["d_loss"] == pytest.approx(o1["d_rl_loss"] + o1["d_fk_loss"], rel=1e-6)
+    before = m.eval_losses(x, y, lengths)["g_mse_loss"]
+    for _ in range(3):
+        m.g_step(x, y, lengths)
+    assert m.eval_losses(x, y, lengths)["g_mse_loss"] < before
+    # (5) padding of every parameter tensor is still exactly zero after the updates
+    for net in (m.G, m.D):
+        flat = net.P.theta.cpu().numpy()
+        from rsrgan_b200 import params
+        for s in net.P.segs.values():
+            n = int(np.prod(s.dev_shape))
+            d = flat[s.off:s.off + n]
+            assert np.array_equal(params.to_dev_layout(s, params.from_dev_layout(s, d)).reshape(-1), d), s.name

@@ -1,0 +1,236 @@
+"""Parity of every sm_100a kernel with float64 CPU math, through the C ABI (ctypes -> librsrgan_sm100.so)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rsr_oracle as O
+from rsrgan_b200 import packing
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=["f16", "bf16"])
+def h(request):
+    from rsrgan_b200 import ops
+    hd = ops.Handle(0, request.param)
+    yield hd
+    hd.close()
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.sqrt(((a - b) ** 2).mean()) / (np.sqrt((b ** 2).mean()) + 1e-30))
+
+
+def tol(h, f16, bf16):
+    return f16 if h.dtype_id == 0 else bf16
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 40, 257), (333, 280, 40), (128, 16, 64), (1000, 1, 1024),
+                                   (512, 1024, 1024), (257, 3040, 560), (1, 8, 8), (4100, 264, 3072)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_all_operand_layouts(h, M, N, K, a_mn, b_mn):
+    """tcgen05 GEMM == exact product of the 16-bit operands (fp32 accumulate): rel RMS 1e-5."""
+    dev, rng = h.device, np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Bm = rng.standard_normal((K, N)).astype(np.float32)
+    ldk, ldm, ldn = packing.round_up(K, 8), packing.round_up(M, 8), packing.round_up(N, 8)
+    if a_mn:
+        At = torch.zeros(K, ldm, dtype=h.h16, device=dev); At[:, :M] = torch.tensor(A.T)
+    else:
+        At = torch.zeros(M, ldk, dtype=h.h16, device=dev); At[:, :K] = torch.tensor(A)
+    if b_mn:
+        Bt = torch.zeros(K, ldn, dtype=h.h16, device=dev); Bt[:, :N] = torch.tensor(Bm)
+    else:
+        Bt = torch.zeros(N, ldk, dtype=h.h16, device=dev); Bt[:, :K] = torch.tensor(Bm.T)
+    ld32 = packing.round_up(N, 4) + 4
+    out = torch.full((M, ld32), 7.0, dtype=torch.float32, device=dev)
+    h.gemm(At, Bt, M, N, K, a_mn=a_mn, b_mn=b_mn, out32=out)
+    torch.cuda.synchronize()
+    A16 = (At[:, :M].T if a_mn else At[:, :K]).double().cpu().numpy()
+    B16 = (Bt[:, :N] if b_mn else Bt[:, :K].T).double().cpu().numpy()
+    assert rel(out[:, :N].cpu().numpy(), A16 @ B16) < 1e-5
+    assert bool((out[:, N:] == 7.0).all())               # nothing written outside [M, N]
+
+
+def test_gemm_fused_epilogue(h):
+    dev, rng = h.device, np.random.default_rng(0)
+    M, N, K = 300, 280, 257
+    A = rng.standard_normal((M, K)).astype(np.float32) * 0.3
+    W = rng.standard_normal((K, N)).astype(np.float32) * 0.1
+    bias, resid = rng.standard_normal(N).astype(np.float32), rng.standard_normal((M, N)).astype(np.float32)
+    dsrc, old = rng.standard_normal((M, N)).astype(np.float32), rng.standard_normal((M, N)).astype(np.float32)
+    At = torch.zeros(M, packing.round_up(K, 8), dtype=h.h16, device=dev); At[:, :K] = torch.tensor(A)
+    Wt = torch.tensor(W, device=dev).to(h.h16)
+    ds = torch.tensor(dsrc, device=dev).to(h.h16)
+    o32, o16 = torch.tensor(old, device=dev), torch.zeros(M, N, dtype=h.h16, device=dev)
+    from rsrgan_b200 import ops
+    h.gemm(At, Wt, M, N, K, b_mn=True, alpha=0.5, beta=2.0, bias=torch.tensor(bias, device=dev),
+           resid=torch.tensor(resid, device=dev), act=ops.ACT_LRELU, dact_src=ds, dact=ops.ACT_RELU, out32=o32, out16=o16)
+    torch.cuda.synchronize()
+    v = 0.5 * (At[:, :K].double().cpu().numpy() @ Wt.double().cpu().numpy()) + bias + resid
+    v = np.maximum(v, 0.3 * v) * (ds.double().cpu().numpy() > 0)
+    assert rel(o32.cpu().numpy(), v + 2.0 * old) < 1e-5
+    assert rel(o16.float().cpu().numpy(), v) < tol(h, 5e-4, 4e-3)
+
+
+def _rec_case(h, B, T, I, C, P, ragged, seed):
+    dev, rng = h.device, np.random.default_rng(seed)
+    Cp = packing.cell_pad(C)
+    x = rng.standard_normal((B, T, I))
+    K = O.xavier(rng, (I + P, 4 * C)) * 2.0
+    b = rng.standard_normal(4 * C) * 0.1
+    wi, wf, wo = (O.xavier(rng, (C,)) for _ in range(3))
+    Wp = O.xavier(rng, (C, P)) * 2.0
+    lengths = rng.integers(max(T // 2, 1), T + 1, size=B) if ragged else np.full(B, T)
+    out_ref, cache = O.lstmp_fwd(x, lengths, K, b, wi, wf, wo, Wp)
+    steps = cache[-1]
+    zx = np.einsum("bti,ig->tbg", x, K[:I]) + b
+    zx_p = packing.pack_cols(zx.reshape(T * B, 4 * C), C).astype(np.float32)
+    Wc_p = packing.pad_first(packing.pack_cols(Wp @ K[I:], C), Cp)
+    wc16 = torch.tensor(Wc_p, device=dev).to(h.h16).contiguous()
+    wcT16 = wc16.t().contiguous()
+    pk = lambda v: torch.tensor(packing.pad_last(v, Cp).astype(np.float32), device=dev)
+    d_wi, d_wf, d_wo = pk(wi), pk(wf), pk(wo)
+    d_len = torch.tensor(lengths.astype(np.int32), device=dev)
+    mt_seq = torch.zeros((T + 1) * B, Cp, dtype=h.h16, device=dev)
+    save = torch.zeros(T * B, 5, Cp, dtype=torch.float32, device=dev)
+    h.lstmp_rec_fwd(B, T, Cp, torch.tensor(zx_p, device=dev), wcT16, d_wi, d_wf, d_wo, d_len, mt_seq, save)
+    torch.cuda.synchronize()
+    mt_ref = np.stack([np.where(steps[t][9], steps[t][8], 0.0) for t in range(T)])
+    got = mt_seq[B:].float().cpu().numpy().reshape(T, B, Cp)
+    res = dict(mt=rel(got[:, :, :C], mt_ref), pad=float(np.abs(got[:, :, C:]).max()) if Cp > C else 0.0,
+               out=rel((got[:, :, :C] @ Wp).transpose(1, 0, 2), out_ref))
+    dout = rng.standard_normal((B, T, P)) * 0.1
+    dx_ref, g_ref = O.lstmp_bwd(dout, cache)
+    dmt = np.einsum("btp,cp->tbc", dout, Wp).reshape(T * B, C)
+    d_dmt = torch.tensor(packing.pad_last(dmt, Cp).astype(np.float32), device=dev)
+    dz16 = torch.zeros(T * B, 4 * Cp, dtype=h.h16, device=dev)
+    dbias = torch.zeros(4 * Cp, dtype=torch.float32, device=dev)
+    dwi, dwf, dwo = (torch.zeros(Cp, dtype=torch.float32, device=dev) for _ in range(3))
+    h.lstmp_rec_bwd(B, T, Cp, d_dmt, wc16, d_wi, d_wf, d_wo, d_len, save, dz16, dbias, dwi, dwf, dwo)
+    torch.cuda.synchronize()
+    dz = packing.unpack_cols(dz16.float().cpu().numpy(), C).reshape(T, B, 4 * C)
+    xin = np.concatenate([x.transpose(1, 0, 2), np.concatenate([np.zeros((1, B, P)), out_ref.transpose(1, 0, 2)[:-1]], 0)], 2)
+    res.update(dbias=rel(packing.unpack_cols(dbias.cpu().numpy(), C), g_ref["bias"]),
+               dwi=rel(dwi.cpu().numpy()[:C], g_ref["w_i_diag"]), dwf=rel(dwf.cpu().numpy()[:C], g_ref["w_f_diag"]),
+               dwo=rel(dwo.cpu().numpy()[:C], g_ref["w_o_diag"]),
+               dx=rel(np.einsum("tbg,ig->bti", dz, K[:I]), dx_ref), dK=rel(np.einsum("tbi,tbg->ig", xin, dz), g_ref["kernel"]))
+    return res
+
+
+@pytest.mark.parametrize("B,T,I,C,P,ragged", [
+    (8, 12, 40, 256, 40, True),          # discriminator_lstm layer (models/discriminator_lstm.py:26-28)
+    (8, 20, 280, 760, 280, True),        # lstm generator layer (models/lstm.py:43-45), C padded 760 -> 768
+    (40, 10, 256, 512, 256, False),      # BASELINE cfg-2 layer, several utterance groups
+    (1, 9, 257, 760, 257, True),         # decode: one utterance (train...py batch_size=1), res_lstm_l layer
+    (3, 1, 40, 256, 40, False),          # a single frame
+])
+def test_lstmp_recurrence_fwd_bwd(h, B, T, I, C, P, ragged):
+    r = _rec_case(h, B, T, I, C, P, ragged, seed=B + T)
+    t = tol(h, 1.5e-3, 1e-2)
+    assert r["pad"] == 0.0
+    for k, v in r.items():
+        if k != "pad":
+            assert v < t, (k, v, r)
+
+
+def test_lstmp_shape_errors(h):
+    z = torch.zeros(8, device=h.device)
+    from rsrgan_b200 import _lib
+    with pytest.raises(_lib.RsrError):
+        h.lstmp_rec_fwd(8, 4, 100, z, z, z, z, z, z.int(), z, None)        # Cp not a multiple of 256
+    with pytest.raises(_lib.RsrError):
+        h.lstmp_rec_fwd(4096, 4, 256, z, z, z, z, z, z.int(), z, None)     # group would not be co-resident
+
+
+def test_staging_losses_update(h):
+    dev, rng = h.device, np.random.default_rng(2)
+    tt = lambda a: torch.tensor(a, device=dev)
+    B, T, D = 5, 7, 40
+    x = rng.standard_normal((B, T, D)).astype(np.float32)
+    mean, std = rng.standard_normal(D).astype(np.float32), (rng.random(D) + 0.5).astype(np.float32)
+    noise = rng.standard_normal((B, D)).astype(np.float32)
+    o16 = torch.zeros(T * B, 40, dtype=h.h16, device=dev)
+    o32 = torch.zeros(T * B, 40, dtype=torch.float32, device=dev)
+    h.stage_input(tt(x), B, T, D, out16=o16, out32=o32, mean=tt(mean), istd=tt(1.0 / std), noise=tt(noise))
+    ref = ((x - mean) * (1.0 / std) + noise[:, None, :]).transpose(1, 0, 2).reshape(T * B, D)
+    assert np.allclose(o32.cpu().numpy(), ref, atol=1e-6)
+    assert rel(o16.float().cpu().numpy(), ref) < tol(h, 5e-4, 4e-3)
+    back = torch.zeros(B, T, D, dtype=torch.float32, device=dev)
+    h.unstage_output(o32, B, T, D, back)
+    assert np.array_equal(back.cpu().numpy(), o32.cpu().numpy().reshape(T, B, D).transpose(1, 0, 2))
+    # CMVN apply / invert (io_funcs/make_tfrecords.py:84-87; train...py:286-287): fp32 within 1 ulp-ish of float64 math
+    xm = rng.standard_normal((1000, 257)).astype(np.float32) * 3 + 1
+    m2, s2 = rng.standard_normal(257).astype(np.float32), (rng.random(257) + 0.5).astype(np.float32)
+    out = torch.empty(1000, 257, device=dev)
+    h.cmvn_apply(tt(xm), tt(m2), tt(s2), out)
+    assert np.allclose(out.cpu().numpy(), O.cmvn_apply(xm, m2.astype(np.float64), s2.astype(np.float64)), rtol=2e-6, atol=2e-6)
+    inv = torch.empty_like(out)
+    h.cmvn_invert(out, tt(m2), tt(s2), inv)
+    assert np.allclose(inv.cpu().numpy(), xm, rtol=1e-5, atol=1e-5)
+    # losses + gradients, with the discriminator_dnn clip
+    n = B * T
+    rl, fk = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    g, y = rng.standard_normal((n, D)).astype(np.float32), rng.standard_normal((n, D)).astype(np.float32)
+    losses = torch.zeros(8, dtype=torch.float32, device=dev)
+    rl4 = torch.zeros(n, 4, device=dev); rl4[:, 0] = tt(rl)
+    fk4 = torch.zeros(n, 4, device=dev); fk4[:, 0] = tt(fk)
+    g1, g2, g3 = (torch.zeros(n, 8, dtype=h.h16, device=dev) for _ in range(3))
+    dg = torch.zeros(n, D, device=dev)
+    h.lsgan_mse_losses(losses, rl=rl4, fk=fk4, ld_logit=4, n_logit=n, clip=True, g=tt(g), y=tt(y), n_frames=n,
+                       d_out=D, lam=10.0, gscale=64.0, d_rl_grad=g1, d_fk_grad=g2, g_adv_grad=g3, ld_grad=8, dg_mse=dg)
+    rc, fc = np.clip(rl, -0.5, 1.5), np.clip(fk, -0.5, 1.5)
+    L = O.lsgan_mse_losses(rc.astype(np.float64), fc.astype(np.float64), g.astype(np.float64), y.astype(np.float64))
+    got = losses.cpu().numpy()
+    for i, k in enumerate(("d_rl_loss", "d_fk_loss", "g_adv_loss", "g_mse_loss")):
+        assert got[i] == pytest.approx(L[k], rel=1e-5)
+    in_rl, in_fk = (rl >= -0.5) & (rl <= 1.5), (fk >= -0.5) & (fk <= 1.5)
+    t16 = tol(h, 5e-4, 4e-3)
+    assert rel(g1[:, 0].float().cpu().numpy(), 64 * 2 * (rc - 1) / n * in_rl) < t16
+    assert rel(g2[:, 0].float().cpu().numpy(), 64 * 2 * (fc - 0) / n * in_fk) < t16
+    assert rel(g3[:, 0].float().cpu().numpy(), 64 * 2 * (fc - 1) / n * in_fk) < t16
+    assert rel(dg.cpu().numpy(), 64 * 10.0 * (g - y) / n) < 1e-6
+    # column sums
+    X = rng.standard_normal((1000, 77)).astype(np.float32)
+    Xd = torch.zeros(1000, 80, dtype=h.h16, device=dev); Xd[:, :77] = tt(X)
+    cs = torch.zeros(77, device=dev)
+    h.colsum16(Xd, 1000, 77, cs)
+    assert rel(cs.cpu().numpy(), Xd[:, :77].double().sum(0).cpu().numpy()) < 1e-5
+
+
+def test_fused_clip_update_sweep(h):
+    """rsr_seg_sumsq + rsr_clip_{adam,sgd}_ema == clip_by_norm per tensor, TF Adam, EMA (gan_rnn_placeholder.py:144-189)."""
+    dev, rng = h.device, np.random.default_rng(3)
+    tt = lambda a: torch.tensor(a, device=dev)
+    sizes = [3072, 1024, 2048]
+    n_el = sum(sizes)
+    seg_id = np.concatenate([np.full(s // 1024, i) for i, s in enumerate(sizes)]).astype(np.int32)
+    theta, grad = rng.standard_normal(n_el).astype(np.float32), rng.standard_normal(n_el).astype(np.float32) * 0.1
+    grad[:3072] *= 50.0                                      # first tensor exceeds the clip norm, the others do not
+    bounds = [(0, 3072), (3072, 4096), (4096, 6144)]
+    d_theta, d_grad, d_seg, d_ema = tt(theta), tt(grad * 8.0), tt(seg_id), tt(theta)
+    d_m, d_v = torch.zeros(n_el, device=dev), torch.zeros(n_el, device=dev)
+    sumsq, th16 = torch.zeros(3, device=dev), torch.zeros(n_el, dtype=h.h16, device=dev)
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.9, 0.999, 0, 0], dtype=torch.float32, device=dev)
+    p = {i: theta[a:b].astype(np.float64) for i, (a, b) in enumerate(bounds)}
+    gd = {i: grad[a:b].astype(np.float64) for i, (a, b) in enumerate(bounds)}
+    m, v_ = {k: np.zeros_like(x) for k, x in p.items()}, {k: np.zeros_like(x) for k, x in p.items()}
+    ema, tstep = {k: x.copy() for k, x in p.items()}, 0
+    for _ in range(3):
+        h.seg_sumsq(d_grad, 1.0 / 8.0, d_seg, 3, sumsq)
+        h.clip_adam_ema(d_grad, 1.0 / 8.0, d_seg, sumsq, 15.0, hyper, 0.9999, d_theta, d_m, d_v, d_ema, th16)
+        cl = {k: O.clip_by_norm(gd[k], 15.0) for k in gd}
+        p, m, v_, tstep = O.adam_update_tf(p, cl, m, v_, tstep, 1e-3)
+        ema = O.ema_update(ema, p)
+    cat = lambda d: np.concatenate([d[0], d[1], d[2]])
+    assert np.abs(d_theta.cpu().numpy() - cat(p)).max() < 1e-6
+    assert np.abs(d_ema.cpu().numpy() - cat(ema)).max() < 1e-6
+    assert rel(th16.float().cpu().numpy(), cat(p)) < tol(h, 5e-4, 4e-3)
+    assert hyper[4].item() == pytest.approx(0.9 ** 4, rel=1e-6) and hyper[5].item() == pytest.approx(0.999 ** 4, rel=1e-6)
+    d_theta2, d_ema2 = tt(theta), tt(theta)
+    hy2 = torch.tensor([0.05, 0, 0, 0, 0, 0, 0, 0], dtype=torch.float32, device=dev)
+    h.seg_sumsq(d_grad, 1.0 / 8.0, d_seg, 3, sumsq)
+    h.clip_sgd_ema(d_grad, 1.0 / 8.0, d_seg, sumsq, 15.0, hy2, 0.9999, d_theta2, d_ema2, None)
+    ref = np.concatenate([theta[a:b] - 0.05 * O.clip_by_norm(grad[a:b].astype(np.float64)) for a, b in bounds])
+    assert np.abs(d_theta2.cpu().numpy() - ref).max() < 1e-6

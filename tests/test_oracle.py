@@ -1,0 +1,156 @@
+"""Pins the CPU oracle (oracle/rsr_oracle.py): against the independent torch-autograd statement,
+finite differences, torch.nn.LSTM(proj_size) and the committed golden vectors.  PARITY UNPINNED
+against TF-1.4 itself (not runnable here) -- see the oracle header."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import make_golden, rsr_oracle as O, torch_ref as R
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def small_gan(g_type="lstm", d_type="lstm", seed=0):
+    rng = np.random.default_rng(seed)
+    gp = O.init_g_lstm(rng, cell=24, proj=12, layers=2) if g_type == "lstm" else O.init_g_res_lstm_l(rng, cell=16, layers=2)
+    dp = O.init_d_lstm(rng, cell=16) if d_type == "lstm" else O.init_d_dnn(rng, units=32, hidden=2)
+    for p in (gp, dp):
+        for k in p:
+            if "bias" in k:
+                p[k] = rng.standard_normal(p[k].shape) * 0.1
+    B, T = 3, 5
+    x, y = rng.standard_normal((B, T, 257)), rng.standard_normal((B, T, 40))
+    lengths = np.array([5, 3, 4])
+    nz = (rng.standard_normal((B, 1, 40)) * 0.05, rng.standard_normal((B, 1, 40)) * 0.05) if d_type == "lstm" else (None, None)
+    return gp, dp, x, y, lengths, nz
+
+
+@pytest.mark.parametrize("g_type,d_type", [("lstm", "lstm"), ("res_lstm_l", "dnn"), ("res_lstm_base", "lstm")])
+@pytest.mark.parametrize("which", ["d", "g"])
+def test_numpy_backward_matches_torch_autograd(g_type, d_type, which):
+    gp, dp, x, y, lengths, (n1, n2) = small_gan(g_type, d_type)
+    st = O.GanState(gp, dp, g_type, d_type)
+    L, grads, g_out = O.tower_losses_and_grads(st, x, y, lengths, which, n1, n2)
+    tg, td = R.to_torch(gp, requires_grad=True), R.to_torch(dp, requires_grad=True)
+    t = lambda a: None if a is None else torch.tensor(a)
+    Lt, gt, g_t = R.grads(tg, td, g_type, d_type, t(x), t(y), torch.tensor(lengths), which, noise_rl=t(n1), noise_fk=t(n2))
+    assert np.allclose(g_out, g_t.detach().numpy(), atol=1e-12)
+    for k in ("d_loss", "g_loss", "g_mse_loss", "g_adv_loss"):
+        assert abs(L[k] - float(Lt[k])) < 1e-10
+    for k in grads:
+        assert np.allclose(grads[k], gt[k].numpy(), atol=1e-10, rtol=1e-8), k
+
+
+def test_lstmp_matches_torch_nn_lstm_without_peepholes():
+    """tf LSTMCell gate order i,j,f,o with forget_bias added at run time  ==  torch.nn.LSTM(proj_size)
+    gate order i,f,g,o with the forget bias folded into b_ih, when the peepholes are zero."""
+    rng = np.random.default_rng(1)
+    B, T, I, C, P = 2, 6, 5, 7, 3
+    x = rng.standard_normal((B, T, I))
+    K = rng.standard_normal((I + P, 4 * C)) * 0.3
+    b = rng.standard_normal(4 * C) * 0.1
+    Wp = rng.standard_normal((C, P)) * 0.3
+    z = np.zeros(C)
+    out, _ = O.lstmp_fwd(x, np.full(B, T), K, b, z, z, z, Wp, forget_bias=1.0)
+    lstm = torch.nn.LSTM(I, C, batch_first=True, proj_size=P).double()
+    i_, j_, f_, o_ = (K[:, k * C:(k + 1) * C] for k in range(4))
+    Kt = np.concatenate([i_, f_, j_, o_], 1)
+    bi, bj, bf, bo = (b[k * C:(k + 1) * C] for k in range(4))
+    bt = np.concatenate([bi, bf + 1.0, bj, bo])
+    with torch.no_grad():
+        lstm.weight_ih_l0.copy_(torch.tensor(Kt[:I].T))
+        lstm.weight_hh_l0.copy_(torch.tensor(Kt[I:].T))
+        lstm.bias_ih_l0.copy_(torch.tensor(bt))
+        lstm.bias_hh_l0.zero_()
+        lstm.weight_hr_l0.copy_(torch.tensor(Wp.T))
+        ref, _ = lstm(torch.tensor(x))
+    assert np.allclose(out, ref.numpy(), atol=1e-12)
+
+
+def test_lstmp_finite_difference_with_peepholes_and_ragged_lengths():
+    rng = np.random.default_rng(2)
+    B, T, I, C, P = 2, 4, 3, 5, 2
+    x = rng.standard_normal((B, T, I))
+    prm = [rng.standard_normal((I + P, 4 * C)) * 0.4, rng.standard_normal(4 * C) * 0.1, rng.standard_normal(C) * 0.5,
+           rng.standard_normal(C) * 0.5, rng.standard_normal(C) * 0.5, rng.standard_normal((C, P)) * 0.4]
+    lengths = np.array([4, 2])
+    w = rng.standard_normal((B, T, P))
+    f = lambda: float((O.lstmp_fwd(x, lengths, *prm)[0] * w).sum())
+    out, cache = O.lstmp_fwd(x, lengths, *prm)
+    assert np.all(out[1, 2:] == 0.0)                     # dynamic_rnn zeroes outputs past sequence_length
+    dx, g = O.lstmp_bwd(w, cache)
+    names = ["kernel", "bias", "w_i_diag", "w_f_diag", "w_o_diag", "proj"]
+    eps = 1e-6
+    for arr, name in zip(prm, names):
+        idx = tuple(rng.integers(0, s) for s in arr.shape)
+        old = arr[idx]
+        arr[idx] = old + eps; fp = f()
+        arr[idx] = old - eps; fm = f()
+        arr[idx] = old
+        assert abs((fp - fm) / (2 * eps) - g[name][idx]) < 1e-6, name
+    idx = (0, 1, 2)
+    old = x[idx]
+    x[idx] = old + eps; fp = f()
+    x[idx] = old - eps; fm = f()
+    x[idx] = old
+    assert abs((fp - fm) / (2 * eps) - dx[idx]) < 1e-6
+    assert np.all(dx[1, 2:] == 0.0)
+
+
+def test_losses_include_padded_frames_and_formulas():
+    """models/gan_rnn_placeholder.py:244-260: means over every element, g_mse = 0.5*mse*output_dim."""
+    rl, fk = np.array([[0.5], [2.0]]), np.array([[0.25], [-1.0]])
+    g, y = np.ones((2, 40)), np.zeros((2, 40))
+    L = O.lsgan_mse_losses(rl, fk, g, y, mse_lambda=10.0)
+    assert L["d_rl_loss"] == pytest.approx((0.25 + 1.0) / 2)
+    assert L["d_fk_loss"] == pytest.approx((0.0625 + 1.0) / 2)
+    assert L["g_adv_loss"] == pytest.approx((0.5625 + 4.0) / 2)
+    assert L["g_mse_loss"] == pytest.approx(0.5 * 1.0 * 40)
+    assert L["g_loss"] == pytest.approx(L["g_adv_loss"] + 10.0 * 20.0)
+
+
+def test_update_rules():
+    g = np.full(100, 3.0)                                  # ||g|| = 30 -> clipped to 15
+    c = O.clip_by_norm(g, 15.0)
+    assert np.linalg.norm(c) == pytest.approx(15.0)
+    assert np.array_equal(O.clip_by_norm(np.ones(4)), np.ones(4))
+    p = OrderedDict(a=np.array([1.0, 2.0]))
+    gr = OrderedDict(a=np.array([0.5, -0.25]))
+    m, v = OrderedDict(a=np.zeros(2)), OrderedDict(a=np.zeros(2))
+    pn, m, v, t = O.adam_update_tf(p, gr, m, v, 0, 1e-3)
+    lr_t = 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    assert np.allclose(pn["a"], p["a"] - lr_t * (0.1 * gr["a"]) / (np.sqrt(0.001 * gr["a"] ** 2) + 1e-8))
+    # torch.optim.Adam puts eps inside the bias-corrected denominator: must differ from the TF form for tiny grads
+    tiny = OrderedDict(a=np.array([1e-9, 1e-9]))
+    pt, _, _, _ = O.adam_update_tf(p, tiny, OrderedDict(a=np.zeros(2)), OrderedDict(a=np.zeros(2)), 0, 1e-3)
+    tp = torch.tensor(p["a"], requires_grad=True)
+    opt = torch.optim.Adam([tp], lr=1e-3)
+    tp.grad = torch.tensor(tiny["a"])
+    opt.step()
+    assert not np.allclose(pt["a"], tp.detach().numpy(), rtol=0, atol=1e-6)
+    s = O.ema_update(OrderedDict(a=np.zeros(2)), OrderedDict(a=np.ones(2)))
+    assert np.allclose(s["a"], 1e-4)
+
+
+def test_exponential_decay_schedule():
+    """utils/ops.py:378-391 with the x num_gpu factor of train...py:525-533."""
+    assert O.exponential_decay(0, 2, 10, 1e-3) == pytest.approx(2e-3)
+    assert O.exponential_decay(5, 2, 10, 1e-3) == pytest.approx(2e-3 * np.exp(5 * np.log(1e-4) / 10))
+    assert O.exponential_decay(9, 2, 10, 1e-3) == pytest.approx(2e-7)
+    assert O.exponential_decay(3, 4, 10, 0.05, multiply_jobs=False) == pytest.approx(0.05 * np.exp(3 * np.log(1e-4) / 10))
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.CASES))
+def test_oracle_reproduces_golden_vectors(name):
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    out = make_golden.compute(name)
+    for k in ("g_out", "g_out_after"):
+        assert np.allclose(out[k], gold[k], atol=1e-10), k
+    for k in gold.files:
+        if k.startswith("loss/"):
+            assert float(out[k]) == pytest.approx(float(gold[k]), rel=1e-10)
+        if k.startswith(("dgrad/", "ggrad/")):
+            assert np.allclose(out[k], gold[k], atol=1e-7, rtol=1e-5), k
