@@ -122,6 +122,7 @@ def test_full_size_properties_cfg2():
     rng = np.random.default_rng(0)
     x, y = rng.standard_normal((B, T, 257)).astype(np.float32), rng.standard_normal((B, T, 40)).astype(np.float32)
     lengths = rng.integers(T // 2, T + 1, size=B)
+    lengths[5] = T
     g1 = m.generate(x, lengths).cpu().numpy()
     b_out = m.G.P.export_tf()["g_model/fully_connected_1/biases"]
     # (1) padded frames: dynamic_rnn zero output -> y = b_out exactly; (2) causality + batch independence:
