@@ -69,6 +69,25 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop = index, [], threading.Event()
 
     def run(self):
+        try:                                   # in-process NVML: a sample every few ms instead of one nvidia-smi fork
+            import pynvml
+            pynvml.nvmlInit()
+            hd = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(hd, pynvml.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(hd, pynvml.NVML_CLOCK_SM)
+                rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hd)
+                self.rows.append([str(sm), str(mx)] + ["Active" if rs & bits[n] else "Not Active"
+                                                       for n in ("hw_slowdown", "hw_thermal_slowdown",
+                                                                 "sw_thermal_slowdown", "sw_power_cap")])
+                self.stop.wait(0.01)
+            return
+        except Exception:
+            pass
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,

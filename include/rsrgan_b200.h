@@ -66,6 +66,8 @@ typedef struct rsr_gemm_args {
     float* out32; int ldc32;      /* fp32 output or NULL */
     void* out16; int ldc16;       /* h16 output or NULL  */
     int tile_n;                   /* 0 = auto */
+    int split_k;                  /* 0 = auto; > 1 only for "out32 += alpha A B" (beta = 1, no other epilogue term):
+                                     partial sums are added into out32 with fp32 atomics */
 } rsr_gemm_args;
 int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a);
 

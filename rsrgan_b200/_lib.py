@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
                 ("dact_src", vp), ("ldd", ci), ("dact", ci),
                 ("out32", vp), ("ldc32", ci),
                 ("out16", vp), ("ldc16", ci),
-                ("tile_n", ci)]
+                ("tile_n", ci), ("split_k", ci)]
 
 
 # name -> argtypes (every symbol include/rsrgan_b200.h declares)

@@ -2,11 +2,13 @@
 //
 //   D[M,N] = epi(alpha * A[M,K] * B[K,N])        16-bit operands, fp32 accumulate in TMEM
 //
-// One CTA computes one 128 x BN output tile.  Warp 0 / lane 0 is the TMA producer
-// (cp.async.bulk.tensor into a ring of 128B-swizzled stages), warp 1 / lane 0 issues
-// tcgen05.mma (UMMA 128 x BN x 16, cta_group::1) and releases stages with tcgen05.commit,
-// then all four warps drain the accumulator with tcgen05.ld (thread <-> row) and apply the
-// bias / residual / activation / activation-gradient epilogue in registers.
+// Persistent kernel, one CTA per SM, 128 x BN output tiles (BN up to 256).  Warp 0 / lane 0 is the
+// TMA producer (cp.async.bulk.tensor into a ring of 128B-swizzled stages), warp 1 / lane 0 issues
+// tcgen05.mma (UMMA 128 x BN x 16, cta_group::1) into one of two TMEM accumulators and releases
+// stages with tcgen05.commit, warps 2-5 drain the other accumulator with tcgen05.ld, transpose it
+// through shared memory so that every global access of the bias / residual / activation /
+// activation-gradient epilogue is coalesced, and hand the accumulator back.  Weight-gradient
+// products (K = all frames of the minibatch, few output tiles) are split along K across CTAs.
 // Operands may be K-major or MN-major (UMMA descriptors do the transposition), so the same
 // kernel serves Y = X W (B MN-major), dX = dY W^T (both K-major) and dW = X^T dY (both
 // MN-major) without materialising transposes.
@@ -24,10 +26,13 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;      // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int EPI_PITCH = 33;          // fp32 words per row of the per-warp transpose tile
 
 struct GemmKParams {
     int M, N, K;
     int bn, stages, a_mn, b_mn, bf;
+    int m_tiles, n_tiles, splits, acc_stride, tmem_cols;
     float alpha, beta;
     const float* bias;
     const float* resid; int ldr;
@@ -54,68 +59,76 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
     }
 }
 
-__global__ void __launch_bounds__(128)
+// Persistent, warp-specialised GEMM.  Each CTA (one per SM) walks tiles tile = blockIdx.x + i*gridDim.x of
+// the (k-split, m, n) tile space.  Three pipelines run concurrently: TMA -> smem ring (full/empty
+// mbarriers), tcgen05.mma -> double-buffered TMEM accumulator (tfull/tempty), and the epilogue warps,
+// which drain accumulator `a` while the MMA warp already fills accumulator `a^1` for the next tile.
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmKParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // 1024-byte alignment for the 128B swizzle atoms
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128B-swizzle atoms need 1024 B alignment
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int a_stage_bytes = BM * BK * 2;                          // 16 KB
     const int b_boxes = p.b_mn ? (p.bn + 63) / 64 : 1;
     const int b_stage_bytes = p.b_mn ? b_boxes * BK * 128 : p.bn * 128;
     const int stage_bytes = a_stage_bytes + ((b_stage_bytes + 1023) & ~1023);
-    const uint32_t bars = smem_base + p.stages * stage_bytes;       // full[s], empty[s], accfull, tmem slot
+    const uint32_t epi_off = (uint32_t)(p.stages * stage_bytes);
+    const uint32_t bars = smem_base + epi_off + 4u * 32u * EPI_PITCH * 4u;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
-    const uint32_t acc_bar = bars + 16u * p.stages;
-    const uint32_t tmem_slot = acc_bar + 8u;
-
-    uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < p.bn) tmem_cols <<= 1;
+    auto tfull_bar = [&](int a) { return bars + 16u * p.stages + 8u * a; };
+    auto tempty_bar = [&](int a) { return bars + 16u * p.stages + 16u + 8u * a; };
+    const uint32_t tmem_slot = bars + 16u * p.stages + 32u;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(acc_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    uint32_t tmem_acc;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    const int m0 = blockIdx.y * BM;
-    const int n0 = blockIdx.x * p.bn;
     const int nkb = (p.K + BK - 1) / BK;
+    const int tiles_mn = p.m_tiles * p.n_tiles;
+    const int total = tiles_mn * p.splits;
 
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer ----------------
             const uint32_t tx = (uint32_t)(a_stage_bytes + b_stage_bytes);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)((kb / p.stages) & 1);
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                const uint32_t sa = smem_base + s * stage_bytes;
-                const uint32_t sb = sa + a_stage_bytes;
-                mbar_expect_tx(full_bar(s), tx);
-                const int k0 = kb * BK;
-                if (!p.a_mn) {
-                    tma_load_2d(sa, &tmA, full_bar(s), k0, m0);                 // box [128 rows][64 k]
-                } else {
-                    tma_load_2d(sa, &tmA, full_bar(s), m0, k0);                 // box [64 k][64 m]
-                    tma_load_2d(sa + BK * 128, &tmA, full_bar(s), m0 + 64, k0);
-                }
-                if (!p.b_mn) {
-                    tma_load_2d(sb, &tmB, full_bar(s), k0, n0);                 // box [bn rows][64 k]
-                } else {
-                    for (int j = 0; j < b_boxes; ++j)
-                        tma_load_2d(sb + j * BK * 128, &tmB, full_bar(s), n0 + 64 * j, k0);  // box [64 k][64 n]
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int ks = tile / tiles_mn, mn = tile % tiles_mn;
+                const int m0 = (mn / p.n_tiles) * BM, n0 = (mn % p.n_tiles) * p.bn;
+                const int kb0 = (int)((long long)ks * nkb / p.splits), kb1 = (int)((long long)(ks + 1) * nkb / p.splits);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sa = smem_base + s * stage_bytes;
+                    const uint32_t sb = sa + a_stage_bytes;
+                    mbar_expect_tx(full_bar(s), tx);
+                    const int k0 = kb * BK;
+                    if (!p.a_mn) {
+                        tma_load_2d(sa, &tmA, full_bar(s), k0, m0);                 // box [128 rows][64 k]
+                    } else {
+                        tma_load_2d(sa, &tmA, full_bar(s), m0, k0);                 // box [64 k][64 m]
+                        tma_load_2d(sa + BK * 128, &tmA, full_bar(s), m0 + 64, k0);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_2d(sb, &tmB, full_bar(s), k0, n0);                 // box [bn rows][64 k]
+                    } else {
+                        for (int j = 0; j < b_boxes; ++j)
+                            tma_load_2d(sb + j * BK * 128, &tmB, full_bar(s), n0 + 64 * j, k0);  // box [64 k][64 n]
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -124,113 +137,119 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) {
             // ---------------- MMA issuer ----------------
             const uint32_t idesc = umma_idesc(BM, p.bn, p.bf, p.a_mn, p.b_mn);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)((kb / p.stages) & 1);
-                mbar_wait(full_bar(s), ph);
+            int s = 0; uint32_t ph = 0;
+            int acc = 0; uint32_t aph = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int ks = tile / tiles_mn;
+                const int kb0 = (int)((long long)ks * nkb / p.splits), kb1 = (int)((long long)(ks + 1) * nkb / p.splits);
+                mbar_wait(tempty_bar(acc), aph ^ 1u);          // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t sa = smem_base + s * stage_bytes;
-                const uint32_t sb = sa + a_stage_bytes;
+                const uint32_t tacc = tmem_base + (uint32_t)(acc * p.acc_stride);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + s * stage_bytes;
+                    const uint32_t sb = sa + a_stage_bytes;
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t da = p.a_mn ? umma_desc_sw128(sa + k * 2048, BK * 128, 1024)
-                                               : umma_desc_sw128(sa + k * 32, 16, 1024);
-                    const uint64_t db = p.b_mn ? umma_desc_sw128(sb + k * 2048, BK * 128, 1024)
-                                               : umma_desc_sw128(sb + k * 32, 16, 1024);
-                    tc_mma_f16(tmem_acc, da, db, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = p.a_mn ? umma_desc_sw128(sa + k * 2048, BK * 128, 1024)
+                                                   : umma_desc_sw128(sa + k * 32, 16, 1024);
+                        const uint64_t db = p.b_mn ? umma_desc_sw128(sb + k * 2048, BK * 128, 1024)
+                                                   : umma_desc_sw128(sb + k * 32, 16, 1024);
+                        tc_mma_f16(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(empty_bar(s));       // frees the stage when these MMAs retire
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
-                tc_commit(empty_bar(s));       // frees the stage when these MMAs retire
+                tc_commit(tfull_bar(acc));         // accumulator complete
+                if (++acc == 2) { acc = 0; aph ^= 1u; }
             }
-            tc_commit(acc_bar);                // accumulator complete
         }
         __syncwarp();
-    }
-
-    // ---------------- epilogue: all 4 warps ----------------
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
-    const int row = m0 + warp * 32 + lane;
-    const bool row_ok = row < p.M;
-    const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < p.bn; c0 += 16) {
-        float v[16];
-        tmem_ld16(lane_addr + (uint32_t)c0, v);
-        const int n = n0 + c0;
-        if (!row_ok || n >= p.N) continue;
-        const bool full = (n + 16 <= p.N);
+    } else {
+        // ---------------- epilogue warps (TMEM -> registers -> smem transpose -> coalesced global) --------
+        const int q = warp & 3;                                // TMEM lane quadrant this warp may access
+        float* st = reinterpret_cast<float*>(smem_gen + epi_off) + (warp - 2) * 32 * EPI_PITCH;
+        const int cpair = 2 * (lane & 15), rsub = lane >> 4;   // read-back mapping: 2 columns x (row parity)
+        int acc = 0; uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const int mn = tile % tiles_mn;
+            const int m0 = (mn / p.n_tiles) * BM, n0 = (mn % p.n_tiles) * p.bn;
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+            const int rbase = m0 + q * 32;
+            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+                float v[32];
+                __syncwarp();                                  // reconverge: tcgen05.ld is .sync.aligned
+                if (c0 + 32 <= p.bn) {
+                    tmem_ld32(taddr + (uint32_t)c0, v);
+                } else {                                       // bn is a multiple of 16
+                    tmem_ld16(taddr + (uint32_t)c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] *= p.alpha;
-        if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (full || n + j < p.N) v[j] += __ldg(p.bias + n + j);
-        }
-        if (p.resid) {
-            const float* r = p.resid + (size_t)row * p.ldr + n;
-            if (full) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 q = *reinterpret_cast<const float4*>(r + j);
-                    v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+                    for (int j = 16; j < 32; ++j) v[j] = 0.f;
                 }
-            } else {
-                for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += r[j];
-            }
-        }
-        if (p.act != RSR_ACT_NONE) {
+                __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
-        }
-        if (p.dsrc) {
-            const uint16_t* d = p.dsrc + (size_t)row * p.ldd + n;
-            if (full) {
-                uint4 q0 = *reinterpret_cast<const uint4*>(d);
-                uint4 q1 = *reinterpret_cast<const uint4*>(d + 8);
-                const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    v[2 * j] *= act_grad_from_out(h2f((uint16_t)(w[j] & 0xFFFF), p.bf), p.dact);
-                    v[2 * j + 1] *= act_grad_from_out(h2f((uint16_t)(w[j] >> 16), p.bf), p.dact);
-                }
-            } else {
-                for (int j = 0; j < 16; ++j)
-                    if (n + j < p.N) v[j] *= act_grad_from_out(h2f(d[j], p.bf), p.dact);
-            }
-        }
-        if (p.out32) {   // fp32 output carries the beta accumulation; the 16-bit output below does not
-            float* o = p.out32 + (size_t)row * p.ldc32 + n;
-            if (full) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    float4 w = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    if (p.beta != 0.0f) {
-                        const float4 q = *reinterpret_cast<const float4*>(o + j);
-                        w.x += p.beta * q.x; w.y += p.beta * q.y; w.z += p.beta * q.z; w.w += p.beta * q.w;
+                for (int j = 0; j < 32; ++j) st[lane * EPI_PITCH + j] = v[j];
+                __syncwarp();
+                const int col = n0 + c0 + cpair;
+                const bool live = (col < p.N) && (c0 + cpair < p.bn);
+                const bool two = (col + 1 < p.N);
+                float b0 = 0.f, b1 = 0.f;
+                if (p.bias && live) { b0 = __ldg(p.bias + col); if (two) b1 = __ldg(p.bias + col + 1); }
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) {
+                    const int r = 2 * i + rsub;
+                    const int row = rbase + r;
+                    if (row >= p.M || !live) break;
+                    float x0 = st[r * EPI_PITCH + cpair] * p.alpha + b0;
+                    float x1 = st[r * EPI_PITCH + cpair + 1] * p.alpha + b1;
+                    if (p.resid) {
+                        const float* rp = p.resid + (size_t)row * p.ldr + col;
+                        if (two) { const float2 t = *reinterpret_cast<const float2*>(rp); x0 += t.x; x1 += t.y; }
+                        else x0 += rp[0];
                     }
-                    *reinterpret_cast<float4*>(o + j) = w;
+                    if (p.act != RSR_ACT_NONE) { x0 = apply_act(x0, p.act); x1 = apply_act(x1, p.act); }
+                    if (p.dsrc) {
+                        const uint16_t* dp = p.dsrc + (size_t)row * p.ldd + col;
+                        if (two) {
+                            const uint32_t w = *reinterpret_cast<const uint32_t*>(dp);
+                            x0 *= act_grad_from_out(h2f((uint16_t)(w & 0xFFFF), p.bf), p.dact);
+                            x1 *= act_grad_from_out(h2f((uint16_t)(w >> 16), p.bf), p.dact);
+                        } else {
+                            x0 *= act_grad_from_out(h2f(dp[0], p.bf), p.dact);
+                        }
+                    }
+                    if (p.out16) {
+                        uint16_t* o = p.out16 + (size_t)row * p.ldc16 + col;
+                        if (two) *reinterpret_cast<uint32_t*>(o) = pack2(x0, x1, p.bf);
+                        else o[0] = f2h(x0, p.bf);
+                    }
+                    if (p.out32) {
+                        float* o = p.out32 + (size_t)row * p.ldc32 + col;
+                        if (p.splits > 1) {                    // split-K partial sums meet in L2 (out32 += ...)
+                            red_add_f32(o, x0);
+                            if (two) red_add_f32(o + 1, x1);
+                        } else if (two) {
+                            float2 w = make_float2(x0, x1);
+                            if (p.beta != 0.0f) { const float2 t = *reinterpret_cast<const float2*>(o); w.x += p.beta * t.x; w.y += p.beta * t.y; }
+                            *reinterpret_cast<float2*>(o) = w;
+                        } else {
+                            o[0] = p.beta != 0.0f ? x0 + p.beta * o[0] : x0;
+                        }
+                    }
                 }
-            } else {
-                for (int j = 0; j < 16; ++j)
-                    if (n + j < p.N) o[j] = p.beta != 0.0f ? v[j] + p.beta * o[j] : v[j];
             }
-        }
-        if (p.out16) {
-            uint16_t* o = p.out16 + (size_t)row * p.ldc16 + n;
-            if (full) {
-                uint4 q0, q1;
-                q0.x = pack2(v[0], v[1], p.bf);  q0.y = pack2(v[2], v[3], p.bf);
-                q0.z = pack2(v[4], v[5], p.bf);  q0.w = pack2(v[6], v[7], p.bf);
-                q1.x = pack2(v[8], v[9], p.bf);  q1.y = pack2(v[10], v[11], p.bf);
-                q1.z = pack2(v[12], v[13], p.bf); q1.w = pack2(v[14], v[15], p.bf);
-                *reinterpret_cast<uint4*>(o) = q0;
-                *reinterpret_cast<uint4*>(o + 8) = q1;
-            } else {
-                for (int j = 0; j < 16; ++j) if (n + j < p.N) o[j] = f2h(v[j], p.bf);
-            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));       // accumulator may be overwritten
+            if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_acc, tmem_cols);
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 }  // namespace
@@ -314,13 +333,17 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     if (a->resid && ((a->ldr & 3) || ((uintptr_t)a->resid & 15))) return RSR_E_SHAPE;
     if (a->dact_src && ((a->ldd & 7) || ((uintptr_t)a->dact_src & 15))) return RSR_E_SHAPE;
 
+    const bool plain_accumulate = a->out32 && !a->out16 && !a->bias && !a->resid && a->act == RSR_ACT_NONE &&
+                                  !a->dact_src && a->beta == 1.0f;
     GemmKParams p;
     p.M = a->M; p.N = a->N; p.K = a->K;
+    const int m_tiles = (a->M + BM - 1) / BM;
     int bn = a->tile_n;
     if (bn <= 0) {
-        // wide tiles for big problems; for small N take N rounded up to 16
         bn = 128;
         if (a->N < 128) bn = (a->N + 15) & ~15;
+        // wide tiles when the problem still fills the machine twice over
+        else if (a->N % 256 == 0 && (long long)m_tiles * (a->N / 256) >= 2LL * h->num_sms) bn = 256;
     }
     if (bn < 16 || bn > 256 || (bn & 15)) return RSR_E_SHAPE;
     p.bn = bn;
@@ -329,18 +352,45 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     p.bias = a->bias; p.resid = a->resid; p.ldr = a->ldr; p.act = a->act;
     p.dsrc = (const uint16_t*)a->dact_src; p.ldd = a->ldd; p.dact = a->dact;
     p.out32 = a->out32; p.ldc32 = a->ldc32; p.out16 = (uint16_t*)a->out16; p.ldc16 = a->ldc16;
+    p.m_tiles = m_tiles;
+    p.n_tiles = (a->N + bn - 1) / bn;
 
     const int a_stage = BM * BK * 2;
     const int b_boxes = p.b_mn ? (bn + 63) / 64 : 1;
     const int b_stage = p.b_mn ? b_boxes * BK * 128 : bn * 128;
     const int stage_bytes = a_stage + ((b_stage + 1023) & ~1023);
     const int nkb = (a->K + BK - 1) / BK;
-    int stages = nkb < 4 ? nkb : 4;
-    // keep two CTAs per SM resident when the tile allows it (epilogue of one overlaps mainloop of the other)
-    while (stages > 2 && stages * stage_bytes > 100 * 1024) --stages;
+    // split-K: only for "out32 += A B" (weight gradients: few output tiles, K = all frames); partial
+    // sums are added into out32 with red.global.add.f32, which is the beta = 1 semantics
+    int splits = a->split_k;
+    const int tiles_mn = p.m_tiles * p.n_tiles;
+    if (splits <= 0) {
+        splits = 1;
+        if (plain_accumulate && tiles_mn < h->num_sms && nkb >= 8) {
+            splits = (h->num_sms + tiles_mn - 1) / tiles_mn;
+            if (splits > nkb / 4) splits = nkb / 4;
+            if (splits < 1) splits = 1;
+        }
+    }
+    if (splits > 1 && !plain_accumulate) return RSR_E_ARG;
+    if (splits > nkb) splits = nkb;
+    p.splits = splits;
+    const int fixed = 1024 /*align slack*/ + 4 * 32 * EPI_PITCH * 4 + 64 + 16 * 8;
+    int stages = (h->max_smem - fixed) / stage_bytes;
+    if (stages > 8) stages = 8;
+    const int kb_per_tile = (nkb + splits - 1) / splits;
+    const long long total_tiles = (long long)tiles_mn * splits;
+    const int grid = (int)(total_tiles < h->num_sms ? total_tiles : h->num_sms);
+    const long long kb_per_cta = (long long)kb_per_tile * ((total_tiles + grid - 1) / grid);
+    if (stages > kb_per_cta) stages = (int)kb_per_cta;
+    if (stages < 1) return RSR_E_SHAPE;
     p.stages = stages;
-    const int smem = stages * stage_bytes + 1024 /*align slack*/ + 16 * stages + 32;
+    const int smem = stages * stage_bytes + fixed + 16 * stages;
     if (smem > h->max_smem) return RSR_E_SHAPE;
+    int acc_stride = 32;
+    while (acc_stride < bn) acc_stride <<= 1;
+    p.acc_stride = acc_stride;
+    p.tmem_cols = 2 * acc_stride;
 
     CUtensorMap tmA, tmB;
     int rc;
@@ -356,8 +406,7 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
         RSR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
         attr_set = true;
     }
-    dim3 grid((a->N + bn - 1) / bn, (a->M + BM - 1) / BM);
-    gemm_tcgen05_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+    gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
     RSR_LAUNCH_CHECK();
     return 0;
 }

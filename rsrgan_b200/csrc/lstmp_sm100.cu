@@ -164,7 +164,7 @@ lstmp_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             if (active) creg[i] = cn;
         }
         __syncthreads();
-        if (tid == 0) { __threadfence(); red_release_add(flag, 1u); }
+        if (tid == 0) red_release_add(flag, 1u);   // release: orders the CTA's writes observed via bar.sync
     }
     tc_fence_before();
     __syncthreads();
@@ -337,7 +337,7 @@ lstmp_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const BwdParams p)
         }
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) { __threadfence(); red_release_add(flag, 1u); }
+        if (tid == 0) red_release_add(flag, 1u);   // release: orders the CTA's writes observed via bar.sync
     }
     if (ms == 0) {
         atomicAdd(p.dw_i + cell, a_dwi); atomicAdd(p.dw_f + cell, a_dwf); atomicAdd(p.dw_o + cell, a_dwo);

@@ -76,7 +76,7 @@ class Handle(object):
     # ------------------------------------------------------------------ GEMM
     def gemm(self, A, B, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, bias=None,
              resid=None, act=ACT_NONE, dact_src=None, dact=ACT_NONE, out32=None, out16=None,
-             tile_n=0, lda=None, ldb=None):
+             tile_n=0, lda=None, ldb=None, split_k=0):
         """D[M,N] = epi(alpha * A B).  A/B are 2-D h16 tensors (or views with a row stride);
         see rsr_gemm in the header for operand major-ness."""
         a = GemmArgs()
@@ -90,7 +90,7 @@ class Handle(object):
         a.dact_src, a.ldd, a.dact = _p(dact_src), (dact_src.stride(0) if dact_src is not None else 0), dact
         a.out32, a.ldc32 = _p(out32), (out32.stride(0) if out32 is not None else 0)
         a.out16, a.ldc16 = _p(out16), (out16.stride(0) if out16 is not None else 0)
-        a.tile_n = tile_n
+        a.tile_n, a.split_k = tile_n, split_k
         self._call("rsr_gemm", 1, self.h, _stream(), C.byref(a), work=2.0 * M * N * K)
 
     # --------------------------------------------------------------- staging
