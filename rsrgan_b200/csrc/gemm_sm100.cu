@@ -26,20 +26,23 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;      // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
-constexpr int EPI_PITCH = 33;          // fp32 words per row of the per-warp transpose tile
+constexpr int EPI_WARPS = 8;                                    // two warps per TMEM lane quadrant
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;               // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
 
 struct GemmKParams {
     int M, N, K;
     int bn, stages, a_mn, b_mn, bf;
     int m_tiles, n_tiles, splits, acc_stride, tmem_cols;
+    int st_stride;            // bytes of epilogue staging per warp (fp32 box 4 KB and/or 16-bit box 2 KB)
+    int reduce32;             // out32 is accumulated with TMA reduce-add (split-K partials, or beta == 1)
     float alpha, beta;
     const float* bias;
     const float* resid; int ldr;
     int act;
     const uint16_t* dsrc; int ldd; int dact;
-    float* out32; int ldc32;
+    float* out32; int ldc32;         // direct access: previous contents when beta is neither 0 nor 1, ragged N edge
     uint16_t* out16; int ldc16;
+    int has32, has16;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -63,12 +66,17 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
 // the (k-split, m, n) tile space.  Three pipelines run concurrently: TMA -> smem ring (full/empty
 // mbarriers), tcgen05.mma -> double-buffered TMEM accumulator (tfull/tempty), and the epilogue warps,
 // which drain accumulator `a` while the MMA warp already fills accumulator `a^1` for the next tile.
+// Epilogue: thread <-> accumulator row, 32 columns at a time (tcgen05.ld 32x32b.x32); epilogue operands
+// (residual, activation-gradient source) are read as 16-byte vectors of that row; results go to a
+// swizzled per-warp staging box and leave with ONE TMA store per box (cp.async.bulk.tensor, or
+// cp.reduce...add for accumulated fp32 outputs), so HBM sees full 128-byte lines and the M / N edges are
+// clipped by the tensor map.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC32, const __grid_constant__ CUtensorMap tmC16,
                     const GemmKParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128B-swizzle atoms need 1024 B alignment
-    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int a_stage_bytes = BM * BK * 2;                          // 16 KB
@@ -76,7 +84,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int b_stage_bytes = p.b_mn ? b_boxes * BK * 128 : p.bn * 128;
     const int stage_bytes = a_stage_bytes + ((b_stage_bytes + 1023) & ~1023);
     const uint32_t epi_off = (uint32_t)(p.stages * stage_bytes);
-    const uint32_t bars = smem_base + epi_off + 4u * 32u * EPI_PITCH * 4u;
+    const uint32_t bars = smem_base + epi_off + (uint32_t)(EPI_WARPS * p.st_stride);
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
     auto tfull_bar = [&](int a) { return bars + 16u * p.stages + 8u * a; };
@@ -86,8 +94,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (p.has32) tma_prefetch_desc(&tmC32);
+        if (p.has16) tma_prefetch_desc(&tmC16);
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -167,10 +177,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         __syncwarp();
     } else {
-        // ---------------- epilogue warps (TMEM -> registers -> smem transpose -> coalesced global) --------
+        // ---------------- epilogue warps ----------------
+        const int ew = warp - 2;
         const int q = warp & 3;                                // TMEM lane quadrant this warp may access
-        float* st = reinterpret_cast<float*>(smem_gen + epi_off) + (warp - 2) * 32 * EPI_PITCH;
-        const int cpair = 2 * (lane & 15), rsub = lane >> 4;   // read-back mapping: 2 columns x (row parity)
+        const int chunk0 = (ew >> 2) * 32;                     // the two warps of a quadrant interleave 32-column chunks
+        const uint32_t st32 = smem_base + epi_off + (uint32_t)(ew * p.st_stride);     // [32 rows][128 B], SW128
+        const uint32_t st16 = st32 + (p.has32 ? 4096u : 0u);                           // [32 rows][ 64 B], SW64
+        const uint32_t sw32 = (uint32_t)(lane & 7), sw16 = (uint32_t)((lane >> 1) & 3);
+        const bool general_beta = p.has32 && !p.reduce32 && p.beta != 0.0f;
         int acc = 0; uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int mn = tile % tiles_mn;
@@ -178,67 +192,115 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
-            const int rbase = m0 + q * 32;
-            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+            const int row0 = m0 + q * 32;
+            const int row = row0 + lane;
+            const bool row_ok = row < p.M;
+            for (int c0 = chunk0; c0 < p.bn; c0 += 64) {
+                const int col0 = n0 + c0;
+                if (col0 >= p.N) break;                        // warp-uniform
+                // epilogue operands of this row (independent of the accumulator: issue first)
+                float bj = 0.f;
+                if (p.bias && col0 + lane < p.N) bj = __ldg(p.bias + col0 + lane);
+                float4 rs[8];
+                uint4 dq[4];
+                if (p.resid) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        rs[c] = (row_ok && col0 + 4 * c < p.N)
+                                    ? __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldr + col0) + c)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (p.dsrc) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        dq[c] = (row_ok && col0 + 8 * c < p.N)
+                                    ? __ldg(reinterpret_cast<const uint4*>(p.dsrc + (size_t)row * p.ldd + col0) + c)
+                                    : make_uint4(0u, 0u, 0u, 0u);
+                }
                 float v[32];
                 __syncwarp();                                  // reconverge: tcgen05.ld is .sync.aligned
                 if (c0 + 32 <= p.bn) {
                     tmem_ld32(taddr + (uint32_t)c0, v);
-                } else {                                       // bn is a multiple of 16
+                } else {                                       // bn is a multiple of 16 (only when n_tiles == 1)
                     tmem_ld16(taddr + (uint32_t)c0, v);
 #pragma unroll
                     for (int j = 16; j < 32; ++j) v[j] = 0.f;
                 }
-                __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) st[lane * EPI_PITCH + j] = v[j];
+                for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], p.alpha, __shfl_sync(0xffffffffu, bj, j));
+                if (p.resid) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { v[4 * c] += rs[c].x; v[4 * c + 1] += rs[c].y; v[4 * c + 2] += rs[c].z; v[4 * c + 3] += rs[c].w; }
+                }
+                if (p.act != RSR_ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+                }
+                if (p.dsrc) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t w[4] = {dq[c].x, dq[c].y, dq[c].z, dq[c].w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            v[8 * c + 2 * k] *= act_grad_from_out(h2f((uint16_t)(w[k] & 0xFFFFu), p.bf), p.dact);
+                            v[8 * c + 2 * k + 1] *= act_grad_from_out(h2f((uint16_t)(w[k] >> 16), p.bf), p.dact);
+                        }
+                    }
+                }
+                if (col0 + 32 > p.N && (p.N & 7)) {
+                    // ragged right edge (N not a multiple of the 16-byte TMA store granule): plain stores
+                    if (row_ok && p.has16) {                   // out16 holds the value without the beta term
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) p.out16[(size_t)row * p.ldc16 + col0 + j] = f2h(v[j], p.bf);
+                    }
+                    if (row_ok && p.has32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (col0 + j < p.N) {
+                                float* o = p.out32 + (size_t)row * p.ldc32 + col0 + j;
+                                if (p.reduce32) red_add_f32(o, v[j]);
+                                else *o = general_beta ? v[j] + p.beta * *o : v[j];
+                            }
+                        }
+                    }
+                    continue;
+                }
+                // the previous boxes of this warp must have been read out of the staging buffers
+                if (lane == 0) tma_wait_group_read<0>();
                 __syncwarp();
-                const int col = n0 + c0 + cpair;
-                const bool live = (col < p.N) && (c0 + cpair < p.bn);
-                const bool two = (col + 1 < p.N);
-                float b0 = 0.f, b1 = 0.f;
-                if (p.bias && live) { b0 = __ldg(p.bias + col); if (two) b1 = __ldg(p.bias + col + 1); }
-#pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    const int r = 2 * i + rsub;
-                    const int row = rbase + r;
-                    if (row >= p.M || !live) break;
-                    float x0 = st[r * EPI_PITCH + cpair] * p.alpha + b0;
-                    float x1 = st[r * EPI_PITCH + cpair + 1] * p.alpha + b1;
-                    if (p.resid) {
-                        const float* rp = p.resid + (size_t)row * p.ldr + col;
-                        if (two) { const float2 t = *reinterpret_cast<const float2*>(rp); x0 += t.x; x1 += t.y; }
-                        else x0 += rp[0];
-                    }
-                    if (p.act != RSR_ACT_NONE) { x0 = apply_act(x0, p.act); x1 = apply_act(x1, p.act); }
-                    if (p.dsrc) {
-                        const uint16_t* dp = p.dsrc + (size_t)row * p.ldd + col;
-                        if (two) {
-                            const uint32_t w = *reinterpret_cast<const uint32_t*>(dp);
-                            x0 *= act_grad_from_out(h2f((uint16_t)(w & 0xFFFF), p.bf), p.dact);
-                            x1 *= act_grad_from_out(h2f((uint16_t)(w >> 16), p.bf), p.dact);
-                        } else {
-                            x0 *= act_grad_from_out(h2f(dp[0], p.bf), p.dact);
+                if (p.has16) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        st_shared_v4(st16 + (uint32_t)lane * 64u + (((uint32_t)c ^ sw16) << 4),
+                                     pack2(v[8 * c], v[8 * c + 1], p.bf), pack2(v[8 * c + 2], v[8 * c + 3], p.bf),
+                                     pack2(v[8 * c + 4], v[8 * c + 5], p.bf), pack2(v[8 * c + 6], v[8 * c + 7], p.bf));
+                }
+                if (p.has32) {
+                    if (general_beta) {                        // out32 = v + beta * out32_old  (beta not in {0, 1})
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            if (row_ok && col0 + 4 * c < p.N) {
+                                const float4 o = *(reinterpret_cast<const float4*>(p.out32 + (size_t)row * p.ldc32 + col0) + c);
+                                v[4 * c] += p.beta * o.x; v[4 * c + 1] += p.beta * o.y; v[4 * c + 2] += p.beta * o.z; v[4 * c + 3] += p.beta * o.w;
+                            }
                         }
                     }
-                    if (p.out16) {
-                        uint16_t* o = p.out16 + (size_t)row * p.ldc16 + col;
-                        if (two) *reinterpret_cast<uint32_t*>(o) = pack2(x0, x1, p.bf);
-                        else o[0] = f2h(x0, p.bf);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        st_shared_v4(st32 + (uint32_t)lane * 128u + (((uint32_t)c ^ sw32) << 4),
+                                     __float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
+                                     __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && row0 < p.M) {
+                    if (p.has16) tma_store_2d(&tmC16, st16, col0, row0);
+                    if (p.has32) {
+                        if (p.reduce32) tma_reduce_add_2d(&tmC32, st32, col0, row0);
+                        else tma_store_2d(&tmC32, st32, col0, row0);
                     }
-                    if (p.out32) {
-                        float* o = p.out32 + (size_t)row * p.ldc32 + col;
-                        if (p.splits > 1) {                    // split-K partial sums meet in L2 (out32 += ...)
-                            red_add_f32(o, x0);
-                            if (two) red_add_f32(o + 1, x1);
-                        } else if (two) {
-                            float2 w = make_float2(x0, x1);
-                            if (p.beta != 0.0f) { const float2 t = *reinterpret_cast<const float2*>(o); w.x += p.beta * t.x; w.y += p.beta * t.y; }
-                            *reinterpret_cast<float2*>(o) = w;
-                        } else {
-                            o[0] = p.beta != 0.0f ? x0 + p.beta * o[0] : x0;
-                        }
-                    }
+                    tma_commit_group();
                 }
             }
             tc_fence_before();
@@ -246,6 +308,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) mbar_arrive(tempty_bar(acc));       // accumulator may be overwritten
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
+        if (lane == 0) tma_wait_group<0>();                    // stores complete before the CTA retires
     }
     tc_fence_before();
     __syncthreads();
@@ -293,22 +356,25 @@ extern "C" int rsr_destroy(rsr_handle* h) {
 
 extern "C" int rsr_num_sms(rsr_handle* h) { return h ? h->num_sms : RSR_E_ARG; }
 
-int rsr_get_tmap(rsr_handle* h, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld,
-                 uint32_t b0, uint32_t b1, CUtensorMap* out) {
-    if (((uintptr_t)ptr & 15) || (ld * 2) % 16 || b0 * 2 != 128 || b1 > 256 || d0 == 0 || d1 == 0) return RSR_E_ARG;
-    TmapKey key{ptr, d0, d1, ld * 2, b0, b1};
+int rsr_get_tmap_ex(rsr_handle* h, const void* ptr, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t ld,
+                    uint32_t b0, uint32_t b1, int swizzle, CUtensorMap* out) {
+    if ((elem_bytes != 2 && elem_bytes != 4) || (swizzle != 64 && swizzle != 128)) return RSR_E_ARG;
+    if (((uintptr_t)ptr & 15) || (ld * elem_bytes) % 16 || (int)(b0 * elem_bytes) != swizzle || b1 > 256 || d0 == 0 || d1 == 0)
+        return RSR_E_ARG;
+    TmapKey key{ptr, d0, d1, ld * elem_bytes, b0, b1, (uint32_t)elem_bytes | ((uint32_t)swizzle << 8)};
     {
         std::lock_guard<std::mutex> g(h->mu);
         auto it = h->tmaps.find(key);
         if (it != h->tmaps.end()) { *out = it->second; return 0; }
     }
     cuuint64_t dims[2] = {d0, d1};
-    cuuint64_t strides[1] = {ld * 2};
+    cuuint64_t strides[1] = {ld * elem_bytes};
     cuuint32_t box[2] = {b0, b1};
     cuuint32_t estr[2] = {1, 1};
     CUtensorMap m;
-    CUresult r = h->encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = h->encode(&m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                           const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return RSR_E_ARG;
     {
@@ -318,6 +384,11 @@ int rsr_get_tmap(rsr_handle* h, const void* ptr, uint64_t d0, uint64_t d1, uint6
     }
     *out = m;
     return 0;
+}
+
+int rsr_get_tmap(rsr_handle* h, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld,
+                 uint32_t b0, uint32_t b1, CUtensorMap* out) {
+    return rsr_get_tmap_ex(h, ptr, 2, d0, d1, ld, b0, b1, 128, out);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -352,6 +423,8 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     p.bias = a->bias; p.resid = a->resid; p.ldr = a->ldr; p.act = a->act;
     p.dsrc = (const uint16_t*)a->dact_src; p.ldd = a->ldd; p.dact = a->dact;
     p.out32 = a->out32; p.ldc32 = a->ldc32; p.out16 = (uint16_t*)a->out16; p.ldc16 = a->ldc16;
+    p.has32 = a->out32 ? 1 : 0; p.has16 = a->out16 ? 1 : 0;
+    p.st_stride = (p.has32 ? 4096 : 0) + (p.has16 ? 2048 : 0);
     p.m_tiles = m_tiles;
     p.n_tiles = (a->N + bn - 1) / bn;
 
@@ -375,7 +448,10 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     if (splits > 1 && !plain_accumulate) return RSR_E_ARG;
     if (splits > nkb) splits = nkb;
     p.splits = splits;
-    const int fixed = 1024 /*align slack*/ + 4 * 32 * EPI_PITCH * 4 + 64 + 16 * 8;
+    // accumulated fp32 outputs (out32 += ..., i.e. beta == 1, and all split-K partials) leave through TMA reduce-add
+    p.reduce32 = (a->out32 && (splits > 1 || a->beta == 1.0f)) ? 1 : 0;
+    if (p.n_tiles > 1 && (bn & 31)) return RSR_E_SHAPE;   // a 32-column store box must not reach into the next tile
+    const int fixed = 1024 /*align slack*/ + EPI_WARPS * p.st_stride + 64 + 16 * 8;
     int stages = (h->max_smem - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
     const int kb_per_tile = (nkb + splits - 1) / splits;
@@ -400,13 +476,22 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     if (!p.b_mn) rc = rsr_get_tmap(h, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, 64, (uint32_t)bn, &tmB);
     else         rc = rsr_get_tmap(h, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK, &tmB);
     if (rc) return rc;
+    CUtensorMap tmC32 = tmA, tmC16 = tmA;   // placeholders when an output is absent (never dereferenced)
+    if (a->out32) {
+        rc = rsr_get_tmap_ex(h, a->out32, 4, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc32, 32, 32, 128, &tmC32);
+        if (rc) return rc;
+    }
+    if (a->out16) {
+        rc = rsr_get_tmap_ex(h, a->out16, 2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc16, 32, 32, 64, &tmC16);
+        if (rc) return rc;
+    }
 
     static bool attr_set = false;
     if (!attr_set) {
         RSR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
         attr_set = true;
     }
-    gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+    gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, tmC32, tmC16, p);
     RSR_LAUNCH_CHECK();
     return 0;
 }

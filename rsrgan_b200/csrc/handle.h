@@ -17,9 +17,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct TmapKey {
-    const void* ptr; uint64_t d0, d1, stride1; uint32_t b0, b1;
+    const void* ptr; uint64_t d0, d1, stride1; uint32_t b0, b1, kind;   // kind = element bytes | swizzle bytes << 8
     bool operator==(const TmapKey& o) const {
-        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride1 == o.stride1 && b0 == o.b0 && b1 == o.b1;
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride1 == o.stride1 && b0 == o.b0 && b1 == o.b1 &&
+               kind == o.kind;
     }
 };
 struct TmapKeyHash {
@@ -29,6 +30,7 @@ struct TmapKeyHash {
         h ^= k.d1 + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
         h ^= k.stride1 + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
         h ^= ((uint64_t)k.b0 << 32 | k.b1) + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h ^= (uint64_t)k.kind + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
         return (size_t)h;
     }
 };
@@ -51,6 +53,10 @@ struct rsr_handle {
 // box [b1 rows, b0 cols], 128-byte swizzle (b0 * 2 bytes must be 128).
 int rsr_get_tmap(rsr_handle* h, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld,
                  uint32_t b0, uint32_t b1, CUtensorMap* out);
+// general form: elem_bytes in {2, 4}; swizzle in {64, 128} bytes and b0 * elem_bytes == swizzle
+// (TMA store targets of the GEMM epilogue: fp32 boxes of 32 columns / 16-bit boxes of 32 columns).
+int rsr_get_tmap_ex(rsr_handle* h, const void* ptr, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t ld,
+                    uint32_t b0, uint32_t b1, int swizzle, CUtensorMap* out);
 
 #define RSR_CHECK_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 #define RSR_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
