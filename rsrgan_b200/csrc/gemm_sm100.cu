@@ -112,7 +112,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int total = tiles_mn * p.splits;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // ---------------- TMA producer ----------------
             const uint32_t tx = (uint32_t)(a_stage_bytes + b_stage_bytes);
             int s = 0; uint32_t ph = 0;
@@ -144,7 +144,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // ---------------- MMA issuer ----------------
             const uint32_t idesc = umma_idesc(BM, p.bn, p.bf, p.a_mn, p.b_mn);
             int s = 0; uint32_t ph = 0;
@@ -185,6 +185,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t st16 = st32 + (p.has32 ? 4096u : 0u);                           // [32 rows][ 64 B], SW64
         const uint32_t sw32 = (uint32_t)(lane & 7), sw16 = (uint32_t)((lane >> 1) & 3);
         const bool general_beta = p.has32 && !p.reduce32 && p.beta != 0.0f;
+        const bool leader = elect_one_sync();                  // issues (and waits for) this warp's TMA stores
         int acc = 0; uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int mn = tile % tiles_mn;
@@ -267,7 +268,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     continue;
                 }
                 // the previous boxes of this warp must have been read out of the staging buffers
-                if (lane == 0) tma_wait_group_read<0>();
+                if (leader) tma_wait_group_read<0>();
                 __syncwarp();
                 if (p.has16) {
 #pragma unroll
@@ -294,7 +295,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0 && row0 < p.M) {
+                if (leader && row0 < p.M) {
                     if (p.has16) tma_store_2d(&tmC16, st16, col0, row0);
                     if (p.has32) {
                         if (p.reduce32) tma_reduce_add_2d(&tmC32, st32, col0, row0);
@@ -308,7 +309,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) mbar_arrive(tempty_bar(acc));       // accumulator may be overwritten
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
-        if (lane == 0) tma_wait_group<0>();                    // stores complete before the CTA retires
+        if (leader) tma_wait_group<0>();                    // stores complete before the CTA retires
     }
     tc_fence_before();
     __syncthreads();

@@ -45,6 +45,8 @@ struct rsr_handle {
     std::mutex mu;
     unsigned int* flags = nullptr;   // device: group-barrier counters, RSR_FLAG_WORDS words
     int flag_cursor = 0;
+    // co-resident clusters of the cluster recurrence kernels: [fwd|bwd][Cp/256 - 1][NB 16|32]; -1 = not queried yet
+    int cluster_cap[2][2][2] = {{{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}};
 };
 
 #define RSR_FLAG_WORDS 4096
@@ -57,6 +59,14 @@ int rsr_get_tmap(rsr_handle* h, const void* ptr, uint64_t d0, uint64_t d1, uint6
 // (TMA store targets of the GEMM epilogue: fp32 boxes of 32 columns / 16-bit boxes of 32 columns).
 int rsr_get_tmap_ex(rsr_handle* h, const void* ptr, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t ld,
                     uint32_t b0, uint32_t b1, int swizzle, CUtensorMap* out);
+
+// cluster (DSMEM) variants of the recurrence, lstmp_cluster_sm100.cu; RSR_E_RESIDENT = not applicable
+int rsr_lstmp_fwd_cluster(rsr_handle* h, void* stream, int B, int T, int Cp, const float* zx, const void* wcT,
+                          const float* w_i, const float* w_f, const float* w_o, float forget_bias,
+                          const int* lengths, void* mt_seq, float* save);
+int rsr_lstmp_bwd_cluster(rsr_handle* h, void* stream, int B, int T, int Cp, const float* dmt, const void* wc,
+                          const float* w_i, const float* w_f, const float* w_o, const int* lengths,
+                          const float* save, void* dz16, float* dbias, float* dw_i, float* dw_f, float* dw_o);
 
 #define RSR_CHECK_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 #define RSR_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)

@@ -20,6 +20,8 @@
 // recurrence dmt_{t-1} += dz_t Wc^T the same way, split 2-D (gate-column slices x output-row
 // slices) so that every CTA's Wc slab fits in shared memory; partial sums meet in L2 via
 // coalesced red.global.add.f32.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "handle.h"
 
@@ -75,7 +77,7 @@ lstmp_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     uint32_t tmem;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
 
-    if (tid == 0) {   // weight slab: resident for the whole sequence
+    if (warp == 0 && elect_one_sync()) {   // weight slab: resident for the whole sequence
         mbar_expect_tx(barA, (uint32_t)KB * 16384u);
         for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * 16384u, &tmW, barA, kb * 64, 128 * j);
     }
@@ -105,26 +107,28 @@ lstmp_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             const int b = b0 + n;
             zxv[n] = b < p.B ? __ldg(p.zx + ((size_t)t * p.B + b) * zx_ld + 128 * j + tid) : 0.f;
         }
-        if (tid == 0) {
+        if (warp == 0) {   // warp-uniform; the elected lane issues TMA / MMA (operands in uniform registers)
             if (t > 0) {
                 const unsigned int want = (unsigned int)G * (unsigned int)t;
                 spin_until_ge(flag, want);
             }
             fence_proxy_async_all();
-            mbar_expect_tx(barB, (uint32_t)KB * NB * 128u);
-            for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * NB * 128u, &tmM, barB, kb * 64, t * p.B + b0);
-            if (t == 0) mbar_wait(barA, 0);
-            mbar_wait(barB, (uint32_t)(t & 1));
-            tc_fence_after();
-            for (int kb = 0; kb < KB; ++kb) {
+            if (elect_one_sync()) {
+                mbar_expect_tx(barB, (uint32_t)KB * NB * 128u);
+                for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * NB * 128u, &tmM, barB, kb * 64, t * p.B + b0);
+                if (t == 0) mbar_wait(barA, 0);
+                mbar_wait(barB, (uint32_t)(t & 1));
+                tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t da = umma_desc_sw128(sA + kb * 16384u + k * 32u, 16, 1024);
-                    const uint64_t db = umma_desc_sw128(sB + kb * NB * 128u + k * 32u, 16, 1024);
-                    tc_mma_f16(tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t da = umma_desc_sw128(sA + kb * 16384u + k * 32u, 16, 1024);
+                        const uint64_t db = umma_desc_sw128(sB + kb * NB * 128u + k * 32u, 16, 1024);
+                        tc_mma_f16(tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+                    }
                 }
+                tc_commit(barM);
             }
-            tc_commit(barM);
         }
         __syncwarp();
         mbar_wait(barM, (uint32_t)(t & 1));
@@ -220,7 +224,7 @@ lstmp_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const BwdParams p)
     uint32_t tmem;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
 
-    if (tid == 0) {
+    if (warp == 0 && elect_one_sync()) {
         mbar_expect_tx(barA, 8u * 16384u);
         for (int mt = 0; mt < 2; ++mt)
             for (int kb = 0; kb < 4; ++kb)
@@ -306,19 +310,21 @@ lstmp_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const BwdParams p)
         if (t == 0) break;                     // no earlier step to feed
         fence_proxy_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
-            for (int mt = 0; mt < 2; ++mt) {
-                for (int kb = 0; kb < 4; ++kb) {
+            if (elect_one_sync()) {
+                for (int mt = 0; mt < 2; ++mt) {
+                    for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = umma_desc_sw128(sA + (mt * 4 + kb) * 16384u + k * 32u, 16, 1024);
-                        const uint64_t db = umma_desc_sw128(sB + kb * NB * 128u + k * 32u, 16, 1024);
-                        tc_mma_f16(tmem + (uint32_t)(mt * NB), da, db, idesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t da = umma_desc_sw128(sA + (mt * 4 + kb) * 16384u + k * 32u, 16, 1024);
+                            const uint64_t db = umma_desc_sw128(sB + kb * NB * 128u + k * 32u, 16, 1024);
+                            tc_mma_f16(tmem + (uint32_t)(mt * NB), da, db, idesc, (kb | k) ? 1u : 0u);
+                        }
                     }
                 }
+                tc_commit(barM);
             }
-            tc_commit(barM);
         }
         __syncwarp();
         mbar_wait(barM, (uint32_t)(step & 1));
@@ -380,6 +386,12 @@ extern "C" int rsr_lstmp_rec_fwd(rsr_handle* h, void* stream, int B, int T, int 
                                  float forget_bias, const int* lengths, void* mt_seq, float* save) {
     if (!h || !zx || !wcT || !w_i || !w_f || !w_o || !lengths || !mt_seq) return RSR_E_ARG;
     if (B <= 0 || T <= 0 || Cp <= 0 || (Cp & 255)) return RSR_E_SHAPE;
+    if (((uintptr_t)zx | (uintptr_t)wcT | (uintptr_t)w_i | (uintptr_t)w_f | (uintptr_t)w_o | (uintptr_t)mt_seq | (uintptr_t)save) & 15)
+        return RSR_E_ARG;
+    if (!getenv("RSR_NO_CLUSTER")) {   // cluster / DSMEM kernel when the cell block count fits one cluster
+        const int rcc = rsr_lstmp_fwd_cluster(h, stream, B, T, Cp, zx, wcT, w_i, w_f, w_o, forget_bias, lengths, mt_seq, save);
+        if (rcc != RSR_E_RESIDENT) return rcc;
+    }
     const int G = Cp / 32;
     const int nb = pick_nb(B, G, h->num_sms, h->max_smem, Cp, true);
     if (!nb) return RSR_E_RESIDENT;
@@ -414,6 +426,12 @@ extern "C" int rsr_lstmp_rec_bwd(rsr_handle* h, void* stream, int B, int T, int 
     if (!h || !dmt || !wc || !w_i || !w_f || !w_o || !lengths || !save || !dz16 || !dbias || !dw_i || !dw_f || !dw_o)
         return RSR_E_ARG;
     if (B <= 0 || T <= 0 || Cp <= 0 || (Cp & 255)) return RSR_E_SHAPE;
+    if (((uintptr_t)dmt | (uintptr_t)wc | (uintptr_t)save | (uintptr_t)dz16) & 15) return RSR_E_ARG;
+    if (!getenv("RSR_NO_CLUSTER")) {
+        const int rcc = rsr_lstmp_bwd_cluster(h, stream, B, T, Cp, dmt, wc, w_i, w_f, w_o, lengths, save, dz16,
+                                              dbias, dw_i, dw_f, dw_o);
+        if (rcc != RSR_E_RESIDENT) return rcc;
+    }
     const int per_grp = (Cp / 64) * (Cp / 256);
     const int nb = pick_nb(B, per_grp, h->num_sms, h->max_smem, Cp, false);
     if (!nb) return RSR_E_RESIDENT;

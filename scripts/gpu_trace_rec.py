@@ -1,0 +1,37 @@
+"""Phase timing of the cluster LSTMP forward kernel (library built with RSR_EXTRA_NVCC_FLAGS=-DRSR_TRACE).
+    python scripts/gpu_trace_rec.py [B] [Cp]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rsrgan_b200 import ops  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+Cp = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+T = 40
+h = ops.Handle(0, "f16")
+dev = h.device
+rows = T * B
+zx = torch.randn(rows, 4 * Cp, device=dev) * 0.5
+wcT = (torch.randn(4 * Cp, Cp, device=dev) * 0.03).to(h.h16)
+w = [torch.randn(Cp, device=dev) * 0.1 for _ in range(3)]
+ln = torch.full((B,), T, dtype=torch.int32, device=dev)
+mt = torch.zeros(rows + B, Cp, dtype=h.h16, device=dev)
+save = torch.zeros(rows, 5 * Cp, device=dev)
+for _ in range(3):
+    h.lstmp_rec_fwd(B, T, Cp, zx, wcT, w[0], w[1], w[2], ln, mt, save)
+torch.cuda.synchronize()
+buf = (C.c_ulonglong * (64 * 8))()
+h.lib.rsr_debug_trace.argtypes = [C.c_void_p, C.c_int]
+rc = h.lib.rsr_debug_trace(buf, 64 * 8)
+tr = np.array(buf[:], dtype=np.int64).reshape(64, 8)[:T]
+names = ["top", "full-wait done", "mma issued", "mma done", "xchg+sync", "gates+send"]
+print("B %d Cp %d rc %d; cycles between trace points (median over steps 5..%d)" % (B, Cp, rc, T - 2))
+d = np.diff(tr[5:T - 1, :6], axis=1)
+for i in range(5):
+    print("  %-16s -> %-16s %7.0f" % (names[i], names[i + 1], np.median(d[:, i])))
+print("  step period %7.0f cycles" % np.median(np.diff(tr[5:T - 1, 0])))

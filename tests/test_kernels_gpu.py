@@ -135,13 +135,26 @@ def test_lstmp_recurrence_fwd_bwd(h, B, T, I, C, P, ragged):
             assert v < t, (k, v, r)
 
 
+@pytest.mark.parametrize("B,T,I,C,P", [(40, 10, 256, 512, 256), (8, 12, 40, 256, 40)])
+def test_lstmp_recurrence_l2_exchange_variant(h, monkeypatch, B, T, I, C, P):
+    """Cp <= 512 normally runs the cluster/DSMEM kernels; RSR_NO_CLUSTER forces the L2-exchange kernels
+    (the only variant for Cp > 512) on the same shapes."""
+    monkeypatch.setenv("RSR_NO_CLUSTER", "1")
+    r = _rec_case(h, B, T, I, C, P, True, seed=7)
+    t = tol(h, 1.5e-3, 1e-2)
+    assert r["pad"] == 0.0
+    for k, v in r.items():
+        if k != "pad":
+            assert v < t, (k, v, r)
+
+
 def test_lstmp_shape_errors(h):
     z = torch.zeros(8, device=h.device)
     from rsrgan_b200 import _lib
     with pytest.raises(_lib.RsrError):
         h.lstmp_rec_fwd(8, 4, 100, z, z, z, z, z, z.int(), z, None)        # Cp not a multiple of 256
     with pytest.raises(_lib.RsrError):
-        h.lstmp_rec_fwd(4096, 4, 256, z, z, z, z, z, z.int(), z, None)     # group would not be co-resident
+        h.lstmp_rec_fwd(4096, 4, 768, z, z, z, z, z, z.int(), z, None)     # L2-exchange groups would not be co-resident
 
 
 def test_staging_losses_update(h):
