@@ -333,13 +333,13 @@ class GAN_RNN(Model):
         self.h.seg_sumsq(P.theta, 1.0, P.seg_id, len(P.segs), P.sumsq)
         self._losses[4:5] = 0.5 * self.l2_scale * (P.sumsq * P.seg_l2.to(F32)).sum()
 
-    def d_step(self, inputs, labels, lengths, noise_rl=None, noise_fk=None, sync=True, _feed=None):
+    def d_step(self, inputs, labels, lengths, noise_rl=None, noise_fk=None, sync=True, _feed=None, _g32=None):
         """One discriminator update: L_D = mean((D(y)-d_real)^2) + mean((D(G(x))-d_fake)^2),
         gradients wrt theta_D only, tower mean, per-tensor clip 15, SGD(lr_d), EMA."""
         x, y_tm, ln, B, T = _feed if _feed is not None else self._feed(inputs, labels, lengths)
         h, G, D, rows = self.h, self.G, self.D, T * B
         gs = self._gscale(rows)
-        g32 = G.fwd(x, B, T, ln, train=False)
+        g32 = _g32 if _g32 is not None else G.fwd(x, B, T, ln, train=False)
         lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=self._noise(B, noise_rl))
         lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"))
         d_rl16 = D.ws.get(("loss", "d_rl16"), rows, 8, h.h16)
@@ -355,13 +355,13 @@ class GAN_RNN(Model):
         self._update(D, gs, adam=False)
         return self._loss_dict(self._losses.tolist(), "d") if sync else self._losses
 
-    def g_step(self, inputs, labels, lengths, noise_fk=None, sync=True, _feed=None):
+    def g_step(self, inputs, labels, lengths, noise_fk=None, sync=True, _feed=None, _g32=None):
         """One generator update: L_G = mean((D(G(x))-d_real)^2) + lambda*0.5*40*mean((G(x)-y)^2) [+ l2],
         gradients wrt theta_G only (through D, D frozen), tower mean, clip 15, Adam(lr_g), EMA."""
         x, y_tm, ln, B, T = _feed if _feed is not None else self._feed(inputs, labels, lengths)
         h, G, D, rows = self.h, self.G, self.D, T * B
         gs = self._gscale(rows)
-        g32 = G.fwd(x, B, T, ln, train=True)
+        g32 = _g32 if _g32 is not None else G.fwd(x, B, T, ln, train=True)
         lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"))
         g_adv16 = D.ws.get(("loss", "g_adv16"), rows, 8, h.h16)
         dg32 = D.ws.get(("loss", "dg32"), rows, g32.shape[1], F32)
@@ -386,11 +386,16 @@ class GAN_RNN(Model):
         x, y_tm, ln, B, T = self._feed(inputs, labels, lengths)
         feed = (x, y_tm, ln, B, T)
         out = OrderedDict()
+        # The reference recomputes G(x) in every sess.run; the generator weights do not
+        # change until the first G update, so the D updates and that first G update all see the SAME G(x):
+        # it is computed once (with the activations the G backward needs) and reused -- same numbers, 2 of the
+        # 3 generator forwards of the schedule.
+        g32 = self.G.fwd(x, B, T, ln, train=self.gen_updates > 0) if self.disc_updates else None
         for _ in range(self.disc_updates):
-            d = self.d_step(None, None, None, sync=False, _feed=feed)
+            d = self.d_step(None, None, None, sync=False, _feed=feed, _g32=g32)
         d_vals = d[:2].clone() if self.disc_updates else None
-        for _ in range(self.gen_updates):
-            g = self.g_step(None, None, None, sync=False, _feed=feed)
+        for k in range(self.gen_updates):
+            g = self.g_step(None, None, None, sync=False, _feed=feed, _g32=g32 if k == 0 else None)
         if not sync:
             return d_vals, g
         if d_vals is not None:
