@@ -492,7 +492,10 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
         RSR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
         attr_set = true;
     }
-    gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, tmC32, tmC16, p);
+    // One CTA per SM, and never next to a CTA of a recurrence kernel (those hold the whole TMEM of their SM for
+    // hundreds of microseconds; a GEMM CTA sharing the SM would sit in tcgen05.alloc until they retire).
+    const int smem_launch = smem < RSR_EXCLUSIVE_SMEM_GEMM ? RSR_EXCLUSIVE_SMEM_GEMM : smem;
+    gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem_launch, (cudaStream_t)stream>>>(tmA, tmB, tmC32, tmC16, p);
     RSR_LAUNCH_CHECK();
     return 0;
 }

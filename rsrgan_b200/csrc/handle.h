@@ -51,6 +51,12 @@ struct rsr_handle {
 
 #define RSR_FLAG_WORDS 4096
 
+// Dynamic shared memory floors that keep TMEM owners apart when kernels of different streams overlap:
+// two recurrence CTAs (each allocates up to all 512 TMEM columns and waits on its cluster) must never share
+// an SM (cross-cluster alloc waits could deadlock), and a GEMM CTA must not share one with either.
+#define RSR_EXCLUSIVE_SMEM_REC (120 * 1024)
+#define RSR_EXCLUSIVE_SMEM_GEMM (160 * 1024)
+
 // 2-D tensor map over a 16-bit row-major matrix [d1 rows, d0 cols] with row pitch `ld` elements,
 // box [b1 rows, b0 cols], 128-byte swizzle (b0 * 2 bytes must be 128).
 int rsr_get_tmap(rsr_handle* h, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld,

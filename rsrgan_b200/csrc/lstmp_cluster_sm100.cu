@@ -462,10 +462,12 @@ lstmp_bwd_cluster_kernel(const CBwdParams p) {
 }
 
 size_t cfwd_smem(int Cp, int nhalf) {
-    return 1024 + (size_t)nhalf * (2 * (size_t)Cp * NB * 2 + 2 * 128 * (size_t)(NB + 1) * 4) + (size_t)nhalf * 32 + 64;
+    const size_t need = 1024 + (size_t)nhalf * (2 * (size_t)Cp * NB * 2 + 2 * 128 * (size_t)(NB + 1) * 4) + (size_t)nhalf * 32 + 64;
+    return need < RSR_EXCLUSIVE_SMEM_REC ? RSR_EXCLUSIVE_SMEM_REC : need;
 }
 size_t cbwd_smem(int Cp, int nhalf) {
-    return 1024 + (size_t)nhalf * (2 * (size_t)NB * 128 + 2 * (size_t)(Cp / 32) * NB * 64) + (size_t)nhalf * 32 + 64;
+    const size_t need = 1024 + (size_t)nhalf * (2 * (size_t)NB * 128 + 2 * (size_t)(Cp / 32) * NB * 64) + (size_t)nhalf * 32 + 64;
+    return need < RSR_EXCLUSIVE_SMEM_REC ? RSR_EXCLUSIVE_SMEM_REC : need;
 }
 
 // Launch geometry of one cluster kernel variant, decided once per (kernel, Cp): does a cluster of

@@ -168,6 +168,11 @@ class GAN_RNN(Model):
         self._losses = torch.zeros(8, dtype=F32, device=dev)
         self._l2 = torch.zeros(1, dtype=F32, device=dev)
         self._pin = {}
+        # CUDA graph of the whole batch schedule (one launch instead of ~150): single-GPU training only;
+        # RSR_NO_GRAPH=1 or use_graph=False runs every kernel eagerly
+        self.use_graph = (_arg(args, "use_graph", True) and os.environ.get("RSR_NO_GRAPH", "0") != "1"
+                          and dev.type == "cuda")
+        self._graphs = {}
         self.g_outputs = None
         self.summaries = None
         self.writer = None
@@ -302,6 +307,7 @@ class GAN_RNN(Model):
     # ------------------------------------------------------------------ updates
     def _update(self, net, gscale, adam):
         P, h = net.P, self.h
+        h.join()                                           # weight gradients computed on the side stream
         if self.world > 1:
             self.dist.all_reduce(P.grad)                   # utils/ops.py:343-376 average_gradients (sum here, 1/N below)
         gmul = 1.0 / (self.world * gscale)
@@ -333,24 +339,31 @@ class GAN_RNN(Model):
         self.h.seg_sumsq(P.theta, 1.0, P.seg_id, len(P.segs), P.sumsq)
         self._losses[4:5] = 0.5 * self.l2_scale * (P.sumsq * P.seg_l2.to(F32)).sum()
 
-    def d_step(self, inputs, labels, lengths, noise_rl=None, noise_fk=None, sync=True, _feed=None, _g32=None):
+    def d_step(self, inputs, labels, lengths, noise_rl=None, noise_fk=None, sync=True, _feed=None, _g32=None,
+               _g_train=False):
         """One discriminator update: L_D = mean((D(y)-d_real)^2) + mean((D(G(x))-d_fake)^2),
         gradients wrt theta_D only, tower mean, per-tensor clip 15, SGD(lr_d), EMA."""
         x, y_tm, ln, B, T = _feed if _feed is not None else self._feed(inputs, labels, lengths)
         h, G, D, rows = self.h, self.G, self.D, T * B
         gs = self._gscale(rows)
-        g32 = _g32 if _g32 is not None else G.fwd(x, B, T, ln, train=False)
-        lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=self._noise(B, noise_rl))
-        lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"))
         d_rl16 = D.ws.get(("loss", "d_rl16"), rows, 8, h.h16)
         d_fk16 = D.ws.get(("loss", "d_fk16"), rows, 8, h.h16)
+        n_rl, n_fk = self._noise(B, noise_rl), self._noise(B, noise_fk, "fk")
         self._losses.zero_()
-        h.lsgan_mse_losses(self._losses, rl=lg_rl, fk=lg_fk, ld_logit=lg_rl.stride(0), n_logit=rows, clip=D.clip,
-                           g=g32, y=y_tm, n_frames=rows, d_out=self.output_dim, d_real=self.d_real,
-                           d_fake=self.d_fake, lam=self.mse_lambda, gscale=gs, d_rl_grad=d_rl16,
-                           d_fk_grad=d_fk16, ld_grad=8)
         h.fill32(D.P.grad, 0.0)
-        D.bwd("rl", d_rl16)
+        kw = dict(n_logit=rows, clip=D.clip, d_real=self.d_real, d_fake=self.d_fake, lam=self.mse_lambda, gscale=gs,
+                  ld_grad=8)
+        # D(labels) does not depend on the generator: its forward, loss and backward run on the side stream
+        # while the generator recurrences (which occupy only the SMs of their clusters) run on this one.
+        with h.side_stream():
+            lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=n_rl)
+            h.lsgan_mse_losses(self._losses, rl=lg_rl, ld_logit=lg_rl.stride(0), d_rl_grad=d_rl16, **kw)
+            D.bwd("rl", d_rl16)
+        g32 = _g32 if _g32 is not None else G.fwd(x, B, T, ln, train=_g_train)
+        self._last_g32 = g32
+        lg_fk = D.fwd("fk", g32, B, T, ln, noise=n_fk)
+        h.lsgan_mse_losses(self._losses, fk=lg_fk, ld_logit=lg_fk.stride(0), g=g32, y=y_tm, n_frames=rows,
+                           d_out=self.output_dim, d_fk_grad=d_fk16, **kw)
         D.bwd("fk", d_fk16)
         self._update(D, gs, adam=False)
         return self._loss_dict(self._losses.tolist(), "d") if sync else self._losses
@@ -379,23 +392,73 @@ class GAN_RNN(Model):
         self._update(G, gs, adam=True)
         return self._loss_dict(self._losses.tolist(), "g") if sync else self._losses
 
-    def train_batch(self, inputs, labels, lengths, sync=True):
-        """The per-batch schedule of train_one_iteration (scripts/train_gan_rnn_placeholder.py:72-101):
-        disc_updates x D update then gen_updates x G update on the SAME minibatch, which is fed to the
-        device once.  Returns the losses of the last D and the last G update."""
-        x, y_tm, ln, B, T = self._feed(inputs, labels, lengths)
-        feed = (x, y_tm, ln, B, T)
-        out = OrderedDict()
+    def _schedule(self, feed):
+        """disc_updates x D update then gen_updates x G update on one fed minibatch (device work only)."""
+        x, y_tm, ln, B, T = feed
         # The reference recomputes G(x) in every sess.run (SURVEY App. C-7); the generator weights do not
         # change until the first G update, so the D updates and that first G update all see the SAME G(x):
         # it is computed once (with the activations the G backward needs) and reused -- same numbers, 2 of the
         # 3 generator forwards of the schedule.
-        g32 = self.G.fwd(x, B, T, ln, train=self.gen_updates > 0) if self.disc_updates else None
+        g32, d, g = None, None, None
         for _ in range(self.disc_updates):
-            d = self.d_step(None, None, None, sync=False, _feed=feed, _g32=g32)
+            d = self.d_step(None, None, None, sync=False, _feed=feed, _g32=g32, _g_train=self.gen_updates > 0)
+            g32 = self._last_g32
         d_vals = d[:2].clone() if self.disc_updates else None
         for k in range(self.gen_updates):
             g = self.g_step(None, None, None, sync=False, _feed=feed, _g32=g32 if k == 0 else None)
+        return d_vals, g
+
+    def _graph_key(self, B, T):
+        # everything a captured kernel receives BY VALUE; learning rates and Adam powers live on the device
+        return (B, T, self.disc_updates, self.gen_updates, self.d_real, self.d_fake, self.mse_lambda,
+                self.disc_noise_std, self.l2_scale, self.world)
+
+    def _schedule_graphed(self, inputs, labels, lengths):
+        """Copies the minibatch into static device buffers and replays the captured schedule.  The first two
+        calls for a given shape / scalar set run eagerly (they allocate the workspace), the third captures."""
+        B, T = int(inputs.shape[0]), int(inputs.shape[1])
+        key = self._graph_key(B, T)
+        st = self._graphs.get(key)
+        if st is None:
+            dev = self.h.device
+            st = dict(calls=0, graph=None, launches=0,
+                      x=torch.empty(B, T, inputs.shape[2], dtype=F32, device=dev),
+                      y=torch.empty(B, T, self.output_dim, dtype=F32, device=dev),
+                      ln=torch.empty(B, dtype=torch.int32, device=dev))
+            if len(self._graphs) > 8:
+                self._graphs.clear()
+            self._graphs[key] = st
+        for dst, src in ((st["x"], inputs), (st["y"], labels), (st["ln"], lengths)):
+            src = src if isinstance(src, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(src))
+            dst.copy_(src, non_blocking=True)              # H2D from pinned memory, or D2D
+        st["calls"] += 1
+        if st["graph"] is None and st["calls"] <= 2:
+            feed = self._feed(st["x"], st["y"], st["ln"])
+            return self._schedule(feed)
+        if st["graph"] is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = self.h.launches
+            with torch.cuda.graph(g):
+                feed = self._feed(st["x"], st["y"], st["ln"])
+                st["out"] = self._schedule(feed)
+            st["graph"], st["launches"] = g, self.h.launches - n0
+            self.h.launches = n0
+        st["graph"].replay()
+        self.h.launches += st["launches"]
+        return st["out"]
+
+    def train_batch(self, inputs, labels, lengths, sync=True):
+        """The per-batch schedule of train_one_iteration (scripts/train_gan_rnn_placeholder.py:72-101):
+        disc_updates x D update then gen_updates x G update on the SAME minibatch, which is fed to the
+        device once.  Returns the losses of the last D and the last G update."""
+        graphable = (self.use_graph and self.world == 1 and self.h.timing is None and self.D is not None
+                     and isinstance(inputs, (torch.Tensor, np.ndarray)))
+        if graphable:
+            d_vals, g = self._schedule_graphed(inputs, labels, lengths)
+        else:
+            d_vals, g = self._schedule(self._feed(inputs, labels, lengths))
+        out = OrderedDict()
         if not sync:
             return d_vals, g
         if d_vals is not None:

@@ -69,16 +69,17 @@ class FC(object):
         """dy16: gradient wrt this layer's PRE-activation.  Returns the gradient wrt the input,
         multiplied by prev_act'(prev_y16) when the producer of x16 was an activated FC."""
         net, h = self.net, self.net.h
+        dx16 = dx32 = None
+        if want_dx:    # the producer layer waits for this: main stream first
+            dx16 = net.ws.get((ctx, self.scope, "dx16"), rows, self.inp, h.h16)
+            dx32 = net.ws.get((ctx, self.scope, "dx32"), rows, self.inp, F32) if want32 else None
+            h.gemm(dy16, net.P.view(self.wname, "theta16"), rows, self.inp, self.outp, resid=resid32,
+                   dact_src=prev_y16, dact=prev_act, out16=dx16, out32=dx32)
         if want_dw:
-            h.gemm(x16, dy16, self.inp, self.outp, rows, a_mn=True, b_mn=True, beta=1.0,
-                   out32=net.P.view(self.wname, "grad"))
-            h.colsum16(dy16, rows, self.outp, net.P.view(self.bname, "grad"), accumulate=True)
-        if not want_dx:
-            return None, None
-        dx16 = net.ws.get((ctx, self.scope, "dx16"), rows, self.inp, h.h16)
-        dx32 = net.ws.get((ctx, self.scope, "dx32"), rows, self.inp, F32) if want32 else None
-        h.gemm(dy16, net.P.view(self.wname, "theta16"), rows, self.inp, self.outp, resid=resid32,
-               dact_src=prev_y16, dact=prev_act, out16=dx16, out32=dx32)
+            with h.side_stream():
+                h.gemm(x16, dy16, self.inp, self.outp, rows, a_mn=True, b_mn=True, beta=1.0,
+                       out32=net.P.view(self.wname, "grad"))
+                h.colsum16(dy16, rows, self.outp, net.P.view(self.bname, "grad"), accumulate=True)
         return dx16, dx32
 
 
@@ -95,6 +96,10 @@ class LSTMP(object):
         self.wc16 = torch.zeros(self.Cp, 4 * self.Cp, dtype=h.h16, device=h.device)    # Wc   (backward operand)
         self.wcT16 = torch.zeros(4 * self.Cp, self.Cp, dtype=h.h16, device=h.device)   # Wc^T (forward operand)
         self.scratch = torch.zeros(7 * self.Cp, dtype=F32, device=h.device)            # sink for unwanted db/dw
+        if self.Cp > 512 and hasattr(h, "overlap"):
+            # L2-exchange recurrence kernels (Cp > 512) spin on counters of co-resident CTAs: nothing else
+            # may take SMs while they run, so the side stream is switched off for this model
+            h.overlap = False
 
     def segs(self):
         return params.lstm_cell(self.prefix, self.I, self.C, self.P)
@@ -147,7 +152,7 @@ class LSTMP(object):
         out = net.ws.get(key + ("out",), rows + B, self.Pp, h.h16)
         sv = net.ws.get(key + ("save",), rows, 5 * Cp, F32)
         dmt = net.ws.get((ctx, "dmt", Cp, B), rows, Cp, F32)
-        dz = net.ws.get((ctx, "dz", Cp, B), rows + B, 4 * Cp, h.h16)
+        dz = net.ws.get(key + ("dz",), rows + B, 4 * Cp, h.h16)       # per layer: the side stream reads it after we return
         dz[rows:].zero_()                                  # dz_{T} = 0 (no step after the last one)
         # dmt = dOut W_proj^T ; the recurrence kernel adds dz_{t+1} Wc^T
         h.gemm(dout16, Wp16, rows, Cp, self.Pp, out32=dmt)
@@ -160,24 +165,24 @@ class LSTMP(object):
         h.lstmp_rec_bwd(B, T, Cp, dmt, self.wc16, P.view(self.prefix + "w_i_diag"),
                         P.view(self.prefix + "w_f_diag"), P.view(self.prefix + "w_o_diag"), lengths, sv,
                         dz, gb, gi, gf, go, work=self.rec_flops(B, T))
+        dx16 = dx32 = None
+        if want_dx:    # the next (earlier) layer waits for this: main stream, before the weight gradients
+            dx16 = net.ws.get(key + ("dx16",), rows, self.Ip, h.h16)
+            dx32 = net.ws.get(key + ("dx32",), rows, self.Ip, F32) if want32 else None
+            h.gemm(dz, Kx16, rows, self.Ip, 4 * Cp, resid=resid32, dact_src=prev_y16, dact=prev_act,
+                   out16=dx16, out32=dx32)
         if want_dw:
-            gK = P.view(self.prefix + "kernel", "grad")
-            # dK = [x_t , m_{t-1}]^T dz_t  (two row blocks of the TF kernel)
-            h.gemm(x16, dz, self.Ip, 4 * Cp, rows, a_mn=True, b_mn=True, beta=1.0, out32=gK[:self.Ip])
-            h.gemm(out, dz, self.Pp, 4 * Cp, rows, a_mn=True, b_mn=True, beta=1.0, out32=gK[self.Ip:])
-            # dW_proj = mt_t^T (dOut_t + dz_{t+1} K_h^T)
-            dmtot = net.ws.get((ctx, "dmtot", self.Pp, B), rows, self.Pp, h.h16)
-            h.gemm(dz[B:], Kh16, rows, self.Pp, 4 * Cp, resid=dout32, out16=dmtot)
-            h.gemm(mt[B:], dmtot, Cp, self.Pp, rows, a_mn=True, b_mn=True, beta=1.0,
-                   out32=P.view(self.prefix + "projection/kernel", "grad"))
-        if not want_dx:
-            return None, None
-        dx16 = net.ws.get(key + ("dx16",), rows, self.Ip, h.h16)
-        dx32 = net.ws.get(key + ("dx32",), rows, self.Ip, F32) if want32 else None
-        h.gemm(dz, Kx16, rows, self.Ip, 4 * Cp, resid=resid32, dact_src=prev_y16, dact=prev_act,
-               out16=dx16, out32=dx32)
+            with h.side_stream():   # weight gradients overlap the next layer's recurrence
+                gK = P.view(self.prefix + "kernel", "grad")
+                # dK = [x_t , m_{t-1}]^T dz_t  (two row blocks of the TF kernel)
+                h.gemm(x16, dz, self.Ip, 4 * Cp, rows, a_mn=True, b_mn=True, beta=1.0, out32=gK[:self.Ip])
+                h.gemm(out, dz, self.Pp, 4 * Cp, rows, a_mn=True, b_mn=True, beta=1.0, out32=gK[self.Ip:])
+                # dW_proj = mt_t^T (dOut_t + dz_{t+1} K_h^T)
+                dmtot = net.ws.get((ctx, "dmtot", self.Pp, B), rows, self.Pp, h.h16)
+                h.gemm(dz[B:], Kh16, rows, self.Pp, 4 * Cp, resid=dout32, out16=dmtot)
+                h.gemm(mt[B:], dmtot, Cp, self.Pp, rows, a_mn=True, b_mn=True, beta=1.0,
+                       out32=P.view(self.prefix + "projection/kernel", "grad"))
         return dx16, dx32
-
 
 class Net(object):
     """Common part: parameter store, workspace, weight-derived operands."""

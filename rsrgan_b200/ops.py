@@ -6,6 +6,7 @@ and returns immediately (asynchronous).  No function has a CPU path.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import torch
@@ -42,6 +43,29 @@ class Handle(object):
         self.num_sms = self.lib.rsr_num_sms(self.h)
         self.launches = 0          # kernels of librsrgan_sm100.so launched so far (bench accounting)
         self.timing = None         # list of (name, start event, end event) while profiling, else None
+        # second stream for work that is independent of the recurrences (which occupy only the SMs of
+        # their clusters): D(real) forward/backward, weight-gradient GEMMs.  `overlap = False` serialises.
+        self.overlap = True
+        self._side = torch.cuda.Stream(device=self.device)
+        self._side_dirty = False
+
+    @contextlib.contextmanager
+    def side_stream(self):
+        """Calls made inside run on the side stream, ordered after everything enqueued so far on the
+        current stream; `join()` makes the current stream wait for them."""
+        if not self.overlap or self.timing is not None:
+            yield
+            return
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            yield
+        self._side_dirty = True
+
+    def join(self):
+        if self._side_dirty:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_dirty = False
 
     def _call(self, name, n_kernels, *args, work=0.0):
         """One C-ABI call on torch's current stream.  With `self.timing` set (bench.py's kernel-share

@@ -9,6 +9,8 @@ gate columns, time-major rows, loss scaling), not the CUDA code.
 """
 from __future__ import annotations
 
+import contextlib
+
 import torch
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_CLIP = 0, 1, 2, 3
@@ -41,6 +43,13 @@ class FakeHandle(object):
         self.launches = 0
 
     def close(self):
+        pass
+
+    @contextlib.contextmanager
+    def side_stream(self):     # no streams on the CPU double: everything is serial
+        yield
+
+    def join(self):
         pass
 
     # ------------------------------------------------------------------ GEMM

@@ -154,3 +154,37 @@ def test_full_size_properties_cfg2():
             n = int(np.prod(s.dev_shape))
             d = flat[s.off:s.off + n]
             assert np.array_equal(params.to_dev_layout(s, params.from_dev_layout(s, d)).reshape(-1), d), s.name
+
+
+@pytest.mark.parametrize("g_type,d_type,kw", [
+    ("lstm", "dnn", dict(g_cell=512, g_proj=256, g_layers=2)),            # cluster kernels + DNN discriminator
+    ("lstm", "lstm", dict(g_cell=256, g_proj=64, g_layers=1, d_cell=256)),  # recurrences on both streams, D input noise
+])
+def test_cuda_graph_and_stream_overlap_match_eager_serial(g_type, d_type, kw):
+    """The captured schedule (CUDA graph, D(real) and weight-gradient GEMMs on the side stream) trains to the
+    same weights as the eager, single-stream schedule: only the order of fp32 atomic accumulation differs."""
+    B, T = 24, 20
+    rng = np.random.default_rng(1)
+    x, y = rng.standard_normal((B, T, 257)).astype(np.float32), rng.standard_normal((B, T, 40)).astype(np.float32)
+    lengths = rng.integers(T // 2, T + 1, size=B)
+    ma = make_model(g_type, d_type, B, init_disc_noise_std=0.0, **kw)
+    mb = make_model(g_type, d_type, B, init_disc_noise_std=0.0, use_graph=False, **kw)
+    mb.h.overlap = False
+    assert ma.use_graph and ma.h.overlap
+    for i in range(5):                                  # calls 1-2 eager (workspace allocation), 3 captures, 4-5 replay
+        oa, ob = ma.train_batch(x, y, lengths), mb.train_batch(x, y, lengths)
+    assert any(st["graph"] is not None for st in ma._graphs.values())
+    for k in ob:
+        assert oa[k] == pytest.approx(ob[k], rel=2e-3, abs=1e-6), k
+    for na, nb in ((ma.G, mb.G), (ma.D, mb.D)):
+        ta, tb = na.P.theta.cpu().numpy(), nb.P.theta.cpu().numpy()
+        assert rms(ta, tb)[1] < 1e-4
+    # a changed by-value scalar (the decayed noise std, train...py:529-533) re-captures instead of replaying stale values
+    n_graphs = len(ma._graphs)
+    ma.disc_noise_std = 0.01 if d_type == "lstm" else 0.0
+    ma.mse_lambda = 5.0
+    mb.mse_lambda = 5.0
+    oa, ob = ma.train_batch(x, y, lengths), mb.train_batch(x, y, lengths)
+    assert len(ma._graphs) == n_graphs + 1
+    if d_type != "lstm":
+        assert oa["g_loss"] == pytest.approx(ob["g_loss"], rel=2e-3)
