@@ -173,6 +173,9 @@ class GAN_RNN(Model):
         self.use_graph = (_arg(args, "use_graph", True) and os.environ.get("RSR_NO_GRAPH", "0") != "1"
                           and dev.type == "cuda")
         self._graphs = {}
+        # With several ranks the schedule runs eagerly: capturing the NCCL all-reduces together with the side
+        # stream hung on 2 x B200 (torch 2.11 / NCCL 2.28.9); RSR_GRAPH_DDP=1 re-enables the attempt.
+        self.graph_ddp = os.environ.get("RSR_GRAPH_DDP", "0") == "1"
         self.g_outputs = None
         self.summaries = None
         self.writer = None
@@ -452,8 +455,8 @@ class GAN_RNN(Model):
         """The per-batch schedule of train_one_iteration (scripts/train_gan_rnn_placeholder.py:72-101):
         disc_updates x D update then gen_updates x G update on the SAME minibatch, which is fed to the
         device once.  Returns the losses of the last D and the last G update."""
-        graphable = (self.use_graph and self.world == 1 and self.h.timing is None and self.D is not None
-                     and isinstance(inputs, (torch.Tensor, np.ndarray)))
+        graphable = (self.use_graph and (self.world == 1 or self.graph_ddp) and self.h.timing is None
+                     and self.D is not None and isinstance(inputs, (torch.Tensor, np.ndarray)))
         if graphable:
             d_vals, g = self._schedule_graphed(inputs, labels, lengths)
         else:
