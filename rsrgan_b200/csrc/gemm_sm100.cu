@@ -33,7 +33,8 @@ struct GemmKParams {
     int M, N, K;
     int bn, stages, a_mn, b_mn, bf;
     int m_tiles, n_tiles, splits, acc_stride, tmem_cols;
-    int st_stride;            // bytes of epilogue staging per warp (fp32 box 4 KB and/or 16-bit box 2 KB)
+    int st_stride;            // bytes of epilogue staging per warp (fp32 box 4 KB and/or 16-bit box 4 KB)
+    int w16;                  // columns per 16-bit store box: 64 (128-byte rows, SW128) or 32 (ragged N; 64-byte rows, SW64)
     int reduce32;             // out32 is accumulated with TMA reduce-add (split-K partials, or beta == 1)
     float alpha, beta;
     const float* bias;
@@ -180,9 +181,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ---------------- epilogue warps ----------------
         const int ew = warp - 2;
         const int q = warp & 3;                                // TMEM lane quadrant this warp may access
-        const int chunk0 = (ew >> 2) * 32;                     // the two warps of a quadrant interleave 32-column chunks
+        const int span = (p.has16 && p.w16 == 64) ? 64 : 32;   // the two warps of a quadrant interleave column spans
         const uint32_t st32 = smem_base + epi_off + (uint32_t)(ew * p.st_stride);     // [32 rows][128 B], SW128
-        const uint32_t st16 = st32 + (p.has32 ? 4096u : 0u);                           // [32 rows][ 64 B], SW64
+        const uint32_t st16 = st32 + (p.has32 ? 4096u : 0u);                           // [32 rows][128 B] SW128 | [32][64 B] SW64
         const uint32_t sw32 = (uint32_t)(lane & 7), sw16 = (uint32_t)((lane >> 1) & 3);
         const bool general_beta = p.has32 && !p.reduce32 && p.beta != 0.0f;
         const bool leader = elect_one_sync();                  // issues (and waits for) this warp's TMA stores
@@ -196,7 +197,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int row0 = m0 + q * 32;
             const int row = row0 + lane;
             const bool row_ok = row < p.M;
-            for (int c0 = chunk0; c0 < p.bn; c0 += 64) {
+            for (int s0 = (ew >> 2) * span; s0 < p.bn; s0 += 2 * span) {
+              bool wrote16 = false;
+              for (int c0 = s0; c0 < s0 + span && c0 < p.bn; c0 += 32) {
                 const int col0 = n0 + c0;
                 if (col0 >= p.N) break;                        // warp-uniform
                 // epilogue operands of this row (independent of the accumulator: issue first)
@@ -233,18 +236,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int c = 0; c < 8; ++c) { v[4 * c] += rs[c].x; v[4 * c + 1] += rs[c].y; v[4 * c + 2] += rs[c].z; v[4 * c + 3] += rs[c].w; }
                 }
-                if (p.act != RSR_ACT_NONE) {
+                // activation / activation-gradient: the selector is hoisted out of the per-element loops
+                if (p.act == RSR_ACT_RELU) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                } else if (p.act == RSR_ACT_LRELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.3f * v[j]);
+                } else if (p.act == RSR_ACT_CLIP) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -0.5f), 1.5f);
                 }
-                if (p.dsrc) {
+                if (p.dsrc && p.dact != RSR_ACT_NONE) {
+                    // relu' / lrelu' from the sign of the stored 16-bit activation OUTPUT (fp16 and bf16 alike:
+                    // y > 0  <=>  sign bit clear and magnitude bits non-zero)
+                    const float neg = p.dact == RSR_ACT_LRELU ? 0.3f : 0.0f;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const uint32_t w[4] = {dq[c].x, dq[c].y, dq[c].z, dq[c].w};
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            v[8 * c + 2 * k] *= act_grad_from_out(h2f((uint16_t)(w[k] & 0xFFFFu), p.bf), p.dact);
-                            v[8 * c + 2 * k + 1] *= act_grad_from_out(h2f((uint16_t)(w[k] >> 16), p.bf), p.dact);
+                            const bool pos_lo = (int16_t)(w[k] & 0xFFFFu) > 0, pos_hi = (int32_t)w[k] >= 0x10000;
+                            v[8 * c + 2 * k] *= pos_lo ? 1.0f : neg;
+                            v[8 * c + 2 * k + 1] *= pos_hi ? 1.0f : neg;
                         }
                     }
                 }
@@ -271,11 +285,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (leader) tma_wait_group_read<0>();
                 __syncwarp();
                 if (p.has16) {
+                    const uint32_t cc0 = (uint32_t)(c0 - s0) >> 3;       // first 16-byte chunk of this half inside the box row
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        st_shared_v4(st16 + (uint32_t)lane * 64u + (((uint32_t)c ^ sw16) << 4),
-                                     pack2(v[8 * c], v[8 * c + 1], p.bf), pack2(v[8 * c + 2], v[8 * c + 3], p.bf),
-                                     pack2(v[8 * c + 4], v[8 * c + 5], p.bf), pack2(v[8 * c + 6], v[8 * c + 7], p.bf));
+                    uint32_t pk[16];
+                    if (p.bf) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+                            pk[k] = *reinterpret_cast<const uint32_t*>(&t);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const __half2 t = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+                            pk[k] = *reinterpret_cast<const uint32_t*>(&t);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t dst = p.w16 == 64 ? st16 + (uint32_t)lane * 128u + (((cc0 + (uint32_t)c) ^ sw32) << 4)
+                                                         : st16 + (uint32_t)lane * 64u + (((uint32_t)c ^ sw16) << 4);
+                        st_shared_v4(dst, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    }
+                    wrote16 = true;
                 }
                 if (p.has32) {
                     if (general_beta) {                        // out32 = v + beta * out32_old  (beta not in {0, 1})
@@ -296,13 +328,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (leader && row0 < p.M) {
-                    if (p.has16) tma_store_2d(&tmC16, st16, col0, row0);
+                    if (p.has16 && p.w16 == 32) tma_store_2d(&tmC16, st16, col0, row0);
                     if (p.has32) {
                         if (p.reduce32) tma_reduce_add_2d(&tmC32, st32, col0, row0);
                         else tma_store_2d(&tmC32, st32, col0, row0);
                     }
                     tma_commit_group();
                 }
+              }
+              if (wrote16 && p.w16 == 64 && leader && row0 < p.M) {   // one 64-column (128-byte rows) box per span
+                  tma_store_2d(&tmC16, st16, n0 + s0, row0);
+                  tma_commit_group();
+              }
             }
             tc_fence_before();
             __syncwarp();
@@ -425,7 +462,7 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     p.dsrc = (const uint16_t*)a->dact_src; p.ldd = a->ldd; p.dact = a->dact;
     p.out32 = a->out32; p.ldc32 = a->ldc32; p.out16 = (uint16_t*)a->out16; p.ldc16 = a->ldc16;
     p.has32 = a->out32 ? 1 : 0; p.has16 = a->out16 ? 1 : 0;
-    p.st_stride = (p.has32 ? 4096 : 0) + (p.has16 ? 2048 : 0);
+    p.st_stride = (p.has32 ? 4096 : 0) + (p.has16 ? 4096 : 0);
     p.m_tiles = m_tiles;
     p.n_tiles = (a->N + bn - 1) / bn;
 
@@ -452,6 +489,9 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     // accumulated fp32 outputs (out32 += ..., i.e. beta == 1, and all split-K partials) leave through TMA reduce-add
     p.reduce32 = (a->out32 && (splits > 1 || a->beta == 1.0f)) ? 1 : 0;
     if (p.n_tiles > 1 && (bn & 31)) return RSR_E_SHAPE;   // a 32-column store box must not reach into the next tile
+    // 16-bit outputs leave in 64-column boxes (128-byte rows: 64-byte rows reach only a fraction of the TMA store
+    // rate) unless N is ragged against the 16-byte store granule or a box would reach into the next tile
+    p.w16 = (a->out16 && (a->N & 7) == 0 && (p.n_tiles == 1 || (bn & 63) == 0)) ? 64 : 32;
     const int fixed = 1024 /*align slack*/ + EPI_WARPS * p.st_stride + 64 + 16 * 8;
     int stages = (h->max_smem - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
@@ -483,7 +523,8 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
         if (rc) return rc;
     }
     if (a->out16) {
-        rc = rsr_get_tmap_ex(h, a->out16, 2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc16, 32, 32, 64, &tmC16);
+        rc = rsr_get_tmap_ex(h, a->out16, 2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc16, (uint32_t)p.w16, 32,
+                             p.w16 == 64 ? 128 : 64, &tmC16);
         if (rc) return rc;
     }
 
