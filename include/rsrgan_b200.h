@@ -113,8 +113,21 @@ int rsr_cmvn_invert(rsr_handle* h, void* stream, const float* y, const float* me
 int rsr_lstmp_rec_fwd(rsr_handle* h, void* stream, int B, int T, int Cp, const float* zx,
                       const void* wcT, const float* w_i, const float* w_f, const float* w_o,
                       float forget_bias, const int* lengths, void* mt_seq, float* save);
-/*   dmt     fp32 [T*B, Cp]    on entry dOut_t * W_proj^T (from rsr_gemm); the kernel adds the
- *                              recurrent term dz_{t+1} * Wc^T in place (atomics), time-reversed
+/* Fully fused LSTMP forward -- "the LSTM cell's gate GEMMs in one tcgen05 tile with the sigmoid/tanh/
+ * elementwise epilogue in registers": z_t = x_t K_x + b + mt_{t-1} Wc computed entirely inside the persistent
+ * cluster kernel (K_x^T and Wc^T slices resident in TMEM as the MMA A operand, x_t tiles prefetched by TMA),
+ * no Zx round trip through HBM.  Same outputs as rsr_gemm(Zx) + rsr_lstmp_rec_fwd.
+ *   x16     h16  [T*B, ldx]   layer input, time-major, zero padded to ldx (multiple of 8) columns
+ *   kxT     h16  [4Cp, Ik]    K_x^T, packed gate rows, Ik = I rounded up to 16, zero padded
+ *   bias    fp32 [4Cp]        packed
+ * Returns RSR_E_RESIDENT (nothing launched) when the variant does not apply -- Cp > 512 or K_x^T does not fit
+ * in TMEM beside Wc^T; the caller then falls back to rsr_gemm + rsr_lstmp_rec_fwd. */
+int rsr_lstmp_fused_fwd(rsr_handle* h, void* stream, int B, int T, int I, int Cp, const void* x16, int ldx,
+                        const void* kxT, const float* bias, const void* wcT, const float* w_i,
+                        const float* w_f, const float* w_o, float forget_bias, const int* lengths,
+                        void* mt_seq, float* save);
+/*   dmt     fp32 [T*B, Cp]    dOut_t * W_proj^T (from rsr_gemm); read only on the cluster path (Cp <= 512), the
+ *                              L2-exchange path (Cp > 512) adds the recurrent term dz_{t+1} * Wc^T in place
  *   wc      h16  [Cp, 4Cp]    Wc, packed columns (backward MMA A operand)
  *   dz16    h16  [T*B, 4Cp]   gate pre-activation gradients, packed columns (output)
  *   dbias   fp32 [4Cp] packed, dw_i, dw_f, dw_o fp32 [Cp]: ACCUMULATED into (caller zeroes)
@@ -185,6 +198,10 @@ int rsr_add_cast(rsr_handle* h, void* stream, const float* a, const float* b, lo
                  float* out32, void* out16);
 
 /* misc ---------------------------------------------------------------------------------- */
+/* dst[c, r] = src[r, c] for r < rows, c < cols (16-bit elements; other elements of dst untouched):
+ * keeps the K_x^T operand of rsr_lstmp_fused_fwd in step with the updated weights. */
+int rsr_transpose16(rsr_handle* h, void* stream, const void* src, int ld_src, int rows, int cols, void* dst,
+                    int ld_dst);
 int rsr_cast16(rsr_handle* h, void* stream, const float* x, long long n, void* out16);
 int rsr_fill32(rsr_handle* h, void* stream, float* x, long long n, float v);
 

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "librsrgan_sm100.so")
 
 RSR_DTYPE_F16, RSR_DTYPE_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_CLIP = 0, 1, 2, 3
+RSR_E_RESIDENT = -4
 ERRORS = {-1: "RSR_E_ARG", -2: "RSR_E_SHAPE", -3: "RSR_E_NODEV", -4: "RSR_E_RESIDENT"}
 
 vp, ci, cf, cll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
@@ -44,6 +45,8 @@ SIGNATURES = {
     "rsr_cmvn_apply": [vp, vp, vp, vp, vp, cll, ci, vp],
     "rsr_cmvn_invert": [vp, vp, vp, vp, vp, cll, ci, vp],
     "rsr_lstmp_rec_fwd": [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, cf, vp, vp, vp],
+    "rsr_lstmp_fused_fwd": [vp, vp, ci, ci, ci, ci, vp, ci, vp, vp, vp, vp, vp, vp, cf, vp, vp, vp],
+    "rsr_transpose16": [vp, vp, vp, ci, ci, ci, vp, ci],
     "rsr_lstmp_rec_bwd": [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "rsr_lsgan_mse_losses": [vp, vp, vp, vp, ci, cll, ci, vp, ci, vp, ci, cll, ci, cf, cf, cf, cf,
                              vp, vp, vp, vp, ci, vp, ci],

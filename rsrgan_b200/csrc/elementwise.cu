@@ -164,6 +164,18 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
     }
 }
 
+__global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __restrict__ src, int ld_src, int rows, int cols,
+                                                          uint16_t* __restrict__ dst, int ld_dst) {
+    __shared__ uint16_t tile[32][34];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int i = ty; i < 32; i += 8)
+        tile[i][tx] = (r0 + i < rows && c0 + tx < cols) ? src[(size_t)(r0 + i) * ld_src + c0 + tx] : (uint16_t)0;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < cols && r0 + tx < rows) dst[(size_t)(c0 + i) * ld_dst + r0 + tx] = tile[tx][i];
+}
+
 __global__ void fill32_kernel(float* x, long long n, float v) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = v;
 }
@@ -415,6 +427,15 @@ extern "C" int rsr_l2_grad(rsr_handle* h, void* stream, float* grad, const float
                            const int* seg_flag, float scale, long long n_elems) {
     if (!h || !grad || !theta || !seg_id || !seg_flag || n_elems <= 0 || (n_elems & 1023)) return RSR_E_ARG;
     l2_grad_kernel<<<(unsigned)(n_elems / 1024), 256, 0, (cudaStream_t)stream>>>(grad, theta, seg_id, seg_flag, scale);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_transpose16(rsr_handle* h, void* stream, const void* src, int ld_src, int rows, int cols, void* dst,
+                               int ld_dst) {
+    if (!h || !src || !dst || rows <= 0 || cols <= 0 || ld_src < cols || ld_dst < rows) return RSR_E_ARG;
+    transpose16_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+        (const uint16_t*)src, ld_src, rows, cols, (uint16_t*)dst, ld_dst);
     RSR_LAUNCH_CHECK();
     return 0;
 }

@@ -46,7 +46,8 @@ struct rsr_handle {
     unsigned int* flags = nullptr;   // device: group-barrier counters, RSR_FLAG_WORDS words
     int flag_cursor = 0;
     // co-resident clusters of the cluster recurrence kernels: [fwd|bwd][Cp/256 - 1][NB 16|32]; -1 = not queried yet
-    int cluster_cap[2][2][2] = {{{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}};
+    int fused_ik[2] = {-1, -1};      // Ik the fused-forward capacity entry was computed for
+    int cluster_cap[3][2][2] = {{{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}};   // [2] = fused fwd
 };
 
 #define RSR_FLAG_WORDS 4096
@@ -70,6 +71,10 @@ int rsr_get_tmap_ex(rsr_handle* h, const void* ptr, int elem_bytes, uint64_t d0,
 int rsr_lstmp_fwd_cluster(rsr_handle* h, void* stream, int B, int T, int Cp, const float* zx, const void* wcT,
                           const float* w_i, const float* w_f, const float* w_o, float forget_bias,
                           const int* lengths, void* mt_seq, float* save);
+int rsr_lstmp_fused_fwd_cluster(rsr_handle* h, void* stream, int B, int T, int I, int Cp, const void* x16, int ldx,
+                                const void* kxT, const float* bias, const void* wcT, const float* w_i,
+                                const float* w_f, const float* w_o, float forget_bias, const int* lengths,
+                                void* mt_seq, float* save);
 int rsr_lstmp_bwd_cluster(rsr_handle* h, void* stream, int B, int T, int Cp, const float* dmt, const void* wc,
                           const float* w_i, const float* w_f, const float* w_o, const int* lengths,
                           const float* save, void* dz16, float* dbias, float* dw_i, float* dw_f, float* dw_o);

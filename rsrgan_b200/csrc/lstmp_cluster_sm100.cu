@@ -55,15 +55,22 @@ struct CFwdParams {
     const int* lengths;         // [B]
     uint16_t* mt_seq;           // [(T+1)*B, Cp]
     float* save;                // [T*B, 5, Cp] or null
+    // fused input half (FUSEX): z_t = x_t K_x + b + mt_{t-1} Wc entirely in this kernel
+    const uint16_t* kxT;        // [4Cp, Ik] packed gate rows of K_x^T, Ik = input width padded to 16, zero padded
+    const float* bias;          // [4Cp] packed
+    int Ik;
 };
 
 // One cluster = one utterance group of NHALF x 16 utterances; CTA j owns cells [32j, 32j+32).  The CTA's
 // 128 gate rows of Wc^T live in TMEM (A operand) for the whole sequence.  Each HALF is an independent
 // recurrence over 16 utterances run by its own 4 warps (own accumulator, buffers, barriers); two halves
 // share the resident weights and overlap each other's DSMEM exchange with MMA + gate math.
-template <int NHALF>
+// FUSEX: the input half x_t K_x is computed here too (K_x^T slice resident in TMEM next to Wc^T, x_t tiles
+// prefetched by TMA one step ahead, its MMAs issued BEFORE the wait for mt_{t-1} so they hide behind the
+// exchange); otherwise Zx = X K_x + b arrives precomputed (fp32, from rsr_gemm).
+template <int NHALF, bool FUSEX>
 __global__ void __launch_bounds__(128 * NHALF, 1)
-lstmp_fwd_cluster_kernel(const CFwdParams p) {
+lstmp_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const CFwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -78,21 +85,27 @@ lstmp_fwd_cluster_kernel(const CFwdParams p) {
 
     constexpr int XP = NB + 1;                                       // xchg pitch in floats
     const uint32_t sB_bytes = (uint32_t)p.Cp * NB * 2u;              // one B-operand buffer [Cp/8][NB][8] 16-bit
-    const uint32_t half_bytes = 2u * sB_bytes + 2u * 128u * XP * 4u; // per half: two B buffers + two xchg buffers
-    const uint32_t sB0 = base + (uint32_t)hh * half_bytes;
+    const int KBX = FUSEX ? (p.Ik + 63) / 64 : 0;                   // 64-wide k sub-tiles of the x_t tile
+    const uint32_t xt_bytes = (uint32_t)KBX * NB * 128u;             // one x_t tile: KBX x [NB x 64] 16-bit, SW128
+    const uint32_t half_bytes = 2u * xt_bytes + 2u * sB_bytes + 2u * 128u * XP * 4u;   // x tiles (1024-aligned) | B buffers | xchg
+    const uint32_t sXt0 = base + (uint32_t)hh * half_bytes;
+    const uint32_t sB0 = sXt0 + 2u * xt_bytes;
     const uint32_t sX = sB0 + 2u * sB_bytes;                         // float xchg[2][128][XP]
-    const uint32_t sBar = base + (uint32_t)NHALF * half_bytes + (uint32_t)hh * 32u;
-    const uint32_t barM = sBar, full0 = sBar + 8, full1 = sBar + 16;
-    const uint32_t tslot = base + (uint32_t)NHALF * half_bytes + (uint32_t)NHALF * 32u;
+    const uint32_t sBar = base + (uint32_t)NHALF * half_bytes + (uint32_t)hh * 64u;
+    const uint32_t barM = sBar, full0 = sBar + 8, full1 = sBar + 16, xfull0 = sBar + 24, xfull1 = sBar + 32;
+    const uint32_t tslot = base + (uint32_t)NHALF * half_bytes + (uint32_t)NHALF * 64u;
     float* xchg = reinterpret_cast<float*>(base_ptr + (sX - base));
 
     // TMEM: columns [0, Cp/2) = this CTA's 128 gate rows of Wc^T (A operand, 2 x 16 bit per column),
     //       columns [Cp/2 + 16 hh, +16) = accumulator of half hh
-    const uint32_t a_cols = (uint32_t)p.Cp / 2u;
+    //       (FUSEX: K_x^T slice in columns [Cp/2, Cp/2 + Ik/2) in between)
+    const uint32_t ax_cols = FUSEX ? (uint32_t)p.Ik / 2u : 0u;
+    const uint32_t a_cols = (uint32_t)p.Cp / 2u + ax_cols;
     uint32_t tcols = 32;
     while (tcols < a_cols + NB * NHALF) tcols <<= 1;
     if (htid == 0) {
-        mbar_init(barM, 1); mbar_init(full0, 1); mbar_init(full1, 1);
+        if (FUSEX) tma_prefetch_desc(&tmX);
+        mbar_init(barM, 1); mbar_init(full0, 1); mbar_init(full1, 1); mbar_init(xfull0, 1); mbar_init(xfull1, 1);
         fence_mbar_init();
         mbar_expect_tx(full1, sB_bytes);        // armed for step 1 (mt_0 of every CTA of the cluster)
         mbar_expect_tx(full0, sB_bytes);        // armed for step 2
@@ -117,6 +130,15 @@ lstmp_fwd_cluster_kernel(const CFwdParams p) {
                 r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
             }
             tmem_st32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cb * 32u, r);
+        }
+        if (FUSEX) {   // K_x^T slice, 16 k (8 columns) per store; rows are zero padded to Ik
+            const uint16_t* xrow = p.kxT + (size_t)(128 * j + 32 * q + lane) * p.Ik;
+            for (int cb = hh; cb < p.Ik / 16; cb += NHALF) {
+                const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(xrow + cb * 16));
+                const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(xrow + cb * 16) + 1);
+                tmem_st8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)p.Cp / 2u + (uint32_t)cb * 8u,
+                         v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w);
+            }
         }
         tmem_st_wait();
     }
@@ -144,30 +166,58 @@ lstmp_fwd_cluster_kernel(const CFwdParams p) {
     const uint32_t idesc = umma_idesc(128, NB, p.bf, 0, 0);
     const size_t zx_ld = (size_t)4 * p.Cp;
     const int grow = 32 * q + lane;             // gate row of this thread in the tile (TMEM lane)
-    const float* zx_col = p.zx + 128 * j + grow;
-    float zx_cur[NB], zx_nxt[NB];
+    const float* zx_col = FUSEX ? nullptr : p.zx + 128 * j + grow;
+    const float bias_r = FUSEX ? __ldg(p.bias + 128 * j + grow) : 0.f;
+    constexpr int NZ = FUSEX ? 1 : NB;
+    float zx_cur[NZ], zx_nxt[NZ];
 #pragma unroll
-    for (int n = 0; n < NB; ++n) {
+    for (int n = 0; n < NZ; ++n) {
         const int b = b0 + n;
-        zx_cur[n] = b < p.B ? __ldg(zx_col + (size_t)b * zx_ld) : 0.f;
+        zx_cur[n] = (!FUSEX && b < p.B) ? __ldg(zx_col + (size_t)b * zx_ld) : 0.f;
         zx_nxt[n] = 0.f;
     }
     const uint64_t db_base = umma_desc_nosw(sB0, NB * 16u, 128u);
     const int KK = p.Cp / 16;
+    const int KKX = FUSEX ? p.Ik / 16 : 0;
     const uint32_t bar_id = 1u + (uint32_t)hh;
+    if (FUSEX && q == 0 && elect_one_sync()) {   // x_0 tile
+        mbar_expect_tx(xfull0, xt_bytes);
+        for (int kb = 0; kb < KBX; ++kb) tma_load_2d(sXt0 + (uint32_t)kb * (NB * 128u), &tmX, xfull0, kb * 64, b0);
+    }
 
     for (int t = 0; t < p.T; ++t) {
         const int buf = t & 1;
         TRACE(0);
-        if (t + 1 < p.T) {   // Zx of the next step does not depend on the recurrence: in flight during this step
+        if (!FUSEX && t + 1 < p.T) {   // Zx of the next step does not depend on the recurrence: in flight during this step
 #pragma unroll
-            for (int n = 0; n < NB; ++n) {
+            for (int n = 0; n < NZ; ++n) {
                 const int b = b0 + n;
                 zx_nxt[n] = b < p.B ? __ldg(zx_col + ((size_t)(t + 1) * p.B + b) * zx_ld) : 0.f;
             }
         }
         if (q == 0) {   // first warp of the half, warp-uniform: the elected lane issues, operands stay in uniform registers
             const uint32_t fb = buf ? full1 : full0;
+            if (FUSEX) {
+                // input half first: it does not depend on mt_{t-1}, so it runs while the exchange is still in flight
+                const uint32_t xb = buf ? xfull1 : xfull0;
+                if (elect_one_sync()) {
+                    if (t + 1 < p.T) {   // prefetch x_{t+1}; its buffer was last read by the MMAs of step t-1 (retired: barM)
+                        const uint32_t xn = buf ? xfull0 : xfull1;
+                        const uint32_t dstx = sXt0 + (uint32_t)(buf ^ 1) * xt_bytes;
+                        mbar_expect_tx(xn, xt_bytes);
+                        for (int kb = 0; kb < KBX; ++kb)
+                            tma_load_2d(dstx + (uint32_t)kb * (NB * 128u), &tmX, xn, kb * 64, (t + 1) * p.B + b0);
+                    }
+                    mbar_wait(xb, (uint32_t)((t >> 1) & 1));
+                    tc_fence_after();
+                    const uint32_t sxt = sXt0 + (uint32_t)buf * xt_bytes;
+                    for (int kk = 0; kk < KKX; ++kk) {
+                        const uint64_t dx = umma_desc_sw128(sxt + (uint32_t)(kk >> 2) * (NB * 128u) + (uint32_t)(kk & 3) * 32u, 16, 1024);
+                        tc_mma_f16_ts(tmem_acc, tmem + (uint32_t)p.Cp / 2u + (uint32_t)kk * 8u, dx, idesc, kk ? 1u : 0u);
+                    }
+                }
+                __syncwarp();
+            }
             if (t > 0) mbar_wait(fb, (uint32_t)(((t - 1) >> 1) & 1));     // all G slices of mt_{t-1} have landed
             TRACE(1);
             fence_proxy_async_smem();
@@ -177,7 +227,7 @@ lstmp_fwd_cluster_kernel(const CFwdParams p) {
                 uint32_t ta = tmem;
 #pragma unroll 8
                 for (int kk = 0; kk < KK; ++kk) {
-                    tc_mma_f16_ts(tmem_acc, ta, db, idesc, kk ? 1u : 0u);
+                    tc_mma_f16_ts(tmem_acc, ta, db, idesc, (FUSEX || kk) ? 1u : 0u);
                     ta += 8u;                               // 16 k = 8 columns
                     db += (uint64_t)((2u * NB * 16u) >> 4); // two k-chunks of [NB rows][16 B]
                 }
@@ -194,7 +244,7 @@ lstmp_fwd_cluster_kernel(const CFwdParams p) {
         tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16), acc);
         float* xc = xchg + buf * 128 * XP;          // quadrant q holds gate q (i, j, f, o) of cells 32j + lane
 #pragma unroll
-        for (int n = 0; n < NB; ++n) xc[grow * XP + n] = acc[n] + zx_cur[n];
+        for (int n = 0; n < NB; ++n) xc[grow * XP + n] = acc[n] + (FUSEX ? bias_r : zx_cur[FUSEX ? 0 : n]);
         tc_fence_before();
         named_bar_sync(bar_id, 128);
         TRACE(4);
@@ -246,7 +296,7 @@ lstmp_fwd_cluster_kernel(const CFwdParams p) {
         }
         TRACE(5);
 #pragma unroll
-        for (int n = 0; n < NB; ++n) zx_cur[n] = zx_nxt[n];
+        for (int n = 0; n < NZ; ++n) zx_cur[n] = zx_nxt[n];
     }
     tc_fence_before();
     __syncthreads();
@@ -461,8 +511,9 @@ lstmp_bwd_cluster_kernel(const CBwdParams p) {
     cluster_sync_all();
 }
 
-size_t cfwd_smem(int Cp, int nhalf) {
-    const size_t need = 1024 + (size_t)nhalf * (2 * (size_t)Cp * NB * 2 + 2 * 128 * (size_t)(NB + 1) * 4) + (size_t)nhalf * 32 + 64;
+size_t cfwd_smem(int Cp, int nhalf, int Ik = 0) {
+    const size_t xt = (size_t)((Ik + 63) / 64) * NB * 128;
+    const size_t need = 1024 + (size_t)nhalf * (2 * xt + 2 * (size_t)Cp * NB * 2 + 2 * 128 * (size_t)(NB + 1) * 4) + (size_t)nhalf * 64 + 64;
     return need < RSR_EXCLUSIVE_SMEM_REC ? RSR_EXCLUSIVE_SMEM_REC : need;
 }
 size_t cbwd_smem(int Cp, int nhalf) {
@@ -489,8 +540,8 @@ int cluster_capacity(K kernel, int G, int threads, size_t smem) {
     return n;
 }
 
-template <typename K, typename P>
-int cluster_launch(K kernel, int groups, int G, int threads, size_t smem, cudaStream_t stream, const P& p) {
+template <typename K, typename... Args>
+int cluster_launch(K kernel, int groups, int G, int threads, size_t smem, cudaStream_t stream, const Args&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(groups * G, 1, 1);
     cfg.blockDim = dim3(threads, 1, 1);
@@ -500,7 +551,7 @@ int cluster_launch(K kernel, int groups, int G, int threads, size_t smem, cudaSt
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
     if (e != cudaSuccess) return (int)e;
     return 0;
 }
@@ -517,7 +568,7 @@ int pick_cluster_halves(rsr_handle* h, int which, K1 k1, K2 k2, int B, int Cp, s
         cap[1] = s2 <= (size_t)h->max_smem ? cluster_capacity(k2, G, 256, s2) : 0;
         if (getenv("RSR_DEBUG"))
             fprintf(stderr, "[rsr] %s cluster kernel Cp=%d: %d-CTA clusters co-resident: 1 half %d, 2 halves %d\n",
-                    which ? "bwd" : "fwd", Cp, G, cap[0], cap[1]);
+                    which == 1 ? "bwd" : which == 2 ? "fused fwd" : "fwd", Cp, G, cap[0], cap[1]);
     }
     const int g1 = (B + NB - 1) / NB;
     if (cap[0] > 0 && (g1 <= cap[0] || cap[1] <= 0)) return 1;
@@ -535,16 +586,46 @@ int rsr_lstmp_fwd_cluster(rsr_handle* h, void* stream, int B, int T, int Cp, con
     if (Cp > 512) return RSR_E_RESIDENT;
     const int G = Cp / 32;
     const size_t s1 = cfwd_smem(Cp, 1), s2 = cfwd_smem(Cp, 2);
-    const int nh = pick_cluster_halves(h, 0, lstmp_fwd_cluster_kernel<1>, lstmp_fwd_cluster_kernel<2>, B, Cp, s1, s2);
+    const int nh = pick_cluster_halves(h, 0, lstmp_fwd_cluster_kernel<1, false>, lstmp_fwd_cluster_kernel<2, false>, B, Cp, s1, s2);
     if (!nh) return RSR_E_RESIDENT;
     const int groups = (B + NB * nh - 1) / (NB * nh);
     CFwdParams p;
+    CUtensorMap tmX = {};   // unused by the unfused variant
+    p.kxT = nullptr; p.bias = nullptr; p.Ik = 0;
     p.wcT = (const uint16_t*)wcT;
     p.B = B; p.T = T; p.Cp = Cp; p.bf = h->dtype == RSR_DTYPE_BF16; p.forget_bias = forget_bias;
     p.zx = zx; p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths;
     p.mt_seq = (uint16_t*)mt_seq; p.save = save;
-    if (nh == 1) return cluster_launch(lstmp_fwd_cluster_kernel<1>, groups, G, 128, s1, (cudaStream_t)stream, p);
-    return cluster_launch(lstmp_fwd_cluster_kernel<2>, groups, G, 256, s2, (cudaStream_t)stream, p);
+    if (nh == 1) return cluster_launch(lstmp_fwd_cluster_kernel<1, false>, groups, G, 128, s1, (cudaStream_t)stream, tmX, p);
+    return cluster_launch(lstmp_fwd_cluster_kernel<2, false>, groups, G, 256, s2, (cudaStream_t)stream, tmX, p);
+}
+
+// Fully fused forward: input GEMM + recurrent GEMM + gate epilogue.  RSR_E_RESIDENT when K_x^T does not fit in
+// TMEM next to Wc^T (caller then runs rsr_gemm for Zx and the unfused kernel).
+int rsr_lstmp_fused_fwd_cluster(rsr_handle* h, void* stream, int B, int T, int I, int Cp, const void* x16, int ldx,
+                                const void* kxT, const float* bias, const void* wcT, const float* w_i,
+                                const float* w_f, const float* w_o, float forget_bias, const int* lengths,
+                                void* mt_seq, float* save) {
+    if (Cp > 512) return RSR_E_RESIDENT;
+    const int Ik = (I + 15) & ~15;
+    if (Cp / 2 + Ik / 2 + 2 * NB > 512) return RSR_E_RESIDENT;
+    const int G = Cp / 32;
+    const size_t s1 = cfwd_smem(Cp, 1, Ik), s2 = cfwd_smem(Cp, 2, Ik);
+    // capacity is cached per Cp for the fused variant too (its shared memory grows with Ik: re-query when it changes)
+    if (h->fused_ik[Cp / 256 - 1] != Ik) { h->cluster_cap[2][Cp / 256 - 1][0] = h->cluster_cap[2][Cp / 256 - 1][1] = -1; h->fused_ik[Cp / 256 - 1] = Ik; }
+    const int nh = pick_cluster_halves(h, 2, lstmp_fwd_cluster_kernel<1, true>, lstmp_fwd_cluster_kernel<2, true>, B, Cp, s1, s2);
+    if (!nh) return RSR_E_RESIDENT;
+    const int groups = (B + NB * nh - 1) / (NB * nh);
+    CUtensorMap tmX;
+    int rc = rsr_get_tmap(h, x16, (uint64_t)ldx, (uint64_t)T * B, (uint64_t)ldx, 64, NB, &tmX);
+    if (rc) return rc;
+    CFwdParams p;
+    p.B = B; p.T = T; p.Cp = Cp; p.bf = h->dtype == RSR_DTYPE_BF16; p.forget_bias = forget_bias;
+    p.zx = nullptr; p.wcT = (const uint16_t*)wcT; p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths;
+    p.mt_seq = (uint16_t*)mt_seq; p.save = save;
+    p.kxT = (const uint16_t*)kxT; p.bias = bias; p.Ik = Ik;
+    if (nh == 1) return cluster_launch(lstmp_fwd_cluster_kernel<1, true>, groups, G, 128, s1, (cudaStream_t)stream, tmX, p);
+    return cluster_launch(lstmp_fwd_cluster_kernel<2, true>, groups, G, 256, s2, (cudaStream_t)stream, tmX, p);
 }
 
 int rsr_lstmp_bwd_cluster(rsr_handle* h, void* stream, int B, int T, int Cp, const float* dmt, const void* wc,

@@ -419,6 +419,20 @@ extern "C" int rsr_lstmp_rec_fwd(rsr_handle* h, void* stream, int B, int T, int 
     return 0;
 }
 
+extern "C" int rsr_lstmp_fused_fwd(rsr_handle* h, void* stream, int B, int T, int I, int Cp, const void* x16, int ldx,
+                                   const void* kxT, const float* bias, const void* wcT, const float* w_i,
+                                   const float* w_f, const float* w_o, float forget_bias, const int* lengths,
+                                   void* mt_seq, float* save) {
+    if (!h || !x16 || !kxT || !bias || !wcT || !w_i || !w_f || !w_o || !lengths || !mt_seq) return RSR_E_ARG;
+    if (B <= 0 || T <= 0 || I <= 0 || Cp <= 0 || (Cp & 255) || ldx < I || (ldx & 7)) return RSR_E_SHAPE;
+    if (((uintptr_t)x16 | (uintptr_t)kxT | (uintptr_t)wcT | (uintptr_t)w_i | (uintptr_t)w_f | (uintptr_t)w_o |
+         (uintptr_t)mt_seq | (uintptr_t)save) & 15)
+        return RSR_E_ARG;
+    if (getenv("RSR_NO_CLUSTER") || getenv("RSR_NO_FUSEX")) return RSR_E_RESIDENT;
+    return rsr_lstmp_fused_fwd_cluster(h, stream, B, T, I, Cp, x16, ldx, kxT, bias, wcT, w_i, w_f, w_o, forget_bias,
+                                       lengths, mt_seq, save);
+}
+
 extern "C" int rsr_lstmp_rec_bwd(rsr_handle* h, void* stream, int B, int T, int Cp, float* dmt,
                                  const void* wc, const float* w_i, const float* w_f, const float* w_o,
                                  const int* lengths, const float* save, void* dz16,

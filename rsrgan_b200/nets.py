@@ -96,6 +96,9 @@ class LSTMP(object):
         self.wc16 = torch.zeros(self.Cp, 4 * self.Cp, dtype=h.h16, device=h.device)    # Wc   (backward operand)
         self.wcT16 = torch.zeros(4 * self.Cp, self.Cp, dtype=h.h16, device=h.device)   # Wc^T (forward operand)
         self.scratch = torch.zeros(7 * self.Cp, dtype=F32, device=h.device)            # sink for unwanted db/dw
+        self.Ik = packing.round_up(I, 16)
+        self.kxT16 = torch.zeros(4 * self.Cp, self.Ik, dtype=h.h16, device=h.device)   # K_x^T (fused forward operand)
+        self.fused = True            # cleared the first time the library says the fused variant does not apply
         if self.Cp > 512 and hasattr(h, "overlap"):
             # L2-exchange recurrence kernels (Cp > 512) spin on counters of co-resident CTAs: nothing else
             # may take SMs while they run, so the side stream is switched off for this model
@@ -121,6 +124,9 @@ class LSTMP(object):
         _, Kh16, Wp16 = self._w()
         h.gemm(Wp16, Kh16, self.Cp, 4 * self.Cp, self.Pp, b_mn=True, out16=self.wc16)
         h.gemm(Kh16, Wp16, 4 * self.Cp, self.Cp, self.Pp, a_mn=True, out16=self.wcT16)
+        if self.fused:
+            Kx16 = self._w()[0]
+            h.transpose16(Kx16, self.Ip, 4 * self.Cp, self.kxT16)
 
     def fwd(self, ctx, x16, B, T, lengths, save=True, want32=False):
         """x16 [T*B, Ip] -> out_seq16 [(T+1)*B, Pp] (slot 0 = zero initial state; rows B.. are
@@ -129,15 +135,22 @@ class LSTMP(object):
         rows, Cp = T * B, self.Cp
         key = (ctx, self.prefix, B)
         Kx16, _, Wp16 = self._w()
-        zx = net.ws.get((ctx, "zx", Cp, B), rows, 4 * Cp, F32)            # shared by layers of equal width
         mt = net.ws.get(key + ("mt",), rows + B, Cp, h.h16)
         out = net.ws.get(key + ("out",), rows + B, self.Pp, h.h16)
         sv = net.ws.get(key + ("save",), rows, 5 * Cp, F32) if save else None
         o32 = net.ws.get(key + ("o32",), rows, self.Pp, F32) if want32 else None
-        h.gemm(x16, Kx16, rows, 4 * Cp, self.Ip, b_mn=True, bias=P.view(self.prefix + "bias"), out32=zx)
-        h.lstmp_rec_fwd(B, T, Cp, zx, self.wcT16, P.view(self.prefix + "w_i_diag"),
-                        P.view(self.prefix + "w_f_diag"), P.view(self.prefix + "w_o_diag"), lengths, mt, sv,
-                        work=self.rec_flops(B, T))
+        peep = (P.view(self.prefix + "w_i_diag"), P.view(self.prefix + "w_f_diag"), P.view(self.prefix + "w_o_diag"))
+        done = False
+        if self.fused:   # input GEMM + recurrent GEMM + gate epilogue in one kernel, no Zx round trip through HBM
+            done = h.lstmp_fused_fwd(B, T, self.I, Cp, x16, self.kxT16, P.view(self.prefix + "bias"), self.wcT16,
+                                     peep[0], peep[1], peep[2], lengths, mt, sv,
+                                     work=self.rec_flops(B, T) + 2.0 * rows * self.I * 4 * self.C)
+            self.fused = done
+        if not done:
+            zx = net.ws.get((ctx, "zx", Cp, B), rows, 4 * Cp, F32)        # shared by layers of equal width
+            h.gemm(x16, Kx16, rows, 4 * Cp, self.Ip, b_mn=True, bias=P.view(self.prefix + "bias"), out32=zx)
+            h.lstmp_rec_fwd(B, T, Cp, zx, self.wcT16, peep[0], peep[1], peep[2], lengths, mt, sv,
+                            work=self.rec_flops(B, T))
         h.gemm(mt[B:], Wp16, rows, self.Pp, Cp, b_mn=True, out16=out[B:], out32=o32)
         return out, o32
 

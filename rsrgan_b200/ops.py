@@ -143,6 +143,30 @@ class Handle(object):
         self._call("rsr_lstmp_rec_fwd", 1, self.h, _stream(), B, T, Cp, _p(zx), _p(wcT), _p(w_i), _p(w_f),
                                          _p(w_o), forget_bias, _p(lengths), _p(mt_seq), _p(save), work=work)
 
+    def lstmp_fused_fwd(self, B, T, I, Cp, x16, kxT, bias, wcT, w_i, w_f, w_o, lengths, mt_seq, save,
+                        forget_bias=1.0, work=0.0):
+        """Returns False (nothing launched) when the fused variant does not apply to this shape."""
+        fn = self.lib.rsr_lstmp_fused_fwd
+        args = (self.h, _stream(), B, T, I, Cp, _p(x16), x16.stride(0), _p(kxT), _p(bias), _p(wcT), _p(w_i), _p(w_f),
+                _p(w_o), forget_bias, _p(lengths), _p(mt_seq), _p(save))
+        if self.timing is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            if rc == 0:
+                self.timing.append(("rsr_lstmp_fused_fwd", e0, e1, work))
+        else:
+            rc = fn(*args)
+        if rc == _lib.RSR_E_RESIDENT:
+            return False
+        check(rc, "rsr_lstmp_fused_fwd")
+        self.launches += 1
+        return True
+
+    def transpose16(self, src, rows, cols, dst):
+        self._call("rsr_transpose16", 1, self.h, _stream(), _p(src), src.stride(0), rows, cols, _p(dst), dst.stride(0))
+
     def lstmp_rec_bwd(self, B, T, Cp, dmt, wc, w_i, w_f, w_o, lengths, save, dz16, dbias, dw_i, dw_f, dw_o,
                       work=0.0):
         self._call("rsr_lstmp_rec_bwd", 1, self.h, _stream(), B, T, Cp, _p(dmt), _p(wc), _p(w_i), _p(w_f),

@@ -52,6 +52,13 @@ class FakeHandle(object):
     def join(self):
         pass
 
+    def lstmp_fused_fwd(self, *a, **k):      # the double has no fused variant: callers fall back to gemm + rec
+        return False
+
+    def transpose16(self, src, rows, cols, dst):
+        self.launches += 1
+        dst[:cols, :rows] = src[:rows, :cols].t()
+
     # ------------------------------------------------------------------ GEMM
     def gemm(self, A, B, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, bias=None, resid=None,
              act=ACT_NONE, dact_src=None, dact=ACT_NONE, out32=None, out16=None, tile_n=0, lda=None, ldb=None):

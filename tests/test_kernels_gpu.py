@@ -148,6 +148,51 @@ def test_lstmp_recurrence_l2_exchange_variant(h, monkeypatch, B, T, I, C, P):
             assert v < t, (k, v, r)
 
 
+@pytest.mark.parametrize("B,T,I,C,P,ragged", [
+    (40, 10, 256, 512, 256, True),       # BASELINE cfg-2 layer: three groups, the last one partial
+    (8, 12, 40, 256, 40, True),          # discriminator_lstm layer: Ik = 48 > I (zero padded K)
+    (20, 6, 257, 256, 257, False),       # 257-wide input (res_lstm_l): ldx = 264, Ik = 272, five 64-wide x sub-tiles
+])
+def test_lstmp_fused_forward(h, B, T, I, C, P, ragged):
+    """rsr_lstmp_fused_fwd (x_t K_x + b + mt_{t-1} Wc + gates in one kernel) == oracle LSTMP forward."""
+    dev, rng = h.device, np.random.default_rng(B + I)
+    Cp, Ip, Ik = packing.cell_pad(C), packing.round_up(I, 8), packing.round_up(I, 16)
+    x = rng.standard_normal((B, T, I))
+    K = O.xavier(rng, (I + P, 4 * C)) * 2.0
+    b = rng.standard_normal(4 * C) * 0.1
+    wi, wf, wo = (O.xavier(rng, (C,)) for _ in range(3))
+    Wp = O.xavier(rng, (C, P)) * 2.0
+    lengths = rng.integers(max(T // 2, 1), T + 1, size=B) if ragged else np.full(B, T)
+    out_ref, cache = O.lstmp_fwd(x, lengths, K, b, wi, wf, wo, Wp)
+    steps = cache[-1]
+    x16 = torch.zeros(T * B, Ip, dtype=h.h16, device=dev)
+    x16[:, :I] = torch.tensor(x.transpose(1, 0, 2).reshape(T * B, I), device=dev).to(h.h16)
+    kx_p = packing.pack_cols(K[:I], C)                                   # [I, 4Cp]
+    kxT = torch.zeros(4 * Cp, Ik, dtype=h.h16, device=dev)
+    kxT[:, :I] = torch.tensor(kx_p.T.copy(), device=dev).to(h.h16)
+    Wc_p = packing.pad_first(packing.pack_cols(Wp @ K[I:], C), Cp)
+    wcT16 = torch.tensor(Wc_p, device=dev).to(h.h16).t().contiguous()
+    pk = lambda v: torch.tensor(packing.pad_last(v, Cp).astype(np.float32), device=dev)
+    bias_p = torch.tensor(packing.pack_cols(b[None], C)[0].astype(np.float32), device=dev)
+    mt_seq = torch.zeros((T + 1) * B, Cp, dtype=h.h16, device=dev)
+    save = torch.zeros(T * B, 5, Cp, dtype=torch.float32, device=dev)
+    ok = h.lstmp_fused_fwd(B, T, I, Cp, x16, kxT, bias_p, wcT16, pk(wi), pk(wf), pk(wo),
+                           torch.tensor(lengths.astype(np.int32), device=dev), mt_seq, save)
+    torch.cuda.synchronize()
+    assert ok
+    mt_ref = np.stack([np.where(steps[t][9], steps[t][8], 0.0) for t in range(T)])
+    got = mt_seq[B:].float().cpu().numpy().reshape(T, B, Cp)
+    t16 = tol(h, 1.5e-3, 1e-2)
+    assert rel(got[:, :, :C], mt_ref) < t16
+    assert Cp == C or float(np.abs(got[:, :, C:]).max()) == 0.0
+    assert rel((got[:, :, :C] @ Wp).transpose(1, 0, 2), out_ref) < t16
+    # transposition helper used to keep K_x^T in step with the weights
+    src = torch.tensor(rng.standard_normal((70, 130)).astype(np.float32), device=dev).to(h.h16)
+    dst = torch.zeros(136, 72, dtype=h.h16, device=dev)
+    h.transpose16(src, 70, 130, dst)
+    assert torch.equal(dst[:130, :70], src.t()) and float(dst[130:].abs().max()) == 0 and float(dst[:, 70:].abs().max()) == 0
+
+
 def test_lstmp_shape_errors(h):
     z = torch.zeros(8, device=h.device)
     from rsrgan_b200 import _lib
