@@ -267,6 +267,13 @@ def main():
         "kernel_shares": {k: {"calls_per_step": v[0] / nprof, "ms_per_step": v[1] / nprof, "share": v[1] / tot}
                           for k, v in sorted(shares.items(), key=lambda kv: -kv[1][1])},
     }
+    if world > 1:
+        # data-parallel invariant: every rank applied the same averaged gradients -> bit-identical weights
+        chk = torch.stack([model.G.P.theta.double().sum(), model.D.P.theta.double().sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out["ranks_in_sync"] = bool(torch.equal(lo, hi))
     if rank == 0:
         out["clocks"] = sampler.summary()
         if world == 1 and not a.no_cpu_baseline:

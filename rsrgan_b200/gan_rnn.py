@@ -173,9 +173,11 @@ class GAN_RNN(Model):
         self.use_graph = (_arg(args, "use_graph", True) and os.environ.get("RSR_NO_GRAPH", "0") != "1"
                           and dev.type == "cuda")
         self._graphs = {}
-        # With several ranks the schedule runs eagerly: capturing the NCCL all-reduces together with the side
-        # stream hung on 2 x B200 (torch 2.11 / NCCL 2.28.9); RSR_GRAPH_DDP=1 re-enables the attempt.
-        self.graph_ddp = os.environ.get("RSR_GRAPH_DDP", "0") == "1"
+        # With several ranks the schedule is captured as one graph SEGMENT per update; the NCCL all-reduce of the
+        # flat gradient buffer runs eagerly between segments (capturing NCCL itself hung on 2 x B200 with
+        # torch 2.11 / NCCL 2.28.9).  RSR_GRAPH_DDP=0: fully eager with several ranks.
+        self.graph_ddp = os.environ.get("RSR_GRAPH_DDP", "1") != "0"
+        self._cap = None
         self.g_outputs = None
         self.summaries = None
         self.writer = None
@@ -312,7 +314,15 @@ class GAN_RNN(Model):
         P, h = net.P, self.h
         h.join()                                           # weight gradients computed on the side stream
         if self.world > 1:
-            self.dist.all_reduce(P.grad)                   # utils/ops.py:343-376 average_gradients (sum here, 1/N below)
+            # utils/ops.py:343-376 average_gradients: sum over ranks here, 1/N folded into the update kernel
+            if self._cap is not None:
+                # graph capture in progress: the collective stays OUTSIDE the graphs -- close the segment, run the
+                # all-reduce eagerly (keeps every rank's collective sequence aligned), open the next segment
+                self._cap_end(P.grad)
+                self.dist.all_reduce(P.grad)
+                self._cap_begin()
+            else:
+                self.dist.all_reduce(P.grad)
         gmul = 1.0 / (self.world * gscale)
         h.seg_sumsq(P.grad, gmul, P.seg_id, len(P.segs), P.sumsq)
         if adam:
@@ -439,17 +449,45 @@ class GAN_RNN(Model):
             feed = self._feed(st["x"], st["y"], st["ln"])
             return self._schedule(feed)
         if st["graph"] is None:
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            n0 = self.h.launches
-            with torch.cuda.graph(g):
-                feed = self._feed(st["x"], st["y"], st["ln"])
-                st["out"] = self._schedule(feed)
-            st["graph"], st["launches"] = g, self.h.launches - n0
-            self.h.launches = n0
-        st["graph"].replay()
+            self._capture(st)
+        for g, ar in st["graph"]:
+            g.replay()
+            if ar is not None:
+                self.dist.all_reduce(ar)
         self.h.launches += st["launches"]
         return st["out"]
+
+    # -- segmented CUDA-graph capture ---------------------------------------------------------------
+    def _cap_begin(self):
+        g = torch.cuda.CUDAGraph()
+        # thread_local: the NCCL watchdog thread and NVML samplers may touch the device while we capture
+        g.capture_begin(pool=self._cap["pool"], capture_error_mode="thread_local")
+        self._cap["g"] = g
+
+    def _cap_end(self, allreduce_after):
+        g = self._cap["g"]
+        g.capture_end()
+        self._cap["segs"].append((g, allreduce_after))
+        self._cap["g"] = None
+
+    def _capture(self, st):
+        torch.cuda.synchronize()
+        cs = torch.cuda.Stream(device=self.h.device)
+        cs.wait_stream(torch.cuda.current_stream())
+        self._cap = dict(pool=torch.cuda.graph_pool_handle(), segs=[], g=None)
+        n0 = self.h.launches
+        try:
+            with torch.cuda.stream(cs):
+                self._cap_begin()
+                feed = self._feed(st["x"], st["y"], st["ln"])
+                st["out"] = self._schedule(feed)
+                self._cap_end(None)
+            st["graph"] = self._cap["segs"]
+        finally:
+            self._cap = None
+        torch.cuda.current_stream().wait_stream(cs)
+        st["launches"] = self.h.launches - n0
+        self.h.launches = n0
 
     def train_batch(self, inputs, labels, lengths, sync=True):
         """The per-batch schedule of train_one_iteration (scripts/train_gan_rnn_placeholder.py:72-101):

@@ -12,6 +12,7 @@ from rsrgan_b200 import ops  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 Cp = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+which = sys.argv[3] if len(sys.argv) > 3 else "fwd"
 T = 40
 h = ops.Handle(0, "f16")
 dev = h.device
@@ -22,15 +23,26 @@ w = [torch.randn(Cp, device=dev) * 0.1 for _ in range(3)]
 ln = torch.full((B,), T, dtype=torch.int32, device=dev)
 mt = torch.zeros(rows + B, Cp, dtype=h.h16, device=dev)
 save = torch.zeros(rows, 5 * Cp, device=dev)
-for _ in range(3):
-    h.lstmp_rec_fwd(B, T, Cp, zx, wcT, w[0], w[1], w[2], ln, mt, save)
+h.lstmp_rec_fwd(B, T, Cp, zx, wcT, w[0], w[1], w[2], ln, mt, save)
+if which == "bwd":
+    wc = wcT.t().contiguous()
+    dmt = torch.randn(rows, Cp, device=dev) * 0.01
+    dz = torch.zeros(rows + B, 4 * Cp, dtype=h.h16, device=dev)
+    db = torch.zeros(4 * Cp, device=dev)
+    dw = [torch.zeros(Cp, device=dev) for _ in range(3)]
+    for _ in range(3):
+        h.lstmp_rec_bwd(B, T, Cp, dmt, wc, w[0], w[1], w[2], ln, save, dz, db, dw[0], dw[1], dw[2])
+else:
+    for _ in range(3):
+        h.lstmp_rec_fwd(B, T, Cp, zx, wcT, w[0], w[1], w[2], ln, mt, save)
 torch.cuda.synchronize()
 buf = (C.c_ulonglong * (64 * 8))()
 h.lib.rsr_debug_trace.argtypes = [C.c_void_p, C.c_int]
 rc = h.lib.rsr_debug_trace(buf, 64 * 8)
 tr = np.array(buf[:], dtype=np.int64).reshape(64, 8)[:T]
-names = ["top", "full-wait done", "mma issued", "mma done", "xchg+sync", "gates+send"]
-print("B %d Cp %d rc %d; cycles between trace points (median over steps 5..%d)" % (B, Cp, rc, T - 2))
+names = (["top", "full-wait done", "mma issued", "mma done", "xchg+sync", "gates+send"] if which == "fwd" else
+         ["top", "loads+wait+sum", "gate bwd", "barrier", "mma done", "ld+send"])
+print(which, "B %d Cp %d rc %d; cycles between trace points (median over steps 5..%d)" % (B, Cp, rc, T - 2))
 d = np.diff(tr[5:T - 1, :6], axis=1)
 for i in range(5):
     print("  %-16s -> %-16s %7.0f" % (names[i], names[i + 1], np.median(d[:, i])))
