@@ -115,6 +115,34 @@ def peaks():
     return 1400.0, 1590.0, 6650.0, "fallback"
 
 
+NCU_SUMMARY = {   # C-ABI call -> committed `ncu --set full` summary of its kernel (profiles/, made by scripts in DESIGN.md 6)
+    "rsr_gemm": "r1_gemm_full_summary.csv",
+    "rsr_lstmp_rec_bwd": "r1_recbwd_full_summary.csv",
+    "rsr_lstmp_rec_fwd": "r1_recfwd_full_summary.csv",
+    "rsr_lstmp_fused_fwd": "r1_recfwd_full_summary.csv",
+}
+
+
+def ncu_traffic(call):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the captured launches) from the
+    committed ncu --set full capture of this kernel, or None."""
+    import csv
+    path = os.path.join(ROOT, "profiles", NCU_SUMMARY.get(call, "-"))
+    if not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n = 0.0, 0
+    for r in rows[2:]:
+        try:
+            b = sum(float(r[hdr.index(k)]) * mult[units[hdr.index(k)]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        except (ValueError, KeyError):
+            continue
+        tot, n = tot + b, n + 1
+    return tot / n if n else None
+
+
 def run_reference(a, cfg):
     """CPU arm: oracle/cpu_baseline.py (port of the reference schedule) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -241,11 +269,18 @@ def main():
     top = max(shares.items(), key=lambda kv: kv[1][1])
     sus, burst, hbm, how = peaks()
     name, (cnt, tms, work) = top
-    ach = work / (tms * 1e-3) / 1e12 if tms > 0 else 0.0
-    roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": sus, "unit": "TFLOP/s",
-                "frac": ach / sus, "traffic": None, "peak_source": how + " (bf16 sustained; fp16 runs at the same rate)",
+    def roof(name, cnt, tms, work):
+        ach = work / (tms * 1e-3) / 1e12 if tms > 0 else 0.0
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": sus, "unit": "TFLOP/s",
+                "frac": ach / sus, "traffic": ncu_traffic(name),
+                "traffic_source": "profiles/" + NCU_SUMMARY[name] + " (ncu --set full, mean over captured launches)"
+                if name in NCU_SUMMARY else None,
+                "peak_source": how + " (bf16 sustained; fp16 runs at the same rate)",
                 "launches_per_step": cnt / nprof, "avg_launch_ms": tms / cnt, "share_of_step": tms / tot,
                 "algorithmic_flops_per_launch": work / cnt}
+    roofline = roof(name, cnt, tms, work)
+    # the fused LSTM-gate kernels named by north_star, reported whatever their share (latency / DSMEM bound)
+    lstm_roofs = [roof(k, *shares[k]) for k in ("rsr_lstmp_fused_fwd", "rsr_lstmp_rec_fwd", "rsr_lstmp_rec_bwd") if k in shares]
     fpf = flops_per_frame(cfg)
     step_tflops = value / world * fpf / 1e12
 
@@ -262,6 +297,7 @@ def main():
                 "d2h_bytes_per_step": 2 * 8 * 4},
         "gpu_launches": launches,
         "roofline": roofline,
+        "roofline_lstm_kernels": lstm_roofs,
         "step_roofline": {"algorithmic_mflop_per_frame": fpf / 1e6, "achieved_tflops_per_gpu": step_tflops,
                           "frac_of_sustained_bf16": step_tflops / sus},
         "kernel_shares": {k: {"calls_per_step": v[0] / nprof, "ms_per_step": v[1] / nprof, "share": v[1] / tot}

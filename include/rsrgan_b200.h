@@ -98,8 +98,9 @@ int rsr_cmvn_invert(rsr_handle* h, void* stream, const float* y, const float* me
  *
  * The recurrence is run in the algebraically folded form
  *     z_t = Zx_t + mt_{t-1} * Wc ,  Wc = W_proj * K_h   (C x 4C),  out_t = mt_t * W_proj
- * so one persistent kernel does every time step with Wc resident in shared memory and the
- * projection becomes a batched GEMM outside the loop.  Columns of every 4C-wide tensor are in
+ * so one persistent kernel does every time step with Wc resident on chip (TMEM for Cp <= 512, where the
+ * CTAs of an utterance group form a thread-block cluster and exchange mt_t through distributed shared
+ * memory; shared memory + L2 exchange for Cp > 512) and the projection becomes a batched GEMM outside the loop.  Columns of every 4C-wide tensor are in
  * PACKED gate order: col = (cell/32)*128 + gate*32 + cell%32, gate in (i, j, f, o); Cp = C padded
  * to a multiple of 256 with zero weights (padded cells stay exactly 0).
  *
