@@ -164,6 +164,39 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
     }
 }
 
+// 16-bit, 16-byte vectorised variant (N and ld multiples of 8, 16-byte aligned base): thread <-> 8 consecutive
+// columns, 32 row lanes per block; block = 256 columns x a slab of rows.
+__global__ void __launch_bounds__(256) colsum16_vec_kernel(const uint16_t* __restrict__ x, int ld, long long M, int N,
+                                                           float* __restrict__ out, int bf, long long rows_per_block) {
+    __shared__ float sh[8][256 + 8];
+    const int cg = threadIdx.x & 31, ry = threadIdx.x >> 5;       // column group (8 columns), row lane
+    const int n0 = blockIdx.x * 256 + cg * 8;
+    const long long r0 = blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block; if (r1 > M) r1 = M;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (n0 < N) {
+        for (long long r = r0 + ry; r < r1; r += 8) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + r * ld + n0));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                s[2 * k] += h2f((uint16_t)(w[k] & 0xFFFFu), bf);
+                s[2 * k + 1] += h2f((uint16_t)(w[k] >> 16), bf);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sh[ry][cg * 8 + k] = s[k];
+    __syncthreads();
+    const int c = threadIdx.x;                                     // one column per thread
+    if (blockIdx.x * 256 + c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][c];
+        atomicAdd(out + blockIdx.x * 256 + c, t);
+    }
+}
+
 __global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __restrict__ src, int ld_src, int rows, int cols,
                                                           uint16_t* __restrict__ dst, int ld_dst) {
     __shared__ uint16_t tile[32][34];
@@ -363,6 +396,19 @@ template <typename T>
 static int colsum_launch(rsr_handle* h, void* stream, const T* x, int ld, long long M, int N, float* out, int accumulate) {
     if (!h || !x || !out || M <= 0 || N <= 0 || ld < N) return RSR_E_ARG;
     if (!accumulate) RSR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, (cudaStream_t)stream));
+    if constexpr (sizeof(T) == 2) {
+        if ((N & 7) == 0 && (ld & 7) == 0 && ((uintptr_t)x & 15) == 0) {
+            const int gxv = (N + 255) / 256;
+            long long gyv = (4LL * h->num_sms + gxv - 1) / gxv;
+            if (gyv > (M + 63) / 64) gyv = (M + 63) / 64;
+            if (gyv < 1) gyv = 1;
+            const long long rpbv = (M + gyv - 1) / gyv;
+            colsum16_vec_kernel<<<dim3(gxv, (unsigned)gyv), 256, 0, (cudaStream_t)stream>>>(
+                (const uint16_t*)x, ld, M, N, out, h->dtype == RSR_DTYPE_BF16, rpbv);
+            RSR_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     const int gx = (N + 31) / 32;
     long long gy = (2LL * h->num_sms + gx - 1) / gx;
     if (gy > (M + 63) / 64) gy = (M + 63) / 64;

@@ -255,6 +255,11 @@ def test_staging_losses_update(h):
     cs = torch.zeros(77, device=dev)
     h.colsum16(Xd, 1000, 77, cs)
     assert rel(cs.cpu().numpy(), Xd[:, :77].double().sum(0).cpu().numpy()) < 1e-5
+    # 16-byte vectorised variant (N, ld multiples of 8), accumulating into a non-zero vector
+    Xv = tt(rng.standard_normal((3001, 520)).astype(np.float32)).to(h.h16)
+    cv = torch.ones(520, device=dev)
+    h.colsum16(Xv, 3001, 520, cv, accumulate=True)
+    assert rel(cv.cpu().numpy(), 1.0 + Xv.double().sum(0).cpu().numpy()) < 1e-5
 
 
 def test_fused_clip_update_sweep(h):
