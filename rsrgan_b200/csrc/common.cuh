@@ -313,6 +313,41 @@ __device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t a, uint32_t
 }
 
 // ---------------------------------------------------------------------------
+// cta_group::2 (two CTAs of a cluster drive one 256-row UMMA; PTX strings as in CUTLASS' sm100 headers)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_dst, uint32_t ncols) {  // one full warp in EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load whose completion bytes go to the mbarrier of the pair's LEADER (even) CTA: `lead_bar` is the
+// shared::cluster address of that barrier (mapa(bar, rank & ~1)); data lands in the executing CTA.
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* m, uint32_t lead_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"((uint64_t)m), "r"(lead_bar), "r"(c0), "r"(c1) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 (128 rows per CTA) and B split along N between the two CTAs;
+// issued by ONE thread of the leader CTA.
+__device__ __forceinline__ void tc_mma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (once all prior MMAs of the pair retired) on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_2cta_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+
+// ---------------------------------------------------------------------------
 // cross-CTA flag helpers (group barriers of the persistent recurrent kernels)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {

@@ -17,6 +17,8 @@
 // models/discriminator_dnn.py:61-93; models/discriminator_lstm.py:100-104), the x_t half of
 // LSTMCell's _Linear (models/lstm.py:90-96) hoisted over all frames, the projection
 // (models/BNLSTMCell.py:207-213) hoisted over all frames, and tf.gradients of all of them.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "handle.h"
 
@@ -60,6 +62,163 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
         case RSR_ACT_RELU: return y > 0.0f ? 1.0f : 0.0f;
         case RSR_ACT_LRELU: return y > 0.0f ? 1.0f : 0.3f;
         default: return 1.0f;
+    }
+}
+
+// Epilogue of ONE 128 x bn accumulator tile, executed by one epilogue warp: thread <-> accumulator row
+// (TMEM lane), 32 columns per tcgen05.ld; bias / residual / activation / activation-gradient in registers;
+// results go through a swizzled per-warp staging box and leave with one TMA store (or reduce-add) per box.
+__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtensorMap* tmC32, const CUtensorMap* tmC16,
+                                              uint32_t taddr, int row0, int n0, int lane, int ew, uint32_t st32,
+                                              uint32_t st16, bool leader) {
+    const int span = (p.has16 && p.w16 == 64) ? 64 : 32;   // the two warps of a quadrant interleave column spans
+    const uint32_t sw32 = (uint32_t)(lane & 7), sw16 = (uint32_t)((lane >> 1) & 3);
+    const bool general_beta = p.has32 && !p.reduce32 && p.beta != 0.0f;
+    const int row = row0 + lane;
+    const bool row_ok = row < p.M;
+    for (int s0 = (ew >> 2) * span; s0 < p.bn; s0 += 2 * span) {
+      bool wrote16 = false;
+      for (int c0 = s0; c0 < s0 + span && c0 < p.bn; c0 += 32) {
+        const int col0 = n0 + c0;
+        if (col0 >= p.N) break;                        // warp-uniform
+        // epilogue operands of this row (independent of the accumulator: issue first)
+        float bj = 0.f;
+        if (p.bias && col0 + lane < p.N) bj = __ldg(p.bias + col0 + lane);
+        float4 rs[8];
+        uint4 dq[4];
+        if (p.resid) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                rs[c] = (row_ok && col0 + 4 * c < p.N)
+                            ? __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldr + col0) + c)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (p.dsrc) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                dq[c] = (row_ok && col0 + 8 * c < p.N)
+                            ? __ldg(reinterpret_cast<const uint4*>(p.dsrc + (size_t)row * p.ldd + col0) + c)
+                            : make_uint4(0u, 0u, 0u, 0u);
+        }
+        float v[32];
+        __syncwarp();                                  // reconverge: tcgen05.ld is .sync.aligned
+        if (c0 + 32 <= p.bn) {
+            tmem_ld32(taddr + (uint32_t)c0, v);
+        } else {                                       // bn is a multiple of 16 (only when n_tiles == 1)
+            tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 16; j < 32; ++j) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], p.alpha, __shfl_sync(0xffffffffu, bj, j));
+        if (p.resid) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { v[4 * c] += rs[c].x; v[4 * c + 1] += rs[c].y; v[4 * c + 2] += rs[c].z; v[4 * c + 3] += rs[c].w; }
+        }
+        // activation / activation-gradient: the selector is hoisted out of the per-element loops
+        if (p.act == RSR_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if (p.act == RSR_ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.3f * v[j]);
+        } else if (p.act == RSR_ACT_CLIP) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -0.5f), 1.5f);
+        }
+        if (p.dsrc && p.dact != RSR_ACT_NONE) {
+            // relu' / lrelu' from the sign of the stored 16-bit activation OUTPUT (fp16 and bf16 alike:
+            // y > 0  <=>  sign bit clear and magnitude bits non-zero)
+            const float neg = p.dact == RSR_ACT_LRELU ? 0.3f : 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t w[4] = {dq[c].x, dq[c].y, dq[c].z, dq[c].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool pos_lo = (int16_t)(w[k] & 0xFFFFu) > 0, pos_hi = (int32_t)w[k] >= 0x10000;
+                    v[8 * c + 2 * k] *= pos_lo ? 1.0f : neg;
+                    v[8 * c + 2 * k + 1] *= pos_hi ? 1.0f : neg;
+                }
+            }
+        }
+        if (col0 + 32 > p.N && (p.N & 7)) {
+            // ragged right edge (N not a multiple of the 16-byte TMA store granule): plain stores
+            if (row_ok && p.has16) {                   // out16 holds the value without the beta term
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < p.N) p.out16[(size_t)row * p.ldc16 + col0 + j] = f2h(v[j], p.bf);
+            }
+            if (row_ok && p.has32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (col0 + j < p.N) {
+                        float* o = p.out32 + (size_t)row * p.ldc32 + col0 + j;
+                        if (p.reduce32) red_add_f32(o, v[j]);
+                        else *o = general_beta ? v[j] + p.beta * *o : v[j];
+                    }
+                }
+            }
+            continue;
+        }
+        // the previous boxes of this warp must have been read out of the staging buffers
+        if (leader) tma_wait_group_read<0>();
+        __syncwarp();
+        if (p.has16) {
+            const uint32_t cc0 = (uint32_t)(c0 - s0) >> 3;       // first 16-byte chunk of this half inside the box row
+#pragma unroll
+            uint32_t pk[16];
+            if (p.bf) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+                    pk[k] = *reinterpret_cast<const uint32_t*>(&t);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const __half2 t = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+                    pk[k] = *reinterpret_cast<const uint32_t*>(&t);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t dst = p.w16 == 64 ? st16 + (uint32_t)lane * 128u + (((cc0 + (uint32_t)c) ^ sw32) << 4)
+                                                 : st16 + (uint32_t)lane * 64u + (((uint32_t)c ^ sw16) << 4);
+                st_shared_v4(dst, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            }
+            wrote16 = true;
+        }
+        if (p.has32) {
+            if (general_beta) {                        // out32 = v + beta * out32_old  (beta not in {0, 1})
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (row_ok && col0 + 4 * c < p.N) {
+                        const float4 o = *(reinterpret_cast<const float4*>(p.out32 + (size_t)row * p.ldc32 + col0) + c);
+                        v[4 * c] += p.beta * o.x; v[4 * c + 1] += p.beta * o.y; v[4 * c + 2] += p.beta * o.z; v[4 * c + 3] += p.beta * o.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                st_shared_v4(st32 + (uint32_t)lane * 128u + (((uint32_t)c ^ sw32) << 4),
+                             __float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
+                             __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (leader && row0 < p.M) {
+            if (p.has16 && p.w16 == 32) tma_store_2d(tmC16, st16, col0, row0);
+            if (p.has32) {
+                if (p.reduce32) tma_reduce_add_2d(tmC32, st32, col0, row0);
+                else tma_store_2d(tmC32, st32, col0, row0);
+            }
+            tma_commit_group();
+        }
+      }
+      if (wrote16 && p.w16 == 64 && leader && row0 < p.M) {   // one 64-column (128-byte rows) box per span
+          tma_store_2d(tmC16, st16, n0 + s0, row0);
+          tma_commit_group();
+      }
     }
 }
 
@@ -181,11 +340,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ---------------- epilogue warps ----------------
         const int ew = warp - 2;
         const int q = warp & 3;                                // TMEM lane quadrant this warp may access
-        const int span = (p.has16 && p.w16 == 64) ? 64 : 32;   // the two warps of a quadrant interleave column spans
         const uint32_t st32 = smem_base + epi_off + (uint32_t)(ew * p.st_stride);     // [32 rows][128 B], SW128
         const uint32_t st16 = st32 + (p.has32 ? 4096u : 0u);                           // [32 rows][128 B] SW128 | [32][64 B] SW64
-        const uint32_t sw32 = (uint32_t)(lane & 7), sw16 = (uint32_t)((lane >> 1) & 3);
-        const bool general_beta = p.has32 && !p.reduce32 && p.beta != 0.0f;
         const bool leader = elect_one_sync();                  // issues (and waits for) this warp's TMA stores
         int acc = 0; uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -195,152 +351,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
             const int row0 = m0 + q * 32;
-            const int row = row0 + lane;
-            const bool row_ok = row < p.M;
-            for (int s0 = (ew >> 2) * span; s0 < p.bn; s0 += 2 * span) {
-              bool wrote16 = false;
-              for (int c0 = s0; c0 < s0 + span && c0 < p.bn; c0 += 32) {
-                const int col0 = n0 + c0;
-                if (col0 >= p.N) break;                        // warp-uniform
-                // epilogue operands of this row (independent of the accumulator: issue first)
-                float bj = 0.f;
-                if (p.bias && col0 + lane < p.N) bj = __ldg(p.bias + col0 + lane);
-                float4 rs[8];
-                uint4 dq[4];
-                if (p.resid) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        rs[c] = (row_ok && col0 + 4 * c < p.N)
-                                    ? __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldr + col0) + c)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if (p.dsrc) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        dq[c] = (row_ok && col0 + 8 * c < p.N)
-                                    ? __ldg(reinterpret_cast<const uint4*>(p.dsrc + (size_t)row * p.ldd + col0) + c)
-                                    : make_uint4(0u, 0u, 0u, 0u);
-                }
-                float v[32];
-                __syncwarp();                                  // reconverge: tcgen05.ld is .sync.aligned
-                if (c0 + 32 <= p.bn) {
-                    tmem_ld32(taddr + (uint32_t)c0, v);
-                } else {                                       // bn is a multiple of 16 (only when n_tiles == 1)
-                    tmem_ld16(taddr + (uint32_t)c0, v);
-#pragma unroll
-                    for (int j = 16; j < 32; ++j) v[j] = 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], p.alpha, __shfl_sync(0xffffffffu, bj, j));
-                if (p.resid) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) { v[4 * c] += rs[c].x; v[4 * c + 1] += rs[c].y; v[4 * c + 2] += rs[c].z; v[4 * c + 3] += rs[c].w; }
-                }
-                // activation / activation-gradient: the selector is hoisted out of the per-element loops
-                if (p.act == RSR_ACT_RELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-                } else if (p.act == RSR_ACT_LRELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.3f * v[j]);
-                } else if (p.act == RSR_ACT_CLIP) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -0.5f), 1.5f);
-                }
-                if (p.dsrc && p.dact != RSR_ACT_NONE) {
-                    // relu' / lrelu' from the sign of the stored 16-bit activation OUTPUT (fp16 and bf16 alike:
-                    // y > 0  <=>  sign bit clear and magnitude bits non-zero)
-                    const float neg = p.dact == RSR_ACT_LRELU ? 0.3f : 0.0f;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint32_t w[4] = {dq[c].x, dq[c].y, dq[c].z, dq[c].w};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const bool pos_lo = (int16_t)(w[k] & 0xFFFFu) > 0, pos_hi = (int32_t)w[k] >= 0x10000;
-                            v[8 * c + 2 * k] *= pos_lo ? 1.0f : neg;
-                            v[8 * c + 2 * k + 1] *= pos_hi ? 1.0f : neg;
-                        }
-                    }
-                }
-                if (col0 + 32 > p.N && (p.N & 7)) {
-                    // ragged right edge (N not a multiple of the 16-byte TMA store granule): plain stores
-                    if (row_ok && p.has16) {                   // out16 holds the value without the beta term
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N) p.out16[(size_t)row * p.ldc16 + col0 + j] = f2h(v[j], p.bf);
-                    }
-                    if (row_ok && p.has32) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (col0 + j < p.N) {
-                                float* o = p.out32 + (size_t)row * p.ldc32 + col0 + j;
-                                if (p.reduce32) red_add_f32(o, v[j]);
-                                else *o = general_beta ? v[j] + p.beta * *o : v[j];
-                            }
-                        }
-                    }
-                    continue;
-                }
-                // the previous boxes of this warp must have been read out of the staging buffers
-                if (leader) tma_wait_group_read<0>();
-                __syncwarp();
-                if (p.has16) {
-                    const uint32_t cc0 = (uint32_t)(c0 - s0) >> 3;       // first 16-byte chunk of this half inside the box row
-#pragma unroll
-                    uint32_t pk[16];
-                    if (p.bf) {
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) {
-                            const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
-                            pk[k] = *reinterpret_cast<const uint32_t*>(&t);
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) {
-                            const __half2 t = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
-                            pk[k] = *reinterpret_cast<const uint32_t*>(&t);
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint32_t dst = p.w16 == 64 ? st16 + (uint32_t)lane * 128u + (((cc0 + (uint32_t)c) ^ sw32) << 4)
-                                                         : st16 + (uint32_t)lane * 64u + (((uint32_t)c ^ sw16) << 4);
-                        st_shared_v4(dst, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                    }
-                    wrote16 = true;
-                }
-                if (p.has32) {
-                    if (general_beta) {                        // out32 = v + beta * out32_old  (beta not in {0, 1})
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            if (row_ok && col0 + 4 * c < p.N) {
-                                const float4 o = *(reinterpret_cast<const float4*>(p.out32 + (size_t)row * p.ldc32 + col0) + c);
-                                v[4 * c] += p.beta * o.x; v[4 * c + 1] += p.beta * o.y; v[4 * c + 2] += p.beta * o.z; v[4 * c + 3] += p.beta * o.w;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        st_shared_v4(st32 + (uint32_t)lane * 128u + (((uint32_t)c ^ sw32) << 4),
-                                     __float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
-                                     __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (leader && row0 < p.M) {
-                    if (p.has16 && p.w16 == 32) tma_store_2d(&tmC16, st16, col0, row0);
-                    if (p.has32) {
-                        if (p.reduce32) tma_reduce_add_2d(&tmC32, st32, col0, row0);
-                        else tma_store_2d(&tmC32, st32, col0, row0);
-                    }
-                    tma_commit_group();
-                }
-              }
-              if (wrote16 && p.w16 == 64 && leader && row0 < p.M) {   // one 64-column (128-byte rows) box per span
-                  tma_store_2d(&tmC16, st16, n0 + s0, row0);
-                  tma_commit_group();
-              }
-            }
+            epilogue_tile(p, &tmC32, &tmC16, taddr, row0, n0, lane, ew, st32, st16, leader);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));       // accumulator may be overwritten
@@ -351,6 +362,153 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+
+// Two-CTA variant (cluster of 2, tcgen05 cta_group::2): a pair of CTAs computes one 256 x bn tile.  Each CTA
+// loads its own 128 rows of A and only HALF of the B tile (bn/2 columns); the leader issues UMMA 256 x bn x 16
+// instructions that run on both SMs, each SM reading the other's B half through the pair's datapath.  Per CTA
+// and k-block the operand traffic drops from 16 KB + 32 KB to 16 KB + 16 KB (bn = 256), which is what limits
+// the one-CTA kernel on the large products (L2 -> SM operand bandwidth).  Barriers: TMA loads of both CTAs
+// complete on the LEADER's full barrier; the leader's commits are multicast to both CTAs' empty / tfull
+// barriers; both CTAs' epilogue warps arrive on the leader's tempty barrier.
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC32, const __grid_constant__ CUtensorMap tmC16,
+                     const GemmKParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                         // 0 = leader
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int hn = p.bn / 2;                                         // B columns held by each CTA
+
+    const int a_stage_bytes = BM * BK * 2;                           // 16 KB
+    const int b_boxes = p.b_mn ? hn / 64 : 1;
+    const int b_stage_bytes = p.b_mn ? b_boxes * BK * 128 : hn * 128;
+    const int stage_bytes = a_stage_bytes + ((b_stage_bytes + 1023) & ~1023);
+    const uint32_t epi_off = (uint32_t)(p.stages * stage_bytes);
+    const uint32_t bars = smem_base + epi_off + (uint32_t)(EPI_WARPS * p.st_stride);
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
+    auto tfull_bar = [&](int a) { return bars + 16u * p.stages + 8u * a; };
+    auto tempty_bar = [&](int a) { return bars + 16u * p.stages + 16u + 8u * a; };
+    const uint32_t tmem_slot = bars + 16u * p.stages + 32u;
+    const uint32_t to_leader = mapa_u32(smem_base, 0u) - smem_base;  // shared::cta -> shared::cluster address in the leader
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (p.has32) tma_prefetch_desc(&tmC32);
+        if (p.has16) tma_prefetch_desc(&tmC16);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2cta(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                              // both CTAs' barriers exist before any remote arrive
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int nkb = (p.K + BK - 1) / BK;
+    const int tiles_mn = p.m_tiles * p.n_tiles;                      // m_tiles counts 256-row tiles here
+    const int total = tiles_mn * p.splits;
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            // ---------------- TMA producer (both CTAs) ----------------
+            const uint32_t tx2 = 2u * (uint32_t)(a_stage_bytes + b_stage_bytes);    // bytes of BOTH CTAs land on the leader's barrier
+            int s = 0; uint32_t ph = 0;
+            for (int tile = pair; tile < total; tile += npairs) {
+                const int ks = tile / tiles_mn, mn = tile % tiles_mn;
+                const int m0 = (mn / p.n_tiles) * 2 * BM + (int)rank * BM, n0 = (mn % p.n_tiles) * p.bn + (int)rank * hn;
+                const int kb0 = (int)((long long)ks * nkb / p.splits), kb1 = (int)((long long)(ks + 1) * nkb / p.splits);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sa = smem_base + s * stage_bytes;
+                    const uint32_t sb = sa + a_stage_bytes;
+                    const uint32_t lead_full = full_bar(s) + to_leader;
+                    if (rank == 0) mbar_expect_tx(full_bar(s), tx2);
+                    const int k0 = kb * BK;
+                    if (!p.a_mn) {
+                        tma_load_2d_2cta(sa, &tmA, lead_full, k0, m0);
+                    } else {
+                        tma_load_2d_2cta(sa, &tmA, lead_full, m0, k0);
+                        tma_load_2d_2cta(sa + BK * 128, &tmA, lead_full, m0 + 64, k0);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_2d_2cta(sb, &tmB, lead_full, k0, n0);
+                    } else {
+                        for (int j = 0; j < b_boxes; ++j)
+                            tma_load_2d_2cta(sb + j * BK * 128, &tmB, lead_full, n0 + 64 * j, k0);
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (rank == 0 && elect_one_sync()) {
+            // ---------------- MMA issuer (leader CTA only) ----------------
+            const uint32_t idesc = umma_idesc(2 * BM, p.bn, p.bf, p.a_mn, p.b_mn);
+            int s = 0; uint32_t ph = 0;
+            int acc = 0; uint32_t aph = 0;
+            for (int tile = pair; tile < total; tile += npairs) {
+                const int ks = tile / tiles_mn;
+                const int kb0 = (int)((long long)ks * nkb / p.splits), kb1 = (int)((long long)(ks + 1) * nkb / p.splits);
+                mbar_wait(tempty_bar(acc), aph ^ 1u);          // both CTAs' epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(acc * p.acc_stride);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full_bar(s), ph);                // both CTAs' stage s has landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + s * stage_bytes;
+                    const uint32_t sb = sa + a_stage_bytes;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = p.a_mn ? umma_desc_sw128(sa + k * 2048, BK * 128, 1024)
+                                                   : umma_desc_sw128(sa + k * 32, 16, 1024);
+                        const uint64_t db = p.b_mn ? umma_desc_sw128(sb + k * 2048, BK * 128, 1024)
+                                                   : umma_desc_sw128(sb + k * 32, 16, 1024);
+                        tc_mma_f16_2cta(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit_2cta_mc(empty_bar(s), (uint16_t)3);   // frees stage s in both CTAs
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+                tc_commit_2cta_mc(tfull_bar(acc), (uint16_t)3);     // accumulator complete in both CTAs
+                if (++acc == 2) { acc = 0; aph ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- epilogue warps (both CTAs, own 128 rows) ----------------
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const uint32_t st32 = smem_base + epi_off + (uint32_t)(ew * p.st_stride);
+        const uint32_t st16 = st32 + (p.has32 ? 4096u : 0u);
+        const bool leader = elect_one_sync();
+        int acc = 0; uint32_t aph = 0;
+        for (int tile = pair; tile < total; tile += npairs) {
+            const int mn = tile % tiles_mn;
+            const int m0 = (mn / p.n_tiles) * 2 * BM + (int)rank * BM, n0 = (mn % p.n_tiles) * p.bn;
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+            epilogue_tile(p, &tmC32, &tmC16, taddr, m0 + q * 32, n0, lane, ew, st32, st16, leader);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) + to_leader);
+            if (++acc == 2) { acc = 0; aph ^= 1u; }
+        }
+        if (leader) tma_wait_group<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                              // the peer may still read this CTA's operands / signal its barriers
+    if (warp == 1) tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 }  // namespace
@@ -446,8 +604,30 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
                                   !a->dact_src && a->beta == 1.0f;
     GemmKParams p;
     p.M = a->M; p.N = a->N; p.K = a->K;
-    const int m_tiles = (a->M + BM - 1) / BM;
-    int bn = a->tile_n;
+    // Two-CTA (cta_group::2) variant for the large products: 256 x bn tiles, half the B traffic per CTA.
+    int two = 0, bn2 = (a->N % 256 == 0) ? 256 : ((a->N % 128 == 0) ? 128 : 0);
+    // (measured on cfg-2 shapes: pays off for K >= 512 and >= 1e10 flop; below that the cluster launch and the two
+    //  cluster barriers cost more than the saved operand traffic)
+    if (a->tile_n <= 0 && bn2 && a->M >= 512 && a->K >= 512 && 2.0 * a->M * a->N * a->K >= 1.0e10 && !getenv("RSR_NO_2CTA")) {
+        if (h->gemm2_pairs < 0) {   // co-resident CTA pairs, queried once
+            cudaFuncSetAttribute(gemm2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2, 1, 1); cfg.blockDim = dim3(GEMM_THREADS, 1, 1); cfg.dynamicSmemBytes = h->max_smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, gemm2_tcgen05_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+            h->gemm2_pairs = n;
+        }
+        const long long pair_tiles = (long long)((a->M + 2 * BM - 1) / (2 * BM)) * (a->N / bn2);
+        // worth it when the pairs are kept busy (split-K multiplies the tile count further down)
+        if (h->gemm2_pairs > 0 && (pair_tiles >= h->gemm2_pairs / 2 || plain_accumulate)) two = 1;
+    }
+    const int units = two ? h->gemm2_pairs : h->num_sms;          // concurrently running tile workers
+    const int m_tiles = two ? (a->M + 2 * BM - 1) / (2 * BM) : (a->M + BM - 1) / BM;
+    int bn = two ? bn2 : a->tile_n;
     if (bn <= 0) {
         bn = 128;
         if (a->N < 128) bn = (a->N + 15) & ~15;
@@ -467,8 +647,9 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     p.n_tiles = (a->N + bn - 1) / bn;
 
     const int a_stage = BM * BK * 2;
-    const int b_boxes = p.b_mn ? (bn + 63) / 64 : 1;
-    const int b_stage = p.b_mn ? b_boxes * BK * 128 : bn * 128;
+    const int bcols = two ? bn / 2 : bn;                           // B columns each CTA holds
+    const int b_boxes = p.b_mn ? (bcols + 63) / 64 : 1;
+    const int b_stage = p.b_mn ? b_boxes * BK * 128 : bcols * 128;
     const int stage_bytes = a_stage + ((b_stage + 1023) & ~1023);
     const int nkb = (a->K + BK - 1) / BK;
     // split-K: only for "out32 += A B" (weight gradients: few output tiles, K = all frames); partial
@@ -477,10 +658,16 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     const int tiles_mn = p.m_tiles * p.n_tiles;
     if (splits <= 0) {
         splits = 1;
-        if (plain_accumulate && tiles_mn < h->num_sms && nkb >= 8) {
-            splits = (h->num_sms + tiles_mn - 1) / tiles_mn;
-            if (splits > nkb / 4) splits = nkb / 4;
-            if (splits < 1) splits = 1;
+        if (plain_accumulate && tiles_mn < units && nkb >= 8) {
+            // cost of a candidate = rounds of the persistent grid x (k-blocks per tile + a per-tile epilogue / pipeline-fill
+            // charge of ~6 k-blocks); more splits also mean more reduce-add traffic, so ties go to the smaller count
+            long long best = -1;
+            const int max_splits = nkb / 4 < 64 ? nkb / 4 : 64;
+            for (int s = 1; s <= max_splits; ++s) {
+                const long long rounds = ((long long)tiles_mn * s + units - 1) / units;
+                const long long cost = rounds * ((nkb + s - 1) / s + 6);
+                if (best < 0 || cost < best) { best = cost; splits = s; }
+            }
         }
     }
     if (splits > 1 && !plain_accumulate) return RSR_E_ARG;
@@ -497,7 +684,7 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     if (stages > 8) stages = 8;
     const int kb_per_tile = (nkb + splits - 1) / splits;
     const long long total_tiles = (long long)tiles_mn * splits;
-    const int grid = (int)(total_tiles < h->num_sms ? total_tiles : h->num_sms);
+    const int grid = (int)(total_tiles < units ? total_tiles : units);   // CTAs, or CTA pairs
     const long long kb_per_cta = (long long)kb_per_tile * ((total_tiles + grid - 1) / grid);
     if (stages > kb_per_cta) stages = (int)kb_per_cta;
     if (stages < 1) return RSR_E_SHAPE;
@@ -514,7 +701,7 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     if (!p.a_mn) rc = rsr_get_tmap(h, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, 64, BM, &tmA);
     else         rc = rsr_get_tmap(h, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BK, &tmA);
     if (rc) return rc;
-    if (!p.b_mn) rc = rsr_get_tmap(h, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, 64, (uint32_t)bn, &tmB);
+    if (!p.b_mn) rc = rsr_get_tmap(h, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, 64, (uint32_t)bcols, &tmB);
     else         rc = rsr_get_tmap(h, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK, &tmB);
     if (rc) return rc;
     CUtensorMap tmC32 = tmA, tmC16 = tmA;   // placeholders when an output is absent (never dereferenced)
@@ -531,11 +718,23 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     static bool attr_set = false;
     if (!attr_set) {
         RSR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        RSR_CHECK_CUDA(cudaFuncSetAttribute(gemm2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
         attr_set = true;
     }
     // One CTA per SM, and never next to a CTA of a recurrence kernel (those hold the whole TMEM of their SM for
     // hundreds of microseconds; a GEMM CTA sharing the SM would sit in tcgen05.alloc until they retire).
     const int smem_launch = smem < RSR_EXCLUSIVE_SMEM_GEMM ? RSR_EXCLUSIVE_SMEM_GEMM : smem;
+    if (two) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * grid, 1, 1); cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem_launch; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        RSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tcgen05_kernel, tmA, tmB, tmC32, tmC16, p));
+        return 0;
+    }
     gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem_launch, (cudaStream_t)stream>>>(tmA, tmB, tmC32, tmC16, p);
     RSR_LAUNCH_CHECK();
     return 0;

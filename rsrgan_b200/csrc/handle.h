@@ -46,6 +46,7 @@ struct rsr_handle {
     unsigned int* flags = nullptr;   // device: group-barrier counters, RSR_FLAG_WORDS words
     int flag_cursor = 0;
     // co-resident clusters of the cluster recurrence kernels: [fwd|bwd][Cp/256 - 1][NB 16|32]; -1 = not queried yet
+    int gemm2_pairs = -1;            // co-resident CTA pairs of the two-CTA GEMM (-1 = not queried yet)
     int fused_ik[2] = {-1, -1};      // Ik the fused-forward capacity entry was computed for
     int cluster_cap[3][2][2] = {{{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}};   // [2] = fused fwd
 };
