@@ -223,8 +223,18 @@ def main():
         model.train_batch(x, y, ln, sync=False)
 
     def step_e2e(i):
+        # every step: H2D of that step's batch from pinned host memory and D2H of its losses.  The copy of batch
+        # i + 1 is started (GAN_RNN.prefetch, a copy stream) before the schedule of batch i is waited for -- the
+        # double buffering any input pipeline does; the first batch of the loop is copied in line.
         x, y, ln = pinned[i % NB]
-        return model.train_batch(x, y, ln, sync=True)        # H2D of the batch, D2H of the losses
+        nx = pinned[(i + 1) % NB]
+        if getattr(step_e2e, "primed", None) != i:
+            model.prefetch(x, y, ln)
+        out = model.train_batch(x, y, ln, sync=False)
+        model.prefetch(*nx)
+        step_e2e.primed = i + 1
+        d_vals, g = out
+        return d_vals.tolist(), g.tolist()                   # D2H read of the step's losses (synchronises)
 
     def timed(fn, steps, warmup, sampler=None):
         for i in range(warmup):

@@ -173,6 +173,7 @@ class GAN_RNN(Model):
         self.use_graph = (_arg(args, "use_graph", True) and os.environ.get("RSR_NO_GRAPH", "0") != "1"
                           and dev.type == "cuda")
         self._graphs = {}
+        self._copy_stream, self._prefetched, self._prefetch_bufs = None, None, {}
         # With several ranks the schedule is captured as one graph SEGMENT per update; the NCCL all-reduce of the
         # flat gradient buffer runs eagerly between segments (capturing NCCL itself hung on 2 x B200 with
         # torch 2.11 / NCCL 2.28.9).  RSR_GRAPH_DDP=0: fully eager with several ranks.
@@ -426,6 +427,46 @@ class GAN_RNN(Model):
         return (B, T, self.disc_updates, self.gen_updates, self.d_real, self.d_fake, self.mse_lambda,
                 self.disc_noise_std, self.l2_scale, self.world)
 
+    def prefetch(self, inputs, labels, lengths):
+        """Starts the host->device copy of the NEXT minibatch on a copy stream, so that it overlaps the batch
+        schedule still running (the reference fills a queue from reader threads for the same reason,
+        scripts/train_gan_rnn_placeholder.py:469-478).  A later train_batch() called with the same objects picks
+        the device copies up instead of copying again.  Host tensors should be pinned."""
+        if self.h.device.type != "cuda":
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.h.device)
+        srcs = []
+        for a, dt in ((inputs, F32), (labels, F32), (lengths, torch.int32)):
+            t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(a))
+            srcs.append((t, dt))
+        key = tuple((tuple(t.shape), dt) for t, dt in srcs)
+        if self._prefetch_bufs.get("key") != key:           # two buffer sets, used alternately
+            self._prefetch_bufs = {"key": key, "sets": [[torch.empty(t.shape, dtype=dt, device=self.h.device)
+                                                         for t, dt in srcs] for _ in range(2)],
+                                   "free": [None, None], "next": 0}
+        pb = self._prefetch_bufs
+        k = pb["next"]
+        pb["next"] = k ^ 1
+        cs = self._copy_stream
+        if pb["free"][k] is not None:
+            cs.wait_event(pb["free"][k])                    # the schedule that read this set (two batches ago) has finished
+        with torch.cuda.stream(cs):
+            for (t, dt), d in zip(srcs, pb["sets"][k]):
+                d.copy_(t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+        self._prefetched = ((id(inputs), id(labels), id(lengths)), k, ev)
+
+    def _take_prefetched(self, inputs, labels, lengths):
+        pf = self._prefetched
+        if pf is None or pf[0] != (id(inputs), id(labels), id(lengths)):
+            return inputs, labels, lengths, None
+        self._prefetched = None
+        torch.cuda.current_stream().wait_event(pf[2])
+        x, y, ln = self._prefetch_bufs["sets"][pf[1]]
+        return x, y, ln, pf[1]
+
     def _schedule_graphed(self, inputs, labels, lengths):
         """Copies the minibatch into static device buffers and replays the captured schedule.  The first two
         calls for a given shape / scalar set run eagerly (they allocate the workspace), the third captures."""
@@ -493,12 +534,17 @@ class GAN_RNN(Model):
         """The per-batch schedule of train_one_iteration (scripts/train_gan_rnn_placeholder.py:72-101):
         disc_updates x D update then gen_updates x G update on the SAME minibatch, which is fed to the
         device once.  Returns the losses of the last D and the last G update."""
+        inputs, labels, lengths, pf_set = self._take_prefetched(inputs, labels, lengths)
         graphable = (self.use_graph and (self.world == 1 or self.graph_ddp) and self.h.timing is None
                      and self.D is not None and isinstance(inputs, (torch.Tensor, np.ndarray)))
         if graphable:
             d_vals, g = self._schedule_graphed(inputs, labels, lengths)
         else:
             d_vals, g = self._schedule(self._feed(inputs, labels, lengths))
+        if pf_set is not None:                              # this prefetch set may be overwritten once the schedule is done
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._prefetch_bufs["free"][pf_set] = ev
         out = OrderedDict()
         if not sync:
             return d_vals, g

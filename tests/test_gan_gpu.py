@@ -188,3 +188,28 @@ def test_cuda_graph_and_stream_overlap_match_eager_serial(g_type, d_type, kw):
     assert len(ma._graphs) == n_graphs + 1
     if d_type != "lstm":
         assert oa["g_loss"] == pytest.approx(ob["g_loss"], rel=2e-3)
+
+
+def test_prefetch_double_buffering_feeds_the_right_batches():
+    """GAN_RNN.prefetch starts the H2D copy of the next minibatch on a copy stream while the current schedule
+    runs; training with it must consume exactly the batches it was given, in order."""
+    B, T = 16, 12
+    rng = np.random.default_rng(4)
+    kw = dict(g_cell=256, g_proj=64, g_layers=1)
+    batches = []
+    for _ in range(3):
+        x, y = rng.standard_normal((B, T, 257)).astype(np.float32), rng.standard_normal((B, T, 40)).astype(np.float32)
+        ln = rng.integers(T // 2, T + 1, size=B).astype(np.float32)      # the reference feeds lengths as float32
+        batches.append(tuple(torch.from_numpy(v).pin_memory() for v in (x, y, ln)))
+    ma, mb = make_model("lstm", "dnn", B, **kw), make_model("lstm", "dnn", B, **kw)
+    order = [0, 1, 2, 0, 1, 2, 1]
+    for i in order:
+        ma.train_batch(*batches[i])
+    mb.prefetch(*batches[order[0]])
+    for n, i in enumerate(order):
+        out = mb.train_batch(*batches[i], sync=False)
+        if n + 1 < len(order):
+            mb.prefetch(*batches[order[n + 1]])
+    torch.cuda.synchronize()
+    for na, nb in ((ma.G, mb.G), (ma.D, mb.D)):
+        assert rms(na.P.theta.cpu().numpy(), nb.P.theta.cpu().numpy())[1] < 1e-4
