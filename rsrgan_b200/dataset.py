@@ -74,7 +74,11 @@ class PaddedBatches(object):
         self.batch_size, self.num_epochs, self.num_buckets = batch_size, num_epochs, num_buckets
         self.left, self.right = left_context, right_context
         self.input_size, self.output_size = input_size, output_size
-        self.cmvn, self.shuffle, self.infer = cmvn, shuffle and not infer, infer
+        # materialise the four arrays once: np.load's NpzFile reads lazily from a zip and is not thread-safe
+        self.cmvn = None if cmvn is None else {k: np.asarray(cmvn[k], np.float64) for k in
+                                               ("mean_inputs", "stddev_inputs", "mean_labels", "stddev_labels")
+                                               if k in cmvn}
+        self.shuffle, self.infer = shuffle and not infer, infer
         self.buffer_size = buffer_size
         self.rng = random.Random(seed)
         self.reader = ArkReader()
@@ -137,7 +141,10 @@ class PaddedBatches(object):
                     nxt["i"] += 1
                 if i >= len(order):
                     return
-                results[i] = self._load(order[i])
+                try:
+                    results[i] = self._load(order[i])
+                except BaseException as e:          # handed to the consumer, which re-raises (never a silent hang)
+                    results[i] = e
                 done[i].set()
 
         threads = [threading.Thread(target=work, daemon=True) for _ in range(self.num_threads)]
@@ -148,6 +155,8 @@ class PaddedBatches(object):
             done[i].wait()
             item, results[i] = results[i], None
             window.release()
+            if isinstance(item, BaseException):
+                raise RuntimeError("reading %s failed" % (order[i][0],)) from item
             if self.num_buckets > 1 and not self.infer:
                 key = min(self.num_buckets, (item[1].shape[0] - 200) // 50)
             else:
@@ -189,6 +198,8 @@ class Prefetcher(object):
             try:
                 for b in iterable:
                     self.q.put(b)
+            except BaseException as e:              # re-raised in the consumer
+                self.q.put(e)
             finally:
                 self.q.put(self._end)
 
@@ -200,4 +211,6 @@ class Prefetcher(object):
             b = self.q.get()
             if b is self._end:
                 return
+            if isinstance(b, BaseException):
+                raise b
             yield b

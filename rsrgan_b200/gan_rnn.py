@@ -413,14 +413,16 @@ class GAN_RNN(Model):
         # change until the first G update, so the D updates and that first G update all see the SAME G(x):
         # it is computed once (with the activations the G backward needs) and reused -- same numbers, 2 of the
         # 3 generator forwards of the schedule.
-        g32, d, g = None, None, None
+        g32 = None
+        d_all, g_all = [], []
         for _ in range(self.disc_updates):
             d = self.d_step(None, None, None, sync=False, _feed=feed, _g32=g32, _g_train=self.gen_updates > 0)
             g32 = self._last_g32
-        d_vals = d[:2].clone() if self.disc_updates else None
+            d_all.append(d[:2].clone())
         for k in range(self.gen_updates):
             g = self.g_step(None, None, None, sync=False, _feed=feed, _g32=g32 if k == 0 else None)
-        return d_vals, g
+            g_all.append(g.clone())
+        return d_all, g_all
 
     def _graph_key(self, B, T):
         # everything a captured kernel receives BY VALUE; learning rates and Adam powers live on the device
@@ -530,7 +532,7 @@ class GAN_RNN(Model):
         st["launches"] = self.h.launches - n0
         self.h.launches = n0
 
-    def train_batch(self, inputs, labels, lengths, sync=True):
+    def train_batch(self, inputs, labels, lengths, sync=True, all_updates=False):
         """The per-batch schedule of train_one_iteration (scripts/train_gan_rnn_placeholder.py:72-101):
         disc_updates x D update then gen_updates x G update on the SAME minibatch, which is fed to the
         device once.  Returns the losses of the last D and the last G update."""
@@ -538,21 +540,31 @@ class GAN_RNN(Model):
         graphable = (self.use_graph and (self.world == 1 or self.graph_ddp) and self.h.timing is None
                      and self.D is not None and isinstance(inputs, (torch.Tensor, np.ndarray)))
         if graphable:
-            d_vals, g = self._schedule_graphed(inputs, labels, lengths)
+            d_all, g_all = self._schedule_graphed(inputs, labels, lengths)
         else:
-            d_vals, g = self._schedule(self._feed(inputs, labels, lengths))
+            d_all, g_all = self._schedule(self._feed(inputs, labels, lengths))
         if pf_set is not None:                              # this prefetch set may be overwritten once the schedule is done
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
             self._prefetch_bufs["free"][pf_set] = ev
-        out = OrderedDict()
+        self._last_all = (d_all, g_all)
         if not sync:
-            return d_vals, g
-        if d_vals is not None:
-            out.update(self._loss_dict(d_vals.tolist() + [0.0] * 3, "d"))
-        if self.gen_updates:
-            out.update(self._loss_dict(g.tolist(), "g"))
+            return (d_all[-1] if d_all else None), (g_all[-1] if g_all else None)
+        if all_updates:
+            return self.last_update_losses()
+        out = OrderedDict()
+        if d_all:
+            out.update(self._loss_dict(d_all[-1].tolist() + [0.0] * 3, "d"))
+        if g_all:
+            out.update(self._loss_dict(g_all[-1].tolist(), "g"))
         return out
+
+    def last_update_losses(self):
+        """Losses of EVERY update of the last train_batch() -- ([D-update dicts], [G-update dicts]) -- as the
+        reference accumulates them per sess.run (scripts/train_gan_rnn_placeholder.py:85-111).  Synchronises."""
+        d_all, g_all = self._last_all
+        return ([self._loss_dict(v.tolist() + [0.0] * 3, "d") for v in d_all],
+                [self._loss_dict(v.tolist(), "g") for v in g_all])
 
     def eval_losses(self, inputs, labels, lengths, noise_rl=None, noise_fk=None, sync=True):
         """Loss-only pass of eval_one_iteration (scripts/train_gan_rnn_placeholder.py:154-172)."""

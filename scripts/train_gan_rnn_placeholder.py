@@ -51,7 +51,8 @@ def exponential_decay(iteration, num_jobs, num_iters, init_lr, multiply_jobs=Tru
 def load_cmvn():
     path = os.path.join(FLAGS.data_dir, "train_cmvn.npz") if FLAGS.data_dir else None
     if path and os.path.isfile(path):
-        return np.load(path)
+        with np.load(path) as z:
+            return {k: z[k] for k in z.files}
     return None
 
 
@@ -75,22 +76,36 @@ def world_mean(model, vals):
     return (t / model.world).tolist()
 
 
+def _train_and_prefetch(model, cur, nxt):
+    """Enqueues the schedule for `cur`, starts the upload of `nxt`, then reads the losses back."""
+    d_last, g_last = model.train_batch(cur[1], cur[2], cur[3], sync=False)
+    model.prefetch(nxt[1], nxt[2], nxt[3])
+    return model.last_update_losses()
+
+
 def train_one_iteration(model, batches, iteration):
     """scripts/train_gan_rnn_placeholder.py:48-133."""
     sums = np.zeros(7)
     d_counter = g_counter = 0
     model.d_real, model.d_fake = 1.0, 0.0
-    for _, inputs, labels, lengths in batches:
-        if inputs.shape[0] != FLAGS.batch_size:          # ragged tail batch: skipped (:69-70)
-            continue
-        for _ in range(model.disc_updates):
-            d = model.d_step(inputs, labels, lengths)
+    # One call per minibatch runs the whole schedule of :72-101 (disc_updates x D, gen_updates x G on the same
+    # batch) on the device; the next minibatch is uploaded meanwhile (GAN_RNN.prefetch).
+    full = (b for b in batches if b[1].shape[0] == FLAGS.batch_size)     # ragged tail batches are skipped (:69-70)
+    cur = next(full, None)
+    if cur is not None:
+        model.prefetch(cur[1], cur[2], cur[3])
+    while cur is not None:
+        nxt = next(full, None)
+        _, inputs, labels, lengths = cur
+        d_list, g_list = model.train_batch(inputs, labels, lengths, all_updates=True) if nxt is None else \
+            _train_and_prefetch(model, cur, nxt)
+        for d in d_list:
             d_counter += 1
             sums[0:3] += world_mean(model, [d["d_rl_loss"], d["d_fk_loss"], d["d_loss"]])
-        for _ in range(model.gen_updates):
-            g = model.g_step(inputs, labels, lengths)
+        for g in g_list:
             g_counter += 1
             sums[3:7] += world_mean(model, [g["g_adv_loss"], g["g_mse_loss"], g["g_l2_loss"], g["g_loss"]])
+        cur = nxt
     d_counter, g_counter = max(d_counter, 1), max(g_counter, 1)
     return tuple(sums[0:3] / d_counter) + tuple(sums[3:7] / g_counter)
 
