@@ -198,6 +198,29 @@ int rsr_l2_grad(rsr_handle* h, void* stream, float* grad, const float* theta, co
 int rsr_add_cast(rsr_handle* h, void* stream, const float* a, const float* b, long long n,
                  float* out32, void* out16);
 
+/* 1-D convolution family -------------------------------------------------------------- */
+/* tf.contrib.layers.conv2d(inputs, C_out, [splice, w], SAME, relu) of models/rced.py:90-101 with
+ * splice = 1 (a 1-D convolution over the 257 spectrum bins of one frame) is computed by rsr_gemm
+ * itself: activations are channels-last 16-bit rows [frames*S, Cp] (frame r = rows r*S .. r*S+S-1,
+ * positions 0..L-1 data, rows L..S-1 zero = the SAME padding shared with the next frame, S-L >= w/2,
+ * plus >= w/2 zero guard rows before the first and after the last frame), and the GEMM A operand is the
+ * OVERLAPPED view   A[m, k*Cp + c] = act[m - w/2 + k, c]   i.e. pointer act - (w/2)*Cp, lda = Cp,
+ * K = w*Cp; B = taps [w*Cin_p, Cout_p].  No im2col matrix is materialised; TMA reads the window.
+ *   forward        Y = relu(A(X) W + b)              then rsr_conv_mask_rows(Y)
+ *   weight grad    dW += A(X)^T dY  (a_mn = 1)       bias grad = rsr_colsum16(dY)
+ *   data grad      dX = A(dY) Wflip, times relu'(X)  Wflip from rsr_conv_w_flip
+ * The three helpers below are the layout glue around those GEMMs. */
+/* x fp32 frames ((B, T, L) batch-major, or [T*B, ldx] time-major) -> out16 [T*B*S, Cp]:
+ * row (t*B+b)*S + p, channel 0 = (x[b,t,p] - mean[p]) * istd[p] (mean/istd NULL = identity), every other
+ * element (channels 1.., rows p >= L) zero.  models/rced.py:46-57 (reshape to [batch, splice, input_dim, 1]). */
+int rsr_conv_stage_frames(rsr_handle* h, void* stream, const float* x, int ldx, int time_major_in,
+                          int B, int T, int L, int S, int Cp, const float* mean, const float* istd,
+                          void* out16);
+/* zeroes rows p in [L, S) of every frame (the GEMM computes garbage there). */
+int rsr_conv_mask_rows(rsr_handle* h, void* stream, void* buf16, long long frames, int S, int L, int Cp);
+/* out[k][co][ci] = w[W-1-k][ci][co]: taps of the transposed convolution (tf.gradients of conv2d wrt its input). */
+int rsr_conv_w_flip(rsr_handle* h, void* stream, const void* w16, int W, int Cin_p, int Cout_p, void* out16);
+
 /* misc ---------------------------------------------------------------------------------- */
 /* dst[c, r] = src[r, c] for r < rows, c < cols (16-bit elements; other elements of dst untouched):
  * keeps the K_x^T operand of rsr_lstmp_fused_fwd in step with the updated weights. */

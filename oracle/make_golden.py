@@ -24,6 +24,14 @@ CASES = {
     # name: (g_type, d_type, sizes, B, T)
     "gan_lstm_dlstm": ("lstm", "lstm", dict(g_cell=64, g_proj=32, g_layers=2, d_cell=32), 3, 7),
     "gan_res_ddnn": ("res_lstm_l", "dnn", dict(g_cell=40, g_layers=2, d_units=64), 2, 5),
+    # BASELINE.json configs[3] in small: RCED generator (models/rced.py, splice = 1) + discriminator_dnn on frames
+    "gan_rced_ddnn": ("rced", "dnn", dict(d_units=64), 3, 2),
+}
+
+# MSE-only trainer (models/dnn_trainer_single_gpu.py; BASELINE.json configs[0] in small): name -> (g_type, sizes, frames)
+MSE_CASES = {
+    "mse_dnn": ("dnn", dict(g_units=64), 24),
+    "mse_rced": ("rced", dict(), 6),
 }
 
 
@@ -32,6 +40,8 @@ def build(name):
     rng = np.random.default_rng(sum(map(ord, name)))
     if g_type == "lstm":
         gp = O.init_g_lstm(rng, cell=sz["g_cell"], proj=sz["g_proj"], layers=sz["g_layers"])
+    elif g_type == "rced":
+        gp = O.init_g_rced(rng)
     else:
         gp = O.init_g_res_lstm_l(rng, cell=sz["g_cell"], layers=sz["g_layers"])
     dp = O.init_d_lstm(rng, cell=sz["d_cell"]) if d_type == "lstm" else O.init_d_dnn(rng, units=sz["d_units"])
@@ -83,10 +93,45 @@ def compute(name):
     return out
 
 
+def compute_mse(name, l2_scale=1e-4, lr=1e-3, steps=2):
+    """x, y, weights; generator output, g_mse / g_l2 / g_loss, raw gradients; losses and output after `steps` Adam updates."""
+    g_type, sz, N = MSE_CASES[name]
+    rng = np.random.default_rng(sum(map(ord, name)))
+    gp = O.init_g_dnn(rng, units=sz["g_units"]) if g_type == "dnn" else O.init_g_rced(rng)
+    for k in gp:
+        if "bias" in k:
+            gp[k] = gp[k] + rng.standard_normal(gp[k].shape) * 0.1
+    out = OrderedDict(x=rng.standard_normal((N, 257)).astype(np.float32),
+                      y=rng.standard_normal((N, 40)).astype(np.float32),
+                      l2_scale=np.float64(l2_scale), lr=np.float64(lr), steps=np.int32(steps))
+    for k, v in gp.items():
+        out["G/" + k] = v.astype(np.float32)
+    st = O.MseState(OrderedDict((k, out["G/" + k].astype(np.float64)) for k in gp), g_type)
+    x64, y64 = out["x"].astype(np.float64), out["y"].astype(np.float64)
+    L, gr, g_out = O.mse_losses_and_grads(st.g, g_type, x64, y64, l2_scale)
+    out["g_out"] = g_out
+    for k, v in L.items():
+        out["loss/" + k] = np.float64(v)
+    for k, v in gr.items():
+        out["ggrad/" + k] = v.astype(np.float32)
+    for _ in range(steps):
+        O.mse_step(st, x64, y64, lr, l2_scale)
+    L, _, g_out = O.mse_losses_and_grads(st.g, g_type, x64, y64, l2_scale)
+    out["g_out_after"] = g_out
+    for k, v in L.items():
+        out["loss_after/" + k] = np.float64(v)
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for name in CASES:
-        np.savez_compressed(os.path.join(OUT, name + ".npz"), **compute(name))
+    import sys
+    only = sys.argv[1:]
+    for name in list(CASES) + list(MSE_CASES):
+        if only and name not in only:
+            continue
+        d = compute(name) if name in CASES else compute_mse(name)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
         print("wrote", name, os.path.getsize(os.path.join(OUT, name + ".npz")), "bytes")
 
 

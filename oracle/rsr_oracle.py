@@ -87,6 +87,35 @@ def linear_bwd(dy, cache):
     return dx, dW, db
 
 
+def conv1d_same_fwd(x, W, b, act=ACT_RELU):
+    """tf.contrib.layers.conv2d(inputs, C_out, [splice, w], padding=SAME, relu) with splice = 1
+    (models/rced.py:90-101): inputs NHWC (N, 1, L, C_in) -> here (N, L, C_in); W is the TF filter
+    (1, w, C_in, C_out); stride 1; w odd, so SAME pads w//2 zeros on both sides.
+        u[n, p, :] = b + sum_k x[n, p - w//2 + k, :] @ W[0, k]"""
+    assert W.shape[0] == 1 and W.shape[1] % 2 == 1, "splice = 1, odd filter width"
+    N, L, _ = x.shape
+    w = W.shape[1]
+    xp = np.zeros((N, L + w - 1, x.shape[2]), x.dtype)
+    xp[:, w // 2:w // 2 + L] = x
+    u = np.zeros((N, L, W.shape[3]), np.result_type(x, W)) + b
+    for k in range(w):
+        u += xp[:, k:k + L] @ W[0, k]
+    return act_fwd(u, act), (xp, W, u, act)
+
+
+def conv1d_same_bwd(dy, cache):
+    xp, W, u, act = cache
+    N, L, _ = u.shape
+    w = W.shape[1]
+    du = act_bwd(u, dy, act)
+    dW = np.zeros_like(W)
+    dxp = np.zeros_like(xp)
+    for k in range(w):
+        dW[0, k] = np.einsum("nlc,nld->cd", xp[:, k:k + L], du)
+        dxp[:, k:k + L] += du @ W[0, k].T
+    return dxp[:, w // 2:w // 2 + L], dW, du.sum((0, 1))
+
+
 # --------------------------------------------------------------------------
 # LSTMP cell with peepholes == tf.contrib.rnn.LSTMCell(use_peepholes=True,
 # num_proj=P, forget_bias=1.0) under tf.nn.dynamic_rnn(sequence_length=...)
@@ -185,6 +214,8 @@ def xavier(rng, shape, dtype=np.float64):
     """tf.contrib.layers.xavier_initializer(): U(+-sqrt(6/(fan_in+fan_out)))."""
     if len(shape) == 1:
         fan_in = fan_out = shape[0]
+    elif len(shape) == 4:      # conv filter (h, w, C_in, C_out): receptive field x channels
+        fan_in, fan_out = shape[0] * shape[1] * shape[2], shape[0] * shape[1] * shape[3]
     else:
         fan_in, fan_out = shape[0], shape[1]
     lim = math.sqrt(6.0 / (fan_in + fan_out))
@@ -223,6 +254,36 @@ def init_g_res_lstm_l(rng, in_dim=257, out_dim=40, cell=760, layers=4,
                    in_dim, cell, in_dim, dtype)
     p["g_model/forward_out/fully_connected/weights"] = xavier(rng, (in_dim, out_dim), dtype)
     p["g_model/forward_out/fully_connected/biases"] = np.zeros(out_dim, dtype)
+    return p
+
+
+def init_g_dnn(rng, in_dim=257, out_dim=40, units=1024, hidden=3, dtype=np.float64):
+    """models/dnn.py:34-35,79-110: in -> units x (1 + hidden) ReLU -> out, xavier weights, zero biases."""
+    p = OrderedDict()
+    dims = [in_dim] + [units] * (hidden + 1) + [out_dim]
+    for l in range(hidden + 2):
+        name = "g_model/fully_connected" + ("" if l == 0 else "_%d" % l)
+        p[name + "/weights"] = xavier(rng, (dims[l], dims[l + 1]), dtype)
+        p[name + "/biases"] = np.zeros(dims[l + 1], dtype)
+    return p
+
+
+RCED_FILTERS = (12, 16, 20, 24, 32, 24, 20, 16, 12)      # models/rced.py:92
+RCED_WIDTHS = (13, 11, 9, 7, 7, 7, 9, 11, 13)            # models/rced.py:93
+
+
+def init_g_rced(rng, in_dim=257, out_dim=40, filters=RCED_FILTERS, widths=RCED_WIDTHS, dtype=np.float64):
+    """models/rced.py:90-114 with splice = 1: nine conv2d [1, w] (xavier, zero bias; contrib default scopes
+    Conv, Conv_1, ...), then FC (in_dim * filters[-1]) -> out_dim with bias 0.1 (:108-113)."""
+    p = OrderedDict()
+    cin = 1
+    for l, (c, w) in enumerate(zip(filters, widths)):
+        name = "g_model/Conv" + ("" if l == 0 else "_%d" % l)
+        p[name + "/weights"] = xavier(rng, (1, w, cin, c), dtype)
+        p[name + "/biases"] = np.zeros(c, dtype)
+        cin = c
+    p["g_model/fully_connected/weights"] = xavier(rng, (in_dim * cin, out_dim), dtype)
+    p["g_model/fully_connected/biases"] = np.full(out_dim, 0.1, dtype)
     return p
 
 
@@ -404,7 +465,73 @@ def d_dnn_bwd(p, dy, caches):
     return dh, g
 
 
+def _fc_names(p, scope):
+    names = sorted({k.rsplit("/", 1)[0] for k in p if k.startswith(scope + "/fully_connected")},
+                   key=lambda s: int(s.split("_")[-1]) if s[-1].isdigit() else 0)
+    return names
+
+
+def g_dnn_fwd(p, x, lengths=None):
+    """models/dnn.py:79-110 applied per frame (no sequence dependence; lengths unused)."""
+    caches = []
+    h = x
+    names = _fc_names(p, "g_model")
+    for n in names[:-1]:
+        h, c = linear_fwd(h, p[n + "/weights"], p[n + "/biases"], ACT_RELU)
+        caches.append(c)
+    y, c = linear_fwd(h, p[names[-1] + "/weights"], p[names[-1] + "/biases"], ACT_NONE)
+    caches.append(c)
+    return y, caches
+
+
+def g_dnn_bwd(p, dy, caches):
+    g = OrderedDict()
+    dh = dy
+    for n, c in zip(reversed(_fc_names(p, "g_model")), reversed(caches)):
+        dh, dW, db = linear_bwd(dh, c)
+        g[n + "/weights"] = dW
+        g[n + "/biases"] = db
+    return dh, g
+
+
+def _conv_names(p):
+    return sorted({k.rsplit("/", 1)[0] for k in p if k.startswith("g_model/Conv")},
+                  key=lambda s: int(s.split("_")[-1]) if s[-1].isdigit() else 0)
+
+
+def g_rced_fwd(p, x, lengths=None):
+    """models/rced.py:46-57,90-114, splice = 1: every frame (leading dims flattened) is a length-257 signal with
+    one channel; nine ReLU convs; the NHWC tensor (N, 1, 257, 12) is flattened position-major / channel-minor
+    (tf.reshape, :106) into the linear output layer."""
+    lead, L = x.shape[:-1], x.shape[-1]
+    h = x.reshape(-1, L, 1)
+    caches = []
+    for n in _conv_names(p):
+        h, c = conv1d_same_fwd(h, p[n + "/weights"], p[n + "/biases"], ACT_RELU)
+        caches.append(c)
+    flat = h.reshape(h.shape[0], -1)
+    y, c = linear_fwd(flat, p["g_model/fully_connected/weights"], p["g_model/fully_connected/biases"], ACT_NONE)
+    caches.append((c, h.shape))
+    return y.reshape(*lead, -1), caches
+
+
+def g_rced_bwd(p, dy, caches):
+    g = OrderedDict()
+    c, hshape = caches[-1]
+    dh, dW, db = linear_bwd(dy.reshape(-1, dy.shape[-1]), c)
+    g["g_model/fully_connected/weights"] = dW
+    g["g_model/fully_connected/biases"] = db
+    dh = dh.reshape(hshape)
+    for n, cc in zip(reversed(_conv_names(p)), reversed(caches[:-1])):
+        dh, dW, db = conv1d_same_bwd(dh, cc)
+        g[n + "/weights"] = dW
+        g[n + "/biases"] = db
+    return dh[..., 0].reshape(dy.shape[:-1] + (-1,)), g
+
+
 GENERATORS = {
+    "dnn": (g_dnn_fwd, g_dnn_bwd),
+    "rced": (g_rced_fwd, g_rced_bwd),
     "lstm": (g_lstm_fwd, g_lstm_bwd),
     "res_lstm_l": (g_res_lstm_l_fwd, g_res_lstm_l_bwd),
     "res_lstm_base": (lambda p, x, l: g_res_lstm_l_fwd(p, x, l, False),
@@ -584,3 +711,43 @@ def g_step(st, towers, lr_g, max_norm=15.0, ema_decay=0.9999, **kw):
         st.g, clipped, st.adam_m, st.adam_v, st.adam_t, lr_g)
     st.g_ema = ema_update(st.g_ema, st.g, ema_decay)
     return [r[0] for r in res], clipped
+
+
+# --------------------------------------------------------------------------
+# MSE-only generator training: models/dnn_trainer_single_gpu.py:93-133
+# (BASELINE.json configs[0]; also the RCED trainer's loss)
+# --------------------------------------------------------------------------
+
+
+def mse_losses_and_grads(g_params, g_type, x, y, l2_scale=0.0):
+    """g_mse = 0.5 * output_dim * mean((G(x)-y)^2) (:109-110); g_l2 = sum over WEIGHTS (contrib
+    l2_regularizer is attached to weights only, dnn.py:64-67,85-86) of l2_scale * 0.5 ||W||^2 (:111-115);
+    gradients of g_mse + g_l2 wrt every g_ variable (:102-104 minimize, no clipping)."""
+    gf, gb = GENERATORS[g_type]
+    g_out, gc = gf(g_params, x, None)
+    out_dim = y.shape[-1]
+    losses = dict(g_mse_loss=0.5 * out_dim * float(np.mean((g_out - y) ** 2)), g_l2_loss=0.0)
+    _, grads = gb(g_params, out_dim * (g_out - y) / g_out.size, gc)
+    grads = OrderedDict((k, grads[k]) for k in g_params)
+    if l2_scale > 0.0:
+        losses["g_l2_loss"] = l2_scale * sum(0.5 * float((v * v).sum()) for k, v in g_params.items()
+                                             if k.endswith("weights"))
+        for k in grads:
+            if k.endswith("weights"):
+                grads[k] = grads[k] + l2_scale * g_params[k]
+    losses["g_loss"] = losses["g_mse_loss"] + losses["g_l2_loss"]
+    return losses, grads, g_out
+
+
+class MseState(object):
+    def __init__(self, g_params, g_type="dnn"):
+        self.g, self.g_type = g_params, g_type
+        z = lambda: OrderedDict((k, np.zeros_like(v)) for k, v in g_params.items())
+        self.adam_m, self.adam_v, self.adam_t = z(), z(), 0
+
+
+def mse_step(st, x, y, lr, l2_scale=0.0):
+    """One DNNTrainer update: Adam(lr) on g_mse + g_l2, no clipping, no EMA."""
+    losses, grads, g_out = mse_losses_and_grads(st.g, st.g_type, x, y, l2_scale)
+    st.g, st.adam_m, st.adam_v, st.adam_t = adam_update_tf(st.g, grads, st.adam_m, st.adam_v, st.adam_t, lr)
+    return losses, grads

@@ -87,7 +87,36 @@ def d_dnn(p, x, lengths=None, noise=None):
     return torch.clamp(y, -0.5, 1.5)
 
 
-GEN = {"lstm": g_lstm, "res_lstm_l": g_res_lstm_l,
+def _fc_names(p, scope):
+    return sorted({k.rsplit("/", 1)[0] for k in p if k.startswith(scope + "/fully_connected")},
+                  key=lambda s: int(s.split("_")[-1]) if s[-1].isdigit() else 0)
+
+
+def g_dnn(p, x, lengths=None):
+    """models/dnn.py:79-110."""
+    names = _fc_names(p, "g_model")
+    h = x
+    for n in names[:-1]:
+        h = torch.relu(h @ p[n + "/weights"] + p[n + "/biases"])
+    return h @ p[names[-1] + "/weights"] + p[names[-1] + "/biases"]
+
+
+def g_rced(p, x, lengths=None):
+    """models/rced.py:90-114 with splice = 1, through torch.nn.functional.conv2d on the NHWC->NCHW tensor."""
+    import torch.nn.functional as F
+    lead, L = x.shape[:-1], x.shape[-1]
+    h = x.reshape(-1, 1, 1, L)                                  # N, C=1, H=splice=1, W=257
+    names = sorted({k.rsplit("/", 1)[0] for k in p if k.startswith("g_model/Conv")},
+                   key=lambda s: int(s.split("_")[-1]) if s[-1].isdigit() else 0)
+    for n in names:
+        W = p[n + "/weights"].permute(3, 2, 0, 1)               # TF HWIO -> torch OIHW
+        h = torch.relu(F.conv2d(h, W, p[n + "/biases"], padding=(0, W.shape[3] // 2)))
+    flat = h.permute(0, 2, 3, 1).reshape(h.shape[0], -1)        # NHWC flatten (tf.reshape, :106)
+    y = flat @ p["g_model/fully_connected/weights"] + p["g_model/fully_connected/biases"]
+    return y.reshape(*lead, -1)
+
+
+GEN = {"lstm": g_lstm, "res_lstm_l": g_res_lstm_l, "dnn": g_dnn, "rced": g_rced,
        "res_lstm_base": lambda p, x, l: g_res_lstm_l(p, x, l, False)}
 DIS = {"lstm": d_lstm, "dnn": d_dnn}
 

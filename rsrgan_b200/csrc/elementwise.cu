@@ -325,6 +325,65 @@ __global__ void __launch_bounds__(256) clip_update_kernel(const float* __restric
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// 1-D convolution family (models/rced.py:90-101): the convolutions themselves run on the tcgen05
+// GEMM over an OVERLAPPED strided view of the channels-last frame buffer (row m of the view =
+// taps m-w/2 .. m+w/2, row pitch = one position), so no im2col matrix is ever written.  What
+// remains here is the layout glue: frames -> padded channels-last rows, re-zeroing the SAME
+// padding rows after each layer, and the flipped/transposed taps for the data gradient.
+// Frame layout: frame r occupies rows [r*S, r*S+S) of a [*, Cp] 16-bit buffer, positions
+// 0..L-1 hold data, rows L..S-1 are the zero padding shared by this frame's right edge and the
+// next frame's left edge (S - L >= w/2).
+// ---------------------------------------------------------------------------------------
+__global__ void conv_stage_frames_kernel(const float* __restrict__ x, int ldx, int time_major_in, int B, int T, int L,
+                                         int S, int Cp, const float* __restrict__ mean, const float* __restrict__ istd,
+                                         uint16_t* __restrict__ out, int bf) {
+    const int chunks = Cp / 8;
+    const long long total = (long long)B * T * S * chunks;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % chunks);
+        const long long row = i / chunks;        // r*S + p
+        const int p = (int)(row % S);
+        const long long r = row / S;             // output frame = t*B + b
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (c == 0 && p < L) {
+            const int b = (int)(r % B);
+            const int t = (int)(r / B);
+            float v = time_major_in ? x[r * ldx + p] : x[((long long)b * T + t) * ldx + p];
+            if (mean) v = (v - mean[p]) * istd[p];
+            o.x = (uint32_t)f2h(v, bf);          // channel 0 = the spectrum bin, channels 1.. are zero padding
+        }
+        *reinterpret_cast<uint4*>(out + row * Cp + 8 * c) = o;
+    }
+}
+
+__global__ void conv_mask_rows_kernel(uint16_t* __restrict__ buf, long long frames, int S, int L, int Cp) {
+    const int chunks = Cp / 8, pad = S - L;
+    const long long total = frames * pad * chunks;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % chunks);
+        const long long q = i / chunks;
+        const int p = L + (int)(q % pad);
+        const long long r = q / pad;
+        *reinterpret_cast<uint4*>(buf + (r * S + p) * Cp + 8 * c) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// out[k][co][ci] = w[W-1-k][ci][co]   (w: [W, Cin_p, Cout_p], out: [W, Cout_p, Cin_p])
+__global__ void conv_w_flip_kernel(const uint16_t* __restrict__ w, int W, int Cin_p, int Cout_p,
+                                   uint16_t* __restrict__ out) {
+    const int total = W * Cin_p * Cout_p;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ci = i % Cin_p;
+        const int co = (i / Cin_p) % Cout_p;
+        const int k = i / (Cin_p * Cout_p);
+        out[i] = w[((W - 1 - k) * Cin_p + ci) * Cout_p + co];
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
@@ -497,6 +556,38 @@ extern "C" int rsr_fill32(rsr_handle* h, void* stream, float* x, long long n, fl
     if (!h || !x || n < 0) return RSR_E_ARG;
     if (n == 0) return 0;
     fill32_kernel<<<grid_for(n, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(x, n, v);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_conv_stage_frames(rsr_handle* h, void* stream, const float* x, int ldx, int time_major_in,
+                                     int B, int T, int L, int S, int Cp, const float* mean, const float* istd,
+                                     void* out16) {
+    if (!h || !x || !out16 || B <= 0 || T <= 0 || L <= 0) return RSR_E_ARG;
+    if ((mean == nullptr) != (istd == nullptr)) return RSR_E_ARG;
+    if (S < L || Cp < 8 || (Cp & 7) || ldx < L || ((uintptr_t)out16 & 15)) return RSR_E_SHAPE;
+    const long long total = (long long)B * T * S * (Cp / 8);
+    conv_stage_frames_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, time_major_in, B, T, L, S, Cp, mean, istd, (uint16_t*)out16, h->dtype == RSR_DTYPE_BF16);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_conv_mask_rows(rsr_handle* h, void* stream, void* buf16, long long frames, int S, int L, int Cp) {
+    if (!h || !buf16 || frames <= 0) return RSR_E_ARG;
+    if (S < L || L <= 0 || Cp < 8 || (Cp & 7) || ((uintptr_t)buf16 & 15)) return RSR_E_SHAPE;
+    if (S == L) return 0;
+    const long long total = frames * (S - L) * (Cp / 8);
+    conv_mask_rows_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        (uint16_t*)buf16, frames, S, L, Cp);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_conv_w_flip(rsr_handle* h, void* stream, const void* w16, int W, int Cin_p, int Cout_p, void* out16) {
+    if (!h || !w16 || !out16 || W <= 0 || Cin_p <= 0 || Cout_p <= 0) return RSR_E_ARG;
+    conv_w_flip_kernel<<<grid_for((long long)W * Cin_p * Cout_p, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        (const uint16_t*)w16, W, Cin_p, Cout_p, (uint16_t*)out16);
     RSR_LAUNCH_CHECK();
     return 0;
 }

@@ -214,7 +214,9 @@ class GAN_RNN(Model):
             p = OrderedDict()
             for s in net.P.segs.values():
                 if "bias" in s.name:
-                    p[s.name] = np.zeros(s.tf_shape, np.float32)
+                    # zeros everywhere except the RCED output layer (models/rced.py:112 constant_initializer(0.1))
+                    rced_out = self.g_type == "rced" and s.name == "g_model/fully_connected/biases"
+                    p[s.name] = np.full(s.tf_shape, 0.1 if rced_out else 0.0, np.float32)
                 elif self.d_type == "dnn" and s.name.startswith("d_model") and s.tf_shape[-1] != 1:
                     std = math.sqrt(2.0 / s.tf_shape[1])
                     v = rng.standard_normal(s.tf_shape)
@@ -224,7 +226,11 @@ class GAN_RNN(Model):
                         bad = np.abs(v) > 2
                     p[s.name] = (v * std).astype(np.float32)
                 else:
-                    fi, fo = (s.tf_shape[0], s.tf_shape[0]) if len(s.tf_shape) == 1 else s.tf_shape
+                    if len(s.tf_shape) == 4:               # conv filter (h, w, C_in, C_out)
+                        rf = s.tf_shape[0] * s.tf_shape[1]
+                        fi, fo = rf * s.tf_shape[2], rf * s.tf_shape[3]
+                    else:
+                        fi, fo = (s.tf_shape[0], s.tf_shape[0]) if len(s.tf_shape) == 1 else s.tf_shape
                     lim = math.sqrt(6.0 / (fi + fo))
                     p[s.name] = rng.uniform(-lim, lim, s.tf_shape).astype(np.float32)
             net.load_tf(p)

@@ -3,7 +3,7 @@
 Mirrors the reference's L2 layer:
   * generators  `lstm` (models/lstm.py:41-129), `res_lstm_l` (models/res_lstm_l.py:41-199),
     `res_lstm_base` (models/res_lstm_base.py:111-131,190) and the frame-level `dnn`
-    (models/dnn.py:32-114);
+    (models/dnn.py:32-114) and `rced` (models/rced.py:34-119, splice = 1);
   * discriminators `discriminator_lstm` (models/discriminator_lstm.py:24-110) and
     `discriminator_dnn` (models/discriminator_dnn.py:21-98, applied per frame).
 The reference hard-codes the layer sizes inside those files; here they are constructor
@@ -197,6 +197,117 @@ class LSTMP(object):
                        out32=P.view(self.prefix + "projection/kernel", "grad"))
         return dx16, dx32
 
+class ConvFrames(object):
+    """The frame layout shared by the layers of the convolutional generator (models/rced.py:46-57, splice = 1):
+    frame r = rows [r*S, r*S+S) of a channels-last 16-bit buffer, positions 0..L-1 data, rows L..S-1 zero (the
+    SAME padding shared with the next frame), GUARD zero rows before the first / after the last frame."""
+    GUARD = 8
+
+    def __init__(self, L, max_width):
+        self.L = L
+        self.S = packing.round_up(L + max_width // 2, 8)
+        assert max_width // 2 <= self.GUARD
+
+    def buf(self, net, key, frames, cp):
+        """-> (whole buffer incl. guards, view of the frames*S data rows)"""
+        t = net.ws.get(key, frames * self.S + 2 * self.GUARD, cp, net.h.h16)
+        return t, t[self.GUARD:self.GUARD + frames * self.S]
+
+    def window(self, whole, frames, cp, width):
+        """Overlapped view A[m, k*cp + c] = act[m - width//2 + k, c]: the GEMM A operand of a SAME convolution
+        (include/rsrgan_b200.h, "1-D convolution family").  No copy."""
+        return whole.as_strided((frames * self.S, width * cp), (cp, 1),
+                                whole.storage_offset() + (self.GUARD - width // 2) * cp)
+
+
+class Conv1dSame(object):
+    """tf.contrib.layers.conv2d(inputs, C_out, [1, w], padding=SAME, activation_fn=relu) -- models/rced.py:94-101 with
+    splice = 1.  Forward, data gradient and weight gradient are rsr_gemm calls over overlapped views."""
+
+    def __init__(self, net, scope, fl, width, c_in, c_out):
+        self.net, self.scope, self.fl, self.W, self.c_in, self.c_out = net, scope, fl, width, c_in, c_out
+        self.cip, self.cop = packing.round_up(c_in, 8), packing.round_up(c_out, 8)
+        self.wname, self.bname = scope + "/weights", scope + "/biases"
+        h = net.h
+        self.wflip16 = torch.zeros(width * self.cop, self.cip, dtype=h.h16, device=h.device)
+
+    def segs(self):
+        return [params.conv_w(self.wname, self.W, self.c_in, self.c_out), params.fc_b(self.bname, self.c_out)]
+
+    def refresh(self):
+        """taps of the transposed convolution (data gradient) after every weight update"""
+        self.net.h.conv_w_flip(self.net.P.view(self.wname, "theta16"), self.W, self.cip, self.cop, self.wflip16)
+
+    def fwd(self, ctx, x_whole, frames):
+        net, h, fl = self.net, self.net.h, self.fl
+        y_whole, y = fl.buf(net, (ctx, self.scope, "y16", frames), frames, self.cop)
+        rows = frames * fl.S
+        h.gemm(fl.window(x_whole, frames, self.cip, self.W), net.P.view(self.wname, "theta16"), rows, self.cop,
+               self.W * self.cip, b_mn=True, bias=net.P.view(self.bname), act=ACT_RELU, out16=y)
+        h.conv_mask_rows(y, frames, fl.S, fl.L, self.cop)
+        return y_whole
+
+    def bwd(self, ctx, x_whole, dy_whole, frames, want_dx=True):
+        """dy_whole: gradient wrt this layer's PRE-activation (padding rows zero).  Returns the gradient wrt the
+        producer's pre-activation (times relu'(x), which also zeroes its padding rows)."""
+        net, h, fl = self.net, self.net.h, self.fl
+        rows = frames * fl.S
+        G = fl.GUARD
+        dy = dy_whole[G:G + rows]
+        dx_whole = None
+        if want_dx:
+            dx_whole, dx = fl.buf(net, (ctx, self.scope, "dx16", frames), frames, self.cip)
+            h.gemm(fl.window(dy_whole, frames, self.cop, self.W), self.wflip16, rows, self.cip, self.W * self.cop,
+                   b_mn=True, dact_src=x_whole[G:G + rows], dact=ACT_RELU, out16=dx)
+        with h.side_stream():
+            h.gemm(fl.window(x_whole, frames, self.cip, self.W), dy, self.W * self.cip, self.cop, rows, a_mn=True,
+                   b_mn=True, beta=1.0, out32=net.P.view(self.wname, "grad"))
+            h.colsum16(dy, rows, self.cop, net.P.view(self.bname, "grad"), accumulate=True)
+        return dx_whole
+
+
+class FCFrames(object):
+    """fully_connected over the flattened NHWC frame (models/rced.py:106-113): one GEMM whose A rows are whole
+    frames of the channels-last buffer (row pitch S*Cp, K = L*Cp; padded channels meet zero weight rows)."""
+
+    def __init__(self, net, scope, fl, chans, n_out):
+        self.net, self.scope, self.fl, self.chans, self.n_out = net, scope, fl, chans, n_out
+        self.cp, self.outp = packing.round_up(chans, 8), packing.round_up(n_out, 8)
+        self.wname, self.bname = scope + "/weights", scope + "/biases"
+
+    def segs(self):
+        return [params.fc_w_frames(self.wname, self.fl.L, self.chans, self.n_out), params.fc_b(self.bname, self.n_out)]
+
+    def refresh(self):
+        pass
+
+    def _frames(self, whole, frames):
+        fl = self.fl
+        return whole.as_strided((frames, fl.L * self.cp), (fl.S * self.cp, 1),
+                                whole.storage_offset() + fl.GUARD * self.cp)
+
+    def fwd(self, ctx, x_whole, frames):
+        net, h = self.net, self.net.h
+        y32 = net.ws.get((ctx, self.scope, "y32"), frames, self.outp, F32)
+        h.gemm(self._frames(x_whole, frames), net.P.view(self.wname, "theta16"), frames, self.outp,
+               self.fl.L * self.cp, b_mn=True, bias=net.P.view(self.bname), out32=y32)
+        return y32
+
+    def bwd(self, ctx, x_whole, dy16, frames):
+        """-> gradient wrt the last convolution's pre-activation, in the frame layout"""
+        net, h, fl = self.net, self.net.h, self.fl
+        K = fl.L * self.cp
+        dx_whole, _ = fl.buf(net, (ctx, self.scope, "dx16", frames), frames, self.cp)
+        xf = self._frames(x_whole, frames)
+        h.gemm(dy16, net.P.view(self.wname, "theta16"), frames, K, self.outp, dact_src=xf, dact=ACT_RELU,
+               out16=self._frames(dx_whole, frames))
+        with h.side_stream():
+            h.gemm(xf, dy16, K, self.outp, frames, a_mn=True, b_mn=True, beta=1.0,
+                   out32=net.P.view(self.wname, "grad"))
+            h.colsum16(dy16, frames, self.outp, net.P.view(self.bname, "grad"), accumulate=True)
+        return dx_whole
+
+
 class Net(object):
     """Common part: parameter store, workspace, weight-derived operands."""
 
@@ -217,6 +328,10 @@ class Net(object):
     def refresh(self):
         for l in self.layers:
             l.refresh()
+
+
+RCED_FILTERS = (12, 16, 20, 24, 32, 24, 20, 16, 12)      # models/rced.py:92
+RCED_WIDTHS = (13, 11, 9, 7, 7, 7, 9, 11, 13)            # models/rced.py:93
 
 
 class Generator(Net):
@@ -249,6 +364,17 @@ class Generator(Net):
                 ls = [FC(net, "g_model/fully_connected" + ("" if i == 0 else "_%d" % i), dims[i], dims[i + 1],
                          ACT_RELU) for i in range(L + 1)]
                 return ls + [FC(net, "g_model/fully_connected_%d" % (L + 1), units, out_dim, ACT_NONE)]
+        elif g_type == "rced":
+            # models/rced.py:92-101: nine [1, w] ReLU convolutions over the spectrum bins of each frame, then
+            # FC (in_dim * 12) -> out_dim.  splice = 1 only (the [splice, w] 2-D case is not on this path).
+            filt, wid = RCED_FILTERS, RCED_WIDTHS
+            self.frames = ConvFrames(in_dim, max(wid))
+
+            def mk(net):
+                ch = (1,) + filt
+                ls = [Conv1dSame(net, "g_model/Conv" + ("" if i == 0 else "_%d" % i), self.frames, wid[i], ch[i],
+                                 ch[i + 1]) for i in range(len(filt))]
+                return ls + [FCFrames(net, "g_model/fully_connected", self.frames, filt[-1], out_dim)]
         else:
             raise ValueError("Unrecognized G type {}".format(g_type))   # models/gan_rnn_placeholder.py:131-132
         super(Generator, self).__init__(handle, mk, adam=True)
@@ -257,6 +383,16 @@ class Generator(Net):
     def fwd(self, x, B, T, lengths, train=True, x_time_major=False):
         """x fp32 (B, T, in_dim) batch-major on the device -> y32 [T*B, out_pad] time-major fp32."""
         h, ws, rows = self.h, self.ws, T * B
+        if self.g_type == "rced":
+            self._B, self._T, self._len = B, T, lengths
+            fl, Ls = self.frames, self.layers
+            a, _ = fl.buf(self, ("g", "x16", rows), rows, Ls[0].cip)
+            h.conv_stage_frames(x, B, T, self.in_dim, fl.S, Ls[0].cip, a[fl.GUARD:], time_major_in=x_time_major)
+            self._acts = [a]
+            for l in Ls[:-1]:
+                a = l.fwd("g", a, rows)
+                self._acts.append(a)
+            return Ls[-1].fwd("g", a, rows)
         ip = packing.round_up(self.in_dim, 8)
         res = self.g_type in ("res_lstm_l", "res_lstm_base")
         x16 = ws.get(("g", "x16", B), rows, ip, h.h16)
@@ -300,6 +436,11 @@ class Generator(Net):
         """dy16 [T*B, out_pad]: (scaled) gradient wrt the generator output.  Accumulates into P.grad."""
         B, T, lengths, rows = self._B, self._T, self._len, self._T * self._B
         acts, Ls = self._acts, self.layers
+        if self.g_type == "rced":
+            d = Ls[-1].bwd("g", acts[-1], dy16, rows)
+            for i in range(len(Ls) - 2, -1, -1):
+                d = Ls[i].bwd("g", acts[i], d, rows, want_dx=i > 0)
+            return
         if self.g_type == "dnn":
             d = dy16
             for i in range(len(Ls) - 1, -1, -1):

@@ -217,3 +217,15 @@ class Handle(object):
 
     def fill32(self, x, v):
         self._call("rsr_fill32", 1, self.h, _stream(), _p(x), x.numel(), v)
+
+    # ------------------------------------------------------------- 1-D conv glue
+    def conv_stage_frames(self, x, B, T, L, S, Cp, out16, mean=None, istd=None, time_major_in=False, ldx=None):
+        self._call("rsr_conv_stage_frames", 1, self.h, _stream(), _p(x),
+                   ldx if ldx is not None else (x.stride(0) if time_major_in else L), int(time_major_in),
+                   B, T, L, S, Cp, _p(mean), _p(istd), _p(out16))
+
+    def conv_mask_rows(self, buf16, frames, S, L, Cp):
+        self._call("rsr_conv_mask_rows", 1, self.h, _stream(), _p(buf16), frames, S, L, Cp)
+
+    def conv_w_flip(self, w16, W, cin_p, cout_p, out16):
+        self._call("rsr_conv_w_flip", 1, self.h, _stream(), _p(w16), W, cin_p, cout_p, _p(out16))

@@ -40,6 +40,21 @@ def fc_b(name, n_out):
     return Seg(name, "vec", (n_out,), (packing.round_up(n_out, 8),))
 
 
+def conv_w(name, width, c_in, c_out):
+    """tf.contrib.layers.conv2d filter (1, w, C_in, C_out) (models/rced.py:94-101, splice = 1) stored as the GEMM
+    B operand [w * Cin_p, Cout_p] of the overlapped-view convolution (channels padded to multiples of 8)."""
+    cip, cop = packing.round_up(c_in, 8), packing.round_up(c_out, 8)
+    return Seg(name, "conv_w", (1, width, c_in, c_out), (width * cip, cop), dict(W=width, Cin_p=cip, Cout_p=cop))
+
+
+def fc_w_frames(name, positions, chans, n_out):
+    """FC over a flattened channels-last frame (models/rced.py:106-113): TF rows = pos * chans + ch; device rows =
+    pos * Cp + ch with zero rows for the padded channels."""
+    cp = packing.round_up(chans, 8)
+    return Seg(name, "fc_w_frames", (positions * chans, n_out), (positions * cp, packing.round_up(n_out, 8)),
+               dict(L=positions, C=chans, Cp=cp))
+
+
 def lstm_cell(prefix, I, C, P):
     """The six variables of one tf.contrib.rnn.LSTMCell(use_peepholes, num_proj) in TF creation order."""
     Ip, Pp, Cp = packing.round_up(I, 8), packing.round_up(P, 8), packing.cell_pad(C)
@@ -67,6 +82,12 @@ def to_dev_layout(seg, a):
         out[:] = packing.pack_cols(a, seg.meta["C"])
     elif seg.kind == "proj":
         out[:a.shape[0], :a.shape[1]] = a
+    elif seg.kind == "conv_w":
+        m = seg.meta
+        out.reshape(m["W"], m["Cin_p"], m["Cout_p"])[:, :a.shape[2], :a.shape[3]] = a[0]
+    elif seg.kind == "fc_w_frames":
+        m = seg.meta
+        out.reshape(m["L"], m["Cp"], -1)[:, :m["C"], :a.shape[1]] = a.reshape(m["L"], m["C"], -1)
     elif seg.kind == "lstm_kernel":
         m = seg.meta
         p = packing.pack_cols(a, m["C"])
@@ -87,6 +108,12 @@ def from_dev_layout(seg, d):
         return packing.unpack_cols(d, seg.meta["C"])
     if seg.kind == "proj":
         return d[:seg.tf_shape[0], :seg.tf_shape[1]].copy()
+    if seg.kind == "conv_w":
+        m = seg.meta
+        return d.reshape(m["W"], m["Cin_p"], m["Cout_p"])[None, :, :seg.tf_shape[2], :seg.tf_shape[3]].copy()
+    if seg.kind == "fc_w_frames":
+        m = seg.meta
+        return d.reshape(m["L"], m["Cp"], -1)[:, :m["C"], :seg.tf_shape[1]].reshape(seg.tf_shape).copy()
     if seg.kind == "lstm_kernel":
         m = seg.meta
         u = packing.unpack_cols(d, m["C"])

@@ -78,6 +78,27 @@ class FakeHandle(object):
         if out32 is not None:
             out32[:M, :N] = v + (beta * out32[:M, :N] if beta != 0.0 else 0.0)
 
+    # ------------------------------------------------------------- 1-D conv glue
+    def conv_stage_frames(self, x, B, T, L, S, Cp, out16, mean=None, istd=None, time_major_in=False, ldx=None):
+        self.launches += 1
+        if time_major_in:
+            v = x[:T * B, :L].float()
+        else:
+            v = x.reshape(B, T, -1)[:, :, :L].float().permute(1, 0, 2).reshape(T * B, L)
+        if mean is not None:
+            v = (v - mean) * istd
+        o = out16[:T * B * S].view(T * B, S, Cp)
+        o.zero_()
+        o[:, :L, 0] = v.to(self.h16)
+
+    def conv_mask_rows(self, buf16, frames, S, L, Cp):
+        self.launches += 1
+        buf16[:frames * S].view(frames, S, Cp)[:, L:].zero_()
+
+    def conv_w_flip(self, w16, W, cin_p, cout_p, out16):
+        self.launches += 1
+        out16.view(W, cout_p, cin_p).copy_(w16.reshape(W, cin_p, cout_p).flip(0).transpose(1, 2))
+
     # --------------------------------------------------------------- staging
     def stage_input(self, x, B, T, D, out16=None, out32=None, mean=None, istd=None, noise=None,
                     time_major_in=False, ldx=None):

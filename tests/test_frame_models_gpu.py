@@ -1,0 +1,167 @@
+"""Frame-level rows of SURVEY.md section 8a on the GPU: the `dnn` generator under DNNTrainer (a13, BASELINE.json
+configs[0]) and the `rced` convolutional generator (a14, configs[3]) alone and inside the GAN with discriminator_dnn,
+against the committed golden vectors and against the oracle at the BASELINE sizes.
+
+Tolerances (fp16 tensor-core operands, fp32 accumulate): generator output absolute RMS < 1e-3 (north_star) and relative
+RMS < 3e-3; losses relative 2e-3 (5e-3 where the loss is the square of a small logit); raw gradients relative RMS 5e-2
+(dnn) / 1e-1 (rced: nine stacked ReLU layers -- a pre-activation within rounding distance of zero flips its mask, and a
+fraction f of flipped entries is an RMS error of sqrt(f); the kernels themselves are checked to 1e-5 / 16-bit rounding
+in test_kernels_gpu.py::test_conv1d_same_overlapped_view_gemm)."""
+import os
+from argparse import Namespace
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rsr_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rms(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    d = float(np.sqrt(((a - b) ** 2).mean()))
+    return d, d / (float(np.sqrt((b ** 2).mean())) + 1e-30)
+
+
+def load_gold(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    gp = OrderedDict((k[2:], z[k]) for k in z.files if k.startswith("G/"))
+    dp = OrderedDict((k[2:], z[k]) for k in z.files if k.startswith("D/"))
+    return z, gp, dp
+
+
+def trainer(**kw):
+    from rsrgan_b200.dnn_trainer import DNNTrainer
+    a = dict(g_learning_rate=1e-3, l2_scale=0.0, seed=3, dtype="f16")
+    a.update(kw)
+    return DNNTrainer(None, Namespace(**a), ["/gpu:0"])
+
+
+@pytest.mark.parametrize("name,kw", [("mse_dnn", dict(g_type="dnn", g_units=64)), ("mse_rced", dict(g_type="rced"))])
+def test_dnn_trainer_golden_vectors(name, kw):
+    z, gp, _ = load_gold(name)
+    N = z["x"].shape[0]
+    gtol = 1e-1 if kw["g_type"] == "rced" else 5e-2
+    m = trainer(batch_size=N, g_learning_rate=float(z["lr"]), l2_scale=float(z["l2_scale"]), **kw)
+    m.load_params(gp)
+    a, r = rms(m.generate(z["x"]).cpu().numpy(), z["g_out"])
+    assert a < 1e-3 and r < 3e-3, (a, r)
+    m.g_learning_rate = 0.0
+    n0 = m.h.launches
+    out = m.train_step(z["x"], z["y"])
+    assert m.h.launches > n0
+    for k in ("g_mse_loss", "g_l2_loss", "g_loss"):
+        assert out[k] == pytest.approx(float(z["loss/" + k]), rel=2e-3), k
+    gs = m._gscale(N)
+    gg = m.G.P.export_tf("grad")
+    for k in gp:
+        assert rms(gg[k] / gs, z["ggrad/" + k])[1] < gtol, k
+    m.load_params(gp)
+    m.G.P.m.zero_(); m.G.P.v.zero_(); m.G.P.hyper[4:6] = torch.tensor([0.9, 0.999], device=m.h.device)
+    m.g_learning_rate = float(z["lr"])
+    for _ in range(int(z["steps"])):
+        m.train_step(z["x"], z["y"])
+    ev = m.eval_losses(z["x"], z["y"])
+    assert ev["g_mse_loss"] == pytest.approx(float(z["loss_after/g_mse_loss"]), rel=5e-3)
+
+
+def test_gan_rced_golden_vectors():
+    from rsrgan_b200.gan_rnn import GAN_RNN
+    z, gp, dp = load_gold("gan_rced_ddnn")
+    B, T = z["x"].shape[:2]
+    a = dict(g_type="rced", d_type="dnn", d_units=64, batch_size=B, init_mse_weight=10.0, init_disc_noise_std=0.05,
+             g_learning_rate=8e-5, d_learning_rate=1e-3, l2_scale=0.0, seed=3, dtype="f16")
+    m = GAN_RNN(None, Namespace(**a), ["/gpu:0"])
+    m.load_params(gp, dp)
+    a_, r = rms(m.generate(z["x"], z["lengths"]).cpu().numpy(), z["g_out"])
+    assert a_ < 1e-3 and r < 3e-3, (a_, r)
+    ev = m.eval_losses(z["x"], z["y"], z["lengths"])
+    for k in ("d_rl_loss", "d_fk_loss", "d_loss", "g_adv_loss", "g_mse_loss", "g_loss"):
+        assert ev[k] == pytest.approx(float(z["loss/" + k]), rel=5e-3, abs=1e-5), k
+    m.d_learning_rate, m.g_learning_rate = 0.0, 0.0
+    gs = m._gscale(B * T)
+    m.d_step(z["x"], z["y"], z["lengths"])
+    dg = m.D.P.export_tf("grad")
+    for k in dp:
+        assert rms(dg[k] / gs, z["dgrad/" + k])[1] < 5e-2, k
+    m.g_step(z["x"], z["y"], z["lengths"])
+    gg = m.G.P.export_tf("grad")
+    for k in gp:
+        assert rms(gg[k] / gs, z["ggrad/" + k])[1] < 1e-1, k
+    # padded elements of the channel-padded taps keep exactly zero weight and gradient
+    for name, s in m.G.P.segs.items():
+        if s.kind == "conv_w":
+            g = m.G.P.view(name, "grad").view(s.meta["W"], s.meta["Cin_p"], s.meta["Cout_p"])
+            assert not g[:, s.tf_shape[2]:].any() and not g[:, :, s.tf_shape[3]:].any(), name
+    # whole batch schedule through train_batch (CUDA-graph path included) stays finite and moves the weights
+    m.load_params(gp, dp)
+    m.d_learning_rate, m.g_learning_rate = 1e-3, 8e-5
+    for _ in range(4):
+        out = m.train_batch(z["x"], z["y"], z["lengths"])
+    assert all(np.isfinite(v) for v in out.values())
+    a_, r = rms(m.G.P.export_tf()["g_model/Conv_4/weights"], gp["g_model/Conv_4/weights"])
+    assert 0 < r < 0.05
+
+
+def test_cfg1_dnn_generator_batch64_one_step_against_oracle():
+    """BASELINE.json configs[0]: DNN generator 257 -> 1024 x 4 -> 40, batch 64 frames, one Adam step."""
+    N = 64
+    m = trainer(g_type="dnn", batch_size=N, l2_scale=1e-5)
+    rng = np.random.default_rng(64)
+    x, y = rng.standard_normal((N, 257)).astype(np.float32), rng.standard_normal((N, 40)).astype(np.float32)
+    g0 = OrderedDict((k, v.astype(np.float64)) for k, v in m.G.P.export_tf().items())
+    assert sum(v.size for v in g0.values()) == 257 * 1024 + 1024 + 3 * (1024 * 1024 + 1024) + 1024 * 40 + 40
+    st = O.MseState(g0, "dnn")
+    g_ref, _ = O.g_dnn_fwd(st.g, x.astype(np.float64))
+    a, r = rms(m.generate(x).cpu().numpy(), g_ref)
+    assert a < 1e-3 and r < 3e-3, (a, r)
+    ours = m.train_step(x, y)
+    ref, grads = O.mse_step(st, x.astype(np.float64), y.astype(np.float64), 1e-3, l2_scale=1e-5)
+    for k in ("g_mse_loss", "g_l2_loss", "g_loss"):
+        assert ours[k] == pytest.approx(ref[k], rel=2e-3), k
+    gs = m._gscale(N)
+    gg = m.G.P.export_tf("grad")
+    for k in g0:
+        assert rms(gg[k] / gs, grads[k])[1] < 5e-2, k
+    # Adam's first step is lr * sign(g) for every entry whose gradient is not tiny: compare the loss after the step
+    ev = m.eval_losses(x, y)
+    ref_after, _, _ = O.mse_losses_and_grads(st.g, "dnn", x.astype(np.float64), y.astype(np.float64), 1e-5)
+    assert ev["g_mse_loss"] == pytest.approx(ref_after["g_mse_loss"], rel=5e-3)
+    assert ev["g_mse_loss"] < ours["g_mse_loss"]
+
+
+def test_cfg4_rced_gan_batch256_against_oracle():
+    """BASELINE.json configs[3]: RCED generator + discriminator_dnn, 256 frames per GPU."""
+    from rsrgan_b200.gan_rnn import GAN_RNN
+    B, T = 256, 1
+    a = dict(g_type="rced", d_type="dnn", batch_size=B, init_mse_weight=10.0, init_disc_noise_std=0.0,
+             g_learning_rate=8e-5, d_learning_rate=1e-3, l2_scale=0.0, seed=3, dtype="f16")
+    m = GAN_RNN(None, Namespace(**a), ["/gpu:0"])
+    rng = np.random.default_rng(256)
+    x, y = rng.standard_normal((B, T, 257)).astype(np.float32), rng.standard_normal((B, T, 40)).astype(np.float32)
+    lengths = np.full(B, T)
+    st = O.GanState(OrderedDict((k, v.astype(np.float64)) for k, v in m.G.P.export_tf().items()),
+                    OrderedDict((k, v.astype(np.float64)) for k, v in m.D.P.export_tf().items()), "rced", "dnn")
+    assert st.g["g_model/fully_connected/biases"][0] == pytest.approx(0.1)      # models/rced.py:112
+    g_ref, _ = O.g_rced_fwd(st.g, x.astype(np.float64))
+    a_, r = rms(m.generate(x, lengths).cpu().numpy(), g_ref)
+    assert a_ < 1e-3 and r < 3e-3, (a_, r)
+    tower = dict(x=x.astype(np.float64), y=y.astype(np.float64), lengths=lengths)
+    ours = m.d_step(x, y, lengths)
+    ref, _ = O.d_step(st, [tower], 1e-3)
+    assert ours["d_loss"] == pytest.approx(ref[0]["d_loss"], rel=5e-3)
+    ours = m.g_step(x, y, lengths)
+    ref, _ = O.g_step(st, [tower], 8e-5)
+    assert ours["g_loss"] == pytest.approx(ref[0]["g_loss"], rel=2e-3)
+    g_ref, _ = O.g_rced_fwd(st.g, x.astype(np.float64))
+    a_, r = rms(m.generate(x, lengths).cpu().numpy(), g_ref)
+    assert a_ < 1e-3 and r < 2e-2, (a_, r)
+    # frames are independent: permuting the frames permutes the outputs (size-independent property)
+    perm = rng.permutation(B)
+    g1 = m.generate(x, lengths).cpu().numpy()
+    g2 = m.generate(x[perm], lengths).cpu().numpy()
+    assert np.abs(g2 - g1[perm]).max() < 1e-6

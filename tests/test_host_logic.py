@@ -47,7 +47,8 @@ def test_packed_gate_columns_roundtrip():
     assert np.array_equal(packing.unpack_cols(p, C), a)
     # gate g of cell c sits at (c//32)*128 + g*32 + c%32
     assert p[0, 1 * 128 + 2 * 32 + 3] == a[0, 2 * C + 35]
-    for s in params.lstm_cell("x/", 257, 760, 257) + [params.fc_w("w", 257, 40), params.fc_b("b", 1)]:
+    for s in params.lstm_cell("x/", 257, 760, 257) + [params.fc_w("w", 257, 40), params.fc_b("b", 1),
+                                                      params.conv_w("c", 13, 12, 20), params.fc_w_frames("f", 257, 12, 40)]:
         t = np.random.default_rng(0).standard_normal(s.tf_shape).astype(np.float32)
         assert np.array_equal(params.from_dev_layout(s, params.to_dev_layout(s, t)), t)
 
@@ -55,6 +56,7 @@ def test_packed_gate_columns_roundtrip():
 @pytest.mark.parametrize("name,kw", [
     ("gan_lstm_dlstm", dict(g_type="lstm", d_type="lstm", g_cell=64, g_proj=32, g_layers=2, d_cell=32)),
     ("gan_res_ddnn", dict(g_type="res_lstm_l", d_type="dnn", g_cell=40, g_layers=2, d_units=64)),
+    ("gan_rced_ddnn", dict(g_type="rced", d_type="dnn", d_units=64)),
 ])
 def test_wiring_matches_golden(name, kw):
     z, gp, dp = load_gold(name)
@@ -68,7 +70,8 @@ def test_wiring_matches_golden(name, kw):
     assert rel(g, z["g_out"]) < 3e-3
     ev = m.eval_losses(z["x"], z["y"], z["lengths"], **nz)
     for k in ("d_rl_loss", "d_fk_loss", "d_loss", "g_adv_loss", "g_mse_loss", "g_loss"):
-        assert ev[k] == pytest.approx(float(z["loss/" + k]), rel=2e-3, abs=1e-5), k
+        # (d_fk of the rced case is the square of a ~0.1 logit computed from a ~0.03-sized generator output)
+        assert ev[k] == pytest.approx(float(z["loss/" + k]), rel=5e-3 if g_type == "rced" else 2e-3, abs=1e-5), k
     # raw gradients of one D update and one G update
     m.d_learning_rate, m.g_learning_rate = 0.0, 0.0             # keep weights fixed: compare gradients only
     gs = m._gscale(B * z["x"].shape[1])
@@ -78,8 +81,10 @@ def test_wiring_matches_golden(name, kw):
         assert rel(dg[k] / gs, z["dgrad/" + k]) < 2e-2, k
     m.g_step(z["x"], z["y"], z["lengths"], noise_fk=nz.get("noise_fk"))
     gg = m.G.P.export_tf("grad")
+    # nine stacked ReLU layers: a pre-activation within rounding distance of zero flips its mask and with it a whole
+    # gradient entry (a fraction f of flipped entries is an RMS error of sqrt(f)), so the bar is looser for rced
     for k in gp:
-        assert rel(gg[k] / gs, z["ggrad/" + k]) < 2e-2, k
+        assert rel(gg[k] / gs, z["ggrad/" + k]) < (1e-1 if g_type == "rced" else 2e-2), k
 
 
 def test_batch_schedule_matches_oracle_after_updates():
@@ -183,3 +188,40 @@ def test_data_parallel_two_ranks_gloo_matches_two_tower_oracle():
         assert rel(res[0][1][k] - dp[k], st.d[k] - dp[k]) < 3e-2, k
     k = "g_model/fully_connected_1/weights"
     assert rel(res[0][2][k] - gp[k], st.g[k] - gp[k]) < 5e-2
+
+
+@pytest.mark.parametrize("name,kw", [("mse_dnn", dict(g_type="dnn", g_units=64)), ("mse_rced", dict(g_type="rced"))])
+def test_dnn_trainer_wiring_matches_golden(name, kw):
+    """DNNTrainer (models/dnn_trainer_single_gpu.py:52-133) through the test double vs the oracle's golden vectors."""
+    from rsrgan_b200.dnn_trainer import DNNTrainer
+    z, gp, _ = load_gold(name)
+    N = z["x"].shape[0]
+    a = dict(batch_size=N, g_learning_rate=float(z["lr"]), l2_scale=float(z["l2_scale"]), seed=3, **kw)
+    m = DNNTrainer(None, Namespace(**a), ["/gpu:0"], handle=FakeHandle("f16"))
+    m.load_params(gp)
+    assert m.G.P.n_params() == sum(v.size for v in gp.values())
+    g = m.generate(z["x"]).numpy()
+    assert g.shape == (N, 40) and rel(g, z["g_out"]) < 3e-3
+    ev = m.eval_losses(z["x"], z["y"])
+    assert ev["g_mse_loss"] == pytest.approx(float(z["loss/g_mse_loss"]), rel=2e-3)
+    assert ev["g_l2_loss"] == pytest.approx(float(z["loss/g_l2_loss"]), rel=1e-3)
+    cv = DNNTrainer(None, Namespace(**a), ["/gpu:0"], cross_validation=True, share=m)
+    assert cv.eval_losses(z["x"], z["y"])["g_l2_loss"] == 0.0   # dnn_trainer_single_gpu.py:111: l2 only when training
+    m.g_learning_rate = 0.0
+    out = m.train_step(z["x"], z["y"])
+    for k in ("g_mse_loss", "g_l2_loss", "g_loss"):
+        assert out[k] == pytest.approx(float(z["loss/" + k]), rel=2e-3), k
+    gs = m._gscale(N)
+    gg = m.G.P.export_tf("grad")
+    for k in gp:
+        assert rel(gg[k] / gs, z["ggrad/" + k]) < (1e-1 if kw["g_type"] == "rced" else 5e-2), k   # ReLU-mask flips, see above
+    # `steps` Adam updates from the golden start point (no clip_by_norm on this trainer)
+    m.load_params(gp)
+    m.G.P.m.zero_(); m.G.P.v.zero_(); m.G.P.hyper[4:6] = torch.tensor([0.9, 0.999])
+    m.g_learning_rate = float(z["lr"])
+    for _ in range(int(z["steps"])):
+        m.train_step(z["x"], z["y"])
+    ev = m.eval_losses(z["x"], z["y"])
+    assert ev["g_mse_loss"] == pytest.approx(float(z["loss_after/g_mse_loss"]), rel=5e-3)
+    with pytest.raises(AttributeError):
+        m.d_step(z["x"], z["y"], None)

@@ -297,3 +297,76 @@ def test_fused_clip_update_sweep(h):
     h.clip_sgd_ema(d_grad, 1.0 / 8.0, d_seg, sumsq, 15.0, hy2, 0.9999, d_theta2, d_ema2, None)
     ref = np.concatenate([theta[a:b] - 0.05 * O.clip_by_norm(grad[a:b].astype(np.float64)) for a, b in bounds])
     assert np.abs(d_theta2.cpu().numpy() - ref).max() < 1e-6
+
+
+@pytest.mark.parametrize("N,w,cin,cout", [(5, 13, 1, 12), (64, 11, 12, 16), (37, 9, 16, 20), (256, 7, 24, 32),
+                                          (256, 9, 24, 20), (3, 13, 16, 12)])
+def test_conv1d_same_overlapped_view_gemm(h, N, w, cin, cout):
+    """models/rced.py:94-101 (splice = 1): forward, weight gradient and data gradient of the SAME convolution as
+    rsr_gemm over the overlapped frame view + rsr_conv_mask_rows / rsr_conv_w_flip, against the oracle's
+    conv1d_same_fwd / _bwd on the same 16-bit operands.  Tolerance: 16-bit output rounding (fp16 2^-11, bf16 2^-8
+    relative) on top of the exact fp32-accumulated product."""
+    from rsrgan_b200.nets import ConvFrames
+    dev, rng = h.device, np.random.default_rng(N + w + cin)
+    L = 257
+    fl = ConvFrames(L, 13)
+    S, G = fl.S, fl.GUARD
+    cip, cop = packing.round_up(cin, 8), packing.round_up(cout, 8)
+    x16 = torch.tensor(rng.standard_normal((N, L, cin)).astype(np.float32)).to(h.h16)
+    W16 = torch.tensor((rng.standard_normal((w, cin, cout)) / np.sqrt(w * cin)).astype(np.float32)).to(h.h16)
+    b = rng.standard_normal(cout).astype(np.float32) * 0.1
+    xb = torch.zeros(N * S + 2 * G, cip, dtype=h.h16, device=dev)
+    xb[G:G + N * S].view(N, S, cip)[:, :L, :cin] = x16.to(dev)
+    Wp = torch.zeros(w, cip, cop, dtype=h.h16, device=dev)
+    Wp[:, :cin, :cout] = W16.to(dev)
+    bp = torch.zeros(cop, dtype=torch.float32, device=dev)
+    bp[:cout] = torch.tensor(b)
+    yb = torch.full((N * S + 2 * G, cop), 3.0, dtype=h.h16, device=dev)
+    yb[:G] = 0; yb[G + N * S:] = 0
+    h.gemm(fl.window(xb, N, cip, w), Wp.view(w * cip, cop), N * S, cop, w * cip, b_mn=True, bias=bp,
+           act=O.ACT_RELU, out16=yb[G:])
+    h.conv_mask_rows(yb[G:], N, S, L, cop)
+    torch.cuda.synchronize()
+    xo, Wo = x16.double().numpy(), W16.double().numpy()[None]
+    y_ref, cache = O.conv1d_same_fwd(xo, Wo, b.astype(np.float64))
+    y = yb[G:G + N * S].view(N, S, cop).float().cpu().numpy()
+    assert rel(y[:, :L, :cout], y_ref) < tol(h, 5e-4, 4e-3)
+    assert not y[:, L:].any() and not y[:, :, cout:].any()          # SAME padding rows and padded channels stay zero
+    assert not yb[:G].any() and not yb[G + N * S:].any()            # guard rows untouched
+    # backward: dY = pre-activation gradient (already masked by relu'), zero in the padding rows
+    dy16 = torch.tensor((rng.standard_normal((N, L, cout)) * (y_ref > 0)).astype(np.float32)).to(h.h16)
+    dyb = torch.zeros(N * S + 2 * G, cop, dtype=h.h16, device=dev)
+    dyb[G:G + N * S].view(N, S, cop)[:, :L, :cout] = dy16.to(dev)
+    dW = torch.zeros(w * cip, cop, dtype=torch.float32, device=dev)
+    h.gemm(fl.window(xb, N, cip, w), dyb[G:G + N * S], w * cip, cop, N * S, a_mn=True, b_mn=True, beta=1.0, out32=dW)
+    db = torch.zeros(cop, dtype=torch.float32, device=dev)
+    h.colsum16(dyb[G:G + N * S], N * S, cop, db)
+    Wf = torch.zeros(w * cop, cip, dtype=h.h16, device=dev)
+    h.conv_w_flip(Wp, w, cip, cop, Wf)
+    dxb = torch.zeros(N * S + 2 * G, cip, dtype=h.h16, device=dev)
+    h.gemm(fl.window(dyb, N, cop, w), Wf, N * S, cip, w * cop, b_mn=True, out16=dxb[G:])
+    torch.cuda.synchronize()
+    # oracle backward with act = none on the already-masked dy (cache's u only matters through act_bwd)
+    xp, Wc, u, _ = cache
+    dx_ref, dW_ref, db_ref = O.conv1d_same_bwd(dy16.double().numpy(), (xp, Wc, u, O.ACT_NONE))
+    assert rel(dW.view(w, cip, cop)[:, :cin, :cout].cpu().numpy(), dW_ref[0]) < 1e-5
+    assert not dW.view(w, cip, cop)[:, cin:].any() and not dW.view(w, cip, cop)[:, :, cout:].any()
+    assert rel(db[:cout].cpu().numpy(), db_ref) < 1e-5
+    dx = dxb[G:G + N * S].view(N, S, cip).float().cpu().numpy()
+    assert rel(dx[:, :L, :cin], dx_ref) < tol(h, 5e-4, 4e-3)
+
+
+def test_conv_stage_frames(h):
+    """(B, T, 257) fp32 frames -> channels-last padded rows, time-major frame order, CMVN fused (models/rced.py:46-57)."""
+    dev, rng = h.device, np.random.default_rng(3)
+    B, T, L, S, Cp = 3, 4, 257, 264, 8
+    x = rng.standard_normal((B, T, L)).astype(np.float32)
+    mean, std = rng.standard_normal(L).astype(np.float32), (rng.random(L) + 0.5).astype(np.float32)
+    out = torch.full((B * T * S, Cp), 5.0, dtype=h.h16, device=dev)
+    t = lambda a: torch.tensor(a, device=dev)
+    h.conv_stage_frames(t(x), B, T, L, S, Cp, out, mean=t(mean), istd=t(1.0 / std))
+    torch.cuda.synchronize()
+    o = out.view(T, B, S, Cp).float().cpu().numpy()
+    ref = ((x - mean) * (1.0 / std)).transpose(1, 0, 2)
+    assert rel(o[:, :, :L, 0], ref) < tol(h, 5e-4, 4e-3)
+    assert not o[:, :, L:].any() and not o[:, :, :, 1:].any()

@@ -15,7 +15,12 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 def small_gan(g_type="lstm", d_type="lstm", seed=0):
     rng = np.random.default_rng(seed)
-    gp = O.init_g_lstm(rng, cell=24, proj=12, layers=2) if g_type == "lstm" else O.init_g_res_lstm_l(rng, cell=16, layers=2)
+    if g_type == "rced":
+        gp = O.init_g_rced(rng)
+    elif g_type == "dnn":
+        gp = O.init_g_dnn(rng, units=32, hidden=2)
+    else:
+        gp = O.init_g_lstm(rng, cell=24, proj=12, layers=2) if g_type == "lstm" else O.init_g_res_lstm_l(rng, cell=16, layers=2)
     dp = O.init_d_lstm(rng, cell=16) if d_type == "lstm" else O.init_d_dnn(rng, units=32, hidden=2)
     for p in (gp, dp):
         for k in p:
@@ -28,7 +33,8 @@ def small_gan(g_type="lstm", d_type="lstm", seed=0):
     return gp, dp, x, y, lengths, nz
 
 
-@pytest.mark.parametrize("g_type,d_type", [("lstm", "lstm"), ("res_lstm_l", "dnn"), ("res_lstm_base", "lstm")])
+@pytest.mark.parametrize("g_type,d_type", [("lstm", "lstm"), ("res_lstm_l", "dnn"), ("res_lstm_base", "lstm"),
+                                           ("rced", "dnn"), ("dnn", "dnn")])
 @pytest.mark.parametrize("which", ["d", "g"])
 def test_numpy_backward_matches_torch_autograd(g_type, d_type, which):
     gp, dp, x, y, lengths, (n1, n2) = small_gan(g_type, d_type)
@@ -154,3 +160,57 @@ def test_oracle_reproduces_golden_vectors(name):
             assert float(out[k]) == pytest.approx(float(gold[k]), rel=1e-10)
         if k.startswith(("dgrad/", "ggrad/")):
             assert np.allclose(out[k], gold[k], atol=1e-7, rtol=1e-5), k
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.MSE_CASES))
+def test_oracle_reproduces_mse_golden_vectors(name):
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    out = make_golden.compute_mse(name)
+    for k in ("g_out", "g_out_after"):
+        assert np.allclose(out[k], gold[k], atol=1e-10), k
+    for k in gold.files:
+        if k.startswith(("loss/", "loss_after/")):
+            assert float(out[k]) == pytest.approx(float(gold[k]), rel=1e-10)
+        if k.startswith("ggrad/"):
+            assert np.allclose(out[k], gold[k], atol=1e-7, rtol=1e-5), k
+
+
+def test_conv1d_same_is_tf_conv2d_same_and_its_gradient():
+    """models/rced.py:94-101: conv2d([1, w], SAME, stride 1) == torch conv2d with padding w//2 (odd w), NHWC<->NCHW and
+    HWIO<->OIHW transposed; hand-written backward == autograd; finite difference on one tap."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(4)
+    N, L, ci, co, w = 3, 19, 5, 4, 7
+    x, W, b = rng.standard_normal((N, L, ci)), rng.standard_normal((1, w, ci, co)) * 0.3, rng.standard_normal(co) * 0.1
+    y, cache = O.conv1d_same_fwd(x, W, b)
+    xt, Wt, bt = (torch.tensor(a, requires_grad=True) for a in (x, W, b))
+    yt = torch.relu(F.conv2d(xt.permute(0, 2, 1).unsqueeze(2), Wt.permute(3, 2, 0, 1), bt, padding=(0, w // 2)))
+    yt = yt.squeeze(2).permute(0, 2, 1)
+    assert np.allclose(y, yt.detach().numpy(), atol=1e-12)
+    dy = rng.standard_normal(y.shape)
+    (yt * torch.tensor(dy)).sum().backward()
+    dx, dW, db = O.conv1d_same_bwd(dy, cache)
+    assert np.allclose(dx, xt.grad.numpy(), atol=1e-12) and np.allclose(dW, Wt.grad.numpy(), atol=1e-12)
+    assert np.allclose(db, bt.grad.numpy(), atol=1e-12)
+    f = lambda: float((O.conv1d_same_fwd(x, W, b)[0] * dy).sum())
+    old, eps = W[0, 2, 1, 3], 1e-6
+    W[0, 2, 1, 3] = old + eps; fp = f()
+    W[0, 2, 1, 3] = old - eps; fm = f()
+    W[0, 2, 1, 3] = old
+    assert abs((fp - fm) / (2 * eps) - dW[0, 2, 1, 3]) < 1e-6
+
+
+def test_mse_trainer_gradients_match_torch_autograd():
+    """models/dnn_trainer_single_gpu.py:106-115: 0.5 * output_dim * mse + l2 on weights only."""
+    rng = np.random.default_rng(5)
+    for g_type, gp in (("dnn", O.init_g_dnn(rng, units=16, hidden=2)), ("rced", O.init_g_rced(rng))):
+        x, y = rng.standard_normal((5, 257)), rng.standard_normal((5, 40))
+        L, grads, g = O.mse_losses_and_grads(gp, g_type, x, y, l2_scale=1e-2)
+        tp = R.to_torch(gp, requires_grad=True)
+        gt = R.GEN[g_type](tp, torch.tensor(x), None)
+        mse = 0.5 * 40 * ((gt - torch.tensor(y)) ** 2).mean()
+        l2 = sum(1e-2 * 0.5 * (v ** 2).sum() for k, v in tp.items() if k.endswith("weights"))
+        (mse + l2).backward()
+        assert L["g_mse_loss"] == pytest.approx(float(mse), rel=1e-12) and L["g_l2_loss"] == pytest.approx(float(l2), rel=1e-12)
+        for k in gp:
+            assert np.allclose(grads[k], tp[k].grad.numpy(), atol=1e-10, rtol=1e-8), k
