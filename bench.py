@@ -38,6 +38,9 @@ CONFIGS = {
     # reference-native sizes of the shipped driver family (models/lstm.py:43-45 + discriminator_lstm)
     "cfgP": dict(g_type="lstm", d_type="lstm", g_cell=760, g_proj=280, g_layers=3, B=8, T=100,
                  name="gan_rnn_placeholder ref-native: lstm G (3xLSTMP 760->280) + discriminator_lstm, B=8 x T=100"),
+    # BASELINE.json configs[4]: res_lstm_l 4 x 1024 (P = 257) + discriminator_lstm, T = 200, B = 64 per GPU
+    "cfg5": dict(g_type="res_lstm_l", d_type="lstm", g_cell=1024, g_proj=257, g_layers=4, B=64, T=200,
+                 name="gan_rnn_placeholder: res_lstm_l G (4xLSTMP 1024->257) + discriminator_lstm, B=64 x T=200 per GPU"),
     "cfgR": dict(g_type="res_lstm_l", d_type="lstm", g_cell=760, g_proj=257, g_layers=4, B=8, T=100,
                  name="run_gan_rnn_placeholder.sh: res_lstm_l G (4xLSTMP 760->257) + discriminator_lstm, B=8 x T=100"),
 }

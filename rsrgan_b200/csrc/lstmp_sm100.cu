@@ -41,6 +41,8 @@ struct FwdParams {
     uint16_t* mt_seq;           // [(T+1)*B, Cp]
     float* save;                // [T*B, 5, Cp] or null
     unsigned int* flags;        // one counter per utterance group
+    int kb_smem;                // K sub-tiles of the weight slab held in shared memory; the rest live in TMEM
+    const uint16_t* wcT;        // [4Cp, Cp] (source of the TMEM-resident part)
 };
 
 template <int NB>
@@ -56,14 +58,20 @@ lstmp_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     const int grp = blockIdx.x / G;
     const int b0 = grp * NB;
 
-    const uint32_t sA = base;                                // KB x [128 x 64] 16-bit, SW128
-    const uint32_t sB = sA + (uint32_t)KB * 16384u;          // KB x [NB x 64]
+    // Weight slab of this CTA: 128 packed gate rows x Cp.  K sub-tiles [0, KS) are resident in shared memory (TMA,
+    // SW128); for Cp > 768 the slab (256 KB at Cp = 1024) does not fit, so sub-tiles [KS, KB) are resident in TMEM
+    // instead and enter the same accumulation as the tcgen05 A-from-TMEM operand.
+    const int KS = p.kb_smem;
+    const uint32_t sA = base;                                // KS x [128 x 64] 16-bit, SW128
+    const uint32_t sB = sA + (uint32_t)KS * 16384u;          // KB x [NB x 64]
     const uint32_t sX = sB + (uint32_t)KB * NB * 128u;       // float xchg[4][32][NB+1]
     const uint32_t sBar = sX + 4u * 32u * (NB + 1) * 4u;
     const uint32_t barA = (sBar + 7u) & ~7u, barB = barA + 8, barM = barA + 16, tslot = barA + 24;
     float* xchg = reinterpret_cast<float*>(smem_raw + (sX - smem_u32(smem_raw)));
 
-    constexpr uint32_t TCOLS = NB < 32 ? 32 : NB;
+    constexpr uint32_t ACOLS = NB < 32 ? 32 : NB;            // accumulator columns
+    uint32_t TCOLS = ACOLS;
+    while (TCOLS < ACOLS + 32u * (uint32_t)(KB - KS)) TCOLS <<= 1;
     if (tid == 0) {
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmM);
@@ -76,10 +84,27 @@ lstmp_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     tc_fence_after();
     uint32_t tmem;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
+    const uint32_t tmem_a = tmem + ACOLS;
 
     if (warp == 0 && elect_one_sync()) {   // weight slab: resident for the whole sequence
-        mbar_expect_tx(barA, (uint32_t)KB * 16384u);
-        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * 16384u, &tmW, barA, kb * 64, 128 * j);
+        mbar_expect_tx(barA, (uint32_t)KS * 16384u);
+        for (int kb = 0; kb < KS; ++kb) tma_load_2d(sA + kb * 16384u, &tmW, barA, kb * 64, 128 * j);
+    }
+    if (KS < KB) {   // thread <-> gate row, 64 k (32 columns of packed 16-bit pairs) per store
+        const uint16_t* wrow = p.wcT + (size_t)(128 * j + tid) * p.Cp;
+        for (int kb = KS; kb < KB; ++kb) {
+            uint32_t r[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(wrow + kb * 64) + c);
+                r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+            }
+            tmem_st32(tmem_a + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kb - KS) * 32u, r);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
     }
 
     // phase-2 ownership: thread <-> (cell cl, utterances n = q*NQ .. q*NQ+NQ-1)
@@ -119,12 +144,19 @@ lstmp_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 if (t == 0) mbar_wait(barA, 0);
                 mbar_wait(barB, (uint32_t)(t & 1));
                 tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb) {
+                for (int kb = 0; kb < KS; ++kb) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t da = umma_desc_sw128(sA + kb * 16384u + k * 32u, 16, 1024);
                         const uint64_t db = umma_desc_sw128(sB + kb * NB * 128u + k * 32u, 16, 1024);
                         tc_mma_f16(tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+                    }
+                }
+                for (int kb = KS; kb < KB; ++kb) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t db = umma_desc_sw128(sB + kb * NB * 128u + k * 32u, 16, 1024);
+                        tc_mma_f16_ts(tmem, tmem_a + (uint32_t)((kb - KS) * 32 + k * 8), db, idesc, 1u);
                     }
                 }
                 tc_commit(barM);
@@ -355,9 +387,12 @@ lstmp_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const BwdParams p)
     if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
+// K sub-tiles of the forward weight slab kept in shared memory (the rest are TMEM-resident): everything up to
+// Cp = 768 (reference-native C = 760), 8 of them (128 KB) beyond that
+int fwd_kb_smem(int Cp) { return Cp <= 768 ? Cp / 64 : 8; }
 size_t fwd_smem(int Cp, int nb) {
     const int KB = Cp / 64;
-    return 1024 + (size_t)KB * 16384 + (size_t)KB * nb * 128 + 4 * 32 * (nb + 1) * 4 + 64;
+    return 1024 + (size_t)fwd_kb_smem(Cp) * 16384 + (size_t)KB * nb * 128 + 4 * 32 * (nb + 1) * 4 + 64;
 }
 size_t bwd_smem(int nb) { return 1024 + 8 * 16384 + (size_t)4 * nb * 128 + 64; }
 
@@ -393,6 +428,7 @@ extern "C" int rsr_lstmp_rec_fwd(rsr_handle* h, void* stream, int B, int T, int 
         if (rcc != RSR_E_RESIDENT) return rcc;
     }
     const int G = Cp / 32;
+    if (32 + 32 * (Cp / 64 - fwd_kb_smem(Cp)) > 512) return RSR_E_SHAPE;   // TMEM-resident part + accumulator: Cp <= 1728
     const int nb = pick_nb(B, G, h->num_sms, h->max_smem, Cp, true);
     if (!nb) return RSR_E_RESIDENT;
     const int groups = (B + nb - 1) / nb;
@@ -406,6 +442,7 @@ extern "C" int rsr_lstmp_rec_fwd(rsr_handle* h, void* stream, int B, int T, int 
     p.B = B; p.T = T; p.Cp = Cp; p.bf = h->dtype == RSR_DTYPE_BF16; p.forget_bias = forget_bias;
     p.zx = zx; p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths;
     p.mt_seq = (uint16_t*)mt_seq; p.save = save;
+    p.kb_smem = fwd_kb_smem(Cp); p.wcT = (const uint16_t*)wcT;
     p.flags = take_flags(h, groups);
     RSR_CHECK_CUDA(cudaMemsetAsync(p.flags, 0, sizeof(unsigned int) * groups, (cudaStream_t)stream));
     if (nb == 16) {

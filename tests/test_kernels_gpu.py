@@ -125,6 +125,8 @@ def _rec_case(h, B, T, I, C, P, ragged, seed):
     (40, 10, 256, 512, 256, False),      # BASELINE cfg-2 layer, several utterance groups
     (1, 9, 257, 760, 257, True),         # decode: one utterance (train...py batch_size=1), res_lstm_l layer
     (3, 1, 40, 256, 40, False),          # a single frame
+    (20, 7, 257, 1024, 257, True),       # BASELINE configs[4] layer (res_lstm_l, C = 1024): weight slab half in TMEM
+    (64, 5, 257, 1000, 257, False),      # same family at the cfg-5 batch (two groups of 32 in the backward), C padded
 ])
 def test_lstmp_recurrence_fwd_bwd(h, B, T, I, C, P, ragged):
     r = _rec_case(h, B, T, I, C, P, ragged, seed=B + T)
