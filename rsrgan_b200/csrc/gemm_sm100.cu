@@ -46,6 +46,7 @@ struct GemmKParams {
     float* out32; int ldc32;         // direct access: previous contents when beta is neither 0 nor 1, ragged N edge
     uint16_t* out16; int ldc16;
     int has32, has16;
+    int fast16;               // 16-bit-only output in 64-column boxes, no residual / alpha: epilogue_fast16
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -222,6 +223,97 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
     }
 }
 
+// Fast path of the epilogue for the shape most of the step's GEMMs have (fully_connected forward and data gradient:
+// 16-bit output only, alpha = 1, no residual, 64-column store boxes): one warp drains a 32-row x 64-column span per
+// iteration with BOTH tcgen05.ld in flight before a single wait, the bias as uniform 16-byte loads (no shuffles), one
+// proxy fence and one TMA store per span -- half the fixed per-chunk cost of the general path below, which was the
+// pacing stage of these GEMMs (ncu: epilogue warps busy 2/3 of the kernel, tensor pipe 41 %).
+template <bool HAS_D>
+__device__ __forceinline__ void epilogue_fast16(const GemmKParams& p, const CUtensorMap* tmC16, uint32_t taddr, int row0,
+                                                int n0, int lane, int ew, uint32_t st16, bool leader) {
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const int row = row0 + lane;
+    const bool row_ok = row < p.M;
+    for (int s0 = (ew >> 2) * 64; s0 < p.bn; s0 += 128) {
+        const int col0 = n0 + s0;
+        if (col0 >= p.N) break;                        // warp-uniform
+        uint4 dq[8];
+        if (HAS_D) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                dq[c] = (row_ok && col0 + 8 * c < p.N)
+                            ? __ldg(reinterpret_cast<const uint4*>(p.dsrc + (size_t)row * p.ldd + col0) + c)
+                            : make_uint4(0u, 0u, 0u, 0u);
+        }
+        uint32_t r[64];
+        __syncwarp();                                  // reconverge: tcgen05.ld is .sync.aligned
+        tmem_ld32_nowait(taddr + (uint32_t)s0, r);
+        tmem_ld32_nowait(taddr + (uint32_t)s0 + 32u, r + 32);
+        tmem_ld_wait();
+        float v[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias) {                                  // same address in every lane: one broadcast transaction each
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                if (col0 + 4 * c < p.N) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + c);
+                    v[4 * c] += b.x; v[4 * c + 1] += b.y; v[4 * c + 2] += b.z; v[4 * c + 3] += b.w;
+                }
+            }
+        }
+        if (p.act == RSR_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if (p.act == RSR_ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.3f * v[j]);
+        } else if (p.act == RSR_ACT_CLIP) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = fminf(fmaxf(v[j], -0.5f), 1.5f);
+        }
+        if (HAS_D && p.dact != RSR_ACT_NONE) {
+            const float neg = p.dact == RSR_ACT_LRELU ? 0.3f : 0.0f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t w[4] = {dq[c].x, dq[c].y, dq[c].z, dq[c].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool pos_lo = (int16_t)(w[k] & 0xFFFFu) > 0, pos_hi = (int32_t)w[k] >= 0x10000;
+                    v[8 * c + 2 * k] *= pos_lo ? 1.0f : neg;
+                    v[8 * c + 2 * k + 1] *= pos_hi ? 1.0f : neg;
+                }
+            }
+        }
+        uint32_t pk[32];
+        if (p.bf) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+                pk[k] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const __half2 t = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+                pk[k] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+        }
+        if (leader) tma_wait_group_read<0>();          // the previous box of this warp has left the staging buffer
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            st_shared_v4(st16 + (uint32_t)lane * 128u + (((uint32_t)c ^ sw) << 4), pk[4 * c], pk[4 * c + 1],
+                         pk[4 * c + 2], pk[4 * c + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (leader && row0 < p.M) {
+            tma_store_2d(tmC16, st16, col0, row0);
+            tma_commit_group();
+        }
+    }
+}
+
 // Persistent, warp-specialised GEMM.  Each CTA (one per SM) walks tiles tile = blockIdx.x + i*gridDim.x of
 // the (k-split, m, n) tile space.  Three pipelines run concurrently: TMA -> smem ring (full/empty
 // mbarriers), tcgen05.mma -> double-buffered TMEM accumulator (tfull/tempty), and the epilogue warps,
@@ -351,7 +443,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
             const int row0 = m0 + q * 32;
-            epilogue_tile(p, &tmC32, &tmC16, taddr, row0, n0, lane, ew, st32, st16, leader);
+            if (p.fast16) {
+                if (p.dsrc) epilogue_fast16<true>(p, &tmC16, taddr, row0, n0, lane, ew, st16, leader);
+                else epilogue_fast16<false>(p, &tmC16, taddr, row0, n0, lane, ew, st16, leader);
+            } else {
+                epilogue_tile(p, &tmC32, &tmC16, taddr, row0, n0, lane, ew, st32, st16, leader);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));       // accumulator may be overwritten
@@ -497,7 +594,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
-            epilogue_tile(p, &tmC32, &tmC16, taddr, m0 + q * 32, n0, lane, ew, st32, st16, leader);
+            if (p.fast16) {
+                if (p.dsrc) epilogue_fast16<true>(p, &tmC16, taddr, m0 + q * 32, n0, lane, ew, st16, leader);
+                else epilogue_fast16<false>(p, &tmC16, taddr, m0 + q * 32, n0, lane, ew, st16, leader);
+            } else {
+                epilogue_tile(p, &tmC32, &tmC16, taddr, m0 + q * 32, n0, lane, ew, st32, st16, leader);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) + to_leader);
@@ -679,6 +781,8 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     // 16-bit outputs leave in 64-column boxes (128-byte rows: 64-byte rows reach only a fraction of the TMA store
     // rate) unless N is ragged against the 16-byte store granule or a box would reach into the next tile
     p.w16 = (a->out16 && (a->N & 7) == 0 && (p.n_tiles == 1 || (bn & 63) == 0)) ? 64 : 32;
+    p.fast16 = (p.w16 == 64 && !a->out32 && !a->resid && a->alpha == 1.0f && (bn & 63) == 0 &&
+                (!a->bias || ((uintptr_t)a->bias & 15) == 0) && !getenv("RSR_NO_FAST_EPI")) ? 1 : 0;
     const int fixed = 1024 /*align slack*/ + EPI_WARPS * p.st_stride + 64 + 16 * 8;
     int stages = (h->max_smem - fixed) / stage_bytes;
     if (stages > 8) stages = 8;

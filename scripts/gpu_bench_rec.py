@@ -47,8 +47,9 @@ def run(B, T, Cp):
 
 
 print("%5s %5s %5s | %10s %10s | %10s %10s" % ("B", "T", "Cp", "fwd us", "us/step", "bwd us", "us/step"))
-for (B, T, Cp) in [(16, 100, 512), (16, 200, 512), (128, 100, 512), (128, 200, 512), (64, 100, 512), (8, 100, 768),
-                   (8, 100, 256), (32, 100, 256), (128, 100, 256)]:
+for (B, T, Cp) in [(16, 100, 512), (32, 100, 512), (48, 100, 512), (64, 100, 512), (96, 100, 512), (112, 100, 512),
+                   (128, 100, 512), (128, 200, 512), (8, 100, 768), (64, 100, 1024), (8, 100, 256), (32, 100, 256),
+                   (128, 100, 256)]:
     try:
         f, b = run(B, T, Cp)
         print("%5d %5d %5d | %10.1f %10.2f | %10.1f %10.2f" % (B, T, Cp, f, f / T, b, b / T), flush=True)
