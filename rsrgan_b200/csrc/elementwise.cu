@@ -20,22 +20,27 @@ inline int grid_for(long long work_items, int threads, int num_sms, int per_sm =
 // ---------------------------------------------------------------------------------------
 // staging: (B,T,D) fp32 batch-major -> [T*B, ld] time-major, 16-bit (+ fp32 copy)
 // ---------------------------------------------------------------------------------------
+// one output row (= one frame) per warp pass: no per-element division, coalesced 4-byte reads / 2-byte writes
 __global__ void stage_input_kernel(const float* __restrict__ x, int ldx, int time_major_in, int B, int T, int D,
                                    const float* __restrict__ mean, const float* __restrict__ istd,
                                    const float* __restrict__ noise, uint16_t* __restrict__ out16, int ld16,
                                    float* __restrict__ out32, int ld32, int bf) {
-    const long long total = (long long)B * T * D;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int d = (int)(i % D);
-        const long long r = i / D;          // output row = t*B + b
+    const long long rows = (long long)B * T;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp0; r < rows; r += nwarps) {          // output row = t*B + b
         const int b = (int)(r % B);
         const int t = (int)(r / B);
-        float v = time_major_in ? x[r * ldx + d] : x[((long long)b * T + t) * ldx + d];
-        if (mean) v = (v - mean[d]) * istd[d];
-        if (noise) v += noise[(long long)b * D + d];
-        if (out16) out16[r * ld16 + d] = f2h(v, bf);
-        if (out32) out32[r * ld32 + d] = v;
+        const float* src = time_major_in ? x + r * ldx : x + ((long long)b * T + t) * ldx;
+        const float* nz = noise ? noise + (long long)b * D : nullptr;
+        for (int d = lane; d < D; d += 32) {
+            float v = src[d];
+            if (mean) v = (v - mean[d]) * istd[d];
+            if (nz) v += nz[d];
+            if (out16) out16[r * ld16 + d] = f2h(v, bf);
+            if (out32) out32[r * ld32 + d] = v;
+        }
     }
 }
 
@@ -395,7 +400,7 @@ extern "C" int rsr_stage_input(rsr_handle* h, void* stream, const float* x, int 
     if (!h || !x || B <= 0 || T <= 0 || D <= 0 || (!out16 && !out32)) return RSR_E_ARG;
     if ((mean == nullptr) != (istd == nullptr)) return RSR_E_ARG;
     if ((out16 && ld16 < D) || (out32 && ld32 < D) || ldx < D) return RSR_E_SHAPE;
-    const long long total = (long long)B * T * D;
+    const long long total = (long long)B * T * 32;              // one warp per row
     stage_input_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
         x, ldx, time_major_in, B, T, D, mean, istd, noise, (uint16_t*)out16, ld16, out32, ld32,
         h->dtype == RSR_DTYPE_BF16);

@@ -352,10 +352,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
         fence_mbar_init();
     }
+    pdl_launch_dependents();                                         // the next kernel's prologue may overlap this one
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                                                      // predecessors' global writes are visible from here on
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -502,11 +504,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
         fence_mbar_init();
     }
+    pdl_launch_dependents();
     if (warp == 1) tmem_alloc_2cta(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                              // both CTAs' barriers exist before any remote arrive
     tc_fence_after();
+    pdl_wait();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -828,18 +832,32 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     // One CTA per SM, and never next to a CTA of a recurrence kernel (those hold the whole TMEM of their SM for
     // hundreds of microseconds; a GEMM CTA sharing the SM would sit in tcgen05.alloc until they retire).
     const int smem_launch = smem < RSR_EXCLUSIVE_SMEM_GEMM ? RSR_EXCLUSIVE_SMEM_GEMM : smem;
+    // programmatic dependent launch (opt-in, RSR_PDL=1): this kernel may begin (prologue only) before its predecessor in
+    // the stream ends.  Measured on cfg-2 inside the CUDA graph: no gain (4.12 ms with, 4.08 ms without) -- the graph's
+    // kernel-to-kernel gaps are already short and the exclusive-SM shared-memory floors leave little to overlap.
+    static const bool pdl = getenv("RSR_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem_launch; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     if (two) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * grid, 1, 1); cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
-        cfg.dynamicSmemBytes = smem_launch; cfg.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
+    if (two) {
+        cfg.gridDim = dim3(2 * grid, 1, 1);
         RSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tcgen05_kernel, tmA, tmB, tmC32, tmC16, p));
         return 0;
     }
-    gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem_launch, (cudaStream_t)stream>>>(tmA, tmB, tmC32, tmC16, p);
-    RSR_LAUNCH_CHECK();
+    cfg.gridDim = dim3(grid, 1, 1);
+    RSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, tmA, tmB, tmC32, tmC16, p));
     return 0;
 }

@@ -388,13 +388,13 @@ class GAN_RNN(Model):
         self._update(D, gs, adam=False)
         return self._loss_dict(self._losses.tolist(), "d") if sync else self._losses
 
-    def g_step(self, inputs, labels, lengths, noise_fk=None, sync=True, _feed=None, _g32=None):
+    def g_step(self, inputs, labels, lengths, noise_fk=None, sync=True, _feed=None, _g32=None, _x_staged=False):
         """One generator update: L_G = mean((D(G(x))-d_real)^2) + lambda*0.5*40*mean((G(x)-y)^2) [+ l2],
         gradients wrt theta_G only (through D, D frozen), tower mean, clip 15, Adam(lr_g), EMA."""
         x, y_tm, ln, B, T = _feed if _feed is not None else self._feed(inputs, labels, lengths)
         h, G, D, rows = self.h, self.G, self.D, T * B
         gs = self._gscale(rows)
-        g32 = _g32 if _g32 is not None else G.fwd(x, B, T, ln, train=True)
+        g32 = _g32 if _g32 is not None else G.fwd(x, B, T, ln, train=True, reuse_staged=_x_staged)
         lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"))
         g_adv16 = D.ws.get(("loss", "g_adv16"), rows, 8, h.h16)
         dg32 = D.ws.get(("loss", "dg32"), rows, g32.shape[1], F32)
@@ -426,7 +426,9 @@ class GAN_RNN(Model):
             g32 = self._last_g32
             d_all.append(d[:2].clone())
         for k in range(self.gen_updates):
-            g = self.g_step(None, None, None, sync=False, _feed=feed, _g32=g32 if k == 0 else None)
+            # the generator has already staged this minibatch (16-bit, time-major) in an earlier forward of the schedule
+            g = self.g_step(None, None, None, sync=False, _feed=feed, _g32=g32 if k == 0 else None,
+                            _x_staged=k > 0 or g32 is not None)
             g_all.append(g.clone())
         return d_all, g_all
 

@@ -380,14 +380,17 @@ class Generator(Net):
         super(Generator, self).__init__(handle, mk, adam=True)
         self.residual = g_type == "res_lstm_l"
 
-    def fwd(self, x, B, T, lengths, train=True, x_time_major=False):
-        """x fp32 (B, T, in_dim) batch-major on the device -> y32 [T*B, out_pad] time-major fp32."""
+    def fwd(self, x, B, T, lengths, train=True, x_time_major=False, reuse_staged=False):
+        """x fp32 (B, T, in_dim) batch-major on the device -> y32 [T*B, out_pad] time-major fp32.
+        reuse_staged: the 16-bit time-major copy of this same x from the previous call is still valid (the second
+        generator forward of a batch schedule sees the same minibatch)."""
         h, ws, rows = self.h, self.ws, T * B
         if self.g_type == "rced":
             self._B, self._T, self._len = B, T, lengths
             fl, Ls = self.frames, self.layers
             a, _ = fl.buf(self, ("g", "x16", rows), rows, Ls[0].cip)
-            h.conv_stage_frames(x, B, T, self.in_dim, fl.S, Ls[0].cip, a[fl.GUARD:], time_major_in=x_time_major)
+            if not reuse_staged:
+                h.conv_stage_frames(x, B, T, self.in_dim, fl.S, Ls[0].cip, a[fl.GUARD:], time_major_in=x_time_major)
             self._acts = [a]
             for l in Ls[:-1]:
                 a = l.fwd("g", a, rows)
@@ -397,7 +400,8 @@ class Generator(Net):
         res = self.g_type in ("res_lstm_l", "res_lstm_base")
         x16 = ws.get(("g", "x16", B), rows, ip, h.h16)
         x32 = ws.get(("g", "x32", B), rows, ip, F32) if self.residual else None
-        h.stage_input(x, B, T, self.in_dim, out16=x16, out32=x32, time_major_in=x_time_major)
+        if not reuse_staged:
+            h.stage_input(x, B, T, self.in_dim, out16=x16, out32=x32, time_major_in=x_time_major)
         self._B, self._T, self._len = B, T, lengths
         if self.g_type == "dnn":
             a = x16

@@ -43,6 +43,9 @@ class Handle(object):
         self.num_sms = self.lib.rsr_num_sms(self.h)
         self.launches = 0          # kernels of librsrgan_sm100.so launched so far (bench accounting)
         self.timing = None         # list of (name, start event, end event) while profiling, else None
+        # list of (name, stream tag, start event, end event) with BOTH streams live (scripts/gpu_timeline.py): unlike
+        # `timing`, the side stream keeps running, so the events give the true concurrent schedule of one eager pass
+        self.timeline = None
         # second stream for work that is independent of the recurrences (which occupy only the SMs of
         # their clusters): D(real) forward/backward, weight-gradient GEMMs.  `overlap = False` serialises.
         self.overlap = True
@@ -72,6 +75,16 @@ class Handle(object):
         pass) the call is bracketed by CUDA events on that stream; elapsed times are read by
         `timing_summary()` after a synchronize."""
         fn = getattr(self.lib, name)
+        if self.timeline is not None:
+            cur = torch.cuda.current_stream()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
+            rc = fn(*args)
+            e1.record(cur)
+            self.timeline.append((name, "side" if cur == self._side else "main", e0, e1, work))
+            check(rc, name)
+            self.launches += n_kernels
+            return
         if self.timing is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -149,13 +162,16 @@ class Handle(object):
         fn = self.lib.rsr_lstmp_fused_fwd
         args = (self.h, _stream(), B, T, I, Cp, _p(x16), x16.stride(0), _p(kxT), _p(bias), _p(wcT), _p(w_i), _p(w_f),
                 _p(w_o), forget_bias, _p(lengths), _p(mt_seq), _p(save))
-        if self.timing is not None:
+        if self.timing is not None or self.timeline is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             rc = fn(*args)
             e1.record()
-            if rc == 0:
+            if rc == 0 and self.timing is not None:
                 self.timing.append(("rsr_lstmp_fused_fwd", e0, e1, work))
+            if rc == 0 and self.timeline is not None:
+                cur = torch.cuda.current_stream()
+                self.timeline.append(("rsr_lstmp_fused_fwd", "side" if cur == self._side else "main", e0, e1, work))
         else:
             rc = fn(*args)
         if rc == _lib.RSR_E_RESIDENT:

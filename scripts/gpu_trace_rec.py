@@ -40,10 +40,11 @@ buf = (C.c_ulonglong * (64 * 8))()
 h.lib.rsr_debug_trace.argtypes = [C.c_void_p, C.c_int]
 rc = h.lib.rsr_debug_trace(buf, 64 * 8)
 tr = np.array(buf[:], dtype=np.int64).reshape(64, 8)[:T]
-names = (["top", "full-wait done", "mma issued", "mma done", "xchg+sync", "gates+send"] if which == "fwd" else
-         ["top", "loads+wait+sum", "gate bwd", "barrier", "mma done", "ld+send"])
+names = (["top", "full-wait done", "mma issued", "mma done", "xchg+sync", "gate math", "st.async sends", "global stores"] if which == "fwd" else
+         ["top", "partials landed", "summed", "gate math", "dz stores", "bar+mma issued", "mma done", "ld+send"])
 print(which, "B %d Cp %d rc %d; cycles between trace points (median over steps 5..%d)" % (B, Cp, rc, T - 2))
-d = np.diff(tr[5:T - 1, :6], axis=1)
-for i in range(5):
+nt = len(names)
+d = np.diff(tr[5:T - 1, :nt], axis=1)
+for i in range(nt - 1):
     print("  %-16s -> %-16s %7.0f" % (names[i], names[i + 1], np.median(d[:, i])))
 print("  step period %7.0f cycles" % np.median(np.diff(tr[5:T - 1, 0])))
