@@ -306,27 +306,29 @@ lstmp_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const BwdParams p)
             }
             __syncthreads();
         }
+        // every dmt value of this thread in flight at once (L2: other CTAs' atomics landed there), then branch-free
+        // gate math -- a per-utterance `if` with the load inside serialised NH L2 round trips per step
+        float dmv[NH];
+#pragma unroll
+        for (int i = 0; i < NH; ++i) {
+            const int b = b0 + half + 2 * i;
+            dmv[i] = b < p.B ? __ldcg(p.dmt + ((size_t)t * p.B + b) * Cp + cell) : 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < NH; ++i) {
             const int n = half + 2 * i;
             const int b = b0 + n;
-            float dz_i = 0.f, dz_j = 0.f, dz_f = 0.f, dz_o = 0.f;
-            const bool active = (b < p.B) && (t < len[i]);
-            if (active) {
-                const size_t row = (size_t)t * p.B + b;
-                const float dm = __ldcg(p.dmt + row * Cp + cell);      // L2: other CTAs' atomics landed there
-                const float tc = tanhf_(s_c[i]);
-                dz_o = dm * tc * s_o[i] * (1.f - s_o[i]);
-                const float dc = dcar[i] + dm * s_o[i] * (1.f - tc * tc) + dz_o * wo;
-                dz_f = dc * s_cp[i] * s_f[i] * (1.f - s_f[i]);
-                dz_i = dc * s_j[i] * s_i[i] * (1.f - s_i[i]);
-                dz_j = dc * s_i[i] * (1.f - s_j[i] * s_j[i]);
-                dcar[i] = dc * s_f[i] + dz_f * wf + dz_i * wi;
-                a_dwo += dz_o * s_c[i]; a_dwf += dz_f * s_cp[i]; a_dwi += dz_i * s_cp[i];
-                a_db[0] += dz_i; a_db[1] += dz_j; a_db[2] += dz_f; a_db[3] += dz_o;
-            } else {
-                dcar[i] = 0.f;
-            }
+            const float m = ((b < p.B) && (t < len[i])) ? 1.f : 0.f;     // frozen steps / rows past the batch: exact zeros
+            const float dm = dmv[i];
+            const float tc = tanhf_(s_c[i]);
+            const float dz_o = m * dm * tc * s_o[i] * (1.f - s_o[i]);
+            const float dc = dcar[i] + dm * s_o[i] * (1.f - tc * tc) + dz_o * wo;
+            const float dz_f = m * dc * s_cp[i] * s_f[i] * (1.f - s_f[i]);
+            const float dz_i = m * dc * s_j[i] * s_i[i] * (1.f - s_i[i]);
+            const float dz_j = m * dc * s_i[i] * (1.f - s_j[i] * s_j[i]);
+            dcar[i] = m * (dc * s_f[i] + dz_f * wf + dz_i * wi);
+            a_dwo += dz_o * s_c[i]; a_dwf += dz_f * s_cp[i]; a_dwi += dz_i * s_cp[i];
+            a_db[0] += dz_i; a_db[1] += dz_j; a_db[2] += dz_f; a_db[3] += dz_o;
             const uint16_t h_i = f2h(dz_i, p.bf), h_j = f2h(dz_j, p.bf), h_f = f2h(dz_f, p.bf), h_o = f2h(dz_o, p.bf);
             // B operand tile (K-major, SW128): row n, local packed column jl*128 + g*32 + c32
             const int cb = (jl * 2) * NB * 128;
