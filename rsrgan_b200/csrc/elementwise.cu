@@ -270,13 +270,8 @@ __global__ void __launch_bounds__(256) seg_sumsq_kernel(const float* __restrict_
 }
 
 // hyper (device, fp32): [0]=lr  [1]=beta1  [2]=beta2  [3]=eps  [4]=beta1_power  [5]=beta2_power  [6]=lr_t
-__global__ void adam_tick_kernel(float* hyper) {
-    // tf.train.AdamOptimizer keeps beta{1,2}_power as fp32 variables; lr_t is formed from the
-    // powers BEFORE they are multiplied (powers start at beta1/beta2).
-    const float b1p = hyper[4], b2p = hyper[5];
-    hyper[6] = hyper[0] * sqrtf(1.f - b2p) / (1.f - b1p);
-}
 __global__ void adam_tock_kernel(float* hyper) {
+    hyper[6] = hyper[0] * sqrtf(1.f - hyper[5]) / (1.f - hyper[4]);   // lr_t of the step just applied (diagnostic)
     hyper[4] *= hyper[1];
     hyper[5] *= hyper[2];
 }
@@ -297,7 +292,10 @@ __global__ void __launch_bounds__(256) clip_update_kernel(const float* __restric
     float gg[4] = {gq.x * sc, gq.y * sc, gq.z * sc, gq.w * sc};
     float tt[4] = {th.x, th.y, th.z, th.w};
     if (ADAM) {
-        const float b1 = hyper[1], b2 = hyper[2], eps = hyper[3], lr_t = hyper[6];
+        // tf.train.AdamOptimizer keeps beta{1,2}_power as fp32 variables; lr_t is formed from the powers BEFORE they
+        // are multiplied (they start at beta1 / beta2); adam_tock_kernel advances them after this sweep
+        const float b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
+        const float lr_t = hyper[0] * sqrtf(1.f - hyper[5]) / (1.f - hyper[4]);
         float4 mq = *reinterpret_cast<const float4*>(m + base);
         float4 vq = *reinterpret_cast<const float4*>(v + base);
         float mm[4] = {mq.x, mq.y, mq.z, mq.w}, vv[4] = {vq.x, vq.y, vq.z, vq.w};
@@ -492,7 +490,8 @@ extern "C" int rsr_colsum32(rsr_handle* h, void* stream, const float* x32, int l
 extern "C" int rsr_seg_sumsq(rsr_handle* h, void* stream, const float* grad, float gmul, const int* seg_id,
                              long long n_elems, int n_seg, float* sumsq) {
     if (!h || !grad || !seg_id || !sumsq || n_elems <= 0 || (n_elems & 1023) || n_seg <= 0) return RSR_E_ARG;
-    RSR_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * n_seg, (cudaStream_t)stream));
+    // (a kernel, not cudaMemsetAsync: inside the captured graph the memset node cost ~10 us of dependency latency)
+    fill32_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sumsq, n_seg, 0.0f);
     seg_sumsq_kernel<<<(unsigned)(n_elems / 1024), 256, 0, (cudaStream_t)stream>>>(grad, gmul, seg_id, sumsq);
     RSR_LAUNCH_CHECK();
     return 0;
@@ -513,7 +512,6 @@ extern "C" int rsr_clip_adam_ema(rsr_handle* h, void* stream, const float* grad,
                                  const float* sumsq, float max_norm, float* hyper, float ema_decay,
                                  long long n_elems, float* theta, float* m, float* v, float* ema, void* theta16) {
     if (!h || !grad || !seg_id || !sumsq || !hyper || !theta || !m || !v || n_elems <= 0 || (n_elems & 1023)) return RSR_E_ARG;
-    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper);
     clip_update_kernel<1><<<(unsigned)(n_elems / 1024), 256, 0, (cudaStream_t)stream>>>(
         grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, m, v, ema, (uint16_t*)theta16,
         h->dtype == RSR_DTYPE_BF16);

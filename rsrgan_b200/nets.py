@@ -15,6 +15,8 @@ arithmetic is done by librsrgan_sm100.so (ops.Handle).  No function here has a C
 """
 from __future__ import annotations
 
+import contextlib
+
 import torch
 
 from . import packing, params
@@ -65,9 +67,11 @@ class FC(object):
         return y16, y32
 
     def bwd(self, ctx, x16, dy16, rows, want_dw=True, want_dx=True, prev_y16=None, prev_act=ACT_NONE,
-            resid32=None, want32=False):
+            resid32=None, want32=False, dw_side=True):
         """dy16: gradient wrt this layer's PRE-activation.  Returns the gradient wrt the input,
-        multiplied by prev_act'(prev_y16) when the producer of x16 was an activated FC."""
+        multiplied by prev_act'(prev_y16) when the producer of x16 was an activated FC.
+        dw_side=False keeps the weight gradient on the calling stream (last layer of a backward pass: the side stream
+        still holds the previous layer's weight-gradient GEMMs and nothing else is left for the main stream to do)."""
         net, h = self.net, self.net.h
         dx16 = dx32 = None
         if want_dx:    # the producer layer waits for this: main stream first
@@ -76,7 +80,7 @@ class FC(object):
             h.gemm(dy16, net.P.view(self.wname, "theta16"), rows, self.inp, self.outp, resid=resid32,
                    dact_src=prev_y16, dact=prev_act, out16=dx16, out32=dx32)
         if want_dw:
-            with h.side_stream():
+            with (h.side_stream() if dw_side else contextlib.nullcontext()):
                 h.gemm(x16, dy16, self.inp, self.outp, rows, a_mn=True, b_mn=True, beta=1.0,
                        out32=net.P.view(self.wname, "grad"))
                 h.colsum16(dy16, rows, self.outp, net.P.view(self.bname, "grad"), accumulate=True)
@@ -326,8 +330,17 @@ class Net(object):
         self.refresh()
 
     def refresh(self):
-        for l in self.layers:
-            l.refresh()
+        """Weight-derived operands after an update.  The per-layer refreshes are tiny and independent: alternate
+        them between the two streams and join."""
+        h = self.h
+        for i, l in enumerate(self.layers):
+            if i & 1 and hasattr(h, "side_stream"):
+                with h.side_stream():
+                    l.refresh()
+            else:
+                l.refresh()
+        if hasattr(h, "join"):
+            h.join()
 
 
 RCED_FILTERS = (12, 16, 20, 24, 32, 24, 20, 16, 12)      # models/rced.py:92
@@ -457,7 +470,7 @@ class Generator(Net):
                 first = i == 1
                 d16, d32 = Ls[i].bwd("g", acts[i], d16, d32, B, T, lengths, prev_y16=acts[1] if first else None,
                                      prev_act=ACT_LRELU if first else ACT_NONE, want32=not first)
-            Ls[0].bwd("g", acts[0], d16, rows, want_dx=False)
+            Ls[0].bwd("g", acts[0], d16, rows, want_dx=False, dw_side=False)
             return
         d16, d32 = Ls[-1].bwd("g", acts[-1], dy16, rows, want32=True)
         for i in range(len(Ls) - 2, -1, -1):
