@@ -71,6 +71,18 @@ typedef struct rsr_gemm_args {
 } rsr_gemm_args;
 int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a);
 
+/* fully_connected with ONE output unit -- the discriminator heads (models/discriminator_dnn.py:90-92,
+ * models/discriminator_lstm.py:100-104).  Same arithmetic as rsr_gemm (16-bit operands, fp32 accumulate) without
+ * the padded tensor-core tile: both directions are HBM streams.
+ *   forward        out32[r * ldo] = sum_k x16[r, k] * w16[k * ldw] + bias[0]          (K multiple of 8)
+ *   data gradient  dx16[r, k] = dy16[r * ldy] * w16[k * ldw] * act'(dact_src[r, k])   (dact_src NULL: no mask;
+ *                  act' from the producer's OUTPUT as in rsr_gemm)
+ * The weight gradient stays rsr_gemm (x^T dy). */
+int rsr_fc1_fwd(rsr_handle* h, void* stream, const void* x16, int ldx, long long rows, int K,
+                const void* w16, int ldw, const float* bias, float* out32, int ldo);
+int rsr_fc1_bwd_dx(rsr_handle* h, void* stream, const void* dy16, int ldy, long long rows, int K,
+                   const void* w16, int ldw, const void* dact_src, int ldd, int dact, void* dx16, int ldo);
+
 /* input staging ---------------------------------------------------------------------- */
 /* x fp32 batch-major (B, T, D) -> h16 time-major [T*B, ld16] (and optional fp32 copy [T*B, ld32]):
  *   v = (x - mean[d]) * istd[d]   (mean/istd NULL = identity; io_funcs/make_tfrecords.py:84-87)

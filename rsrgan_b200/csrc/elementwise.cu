@@ -387,6 +387,70 @@ __global__ void conv_w_flip_kernel(const uint16_t* __restrict__ w, int W, int Ci
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// fully_connected with ONE output unit (the discriminator heads, models/discriminator_dnn.py:90-92,
+// models/discriminator_lstm.py:100-104): a 128 x 16 tensor-core tile is almost all padding there, and both
+// directions are pure HBM streams -- forward = one dot product per row, data gradient = an outer product masked by
+// the producer's relu'.  One warp per row, 16-byte chunks per lane, the weight column staged in shared memory.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fc1_fwd_kernel(const uint16_t* __restrict__ x, int ldx, long long rows, int K,
+                                                      const uint16_t* __restrict__ w, int ldw, const float* __restrict__ bias,
+                                                      float* __restrict__ out, int ldo, int bf) {
+    extern __shared__ float fc1_w[];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) fc1_w[k] = h2f(w[(size_t)k * ldw], bf);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float b0 = bias ? bias[0] : 0.f;
+    for (long long r = warp0; r < rows; r += nwarps) {
+        const uint16_t* xr = x + r * ldx;
+        float acc = 0.f;
+        for (int k0 = lane * 8; k0 < K; k0 += 256) {       // K is a multiple of 8 (zero-padded activations)
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(xr + k0));
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc = fmaf(h2f((uint16_t)(u[i] & 0xFFFFu), bf), fc1_w[k0 + 2 * i], acc);
+                acc = fmaf(h2f((uint16_t)(u[i] >> 16), bf), fc1_w[k0 + 2 * i + 1], acc);
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[r * ldo] = acc + b0;
+    }
+}
+
+// dx[r, k] = dy[r] * w[k] * act'(y[r, k])   (y = the producer's activation OUTPUT; dact NONE: no mask)
+__global__ void __launch_bounds__(256) fc1_bwd_dx_kernel(const uint16_t* __restrict__ dy, int ldy, long long rows, int K,
+                                                         const uint16_t* __restrict__ w, int ldw,
+                                                         const uint16_t* __restrict__ y, int ldd, int dact,
+                                                         uint16_t* __restrict__ dx, int ldo, int bf) {
+    extern __shared__ float fc1_w[];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) fc1_w[k] = h2f(w[(size_t)k * ldw], bf);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float neg = dact == RSR_ACT_LRELU ? 0.3f : 0.0f;
+    const bool mask = y != nullptr && dact != RSR_ACT_NONE;
+    for (long long r = warp0; r < rows; r += nwarps) {
+        const float g = h2f(dy[r * ldy], bf);
+        for (int k0 = lane * 8; k0 < K; k0 += 256) {
+            uint4 q = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);   // any positive pattern
+            if (mask) q = __ldg(reinterpret_cast<const uint4*>(y + r * ldd + k0));
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool pos_lo = !mask || (int16_t)(u[i] & 0xFFFFu) > 0, pos_hi = !mask || (int32_t)u[i] >= 0x10000;
+                o[i] = pack2(g * fc1_w[k0 + 2 * i] * (pos_lo ? 1.0f : neg), g * fc1_w[k0 + 2 * i + 1] * (pos_hi ? 1.0f : neg), bf);
+            }
+            *reinterpret_cast<uint4*>(dx + r * ldo + k0) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
@@ -591,6 +655,29 @@ extern "C" int rsr_conv_w_flip(rsr_handle* h, void* stream, const void* w16, int
     if (!h || !w16 || !out16 || W <= 0 || Cin_p <= 0 || Cout_p <= 0) return RSR_E_ARG;
     conv_w_flip_kernel<<<grid_for((long long)W * Cin_p * Cout_p, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
         (const uint16_t*)w16, W, Cin_p, Cout_p, (uint16_t*)out16);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_fc1_fwd(rsr_handle* h, void* stream, const void* x16, int ldx, long long rows, int K,
+                           const void* w16, int ldw, const float* bias, float* out32, int ldo) {
+    if (!h || !x16 || !w16 || !out32 || rows <= 0 || K <= 0 || ldo <= 0 || ldw <= 0) return RSR_E_ARG;
+    if ((K & 7) || (ldx & 7) || ldx < K || ((uintptr_t)x16 & 15) || K > 8192) return RSR_E_SHAPE;
+    // few, long-lived blocks: every block stages the strided weight column once
+    fc1_fwd_kernel<<<grid_for(rows * 32, 256, h->num_sms, 2), 256, (size_t)K * 4, (cudaStream_t)stream>>>(
+        (const uint16_t*)x16, ldx, rows, K, (const uint16_t*)w16, ldw, bias, out32, ldo, h->dtype == RSR_DTYPE_BF16);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_fc1_bwd_dx(rsr_handle* h, void* stream, const void* dy16, int ldy, long long rows, int K,
+                              const void* w16, int ldw, const void* dact_src, int ldd, int dact, void* dx16, int ldo) {
+    if (!h || !dy16 || !w16 || !dx16 || rows <= 0 || K <= 0 || ldy <= 0 || ldw <= 0) return RSR_E_ARG;
+    if ((K & 7) || (ldo & 7) || ldo < K || ((uintptr_t)dx16 & 15) || K > 8192) return RSR_E_SHAPE;
+    if (dact_src && ((ldd & 7) || ldd < K || ((uintptr_t)dact_src & 15))) return RSR_E_SHAPE;
+    fc1_bwd_dx_kernel<<<grid_for(rows * 32, 256, h->num_sms, 2), 256, (size_t)K * 4, (cudaStream_t)stream>>>(
+        (const uint16_t*)dy16, ldy, rows, K, (const uint16_t*)w16, ldw, (const uint16_t*)dact_src, ldd, dact,
+        (uint16_t*)dx16, ldo, h->dtype == RSR_DTYPE_BF16);
     RSR_LAUNCH_CHECK();
     return 0;
 }

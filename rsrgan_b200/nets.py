@@ -62,6 +62,10 @@ class FC(object):
         net, h = self.net, self.net.h
         y16 = net.ws.get((ctx, self.scope, "y16"), rows, self.outp, h.h16) if want16 else None
         y32 = net.ws.get((ctx, self.scope, "y32"), rows, self.outp, F32) if want32 else None
+        if self.n_out == 1 and self.act == ACT_NONE and want32 and not want16 and self.inp >= 64:
+            # one output unit: a dot product per row (HBM stream) instead of a padded tensor-core tile
+            h.fc1_fwd(x16, rows, self.inp, net.P.view(self.wname, "theta16"), net.P.view(self.bname), y32)
+            return y16, y32
         h.gemm(x16, net.P.view(self.wname, "theta16"), rows, self.outp, self.inp, b_mn=True,
                bias=net.P.view(self.bname), act=self.act, out16=y16, out32=y32)
         return y16, y32
@@ -77,8 +81,12 @@ class FC(object):
         if want_dx:    # the producer layer waits for this: main stream first
             dx16 = net.ws.get((ctx, self.scope, "dx16"), rows, self.inp, h.h16)
             dx32 = net.ws.get((ctx, self.scope, "dx32"), rows, self.inp, F32) if want32 else None
-            h.gemm(dy16, net.P.view(self.wname, "theta16"), rows, self.inp, self.outp, resid=resid32,
-                   dact_src=prev_y16, dact=prev_act, out16=dx16, out32=dx32)
+            if self.n_out == 1 and resid32 is None and not want32 and self.inp >= 64:
+                h.fc1_bwd_dx(dy16, rows, self.inp, net.P.view(self.wname, "theta16"), dx16, dact_src=prev_y16,
+                             dact=prev_act)      # outer product masked by the producer's relu' (HBM stream)
+            else:
+                h.gemm(dy16, net.P.view(self.wname, "theta16"), rows, self.inp, self.outp, resid=resid32,
+                       dact_src=prev_y16, dact=prev_act, out16=dx16, out32=dx32)
         if want_dw:
             with (h.side_stream() if dw_side else contextlib.nullcontext()):
                 h.gemm(x16, dy16, self.inp, self.outp, rows, a_mn=True, b_mn=True, beta=1.0,

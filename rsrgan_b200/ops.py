@@ -245,3 +245,13 @@ class Handle(object):
 
     def conv_w_flip(self, w16, W, cin_p, cout_p, out16):
         self._call("rsr_conv_w_flip", 1, self.h, _stream(), _p(w16), W, cin_p, cout_p, _p(out16))
+
+    # ------------------------------------------------- one-output fully_connected (discriminator heads)
+    def fc1_fwd(self, x16, rows, K, w16, bias, out32):
+        self._call("rsr_fc1_fwd", 1, self.h, _stream(), _p(x16), x16.stride(0), rows, K, _p(w16), w16.stride(0),
+                   _p(bias), _p(out32), out32.stride(0), work=2.0 * rows * K)
+
+    def fc1_bwd_dx(self, dy16, rows, K, w16, dx16, dact_src=None, dact=ACT_NONE):
+        self._call("rsr_fc1_bwd_dx", 1, self.h, _stream(), _p(dy16), dy16.stride(0), rows, K, _p(w16), w16.stride(0),
+                   _p(dact_src), dact_src.stride(0) if dact_src is not None else 0, dact, _p(dx16), dx16.stride(0),
+                   work=2.0 * rows * K)

@@ -78,6 +78,18 @@ class FakeHandle(object):
         if out32 is not None:
             out32[:M, :N] = v + (beta * out32[:M, :N] if beta != 0.0 else 0.0)
 
+    # ------------------------------------------------- one-output fully_connected
+    def fc1_fwd(self, x16, rows, K, w16, bias, out32):
+        self.launches += 1
+        out32[:rows, 0] = x16[:rows, :K].float() @ w16[:K, 0].float() + (bias[0] if bias is not None else 0.0)
+
+    def fc1_bwd_dx(self, dy16, rows, K, w16, dx16, dact_src=None, dact=ACT_NONE):
+        self.launches += 1
+        v = dy16[:rows, :1].float() * w16[:K, 0].float().reshape(1, K)
+        if dact_src is not None:
+            v = v * _dact(dact_src[:rows, :K].float(), dact)
+        dx16[:rows, :K] = v.to(self.h16)
+
     # ------------------------------------------------------------- 1-D conv glue
     def conv_stage_frames(self, x, B, T, L, S, Cp, out16, mean=None, istd=None, time_major_in=False, ldx=None):
         self.launches += 1

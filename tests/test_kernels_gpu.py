@@ -372,3 +372,31 @@ def test_conv_stage_frames(h):
     ref = ((x - mean) * (1.0 / std)).transpose(1, 0, 2)
     assert rel(o[:, :, :L, 0], ref) < tol(h, 5e-4, 4e-3)
     assert not o[:, :, L:].any() and not o[:, :, :, 1:].any()
+
+
+@pytest.mark.parametrize("rows,K", [(12800, 1024), (37, 64), (1000, 264)])
+def test_fc1_forward_and_data_gradient(h, rows, K):
+    """One-output fully_connected (discriminator heads): dot product per row and the relu'-masked outer product, against
+    the exact product of the same 16-bit operands."""
+    dev, rng = h.device, np.random.default_rng(rows + K)
+    x16 = torch.tensor(rng.standard_normal((rows, K)).astype(np.float32), device=dev).to(h.h16)
+    w16 = torch.zeros(K, 8, dtype=h.h16, device=dev)
+    w16[:, 0] = torch.tensor((rng.standard_normal(K) * 0.05).astype(np.float32), device=dev).to(h.h16)
+    bias = torch.tensor([0.25] + [0.0] * 7, device=dev)
+    out = torch.full((rows, 8), 9.0, device=dev)
+    h.fc1_fwd(x16, rows, K, w16, bias, out)
+    torch.cuda.synchronize()
+    ref = x16.double().cpu().numpy() @ w16[:, 0].double().cpu().numpy() + 0.25
+    assert rel(out[:, 0].cpu().numpy(), ref) < 1e-5
+    assert bool((out[:, 1:] == 9.0).all())
+    y16 = torch.tensor(np.maximum(rng.standard_normal((rows, K)), 0).astype(np.float32), device=dev).to(h.h16)
+    dy16 = torch.zeros(rows, 8, dtype=h.h16, device=dev)
+    dy16[:, 0] = torch.tensor(rng.standard_normal(rows).astype(np.float32), device=dev).to(h.h16)
+    for src, act in ((y16, O.ACT_RELU), (y16, O.ACT_LRELU), (None, O.ACT_NONE)):
+        dx = torch.zeros(rows, K, dtype=h.h16, device=dev)
+        h.fc1_bwd_dx(dy16, rows, K, w16, dx, dact_src=src, dact=act)
+        torch.cuda.synchronize()
+        r = np.outer(dy16[:, 0].double().cpu().numpy(), w16[:, 0].double().cpu().numpy())
+        if src is not None:
+            r = r * np.where(y16.double().cpu().numpy() > 0, 1.0, 0.3 if act == O.ACT_LRELU else 0.0)
+        assert rel(dx.float().cpu().numpy(), r) < tol(h, 5e-4, 4e-3)
