@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the RSRGAN GAN-training hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfgP|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg4|cfg5|cfgP|cfgR]
 
 metric : GAN train frames/sec (257-d LPS -> 40-d MFCC)
 step   : one batch schedule of scripts/train_gan_rnn_placeholder.py:72-101 = 1 D update + 2 G updates
@@ -41,6 +41,9 @@ CONFIGS = {
     # BASELINE.json configs[4]: res_lstm_l 4 x 1024 (P = 257) + discriminator_lstm, T = 200, B = 64 per GPU
     "cfg5": dict(g_type="res_lstm_l", d_type="lstm", g_cell=1024, g_proj=257, g_layers=4, B=64, T=200,
                  name="gan_rnn_placeholder: res_lstm_l G (4xLSTMP 1024->257) + discriminator_lstm, B=64 x T=200 per GPU"),
+    # BASELINE.json configs[3]: RCED convolutional generator (splice = 1) + discriminator_dnn, 256 frames per GPU
+    "cfg4": dict(g_type="rced", d_type="dnn", g_cell=None, g_proj=None, g_layers=None, B=256, T=1,
+                 name="frame GAN: RCED generator (9 x conv1d SAME + FC) + discriminator_dnn(1024x4), 256 frames per GPU"),
     "cfgR": dict(g_type="res_lstm_l", d_type="lstm", g_cell=760, g_proj=257, g_layers=4, B=8, T=100,
                  name="run_gan_rnn_placeholder.sh: res_lstm_l G (4xLSTMP 760->257) + discriminator_lstm, B=8 x T=100"),
 }
@@ -50,7 +53,10 @@ def flops_per_frame(cfg):
     """7 F_G + 10 F_D algorithmic forward-equivalent flops per input frame per schedule."""
     def lstmp(i, c, p):
         return 2 * (i + p) * 4 * c + 2 * c * p
-    if cfg["g_type"] == "lstm":
+    if cfg["g_type"] == "rced":
+        ch, wd = (1, 12, 16, 20, 24, 32, 24, 20, 16, 12), (13, 11, 9, 7, 7, 7, 9, 11, 13)     # models/rced.py:92-93
+        fg = sum(2 * 257 * w * ch[i] * ch[i + 1] for i, w in enumerate(wd)) + 2 * 257 * 12 * 40
+    elif cfg["g_type"] == "lstm":
         p, c = cfg["g_proj"], cfg["g_cell"]
         fg = 2 * 257 * p + cfg["g_layers"] * lstmp(p, c, p) + 2 * p * 40
     else:
@@ -204,7 +210,7 @@ def main():
 
     B, T = cfg["B"], cfg["T"]
     args = Namespace(g_type=cfg["g_type"], d_type=cfg["d_type"], batch_size=B, num_gpu=world,
-                     g_cell=cfg["g_cell"], g_proj=cfg["g_proj"], g_layers=cfg["g_layers"],
+                     **{k: cfg[k] for k in ("g_cell", "g_proj", "g_layers") if cfg[k] is not None},
                      init_mse_weight=10.0, init_disc_noise_std=0.05, l2_scale=0.0, dtype=a.dtype, seed=1234,
                      # run_gan_rnn_placeholder.sh:127-128, times num_gpu (train...py:458-459)
                      g_learning_rate=8e-5 * world, d_learning_rate=1e-3 * world)
@@ -325,7 +331,7 @@ def main():
         out["ranks_in_sync"] = bool(torch.equal(lo, hi))
     if rank == 0:
         out["clocks"] = sampler.summary()
-        if world == 1 and not a.no_cpu_baseline:
+        if world == 1 and not a.no_cpu_baseline and cfg["g_type"] != "rced":
             from oracle import cpu_baseline as cb
             Bs = 32
             v, dt, cores = cb.time_schedule(cfg, Bs, T, steps=2, warmup=0)
