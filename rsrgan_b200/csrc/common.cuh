@@ -123,6 +123,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
         ::"r"(dst), "l"((uint64_t)m), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+// 3-D tile load MULTICAST to every CTA of the cluster named in `mask`: one L2 read, the same box lands at the same
+// shared-memory offset of each destination CTA and completes `bytes` on each destination's mbarrier at offset `bar`.
+__device__ __forceinline__ void tma_load_3d_multicast(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                      int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"((uint64_t)m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+
 // TMA 2-D tile STORE / REDUCE-ADD shared -> global (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

@@ -59,6 +59,7 @@ struct CFwdParams {
     const uint16_t* kxT;        // [4Cp, Ik] packed gate rows of K_x^T, Ik = input width padded to 16, zero padded
     const float* bias;          // [4Cp] packed
     int Ik;
+    int xmode;                  // exchange of mt_t: 0 = st.async all-gather (DSMEM), 1 = via L2 + TMA multicast (tmM)
 };
 
 // One cluster = one utterance group of NHALF x 16 utterances; CTA j owns cells [32j, 32j+32).  The CTA's
@@ -70,7 +71,8 @@ struct CFwdParams {
 // exchange); otherwise Zx = X K_x + b arrives precomputed (fp32, from rsr_gemm).
 template <int NHALF, bool FUSEX>
 __global__ void __launch_bounds__(128 * NHALF, 1)
-lstmp_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const CFwdParams p) {
+lstmp_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM,
+                         const CFwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -105,6 +107,7 @@ lstmp_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const CFwdPara
     while (tcols < a_cols + NB * NHALF) tcols <<= 1;
     if (htid == 0) {
         if (FUSEX) tma_prefetch_desc(&tmX);
+        if (p.xmode) tma_prefetch_desc(&tmM);
         mbar_init(barM, 1); mbar_init(full0, 1); mbar_init(full1, 1); mbar_init(xfull0, 1); mbar_init(xfull1, 1);
         fence_mbar_init();
         mbar_expect_tx(full1, sB_bytes);        // armed for step 1 (mt_0 of every CTA of the cluster)
@@ -272,28 +275,46 @@ lstmp_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const CFwdPara
             }
             const uint32_t lo = pack2(mtv[0], mtv[1], p.bf), hi = pack2(mtv[2], mtv[3], p.bf);
             TRACE(5);
-            if (t + 1 < p.T) {
-                // pair (quad 2k, quad 2k+1) -> one 16-byte k-chunk (8 cells) of row n
-                const uint32_t plo = __shfl_xor_sync(0xffffffffu, lo, 1), phi = __shfl_xor_sync(0xffffffffu, hi, 1);
-                const bool odd = a & 1;
-                const uint32_t w0 = odd ? plo : lo, w1 = odd ? phi : hi, w2 = odd ? lo : plo, w3 = odd ? hi : phi;
-                const uint32_t off = (uint32_t)(4 * j + (a >> 1)) * (NB * 16u) + (uint32_t)n * 16u;
-                const uint32_t dst = sB0 + (uint32_t)(buf ^ 1) * sB_bytes + off;
-                const uint32_t dbar = buf ? full0 : full1;
+            const size_t row = (size_t)t * p.B + b_own;
+            if (p.xmode == 0) {
+                if (t + 1 < p.T) {
+                    // pair (quad 2k, quad 2k+1) -> one 16-byte k-chunk (8 cells) of row n
+                    const uint32_t plo = __shfl_xor_sync(0xffffffffu, lo, 1), phi = __shfl_xor_sync(0xffffffffu, hi, 1);
+                    const bool odd = a & 1;
+                    const uint32_t w0 = odd ? plo : lo, w1 = odd ? phi : hi, w2 = odd ? lo : plo, w3 = odd ? hi : phi;
+                    const uint32_t off = (uint32_t)(4 * j + (a >> 1)) * (NB * 16u) + (uint32_t)n * 16u;
+                    const uint32_t dst = sB0 + (uint32_t)(buf ^ 1) * sB_bytes + off;
+                    const uint32_t dbar = buf ? full0 : full1;
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (k < HG) st_async_v4(dst + rdelta[k], w0, w1, w2, w3, dbar + rdelta[k]);
-            }
-            TRACE(6);
-            if (b_own < p.B) {      // off the critical path: operands of the hoisted projection GEMM and of the backward pass
-                const size_t row = (size_t)t * p.B + b_own;
-                *reinterpret_cast<uint2*>(p.mt_seq + (row + p.B) * p.Cp + cell0) = make_uint2(lo, hi);
-                if (p.save) {
-                    float* s = p.save + row * 5 * p.Cp + cell0;
-#pragma unroll
-                    for (int k = 0; k < 5; ++k)
-                        *reinterpret_cast<float4*>(s + (size_t)k * p.Cp) = make_float4(sv[k][0], sv[k][1], sv[k][2], sv[k][3]);
+                    for (int k = 0; k < 8; ++k)
+                        if (k < HG) st_async_v4(dst + rdelta[k], w0, w1, w2, w3, dbar + rdelta[k]);
                 }
+                TRACE(6);
+                // off the critical path: operand of the hoisted projection GEMM and of the backward pass
+                if (b_own < p.B) *reinterpret_cast<uint2*>(p.mt_seq + (row + p.B) * p.Cp + cell0) = make_uint2(lo, hi);
+            } else {
+                // The global copy of mt_t (needed anyway) is the exchange medium: each CTA stores its 32-cell slice
+                // (1 KB per half) and one elected thread multicasts that slice from L2 into the B-operand buffer of
+                // every CTA of the cluster with a single 3-D TMA load -- 1 KB leaves the SM instead of 16 KB of
+                // st.async traffic (same step time in practice, see fwd_xmode).
+                if (b_own < p.B) *reinterpret_cast<uint2*>(p.mt_seq + (row + p.B) * p.Cp + cell0) = make_uint2(lo, hi);
+                if (t + 1 < p.T) {
+                    fence_proxy_async_all();                 // generic-proxy stores -> visible to the async proxy (TMA)
+                    named_bar_sync(bar_id, 128);
+                    if (q == 0 && elect_one_sync()) {
+                        const uint32_t dst = sB0 + (uint32_t)(buf ^ 1) * sB_bytes + (uint32_t)(4 * j) * (NB * 16u);
+                        const uint32_t dbar = buf ? full0 : full1;
+                        tma_load_3d_multicast(dst, &tmM, dbar, 0, (t + 1) * p.B + b0, 4 * (int)j,
+                                              (uint16_t)((1u << G) - 1u));
+                    }
+                }
+                TRACE(6);
+            }
+            if (b_own < p.B && p.save) {
+                float* s = p.save + row * 5 * p.Cp + cell0;
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                    *reinterpret_cast<float4*>(s + (size_t)k * p.Cp) = make_float4(sv[k][0], sv[k][1], sv[k][2], sv[k][3]);
             }
         }
         TRACE(7);
@@ -643,6 +664,31 @@ int pick_cluster_halves(rsr_handle* h, int which, K1 k1, K2 k2, int B, int Cp, s
 
 }  // namespace
 
+// 3-D view of mt_seq [(T+1)*B, Cp] for the multicast exchange: (8 cells = 16 B | row | k-chunk of 8 cells), box
+// (8, NB, 4) = one CTA's 32-cell slice of NB utterances, landing in shared memory as [k-chunk][row][16 B] -- the
+// no-swizzle K-major core-matrix layout of the recurrent B operand.
+int make_mt_tmap(rsr_handle* h, const void* mt_seq, int B, int T, int Cp, CUtensorMap* out) {
+    cuuint64_t dims[3] = {8, (cuuint64_t)(T + 1) * B, (cuuint64_t)Cp / 8};
+    cuuint64_t strides[2] = {(cuuint64_t)Cp * 2, 16};
+    cuuint32_t box[3] = {8, (cuuint32_t)NB, 4};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = h->encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(mt_seq), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : RSR_E_ARG;
+}
+
+// Exchange mode of the forward kernels: st.async all-gather over DSMEM (default) or, with RSR_FWD_XCHG=l2mc, through
+// the global copy of mt_t + one multicast TMA load per CTA and step.  Measured on B200 (Cp = 512): the same step time
+// at B = 128 (2.87 vs 2.96 us) and at one half per cluster (2.27 vs 2.33), slower at Cp = 256 (2.24 vs 1.97) -- the
+// exchange costs ~2300 cycles of latency either way (st.async issue + landing vs store + proxy fence + L2 read), so
+// the 16 KB/step of DSMEM traffic is not what paces the kernel.  Kept as a tested alternative.
+int fwd_xmode(int nhalf) {
+    (void)nhalf;
+    const char* e = getenv("RSR_FWD_XCHG");
+    return (e && e[0] == 'l') ? 1 : 0;
+}
+
 // Returns 0 when launched, RSR_E_RESIDENT when the cluster variant does not apply (caller falls back to
 // the L2-exchange kernels of lstmp_sm100.cu), other values on error.
 int rsr_lstmp_fwd_cluster(rsr_handle* h, void* stream, int B, int T, int Cp, const float* zx, const void* wcT,
@@ -655,14 +701,16 @@ int rsr_lstmp_fwd_cluster(rsr_handle* h, void* stream, int B, int T, int Cp, con
     if (!nh) return RSR_E_RESIDENT;
     const int groups = (B + NB * nh - 1) / (NB * nh);
     CFwdParams p;
-    CUtensorMap tmX = {};   // unused by the unfused variant
+    CUtensorMap tmX = {}, tmM = {};   // tmX unused by the unfused variant
     p.kxT = nullptr; p.bias = nullptr; p.Ik = 0;
+    p.xmode = fwd_xmode(nh);
+    if (p.xmode) { const int rc = make_mt_tmap(h, mt_seq, B, T, Cp, &tmM); if (rc) return rc; }
     p.wcT = (const uint16_t*)wcT;
     p.B = B; p.T = T; p.Cp = Cp; p.bf = h->dtype == RSR_DTYPE_BF16; p.forget_bias = forget_bias;
     p.zx = zx; p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths;
     p.mt_seq = (uint16_t*)mt_seq; p.save = save;
-    if (nh == 1) return cluster_launch(lstmp_fwd_cluster_kernel<1, false>, groups, G, 128, s1, (cudaStream_t)stream, tmX, p);
-    return cluster_launch(lstmp_fwd_cluster_kernel<2, false>, groups, G, 256, s2, (cudaStream_t)stream, tmX, p);
+    if (nh == 1) return cluster_launch(lstmp_fwd_cluster_kernel<1, false>, groups, G, 128, s1, (cudaStream_t)stream, tmX, tmM, p);
+    return cluster_launch(lstmp_fwd_cluster_kernel<2, false>, groups, G, 256, s2, (cudaStream_t)stream, tmX, tmM, p);
 }
 
 // Fully fused forward: input GEMM + recurrent GEMM + gate epilogue.  RSR_E_RESIDENT when K_x^T does not fit in
@@ -689,8 +737,11 @@ int rsr_lstmp_fused_fwd_cluster(rsr_handle* h, void* stream, int B, int T, int I
     p.zx = nullptr; p.wcT = (const uint16_t*)wcT; p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths;
     p.mt_seq = (uint16_t*)mt_seq; p.save = save;
     p.kxT = (const uint16_t*)kxT; p.bias = bias; p.Ik = Ik;
-    if (nh == 1) return cluster_launch(lstmp_fwd_cluster_kernel<1, true>, groups, G, 128, s1, (cudaStream_t)stream, tmX, p);
-    return cluster_launch(lstmp_fwd_cluster_kernel<2, true>, groups, G, 256, s2, (cudaStream_t)stream, tmX, p);
+    CUtensorMap tmM = {};
+    p.xmode = fwd_xmode(nh);
+    if (p.xmode) { rc = make_mt_tmap(h, mt_seq, B, T, Cp, &tmM); if (rc) return rc; }
+    if (nh == 1) return cluster_launch(lstmp_fwd_cluster_kernel<1, true>, groups, G, 128, s1, (cudaStream_t)stream, tmX, tmM, p);
+    return cluster_launch(lstmp_fwd_cluster_kernel<2, true>, groups, G, 256, s2, (cudaStream_t)stream, tmX, tmM, p);
 }
 
 int rsr_lstmp_bwd_cluster(rsr_handle* h, void* stream, int B, int T, int Cp, const float* dmt, const void* wc,

@@ -150,6 +150,17 @@ def test_lstmp_recurrence_l2_exchange_variant(h, monkeypatch, B, T, I, C, P):
             assert v < t, (k, v, r)
 
 
+def test_lstmp_forward_l2_multicast_exchange(h, monkeypatch):
+    """RSR_FWD_XCHG=l2mc: mt_t travels through its global copy + one multicast TMA load per CTA instead of st.async."""
+    monkeypatch.setenv("RSR_FWD_XCHG", "l2mc")
+    for (B, T, I, C, P, ragged) in ((40, 10, 256, 512, 256, True), (8, 12, 40, 256, 40, True)):
+        r = _rec_case(h, B, T, I, C, P, ragged, seed=11)
+        assert r["pad"] == 0.0
+        for k, v in r.items():
+            if k != "pad":
+                assert v < tol(h, 1.5e-3, 1e-2), (k, v, r)
+
+
 @pytest.mark.parametrize("B,T,I,C,P,ragged", [
     (40, 10, 256, 512, 256, True),       # BASELINE cfg-2 layer: three groups, the last one partial
     (8, 12, 40, 256, 40, True),          # discriminator_lstm layer: Ik = 48 > I (zero padded K)
