@@ -204,10 +204,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # stdout carries exactly ONE JSON line: while the benchmark runs, file descriptor 1 points at stderr, so that
+    # banners written by native libraries (the "NCCL version ..." line appears on stdout at communicator creation)
+    # cannot precede it; the descriptor is restored just before the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout when
-        # NCCL_DEBUG is set in the environment) goes to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from rsrgan_b200.gan_rnn import GAN_RNN
 
@@ -341,7 +344,10 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                                    "sample": "%d of %d utterances x %d frames, 2 schedules (median), torch-CPU fp32 restatement "
                                              "of the reference (TF-1.4 unavailable)" % (Bs, B, T)}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(out), flush=True)
+        os.dup2(2, 1)                                        # anything printed during teardown goes to stderr again
     if world > 1:
         dist.destroy_process_group()
 

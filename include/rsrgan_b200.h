@@ -180,7 +180,9 @@ int rsr_colsum32(rsr_handle* h, void* stream, const float* x32, int ld, long lon
  * multiple of 1024 elements, seg_id[k] = segment of the k-th 1024-element block (device int32).
  * Gradients arrive summed over ranks (ncclAllReduce replaces utils/ops.py:343-376
  * average_gradients) and multiplied by the static loss scale: gmul = 1 / (world_size * loss_scale).
- *   pass 1  rsr_seg_sumsq : sumsq[s] = sum over segment s of (gmul*g)^2        (zeroed inside)
+ *   pass 1  rsr_seg_sumsq : sumsq[s] = sum over segment s of (gmul*g)^2        (deterministic: per-block partials, then
+ *           a fixed-order sum per segment -- no atomics, so every data-parallel rank derives bit-identical clip scales;
+ *           calls on one handle must be stream-ordered, the partials live in the handle's workspace)
  *   pass 2  ghat = gmul*g * max_norm / max(sqrt(sumsq[s]), max_norm)           (tf.clip_by_norm per tensor, :177-182)
  *           SGD : theta -= lr * ghat                                            (:144)
  *           Adam: m = b1 m + (1-b1) ghat ; v = b2 v + (1-b2) ghat^2 ;

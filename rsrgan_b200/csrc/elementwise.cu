@@ -252,8 +252,12 @@ __global__ void __launch_bounds__(256) l2_grad_kernel(float* __restrict__ g, con
 // ---------------------------------------------------------------------------------------
 // update sweep. One block = 1024 contiguous elements of exactly one segment (tensor).
 // ---------------------------------------------------------------------------------------
+// Deterministic (no atomics): pass 1 leaves one partial sum per 1024-element block, pass 2 adds the partials of each
+// segment in a fixed order.  Every data-parallel rank therefore derives bit-identical clip scales from the all-reduced
+// gradients and the replicas' weights stay bit-identical (an atomicAdd version let them drift apart by ulps whenever a
+// tensor's norm exceeded the clip threshold).
 __global__ void __launch_bounds__(256) seg_sumsq_kernel(const float* __restrict__ g, float gmul,
-                                                        const int* __restrict__ seg_id, float* __restrict__ sumsq) {
+                                                        float* __restrict__ partials) {
     __shared__ float sh[8];
     const long long base = (long long)blockIdx.x * 1024 + threadIdx.x * 4;
     const float4 q = *reinterpret_cast<const float4*>(g + base);
@@ -265,11 +269,37 @@ __global__ void __launch_bounds__(256) seg_sumsq_kernel(const float* __restrict_
     if (threadIdx.x < 32) {
         float t = threadIdx.x < 8 ? sh[threadIdx.x] : 0.f;
         t = warp_sum(t);
-        if (threadIdx.x == 0 && t != 0.f) atomicAdd(sumsq + seg_id[blockIdx.x], t);
+        if (threadIdx.x == 0) partials[blockIdx.x] = t;
     }
 }
+// one block per segment: its 1024-blocks are contiguous in seg_id (non-decreasing)
+__global__ void __launch_bounds__(256) seg_sumsq_finish_kernel(const float* __restrict__ partials,
+                                                               const int* __restrict__ seg_id, int n_blocks,
+                                                               float* __restrict__ sumsq) {
+    __shared__ float sh[256];
+    __shared__ int range[2];
+    const int seg = blockIdx.x;
+    if (threadIdx.x < 2) {                       // first block with seg_id >= seg + threadIdx.x
+        const int want = seg + (int)threadIdx.x;
+        int lo = 0, hi = n_blocks;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (seg_id[mid] < want) lo = mid + 1; else hi = mid;
+        }
+        range[threadIdx.x] = lo;
+    }
+    __syncthreads();
+    float s = 0.f;
+    for (int i = range[0] + (int)threadIdx.x; i < range[1]; i += 256) s += partials[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sumsq[seg] = sh[0];
+}
 
-// hyper (device, fp32): [0]=lr  [1]=beta1  [2]=beta2  [3]=eps  [4]=beta1_power  [5]=beta2_power  [6]=lr_t
 __global__ void adam_tock_kernel(float* hyper) {
     hyper[6] = hyper[0] * sqrtf(1.f - hyper[5]) / (1.f - hyper[4]);   // lr_t of the step just applied (diagnostic)
     hyper[4] *= hyper[1];
@@ -554,9 +584,11 @@ extern "C" int rsr_colsum32(rsr_handle* h, void* stream, const float* x32, int l
 extern "C" int rsr_seg_sumsq(rsr_handle* h, void* stream, const float* grad, float gmul, const int* seg_id,
                              long long n_elems, int n_seg, float* sumsq) {
     if (!h || !grad || !seg_id || !sumsq || n_elems <= 0 || (n_elems & 1023) || n_seg <= 0) return RSR_E_ARG;
-    // (a kernel, not cudaMemsetAsync: inside the captured graph the memset node cost ~10 us of dependency latency)
-    fill32_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sumsq, n_seg, 0.0f);
-    seg_sumsq_kernel<<<(unsigned)(n_elems / 1024), 256, 0, (cudaStream_t)stream>>>(grad, gmul, seg_id, sumsq);
+    const long long n_blocks = n_elems / 1024;
+    if (n_blocks > RSR_PARTIAL_WORDS) return RSR_E_SHAPE;
+    // (calls that share a handle must be stream-ordered: the per-block partials live in the handle's workspace)
+    seg_sumsq_kernel<<<(unsigned)n_blocks, 256, 0, (cudaStream_t)stream>>>(grad, gmul, h->partials);
+    seg_sumsq_finish_kernel<<<n_seg, 256, 0, (cudaStream_t)stream>>>(h->partials, seg_id, (int)n_blocks, sumsq);
     RSR_LAUNCH_CHECK();
     return 0;
 }

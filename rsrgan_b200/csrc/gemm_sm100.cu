@@ -645,6 +645,7 @@ extern "C" int rsr_create(rsr_handle** out, int device, int dtype) {
     e = cudaMalloc(&h->flags, RSR_FLAG_WORDS * sizeof(unsigned int));
     if (e != cudaSuccess) { delete h; return (int)e; }
     cudaMemset(h->flags, 0, RSR_FLAG_WORDS * sizeof(unsigned int));
+    if (cudaMalloc(&h->partials, RSR_PARTIAL_WORDS * sizeof(float)) != cudaSuccess) { cudaFree(h->flags); delete h; return RSR_E_NODEV; }
     *out = h;
     return 0;
 }
@@ -652,6 +653,7 @@ extern "C" int rsr_create(rsr_handle** out, int device, int dtype) {
 extern "C" int rsr_destroy(rsr_handle* h) {
     if (!h) return RSR_E_ARG;
     if (h->flags) cudaFree(h->flags);
+    if (h->partials) cudaFree(h->partials);
     delete h;
     return 0;
 }

@@ -45,6 +45,7 @@ struct rsr_handle {
     std::mutex mu;
     unsigned int* flags = nullptr;   // device: group-barrier counters, RSR_FLAG_WORDS words
     int flag_cursor = 0;
+    float* partials = nullptr;       // device: per-1024-block partial sums of rsr_seg_sumsq, RSR_PARTIAL_WORDS floats
     // co-resident clusters of the cluster recurrence kernels: [fwd|bwd][Cp/256 - 1][NB 16|32]; -1 = not queried yet
     int gemm2_pairs = -1;            // co-resident CTA pairs of the two-CTA GEMM (-1 = not queried yet)
     int fused_ik[2] = {-1, -1};      // Ik the fused-forward capacity entry was computed for
@@ -52,6 +53,7 @@ struct rsr_handle {
 };
 
 #define RSR_FLAG_WORDS 4096
+#define RSR_PARTIAL_WORDS (1 << 17)   // 128 Mi parameters per network
 
 // Dynamic shared memory floors that keep TMEM owners apart when kernels of different streams overlap:
 // two recurrence CTAs (each allocates up to all 512 TMEM columns and waits on its cluster) must never share
