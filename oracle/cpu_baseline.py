@@ -24,7 +24,11 @@ from . import rsr_oracle as O
 def _params(model_cfg, seed):
     rng = np.random.default_rng(seed)
     g_type, d_type = model_cfg["g_type"], model_cfg["d_type"]
-    if g_type == "lstm":
+    if g_type == "rced":
+        gp = O.init_g_rced(rng, dtype=np.float32)
+    elif g_type == "dnn":
+        gp = O.init_g_dnn(rng, dtype=np.float32)
+    elif g_type == "lstm":
         gp = O.init_g_lstm(rng, cell=model_cfg["g_cell"], proj=model_cfg["g_proj"], layers=model_cfg["g_layers"],
                            dtype=np.float32)
     else:
