@@ -158,8 +158,8 @@ def run_reference(a, cfg):
     if rank != 0:
         return
     from oracle import cpu_baseline as cb
-    Bs = min(32, cfg["B"])                   # bounded sample: 32 utterances x T frames per step (the CPU port runs
-                                             # 1.7x more frames/s on 32 utterances than on 8: the favourable sample)
+    Bs = max(1, min(cfg["B"], 3200 // cfg["T"]))   # bounded sample of ~3200 frames per step (cfg-2: 32 utterances x 100;
+                                                   # the CPU port runs 1.7x more frames/s on 32 utterances than on 8)
     gan = cb.CpuGan(cfg, 1234)
     import torch
     g = torch.Generator().manual_seed(1234)
@@ -340,7 +340,7 @@ def main():
         out["clocks"] = sampler.summary()
         if world == 1 and not a.no_cpu_baseline:
             from oracle import cpu_baseline as cb
-            Bs = min(32, B)
+            Bs = max(1, min(B, 3200 // T))
             v, dt, cores = cb.time_schedule(cfg, Bs, T, steps=2, warmup=0)
             out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                                    "sample": "%d of %d utterances x %d frames, 2 schedules (median), torch-CPU fp32 restatement "
