@@ -169,18 +169,32 @@ class LSTMP(object):
     def bwd(self, ctx, x16, dout16, dout32, B, T, lengths, want_dw=True, want_dx=True, prev_y16=None,
             prev_act=ACT_NONE, resid32=None, want32=False):
         """dout16/dout32: gradient wrt the layer output [T*B, Pp] (dout32 needed iff want_dw)."""
+        self.bwd_pre(ctx, dout16, B, T)
+        dx16, dx32 = self.bwd_main(ctx, dout16, B, T, lengths, want_dw=want_dw, want_dx=want_dx, prev_y16=prev_y16,
+                                   prev_act=prev_act, resid32=resid32, want32=want32)
+        if want_dw:
+            self.bwd_side(ctx, x16, dout32, B, T)
+        return dx16, dx32
+
+    # The backward pass in three pieces, so that a network can enqueue the NEXT layer's bwd_pre (a small GEMM on the
+    # critical path) before THIS layer's weight-gradient GEMMs start competing for SMs on the side stream.
+    def bwd_pre(self, ctx, dout16, B, T):
+        """dmt = dOut W_proj^T ; the recurrence kernel adds dz_{t+1} Wc^T"""
+        net, h = self.net, self.net.h
+        rows, Cp = T * B, self.Cp
+        dmt = net.ws.get((ctx, "dmt", Cp, B), rows, Cp, F32)
+        h.gemm(dout16, self._w()[2], rows, Cp, self.Pp, out32=dmt)
+
+    def bwd_main(self, ctx, dout16, B, T, lengths, want_dw=True, want_dx=True, prev_y16=None, prev_act=ACT_NONE,
+                 resid32=None, want32=False):
         net, h, P = self.net, self.net.h, self.net.P
         rows, Cp = T * B, self.Cp
         key = (ctx, self.prefix, B)
         Kx16, Kh16, Wp16 = self._w()
-        mt = net.ws.get(key + ("mt",), rows + B, Cp, h.h16)
-        out = net.ws.get(key + ("out",), rows + B, self.Pp, h.h16)
         sv = net.ws.get(key + ("save",), rows, 5 * Cp, F32)
         dmt = net.ws.get((ctx, "dmt", Cp, B), rows, Cp, F32)
         dz = net.ws.get(key + ("dz",), rows + B, 4 * Cp, h.h16)       # per layer: the side stream reads it after we return
-        dz[rows:].zero_()                                  # dz_{T} = 0 (no step after the last one)
-        # dmt = dOut W_proj^T ; the recurrence kernel adds dz_{t+1} Wc^T
-        h.gemm(dout16, Wp16, rows, Cp, self.Pp, out32=dmt)
+        dz[rows:].zero_()                                  # dz_{T} = 0 (no step after the last one; T varies per batch)
         if want_dw:
             gb = P.view(self.prefix + "bias", "grad")
             gi, gf, go = (P.view(self.prefix + n, "grad") for n in ("w_i_diag", "w_f_diag", "w_o_diag"))
@@ -196,18 +210,28 @@ class LSTMP(object):
             dx32 = net.ws.get(key + ("dx32",), rows, self.Ip, F32) if want32 else None
             h.gemm(dz, Kx16, rows, self.Ip, 4 * Cp, resid=resid32, dact_src=prev_y16, dact=prev_act,
                    out16=dx16, out32=dx32)
-        if want_dw:
-            with h.side_stream():   # weight gradients overlap the next layer's recurrence
-                gK = P.view(self.prefix + "kernel", "grad")
-                # dK = [x_t , m_{t-1}]^T dz_t  (two row blocks of the TF kernel)
-                h.gemm(x16, dz, self.Ip, 4 * Cp, rows, a_mn=True, b_mn=True, beta=1.0, out32=gK[:self.Ip])
-                h.gemm(out, dz, self.Pp, 4 * Cp, rows, a_mn=True, b_mn=True, beta=1.0, out32=gK[self.Ip:])
-                # dW_proj = mt_t^T (dOut_t + dz_{t+1} K_h^T)
-                dmtot = net.ws.get((ctx, "dmtot", self.Pp, B), rows, self.Pp, h.h16)
-                h.gemm(dz[B:], Kh16, rows, self.Pp, 4 * Cp, resid=dout32, out16=dmtot)
-                h.gemm(mt[B:], dmtot, Cp, self.Pp, rows, a_mn=True, b_mn=True, beta=1.0,
-                       out32=P.view(self.prefix + "projection/kernel", "grad"))
         return dx16, dx32
+
+    def bwd_side(self, ctx, x16, dout32, B, T):
+        """weight gradients, on the side stream: they overlap the next layer's recurrence"""
+        net, h, P = self.net, self.net.h, self.net.P
+        rows, Cp = T * B, self.Cp
+        key = (ctx, self.prefix, B)
+        Kx16, Kh16, Wp16 = self._w()
+        mt = net.ws.get(key + ("mt",), rows + B, Cp, h.h16)
+        out = net.ws.get(key + ("out",), rows + B, self.Pp, h.h16)
+        dz = net.ws.get(key + ("dz",), rows + B, 4 * Cp, h.h16)
+        with h.side_stream():
+            gK = P.view(self.prefix + "kernel", "grad")
+            # dK = [x_t , m_{t-1}]^T dz_t  (two row blocks of the TF kernel)
+            h.gemm(x16, dz, self.Ip, 4 * Cp, rows, a_mn=True, b_mn=True, beta=1.0, out32=gK[:self.Ip])
+            h.gemm(out, dz, self.Pp, 4 * Cp, rows, a_mn=True, b_mn=True, beta=1.0, out32=gK[self.Ip:])
+            # dW_proj = mt_t^T (dOut_t + dz_{t+1} K_h^T)
+            dmtot = net.ws.get((ctx, "dmtot", self.Pp, B), rows, self.Pp, h.h16)
+            h.gemm(dz[B:], Kh16, rows, self.Pp, 4 * Cp, resid=dout32, out16=dmtot)
+            h.gemm(mt[B:], dmtot, Cp, self.Pp, rows, a_mn=True, b_mn=True, beta=1.0,
+                   out32=P.view(self.prefix + "projection/kernel", "grad"))
+
 
 class ConvFrames(object):
     """The frame layout shared by the layers of the convolutional generator (models/rced.py:46-57, splice = 1):
@@ -474,10 +498,15 @@ class Generator(Net):
             return
         if self.g_type == "lstm":
             d16, d32 = Ls[-1].bwd("g", acts[-1], dy16, rows, want32=True)
+            Ls[-2].bwd_pre("g", d16, B, T)
             for i in range(len(Ls) - 2, 0, -1):
                 first = i == 1
-                d16, d32 = Ls[i].bwd("g", acts[i], d16, d32, B, T, lengths, prev_y16=acts[1] if first else None,
-                                     prev_act=ACT_LRELU if first else ACT_NONE, want32=not first)
+                dout32 = d32
+                d16, d32 = Ls[i].bwd_main("g", d16, B, T, lengths, prev_y16=acts[1] if first else None,
+                                          prev_act=ACT_LRELU if first else ACT_NONE, want32=not first)
+                if not first:
+                    Ls[i - 1].bwd_pre("g", d16, B, T)     # critical path first, then this layer's weight gradients
+                Ls[i].bwd_side("g", acts[i], dout32, B, T)
             Ls[0].bwd("g", acts[0], d16, rows, want_dx=False, dw_side=False)
             return
         d16, d32 = Ls[-1].bwd("g", acts[-1], dy16, rows, want32=True)
