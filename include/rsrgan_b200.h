@@ -235,6 +235,50 @@ int rsr_conv_mask_rows(rsr_handle* h, void* stream, void* buf16, long long frame
 /* out[k][co][ci] = w[W-1-k][ci][co]: taps of the transposed convolution (tf.gradients of conv2d wrt its input). */
 int rsr_conv_w_flip(rsr_handle* h, void* stream, const void* w16, int W, int Cin_p, int Cout_p, void* out16);
 
+/* batch_norm(renorm) / dropout behind a fully_connected ----------------------------------- */
+/* tf.contrib.layers.fully_connected(..., normalizer_fn=batch_norm, normalizer_params={is_training, scale=True,
+ * renorm=True}) followed by tf.nn.dropout -- models/dnn.py:56-62,79-94, models/discriminator_dnn.py:36-46,61-83,
+ * models/lstm.py:61-67,82-87.  With a normalizer the layer has no bias; contrib batch_norm defaults: decay 0.999,
+ * epsilon 1e-3, center=True, renorm_decay 0.99, no renorm clipping; reduction over every row (all axes but the last).
+ * The GEMM writes the fp32 pre-activation z [rows, N] (rsr_gemm, out32, no bias / activation); these entries do the
+ * rest as HBM streams.  N and every leading dimension are multiples of 4.
+ *
+ *   state fp32 [6, N]: moving_mean, moving_variance, renorm_mean, renorm_stddev, renorm_mean_weight,
+ *                      renorm_stddev_weight (the two weights are TF scalars, replicated per column)
+ *   coef  fp32 [8, N]: A, B (y = z A + B), mean, 1/stddev, r, d  (written by the forward entries) and the two column
+ *                      means the backward pass derives (rows 6, 7)
+ *   scratch fp32 [RSR_BN_SCRATCH_FLOATS(N)]: per-split partial moments; calls sharing one scratch must be stream-ordered
+ *
+ * rsr_bn_train_stats (is_training=True): mean/variance of z over rows (Welford per thread, fixed-order merges -- no
+ *   atomics), stddev = sqrt(var + eps); r = stddev / (renorm_stddev + (1 - renorm_stddev_weight) stddev),
+ *   d = (mean - (renorm_mean + (1 - renorm_mean_weight) mean)) / (same denominator), both constants for the gradient;
+ *   A = r gamma / stddev, B = d gamma + beta - mean A.  update_state != 0 also runs the UPDATE_OPS: renorm averages with
+ *   renorm_momentum, then moving_mean / moving_variance with `momentum` towards the de-biased renorm values
+ *   (models/dnn_trainer_single_gpu.py:101-104 runs them; models/gan_rnn_placeholder.py:169-175 does not).
+ * rsr_bn_eval_coef (is_training=False): A = gamma rsqrt(moving_variance + eps), B = beta - moving_mean A.
+ * rsr_affine_act_drop: out16 = dropout(act(z A + B)); A NULL = 1 (plain bias in B).  keep_prob >= 1: no dropout;
+ *   otherwise element (r, c) is kept iff the top 24 bits of splitmix64(key ^ (r N + c)) < floor(keep_prob 2^24), with
+ *   key = splitmix64(rng[0] + 0x9E3779B97F4A7C15 (rng[1] 65536 + salt)), and kept values are divided by keep_prob
+ *   (tf.nn.dropout).  rng = device {seed, tick}; rsr_rng_tick advances tick (once per update), salt names the layer call.
+ * rsr_bn_bwd: da16 = gradient wrt the layer OUTPUT.  g = da act'(y) [kept / keep_prob];  dbeta += sum g;
+ *   bn != 0: dgamma += r sum(g x_hat) + d sum(g),  dz = A (g - mean(g) - x_hat mean(g x_hat));   bn == 0 (bias + activation
+ *   + dropout only; `bias` replaces coef): dz = g.  The mask is regenerated from the same (rng, salt).
+ *   dgamma / dbeta / dz16 may be NULL. */
+#define RSR_BN_SCRATCH_FLOATS(N) (192LL * (N))
+int rsr_bn_train_stats(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,
+                       const float* gamma, const float* beta, float eps, float* state, float momentum,
+                       float renorm_momentum, int update_state, float* coef, float* scratch);
+int rsr_bn_eval_coef(rsr_handle* h, void* stream, int N, const float* gamma, const float* beta, float eps,
+                     const float* state, float* coef);
+int rsr_affine_act_drop(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,
+                        const float* A, const float* Bc, int act, float keep_prob,
+                        const unsigned long long* rng, unsigned salt, void* out16, int ld16);
+int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldda, const float* z, int ldz,
+               long long rows, int N, int act, float keep_prob, const unsigned long long* rng, unsigned salt,
+               int bn, float* coef, const float* bias, float* dgamma, float* dbeta, void* dz16, int lddz,
+               float* scratch);
+int rsr_rng_tick(rsr_handle* h, void* stream, unsigned long long* rng);
+
 /* misc ---------------------------------------------------------------------------------- */
 /* dst[c, r] = src[r, c] for r < rows, c < cols (16-bit elements; other elements of dst untouched):
  * keeps the K_x^T operand of rsr_lstmp_fused_fwd in step with the updated weights. */

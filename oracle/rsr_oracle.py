@@ -87,6 +87,141 @@ def linear_bwd(dy, cache):
     return dx, dW, db
 
 
+# --- contrib batch_norm(renorm=True, scale=True) and dropout behind a fully_connected ---------------------
+# models/dnn.py:56-62,79-94, models/discriminator_dnn.py:36-46,61-83, models/lstm.py:61-67,82-87.
+# TF-1.4 contrib batch_norm with renorm=True resolves to tf.layers.BatchNormalization(momentum=0.999,
+# epsilon=1e-3, center=True, scale=True, renorm=True, renorm_clipping=None, renorm_momentum=0.99), non-fused;
+# fully_connected drops its bias when a normalizer_fn is given.  (TF upstream behaviour, not visible in the
+# reference tree -- an assumption like the others listed in the module docstring.)
+
+BN_EPS, BN_DECAY, BN_RENORM_DECAY = 1e-3, 0.999, 0.99
+BN_STATE_KEYS = ("moving_mean", "moving_variance", "renorm_mean", "renorm_stddev", "renorm_mean_weight",
+                 "renorm_stddev_weight")
+
+
+def bn_init_state(n, dtype=np.float64):
+    """moving_mean 0, moving_variance 1; TF 1.4 zero-initialises all four renorm variables ("we initialize
+    renorm_stddev to 0, and maintain the (0-initialized) renorm_stddev_weight"), so the first batch sees r = 1, d = 0."""
+    return OrderedDict(moving_mean=np.zeros(n, dtype), moving_variance=np.ones(n, dtype),
+                       renorm_mean=np.zeros(n, dtype), renorm_stddev=np.zeros(n, dtype),
+                       renorm_mean_weight=np.zeros((), dtype), renorm_stddev_weight=np.zeros((), dtype))
+
+
+def bn_renorm_train_fwd(z, gamma, beta, st, update=True, eps=BN_EPS, decay=BN_DECAY, renorm_decay=BN_RENORM_DECAY):
+    """training=True branch of BatchNormalization.call + _renorm_correction_and_moments.  Moments over every
+    axis but the last (nn.moments: biased variance).  r, d use the PRE-update renorm averages and are constants
+    for the gradient (stop_gradient).  `st` is updated in place when update=True (the UPDATE_OPS)."""
+    z2 = z.reshape(-1, z.shape[-1])
+    mean = z2.mean(0)
+    var = ((z2 - mean) ** 2).mean(0)
+    stddev = np.sqrt(var + eps)
+    mixed_mean = st["renorm_mean"] + (1.0 - st["renorm_mean_weight"]) * mean
+    mixed_std = st["renorm_stddev"] + (1.0 - st["renorm_stddev_weight"]) * stddev
+    r = stddev / mixed_std
+    d = (mean - mixed_mean) / mixed_std
+    xhat = (z - mean) / stddev
+    y = (xhat * r + d) * gamma + beta
+    if update:
+        k = 1.0 - renorm_decay
+        # assign_moving_average(var, value, decay, zero_debias=False): var -= (var - value) * (1 - decay)
+        st["renorm_mean"] = st["renorm_mean"] - (st["renorm_mean"] - mean) * k
+        st["renorm_mean_weight"] = st["renorm_mean_weight"] - (st["renorm_mean_weight"] - 1.0) * k
+        st["renorm_stddev"] = st["renorm_stddev"] - (st["renorm_stddev"] - stddev) * k
+        st["renorm_stddev_weight"] = st["renorm_stddev_weight"] - (st["renorm_stddev_weight"] - 1.0) * k
+        new_mean = st["renorm_mean"] / st["renorm_mean_weight"]
+        new_std = st["renorm_stddev"] / st["renorm_stddev_weight"]
+        new_var = new_std ** 2 - eps
+        st["moving_mean"] = st["moving_mean"] - (st["moving_mean"] - new_mean) * (1.0 - decay)
+        st["moving_variance"] = st["moving_variance"] - (st["moving_variance"] - new_var) * (1.0 - decay)
+    return y, (xhat, r, d, gamma, stddev)
+
+
+def bn_renorm_train_bwd(dy, cache):
+    xhat, r, d, gamma, stddev = cache
+    dy2, xh2 = dy.reshape(-1, dy.shape[-1]), xhat.reshape(-1, xhat.shape[-1])
+    s1, s2 = dy2.sum(0), (dy2 * xh2).sum(0)
+    n = dy2.shape[0]
+    dgamma = r * s2 + d * s1
+    dbeta = s1
+    dz = (gamma * r / stddev) * (dy - s1 / n - xhat * (s2 / n))
+    return dz, dgamma, dbeta
+
+
+def bn_eval_fwd(z, gamma, beta, st, eps=BN_EPS):
+    """training=False: nn.batch_normalization(z, moving_mean, moving_variance, beta, gamma, eps)."""
+    return (z - st["moving_mean"]) / np.sqrt(st["moving_variance"] + eps) * gamma + beta
+
+
+_U64 = np.uint64
+
+
+def _splitmix64(x):
+    x = np.asarray(x, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = x ^ (x >> _U64(30))
+        x = x * _U64(0xbf58476d1ce4e5b9)
+        x = x ^ (x >> _U64(27))
+        x = x * _U64(0x94d049bb133111eb)
+        x = x ^ (x >> _U64(31))
+    return x
+
+
+def dropout_mask(seed, tick, salt, rows, n, keep_prob):
+    """The counter-based mask of rsr_affine_act_drop (include/rsrgan_b200.h): tf.nn.dropout keeps an element with
+    probability keep_prob and divides kept values by keep_prob (models/dnn.py:28-30); TF's own random stream
+    cannot be reproduced, so the mask generator is part of the C ABI and restated here bit-exactly."""
+    with np.errstate(over="ignore"):
+        key = _splitmix64(_U64(seed) + _U64(0x9E3779B97F4A7C15) * (_U64(tick) * _U64(65536) + _U64(salt)))
+        idx = np.arange(rows * n, dtype=np.uint64).reshape(rows, n)
+        bits = (_splitmix64(key ^ idx) >> _U64(40)).astype(np.uint32)
+    return bits < np.uint32(int(keep_prob * 16777216.0))
+
+
+def fc_block_fwd(p, name, h, act, opts, salt):
+    """One fully_connected call site with its optional normalizer and dropout.  opts (all optional):
+    bn_state {name/BatchNorm/<key>}, train (True), update (False), keep_prob (1.0), rng (seed, tick)."""
+    opts = opts or {}
+    train = opts.get("train", True)
+    W = p[name + "/weights"]
+    bn = (name + "/BatchNorm/gamma") in p
+    bc = None
+    if bn:
+        z = h @ W
+        gamma, beta = p[name + "/BatchNorm/gamma"], p[name + "/BatchNorm/beta"]
+        st = OrderedDict((k, opts["bn_state"][name + "/BatchNorm/" + k]) for k in BN_STATE_KEYS)
+        if train:
+            y, bc = bn_renorm_train_fwd(z, gamma, beta, st, update=opts.get("update", False))
+            for k in BN_STATE_KEYS:
+                opts["bn_state"][name + "/BatchNorm/" + k] = st[k]
+        else:
+            y = bn_eval_fwd(z, gamma, beta, st)
+    else:
+        y = h @ W + p[name + "/biases"]
+    a = act_fwd(y, act)
+    keep = opts.get("keep_prob", 1.0) if train else 1.0
+    mask = None
+    if keep < 1.0:
+        seed, tick = opts["rng"]
+        lead = a.shape[:-1]
+        mask = dropout_mask(seed, tick, salt, int(np.prod(lead)), a.shape[-1], keep).reshape(a.shape)
+        a = np.where(mask, a / keep, 0.0)
+    return a, (h, W, y, act, bc, mask, keep)
+
+
+def fc_block_bwd(da, cache, name, g):
+    h, W, y, act, bc, mask, keep = cache
+    if mask is not None:
+        da = np.where(mask, da / keep, 0.0)
+    dy = act_bwd(y, da, act)
+    if bc is not None:
+        dz, g[name + "/BatchNorm/gamma"], g[name + "/BatchNorm/beta"] = bn_renorm_train_bwd(dy, bc)
+    else:
+        dz = dy
+        g[name + "/biases"] = dz.reshape(-1, dz.shape[-1]).sum(0)
+    g[name + "/weights"] = h.reshape(-1, h.shape[-1]).T @ dz.reshape(-1, dz.shape[-1])
+    return dz @ W.T
+
+
 def conv1d_same_fwd(x, W, b, act=ACT_RELU):
     """tf.contrib.layers.conv2d(inputs, C_out, [splice, w], padding=SAME, relu) with splice = 1
     (models/rced.py:90-101): inputs NHWC (N, 1, L, C_in) -> here (N, L, C_in); W is the TF filter
@@ -257,14 +392,34 @@ def init_g_res_lstm_l(rng, in_dim=257, out_dim=40, cell=760, layers=4,
     return p
 
 
-def init_g_dnn(rng, in_dim=257, out_dim=40, units=1024, hidden=3, dtype=np.float64):
-    """models/dnn.py:34-35,79-110: in -> units x (1 + hidden) ReLU -> out, xavier weights, zero biases."""
+def _bn_vars(p, name, n, dtype):
+    """beta zeros, gamma ones (contrib batch_norm defaults with scale=True); replaces the layer's bias."""
+    p[name + "/BatchNorm/beta"] = np.zeros(n, dtype)
+    p[name + "/BatchNorm/gamma"] = np.ones(n, dtype)
+
+
+def init_bn_state(p, dtype=np.float64):
+    """Non-trainable batch_norm variables of every normalised layer in p, keyed by their TF names."""
+    st = OrderedDict()
+    for k in p:
+        if k.endswith("/BatchNorm/gamma"):
+            for kk, v in bn_init_state(p[k].shape[0], dtype).items():
+                st[k[:-len("gamma")] + kk] = v
+    return st
+
+
+def init_g_dnn(rng, in_dim=257, out_dim=40, units=1024, hidden=3, dtype=np.float64, batch_norm=False):
+    """models/dnn.py:34-35,79-110: in -> units x (1 + hidden) ReLU -> out, xavier weights, zero biases
+    (hidden layers: BatchNorm beta / gamma instead of biases when batch_norm, :56-62)."""
     p = OrderedDict()
     dims = [in_dim] + [units] * (hidden + 1) + [out_dim]
     for l in range(hidden + 2):
         name = "g_model/fully_connected" + ("" if l == 0 else "_%d" % l)
         p[name + "/weights"] = xavier(rng, (dims[l], dims[l + 1]), dtype)
-        p[name + "/biases"] = np.zeros(dims[l + 1], dtype)
+        if batch_norm and l < hidden + 1:
+            _bn_vars(p, name, dims[l + 1], dtype)
+        else:
+            p[name + "/biases"] = np.zeros(dims[l + 1], dtype)
     return p
 
 
@@ -298,7 +453,7 @@ def init_d_lstm(rng, in_dim=40, cell=256, proj=40, layers=2, dtype=np.float64):
     return p
 
 
-def init_d_dnn(rng, in_dim=40, units=1024, hidden=3, dtype=np.float64):
+def init_d_dnn(rng, in_dim=40, units=1024, hidden=3, dtype=np.float64, batch_norm=False):
     """models/discriminator_dnn.py:23-27,61-93: truncN(0, sqrt(2/units)) hidden
     weights (truncation at 2 sigma), xavier output layer, zero biases."""
     p = OrderedDict()
@@ -316,7 +471,10 @@ def init_d_dnn(rng, in_dim=40, units=1024, hidden=3, dtype=np.float64):
     for l in range(hidden + 1):
         name = "d_model/fully_connected" + ("" if l == 0 else "_%d" % l)
         p[name + "/weights"] = truncn((dims[l], dims[l + 1]))
-        p[name + "/biases"] = np.zeros(dims[l + 1], dtype)
+        if batch_norm:
+            _bn_vars(p, name, dims[l + 1], dtype)
+        else:
+            p[name + "/biases"] = np.zeros(dims[l + 1], dtype)
     name = "d_model/fully_connected_%d" % (hidden + 1)
     p[name + "/weights"] = xavier(rng, (units, 1), dtype)
     p[name + "/biases"] = np.zeros(1, dtype)
@@ -435,19 +593,19 @@ def d_lstm_bwd(p, dy, caches):
 
 
 def _dnn_names(p):
-    names = sorted({k.rsplit("/", 1)[0] for k in p if k.startswith("d_model/fully_connected")},
+    names = sorted({k.rsplit("/", 1)[0] for k in p if k.startswith("d_model/fully_connected") and k.endswith("/weights")},
                    key=lambda s: int(s.split("_")[-1]) if s[-1].isdigit() else 0)
     return names
 
 
-def d_dnn_fwd(p, x, lengths=None, noise=None):
+def d_dnn_fwd(p, x, lengths=None, noise=None, opts=None, salt0=256):
     """models/discriminator_dnn.py:61-93 applied per frame (fully_connected
-    broadcasts over leading dims; SURVEY App. C-15 adapter: lengths ignored)."""
+    broadcasts over leading dims; SURVEY App. C-15 adapter: lengths ignored).  opts: see fc_block_fwd."""
     caches = []
     h = x
     names = _dnn_names(p)
-    for n in names[:-1]:
-        h, c = linear_fwd(h, p[n + "/weights"], p[n + "/biases"], ACT_RELU)
+    for i, n in enumerate(names[:-1]):
+        h, c = fc_block_fwd(p, n, h, ACT_RELU, opts, salt0 + i)
         caches.append(c)
     y, c = linear_fwd(h, p[names[-1] + "/weights"], p[names[-1] + "/biases"], ACT_CLIP)
     caches.append(c)
@@ -457,27 +615,26 @@ def d_dnn_fwd(p, x, lengths=None, noise=None):
 def d_dnn_bwd(p, dy, caches):
     g = OrderedDict()
     names = _dnn_names(p)
-    dh = dy
-    for n, c in zip(reversed(names), reversed(caches)):
-        dh, dW, db = linear_bwd(dh, c)
-        g[n + "/weights"] = dW
-        g[n + "/biases"] = db
+    dh, dW, db = linear_bwd(dy, caches[-1])
+    g[names[-1] + "/weights"], g[names[-1] + "/biases"] = dW, db
+    for n, c in zip(reversed(names[:-1]), reversed(caches[:-1])):
+        dh = fc_block_bwd(dh, c, n, g)
     return dh, g
 
 
 def _fc_names(p, scope):
-    names = sorted({k.rsplit("/", 1)[0] for k in p if k.startswith(scope + "/fully_connected")},
+    names = sorted({k.rsplit("/", 1)[0] for k in p if k.startswith(scope + "/fully_connected") and k.endswith("/weights")},
                    key=lambda s: int(s.split("_")[-1]) if s[-1].isdigit() else 0)
     return names
 
 
-def g_dnn_fwd(p, x, lengths=None):
-    """models/dnn.py:79-110 applied per frame (no sequence dependence; lengths unused)."""
+def g_dnn_fwd(p, x, lengths=None, opts=None, salt0=0):
+    """models/dnn.py:79-110 applied per frame (no sequence dependence; lengths unused).  opts: see fc_block_fwd."""
     caches = []
     h = x
     names = _fc_names(p, "g_model")
-    for n in names[:-1]:
-        h, c = linear_fwd(h, p[n + "/weights"], p[n + "/biases"], ACT_RELU)
+    for i, n in enumerate(names[:-1]):
+        h, c = fc_block_fwd(p, n, h, ACT_RELU, opts, salt0 + i)
         caches.append(c)
     y, c = linear_fwd(h, p[names[-1] + "/weights"], p[names[-1] + "/biases"], ACT_NONE)
     caches.append(c)
@@ -486,11 +643,11 @@ def g_dnn_fwd(p, x, lengths=None):
 
 def g_dnn_bwd(p, dy, caches):
     g = OrderedDict()
-    dh = dy
-    for n, c in zip(reversed(_fc_names(p, "g_model")), reversed(caches)):
-        dh, dW, db = linear_bwd(dh, c)
-        g[n + "/weights"] = dW
-        g[n + "/biases"] = db
+    names = _fc_names(p, "g_model")
+    dh, dW, db = linear_bwd(dy, caches[-1])
+    g[names[-1] + "/weights"], g[names[-1] + "/biases"] = dW, db
+    for n, c in zip(reversed(names[:-1]), reversed(caches[:-1])):
+        dh = fc_block_bwd(dh, c, n, g)
     return dh, g
 
 
@@ -662,14 +819,19 @@ class GanState(object):
 
 
 def tower_losses_and_grads(st, x, y, lengths, which, noise_rl=None, noise_fk=None,
-                           mse_lambda=10.0, d_real=1.0, d_fake=0.0, l2_scale=0.0):
+                           mse_lambda=10.0, d_real=1.0, d_fake=0.0, l2_scale=0.0, g_opts=None, d_opts=None):
     """One tower of build_model_single_gpu (gan_rnn_placeholder.py:191-298) plus
     compute_gradients wrt d_vars (which='d') or g_vars (which='g')."""
     gf, gb = GENERATORS[st.g_type]
     df, db_ = DISCRIMINATORS[st.d_type]
-    g_out, gc = gf(st.g, x, lengths)
-    lr_, crl = df(st.d, y, lengths, noise_rl)
-    lf_, cfk = df(st.d, g_out, lengths, noise_fk)
+    # g_opts / d_opts: batch_norm state, dropout stream (fc_block_fwd); salts: G layers 0.., D(labels) 256.., D(G(x)) 512..
+    g_out, gc = gf(st.g, x, lengths) if g_opts is None else gf(st.g, x, lengths, opts=g_opts, salt0=0)
+    if d_opts is None:
+        lr_, crl = df(st.d, y, lengths, noise_rl)
+        lf_, cfk = df(st.d, g_out, lengths, noise_fk)
+    else:
+        lr_, crl = df(st.d, y, lengths, noise_rl, opts=d_opts, salt0=256)
+        lf_, cfk = df(st.d, g_out, lengths, noise_fk, opts=d_opts, salt0=512)
     losses = lsgan_mse_losses(lr_, lf_, g_out, y, d_real, d_fake, mse_lambda, y.shape[-1])
     if l2_scale > 0.0:
         losses["g_l2_loss"] = l2_loss_g(st.g, l2_scale)
@@ -719,12 +881,12 @@ def g_step(st, towers, lr_g, max_norm=15.0, ema_decay=0.9999, **kw):
 # --------------------------------------------------------------------------
 
 
-def mse_losses_and_grads(g_params, g_type, x, y, l2_scale=0.0):
+def mse_losses_and_grads(g_params, g_type, x, y, l2_scale=0.0, g_opts=None):
     """g_mse = 0.5 * output_dim * mean((G(x)-y)^2) (:109-110); g_l2 = sum over WEIGHTS (contrib
     l2_regularizer is attached to weights only, dnn.py:64-67,85-86) of l2_scale * 0.5 ||W||^2 (:111-115);
     gradients of g_mse + g_l2 wrt every g_ variable (:102-104 minimize, no clipping)."""
     gf, gb = GENERATORS[g_type]
-    g_out, gc = gf(g_params, x, None)
+    g_out, gc = gf(g_params, x, None) if g_opts is None else gf(g_params, x, None, opts=g_opts, salt0=0)
     out_dim = y.shape[-1]
     losses = dict(g_mse_loss=0.5 * out_dim * float(np.mean((g_out - y) ** 2)), g_l2_loss=0.0)
     _, grads = gb(g_params, out_dim * (g_out - y) / g_out.size, gc)
@@ -746,8 +908,9 @@ class MseState(object):
         self.adam_m, self.adam_v, self.adam_t = z(), z(), 0
 
 
-def mse_step(st, x, y, lr, l2_scale=0.0):
-    """One DNNTrainer update: Adam(lr) on g_mse + g_l2, no clipping, no EMA."""
-    losses, grads, g_out = mse_losses_and_grads(st.g, st.g_type, x, y, l2_scale)
+def mse_step(st, x, y, lr, l2_scale=0.0, g_opts=None):
+    """One DNNTrainer update: Adam(lr) on g_mse + g_l2, no clipping, no EMA.  With batch_norm the UPDATE_OPS run
+    with the step (dnn_trainer_single_gpu.py:101-104): pass g_opts with update=True."""
+    losses, grads, g_out = mse_losses_and_grads(st.g, st.g_type, x, y, l2_scale, g_opts)
     st.g, st.adam_m, st.adam_v, st.adam_t = adam_update_tf(st.g, grads, st.adam_m, st.adam_v, st.adam_t, lr)
     return losses, grads

@@ -77,27 +77,68 @@ def d_lstm(p, x, lengths, noise=None):
     return h @ p["d_model/fully_connected/weights"] + p["d_model/fully_connected/biases"]
 
 
-def d_dnn(p, x, lengths=None, noise=None):
-    names = sorted({k.rsplit("/", 1)[0] for k in p if k.startswith("d_model/fully_connected")},
+def bn_renorm_train(z, gamma, beta, st, eps=1e-3):
+    """tf.layers.BatchNormalization(renorm=True).call, training branch, written independently of the numpy oracle:
+    torch moments + nn.batch_normalization form x * inv + (offset - mean * inv); r and d detached (stop_gradient).
+    `st` holds the PRE-update renorm variables (torch tensors or floats); the state update is not differentiated."""
+    red = tuple(range(z.dim() - 1))
+    mean = z.mean(red)
+    var = z.var(red, unbiased=False)
+    stddev = torch.sqrt(var + eps)
+    denom = st["renorm_stddev"] + (1.0 - st["renorm_stddev_weight"]) * stddev
+    r = (stddev / denom).detach()
+    d = ((mean - (st["renorm_mean"] + (1.0 - st["renorm_mean_weight"]) * mean)) / denom).detach()
+    scale, offset = r * gamma, d * gamma + beta
+    inv = torch.rsqrt(var + eps) * scale
+    return z * inv + (offset - mean * inv)
+
+
+def _fc_block(p, n, h, act, opts, salt):
+    from . import rsr_oracle as O
+    opts = opts or {}
+    train = opts.get("train", True)
+    if (n + "/BatchNorm/gamma") in p:
+        z = h @ p[n + "/weights"]
+        st = {k: torch.as_tensor(opts["bn_state"][n + "/BatchNorm/" + k], dtype=z.dtype) for k in O.BN_STATE_KEYS}
+        if train:
+            y = bn_renorm_train(z, p[n + "/BatchNorm/gamma"], p[n + "/BatchNorm/beta"], st)
+        else:
+            y = torch.nn.functional.batch_norm(z.reshape(-1, z.shape[-1]), st["moving_mean"], st["moving_variance"],
+                                               p[n + "/BatchNorm/gamma"], p[n + "/BatchNorm/beta"], False, 0.0,
+                                               1e-3).reshape(z.shape)
+    else:
+        y = h @ p[n + "/weights"] + p[n + "/biases"]
+    a = act(y)
+    keep = opts.get("keep_prob", 1.0) if train else 1.0
+    if keep < 1.0:
+        seed, tick = opts["rng"]
+        rows = int(a.numel() // a.shape[-1])
+        m = torch.as_tensor(O.dropout_mask(seed, tick, salt, rows, a.shape[-1], keep).reshape(tuple(a.shape)))
+        a = torch.where(m, a / keep, torch.zeros_like(a))
+    return a
+
+
+def d_dnn(p, x, lengths=None, noise=None, opts=None, salt0=256):
+    names = sorted({k.rsplit("/", 1)[0] for k in p if k.startswith("d_model/fully_connected") and k.endswith("/weights")},
                    key=lambda s: int(s.split("_")[-1]) if s[-1].isdigit() else 0)
     h = x
-    for n in names[:-1]:
-        h = torch.relu(h @ p[n + "/weights"] + p[n + "/biases"])
+    for i, n in enumerate(names[:-1]):
+        h = _fc_block(p, n, h, torch.relu, opts, salt0 + i)
     y = h @ p[names[-1] + "/weights"] + p[names[-1] + "/biases"]
     return torch.clamp(y, -0.5, 1.5)
 
 
 def _fc_names(p, scope):
-    return sorted({k.rsplit("/", 1)[0] for k in p if k.startswith(scope + "/fully_connected")},
+    return sorted({k.rsplit("/", 1)[0] for k in p if k.startswith(scope + "/fully_connected") and k.endswith("/weights")},
                   key=lambda s: int(s.split("_")[-1]) if s[-1].isdigit() else 0)
 
 
-def g_dnn(p, x, lengths=None):
+def g_dnn(p, x, lengths=None, opts=None, salt0=0):
     """models/dnn.py:79-110."""
     names = _fc_names(p, "g_model")
     h = x
-    for n in names[:-1]:
-        h = torch.relu(h @ p[n + "/weights"] + p[n + "/biases"])
+    for i, n in enumerate(names[:-1]):
+        h = _fc_block(p, n, h, torch.relu, opts, salt0 + i)
     return h @ p[names[-1] + "/weights"] + p[names[-1] + "/biases"]
 
 
@@ -122,11 +163,15 @@ DIS = {"lstm": d_lstm, "dnn": d_dnn}
 
 
 def losses(gp, dp, g_type, d_type, x, y, lengths, noise_rl=None, noise_fk=None,
-           mse_lambda=10.0, d_real=1.0, d_fake=0.0):
+           mse_lambda=10.0, d_real=1.0, d_fake=0.0, g_opts=None, d_opts=None):
     """models/gan_rnn_placeholder.py:196-260."""
-    g = GEN[g_type](gp, x, lengths)
-    rl = DIS[d_type](dp, y, lengths, noise_rl)
-    fk = DIS[d_type](dp, g, lengths, noise_fk)
+    g = GEN[g_type](gp, x, lengths) if g_opts is None else GEN[g_type](gp, x, lengths, opts=g_opts, salt0=0)
+    if d_opts is None:
+        rl = DIS[d_type](dp, y, lengths, noise_rl)
+        fk = DIS[d_type](dp, g, lengths, noise_fk)
+    else:
+        rl = DIS[d_type](dp, y, lengths, noise_rl, opts=d_opts, salt0=256)
+        fk = DIS[d_type](dp, g, lengths, noise_fk, opts=d_opts, salt0=512)
     d_rl = ((rl - d_real) ** 2).mean()
     d_fk = ((fk - d_fake) ** 2).mean()
     g_adv = ((fk - d_real) ** 2).mean()

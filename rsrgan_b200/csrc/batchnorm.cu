@@ -1,0 +1,384 @@
+// tf.contrib.layers.batch_norm(is_training, scale=True, renorm=True) between a bias-free
+// fully_connected and its activation, and tf.nn.dropout behind it -- the optional normalizer /
+// dropout of models/dnn.py:56-62,79-110, models/discriminator_dnn.py:36-46,61-90 and
+// models/lstm.py:61-67,82-87.  All kernels are HBM streams over the fp32 pre-activation z
+// [rows, N] that the tensor-core GEMM wrote:
+//   statistics      one read of z  (4 B / element), per-thread Welford, fixed-order Chan merges
+//   normalise       one read of z + one 16-bit write (6 B / element), activation and dropout fused
+//   backward        two reads of z and of the incoming 16-bit gradient + one 16-bit write
+//                   (2 x 6 + 2 B / element): column sums first, then dz
+// Reductions never use atomics: every column's partials are merged in one fixed order, so
+// data-parallel replicas that see the same rows produce bit-identical statistics.
+#include "common.cuh"
+#include "handle.h"
+
+using namespace rsr;
+
+namespace {
+
+constexpr int BN_COLS = 128;     // columns per block (32 threads x float4)
+constexpr int BN_LANES = 8;      // row lanes per block
+constexpr int BN_MAX_SPLITS = 64;
+
+__host__ __device__ inline int bn_splits(long long rows) {
+    long long s = rows / 64;
+    if (s < 1) s = 1;
+    if (s > BN_MAX_SPLITS) s = BN_MAX_SPLITS;
+    return (int)s;
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+// counter-based dropout mask: the backward pass regenerates it from (seed, tick, salt, element index)
+__device__ __forceinline__ uint64_t drop_key(const unsigned long long* rng, unsigned salt) {
+    return splitmix64(rng[0] + 0x9E3779B97F4A7C15ull * (rng[1] * 65536ull + salt));
+}
+__device__ __forceinline__ bool drop_keep(uint64_t key, uint64_t idx, uint32_t thr24) {
+    return (uint32_t)(splitmix64(key ^ idx) >> 40) < thr24;
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == RSR_ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == RSR_ACT_LRELU) return fmaxf(v, 0.3f * v);
+    return v;
+}
+__device__ __forceinline__ float act_slope(float y, int act) {
+    if (act == RSR_ACT_RELU) return y > 0.0f ? 1.0f : 0.0f;
+    if (act == RSR_ACT_LRELU) return y > 0.0f ? 1.0f : 0.3f;
+    return 1.0f;
+}
+
+struct BnBwdIn {
+    const uint16_t* da; int ldda;   // gradient wrt the layer output (after activation and dropout)
+    const float* A; const float* Bc; const float* mean; const float* inv_std;
+    int act; uint32_t thr24; float inv_keep; const unsigned long long* rng; unsigned salt; int bf;
+};
+
+// gradient wrt the normalised value y = z A + B of 4 consecutive columns, and x_hat
+__device__ __forceinline__ void bwd_elem4(const BnBwdIn& p, const float4 z, long long r, int c, int N, uint64_t key,
+                                          float g[4], float xh[4]) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p.da + r * p.ldda + c);
+    const uint16_t hv[4] = {(uint16_t)(raw.x & 0xffff), (uint16_t)(raw.x >> 16), (uint16_t)(raw.y & 0xffff),
+                            (uint16_t)(raw.y >> 16)};
+    const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float y = fmaf(zz[k], p.A ? p.A[c + k] : 1.0f, p.Bc[c + k]);
+        float gv = h2f(hv[k], p.bf) * act_slope(y, p.act);
+        if (p.thr24 < (1u << 24)) gv = drop_keep(key, (uint64_t)r * (uint64_t)N + (uint64_t)(c + k), p.thr24) ? gv * p.inv_keep : 0.0f;
+        g[k] = gv;
+        xh[k] = p.mean ? (zz[k] - p.mean[c + k]) * p.inv_std[c + k] : 0.0f;
+    }
+}
+
+// MODE 0: per-split (count, mean, M2) of z.   MODE 1: per-split (sum g, sum g x_hat).
+// grid (ceil(N / 128), splits), block (32, 8); partial layout [split][3 | 2][N]
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict__ z, int ldz, long long rows, int N,
+                                                         BnBwdIn p, float* __restrict__ partial) {
+    __shared__ float sm[BN_LANES][3][BN_COLS];
+    const int c = blockIdx.x * BN_COLS + threadIdx.x * 4;
+    const int splits = gridDim.y;
+    const long long chunk = (rows + splits - 1) / splits;
+    const long long r0 = (long long)blockIdx.y * chunk;
+    const long long r1 = r0 + chunk < rows ? r0 + chunk : rows;
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+    float n = 0.f;
+    uint64_t key = 0;
+    if (MODE == 1 && p.thr24 < (1u << 24)) key = drop_key(p.rng, p.salt);
+    if (c < N) {
+        for (long long r = r0 + threadIdx.y; r < r1; r += BN_LANES) {
+            const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + c);
+            if (MODE == 0) {
+                n += 1.0f;
+                const float inv_n = 1.0f / n;
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {          // Welford: a0 = running mean, a1 = M2
+                    const float d = vv[k] - a0[k];
+                    a0[k] += d * inv_n;
+                    a1[k] = fmaf(d, vv[k] - a0[k], a1[k]);
+                }
+            } else {
+                float g[4], xh[4];
+                bwd_elem4(p, v, r, c, N, key, g, xh);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { a0[k] += g[k]; a1[k] = fmaf(g[k], xh[k], a1[k]); }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        sm[threadIdx.y][0][threadIdx.x * 4 + k] = a0[k];
+        sm[threadIdx.y][1][threadIdx.x * 4 + k] = a1[k];
+    }
+    if (MODE == 0) sm[threadIdx.y][2][threadIdx.x * 4] = n;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < N) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int cc = threadIdx.x * 4 + k;
+            if (MODE == 0) {
+                float na = 0.f, ma = 0.f, qa = 0.f;
+                for (int l = 0; l < BN_LANES; ++l) {       // Chan merge, fixed order
+                    const float nb = sm[l][2][threadIdx.x * 4];
+                    if (nb == 0.f) continue;
+                    const float mb = sm[l][0][cc], qb = sm[l][1][cc];
+                    const float nab = na + nb, d = mb - ma;
+                    ma += d * (nb / nab);
+                    qa += qb + d * d * (na * nb / nab);
+                    na = nab;
+                }
+                partial[((long long)blockIdx.y * 3 + 0) * N + c + k] = na;
+                partial[((long long)blockIdx.y * 3 + 1) * N + c + k] = ma;
+                partial[((long long)blockIdx.y * 3 + 2) * N + c + k] = qa;
+            } else {
+                float s1 = 0.f, s2 = 0.f;
+                for (int l = 0; l < BN_LANES; ++l) { s1 += sm[l][0][cc]; s2 += sm[l][1][cc]; }
+                partial[((long long)blockIdx.y * 2 + 0) * N + c + k] = s1;
+                partial[((long long)blockIdx.y * 2 + 1) * N + c + k] = s2;
+            }
+        }
+    }
+}
+
+// state rows: 0 moving_mean 1 moving_variance 2 renorm_mean 3 renorm_stddev 4 renorm_mean_weight 5 renorm_stddev_weight
+// coef  rows: 0 A = scale / stddev  1 B = offset - mean A  2 mean  3 1 / stddev  4 r  5 d  6 mean(g)  7 mean(g x_hat)
+__global__ void bn_finish_train_kernel(const float* __restrict__ partial, int splits, long long rows, int N,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                       float* __restrict__ state, float momentum, float renorm_momentum,
+                                       int update_state, float* __restrict__ coef) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    float na = 0.f, ma = 0.f, qa = 0.f;
+    for (int s = 0; s < splits; ++s) {
+        const float nb = partial[((long long)s * 3 + 0) * N + c];
+        if (nb == 0.f) continue;
+        const float mb = partial[((long long)s * 3 + 1) * N + c], qb = partial[((long long)s * 3 + 2) * N + c];
+        const float nab = na + nb, d = mb - ma;
+        ma += d * (nb / nab);
+        qa += qb + d * d * (na * nb / nab);
+        na = nab;
+    }
+    const float mean = ma, var = qa / (float)rows;
+    const float stddev = sqrtf(var + eps);
+    float* mm = state + 0 * (long long)N; float* mv = state + 1 * (long long)N;
+    float* rm = state + 2 * (long long)N; float* rs = state + 3 * (long long)N;
+    float* rmw = state + 4 * (long long)N; float* rsw = state + 5 * (long long)N;
+    // corrections from the PRE-update renorm averages, "as if they were initialised with this batch's moments"
+    const float mixed_mean = rm[c] + (1.0f - rmw[c]) * mean;
+    const float mixed_std = rs[c] + (1.0f - rsw[c]) * stddev;
+    const float r = stddev / mixed_std;
+    const float d = (mean - mixed_mean) / mixed_std;
+    const float scale = r * gamma[c], offset = fmaf(d, gamma[c], beta[c]);
+    const float A = scale / stddev;
+    coef[0 * (long long)N + c] = A;
+    coef[1 * (long long)N + c] = offset - mean * A;
+    coef[2 * (long long)N + c] = mean;
+    coef[3 * (long long)N + c] = 1.0f / stddev;
+    coef[4 * (long long)N + c] = r;
+    coef[5 * (long long)N + c] = d;
+    if (update_state) {
+        const float k = 1.0f - renorm_momentum;
+        const float rm_n = rm[c] - (rm[c] - mean) * k, rmw_n = rmw[c] - (rmw[c] - 1.0f) * k;
+        const float rs_n = rs[c] - (rs[c] - stddev) * k, rsw_n = rsw[c] - (rsw[c] - 1.0f) * k;
+        const float new_mean = rm_n / rmw_n, new_std = rs_n / rsw_n;
+        const float new_var = new_std * new_std - eps;
+        rm[c] = rm_n; rmw[c] = rmw_n; rs[c] = rs_n; rsw[c] = rsw_n;
+        mm[c] -= (mm[c] - new_mean) * (1.0f - momentum);
+        mv[c] -= (mv[c] - new_var) * (1.0f - momentum);
+    }
+}
+
+__global__ void bn_eval_coef_kernel(int N, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                    const float* __restrict__ state, float* __restrict__ coef) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    const float inv = rsqrtf(state[1 * (long long)N + c] + eps);
+    const float A = gamma[c] * inv;
+    coef[0 * (long long)N + c] = A;
+    coef[1 * (long long)N + c] = beta[c] - state[c] * A;
+    coef[2 * (long long)N + c] = state[c];
+    coef[3 * (long long)N + c] = inv;
+    coef[4 * (long long)N + c] = 1.0f;
+    coef[5 * (long long)N + c] = 0.0f;
+}
+
+__global__ void __launch_bounds__(256) affine_act_drop_kernel(const float* __restrict__ z, int ldz, long long rows,
+                                                              int N, const float* __restrict__ A,
+                                                              const float* __restrict__ Bc, int act, uint32_t thr24,
+                                                              float inv_keep, const unsigned long long* __restrict__ rng,
+                                                              unsigned salt, uint16_t* __restrict__ out, int ldo, int bf) {
+    const int n4 = N >> 2;
+    const long long total = rows * n4;
+    uint64_t key = 0;
+    if (thr24 < (1u << 24)) key = drop_key(rng, salt);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / n4;
+        const int c = (int)(i - r * n4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + c);
+        const float4 a = A ? *reinterpret_cast<const float4*>(A + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 b = *reinterpret_cast<const float4*>(Bc + c);
+        float y[4] = {fmaf(v.x, a.x, b.x), fmaf(v.y, a.y, b.y), fmaf(v.z, a.z, b.z), fmaf(v.w, a.w, b.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            y[k] = act_apply(y[k], act);
+            if (thr24 < (1u << 24))
+                y[k] = drop_keep(key, (uint64_t)r * (uint64_t)N + (uint64_t)(c + k), thr24) ? y[k] * inv_keep : 0.0f;
+        }
+        uint2 o;
+        o.x = pack2(y[0], y[1], bf);
+        o.y = pack2(y[2], y[3], bf);
+        *reinterpret_cast<uint2*>(out + r * ldo + c) = o;
+    }
+}
+
+// column totals of the backward partials; parameter gradients; means for the dz kernel
+__global__ void bn_bwd_finish_kernel(const float* __restrict__ partial, int splits, long long rows, int N, int bn,
+                                     float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    float s1 = 0.f, s2 = 0.f;
+    for (int s = 0; s < splits; ++s) {
+        s1 += partial[((long long)s * 2 + 0) * N + c];
+        s2 += partial[((long long)s * 2 + 1) * N + c];
+    }
+    if (bn) {
+        // y = (x_hat r + d) gamma + beta with r, d under stop_gradient
+        // atomics: the D(labels) and D(G(x)) backward passes of one update run on two streams (two addends: order-free)
+        if (dgamma) atomicAdd(dgamma + c, coef[4 * (long long)N + c] * s2 + coef[5 * (long long)N + c] * s1);
+        coef[6 * (long long)N + c] = s1 / (float)rows;
+        coef[7 * (long long)N + c] = s2 / (float)rows;
+    }
+    if (dbeta) atomicAdd(dbeta + c, s1);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ z, int ldz, long long rows, int N,
+                                                           BnBwdIn p, int bn, const float* __restrict__ m1,
+                                                           const float* __restrict__ m2, uint16_t* __restrict__ dz,
+                                                           int lddz) {
+    const int n4 = N >> 2;
+    const long long total = rows * n4;
+    uint64_t key = 0;
+    if (p.thr24 < (1u << 24)) key = drop_key(p.rng, p.salt);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / n4;
+        const int c = (int)(i - r * n4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + c);
+        float g[4], xh[4];
+        bwd_elem4(p, v, r, c, N, key, g, xh);
+        if (bn) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) g[k] = p.A[c + k] * (g[k] - m1[c + k] - xh[k] * m2[c + k]);
+        }
+        uint2 o;
+        o.x = pack2(g[0], g[1], p.bf);
+        o.y = pack2(g[2], g[3], p.bf);
+        *reinterpret_cast<uint2*>(dz + r * lddz + c) = o;
+    }
+}
+
+__global__ void rng_tick_kernel(unsigned long long* rng) { rng[1] += 1ull; }
+
+inline uint32_t keep_threshold(float keep_prob) {
+    if (!(keep_prob < 1.0f)) return 1u << 24;
+    double t = (double)keep_prob * 16777216.0;
+    if (t < 0) t = 0;
+    return (uint32_t)t;
+}
+
+inline int ew_grid(long long items, int num_sms) {
+    long long blocks = (items + 255) / 256;
+    const long long cap = (long long)num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" int rsr_bn_train_stats(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,
+                                  const float* gamma, const float* beta, float eps, float* state, float momentum,
+                                  float renorm_momentum, int update_state, float* coef, float* scratch) {
+    if (!h || !z || !gamma || !beta || !state || !coef || !scratch || rows <= 0 || N <= 0) return RSR_E_ARG;
+    if ((N & 3) || (ldz & 3)) return RSR_E_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int splits = bn_splits(rows);
+    BnBwdIn none = {};
+    dim3 grid((N + BN_COLS - 1) / BN_COLS, splits), block(32, BN_LANES);
+    bn_partial_kernel<0><<<grid, block, 0, st>>>(z, ldz, rows, N, none, scratch);
+    RSR_LAUNCH_CHECK();
+    bn_finish_train_kernel<<<(N + 127) / 128, 128, 0, st>>>(scratch, splits, rows, N, gamma, beta, eps, state, momentum,
+                                                            renorm_momentum, update_state, coef);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_bn_eval_coef(rsr_handle* h, void* stream, int N, const float* gamma, const float* beta, float eps,
+                                const float* state, float* coef) {
+    if (!h || !gamma || !beta || !state || !coef || N <= 0) return RSR_E_ARG;
+    bn_eval_coef_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, gamma, beta, eps, state, coef);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_affine_act_drop(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,
+                                   const float* A, const float* Bc, int act, float keep_prob,
+                                   const unsigned long long* rng, unsigned salt, void* out16, int ld16) {
+    if (!h || !z || !Bc || !out16 || rows <= 0 || N <= 0) return RSR_E_ARG;
+    if ((N & 3) || (ldz & 3) || (ld16 & 3)) return RSR_E_SHAPE;
+    if (act != RSR_ACT_NONE && act != RSR_ACT_RELU && act != RSR_ACT_LRELU) return RSR_E_SHAPE;
+    const uint32_t thr = keep_threshold(keep_prob);
+    if (thr < (1u << 24) && (!rng || thr == 0)) return RSR_E_ARG;
+    affine_act_drop_kernel<<<ew_grid(rows * (N >> 2), h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        z, ldz, rows, N, A, Bc, act, thr, thr < (1u << 24) ? 1.0f / keep_prob : 1.0f, rng, salt, (uint16_t*)out16, ld16,
+        h->dtype == RSR_DTYPE_BF16);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldda, const float* z, int ldz,
+                          long long rows, int N, int act, float keep_prob, const unsigned long long* rng, unsigned salt,
+                          int bn, float* coef, const float* bias, float* dgamma, float* dbeta, void* dz16, int lddz,
+                          float* scratch) {
+    if (!h || !da16 || !z || !scratch || rows <= 0 || N <= 0) return RSR_E_ARG;
+    if (bn ? !coef : !bias) return RSR_E_ARG;
+    if ((N & 3) || (ldz & 3) || (ldda & 3) || (lddz & 3)) return RSR_E_SHAPE;
+    if (act != RSR_ACT_NONE && act != RSR_ACT_RELU && act != RSR_ACT_LRELU) return RSR_E_SHAPE;
+    const uint32_t thr = keep_threshold(keep_prob);
+    if (thr < (1u << 24) && (!rng || thr == 0)) return RSR_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    BnBwdIn p;
+    p.da = (const uint16_t*)da16; p.ldda = ldda;
+    if (bn) { p.A = coef; p.Bc = coef + (long long)N; p.mean = coef + 2ll * N; p.inv_std = coef + 3ll * N; }
+    else { p.A = nullptr; p.Bc = bias; p.mean = nullptr; p.inv_std = nullptr; }
+    p.act = act; p.thr24 = thr; p.inv_keep = thr < (1u << 24) ? 1.0f / keep_prob : 1.0f; p.rng = rng; p.salt = salt;
+    p.bf = h->dtype == RSR_DTYPE_BF16;
+    const int splits = bn_splits(rows);
+    if (bn || dbeta) {
+        dim3 grid((N + BN_COLS - 1) / BN_COLS, splits), block(32, BN_LANES);
+        bn_partial_kernel<1><<<grid, block, 0, st>>>(z, ldz, rows, N, p, scratch);
+        RSR_LAUNCH_CHECK();
+        bn_bwd_finish_kernel<<<(N + 127) / 128, 128, 0, st>>>(scratch, splits, rows, N, bn, coef, dgamma, dbeta);
+        RSR_LAUNCH_CHECK();
+    }
+    if (dz16) {
+        bn_bwd_apply_kernel<<<ew_grid(rows * (N >> 2), h->num_sms), 256, 0, st>>>(
+            z, ldz, rows, N, p, bn, bn ? coef + 6ll * N : nullptr, bn ? coef + 7ll * N : nullptr, (uint16_t*)dz16, lddz);
+        RSR_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int rsr_rng_tick(rsr_handle* h, void* stream, unsigned long long* rng) {
+    if (!h || !rng) return RSR_E_ARG;
+    rng_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rng);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}

@@ -42,6 +42,13 @@ class DNNTrainer(GAN_RNN):
         super(DNNTrainer, self).__init__(sess, args, devices, cross_validation=cross_validation, infer=True,
                                          name=name, handle=handle, share=share)
         self.infer = False
+        if share is None:
+            # contrib l2_regularizer is attached to the layer WEIGHTS only (models/dnn.py:64-67,85-86), so BatchNorm
+            # beta / gamma are not regularised here (the GAN's rule is `"bias" not in name`, gan_rnn_placeholder.py:254)
+            P = self.G.P
+            P.seg_l2 = torch.tensor(np.array([1 if s.name.endswith("weights") else 0 for s in P.segs.values()],
+                                             np.int32), device=P.seg_l2.device)
+        self.update_bn_stats = True              # UPDATE_OPS run with the step (dnn_trainer_single_gpu.py:101-104)
         self.max_grad_norm = 1e30                # no clip_by_norm on this trainer (the update kernel's clip is a no-op)
         self.mse_lambda = 1.0
         self.g_learning_rate = float(_arg(args, "g_learning_rate", 0.001))
@@ -57,6 +64,7 @@ class DNNTrainer(GAN_RNN):
         B, T = int(x3.shape[0]), int(x3.shape[1])
         x, y_tm, ln, B, T = self._feed(x3, y3, np.full(B, T, np.int32))
         h, G, rows = self.h, self.G, T * B
+        self._mode(train)
         gs = self._gscale(rows) if want_grad else 1.0
         g32 = G.fwd(x, B, T, ln, train=train)
         dg32 = G.ws.get(("loss", "dg32"), rows, g32.shape[1], F32) if want_grad else None

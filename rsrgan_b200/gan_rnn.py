@@ -103,10 +103,12 @@ class GAN_RNN(Model):
         self.max_grad_norm = 15                            # :70
         self.keep_prob = 1.0 if cross_validation else _arg(args, "keep_prob", 1.0)
         self.batch_norm = _arg(args, "batch_norm", False)
-        if self.batch_norm or self.keep_prob < 1.0:
-            # contrib batch_norm(renorm) / DropoutWrapper (models/lstm.py:61-67,99-102): off in the
-            # shipped driver (run_gan_rnn_placeholder.sh:131); not part of the B200 hot path yet.
-            raise NotImplementedError("batch_norm / dropout are not implemented (SURVEY.md section 8f)")
+        # contrib batch_norm(renorm) on the fully_connected layers and tf.nn.dropout behind them are nets.FCBN
+        # (csrc/batchnorm.cu); DropoutWrapper on the LSTM generators raises NotImplementedError in nets.Generator.
+        # This trainer never runs the UPDATE_OPS (:169-175 has no control dependency on them), so the moving
+        # averages of a batch-normalised GAN stay at their initial values -- reference behaviour, kept
+        # (`update_bn_stats = True` opts out); DNNTrainer does run them.
+        self.update_bn_stats = False
         self.batch_size = _arg(args, "batch_size", 8)
         self.devices = devices
         self.num_gpu = _arg(args, "num_gpu", 1)
@@ -144,7 +146,11 @@ class GAN_RNN(Model):
                 dev = int(d0.split(":")[-1]) if ":" in d0 else 0
             self.h = handle if handle is not None else ops.Handle(dev, _arg(args, "dtype", "f16"))
             in_dim = self.input_dim * (self.left_context + 1 + self.right_context)
-            gk = dict(in_dim=in_dim, out_dim=self.output_dim)
+            # models/dnn.py:64-68: the dnn generator drops out only when it is also regularised (else keep_prob = 1)
+            g_keep = self.keep_prob
+            if self.g_type == "dnn" and not _arg(args, "l2_scale", 0.0) > 0.0:
+                g_keep = 1.0
+            gk = dict(in_dim=in_dim, out_dim=self.output_dim, batch_norm=bool(self.batch_norm), keep_prob=g_keep)
             for k_arg, k in (("g_cell", "cell"), ("g_proj", "proj"), ("g_layers", "layers"), ("g_units", "units")):
                 v = _arg(args, k_arg, None)
                 if v is not None:
@@ -155,13 +161,16 @@ class GAN_RNN(Model):
             self.G = nets.Generator(self.h, self.g_type, **gk)
             self.D = None
             if not infer:
-                dk = dict(in_dim=self.output_dim)
+                dk = dict(in_dim=self.output_dim, batch_norm=bool(self.batch_norm), keep_prob=self.keep_prob)
                 for k_arg, k in (("d_cell", "cell"), ("d_proj", "proj"), ("d_layers", "layers"), ("d_units", "units")):
                     v = _arg(args, k_arg, None)
                     if v is not None:
                         dk[k] = v
                 self.D = nets.Discriminator(self.h, self.d_type, **dk)
             self.init_weights(_arg(args, "seed", 1234))
+            for net in (self.G, self.D):
+                if net is not None:
+                    net.rng[0] = int(_arg(args, "seed", 1234))
         self.g_learning_rate = float(_arg(args, "g_learning_rate", 0.0003))
         self.d_learning_rate = float(_arg(args, "d_learning_rate", 0.001))
         dev = self.h.device
@@ -213,7 +222,9 @@ class GAN_RNN(Model):
         def init(net):
             p = OrderedDict()
             for s in net.P.segs.values():
-                if "bias" in s.name:
+                if s.name.endswith("/BatchNorm/gamma") or s.name.endswith("/BatchNorm/beta"):
+                    p[s.name] = np.full(s.tf_shape, 1.0 if s.name.endswith("gamma") else 0.0, np.float32)
+                elif "bias" in s.name:
                     # zeros everywhere except the RCED output layer (models/rced.py:112 constant_initializer(0.1))
                     rced_out = self.g_type == "rced" and s.name == "g_model/fully_connected/biases"
                     p[s.name] = np.full(s.tf_shape, 0.1 if rced_out else 0.0, np.float32)
@@ -250,6 +261,10 @@ class GAN_RNN(Model):
         sd = OrderedDict(G=self.G.P.state_dict())
         if self.D is not None:
             sd["D"] = self.D.P.state_dict()
+        for net, key in ((self.G, "G"), (self.D, "D")):
+            if net is not None and net.fcbn:             # non-trainable batch_norm variables + dropout stream
+                sd[key]["bn_state"] = net.bn_state_tf()
+                sd[key]["rng"] = net.rng.cpu().numpy()
         sd["scalars"] = dict(mse_lambda=self.mse_lambda, disc_noise_std=self.disc_noise_std,
                              d_learning_rate=self.d_learning_rate, g_learning_rate=self.g_learning_rate,
                              d_real=self.d_real, d_fake=self.d_fake)
@@ -260,6 +275,9 @@ class GAN_RNN(Model):
             if net is None or key not in sd:
                 continue
             net.P.load_state_dict(sd[key])
+            if "bn_state" in sd[key]:
+                net.load_bn_state_tf(sd[key]["bn_state"])
+                net.rng.copy_(torch.as_tensor(np.asarray(sd[key]["rng"], np.int64)))
             if moving_average:                              # :47-53 restore the EMA shadows as the weights
                 net.P.theta.copy_(net.P.ema)
             net.P.refresh16()
@@ -317,8 +335,19 @@ class GAN_RNN(Model):
         return float(2.0 ** round(math.log2(max(rows / max(self.mse_lambda, 1.0), 1.0))))
 
     # ------------------------------------------------------------------ updates
+    def _mode(self, training):
+        """is_training of the graph about to run (batch_norm statistics, dropout): False on the cross-validation /
+        inference models (models/dnn.py:50, models/discriminator_dnn.py:30)."""
+        for net in (self.G, self.D):
+            if net is not None:
+                net.training = bool(training) and not self.cross_validation
+                net.bn_update = bool(self.update_bn_stats)
+
     def _update(self, net, gscale, adam):
         P, h = net.P, self.h
+        for n in (self.G, self.D):                         # next update draws new dropout masks in both networks
+            if n is not None:
+                n.tick()
         h.join()                                           # weight gradients computed on the side stream
         if self.world > 1:
             # utils/ops.py:343-376 average_gradients: sum over ranks here, 1/N folded into the update kernel
@@ -365,6 +394,7 @@ class GAN_RNN(Model):
         gradients wrt theta_D only, tower mean, per-tensor clip 15, SGD(lr_d), EMA."""
         x, y_tm, ln, B, T = _feed if _feed is not None else self._feed(inputs, labels, lengths)
         h, G, D, rows = self.h, self.G, self.D, T * B
+        self._mode(True)
         gs = self._gscale(rows)
         d_rl16 = D.ws.get(("loss", "d_rl16"), rows, 8, h.h16)
         d_fk16 = D.ws.get(("loss", "d_fk16"), rows, 8, h.h16)
@@ -393,6 +423,7 @@ class GAN_RNN(Model):
         gradients wrt theta_G only (through D, D frozen), tower mean, clip 15, Adam(lr_g), EMA."""
         x, y_tm, ln, B, T = _feed if _feed is not None else self._feed(inputs, labels, lengths)
         h, G, D, rows = self.h, self.G, self.D, T * B
+        self._mode(True)
         gs = self._gscale(rows)
         g32 = _g32 if _g32 is not None else G.fwd(x, B, T, ln, train=True, reuse_staged=_x_staged)
         lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"))
@@ -421,9 +452,10 @@ class GAN_RNN(Model):
         # 3 generator forwards of the schedule.
         g32 = None
         d_all, g_all = [], []
+        share = self.G.keep_prob >= 1.0                    # a generator with dropout draws a new mask per sess.run
         for _ in range(self.disc_updates):
             d = self.d_step(None, None, None, sync=False, _feed=feed, _g32=g32, _g_train=self.gen_updates > 0)
-            g32 = self._last_g32
+            g32 = self._last_g32 if share else None
             d_all.append(d[:2].clone())
         for k in range(self.gen_updates):
             # the generator has already staged this minibatch (16-bit, time-major) in an earlier forward of the schedule
@@ -578,6 +610,7 @@ class GAN_RNN(Model):
         """Loss-only pass of eval_one_iteration (scripts/train_gan_rnn_placeholder.py:154-172)."""
         x, y_tm, ln, B, T = self._feed(inputs, labels, lengths)
         h, G, D, rows = self.h, self.G, self.D, T * B
+        self._mode(False)
         g32 = G.fwd(x, B, T, ln, train=False)
         lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=self._noise(B, noise_rl), train=False)
         lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"), train=False)
@@ -591,6 +624,7 @@ class GAN_RNN(Model):
         """G(inputs) as a (B, T, output_dim) fp32 device tensor; with mean/std the decode-time inverse
         CMVN y*std+mean (scripts/train_gan_rnn_placeholder.py:286-287) is fused into the un-staging."""
         x, _, ln, B, T = self._feed(inputs, None, lengths)
+        self._mode(False)
         y32 = self.G.fwd(x, B, T, ln, train=False)
         out = torch.empty(B, T, self.output_dim, dtype=F32, device=self.h.device)
         m = None if mean is None else self._to_dev("cm_mean", mean, F32)

@@ -95,6 +95,107 @@ class FC(object):
         return dx16, dx32
 
 
+CTX_SALT = {"g": 0, "rl": 256, "fk": 512}     # dropout stream per layer call: salt = CTX_SALT[ctx] + layer index
+
+
+class FCBN(FC):
+    """fully_connected with its optional normalizer and dropout: tf.contrib.layers.fully_connected(x, n_out,
+    activation_fn, normalizer_fn=batch_norm, normalizer_params={is_training, scale=True, renorm=True}) then
+    tf.nn.dropout(keep_prob) -- models/dnn.py:56-62,79-102, models/discriminator_dnn.py:36-46,61-83,
+    models/lstm.py:61-67,82-87.  With the normalizer the layer has BatchNorm/beta and BatchNorm/gamma instead of a bias.
+    The tensor-core GEMM writes the fp32 pre-activation; statistics, normalisation, activation, dropout and their
+    gradients are the HBM-stream kernels of csrc/batchnorm.cu.  `bwd` takes the gradient wrt the layer OUTPUT."""
+
+    STATE_KEYS = ("moving_mean", "moving_variance", "renorm_mean", "renorm_stddev", "renorm_mean_weight",
+                  "renorm_stddev_weight")
+
+    def __init__(self, net, scope, n_in, n_out, act, bn, index):
+        super(FCBN, self).__init__(net, scope, n_in, n_out, act)
+        self.bn, self.index = bool(bn), index
+        self.betaname, self.gname = scope + "/BatchNorm/beta", scope + "/BatchNorm/gamma"
+        self.state = None
+        if self.bn:
+            # moving_mean 0, moving_variance 1, the four renorm variables 0 (TF 1.4 zero-initialises them)
+            self.state = torch.zeros(6, self.outp, dtype=F32, device=net.h.device)
+            self.state[1].fill_(1.0)
+        self._mode = {}
+
+    def segs(self):
+        if not self.bn:
+            return super(FCBN, self).segs()
+        return [params.fc_w(self.wname, self.n_in, self.n_out), params.fc_b(self.betaname, self.n_out),
+                params.fc_b(self.gname, self.n_out)]
+
+    def _bufs(self, ctx, rows):
+        ws = self.net.ws
+        return (ws.get((ctx, self.scope, "z32"), rows, self.outp, F32),
+                ws.get((ctx, self.scope, "bn_coef"), 8, self.outp, F32),
+                ws.get((ctx, self.scope, "bn_scratch"), 192, self.outp, F32))
+
+    def fwd(self, ctx, x16, rows, want16=True, want32=False):
+        net, h = self.net, self.net.h
+        z32, coef, scratch = self._bufs(ctx, rows)
+        y16 = net.ws.get((ctx, self.scope, "y16"), rows, self.outp, h.h16)
+        h.gemm(x16, net.P.view(self.wname, "theta16"), rows, self.outp, self.inp, b_mn=True, out32=z32)
+        keep = net.keep_prob if net.training else 1.0
+        if self.bn:
+            if net.training:
+                h.bn_train_stats(z32, rows, self.outp, net.P.view(self.gname), net.P.view(self.betaname), self.state,
+                                 coef, scratch, update_state=net.bn_update)
+            else:
+                h.bn_eval_coef(self.outp, net.P.view(self.gname), net.P.view(self.betaname), self.state, coef)
+            A, Bc = coef[0], coef[1]
+        else:
+            A, Bc = None, net.P.view(self.bname)
+        self._mode[ctx] = keep
+        h.affine_act_drop(z32, rows, self.outp, A, Bc, self.act, keep, net.rng, CTX_SALT[ctx] + self.index, y16)
+        return y16, None
+
+    def bwd(self, ctx, x16, da16, rows, want_dw=True, want_dx=True, resid32=None, want32=False, dw_side=True, **_):
+        net, h = self.net, self.net.h
+        z32, coef, scratch = self._bufs(ctx, rows)
+        dz16 = net.ws.get((ctx, self.scope, "dz16"), rows, self.outp, h.h16)
+        P = net.P
+        if self.bn:
+            h.bn_bwd(da16, z32, rows, self.outp, self.act, self._mode[ctx], net.rng, CTX_SALT[ctx] + self.index, True,
+                     coef, None, P.view(self.gname, "grad") if want_dw else None,
+                     P.view(self.betaname, "grad") if want_dw else None, dz16, scratch)
+        else:
+            h.bn_bwd(da16, z32, rows, self.outp, self.act, self._mode[ctx], net.rng, CTX_SALT[ctx] + self.index, False,
+                     None, P.view(self.bname), None, P.view(self.bname, "grad") if want_dw else None, dz16, scratch)
+        dx16 = dx32 = None
+        if want_dx:
+            dx16 = net.ws.get((ctx, self.scope, "dx16"), rows, self.inp, h.h16)
+            dx32 = net.ws.get((ctx, self.scope, "dx32"), rows, self.inp, F32) if want32 else None
+            h.gemm(dz16, P.view(self.wname, "theta16"), rows, self.inp, self.outp, resid=resid32, out16=dx16,
+                   out32=dx32)
+        if want_dw:
+            with (h.side_stream() if dw_side else contextlib.nullcontext()):
+                h.gemm(x16, dz16, self.inp, self.outp, rows, a_mn=True, b_mn=True, beta=1.0,
+                       out32=P.view(self.wname, "grad"))
+        return dx16, dx32
+
+    # -- non-trainable variables <-> TF names ------------------------------------------------
+    def export_state(self):
+        out = {}
+        if self.bn:
+            st = self.state.detach().cpu().numpy()
+            for i, k in enumerate(self.STATE_KEYS):
+                out[self.scope + "/BatchNorm/" + k] = st[i, :self.n_out].copy() if i < 4 else st[i, 0].copy()
+        return out
+
+    def load_state(self, d):
+        if self.bn:
+            for i, k in enumerate(self.STATE_KEYS):
+                v = torch.as_tensor(d[self.scope + "/BatchNorm/" + k], dtype=F32)
+                if i < 4:
+                    self.state[i].zero_()
+                    self.state[i, :self.n_out] = v.to(self.state.device)
+                else:
+                    self.state[i].fill_(float(v))
+            self.state[1, self.n_out:] = 1.0
+
+
 class LSTMP(object):
     """tf.contrib.rnn.LSTMCell(C, use_peepholes=True, num_proj=P, forget_bias=1.0) under
     tf.nn.dynamic_rnn(sequence_length) -- models/lstm.py:89-112, models/res_lstm_l.py:86-138,
@@ -350,6 +451,13 @@ class Net(object):
     def __init__(self, handle, layers_fn, adam):
         self.h = handle
         self.ws = Workspace(handle)
+        # batch_norm / dropout mode (FCBN layers): `training` = is_training of the graph being run (False for the
+        # cross-validation / inference models), `bn_update` = whether the UPDATE_OPS run with the step
+        # (models/dnn_trainer_single_gpu.py:101-104 yes; models/gan_rnn_placeholder.py:169-175 no), `rng` = device
+        # {seed, tick} of the dropout stream (rsr_affine_act_drop)
+        self.training, self.bn_update = True, False
+        self.keep_prob = getattr(self, "keep_prob", 1.0)
+        self.rng = torch.tensor([1234, 0], dtype=torch.int64, device=handle.device)
         self.layers = layers_fn(self)
         segs = []
         for l in self.layers:
@@ -360,6 +468,29 @@ class Net(object):
         self.P.load_tf(p)
         self.P.ema.copy_(self.P.theta)
         self.refresh()
+
+    @property
+    def fcbn(self):
+        return any(isinstance(l, FCBN) for l in self.layers)
+
+    def bn_state_tf(self):
+        """Non-trainable batch_norm variables keyed by their TF names (saved with the checkpoint, like tf.train.Saver
+        saves every global variable, models/gan_rnn_placeholder.py:26-34)."""
+        out = {}
+        for l in self.layers:
+            if isinstance(l, FCBN):
+                out.update(l.export_state())
+        return out
+
+    def load_bn_state_tf(self, d):
+        for l in self.layers:
+            if isinstance(l, FCBN):
+                l.load_state(d)
+
+    def tick(self):
+        """Advance the dropout stream (once per update, after the backward pass regenerated its masks)."""
+        if self.keep_prob < 1.0:
+            self.h.rng_tick(self.rng)
 
     def refresh(self):
         """Weight-derived operands after an update.  The per-layer refreshes are tiny and independent: alternate
@@ -381,14 +512,24 @@ RCED_WIDTHS = (13, 11, 9, 7, 7, 7, 9, 11, 13)            # models/rced.py:93
 
 class Generator(Net):
     def __init__(self, handle, g_type="lstm", in_dim=257, out_dim=40, cell=760, proj=280, layers=None,
-                 units=1024):
+                 units=1024, batch_norm=False, keep_prob=1.0):
         self.g_type, self.in_dim, self.out_dim = g_type, in_dim, out_dim
+        self.keep_prob = float(keep_prob) if g_type == "dnn" else 1.0
+        if keep_prob < 1.0 and g_type in ("lstm", "res_lstm_l", "res_lstm_base"):
+            # DropoutWrapper(output_keep_prob) on every LSTM layer (models/lstm.py:99-102): not on this path yet
+            raise NotImplementedError("dropout on the LSTM generators (DropoutWrapper) is not implemented")
+        if (batch_norm or keep_prob < 1.0) and g_type == "rced":
+            raise NotImplementedError("batch_norm / dropout on the rced generator are not implemented")
+        # res_lstm_l / res_lstm_base build normalizer_params but never pass them on (models/res_lstm_l.py:58-67,81-82):
+        # batch_norm is a no-op there, exactly as in the reference
+        special = batch_norm or self.keep_prob < 1.0
         if g_type == "lstm":
             # models/lstm.py:43-45: cell 760, projection 280, 3 layers
             L = 3 if layers is None else layers
 
             def mk(net):
-                ls = [FC(net, "g_model/fully_connected", in_dim, proj, ACT_LRELU)]
+                ls = [FCBN(net, "g_model/fully_connected", in_dim, proj, ACT_LRELU, True, 0) if batch_norm else
+                      FC(net, "g_model/fully_connected", in_dim, proj, ACT_LRELU)]
                 ls += [LSTMP(net, "g_model/rnn/multi_rnn_cell/cell_%d/lstm_cell/" % i, proj, cell, proj)
                        for i in range(L)]
                 return ls + [FC(net, "g_model/fully_connected_1", proj, out_dim, ACT_NONE)]
@@ -406,8 +547,11 @@ class Generator(Net):
 
             def mk(net):
                 dims = [in_dim] + [units] * (L + 1)
-                ls = [FC(net, "g_model/fully_connected" + ("" if i == 0 else "_%d" % i), dims[i], dims[i + 1],
-                         ACT_RELU) for i in range(L + 1)]
+                name = lambda i: "g_model/fully_connected" + ("" if i == 0 else "_%d" % i)
+                if special:
+                    ls = [FCBN(net, name(i), dims[i], dims[i + 1], ACT_RELU, batch_norm, i) for i in range(L + 1)]
+                else:
+                    ls = [FC(net, name(i), dims[i], dims[i + 1], ACT_RELU) for i in range(L + 1)]
                 return ls + [FC(net, "g_model/fully_connected_%d" % (L + 1), units, out_dim, ACT_NONE)]
         elif g_type == "rced":
             # models/rced.py:92-101: nine [1, w] ReLU convolutions over the spectrum bins of each frame, then
@@ -492,9 +636,10 @@ class Generator(Net):
             return
         if self.g_type == "dnn":
             d = dy16
+            plain = not self.fcbn          # FCBN layers take the gradient wrt their OUTPUT and apply act' themselves
             for i in range(len(Ls) - 1, -1, -1):
-                d, _ = Ls[i].bwd("g", acts[i], d, rows, want_dx=i > 0, prev_y16=acts[i] if i > 0 else None,
-                                 prev_act=ACT_RELU)
+                d, _ = Ls[i].bwd("g", acts[i], d, rows, want_dx=i > 0, prev_y16=acts[i] if i > 0 and plain else None,
+                                 prev_act=ACT_RELU if plain else ACT_NONE)
             return
         if self.g_type == "lstm":
             d16, d32 = Ls[-1].bwd("g", acts[-1], dy16, rows, want32=True)
@@ -502,8 +647,9 @@ class Generator(Net):
             for i in range(len(Ls) - 2, 0, -1):
                 first = i == 1
                 dout32 = d32
-                d16, d32 = Ls[i].bwd_main("g", d16, B, T, lengths, prev_y16=acts[1] if first else None,
-                                          prev_act=ACT_LRELU if first else ACT_NONE, want32=not first)
+                mask = first and not self.fcbn      # an FCBN first layer applies its own activation gradient
+                d16, d32 = Ls[i].bwd_main("g", d16, B, T, lengths, prev_y16=acts[1] if mask else None,
+                                          prev_act=ACT_LRELU if mask else ACT_NONE, want32=not first)
                 if not first:
                     Ls[i - 1].bwd_pre("g", d16, B, T)     # critical path first, then this layer's weight gradients
                 Ls[i].bwd_side("g", acts[i], dout32, B, T)
@@ -516,8 +662,13 @@ class Generator(Net):
 
 
 class Discriminator(Net):
-    def __init__(self, handle, d_type="lstm", in_dim=40, cell=256, proj=40, layers=None, units=1024):
+    def __init__(self, handle, d_type="lstm", in_dim=40, cell=256, proj=40, layers=None, units=1024,
+                 batch_norm=False, keep_prob=1.0):
         self.d_type, self.in_dim = d_type, in_dim
+        # discriminator_lstm builds normalizer_params / keep_prob but uses neither (models/discriminator_lstm.py:37-52,
+        # 64): both are no-ops there, as in the reference
+        self.keep_prob = float(keep_prob) if d_type == "dnn" else 1.0
+        special = d_type == "dnn" and (batch_norm or self.keep_prob < 1.0)
         if d_type == "lstm":
             # models/discriminator_lstm.py:26-28: cell 256, projection 40, 2 layers, FC -> 1 (no clip, :105)
             L = 2 if layers is None else layers
@@ -533,8 +684,11 @@ class Discriminator(Net):
 
             def mk(net):
                 dims = [in_dim] + [units] * (L + 1)
-                ls = [FC(net, "d_model/fully_connected" + ("" if i == 0 else "_%d" % i), dims[i], dims[i + 1],
-                         ACT_RELU) for i in range(L + 1)]
+                name = lambda i: "d_model/fully_connected" + ("" if i == 0 else "_%d" % i)
+                if special:
+                    ls = [FCBN(net, name(i), dims[i], dims[i + 1], ACT_RELU, batch_norm, i) for i in range(L + 1)]
+                else:
+                    ls = [FC(net, name(i), dims[i], dims[i + 1], ACT_RELU) for i in range(L + 1)]
                 return ls + [FC(net, "d_model/fully_connected_%d" % (L + 1), units, 1, ACT_NONE)]
         else:
             raise ValueError("Unrecognized D type {}".format(d_type))
@@ -578,9 +732,10 @@ class Discriminator(Net):
                                      want32=want_dw and not last)
             return d16
         d = dlogit16
+        plain = not self.fcbn
         for i in range(len(Ls) - 1, -1, -1):
             last = i == 0
             d, _ = Ls[i].bwd(ctx, acts[i], d, rows, want_dw=want_dw, want_dx=(not last) or want_dx,
-                             prev_y16=None if last else acts[i], prev_act=ACT_RELU,
+                             prev_y16=None if last or not plain else acts[i], prev_act=ACT_RELU if plain else ACT_NONE,
                              resid32=resid32 if last else None)
         return d

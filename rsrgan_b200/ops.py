@@ -255,3 +255,27 @@ class Handle(object):
         self._call("rsr_fc1_bwd_dx", 1, self.h, _stream(), _p(dy16), dy16.stride(0), rows, K, _p(w16), w16.stride(0),
                    _p(dact_src), dact_src.stride(0) if dact_src is not None else 0, dact, _p(dx16), dx16.stride(0),
                    work=2.0 * rows * K)
+
+    # ------------------------------------------------------ batch_norm(renorm) / dropout
+    BN_EPS, BN_DECAY, BN_RENORM_DECAY = 1e-3, 0.999, 0.99     # contrib batch_norm defaults (TF 1.4)
+
+    def bn_train_stats(self, z32, rows, N, gamma, beta, state, coef, scratch, update_state=False):
+        self._call("rsr_bn_train_stats", 2, self.h, _stream(), _p(z32), z32.stride(0), rows, N, _p(gamma), _p(beta),
+                   self.BN_EPS, _p(state), self.BN_DECAY, self.BN_RENORM_DECAY, int(update_state), _p(coef),
+                   _p(scratch))
+
+    def bn_eval_coef(self, N, gamma, beta, state, coef):
+        self._call("rsr_bn_eval_coef", 1, self.h, _stream(), N, _p(gamma), _p(beta), self.BN_EPS, _p(state), _p(coef))
+
+    def affine_act_drop(self, z32, rows, N, A, Bc, act, keep_prob, rng, salt, out16):
+        self._call("rsr_affine_act_drop", 1, self.h, _stream(), _p(z32), z32.stride(0), rows, N, _p(A), _p(Bc), act,
+                   float(keep_prob), _p(rng), int(salt), _p(out16), out16.stride(0))
+
+    def bn_bwd(self, da16, z32, rows, N, act, keep_prob, rng, salt, bn, coef, bias, dgamma, dbeta, dz16, scratch):
+        n = (2 if (bn or dbeta is not None) else 0) + (1 if dz16 is not None else 0)
+        self._call("rsr_bn_bwd", n, self.h, _stream(), _p(da16), da16.stride(0), _p(z32), z32.stride(0), rows, N, act,
+                   float(keep_prob), _p(rng), int(salt), int(bn), _p(coef), _p(bias), _p(dgamma), _p(dbeta),
+                   _p(dz16), dz16.stride(0) if dz16 is not None else 0, _p(scratch))
+
+    def rng_tick(self, rng):
+        self._call("rsr_rng_tick", 1, self.h, _stream(), _p(rng))

@@ -296,3 +296,81 @@ class FakeHandle(object):
     def fill32(self, x, v):
         self.launches += 1
         x.fill_(v)
+
+    # ------------------------------------------------------ batch_norm(renorm) / dropout
+    BN_EPS, BN_DECAY, BN_RENORM_DECAY = 1e-3, 0.999, 0.99
+
+    def bn_train_stats(self, z32, rows, N, gamma, beta, state, coef, scratch, update_state=False):
+        self.launches += 2
+        z = z32[:rows, :N]
+        mean = z.mean(0)
+        var = ((z - mean) ** 2).mean(0)
+        std = torch.sqrt(var + self.BN_EPS)
+        mm, mv, rm, rs, rmw, rsw = (state[i, :N] for i in range(6))
+        denom = rs + (1 - rsw) * std
+        r, d = std / denom, (mean - (rm + (1 - rmw) * mean)) / denom
+        A = r * gamma[:N] / std
+        coef[0, :N], coef[1, :N], coef[2, :N], coef[3, :N] = A, d * gamma[:N] + beta[:N] - mean * A, mean, 1.0 / std
+        coef[4, :N], coef[5, :N] = r, d
+        if update_state:
+            k = 1 - self.BN_RENORM_DECAY
+            rm -= (rm - mean) * k
+            rmw -= (rmw - 1) * k
+            rs -= (rs - std) * k
+            rsw -= (rsw - 1) * k
+            mm -= (mm - rm / rmw) * (1 - self.BN_DECAY)
+            mv -= (mv - ((rs / rsw) ** 2 - self.BN_EPS)) * (1 - self.BN_DECAY)
+
+    def bn_eval_coef(self, N, gamma, beta, state, coef):
+        self.launches += 1
+        inv = torch.rsqrt(state[1, :N] + self.BN_EPS)
+        coef[0, :N], coef[1, :N] = gamma[:N] * inv, beta[:N] - state[0, :N] * gamma[:N] * inv
+        coef[2, :N], coef[3, :N], coef[4, :N], coef[5, :N] = state[0, :N], inv, 1.0, 0.0
+
+    @staticmethod
+    def _drop_mask(rng, salt, rows, N, keep_prob):
+        import numpy as np
+        M = (1 << 64) - 1
+
+        def sm(x):                                     # splitmix64 finaliser on numpy uint64 (wraps)
+            x = x ^ (x >> np.uint64(30))
+            x = x * np.uint64(0xbf58476d1ce4e5b9)
+            x = x ^ (x >> np.uint64(27))
+            x = x * np.uint64(0x94d049bb133111eb)
+            return x ^ (x >> np.uint64(31))
+        seed, tick = (int(v) & M for v in rng.tolist())
+        with np.errstate(over="ignore"):
+            key = sm(np.uint64((seed + 0x9E3779B97F4A7C15 * (tick * 65536 + salt)) & M))
+            bits = sm(key ^ np.arange(rows * N, dtype=np.uint64).reshape(rows, N)) >> np.uint64(40)
+        return torch.from_numpy((bits < np.uint64(int(keep_prob * 16777216.0))))
+
+    def affine_act_drop(self, z32, rows, N, A, Bc, act, keep_prob, rng, salt, out16):
+        self.launches += 1
+        y = z32[:rows, :N] * (A[:N] if A is not None else 1.0) + Bc[:N]
+        a = _act(y, act)
+        if keep_prob < 1.0:
+            a = torch.where(self._drop_mask(rng, salt, rows, N, keep_prob), a / keep_prob, torch.zeros_like(a))
+        out16[:rows, :N] = a.to(self.h16)
+
+    def bn_bwd(self, da16, z32, rows, N, act, keep_prob, rng, salt, bn, coef, bias, dgamma, dbeta, dz16, scratch):
+        self.launches += 3
+        z = z32[:rows, :N]
+        y = z * coef[0, :N] + coef[1, :N] if bn else z + bias[:N]
+        g = da16[:rows, :N].float() * _dact(y, act)
+        if keep_prob < 1.0:
+            g = torch.where(self._drop_mask(rng, salt, rows, N, keep_prob), g / keep_prob, torch.zeros_like(g))
+        s1 = g.sum(0)
+        if dbeta is not None:
+            dbeta[:N] += s1
+        if bn:
+            xh = (z - coef[2, :N]) * coef[3, :N]
+            s2 = (g * xh).sum(0)
+            if dgamma is not None:
+                dgamma[:N] += coef[4, :N] * s2 + coef[5, :N] * s1
+            g = coef[0, :N] * (g - s1 / rows - xh * (s2 / rows))
+        if dz16 is not None:
+            dz16[:rows, :N] = g.to(self.h16)
+
+    def rng_tick(self, rng):
+        self.launches += 1
+        rng[1] += 1

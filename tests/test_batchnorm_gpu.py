@@ -1,0 +1,289 @@
+"""csrc/batchnorm.cu on the GPU, through the C ABI: batch_norm(renorm) statistics / normalisation / backward and the
+counter-based dropout against the float64 oracle, then nets.FCBN inside DNNTrainer and GAN_RNN.
+
+Tolerances: the kernels are fp32 streams over an fp32 pre-activation -> statistics and coefficients 1e-5 relative RMS
+against float64; 16-bit outputs within half an ulp of the oracle value (relative RMS 1e-3 f16 / 8e-3 bf16); the
+dropout mask is integer arithmetic and must be BIT-EXACT.  Model level: as tests/test_frame_models_gpu.py."""
+import copy
+from argparse import Namespace
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rsr_oracle as O
+
+pytestmark = pytest.mark.gpu
+F32 = torch.float32
+
+
+@pytest.fixture(scope="module", params=["f16", "bf16"])
+def h(request):
+    from rsrgan_b200 import ops
+    hd = ops.Handle(0, request.param)
+    yield hd
+    hd.close()
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.sqrt(((a - b) ** 2).mean()) / (np.sqrt((b ** 2).mean()) + 1e-30))
+
+
+def tol(h, f16, bf16):
+    return f16 if h.dtype_id == 0 else bf16
+
+
+def state_arrays(st, N):
+    a = np.zeros((6, N), np.float32)
+    for i, k in enumerate(O.BN_STATE_KEYS):
+        a[i] = st[k]
+    return a
+
+
+def warm(st, rng):
+    st["renorm_mean_weight"] = np.float64(0.26)
+    st["renorm_stddev_weight"] = np.float64(0.26)
+    st["renorm_stddev"] = 0.26 * (1.5 + 0.3 * rng.random(st["renorm_stddev"].shape))
+    st["renorm_mean"] = 0.26 * (0.5 + 0.2 * rng.standard_normal(st["renorm_mean"].shape))
+    st["moving_mean"] = 0.1 * rng.standard_normal(st["moving_mean"].shape)
+    st["moving_variance"] = 1 + 0.2 * rng.random(st["moving_variance"].shape)
+    return st
+
+
+# rows: one split / ragged splits / empty trailing split / the cfg-2 size; N: one float4 ... several column tiles
+@pytest.mark.parametrize("rows,N", [(1, 8), (64, 40), (300, 280), (4097, 1024), (12800, 1024), (100, 136)])
+@pytest.mark.parametrize("update", [False, True])
+def test_bn_train_stats_and_state(h, rows, N, update):
+    dev, rng = h.device, np.random.default_rng(rows + N)
+    ld = N + 4
+    z = (rng.standard_normal((rows, N)) * (0.5 + rng.random(N)) + 3.0 * rng.standard_normal(N)).astype(np.float32)
+    gamma, beta = (1 + 0.2 * rng.standard_normal(N)).astype(np.float32), rng.standard_normal(N).astype(np.float32)
+    st = warm(O.bn_init_state(N), rng)
+    zt = torch.zeros(rows, ld, dtype=F32, device=dev)
+    zt[:, :N] = torch.tensor(z)
+    state = torch.tensor(state_arrays(st, N), device=dev)
+    coef = torch.zeros(8, N, dtype=F32, device=dev)
+    scratch = torch.zeros(192, N, dtype=F32, device=dev)
+    h.bn_train_stats(zt, rows, N, torch.tensor(gamma, device=dev), torch.tensor(beta, device=dev), state, coef, scratch,
+                     update_state=update)
+    torch.cuda.synchronize()
+    st_ref = copy.deepcopy(st)
+    y_ref, (xh, r, d, _, std) = O.bn_renorm_train_fwd(z.astype(np.float64), gamma.astype(np.float64),
+                                                        beta.astype(np.float64), st_ref, update=update)
+    c = coef.cpu().numpy().astype(np.float64)
+    mean = z.astype(np.float64).mean(0)
+    assert rel(c[2], mean) < 1e-5 and rel(c[3], 1.0 / std) < 1e-5
+    assert rel(c[4], r) < 1e-5 and rel(c[5] + 1.0, d + 1.0) < 1e-5
+    # y = z A + B reproduces the oracle's normalised value
+    assert rel(z * c[0] + c[1], y_ref) < 2e-5
+    s = state.cpu().numpy()
+    for i, k in enumerate(O.BN_STATE_KEYS):
+        want = np.broadcast_to(st_ref[k], (N,))
+        assert rel(s[i] + 1.0, want + 1.0) < 1e-5, k
+        if not update:
+            assert np.array_equal(s[i], state_arrays(st, N)[i]), k
+
+
+def test_bn_eval_coef(h):
+    dev, rng, N = h.device, np.random.default_rng(1), 280
+    st = warm(O.bn_init_state(N), rng)
+    gamma, beta = (1 + 0.2 * rng.standard_normal(N)).astype(np.float32), rng.standard_normal(N).astype(np.float32)
+    coef = torch.zeros(8, N, dtype=F32, device=dev)
+    h.bn_eval_coef(N, torch.tensor(gamma, device=dev), torch.tensor(beta, device=dev),
+                   torch.tensor(state_arrays(st, N), device=dev), coef)
+    z = rng.standard_normal((50, N))
+    c = coef.cpu().numpy().astype(np.float64)
+    assert rel(z * c[0] + c[1], O.bn_eval_fwd(z, gamma.astype(np.float64), beta.astype(np.float64), st)) < 1e-5
+    assert np.all(c[4] == 1.0) and np.all(c[5] == 0.0)
+
+
+@pytest.mark.parametrize("rows,N", [(7, 8), (300, 280), (12800, 1024)])
+@pytest.mark.parametrize("act", [O.ACT_RELU, O.ACT_LRELU, O.ACT_NONE])
+@pytest.mark.parametrize("keep", [1.0, 0.8])
+def test_affine_act_drop_and_mask_bit_exact(h, rows, N, act, keep):
+    dev, rng = h.device, np.random.default_rng(rows + N + act)
+    z = rng.standard_normal((rows, N)).astype(np.float32)
+    A, Bc = (1 + 0.3 * rng.standard_normal(N)).astype(np.float32), rng.standard_normal(N).astype(np.float32)
+    seed, tick, salt = 99, 5, 513
+    rngbuf = torch.tensor([seed, tick], dtype=torch.int64, device=dev)
+    out = torch.zeros(rows, N + 8, dtype=h.h16, device=dev)
+    h.affine_act_drop(torch.tensor(z, device=dev), rows, N, torch.tensor(A, device=dev), torch.tensor(Bc, device=dev),
+                      act, keep, rngbuf, salt, out)
+    torch.cuda.synchronize()
+    y = O.act_fwd(z.astype(np.float64) * A + Bc, act)
+    got = out[:, :N].float().cpu().numpy()
+    if keep < 1.0:
+        mask = O.dropout_mask(seed, tick, salt, rows, N, keep)
+        y = np.where(mask, y / keep, 0.0)
+        nz = np.abs(y) > 1e-3                      # away from values that round to zero anyway
+        assert np.array_equal(got[nz] != 0, mask[nz]) and not got[~mask].any()
+    assert rel(got, y) < tol(h, 1e-3, 8e-3)
+    assert not out[:, N:].any()
+    # the tick kernel advances the stream: a different mask
+    if keep < 1.0 and rows > 100:
+        h.rng_tick(rngbuf)
+        out2 = torch.zeros_like(out)
+        h.affine_act_drop(torch.tensor(z, device=dev), rows, N, torch.tensor(A, device=dev),
+                          torch.tensor(Bc, device=dev), act, keep, rngbuf, salt, out2)
+        assert rngbuf.tolist() == [seed, tick + 1]
+        m2 = O.dropout_mask(seed, tick + 1, salt, rows, N, keep)
+        assert not out2[:, :N].float().cpu().numpy()[~m2].any() and not np.array_equal(m2, mask)
+
+
+@pytest.mark.parametrize("rows,N", [(5, 8), (300, 280), (12800, 1024)])
+@pytest.mark.parametrize("bn,act,keep", [(1, O.ACT_RELU, 1.0), (1, O.ACT_RELU, 0.8), (1, O.ACT_LRELU, 1.0),
+                                         (0, O.ACT_RELU, 0.7)])
+def test_bn_backward(h, rows, N, bn, act, keep):
+    dev, rng = h.device, np.random.default_rng(rows * 3 + N + act)
+    z = (rng.standard_normal((rows, N)) + rng.standard_normal(N)).astype(np.float32)
+    gamma, beta = (1 + 0.2 * rng.standard_normal(N)).astype(np.float32), (0.3 * rng.standard_normal(N)).astype(np.float32)
+    st = warm(O.bn_init_state(N), rng)
+    seed, tick, salt = 5, 2, 258
+    rngbuf = torch.tensor([seed, tick], dtype=torch.int64, device=dev)
+    zt = torch.tensor(z, device=dev)
+    gam_t, bet_t = torch.tensor(gamma, device=dev), torch.tensor(beta, device=dev)
+    coef = torch.zeros(8, N, dtype=F32, device=dev)
+    scratch = torch.zeros(192, N, dtype=F32, device=dev)
+    da = (rng.standard_normal((rows, N)) * 0.1).astype(np.float32)
+    da16 = torch.tensor(da, device=dev).to(h.h16)
+    da_r = da16.double().cpu().numpy()                 # the 16-bit values the kernel actually reads
+    dgam = torch.full((N,), 0.5, dtype=F32, device=dev)
+    dbet = torch.full((N,), -0.25, dtype=F32, device=dev)
+    dz16 = torch.zeros(rows, N, dtype=h.h16, device=dev)
+    z64 = z.astype(np.float64)
+    if bn:
+        h.bn_train_stats(zt, rows, N, gam_t, bet_t, torch.tensor(state_arrays(st, N), device=dev), coef, scratch)
+        y, cache = O.bn_renorm_train_fwd(z64, gamma.astype(np.float64), beta.astype(np.float64), copy.deepcopy(st),
+                                         update=False)
+    else:
+        y = z64 + beta
+    h.bn_bwd(da16, zt, rows, N, act, keep, rngbuf, salt, bool(bn), coef if bn else None, None if bn else bet_t,
+             dgam if bn else None, dbet, dz16, scratch)
+    torch.cuda.synchronize()
+    g = da_r.copy()
+    if keep < 1.0:
+        g = np.where(O.dropout_mask(seed, tick, salt, rows, N, keep), g / keep, 0.0)
+    dy = O.act_bwd(y, g, act)
+    if bn:
+        dz, dgamma, dbeta = O.bn_renorm_train_bwd(dy, cache)
+        assert rel(dgam.cpu().numpy() - 0.5, dgamma) < 1e-4        # accumulated INTO the gradient buffer
+    else:
+        dz, dbeta = dy, dy.sum(0)
+    if rows > 1:
+        assert rel(dbet.cpu().numpy() + 0.25, dbeta) < 1e-4
+    got = dz16.float().cpu().numpy()
+    assert rel(got, dz) < tol(h, 1e-3, 8e-3)
+    if bn and rows >= 300 and keep == 1.0:
+        # size-independent property of the batch-norm gradient: dz is orthogonal to 1 and to x_hat, column by column
+        xh = cache[0]
+        scale = np.abs(dz).sum(0) + 1e-30
+        assert np.abs(dz.sum(0) / scale).max() < 1e-9
+        assert np.abs(got.astype(np.float64).sum(0) / scale).max() < tol(h, 2e-3, 2e-2)
+        assert np.abs((got * xh).sum(0) / scale).max() < tol(h, 2e-3, 2e-2)
+
+
+def test_bn_shape_errors(h):
+    from rsrgan_b200._lib import RsrError
+    dev = h.device
+    z = torch.zeros(8, 10, dtype=F32, device=dev)
+    v = torch.zeros(16, dtype=F32, device=dev)
+    with pytest.raises(RsrError, match="RSR_E_SHAPE"):           # N not a multiple of 4
+        h.bn_train_stats(z, 8, 10, v, v, torch.zeros(6, 10, device=dev), torch.zeros(8, 10, device=dev),
+                         torch.zeros(192, 10, device=dev))
+    with pytest.raises(RsrError, match="RSR_E_ARG"):             # dropout without a stream
+        h.affine_act_drop(torch.zeros(8, 8, device=dev), 8, 8, None, v, 1, 0.5, None, 0,
+                          torch.zeros(8, 8, dtype=h.h16, device=dev))
+
+
+# ------------------------------------------------------------------ model level
+def tf32(p):
+    return OrderedDict((k, np.asarray(v, np.float32)) for k, v in p.items())
+
+
+def perturb_bn(p, rng):
+    for k in p:
+        if "BatchNorm" in k:
+            p[k] = p[k] + 0.1 * rng.standard_normal(p[k].shape)
+    return p
+
+
+def test_dnn_trainer_with_batch_norm_reference_driver_shape():
+    """What run_dnn_single_gpu.sh trains (:129-145): splice 11 x 257 inputs, batch 256, batch_norm on, dropout + l2;
+    three Adam steps with the UPDATE_OPS against the oracle, then the inference graph on the moving averages."""
+    from rsrgan_b200.dnn_trainer import DNNTrainer
+    rng = np.random.default_rng(21)
+    N, I, U = 256, 257 * 11, 1024
+    args = Namespace(g_type="dnn", batch_size=N, input_dim=257, left_context=5, right_context=5, output_dim=40,
+                     g_units=U, batch_norm=True, keep_prob=0.8, l2_scale=1e-5, g_learning_rate=1e-3, seed=11,
+                     dtype="f16")
+    m = DNNTrainer(None, args, ["/gpu:0"])
+    gp = perturb_bn(O.init_g_dnn(rng, in_dim=I, out_dim=40, units=U, hidden=3, batch_norm=True), rng)
+    m.load_params(tf32(gp))
+    bst = O.init_bn_state(gp)
+    st = O.MseState(OrderedDict((k, v.copy()) for k, v in gp.items()), "dnn")
+    n0 = m.h.launches
+    for step in range(3):
+        x, y = rng.standard_normal((N, I)).astype(np.float32), rng.standard_normal((N, 40)).astype(np.float32)
+        out = m.train_step(x, y)
+        opts = dict(bn_state=bst, update=True, keep_prob=0.8, rng=(11, step))
+        losses, _ = O.mse_step(st, x.astype(np.float64), y.astype(np.float64), 1e-3, l2_scale=1e-5, g_opts=opts)
+        assert out["g_mse_loss"] == pytest.approx(losses["g_mse_loss"], rel=3e-3)
+        assert out["g_l2_loss"] == pytest.approx(losses["g_l2_loss"], rel=1e-3)
+    assert m.h.launches > n0
+    mine = m.G.bn_state_tf()
+    for k in bst:
+        assert rel(np.asarray(mine[k]) + 1.0, np.asarray(bst[k]) + 1.0) < 1e-3, k
+    cv = DNNTrainer(None, args, ["/gpu:0"], cross_validation=True, share=m)
+    g = cv.generate(x).cpu().numpy()
+    g_ref, _ = O.g_dnn_fwd(st.g, x.astype(np.float64), None, opts=dict(bn_state=bst, train=False))
+    d = float(np.sqrt(((g - g_ref) ** 2).mean()))
+    assert d < 1e-3 * max(1.0, float(np.sqrt((g_ref ** 2).mean()))) * 3, d
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_gan_batch_norm_and_dropout(graph):
+    """dnn generator + discriminator_dnn, batch_norm in both, dropout in D: gradients of one D and one G update against
+    the oracle; then the whole schedule (eager and as a CUDA graph: the tick kernel and the statistics are captured)."""
+    from rsrgan_b200.gan_rnn import GAN_RNN
+    rng = np.random.default_rng(6)
+    B, T, I, U = 8, 50, 257, 256
+    args = Namespace(g_type="dnn", d_type="dnn", batch_size=B, input_dim=I, output_dim=40, g_units=U, g_layers=1,
+                     d_units=U, d_layers=1, batch_norm=True, keep_prob=0.75, init_mse_weight=10.0, l2_scale=0.0,
+                     g_learning_rate=0.0, d_learning_rate=0.0, seed=4, dtype="f16", use_graph=graph)
+    m = GAN_RNN(None, args, ["/gpu:0"])
+    gp = perturb_bn(O.init_g_dnn(rng, in_dim=I, out_dim=40, units=U, hidden=1, batch_norm=True), rng)
+    dp = perturb_bn(O.init_d_dnn(rng, in_dim=40, units=U, hidden=1, batch_norm=True), rng)
+    m.load_params(tf32(gp), tf32(dp))
+    x = rng.standard_normal((B, T, I)).astype(np.float32)
+    y = rng.standard_normal((B, T, 40)).astype(np.float32)
+    ln = np.full(B, T)
+    xt, yt = x.transpose(1, 0, 2).astype(np.float64), y.transpose(1, 0, 2).astype(np.float64)   # library rows = t*B + b
+    st = O.GanState(gp, dp, "dnn", "dnn")
+    gbs, dbs = O.init_bn_state(gp), O.init_bn_state(dp)
+    if not graph:
+        gs = m._gscale(B * T)
+        for tick, which in enumerate("dg"):
+            go, do = dict(bn_state=copy.deepcopy(gbs)), dict(bn_state=copy.deepcopy(dbs), keep_prob=0.75, rng=(4, tick))
+            L, G, _ = O.tower_losses_and_grads(st, xt, yt, ln, which, g_opts=go, d_opts=do)
+            out = (m.d_step if which == "d" else m.g_step)(x, y, ln)
+            net, keys = (m.D, ("d_rl_loss", "d_fk_loss")) if which == "d" else (m.G, ("g_adv_loss", "g_mse_loss"))
+            for k in keys:
+                assert out[k] == pytest.approx(L[k], rel=3e-3, abs=1e-5), k
+            mine = net.P.export_tf("grad")
+            for k in G:
+                assert rel(mine[k] / gs, G[k]) < 5e-2, (which, k)
+        return
+    # three schedules through train_batch: the third replays the captured graph; the dropout stream advances 3 per schedule
+    outs = [m.train_batch(x, y, ln) for _ in range(4)]
+    torch.cuda.synchronize()
+    assert int(m.D.rng[1]) == 12
+    # learning rates are 0, so every schedule sees the same weights: losses differ only through the dropout masks of D
+    vals = [o["d_fk_loss"] for o in outs]
+    assert all(np.isfinite(v) for v in vals) and len(set(vals)) == len(vals)
+    for tick0, o in zip((0, 3, 6, 9), outs):
+        do = dict(bn_state=copy.deepcopy(dbs), keep_prob=0.75, rng=(4, tick0))
+        L, _, _ = O.tower_losses_and_grads(st, xt, yt, ln, "d", g_opts=dict(bn_state=copy.deepcopy(gbs)), d_opts=do)
+        assert o["d_rl_loss"] == pytest.approx(L["d_rl_loss"], rel=3e-3) and \
+            o["d_fk_loss"] == pytest.approx(L["d_fk_loss"], rel=3e-3, abs=1e-5)
