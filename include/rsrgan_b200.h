@@ -257,14 +257,16 @@ int rsr_conv_w_flip(rsr_handle* h, void* stream, const void* w16, int W, int Cin
  *   (models/dnn_trainer_single_gpu.py:101-104 runs them; models/gan_rnn_placeholder.py:169-175 does not).
  * rsr_bn_eval_coef (is_training=False): A = gamma rsqrt(moving_variance + eps), B = beta - moving_mean A.
  * rsr_affine_act_drop: out16 = dropout(act(z A + B)); A NULL = 1 (plain bias in B).  keep_prob >= 1: no dropout;
- *   otherwise element (r, c) is kept iff the top 24 bits of splitmix64(key ^ (r N + c)) < floor(keep_prob 2^24), with
- *   key = splitmix64(rng[0] + 0x9E3779B97F4A7C15 (rng[1] 65536 + salt)), and kept values are divided by keep_prob
- *   (tf.nn.dropout).  rng = device {seed, tick}; rsr_rng_tick advances tick (once per update), salt names the layer call.
+ *   otherwise one hash serves each (even, odd) column pair: with i = r N + c, h = splitmix64(key ^ (i >> 1)) and
+ *   key = splitmix64(rng[0] + 0x9E3779B97F4A7C15 (rng[1] 65536 + salt)), element (r, c) is kept iff
+ *   (c even ? h >> 40 : (h >> 16) & 0xffffff) < floor(keep_prob 2^24) (keep_prob as the float32 passed); kept values are
+ *   divided by keep_prob (tf.nn.dropout).  rng = device {seed, tick}; rsr_rng_tick advances tick (once per update), salt
+ *   names the layer call.
  * rsr_bn_bwd: da16 = gradient wrt the layer OUTPUT.  g = da act'(y) [kept / keep_prob];  dbeta += sum g;
  *   bn != 0: dgamma += r sum(g x_hat) + d sum(g),  dz = A (g - mean(g) - x_hat mean(g x_hat));   bn == 0 (bias + activation
  *   + dropout only; `bias` replaces coef): dz = g.  The mask is regenerated from the same (rng, salt).
  *   dgamma / dbeta / dz16 may be NULL. */
-#define RSR_BN_SCRATCH_FLOATS(N) (192LL * (N))
+#define RSR_BN_SCRATCH_FLOATS(N) (384LL * (N))
 int rsr_bn_train_stats(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,
                        const float* gamma, const float* beta, float eps, float* state, float momentum,
                        float renorm_momentum, int update_state, float* coef, float* scratch);

@@ -168,13 +168,20 @@ def _splitmix64(x):
 
 def dropout_mask(seed, tick, salt, rows, n, keep_prob):
     """The counter-based mask of rsr_affine_act_drop (include/rsrgan_b200.h): tf.nn.dropout keeps an element with
-    probability keep_prob and divides kept values by keep_prob (models/dnn.py:28-30); TF's own random stream
-    cannot be reproduced, so the mask generator is part of the C ABI and restated here bit-exactly."""
+    probability keep_prob and divides kept values by keep_prob (models/dnn.py:116-121); TF's own random stream
+    cannot be reproduced, so the mask generator is part of the C ABI and restated here bit-exactly.
+    One splitmix64 hash per (even, odd) column pair: element (r, c) with flat index i = r n + c uses
+    h = splitmix64(key ^ (i >> 1)), bits 63..40 for even c and bits 39..16 for odd c (n is even)."""
+    assert n % 2 == 0
     with np.errstate(over="ignore"):
         key = _splitmix64(_U64(seed) + _U64(0x9E3779B97F4A7C15) * (_U64(tick) * _U64(65536) + _U64(salt)))
-        idx = np.arange(rows * n, dtype=np.uint64).reshape(rows, n)
-        bits = (_splitmix64(key ^ idx) >> _U64(40)).astype(np.uint32)
-    return bits < np.uint32(int(keep_prob * 16777216.0))
+        pair = np.arange(rows * n // 2, dtype=np.uint64)
+        hsh = _splitmix64(key ^ pair)
+        bits = np.empty((rows * n // 2, 2), np.uint32)
+        bits[:, 0] = (hsh >> _U64(40)).astype(np.uint32)
+        bits[:, 1] = ((hsh >> _U64(16)) & _U64(0xffffff)).astype(np.uint32)
+    # the C ABI receives keep_prob as a float32: the threshold is floor(float32(keep_prob) * 2^24)
+    return bits.reshape(rows, n) < np.uint32(int(float(np.float32(keep_prob)) * 16777216.0))
 
 
 def fc_block_fwd(p, name, h, act, opts, salt):

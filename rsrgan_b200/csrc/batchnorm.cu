@@ -18,10 +18,12 @@ namespace {
 
 constexpr int BN_COLS = 128;     // columns per block (32 threads x float4)
 constexpr int BN_LANES = 8;      // row lanes per block
-constexpr int BN_MAX_SPLITS = 64;
+constexpr int BN_MAX_SPLITS = 128;   // RSR_BN_SCRATCH_FLOATS(N) = 3 * BN_MAX_SPLITS * N
+constexpr int FIN_COLS = 32;         // finish kernels: 32 columns x 16 split lanes per block
+constexpr int FIN_LANES = 16;
 
 __host__ __device__ inline int bn_splits(long long rows) {
-    long long s = rows / 64;
+    long long s = rows / 32;
     if (s < 1) s = 1;
     if (s > BN_MAX_SPLITS) s = BN_MAX_SPLITS;
     return (int)s;
@@ -37,8 +39,11 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 __device__ __forceinline__ uint64_t drop_key(const unsigned long long* rng, unsigned salt) {
     return splitmix64(rng[0] + 0x9E3779B97F4A7C15ull * (rng[1] * 65536ull + salt));
 }
-__device__ __forceinline__ bool drop_keep(uint64_t key, uint64_t idx, uint32_t thr24) {
-    return (uint32_t)(splitmix64(key ^ idx) >> 40) < thr24;
+// one hash serves the two elements of an (even, odd) column pair: bits 63..40 and bits 39..16
+__device__ __forceinline__ void drop_keep2(uint64_t key, uint64_t idx_even, uint32_t thr24, bool& k0, bool& k1) {
+    const uint64_t hsh = splitmix64(key ^ (idx_even >> 1));
+    k0 = (uint32_t)(hsh >> 40) < thr24;
+    k1 = ((uint32_t)(hsh >> 16) & 0xffffffu) < thr24;
 }
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -58,25 +63,45 @@ struct BnBwdIn {
     int act; uint32_t thr24; float inv_keep; const unsigned long long* rng; unsigned salt; int bf;
 };
 
+// per-thread column coefficients (4 consecutive columns), loaded once
+struct Col4 { float A[4], B[4], mean[4], istd[4]; };
+__device__ __forceinline__ Col4 load_col4(const BnBwdIn& p, int c) {
+    Col4 k;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        k.A[j] = p.A ? p.A[c + j] : 1.0f;
+        k.B[j] = p.Bc[c + j];
+        k.mean[j] = p.mean ? p.mean[c + j] : 0.0f;
+        k.istd[j] = p.mean ? p.inv_std[c + j] : 0.0f;
+    }
+    return k;
+}
+
 // gradient wrt the normalised value y = z A + B of 4 consecutive columns, and x_hat
-__device__ __forceinline__ void bwd_elem4(const BnBwdIn& p, const float4 z, long long r, int c, int N, uint64_t key,
-                                          float g[4], float xh[4]) {
-    const uint2 raw = *reinterpret_cast<const uint2*>(p.da + r * p.ldda + c);
+__device__ __forceinline__ void bwd_elem4(const BnBwdIn& p, const Col4& k, const float4 z, const uint2 raw, long long r,
+                                          int c, int N, uint64_t key, float g[4], float xh[4]) {
     const uint16_t hv[4] = {(uint16_t)(raw.x & 0xffff), (uint16_t)(raw.x >> 16), (uint16_t)(raw.y & 0xffff),
                             (uint16_t)(raw.y >> 16)};
     const float zz[4] = {z.x, z.y, z.z, z.w};
+    bool keep[4] = {true, true, true, true};
+    if (p.thr24 < (1u << 24)) {
+        const uint64_t idx = (uint64_t)r * (uint64_t)N + (uint64_t)c;
+        drop_keep2(key, idx, p.thr24, keep[0], keep[1]);
+        drop_keep2(key, idx + 2, p.thr24, keep[2], keep[3]);
+    }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float y = fmaf(zz[k], p.A ? p.A[c + k] : 1.0f, p.Bc[c + k]);
-        float gv = h2f(hv[k], p.bf) * act_slope(y, p.act);
-        if (p.thr24 < (1u << 24)) gv = drop_keep(key, (uint64_t)r * (uint64_t)N + (uint64_t)(c + k), p.thr24) ? gv * p.inv_keep : 0.0f;
-        g[k] = gv;
-        xh[k] = p.mean ? (zz[k] - p.mean[c + k]) * p.inv_std[c + k] : 0.0f;
+    for (int j = 0; j < 4; ++j) {
+        const float y = fmaf(zz[j], k.A[j], k.B[j]);
+        const float gv = h2f(hv[j], p.bf) * act_slope(y, p.act);
+        g[j] = keep[j] ? gv * p.inv_keep : 0.0f;
+        xh[j] = (zz[j] - k.mean[j]) * k.istd[j];
     }
 }
 
 // MODE 0: per-split (count, mean, M2) of z.   MODE 1: per-split (sum g, sum g x_hat).
 // grid (ceil(N / 128), splits), block (32, 8); partial layout [split][3 | 2][N]
+// MODE 0 uses shifted sums (shift = the first value the thread sees: no cancellation, no per-element division, no
+// dependency chain between the loads), converted to (n, mean, M2) per thread and merged pairwise (Chan) in a fixed order.
 template <int MODE>
 __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict__ z, int ldz, long long rows, int N,
                                                          BnBwdIn p, float* __restrict__ partial) {
@@ -88,24 +113,45 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict
     const long long r1 = r0 + chunk < rows ? r0 + chunk : rows;
     float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
     float n = 0.f;
-    uint64_t key = 0;
-    if (MODE == 1 && p.thr24 < (1u << 24)) key = drop_key(p.rng, p.salt);
     if (c < N) {
-        for (long long r = r0 + threadIdx.y; r < r1; r += BN_LANES) {
-            const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + c);
-            if (MODE == 0) {
-                n += 1.0f;
-                const float inv_n = 1.0f / n;
+        if (MODE == 0) {
+            float sh[4] = {0.f, 0.f, 0.f, 0.f};
+            const long long rf = r0 + threadIdx.y;
+            if (rf < r1) {
+                const float4 v = *reinterpret_cast<const float4*>(z + rf * ldz + c);
+                sh[0] = v.x; sh[1] = v.y; sh[2] = v.z; sh[3] = v.w;
+            }
+#pragma unroll 4
+            for (long long r = rf; r < r1; r += BN_LANES) {
+                const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + c);
                 const float vv[4] = {v.x, v.y, v.z, v.w};
+                n += 1.0f;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {          // Welford: a0 = running mean, a1 = M2
-                    const float d = vv[k] - a0[k];
-                    a0[k] += d * inv_n;
-                    a1[k] = fmaf(d, vv[k] - a0[k], a1[k]);
+                for (int k = 0; k < 4; ++k) {
+                    const float d = vv[k] - sh[k];
+                    a0[k] += d;
+                    a1[k] = fmaf(d, d, a1[k]);
                 }
-            } else {
+            }
+            if (n > 0.f) {
+                const float inv_n = 1.0f / n;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {          // -> a0 = mean, a1 = M2 of this thread's rows
+                    const float s = a0[k];
+                    a0[k] = sh[k] + s * inv_n;
+                    a1[k] = fmaxf(a1[k] - s * s * inv_n, 0.0f);
+                }
+            }
+        } else {
+            uint64_t key = 0;
+            if (p.thr24 < (1u << 24)) key = drop_key(p.rng, p.salt);
+            const Col4 k4 = load_col4(p, c);
+#pragma unroll 4
+            for (long long r = r0 + threadIdx.y; r < r1; r += BN_LANES) {
+                const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + c);
+                const uint2 raw = *reinterpret_cast<const uint2*>(p.da + r * p.ldda + c);
                 float g[4], xh[4];
-                bwd_elem4(p, v, r, c, N, key, g, xh);
+                bwd_elem4(p, k4, v, raw, r, c, N, key, g, xh);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { a0[k] += g[k]; a1[k] = fmaf(g[k], xh[k], a1[k]); }
             }
@@ -146,24 +192,57 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict
     }
 }
 
+// Merges the per-split partials of one column: block (32 columns, 16 split lanes); lane y merges splits y, y + 16, ...
+// in order, then lane 0 merges the 16 lane results in order -- coalesced loads, a chain of splits/16 + 16 merges
+// instead of `splits`, and still one fixed order (bit-identical across replicas).
+__device__ __forceinline__ void chan_merge(float& na, float& ma, float& qa, float nb, float mb, float qb) {
+    if (nb == 0.f) return;
+    const float nab = na + nb, d = mb - ma;
+    ma += d * (nb / nab);
+    qa += qb + d * d * (na * nb / nab);
+    na = nab;
+}
+__device__ __forceinline__ bool merge_moments(const float* __restrict__ partial, int splits, int N, int c, float& n,
+                                              float& m, float& q) {
+    __shared__ float sm[FIN_LANES][3][FIN_COLS];
+    float na = 0.f, ma = 0.f, qa = 0.f;
+    if (c < N)
+        for (int s = threadIdx.y; s < splits; s += FIN_LANES)
+            chan_merge(na, ma, qa, partial[((long long)s * 3 + 0) * N + c], partial[((long long)s * 3 + 1) * N + c],
+                       partial[((long long)s * 3 + 2) * N + c]);
+    sm[threadIdx.y][0][threadIdx.x] = na; sm[threadIdx.y][1][threadIdx.x] = ma; sm[threadIdx.y][2][threadIdx.x] = qa;
+    __syncthreads();
+    if (threadIdx.y != 0 || c >= N) return false;
+    for (int l = 1; l < FIN_LANES; ++l) chan_merge(na, ma, qa, sm[l][0][threadIdx.x], sm[l][1][threadIdx.x], sm[l][2][threadIdx.x]);
+    n = na; m = ma; q = qa;
+    return true;
+}
+__device__ __forceinline__ bool merge_sums(const float* __restrict__ partial, int splits, int N, int c, float& s1,
+                                           float& s2) {
+    __shared__ float sm[FIN_LANES][2][FIN_COLS];
+    float a = 0.f, b = 0.f;
+    if (c < N)
+        for (int s = threadIdx.y; s < splits; s += FIN_LANES) {
+            a += partial[((long long)s * 2 + 0) * N + c];
+            b += partial[((long long)s * 2 + 1) * N + c];
+        }
+    sm[threadIdx.y][0][threadIdx.x] = a; sm[threadIdx.y][1][threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.y != 0 || c >= N) return false;
+    for (int l = 1; l < FIN_LANES; ++l) { a += sm[l][0][threadIdx.x]; b += sm[l][1][threadIdx.x]; }
+    s1 = a; s2 = b;
+    return true;
+}
+
 // state rows: 0 moving_mean 1 moving_variance 2 renorm_mean 3 renorm_stddev 4 renorm_mean_weight 5 renorm_stddev_weight
 // coef  rows: 0 A = scale / stddev  1 B = offset - mean A  2 mean  3 1 / stddev  4 r  5 d  6 mean(g)  7 mean(g x_hat)
 __global__ void bn_finish_train_kernel(const float* __restrict__ partial, int splits, long long rows, int N,
                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                        float* __restrict__ state, float momentum, float renorm_momentum,
                                        int update_state, float* __restrict__ coef) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
-    float na = 0.f, ma = 0.f, qa = 0.f;
-    for (int s = 0; s < splits; ++s) {
-        const float nb = partial[((long long)s * 3 + 0) * N + c];
-        if (nb == 0.f) continue;
-        const float mb = partial[((long long)s * 3 + 1) * N + c], qb = partial[((long long)s * 3 + 2) * N + c];
-        const float nab = na + nb, d = mb - ma;
-        ma += d * (nb / nab);
-        qa += qb + d * d * (na * nb / nab);
-        na = nab;
-    }
+    const int c = blockIdx.x * FIN_COLS + threadIdx.x;
+    float na, ma, qa;
+    if (!merge_moments(partial, splits, N, c, na, ma, qa)) return;
     const float mean = ma, var = qa / (float)rows;
     const float stddev = sqrtf(var + eps);
     float* mm = state + 0 * (long long)N; float* mv = state + 1 * (long long)N;
@@ -208,28 +287,34 @@ __global__ void bn_eval_coef_kernel(int N, const float* __restrict__ gamma, cons
     coef[5 * (long long)N + c] = 0.0f;
 }
 
+// Every thread owns one group of 4 columns for the whole launch (the grid is sized so that the thread count is a
+// multiple of N / 4): coefficients live in registers, no per-element index division, rows advance by a constant.
 __global__ void __launch_bounds__(256) affine_act_drop_kernel(const float* __restrict__ z, int ldz, long long rows,
                                                               int N, const float* __restrict__ A,
                                                               const float* __restrict__ Bc, int act, uint32_t thr24,
                                                               float inv_keep, const unsigned long long* __restrict__ rng,
                                                               unsigned salt, uint16_t* __restrict__ out, int ldo, int bf) {
     const int n4 = N >> 2;
-    const long long total = rows * n4;
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long rstep = ((long long)gridDim.x * blockDim.x) / n4;
+    const int c = (int)(tid % n4) * 4;
     uint64_t key = 0;
     if (thr24 < (1u << 24)) key = drop_key(rng, salt);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / n4;
-        const int c = (int)(i - r * n4) * 4;
+    const float4 a = A ? *reinterpret_cast<const float4*>(A + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 b = *reinterpret_cast<const float4*>(Bc + c);
+#pragma unroll 4
+    for (long long r = tid / n4; r < rows; r += rstep) {
         const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + c);
-        const float4 a = A ? *reinterpret_cast<const float4*>(A + c) : make_float4(1.f, 1.f, 1.f, 1.f);
-        const float4 b = *reinterpret_cast<const float4*>(Bc + c);
         float y[4] = {fmaf(v.x, a.x, b.x), fmaf(v.y, a.y, b.y), fmaf(v.z, a.z, b.z), fmaf(v.w, a.w, b.w)};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            y[k] = act_apply(y[k], act);
-            if (thr24 < (1u << 24))
-                y[k] = drop_keep(key, (uint64_t)r * (uint64_t)N + (uint64_t)(c + k), thr24) ? y[k] * inv_keep : 0.0f;
+        for (int k = 0; k < 4; ++k) y[k] = act_apply(y[k], act);
+        if (thr24 < (1u << 24)) {
+            bool keep[4];
+            const uint64_t idx = (uint64_t)r * (uint64_t)N + (uint64_t)c;
+            drop_keep2(key, idx, thr24, keep[0], keep[1]);
+            drop_keep2(key, idx + 2, thr24, keep[2], keep[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) y[k] = keep[k] ? y[k] * inv_keep : 0.0f;
         }
         uint2 o;
         o.x = pack2(y[0], y[1], bf);
@@ -241,13 +326,9 @@ __global__ void __launch_bounds__(256) affine_act_drop_kernel(const float* __res
 // column totals of the backward partials; parameter gradients; means for the dz kernel
 __global__ void bn_bwd_finish_kernel(const float* __restrict__ partial, int splits, long long rows, int N, int bn,
                                      float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
-    float s1 = 0.f, s2 = 0.f;
-    for (int s = 0; s < splits; ++s) {
-        s1 += partial[((long long)s * 2 + 0) * N + c];
-        s2 += partial[((long long)s * 2 + 1) * N + c];
-    }
+    const int c = blockIdx.x * FIN_COLS + threadIdx.x;
+    float s1, s2;
+    if (!merge_sums(partial, splits, N, c, s1, s2)) return;
     if (bn) {
         // y = (x_hat r + d) gamma + beta with r, d under stop_gradient
         // atomics: the D(labels) and D(G(x)) backward passes of one update run on two streams (two addends: order-free)
@@ -263,19 +344,26 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ m2, uint16_t* __restrict__ dz,
                                                            int lddz) {
     const int n4 = N >> 2;
-    const long long total = rows * n4;
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long rstep = ((long long)gridDim.x * blockDim.x) / n4;
+    const int c = (int)(tid % n4) * 4;
     uint64_t key = 0;
     if (p.thr24 < (1u << 24)) key = drop_key(p.rng, p.salt);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / n4;
-        const int c = (int)(i - r * n4) * 4;
+    const Col4 k4 = load_col4(p, c);
+    float u1[4] = {0.f, 0.f, 0.f, 0.f}, u2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (bn) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { u1[k] = m1[c + k]; u2[k] = m2[c + k]; }
+    }
+#pragma unroll 4
+    for (long long r = tid / n4; r < rows; r += rstep) {
         const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + c);
+        const uint2 raw = *reinterpret_cast<const uint2*>(p.da + r * p.ldda + c);
         float g[4], xh[4];
-        bwd_elem4(p, v, r, c, N, key, g, xh);
+        bwd_elem4(p, k4, v, raw, r, c, N, key, g, xh);
         if (bn) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) g[k] = p.A[c + k] * (g[k] - m1[c + k] - xh[k] * m2[c + k]);
+            for (int k = 0; k < 4; ++k) g[k] = k4.A[k] * (g[k] - u1[k] - xh[k] * u2[k]);
         }
         uint2 o;
         o.x = pack2(g[0], g[1], p.bf);
@@ -293,11 +381,16 @@ inline uint32_t keep_threshold(float keep_prob) {
     return (uint32_t)t;
 }
 
-inline int ew_grid(long long items, int num_sms) {
-    long long blocks = (items + 255) / 256;
+inline long long gcd_ll(long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; }
+
+// blocks of 256 threads whose total is a multiple of n4 (= N / 4), about 8 per SM, at most one thread per item
+inline int ew_grid(long long rows, int n4, int num_sms) {
+    const long long unit = n4 / gcd_ll(n4, 256);            // blocks per whole number of rows
+    long long want = (rows * n4 + 255) / 256;
     const long long cap = (long long)num_sms * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
+    if (want > cap) want = cap;
+    long long blocks = (want + unit - 1) / unit * unit;
+    if (blocks < unit) blocks = unit;
     return (int)blocks;
 }
 
@@ -314,7 +407,7 @@ extern "C" int rsr_bn_train_stats(rsr_handle* h, void* stream, const float* z, i
     dim3 grid((N + BN_COLS - 1) / BN_COLS, splits), block(32, BN_LANES);
     bn_partial_kernel<0><<<grid, block, 0, st>>>(z, ldz, rows, N, none, scratch);
     RSR_LAUNCH_CHECK();
-    bn_finish_train_kernel<<<(N + 127) / 128, 128, 0, st>>>(scratch, splits, rows, N, gamma, beta, eps, state, momentum,
+    bn_finish_train_kernel<<<(N + FIN_COLS - 1) / FIN_COLS, dim3(FIN_COLS, FIN_LANES), 0, st>>>(scratch, splits, rows, N, gamma, beta, eps, state, momentum,
                                                             renorm_momentum, update_state, coef);
     RSR_LAUNCH_CHECK();
     return 0;
@@ -336,7 +429,7 @@ extern "C" int rsr_affine_act_drop(rsr_handle* h, void* stream, const float* z, 
     if (act != RSR_ACT_NONE && act != RSR_ACT_RELU && act != RSR_ACT_LRELU) return RSR_E_SHAPE;
     const uint32_t thr = keep_threshold(keep_prob);
     if (thr < (1u << 24) && (!rng || thr == 0)) return RSR_E_ARG;
-    affine_act_drop_kernel<<<ew_grid(rows * (N >> 2), h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+    affine_act_drop_kernel<<<ew_grid(rows, N >> 2, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
         z, ldz, rows, N, A, Bc, act, thr, thr < (1u << 24) ? 1.0f / keep_prob : 1.0f, rng, salt, (uint16_t*)out16, ld16,
         h->dtype == RSR_DTYPE_BF16);
     RSR_LAUNCH_CHECK();
@@ -365,11 +458,11 @@ extern "C" int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldd
         dim3 grid((N + BN_COLS - 1) / BN_COLS, splits), block(32, BN_LANES);
         bn_partial_kernel<1><<<grid, block, 0, st>>>(z, ldz, rows, N, p, scratch);
         RSR_LAUNCH_CHECK();
-        bn_bwd_finish_kernel<<<(N + 127) / 128, 128, 0, st>>>(scratch, splits, rows, N, bn, coef, dgamma, dbeta);
+        bn_bwd_finish_kernel<<<(N + FIN_COLS - 1) / FIN_COLS, dim3(FIN_COLS, FIN_LANES), 0, st>>>(scratch, splits, rows, N, bn, coef, dgamma, dbeta);
         RSR_LAUNCH_CHECK();
     }
     if (dz16) {
-        bn_bwd_apply_kernel<<<ew_grid(rows * (N >> 2), h->num_sms), 256, 0, st>>>(
+        bn_bwd_apply_kernel<<<ew_grid(rows, N >> 2, h->num_sms), 256, 0, st>>>(
             z, ldz, rows, N, p, bn, bn ? coef + 6ll * N : nullptr, bn ? coef + 7ll * N : nullptr, (uint16_t*)dz16, lddz);
         RSR_LAUNCH_CHECK();
     }

@@ -341,8 +341,9 @@ class FakeHandle(object):
         seed, tick = (int(v) & M for v in rng.tolist())
         with np.errstate(over="ignore"):
             key = sm(np.uint64((seed + 0x9E3779B97F4A7C15 * (tick * 65536 + salt)) & M))
-            bits = sm(key ^ np.arange(rows * N, dtype=np.uint64).reshape(rows, N)) >> np.uint64(40)
-        return torch.from_numpy((bits < np.uint64(int(keep_prob * 16777216.0))))
+            hsh = sm(key ^ np.arange(rows * N // 2, dtype=np.uint64))      # one hash per (even, odd) column pair
+            bits = np.stack([hsh >> np.uint64(40), (hsh >> np.uint64(16)) & np.uint64(0xffffff)], 1).reshape(rows, N)
+        return torch.from_numpy((bits < np.uint64(int(float(np.float32(keep_prob)) * 16777216.0))))
 
     def affine_act_drop(self, z32, rows, N, A, Bc, act, keep_prob, rng, salt, out16):
         self.launches += 1
