@@ -266,7 +266,7 @@ int rsr_conv_w_flip(rsr_handle* h, void* stream, const void* w16, int W, int Cin
  *   bn != 0: dgamma += r sum(g x_hat) + d sum(g),  dz = A (g - mean(g) - x_hat mean(g x_hat));   bn == 0 (bias + activation
  *   + dropout only; `bias` replaces coef): dz = g.  The mask is regenerated from the same (rng, salt).
  *   dgamma / dbeta / dz16 may be NULL. */
-#define RSR_BN_SCRATCH_FLOATS(N) (384LL * (N))
+#define RSR_BN_SCRATCH_FLOATS(N) (768LL * (N))
 int rsr_bn_train_stats(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,
                        const float* gamma, const float* beta, float eps, float* state, float momentum,
                        float renorm_momentum, int update_state, float* coef, float* scratch);

@@ -9,6 +9,8 @@
 //                   (2 x 6 + 2 B / element): column sums first, then dz
 // Reductions never use atomics: every column's partials are merged in one fixed order, so
 // data-parallel replicas that see the same rows produce bit-identical statistics.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "handle.h"
 
@@ -16,16 +18,26 @@ using namespace rsr;
 
 namespace {
 
-constexpr int BN_COLS = 128;     // columns per block (32 threads x float4)
-constexpr int BN_LANES = 8;      // row lanes per block
-constexpr int BN_MAX_SPLITS = 128;   // RSR_BN_SCRATCH_FLOATS(N) = 3 * BN_MAX_SPLITS * N
+// reduction kernels: 256-thread blocks of TX column groups (float4 each) x 256 / TX row lanes; a wider TX reads longer
+// contiguous runs of every row (TX * 16 bytes) at the price of more row splits to merge
+constexpr int BN_MAX_SPLITS = 256;   // RSR_BN_SCRATCH_FLOATS(N) = 3 * BN_MAX_SPLITS * N
 constexpr int FIN_COLS = 32;         // finish kernels: 32 columns x 16 split lanes per block
 constexpr int FIN_LANES = 16;
 
-__host__ __device__ inline int bn_splits(long long rows) {
-    long long s = rows / 32;
-    if (s < 1) s = 1;
+// Row splits of the two reduction kernels: one wave of 3 resident 256-thread blocks per SM over all column tiles
+// (fat blocks: no wave quantisation, few partials to merge), at least 8 rows per split.
+inline int bn_tx(int N) {
+    static const int forced = getenv("RSR_BN_TX") ? atoi(getenv("RSR_BN_TX")) : 0;      // tuning aid: 32 | 64 | 128
+    if (forced == 32 || forced == 64 || forced == 128) return forced;
+    return N >= 512 ? 64 : 32;
+}
+inline int bn_splits(long long rows, int N, int num_sms) {
+    const int cols = bn_tx(N) * 4;
+    const int tiles = (N + cols - 1) / cols;
+    long long s = (3LL * num_sms) / tiles;
+    if (s > rows / 8) s = rows / 8;
     if (s > BN_MAX_SPLITS) s = BN_MAX_SPLITS;
+    if (s < 1) s = 1;
     return (int)s;
 }
 
@@ -99,12 +111,13 @@ __device__ __forceinline__ void bwd_elem4(const BnBwdIn& p, const Col4& k, const
 }
 
 // MODE 0: per-split (count, mean, M2) of z.   MODE 1: per-split (sum g, sum g x_hat).
-// grid (ceil(N / 128), splits), block (32, 8); partial layout [split][3 | 2][N]
+// grid (ceil(N / (4 TX)), splits), block (TX, 256 / TX); partial layout [split][3 | 2][N]
 // MODE 0 uses shifted sums (shift = the first value the thread sees: no cancellation, no per-element division, no
 // dependency chain between the loads), converted to (n, mean, M2) per thread and merged pairwise (Chan) in a fixed order.
-template <int MODE>
+template <int MODE, int TX>
 __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict__ z, int ldz, long long rows, int N,
                                                          BnBwdIn p, float* __restrict__ partial) {
+    constexpr int BN_COLS = TX * 4, BN_LANES = 256 / TX;
     __shared__ float sm[BN_LANES][3][BN_COLS];
     const int c = blockIdx.x * BN_COLS + threadIdx.x * 4;
     const int splits = gridDim.y;
@@ -121,9 +134,7 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict
                 const float4 v = *reinterpret_cast<const float4*>(z + rf * ldz + c);
                 sh[0] = v.x; sh[1] = v.y; sh[2] = v.z; sh[3] = v.w;
             }
-#pragma unroll 4
-            for (long long r = rf; r < r1; r += BN_LANES) {
-                const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + c);
+            auto acc = [&](const float4 v) {
                 const float vv[4] = {v.x, v.y, v.z, v.w};
                 n += 1.0f;
 #pragma unroll
@@ -132,7 +143,16 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict
                     a0[k] += d;
                     a1[k] = fmaf(d, d, a1[k]);
                 }
+            };
+            long long r = rf;
+            for (; r + 3 * BN_LANES < r1; r += 4 * BN_LANES) {       // four independent 16-byte loads in flight
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(z + (r + u * BN_LANES) * ldz + c);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc(v[u]);
             }
+            for (; r < r1; r += BN_LANES) acc(*reinterpret_cast<const float4*>(z + r * ldz + c));
             if (n > 0.f) {
                 const float inv_n = 1.0f / n;
 #pragma unroll
@@ -146,8 +166,24 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict
             uint64_t key = 0;
             if (p.thr24 < (1u << 24)) key = drop_key(p.rng, p.salt);
             const Col4 k4 = load_col4(p, c);
-#pragma unroll 4
-            for (long long r = r0 + threadIdx.y; r < r1; r += BN_LANES) {
+            long long r = r0 + threadIdx.y;
+            for (; r + BN_LANES < r1; r += 2 * BN_LANES) {           // two rows (4 loads) in flight
+                float4 v[2];
+                uint2 raw[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    v[u] = *reinterpret_cast<const float4*>(z + (r + u * BN_LANES) * ldz + c);
+                    raw[u] = *reinterpret_cast<const uint2*>(p.da + (r + u * BN_LANES) * p.ldda + c);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    float g[4], xh[4];
+                    bwd_elem4(p, k4, v[u], raw[u], r + u * BN_LANES, c, N, key, g, xh);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { a0[k] += g[k]; a1[k] = fmaf(g[k], xh[k], a1[k]); }
+                }
+            }
+            for (; r < r1; r += BN_LANES) {
                 const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + c);
                 const uint2 raw = *reinterpret_cast<const uint2*>(p.da + r * p.ldda + c);
                 float g[4], xh[4];
@@ -202,14 +238,22 @@ __device__ __forceinline__ void chan_merge(float& na, float& ma, float& qa, floa
     qa += qb + d * d * (na * nb / nab);
     na = nab;
 }
+constexpr int FIN_PER_LANE = BN_MAX_SPLITS / FIN_LANES;
 __device__ __forceinline__ bool merge_moments(const float* __restrict__ partial, int splits, int N, int c, float& n,
                                               float& m, float& q) {
     __shared__ float sm[FIN_LANES][3][FIN_COLS];
+    float pn[FIN_PER_LANE], pm[FIN_PER_LANE], pq[FIN_PER_LANE];
+#pragma unroll
+    for (int i = 0; i < FIN_PER_LANE; ++i) {               // every load in flight before the first merge
+        const int s = threadIdx.y + i * FIN_LANES;
+        const bool ok = c < N && s < splits;
+        pn[i] = ok ? partial[((long long)s * 3 + 0) * N + c] : 0.f;
+        pm[i] = ok ? partial[((long long)s * 3 + 1) * N + c] : 0.f;
+        pq[i] = ok ? partial[((long long)s * 3 + 2) * N + c] : 0.f;
+    }
     float na = 0.f, ma = 0.f, qa = 0.f;
-    if (c < N)
-        for (int s = threadIdx.y; s < splits; s += FIN_LANES)
-            chan_merge(na, ma, qa, partial[((long long)s * 3 + 0) * N + c], partial[((long long)s * 3 + 1) * N + c],
-                       partial[((long long)s * 3 + 2) * N + c]);
+#pragma unroll
+    for (int i = 0; i < FIN_PER_LANE; ++i) chan_merge(na, ma, qa, pn[i], pm[i], pq[i]);
     sm[threadIdx.y][0][threadIdx.x] = na; sm[threadIdx.y][1][threadIdx.x] = ma; sm[threadIdx.y][2][threadIdx.x] = qa;
     __syncthreads();
     if (threadIdx.y != 0 || c >= N) return false;
@@ -220,12 +264,17 @@ __device__ __forceinline__ bool merge_moments(const float* __restrict__ partial,
 __device__ __forceinline__ bool merge_sums(const float* __restrict__ partial, int splits, int N, int c, float& s1,
                                            float& s2) {
     __shared__ float sm[FIN_LANES][2][FIN_COLS];
+    float pa[FIN_PER_LANE], pb[FIN_PER_LANE];
+#pragma unroll
+    for (int i = 0; i < FIN_PER_LANE; ++i) {
+        const int s = threadIdx.y + i * FIN_LANES;
+        const bool ok = c < N && s < splits;
+        pa[i] = ok ? partial[((long long)s * 2 + 0) * N + c] : 0.f;
+        pb[i] = ok ? partial[((long long)s * 2 + 1) * N + c] : 0.f;
+    }
     float a = 0.f, b = 0.f;
-    if (c < N)
-        for (int s = threadIdx.y; s < splits; s += FIN_LANES) {
-            a += partial[((long long)s * 2 + 0) * N + c];
-            b += partial[((long long)s * 2 + 1) * N + c];
-        }
+#pragma unroll
+    for (int i = 0; i < FIN_PER_LANE; ++i) { a += pa[i]; b += pb[i]; }
     sm[threadIdx.y][0][threadIdx.x] = a; sm[threadIdx.y][1][threadIdx.x] = b;
     __syncthreads();
     if (threadIdx.y != 0 || c >= N) return false;
@@ -374,6 +423,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 
 __global__ void rng_tick_kernel(unsigned long long* rng) { rng[1] += 1ull; }
 
+template <int MODE>
+void launch_partial(int tx, int splits, cudaStream_t st, const float* z, int ldz, long long rows, int N,
+                    const BnBwdIn& p, float* scratch) {
+    const dim3 grid((N + tx * 4 - 1) / (tx * 4), splits), block(tx, 256 / tx);
+    if (tx == 128) bn_partial_kernel<MODE, 128><<<grid, block, 0, st>>>(z, ldz, rows, N, p, scratch);
+    else if (tx == 64) bn_partial_kernel<MODE, 64><<<grid, block, 0, st>>>(z, ldz, rows, N, p, scratch);
+    else bn_partial_kernel<MODE, 32><<<grid, block, 0, st>>>(z, ldz, rows, N, p, scratch);
+}
+
 inline uint32_t keep_threshold(float keep_prob) {
     if (!(keep_prob < 1.0f)) return 1u << 24;
     double t = (double)keep_prob * 16777216.0;
@@ -402,10 +460,9 @@ extern "C" int rsr_bn_train_stats(rsr_handle* h, void* stream, const float* z, i
     if (!h || !z || !gamma || !beta || !state || !coef || !scratch || rows <= 0 || N <= 0) return RSR_E_ARG;
     if ((N & 3) || (ldz & 3)) return RSR_E_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
-    const int splits = bn_splits(rows);
+    const int splits = bn_splits(rows, N, h->num_sms);
     BnBwdIn none = {};
-    dim3 grid((N + BN_COLS - 1) / BN_COLS, splits), block(32, BN_LANES);
-    bn_partial_kernel<0><<<grid, block, 0, st>>>(z, ldz, rows, N, none, scratch);
+    launch_partial<0>(bn_tx(N), splits, st, z, ldz, rows, N, none, scratch);
     RSR_LAUNCH_CHECK();
     bn_finish_train_kernel<<<(N + FIN_COLS - 1) / FIN_COLS, dim3(FIN_COLS, FIN_LANES), 0, st>>>(scratch, splits, rows, N, gamma, beta, eps, state, momentum,
                                                             renorm_momentum, update_state, coef);
@@ -453,10 +510,9 @@ extern "C" int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldd
     else { p.A = nullptr; p.Bc = bias; p.mean = nullptr; p.inv_std = nullptr; }
     p.act = act; p.thr24 = thr; p.inv_keep = thr < (1u << 24) ? 1.0f / keep_prob : 1.0f; p.rng = rng; p.salt = salt;
     p.bf = h->dtype == RSR_DTYPE_BF16;
-    const int splits = bn_splits(rows);
+    const int splits = bn_splits(rows, N, h->num_sms);
     if (bn || dbeta) {
-        dim3 grid((N + BN_COLS - 1) / BN_COLS, splits), block(32, BN_LANES);
-        bn_partial_kernel<1><<<grid, block, 0, st>>>(z, ldz, rows, N, p, scratch);
+        launch_partial<1>(bn_tx(N), splits, st, z, ldz, rows, N, p, scratch);
         RSR_LAUNCH_CHECK();
         bn_bwd_finish_kernel<<<(N + FIN_COLS - 1) / FIN_COLS, dim3(FIN_COLS, FIN_LANES), 0, st>>>(scratch, splits, rows, N, bn, coef, dgamma, dbeta);
         RSR_LAUNCH_CHECK();

@@ -130,7 +130,7 @@ class FCBN(FC):
         ws = self.net.ws
         return (ws.get((ctx, self.scope, "z32"), rows, self.outp, F32),
                 ws.get((ctx, self.scope, "bn_coef"), 8, self.outp, F32),
-                ws.get((ctx, self.scope, "bn_scratch"), 384, self.outp, F32))
+                ws.get((ctx, self.scope, "bn_scratch"), 768, self.outp, F32))
 
     def fwd(self, ctx, x16, rows, want16=True, want32=False):
         net, h = self.net, self.net.h

@@ -31,7 +31,7 @@ for _ in range(SETS):
                      da=(0.1 * torch.randn(rows, N, device=dev, generator=g)).half(),
                      out=torch.zeros(rows, N, dtype=torch.float16, device=dev),
                      dz=torch.zeros(rows, N, dtype=torch.float16, device=dev),
-                     coef=torch.zeros(8, N, device=dev), scratch=torch.zeros(384, N, device=dev),
+                     coef=torch.zeros(8, N, device=dev), scratch=torch.zeros(768, N, device=dev),
                      state=torch.zeros(6, N, device=dev)))
 gamma, beta = torch.ones(N, device=dev), torch.zeros(N, device=dev)
 dgam, dbet = torch.zeros(N, device=dev), torch.zeros(N, device=dev)

@@ -65,7 +65,7 @@ def test_bn_train_stats_and_state(h, rows, N, update):
     zt[:, :N] = torch.tensor(z)
     state = torch.tensor(state_arrays(st, N), device=dev)
     coef = torch.zeros(8, N, dtype=F32, device=dev)
-    scratch = torch.zeros(384, N, dtype=F32, device=dev)
+    scratch = torch.zeros(768, N, dtype=F32, device=dev)
     h.bn_train_stats(zt, rows, N, torch.tensor(gamma, device=dev), torch.tensor(beta, device=dev), state, coef, scratch,
                      update_state=update)
     torch.cuda.synchronize()
@@ -145,7 +145,7 @@ def test_bn_backward(h, rows, N, bn, act, keep):
     zt = torch.tensor(z, device=dev)
     gam_t, bet_t = torch.tensor(gamma, device=dev), torch.tensor(beta, device=dev)
     coef = torch.zeros(8, N, dtype=F32, device=dev)
-    scratch = torch.zeros(384, N, dtype=F32, device=dev)
+    scratch = torch.zeros(768, N, dtype=F32, device=dev)
     da = (rng.standard_normal((rows, N)) * 0.1).astype(np.float32)
     da16 = torch.tensor(da, device=dev).to(h.h16)
     da_r = da16.double().cpu().numpy()                 # the 16-bit values the kernel actually reads
@@ -191,7 +191,7 @@ def test_bn_shape_errors(h):
     v = torch.zeros(16, dtype=F32, device=dev)
     with pytest.raises(RsrError, match="RSR_E_SHAPE"):           # N not a multiple of 4
         h.bn_train_stats(z, 8, 10, v, v, torch.zeros(6, 10, device=dev), torch.zeros(8, 10, device=dev),
-                         torch.zeros(384, 10, device=dev))
+                         torch.zeros(768, 10, device=dev))
     with pytest.raises(RsrError, match="RSR_E_ARG"):             # dropout without a stream
         h.affine_act_drop(torch.zeros(8, 8, device=dev), 8, 8, None, v, 1, 0.5, None, 0,
                           torch.zeros(8, 8, dtype=h.h16, device=dev))
