@@ -256,7 +256,9 @@ int rsr_conv_w_flip(rsr_handle* h, void* stream, const void* w16, int W, int Cin
  *   renorm_momentum, then moving_mean / moving_variance with `momentum` towards the de-biased renorm values
  *   (models/dnn_trainer_single_gpu.py:101-104 runs them; models/gan_rnn_placeholder.py:169-175 does not).
  * rsr_bn_eval_coef (is_training=False): A = gamma rsqrt(moving_variance + eps), B = beta - moving_mean A.
- * rsr_affine_act_drop: out16 = dropout(act(z A + B)); A NULL = 1 (plain bias in B).  keep_prob >= 1: no dropout;
+ * rsr_affine_act_drop: out16 / out32 (either may be NULL) = dropout(act(z A + B)); A NULL = 1 (plain bias in B).  With
+ *   A NULL, B = 0 and no activation it is tf.contrib.rnn.DropoutWrapper(output_keep_prob) on an LSTM layer's output
+ *   (models/lstm.py:99-102, models/res_lstm_l.py:96-99), and rsr_bn_bwd(bn = 0) its gradient.  keep_prob >= 1: no dropout;
  *   otherwise one hash serves each (even, odd) column pair: with i = r N + c, h = splitmix64(key ^ (i >> 1)) and
  *   key = splitmix64(rng[0] + 0x9E3779B97F4A7C15 (rng[1] 65536 + salt)), element (r, c) is kept iff
  *   (c even ? h >> 40 : (h >> 16) & 0xffffff) < floor(keep_prob 2^24) (keep_prob as the float32 passed); kept values are
@@ -265,7 +267,7 @@ int rsr_conv_w_flip(rsr_handle* h, void* stream, const void* w16, int W, int Cin
  * rsr_bn_bwd: da16 = gradient wrt the layer OUTPUT.  g = da act'(y) [kept / keep_prob];  dbeta += sum g;
  *   bn != 0: dgamma += r sum(g x_hat) + d sum(g),  dz = A (g - mean(g) - x_hat mean(g x_hat));   bn == 0 (bias + activation
  *   + dropout only; `bias` replaces coef): dz = g.  The mask is regenerated from the same (rng, salt).
- *   dgamma / dbeta / dz16 may be NULL. */
+ *   dgamma / dbeta / dz16 / dz32 (an fp32 copy of dz) may be NULL. */
 #define RSR_BN_SCRATCH_FLOATS(N) (768LL * (N))
 int rsr_bn_train_stats(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,
                        const float* gamma, const float* beta, float eps, float* state, float momentum,
@@ -274,11 +276,11 @@ int rsr_bn_eval_coef(rsr_handle* h, void* stream, int N, const float* gamma, con
                      const float* state, float* coef);
 int rsr_affine_act_drop(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,
                         const float* A, const float* Bc, int act, float keep_prob,
-                        const unsigned long long* rng, unsigned salt, void* out16, int ld16);
+                        const unsigned long long* rng, unsigned salt, void* out16, int ld16, float* out32, int ld32);
 int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldda, const float* z, int ldz,
                long long rows, int N, int act, float keep_prob, const unsigned long long* rng, unsigned salt,
                int bn, float* coef, const float* bias, float* dgamma, float* dbeta, void* dz16, int lddz,
-               float* scratch);
+               float* dz32, int lddz32, float* scratch);
 int rsr_rng_tick(rsr_handle* h, void* stream, unsigned long long* rng);
 
 /* misc ---------------------------------------------------------------------------------- */

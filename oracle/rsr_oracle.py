@@ -209,10 +209,37 @@ def fc_block_fwd(p, name, h, act, opts, salt):
     mask = None
     if keep < 1.0:
         seed, tick = opts["rng"]
-        lead = a.shape[:-1]
-        mask = dropout_mask(seed, tick, salt, int(np.prod(lead)), a.shape[-1], keep).reshape(a.shape)
+        rows, n = int(np.prod(a.shape[:-1])), a.shape[-1]
+        # the library's rows are the flattened leading axes IN THE ORDER GIVEN (feed time-major data to match its
+        # t*B+b rows) and its row pitch is the width padded to a multiple of 8
+        mask = dropout_mask(seed, tick, salt, rows, -(-n // 8) * 8, keep)[:, :n].reshape(a.shape)
         a = np.where(mask, a / keep, 0.0)
     return a, (h, W, y, act, bc, mask, keep)
+
+
+def seq_dropout_fwd(a, opts, salt):
+    """tf.contrib.rnn.DropoutWrapper(cell, output_keep_prob=keep_prob) (models/lstm.py:99-102, models/res_lstm_l.py:
+    96-99): the layer OUTPUT handed to the next layer is dropped, the recurrent state is not.  a: (B, T, P) batch-major;
+    the mask is drawn in the library's layout -- time-major rows t*B+b, row pitch P padded to a multiple of 8."""
+    opts = opts or {}
+    keep = opts.get("keep_prob", 1.0) if opts.get("train", True) else 1.0
+    if keep >= 1.0:
+        return a, None
+    B, T, P = a.shape
+    seed, tick = opts["rng"]
+    Pp = -(-P // 8) * 8
+    m = dropout_mask(seed, tick, salt, T * B, Pp, keep).reshape(T, B, Pp)[:, :, :P].transpose(1, 0, 2)
+    return np.where(m, a / keep, 0.0), (m, keep)
+
+
+def seq_dropout_bwd(da, cache):
+    if cache is None:
+        return da
+    m, keep = cache
+    return np.where(m, da / keep, 0.0)
+
+
+LSTM_SALT = 16       # dropout stream of LSTM layer l of a generator: salt0 + LSTM_SALT + l
 
 
 def fc_block_bwd(da, cache, name, g):
@@ -513,16 +540,17 @@ def _cell_prefixes(p, scope):
     return pre
 
 
-def g_lstm_fwd(p, x, lengths):
-    """models/lstm.py:82-124: FC(leakyrelu .3) -> stacked LSTMP -> FC(linear).
+def g_lstm_fwd(p, x, lengths, opts=None, salt0=0):
+    """models/lstm.py:82-124: FC(leakyrelu .3) [batch_norm(renorm) when built with it, :61-67,84-85] -> stacked LSTMP
+    [DropoutWrapper on every layer's output when training with keep_prob < 1, :99-102] -> FC(linear).
     MultiRNNCell per-timestep stacking == layer-after-layer over the sequence."""
     caches = []
-    h, c0 = linear_fwd(x, p["g_model/fully_connected/weights"],
-                       p["g_model/fully_connected/biases"], ACT_LRELU)
+    h, c0 = fc_block_fwd(p, "g_model/fully_connected", x, ACT_LRELU, dict(opts or {}, keep_prob=1.0), salt0)
     caches.append(c0)
-    for pre in _cell_prefixes(p, "g_model/rnn/"):
+    for l, pre in enumerate(_cell_prefixes(p, "g_model/rnn/")):
         h, cc = lstmp_fwd(h, lengths, *_cell_params(p, pre))
-        caches.append(cc)
+        h, dc = seq_dropout_fwd(h, opts, salt0 + LSTM_SALT + l)
+        caches.append((cc, dc))
     y, c1 = linear_fwd(h, p["g_model/fully_connected_1/weights"],
                        p["g_model/fully_connected_1/biases"], ACT_NONE)
     caches.append(c1)
@@ -536,23 +564,24 @@ def g_lstm_bwd(p, dy, caches):
     g["g_model/fully_connected_1/biases"] = db
     pres = _cell_prefixes(p, "g_model/rnn/")
     for l in range(len(pres) - 1, -1, -1):
-        dh, cg = lstmp_bwd(dh, caches[1 + l])
+        cc, dc = caches[1 + l]
+        dh, cg = lstmp_bwd(seq_dropout_bwd(dh, dc), cc)
         _cell_grads(g, pres[l], cg)
-    dx, dW, db = linear_bwd(dh, caches[0])
-    g["g_model/fully_connected/weights"] = dW
-    g["g_model/fully_connected/biases"] = db
+    dx = fc_block_bwd(dh, caches[0], "g_model/fully_connected", g)
     return dx, g
 
 
-def g_res_lstm_l_fwd(p, x, lengths, residual=True):
+def g_res_lstm_l_fwd(p, x, lengths, residual=True, opts=None, salt0=0):
     """models/res_lstm_l.py:101-138,187-194: x_{l+1} = LSTMP_l(x_l) + x_l,
-    y = FC(out_L + x_L).  residual=False is models/res_lstm_base.py:111-131,190."""
+    y = FC(out_L + x_L).  residual=False is models/res_lstm_base.py:111-131,190.  Each of the four cells is wrapped
+    in DropoutWrapper(output_keep_prob) when training with keep_prob < 1 (:96-99): the dropped output enters the sum."""
     caches = []
     xin = x
     pres = _cell_prefixes(p, "g_model/lstm_cell_")
-    for pre in pres:
+    for l, pre in enumerate(pres):
         o, cc = lstmp_fwd(xin, lengths, *_cell_params(p, pre))
-        caches.append(cc)
+        o, dc = seq_dropout_fwd(o, opts, salt0 + LSTM_SALT + l)
+        caches.append((cc, dc))
         xin = o + xin if residual else o
     y, c1 = linear_fwd(xin, p["g_model/forward_out/fully_connected/weights"],
                        p["g_model/forward_out/fully_connected/biases"], ACT_NONE)
@@ -567,7 +596,8 @@ def g_res_lstm_l_bwd(p, dy, caches, residual=True):
     g["g_model/forward_out/fully_connected/biases"] = db
     pres = _cell_prefixes(p, "g_model/lstm_cell_")
     for l in range(len(pres) - 1, -1, -1):
-        dprev, cg = lstmp_bwd(dxin, caches[l])
+        cc, dc = caches[l]
+        dprev, cg = lstmp_bwd(seq_dropout_bwd(dxin, dc), cc)
         _cell_grads(g, pres[l], cg)
         dxin = dprev + dxin if residual else dprev
     return dxin, g
@@ -698,7 +728,7 @@ GENERATORS = {
     "rced": (g_rced_fwd, g_rced_bwd),
     "lstm": (g_lstm_fwd, g_lstm_bwd),
     "res_lstm_l": (g_res_lstm_l_fwd, g_res_lstm_l_bwd),
-    "res_lstm_base": (lambda p, x, l: g_res_lstm_l_fwd(p, x, l, False),
+    "res_lstm_base": (lambda p, x, l, **kw: g_res_lstm_l_fwd(p, x, l, False, **kw),
                       lambda p, dy, c: g_res_lstm_l_bwd(p, dy, c, False)),
 }
 DISCRIMINATORS = {

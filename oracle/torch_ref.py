@@ -54,17 +54,31 @@ def lrelu(x):
     return torch.maximum(x, 0.3 * x)
 
 
-def g_lstm(p, x, lengths):
-    h = lrelu(x @ p["g_model/fully_connected/weights"] + p["g_model/fully_connected/biases"])
-    for pre in _cells(p, "g_model/rnn/"):
-        h = _cell(p, pre, h, lengths)
+def _seq_drop(a, opts, salt):
+    """DropoutWrapper(output_keep_prob): mask drawn in the library layout (time-major rows, padded pitch)."""
+    from . import rsr_oracle as O
+    opts = opts or {}
+    keep = opts.get("keep_prob", 1.0) if opts.get("train", True) else 1.0
+    if keep >= 1.0:
+        return a
+    B, T, P = a.shape
+    Pp = -(-P // 8) * 8
+    seed, tick = opts["rng"]
+    m = O.dropout_mask(seed, tick, salt, T * B, Pp, keep).reshape(T, B, Pp)[:, :, :P].transpose(1, 0, 2)
+    return torch.where(torch.as_tensor(m.copy()), a / keep, torch.zeros_like(a))
+
+
+def g_lstm(p, x, lengths, opts=None, salt0=0):
+    h = _fc_block(p, "g_model/fully_connected", x, lrelu, dict(opts or {}, keep_prob=1.0), salt0)
+    for l, pre in enumerate(_cells(p, "g_model/rnn/")):
+        h = _seq_drop(_cell(p, pre, h, lengths), opts, salt0 + 16 + l)
     return h @ p["g_model/fully_connected_1/weights"] + p["g_model/fully_connected_1/biases"]
 
 
-def g_res_lstm_l(p, x, lengths, residual=True):
+def g_res_lstm_l(p, x, lengths, residual=True, opts=None, salt0=0):
     xin = x
-    for pre in _cells(p, "g_model/lstm_cell_"):
-        o = _cell(p, pre, xin, lengths)
+    for l, pre in enumerate(_cells(p, "g_model/lstm_cell_")):
+        o = _seq_drop(_cell(p, pre, xin, lengths), opts, salt0 + 16 + l)
         xin = o + xin if residual else o
     return xin @ p["g_model/forward_out/fully_connected/weights"] + \
         p["g_model/forward_out/fully_connected/biases"]
@@ -158,7 +172,7 @@ def g_rced(p, x, lengths=None):
 
 
 GEN = {"lstm": g_lstm, "res_lstm_l": g_res_lstm_l, "dnn": g_dnn, "rced": g_rced,
-       "res_lstm_base": lambda p, x, l: g_res_lstm_l(p, x, l, False)}
+       "res_lstm_base": lambda p, x, l, **kw: g_res_lstm_l(p, x, l, False, **kw)}
 DIS = {"lstm": d_lstm, "dnn": d_dnn}
 
 

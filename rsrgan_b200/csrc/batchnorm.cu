@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(256) affine_act_drop_kernel(const float* __res
                                                               int N, const float* __restrict__ A,
                                                               const float* __restrict__ Bc, int act, uint32_t thr24,
                                                               float inv_keep, const unsigned long long* __restrict__ rng,
-                                                              unsigned salt, uint16_t* __restrict__ out, int ldo, int bf) {
+                                                              unsigned salt, uint16_t* __restrict__ out, int ldo,
+                                                              float* __restrict__ out32, int ldo32, int bf) {
     const int n4 = N >> 2;
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long rstep = ((long long)gridDim.x * blockDim.x) / n4;
@@ -365,10 +366,13 @@ __global__ void __launch_bounds__(256) affine_act_drop_kernel(const float* __res
 #pragma unroll
             for (int k = 0; k < 4; ++k) y[k] = keep[k] ? y[k] * inv_keep : 0.0f;
         }
-        uint2 o;
-        o.x = pack2(y[0], y[1], bf);
-        o.y = pack2(y[2], y[3], bf);
-        *reinterpret_cast<uint2*>(out + r * ldo + c) = o;
+        if (out) {
+            uint2 o;
+            o.x = pack2(y[0], y[1], bf);
+            o.y = pack2(y[2], y[3], bf);
+            *reinterpret_cast<uint2*>(out + r * ldo + c) = o;
+        }
+        if (out32) *reinterpret_cast<float4*>(out32 + r * ldo32 + c) = make_float4(y[0], y[1], y[2], y[3]);
     }
 }
 
@@ -391,7 +395,7 @@ __global__ void bn_bwd_finish_kernel(const float* __restrict__ partial, int spli
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ z, int ldz, long long rows, int N,
                                                            BnBwdIn p, int bn, const float* __restrict__ m1,
                                                            const float* __restrict__ m2, uint16_t* __restrict__ dz,
-                                                           int lddz) {
+                                                           int lddz, float* __restrict__ dz32, int lddz32) {
     const int n4 = N >> 2;
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long rstep = ((long long)gridDim.x * blockDim.x) / n4;
@@ -414,10 +418,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 #pragma unroll
             for (int k = 0; k < 4; ++k) g[k] = k4.A[k] * (g[k] - u1[k] - xh[k] * u2[k]);
         }
-        uint2 o;
-        o.x = pack2(g[0], g[1], p.bf);
-        o.y = pack2(g[2], g[3], p.bf);
-        *reinterpret_cast<uint2*>(dz + r * lddz + c) = o;
+        if (dz) {
+            uint2 o;
+            o.x = pack2(g[0], g[1], p.bf);
+            o.y = pack2(g[2], g[3], p.bf);
+            *reinterpret_cast<uint2*>(dz + r * lddz + c) = o;
+        }
+        if (dz32) *reinterpret_cast<float4*>(dz32 + r * lddz32 + c) = make_float4(g[0], g[1], g[2], g[3]);
     }
 }
 
@@ -480,15 +487,16 @@ extern "C" int rsr_bn_eval_coef(rsr_handle* h, void* stream, int N, const float*
 
 extern "C" int rsr_affine_act_drop(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,
                                    const float* A, const float* Bc, int act, float keep_prob,
-                                   const unsigned long long* rng, unsigned salt, void* out16, int ld16) {
-    if (!h || !z || !Bc || !out16 || rows <= 0 || N <= 0) return RSR_E_ARG;
-    if ((N & 3) || (ldz & 3) || (ld16 & 3)) return RSR_E_SHAPE;
+                                   const unsigned long long* rng, unsigned salt, void* out16, int ld16, float* out32,
+                                   int ld32) {
+    if (!h || !z || !Bc || (!out16 && !out32) || rows <= 0 || N <= 0) return RSR_E_ARG;
+    if ((N & 3) || (ldz & 3) || (out16 && (ld16 & 3)) || (out32 && (ld32 & 3))) return RSR_E_SHAPE;
     if (act != RSR_ACT_NONE && act != RSR_ACT_RELU && act != RSR_ACT_LRELU) return RSR_E_SHAPE;
     const uint32_t thr = keep_threshold(keep_prob);
     if (thr < (1u << 24) && (!rng || thr == 0)) return RSR_E_ARG;
     affine_act_drop_kernel<<<ew_grid(rows, N >> 2, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
         z, ldz, rows, N, A, Bc, act, thr, thr < (1u << 24) ? 1.0f / keep_prob : 1.0f, rng, salt, (uint16_t*)out16, ld16,
-        h->dtype == RSR_DTYPE_BF16);
+        out32, ld32, h->dtype == RSR_DTYPE_BF16);
     RSR_LAUNCH_CHECK();
     return 0;
 }
@@ -496,10 +504,10 @@ extern "C" int rsr_affine_act_drop(rsr_handle* h, void* stream, const float* z, 
 extern "C" int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldda, const float* z, int ldz,
                           long long rows, int N, int act, float keep_prob, const unsigned long long* rng, unsigned salt,
                           int bn, float* coef, const float* bias, float* dgamma, float* dbeta, void* dz16, int lddz,
-                          float* scratch) {
+                          float* dz32, int lddz32, float* scratch) {
     if (!h || !da16 || !z || !scratch || rows <= 0 || N <= 0) return RSR_E_ARG;
     if (bn ? !coef : !bias) return RSR_E_ARG;
-    if ((N & 3) || (ldz & 3) || (ldda & 3) || (lddz & 3)) return RSR_E_SHAPE;
+    if ((N & 3) || (ldz & 3) || (ldda & 3) || (dz16 && (lddz & 3)) || (dz32 && (lddz32 & 3))) return RSR_E_SHAPE;
     if (act != RSR_ACT_NONE && act != RSR_ACT_RELU && act != RSR_ACT_LRELU) return RSR_E_SHAPE;
     const uint32_t thr = keep_threshold(keep_prob);
     if (thr < (1u << 24) && (!rng || thr == 0)) return RSR_E_ARG;
@@ -517,9 +525,10 @@ extern "C" int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldd
         bn_bwd_finish_kernel<<<(N + FIN_COLS - 1) / FIN_COLS, dim3(FIN_COLS, FIN_LANES), 0, st>>>(scratch, splits, rows, N, bn, coef, dgamma, dbeta);
         RSR_LAUNCH_CHECK();
     }
-    if (dz16) {
+    if (dz16 || dz32) {
         bn_bwd_apply_kernel<<<ew_grid(rows, N >> 2, h->num_sms), 256, 0, st>>>(
-            z, ldz, rows, N, p, bn, bn ? coef + 6ll * N : nullptr, bn ? coef + 7ll * N : nullptr, (uint16_t*)dz16, lddz);
+            z, ldz, rows, N, p, bn, bn ? coef + 6ll * N : nullptr, bn ? coef + 7ll * N : nullptr, (uint16_t*)dz16, lddz,
+            dz32, lddz32);
         RSR_LAUNCH_CHECK();
     }
     return 0;

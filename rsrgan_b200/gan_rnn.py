@@ -104,7 +104,7 @@ class GAN_RNN(Model):
         self.keep_prob = 1.0 if cross_validation else _arg(args, "keep_prob", 1.0)
         self.batch_norm = _arg(args, "batch_norm", False)
         # contrib batch_norm(renorm) on the fully_connected layers and tf.nn.dropout behind them are nets.FCBN
-        # (csrc/batchnorm.cu); DropoutWrapper on the LSTM generators raises NotImplementedError in nets.Generator.
+        # (csrc/batchnorm.cu); DropoutWrapper on the LSTM generators is nets.Generator._drop_fwd / _drop_bwd.
         # This trainer never runs the UPDATE_OPS (:169-175 has no control dependency on them), so the moving
         # averages of a batch-normalised GAN stay at their initial values -- reference behaviour, kept
         # (`update_bn_stats = True` opts out); DNNTrainer does run them.

@@ -96,6 +96,7 @@ class FC(object):
 
 
 CTX_SALT = {"g": 0, "rl": 256, "fk": 512}     # dropout stream per layer call: salt = CTX_SALT[ctx] + layer index
+LSTM_SALT = 16                                # ... + LSTM_SALT + l for the DropoutWrapper of LSTM layer l
 
 
 class FCBN(FC):
@@ -109,9 +110,9 @@ class FCBN(FC):
     STATE_KEYS = ("moving_mean", "moving_variance", "renorm_mean", "renorm_stddev", "renorm_mean_weight",
                   "renorm_stddev_weight")
 
-    def __init__(self, net, scope, n_in, n_out, act, bn, index):
+    def __init__(self, net, scope, n_in, n_out, act, bn, index, drop=True):
         super(FCBN, self).__init__(net, scope, n_in, n_out, act)
-        self.bn, self.index = bool(bn), index
+        self.bn, self.index, self.drop = bool(bn), index, drop
         self.betaname, self.gname = scope + "/BatchNorm/beta", scope + "/BatchNorm/gamma"
         self.state = None
         if self.bn:
@@ -137,7 +138,7 @@ class FCBN(FC):
         z32, coef, scratch = self._bufs(ctx, rows)
         y16 = net.ws.get((ctx, self.scope, "y16"), rows, self.outp, h.h16)
         h.gemm(x16, net.P.view(self.wname, "theta16"), rows, self.outp, self.inp, b_mn=True, out32=z32)
-        keep = net.keep_prob if net.training else 1.0
+        keep = net.keep_prob if net.training and self.drop else 1.0
         if self.bn:
             if net.training:
                 h.bn_train_stats(z32, rows, self.outp, net.P.view(self.gname), net.P.view(self.betaname), self.state,
@@ -514,21 +515,21 @@ class Generator(Net):
     def __init__(self, handle, g_type="lstm", in_dim=257, out_dim=40, cell=760, proj=280, layers=None,
                  units=1024, batch_norm=False, keep_prob=1.0):
         self.g_type, self.in_dim, self.out_dim = g_type, in_dim, out_dim
-        self.keep_prob = float(keep_prob) if g_type == "dnn" else 1.0
-        if keep_prob < 1.0 and g_type in ("lstm", "res_lstm_l", "res_lstm_base"):
-            # DropoutWrapper(output_keep_prob) on every LSTM layer (models/lstm.py:99-102): not on this path yet
-            raise NotImplementedError("dropout on the LSTM generators (DropoutWrapper) is not implemented")
+        # dnn: tf.nn.dropout behind every hidden layer (FCBN); LSTM generators: DropoutWrapper(output_keep_prob) on every
+        # LSTM layer's output (models/lstm.py:99-102, models/res_lstm_l.py:96-99) = _drop_fwd / _drop_bwd below
+        self.keep_prob = float(keep_prob)
+        self._dropping = False
         if (batch_norm or keep_prob < 1.0) and g_type == "rced":
             raise NotImplementedError("batch_norm / dropout on the rced generator are not implemented")
         # res_lstm_l / res_lstm_base build normalizer_params but never pass them on (models/res_lstm_l.py:58-67,81-82):
         # batch_norm is a no-op there, exactly as in the reference
-        special = batch_norm or self.keep_prob < 1.0
+        special = g_type == "dnn" and (batch_norm or self.keep_prob < 1.0)
         if g_type == "lstm":
             # models/lstm.py:43-45: cell 760, projection 280, 3 layers
             L = 3 if layers is None else layers
 
             def mk(net):
-                ls = [FCBN(net, "g_model/fully_connected", in_dim, proj, ACT_LRELU, True, 0) if batch_norm else
+                ls = [FCBN(net, "g_model/fully_connected", in_dim, proj, ACT_LRELU, True, 0, drop=False) if batch_norm else
                       FC(net, "g_model/fully_connected", in_dim, proj, ACT_LRELU)]
                 ls += [LSTMP(net, "g_model/rnn/multi_rnn_cell/cell_%d/lstm_cell/" % i, proj, cell, proj)
                        for i in range(L)]
@@ -569,6 +570,25 @@ class Generator(Net):
         super(Generator, self).__init__(handle, mk, adam=True)
         self.residual = g_type == "res_lstm_l"
 
+    # DropoutWrapper(output_keep_prob): the output handed to the next layer is dropped, the recurrent state is not
+    def _drop_fwd(self, li, o32, rows, want32=False):
+        h, ws, Pp = self.h, self.ws, o32.shape[1]
+        xd16 = ws.get(("g", "drop16", li), rows, Pp, h.h16)
+        xd32 = ws.get(("g", "drop32", li), rows, Pp, F32) if want32 else None
+        zeros = ws.get(("g", "zeros", Pp), 1, Pp, F32)[0]
+        h.affine_act_drop(o32, rows, Pp, None, zeros, ACT_NONE, self.keep_prob, self.rng,
+                          CTX_SALT["g"] + LSTM_SALT + li, xd16, out32=xd32)
+        return xd16, xd32
+
+    def _drop_bwd(self, li, d16, o32, rows):
+        h, ws, Pp = self.h, self.ws, o32.shape[1]
+        dd16 = ws.get(("g", "ddrop16", li), rows, Pp, h.h16)
+        dd32 = ws.get(("g", "ddrop32", li), rows, Pp, F32)
+        zeros = ws.get(("g", "zeros", Pp), 1, Pp, F32)[0]
+        h.bn_bwd(d16, o32, rows, Pp, ACT_NONE, self.keep_prob, self.rng, CTX_SALT["g"] + LSTM_SALT + li, False, None,
+                 zeros, None, None, dd16, ws.get(("g", "drop_scratch"), 1, 8, F32), dz32=dd32)
+        return dd16, dd32
+
     def fwd(self, x, B, T, lengths, train=True, x_time_major=False, reuse_staged=False):
         """x fp32 (B, T, in_dim) batch-major on the device -> y32 [T*B, out_pad] time-major fp32.
         reuse_staged: the 16-bit time-major copy of this same x from the previous call is still valid (the second
@@ -600,27 +620,34 @@ class Generator(Net):
                 self._acts.append(a)
             _, y32 = self.layers[-1].fwd("g", a, rows, want16=False, want32=True)
             return y32
+        drop = self._dropping = self.training and self.keep_prob < 1.0
+        self._o32 = []
         if not res:
             h0, _ = self.layers[0].fwd("g", x16, rows)
             self._acts = [x16, h0]
             a = h0
-            for l in self.layers[1:-1]:
-                seq, _ = l.fwd("g", a, B, T, lengths, save=train)
-                a = seq[B:]
+            for li, l in enumerate(self.layers[1:-1]):
+                seq, o32 = l.fwd("g", a, B, T, lengths, save=train, want32=drop)
+                a = self._drop_fwd(li, o32, rows)[0] if drop else seq[B:]
+                self._o32.append(o32)
                 self._acts.append(a)
             _, y32 = self.layers[-1].fwd("g", a, rows, want16=False, want32=True)
             return y32
         a16, a32 = x16, x32
         self._acts = [x16]
         for i, l in enumerate(self.layers[:-1]):
-            seq, o32 = l.fwd("g", a16, B, T, lengths, save=train, want32=self.residual)
+            seq, o32 = l.fwd("g", a16, B, T, lengths, save=train, want32=self.residual or drop)
+            self._o32.append(o32)
+            od16 = seq[B:]
+            if drop:
+                od16, o32 = self._drop_fwd(i, o32, rows, want32=self.residual)
             if self.residual:                      # x_{l+1} = out_l + x_l   (models/res_lstm_l.py:116,127,138,187)
                 n16 = ws.get(("g", "xr16", i, B), rows, ip, h.h16)
                 n32 = ws.get(("g", "xr32", i, B), rows, ip, F32)
                 h.add_cast(o32, a32, rows * ip, out32=n32, out16=n16)
                 a16, a32 = n16, n32
             else:
-                a16 = seq[B:]
+                a16 = od16
             self._acts.append(a16)
         _, y32 = self.layers[-1].fwd("g", a16, rows, want16=False, want32=True)
         return y32
@@ -641,6 +668,16 @@ class Generator(Net):
                 d, _ = Ls[i].bwd("g", acts[i], d, rows, want_dx=i > 0, prev_y16=acts[i] if i > 0 and plain else None,
                                  prev_act=ACT_RELU if plain else ACT_NONE)
             return
+        if self.g_type == "lstm" and self._dropping:
+            d16, d32 = Ls[-1].bwd("g", acts[-1], dy16, rows, want32=True)     # wrt the DROPPED output of the last LSTM
+            for i in range(len(Ls) - 2, 0, -1):
+                first = i == 1
+                mask = first and not self.fcbn
+                d16, d32 = self._drop_bwd(i - 1, d16, self._o32[i - 1], rows)
+                d16, d32 = Ls[i].bwd("g", acts[i], d16, d32, B, T, lengths, prev_y16=acts[1] if mask else None,
+                                     prev_act=ACT_LRELU if mask else ACT_NONE, want32=not first)
+            Ls[0].bwd("g", acts[0], d16, rows, want_dx=False, dw_side=False)
+            return
         if self.g_type == "lstm":
             d16, d32 = Ls[-1].bwd("g", acts[-1], dy16, rows, want32=True)
             Ls[-2].bwd_pre("g", d16, B, T)
@@ -657,7 +694,9 @@ class Generator(Net):
             return
         d16, d32 = Ls[-1].bwd("g", acts[-1], dy16, rows, want32=True)
         for i in range(len(Ls) - 2, -1, -1):
-            d16, d32 = Ls[i].bwd("g", acts[i], d16, d32, B, T, lengths, want_dx=i > 0,
+            # in_{l+1} = drop(out_l) + in_l: the skip path carries d32 as it is, the layer sees the masked gradient
+            o16, o32 = self._drop_bwd(i, d16, self._o32[i], rows) if self._dropping else (d16, d32)
+            d16, d32 = Ls[i].bwd("g", acts[i], o16, o32, B, T, lengths, want_dx=i > 0,
                                  resid32=d32 if self.residual else None, want32=True)
 
 

@@ -267,15 +267,18 @@ class Handle(object):
     def bn_eval_coef(self, N, gamma, beta, state, coef):
         self._call("rsr_bn_eval_coef", 1, self.h, _stream(), N, _p(gamma), _p(beta), self.BN_EPS, _p(state), _p(coef))
 
-    def affine_act_drop(self, z32, rows, N, A, Bc, act, keep_prob, rng, salt, out16):
+    def affine_act_drop(self, z32, rows, N, A, Bc, act, keep_prob, rng, salt, out16, out32=None):
         self._call("rsr_affine_act_drop", 1, self.h, _stream(), _p(z32), z32.stride(0), rows, N, _p(A), _p(Bc), act,
-                   float(keep_prob), _p(rng), int(salt), _p(out16), out16.stride(0))
+                   float(keep_prob), _p(rng), int(salt), _p(out16), out16.stride(0) if out16 is not None else 0,
+                   _p(out32), out32.stride(0) if out32 is not None else 0)
 
-    def bn_bwd(self, da16, z32, rows, N, act, keep_prob, rng, salt, bn, coef, bias, dgamma, dbeta, dz16, scratch):
-        n = (2 if (bn or dbeta is not None) else 0) + (1 if dz16 is not None else 0)
+    def bn_bwd(self, da16, z32, rows, N, act, keep_prob, rng, salt, bn, coef, bias, dgamma, dbeta, dz16, scratch,
+               dz32=None):
+        n = (2 if (bn or dbeta is not None) else 0) + (1 if (dz16 is not None or dz32 is not None) else 0)
         self._call("rsr_bn_bwd", n, self.h, _stream(), _p(da16), da16.stride(0), _p(z32), z32.stride(0), rows, N, act,
                    float(keep_prob), _p(rng), int(salt), int(bn), _p(coef), _p(bias), _p(dgamma), _p(dbeta),
-                   _p(dz16), dz16.stride(0) if dz16 is not None else 0, _p(scratch))
+                   _p(dz16), dz16.stride(0) if dz16 is not None else 0, _p(dz32),
+                   dz32.stride(0) if dz32 is not None else 0, _p(scratch))
 
     def rng_tick(self, rng):
         self._call("rsr_rng_tick", 1, self.h, _stream(), _p(rng))

@@ -345,15 +345,19 @@ class FakeHandle(object):
             bits = np.stack([hsh >> np.uint64(40), (hsh >> np.uint64(16)) & np.uint64(0xffffff)], 1).reshape(rows, N)
         return torch.from_numpy((bits < np.uint64(int(float(np.float32(keep_prob)) * 16777216.0))))
 
-    def affine_act_drop(self, z32, rows, N, A, Bc, act, keep_prob, rng, salt, out16):
+    def affine_act_drop(self, z32, rows, N, A, Bc, act, keep_prob, rng, salt, out16, out32=None):
         self.launches += 1
         y = z32[:rows, :N] * (A[:N] if A is not None else 1.0) + Bc[:N]
         a = _act(y, act)
         if keep_prob < 1.0:
             a = torch.where(self._drop_mask(rng, salt, rows, N, keep_prob), a / keep_prob, torch.zeros_like(a))
-        out16[:rows, :N] = a.to(self.h16)
+        if out16 is not None:
+            out16[:rows, :N] = a.to(self.h16)
+        if out32 is not None:
+            out32[:rows, :N] = a
 
-    def bn_bwd(self, da16, z32, rows, N, act, keep_prob, rng, salt, bn, coef, bias, dgamma, dbeta, dz16, scratch):
+    def bn_bwd(self, da16, z32, rows, N, act, keep_prob, rng, salt, bn, coef, bias, dgamma, dbeta, dz16, scratch,
+               dz32=None):
         self.launches += 3
         z = z32[:rows, :N]
         y = z * coef[0, :N] + coef[1, :N] if bn else z + bias[:N]
@@ -371,6 +375,8 @@ class FakeHandle(object):
             g = coef[0, :N] * (g - s1 / rows - xh * (s2 / rows))
         if dz16 is not None:
             dz16[:rows, :N] = g.to(self.h16)
+        if dz32 is not None:
+            dz32[:rows, :N] = g
 
     def rng_tick(self, rng):
         self.launches += 1

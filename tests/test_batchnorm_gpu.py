@@ -295,3 +295,41 @@ def test_gan_batch_norm_and_dropout(graph):
         L, _, _ = O.tower_losses_and_grads(st, xt, yt, ln, "d", g_opts=dict(bn_state=copy.deepcopy(gbs)), d_opts=do)
         assert o["d_rl_loss"] == pytest.approx(L["d_rl_loss"], rel=3e-3) and \
             o["d_fk_loss"] == pytest.approx(L["d_fk_loss"], rel=3e-3, abs=1e-5)
+
+
+@pytest.mark.parametrize("g_type,kw", [("lstm", dict(g_cell=128, g_proj=64, g_layers=2, batch_norm=True)),
+                                       ("res_lstm_l", dict(g_cell=128, g_layers=2)),
+                                       ("res_lstm_base", dict(g_cell=128, g_layers=2))])
+def test_lstm_generator_dropout_wrapper(g_type, kw):
+    """DropoutWrapper(output_keep_prob) on every LSTM layer of the generator (models/lstm.py:99-102,
+    models/res_lstm_l.py:96-99; P = 257 exercises the padded row pitch 264 of the mask), batch_norm on the lstm
+    generator's first layer, ragged lengths: losses and raw gradients of one G update, then the whole schedule twice
+    (the generator forward is NOT shared between the D and the first G update when it drops)."""
+    from rsrgan_b200.gan_rnn import GAN_RNN
+    rng = np.random.default_rng(8)
+    B, T = 6, 20
+    a = Namespace(g_type=g_type, d_type="lstm", batch_size=B, d_cell=64, keep_prob=0.8, init_mse_weight=10.0,
+                  init_disc_noise_std=0.0, g_learning_rate=0.0, d_learning_rate=0.0, seed=5, dtype="f16",
+                  use_graph=False, **kw)
+    m = GAN_RNN(None, a, ["/gpu:0"])
+    gp, dp = m.G.P.export_tf(dtype=np.float64), m.D.P.export_tf(dtype=np.float64)
+    x = rng.standard_normal((B, T, 257)).astype(np.float32)
+    y = rng.standard_normal((B, T, 40)).astype(np.float32)
+    ln = np.array([T, T - 7, T - 1, T // 2, T, 3])
+    st = O.GanState(gp, dp, g_type, "lstm")
+    go = dict(bn_state=O.init_bn_state(gp), keep_prob=0.8, rng=(5, 0))
+    L, G, _ = O.tower_losses_and_grads(st, x.astype(np.float64), y.astype(np.float64), ln, "g", g_opts=go)
+    out = m.g_step(x, y, ln)
+    gs = m._gscale(B * T)
+    for k in ("g_adv_loss", "g_mse_loss"):
+        assert out[k] == pytest.approx(L[k], rel=3e-3, abs=1e-5), k
+    mine = m.G.P.export_tf("grad")
+    for k in G:
+        assert rel(mine[k] / gs, G[k]) < 5e-2, k
+    n0 = int(m.G.rng[1])
+    o1 = m.train_batch(x, y, ln)
+    o2 = m.train_batch(x, y, ln)
+    assert int(m.G.rng[1]) == n0 + 6 and o1["g_mse_loss"] != o2["g_mse_loss"]       # new masks every update
+    go = dict(bn_state=O.init_bn_state(gp), keep_prob=0.8, rng=(5, n0 + 5))          # last G update of the 2nd schedule
+    L2, _, _ = O.tower_losses_and_grads(st, x.astype(np.float64), y.astype(np.float64), ln, "g", g_opts=go)
+    assert o2["g_mse_loss"] == pytest.approx(L2["g_mse_loss"], rel=3e-3)

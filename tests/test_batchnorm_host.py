@@ -257,5 +257,45 @@ def test_lstm_generator_first_layer_batch_norm_and_noops():
     b = Namespace(**dict(vars(a), g_type="res_lstm_l"))
     m2 = GAN_RNN(None, b, ["/gpu:0"], handle=FakeHandle("f16"))
     assert not m2.G.fcbn and not m2.D.fcbn
-    with pytest.raises(NotImplementedError):
-        GAN_RNN(None, Namespace(**dict(vars(a), keep_prob=0.9)), ["/gpu:0"], handle=FakeHandle("f16"))
+
+
+@pytest.mark.parametrize("g_type", ["lstm", "res_lstm_l", "res_lstm_base"])
+def test_lstm_generator_dropout_wrapper_matches_oracle(g_type):
+    """DropoutWrapper(output_keep_prob) on every LSTM layer of the generator (models/lstm.py:99-102,
+    models/res_lstm_l.py:96-99), batch_norm on the lstm generator's first layer: losses and raw gradients of a G update."""
+    rng = np.random.default_rng(8)
+    B, T = 3, 6
+    a = Namespace(g_type=g_type, d_type="lstm", batch_size=B, g_cell=40, g_proj=24, g_layers=2, d_cell=32,
+                  batch_norm=g_type == "lstm", keep_prob=0.8, init_mse_weight=10.0, init_disc_noise_std=0.0,
+                  g_learning_rate=0.0, d_learning_rate=0.0, seed=5)
+    m = GAN_RNN(None, a, ["/gpu:0"], handle=FakeHandle("f16"))
+    assert m.G.keep_prob == 0.8 and m.D.keep_prob == 1.0
+    gp, dp = m.G.P.export_tf(dtype=np.float64), m.D.P.export_tf(dtype=np.float64)
+    if g_type == "lstm":
+        for k in gp:
+            if "BatchNorm" in k:
+                gp[k] = gp[k] + 0.1 * rng.standard_normal(gp[k].shape)
+        m.load_params(tf32(gp), None)
+        gp = m.G.P.export_tf(dtype=np.float64)
+    x = rng.standard_normal((B, T, 257)).astype(np.float32)
+    y = rng.standard_normal((B, T, 40)).astype(np.float32)
+    ln = np.array([T, T - 2, T - 1])
+    st = O.GanState(gp, dp, g_type, "lstm")
+    go = dict(bn_state=O.init_bn_state(gp), keep_prob=0.8, rng=(5, 0))
+    L, G, _ = O.tower_losses_and_grads(st, x.astype(np.float64), y.astype(np.float64), ln, "g", g_opts=go)
+    out = m.g_step(x, y, ln)
+    gs = m._gscale(B * T)
+    for k in ("g_adv_loss", "g_mse_loss"):
+        assert out[k] == pytest.approx(L[k], rel=3e-3, abs=1e-5), k
+    mine = m.G.P.export_tf("grad")
+    for k in G:
+        assert rel(mine[k] / gs, G[k]) < 3e-2, k
+    assert int(m.G.rng[1]) == 1
+    # the cross-validation graph keeps everything (lstm.keep_prob = 1.0 when not training, models/lstm.py:72-73)
+    cv = GAN_RNN(None, a, ["/gpu:0"], cross_validation=True, share=m)
+    g_cv = cv.generate(x, ln).numpy()
+    g_ref, _ = GEN_FWD[g_type](gp, x.astype(np.float64), ln, opts=dict(bn_state=O.init_bn_state(gp), train=False))
+    assert rel(g_cv, g_ref) < 3e-3
+
+
+GEN_FWD = {k: v[0] for k, v in O.GENERATORS.items()}
