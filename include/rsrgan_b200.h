@@ -283,6 +283,20 @@ int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldda, const fl
                float* dz32, int lddz32, float* scratch);
 int rsr_rng_tick(rsr_handle* h, void* stream, unsigned long long* rng);
 
+/* Kaldi compressed matrix ("CM" ark entries) decoded on the device -- io_funcs/kaldi_io.py:121-161 (uint16_to_float,
+ * char_to_float, read_compress) fused with the CMVN of io_funcs/make_tfrecords.py:84-87.
+ *   col_hdr  u16 [cols, 4]    PerColHeader percentiles (0, 25, 75, 100), as on disk (little endian)
+ *   data     u8  [cols, rows] the byte matrix, column-major as on disk
+ *   min_value, range          GlobalHeader floats
+ *   out64    f64 [rows, ld64] the reader's float64 matrix, or NULL
+ *   out32    f32 [rows, ld32] float32((x - mean[c]) / std[c]) evaluated in float64 (mean/std f64 [cols]), or float32(x)
+ *                             when mean/std are NULL; or NULL
+ * float64 arithmetic in the reference's operation order with round-to-nearest intrinsics: BIT-IDENTICAL to the Python
+ * reader (tests/golden/kaldi_small_expected.npz was produced by the reference's own reader). */
+int rsr_ark_decompress(rsr_handle* h, void* stream, const void* col_hdr, const void* data, float min_value, float range,
+                       int rows, int cols, double* out64, int ld64, const double* mean, const double* std,
+                       float* out32, int ld32);
+
 /* misc ---------------------------------------------------------------------------------- */
 /* dst[c, r] = src[r, c] for r < rows, c < cols (16-bit elements; other elements of dst untouched):
  * keeps the K_x^T operand of rsr_lstmp_fused_fwd in step with the updated weights. */

@@ -69,6 +69,7 @@ SIGNATURES = {
     "rsr_affine_act_drop": [vp, vp, vp, ci, cll, ci, vp, vp, ci, cf, vp, C.c_uint, vp, ci, vp, ci],
     "rsr_bn_bwd": [vp, vp, vp, ci, vp, ci, cll, ci, ci, cf, vp, C.c_uint, ci, vp, vp, vp, vp, vp, ci, vp, ci, vp],
     "rsr_rng_tick": [vp, vp, vp],
+    "rsr_ark_decompress": [vp, vp, vp, vp, cf, cf, ci, ci, vp, ci, vp, vp, vp, ci],
 }
 
 _lib = None

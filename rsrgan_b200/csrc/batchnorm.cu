@@ -338,6 +338,7 @@ __global__ void bn_eval_coef_kernel(int N, const float* __restrict__ gamma, cons
 
 // Every thread owns one group of 4 columns for the whole launch (the grid is sized so that the thread count is a
 // multiple of N / 4): coefficients live in registers, no per-element index division, rows advance by a constant.
+template <bool O16, bool O32>
 __global__ void __launch_bounds__(256) affine_act_drop_kernel(const float* __restrict__ z, int ldz, long long rows,
                                                               int N, const float* __restrict__ A,
                                                               const float* __restrict__ Bc, int act, uint32_t thr24,
@@ -366,13 +367,13 @@ __global__ void __launch_bounds__(256) affine_act_drop_kernel(const float* __res
 #pragma unroll
             for (int k = 0; k < 4; ++k) y[k] = keep[k] ? y[k] * inv_keep : 0.0f;
         }
-        if (out) {
+        if (O16) {
             uint2 o;
             o.x = pack2(y[0], y[1], bf);
             o.y = pack2(y[2], y[3], bf);
             *reinterpret_cast<uint2*>(out + r * ldo + c) = o;
         }
-        if (out32) *reinterpret_cast<float4*>(out32 + r * ldo32 + c) = make_float4(y[0], y[1], y[2], y[3]);
+        if (O32) *reinterpret_cast<float4*>(out32 + r * ldo32 + c) = make_float4(y[0], y[1], y[2], y[3]);
     }
 }
 
@@ -392,6 +393,7 @@ __global__ void bn_bwd_finish_kernel(const float* __restrict__ partial, int spli
     if (dbeta) atomicAdd(dbeta + c, s1);
 }
 
+template <bool O16, bool O32>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ z, int ldz, long long rows, int N,
                                                            BnBwdIn p, int bn, const float* __restrict__ m1,
                                                            const float* __restrict__ m2, uint16_t* __restrict__ dz,
@@ -418,13 +420,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 #pragma unroll
             for (int k = 0; k < 4; ++k) g[k] = k4.A[k] * (g[k] - u1[k] - xh[k] * u2[k]);
         }
-        if (dz) {
+        if (O16) {
             uint2 o;
             o.x = pack2(g[0], g[1], p.bf);
             o.y = pack2(g[2], g[3], p.bf);
             *reinterpret_cast<uint2*>(dz + r * lddz + c) = o;
         }
-        if (dz32) *reinterpret_cast<float4*>(dz32 + r * lddz32 + c) = make_float4(g[0], g[1], g[2], g[3]);
+        if (O32) *reinterpret_cast<float4*>(dz32 + r * lddz32 + c) = make_float4(g[0], g[1], g[2], g[3]);
     }
 }
 
@@ -494,9 +496,16 @@ extern "C" int rsr_affine_act_drop(rsr_handle* h, void* stream, const float* z, 
     if (act != RSR_ACT_NONE && act != RSR_ACT_RELU && act != RSR_ACT_LRELU) return RSR_E_SHAPE;
     const uint32_t thr = keep_threshold(keep_prob);
     if (thr < (1u << 24) && (!rng || thr == 0)) return RSR_E_ARG;
-    affine_act_drop_kernel<<<ew_grid(rows, N >> 2, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
-        z, ldz, rows, N, A, Bc, act, thr, thr < (1u << 24) ? 1.0f / keep_prob : 1.0f, rng, salt, (uint16_t*)out16, ld16,
-        out32, ld32, h->dtype == RSR_DTYPE_BF16);
+    const int grid = ew_grid(rows, N >> 2, h->num_sms);
+    const float ik = thr < (1u << 24) ? 1.0f / keep_prob : 1.0f;
+    const int bf = h->dtype == RSR_DTYPE_BF16;
+    cudaStream_t st = (cudaStream_t)stream;
+#define RSR_AFFINE(O16, O32) affine_act_drop_kernel<O16, O32><<<grid, 256, 0, st>>>( \
+        z, ldz, rows, N, A, Bc, act, thr, ik, rng, salt, (uint16_t*)out16, ld16, out32, ld32, bf)
+    if (out16 && out32) RSR_AFFINE(true, true);
+    else if (out16) RSR_AFFINE(true, false);
+    else RSR_AFFINE(false, true);
+#undef RSR_AFFINE
     RSR_LAUNCH_CHECK();
     return 0;
 }
@@ -526,9 +535,14 @@ extern "C" int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldd
         RSR_LAUNCH_CHECK();
     }
     if (dz16 || dz32) {
-        bn_bwd_apply_kernel<<<ew_grid(rows, N >> 2, h->num_sms), 256, 0, st>>>(
-            z, ldz, rows, N, p, bn, bn ? coef + 6ll * N : nullptr, bn ? coef + 7ll * N : nullptr, (uint16_t*)dz16, lddz,
-            dz32, lddz32);
+        const int grid = ew_grid(rows, N >> 2, h->num_sms);
+#define RSR_APPLY(O16, O32) bn_bwd_apply_kernel<O16, O32><<<grid, 256, 0, st>>>( \
+        z, ldz, rows, N, p, bn, bn ? coef + 6ll * N : nullptr, bn ? coef + 7ll * N : nullptr, (uint16_t*)dz16, lddz, \
+        dz32, lddz32)
+        if (dz16 && dz32) RSR_APPLY(true, true);
+        else if (dz16) RSR_APPLY(true, false);
+        else RSR_APPLY(false, true);
+#undef RSR_APPLY
         RSR_LAUNCH_CHECK();
     }
     return 0;

@@ -713,3 +713,71 @@ extern "C" int rsr_fc1_bwd_dx(rsr_handle* h, void* stream, const void* dy16, int
     RSR_LAUNCH_CHECK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// Kaldi compressed matrix ("CM") decode, io_funcs/kaldi_io.py:121-161, fused with the CMVN of
+// io_funcs/make_tfrecords.py:84-87.  Bytes are column-major on disk, the result is row-major: a
+// 32-column x 128-row byte tile goes through shared memory (byte reads coalesced along rows, fp32 / fp64 writes
+// coalesced along columns).  All arithmetic is float64 with the reference's operation order and explicit
+// round-to-nearest intrinsics (no FMA contraction), so the result is bit-identical to the Python reader.
+// ---------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ double u16_to_double(double minv, double range, unsigned v) {
+    // min_value + range * 1.52590218966964e-05 * value  (left to right)
+    return __dadd_rn(minv, __dmul_rn(__dmul_rn(range, 1.52590218966964e-05), (double)v));
+}
+
+__global__ void __launch_bounds__(256) ark_decompress_kernel(const uint16_t* __restrict__ hdr,
+                                                             const uint8_t* __restrict__ data, double minv, double range,
+                                                             int rows, int cols, double* __restrict__ out64, int ld64,
+                                                             const double* __restrict__ mean,
+                                                             const double* __restrict__ stdv, float* __restrict__ out32,
+                                                             int ld32) {
+    __shared__ uint8_t tile[32][132];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 128;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int ci = ty; ci < 32; ci += 8) {
+        const int c = c0 + ci;
+        if (c < cols) {
+            const uint8_t* src = data + (long long)c * rows;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = r0 + k * 32 + tx;
+                if (r < rows) tile[ci][k * 32 + tx] = src[r];
+            }
+        }
+    }
+    __syncthreads();
+    const int c = c0 + tx;
+    if (c >= cols) return;
+    const double p0 = u16_to_double(minv, range, hdr[c * 4 + 0]), p25 = u16_to_double(minv, range, hdr[c * 4 + 1]);
+    const double p75 = u16_to_double(minv, range, hdr[c * 4 + 2]), p100 = u16_to_double(minv, range, hdr[c * 4 + 3]);
+    const double d_lo = __dsub_rn(p25, p0), d_mid = __dsub_rn(p75, p25), d_hi = __dsub_rn(p100, p75);
+    const double mu = mean ? mean[c] : 0.0, sd = stdv ? stdv[c] : 1.0;
+    for (int rr = ty; rr < 128; rr += 8) {
+        const int r = r0 + rr;
+        if (r >= rows) break;
+        const int v = tile[tx][rr];
+        double x;
+        if (v < 64) x = __dadd_rn(p0, __dmul_rn(__dmul_rn(d_lo, (double)v), 1.0 / 64.0));
+        else if (v <= 192) x = __dadd_rn(p25, __dmul_rn(__dmul_rn(d_mid, (double)(v - 64)), 1.0 / 128.0));
+        else x = __dadd_rn(p75, __dmul_rn(__dmul_rn(d_hi, (double)(v - 192)), 1.0 / 63.0));
+        if (out64) out64[(long long)r * ld64 + c] = x;
+        if (out32) out32[(long long)r * ld32 + c] = (float)(mean ? __ddiv_rn(__dsub_rn(x, mu), sd) : x);
+    }
+}
+}  // namespace
+
+extern "C" int rsr_ark_decompress(rsr_handle* h, void* stream, const void* col_hdr, const void* data, float min_value,
+                                  float range, int rows, int cols, double* out64, int ld64, const double* mean,
+                                  const double* std, float* out32, int ld32) {
+    if (!h || !col_hdr || !data || (!out64 && !out32) || rows <= 0 || cols <= 0) return RSR_E_ARG;
+    if ((mean == nullptr) != (std == nullptr)) return RSR_E_ARG;
+    if ((out64 && ld64 < cols) || (out32 && ld32 < cols)) return RSR_E_SHAPE;
+    dim3 grid((cols + 31) / 32, (rows + 127) / 128), block(32, 8);
+    ark_decompress_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const uint16_t*)col_hdr, (const uint8_t*)data,
+                                                                   (double)min_value, (double)range, rows, cols, out64,
+                                                                   ld64, mean, std, out32, ld32);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}

@@ -99,6 +99,46 @@ class ArkReader(object):
                 sys.exit(1)
             return np.reshape(mat, (rows, cols))
 
+    # -- device-side decode of compressed entries -------------------------------------------
+    @staticmethod
+    def read_compressed_raw(ark_file, ark_offset=0):
+        """The undecoded pieces of a `CM` entry: (min_value, range, rows, cols, col_hdr uint16 [cols, 4],
+        data uint8 [cols, rows]) exactly as on disk (io_funcs/kaldi_io.py:88-102,139-161); None for any other type."""
+        with open(ark_file, "rb") as f:
+            f.seek(int(ark_offset), 0)
+            header = struct.unpack("<xcccc", f.read(5))
+            if header[0] != b"B" or header[1] != b"C" or header[2] != b"M" or header[3] == b"2":
+                return None
+            min_value, rng, rows, cols = struct.unpack("<ffii", f.read(16))
+            hdr = np.frombuffer(f.read(8 * cols), dtype="<u2").reshape(cols, 4)
+            data = np.frombuffer(f.read(rows * cols), dtype=np.uint8).reshape(cols, rows)
+            return min_value, rng, rows, cols, hdr, data
+
+    def read_ark_device(self, handle, ark_file, ark_offset=0, mean=None, std=None):
+        """read_ark + the CMVN of io_funcs/make_tfrecords.py:84-87 with the decode on the GPU: a `CM` entry travels to
+        the device as BYTES (1 byte per element instead of 4) and `rsr_ark_decompress` produces
+        float32((x - mean) / std) evaluated in float64, bit-identical to the host path.  Returns a float32 device
+        tensor (rows, cols).  Uncompressed entries are decoded on the host (they are plain arrays) and normalised by
+        the same float64 expression before the upload."""
+        import torch
+        raw = self.read_compressed_raw(ark_file, ark_offset)
+        dev = handle.device
+        if raw is None:
+            m = self.read_ark(ark_file, ark_offset).astype(np.float64)
+            if mean is not None:
+                m = (m - np.asarray(mean, np.float64)) / np.asarray(std, np.float64)
+            return torch.from_numpy(np.ascontiguousarray(m.astype(np.float32))).to(dev)
+        min_value, rng, rows, cols, hdr, data = raw
+        hdr_d = torch.from_numpy(hdr.view(np.int16).copy()).to(dev)      # the 16 raw bits; torch has no uint16 arithmetic
+        data_d = torch.from_numpy(data.copy()).to(dev)
+        out = torch.empty(rows, cols, dtype=torch.float32, device=dev)
+        mean_d = std_d = None
+        if mean is not None:
+            mean_d = torch.from_numpy(np.ascontiguousarray(mean, dtype=np.float64)).to(dev)
+            std_d = torch.from_numpy(np.ascontiguousarray(std, dtype=np.float64)).to(dev)
+        handle.ark_decompress(hdr_d, data_d, min_value, rng, rows, cols, out32=out, mean=mean_d, std=std_d)
+        return out
+
     def read_next_utt(self):
         if len(self.scp_data) == 0:
             return None, None, True

@@ -282,3 +282,11 @@ class Handle(object):
 
     def rng_tick(self, rng):
         self._call("rsr_rng_tick", 1, self.h, _stream(), _p(rng))
+
+    # ------------------------------------------------------ Kaldi compressed-matrix decode
+    def ark_decompress(self, col_hdr, data, min_value, rng, rows, cols, out64=None, out32=None, mean=None, std=None):
+        """col_hdr: device int16/uint16-as-int16 [cols, 4]; data: device uint8 [cols, rows] (both as read from the ark);
+        mean/std: device float64 [cols] (CMVN in float64, make_tfrecords.py:84-87) or None."""
+        self._call("rsr_ark_decompress", 1, self.h, _stream(), _p(col_hdr), _p(data), float(min_value), float(rng),
+                   int(rows), int(cols), _p(out64), out64.stride(0) if out64 is not None else 0, _p(mean), _p(std),
+                   _p(out32), out32.stride(0) if out32 is not None else 0)

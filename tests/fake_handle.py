@@ -381,3 +381,18 @@ class FakeHandle(object):
     def rng_tick(self, rng):
         self.launches += 1
         rng[1] += 1
+
+    # ------------------------------------------------------ Kaldi compressed-matrix decode
+    def ark_decompress(self, col_hdr, data, min_value, rng, rows, cols, out64=None, out32=None, mean=None, std=None):
+        import io
+        import numpy as np
+        from rsrgan_b200.kaldi_io import ArkReader
+        self.launches += 1
+        buf = io.BytesIO(col_hdr.numpy().view(np.uint16).astype("<u2").tobytes() + data.numpy().tobytes())
+        m = ArkReader().read_compress(min_value, rng, rows, cols, buf)
+        if out64 is not None:
+            out64[:rows, :cols] = torch.from_numpy(m)
+        if out32 is not None:
+            if mean is not None:
+                m = (m - mean.numpy()) / std.numpy()
+            out32[:rows, :cols] = torch.from_numpy(m.astype(np.float32))

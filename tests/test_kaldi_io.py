@@ -65,3 +65,31 @@ def test_cmvn_conversion_and_apply(tmp_path):
     x = np.random.default_rng(1).standard_normal((6, 5)).astype(np.float32)
     z = O.cmvn_apply(x, m, s)
     assert z.dtype == np.float32 and np.allclose(O.cmvn_invert(z, m, s), x, atol=1e-5)
+
+
+def test_read_ark_device_host_double():
+    """read_ark_device through the CPU test double: same bits as read_ark + float64 CMVN (the CUDA kernel is checked in
+    tests/test_kernels_gpu.py::test_ark_decompress_bit_exact)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fake_handle import FakeHandle
+    exp = np.load(os.path.join(GOLD, "kaldi_small_expected.npz"))
+    r = kaldi_io.ArkReader()
+    cwd = os.getcwd()
+    os.chdir(GOLD)
+    try:
+        r(os.path.join(GOLD, "kaldi_small.scp"))
+        h = FakeHandle("f16")
+        for k in ("utt_cm", "utt_fm"):
+            path, off = r.scp_data[r.utt_ids.index(k)]
+            cols = exp[k].shape[1]
+            mean, std = np.linspace(-1, 1, cols), np.linspace(0.5, 2, cols)
+            got = r.read_ark_device(h, path, off, mean, std).numpy()
+            want = ((exp[k].astype(np.float64) - mean) / std).astype(np.float32)
+            assert got.dtype == np.float32 and np.array_equal(got, want), k
+            assert np.array_equal(r.read_ark_device(h, path, off).numpy(), exp[k].astype(np.float32)), k
+        raw = kaldi_io.ArkReader.read_compressed_raw(*r.scp_data[r.utt_ids.index("utt_cm")])
+        assert raw[2:4] == exp["utt_cm"].shape and raw[4].shape == (raw[3], 4) and raw[5].shape == (raw[3], raw[2])
+        assert kaldi_io.ArkReader.read_compressed_raw(*r.scp_data[r.utt_ids.index("utt_dm")]) is None
+    finally:
+        os.chdir(cwd)

@@ -411,3 +411,47 @@ def test_fc1_forward_and_data_gradient(h, rows, K):
         if src is not None:
             r = r * np.where(y16.double().cpu().numpy() > 0, 1.0, 0.3 if act == O.ACT_LRELU else 0.0)
         assert rel(dx.float().cpu().numpy(), r) < tol(h, 5e-4, 4e-3)
+
+
+def test_ark_decompress_bit_exact(h):
+    """rsr_ark_decompress == the reference's compressed-matrix reader, bit for bit: (i) the `CM` entry of the golden
+    archive, whose expected float64 matrix was produced by the REFERENCE's io_funcs/kaldi_io.py (tests/golden/
+    make_kaldi_golden.py); (ii) random headers / bytes at ragged and utterance sizes against our host reader (itself
+    pinned to the reference on that fixture), with and without the float64 CMVN of make_tfrecords.py:84-87."""
+    import io
+    import os
+    from rsrgan_b200 import kaldi_io
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    dev = h.device
+    exp = np.load(os.path.join(gold, "kaldi_small_expected.npz"))["utt_cm"]
+    r = kaldi_io.ArkReader()
+    cwd = os.getcwd()
+    os.chdir(gold)
+    try:
+        r(os.path.join(gold, "kaldi_small.scp"))
+        path, off = r.scp_data[r.utt_ids.index("utt_cm")]
+        mn, rg, rows, cols, hdr, data = kaldi_io.ArkReader.read_compressed_raw(path, off)
+        got32 = r.read_ark_device(h, path, off).cpu().numpy()
+    finally:
+        os.chdir(cwd)
+    out64 = torch.zeros(rows, cols, dtype=torch.float64, device=dev)
+    h.ark_decompress(torch.from_numpy(hdr.view(np.int16).copy()).to(dev), torch.from_numpy(data.copy()).to(dev), mn, rg,
+                     rows, cols, out64=out64)
+    assert np.array_equal(out64.cpu().numpy(), exp)                      # float64, identical bits
+    assert np.array_equal(got32, exp.astype(np.float32))
+    rng = np.random.default_rng(0)
+    for rows, cols in ((1, 1), (9, 40), (131, 257), (1000, 257), (129, 33)):
+        hdr = np.sort(rng.integers(0, 65536, (cols, 4)), axis=1).astype("<u2")
+        data = rng.integers(0, 256, (cols, rows)).astype(np.uint8)
+        mn, rg = np.float32(-12.5), np.float32(31.25 + rows)
+        want = kaldi_io.ArkReader().read_compress(mn, rg, rows, cols, io.BytesIO(hdr.tobytes() + data.tobytes()))
+        mean, std = rng.standard_normal(cols), 0.5 + rng.random(cols)
+        ld = cols + 3
+        o64 = torch.full((rows, ld), 7.0, dtype=torch.float64, device=dev)
+        o32 = torch.full((rows, ld), 7.0, dtype=torch.float32, device=dev)
+        h.ark_decompress(torch.from_numpy(hdr.view(np.int16).copy()).to(dev), torch.from_numpy(data).to(dev), mn, rg,
+                         rows, cols, out64=o64, out32=o32, mean=torch.from_numpy(mean).to(dev),
+                         std=torch.from_numpy(std).to(dev))
+        assert np.array_equal(o64[:, :cols].cpu().numpy(), want), (rows, cols)
+        assert np.array_equal(o32[:, :cols].cpu().numpy(), ((want - mean) / std).astype(np.float32)), (rows, cols)
+        assert bool((o64[:, cols:] == 7.0).all()) and bool((o32[:, cols:] == 7.0).all())
