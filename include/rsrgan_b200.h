@@ -297,6 +297,11 @@ int rsr_ark_decompress(rsr_handle* h, void* stream, const void* col_hdr, const v
                        int rows, int cols, double* out64, int ld64, const double* mean, const double* std,
                        float* out32, int ld32);
 
+/* CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the checksum of TensorFlow checkpoint-V2
+ * tensor-bundle files, used by rsrgan_b200/tf_checkpoint.py to read / write the reference's `GAN_RNN-<step>`
+ * checkpoints (models/gan_rnn_placeholder.py:26-60).  Needs no device.  Returns the checksum (not a status). */
+unsigned int rsr_crc32c_host(const void* data_host, unsigned long long n, unsigned int crc);
+
 /* misc ---------------------------------------------------------------------------------- */
 /* dst[c, r] = src[r, c] for r < rows, c < cols (16-bit elements; other elements of dst untouched):
  * keeps the K_x^T operand of rsr_lstmp_fused_fwd in step with the updated weights. */

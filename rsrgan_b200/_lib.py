@@ -70,7 +70,10 @@ SIGNATURES = {
     "rsr_bn_bwd": [vp, vp, vp, ci, vp, ci, cll, ci, ci, cf, vp, C.c_uint, ci, vp, vp, vp, vp, vp, ci, vp, ci, vp],
     "rsr_rng_tick": [vp, vp, vp],
     "rsr_ark_decompress": [vp, vp, vp, vp, cf, cf, ci, ci, vp, ci, vp, vp, vp, ci],
+    "rsr_crc32c_host": [vp, C.c_ulonglong, C.c_uint],
 }
+
+RESTYPES = {"rsr_crc32c_host": C.c_uint}       # everything else returns an int status
 
 _lib = None
 
@@ -87,7 +90,7 @@ def load():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
-            fn.restype = ci
+            fn.restype = RESTYPES.get(name, ci)
         _lib = lib
     return _lib
 

@@ -25,7 +25,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from . import nets, ops
+from . import nets, ops, tf_checkpoint
 
 F32 = torch.float32
 
@@ -39,7 +39,12 @@ def _arg(args, name, default):
 class Model(object):
     """models/gan_rnn_placeholder.py:20-60 -- save / load with the TF Saver conventions
     (files <save_dir>/<name>-<step>, a `checkpoint` index naming the latest, max_to_keep=10).
-    The container is torch.save of {TF variable name -> array}; see DESIGN.md for TF-ckpt interop."""
+    Two containers: torch.save of the state dict (`<name>-<step>.pt`, default) and TensorFlow's own checkpoint-V2
+    tensor bundle (`<name>-<step>.index` + `.data-00000-of-00001`, `ckpt_format = "tf"`, rsrgan_b200/tf_checkpoint.py);
+    `load` takes whichever the directory holds, so a checkpoint directory written by the reference can be resumed or
+    decoded here."""
+
+    ckpt_format = "pt"
 
     def __init__(self, name="BaseModel"):
         self.name = name
@@ -47,25 +52,44 @@ class Model(object):
     def _ckpt_path(self, save_dir, step):
         return os.path.join(save_dir, "%s-%d.pt" % (self.name, step))
 
+    @staticmethod
+    def _kept(save_dir):
+        """checkpoint names listed by the `checkpoint` file, oldest first (our one-name-per-line list or TF's
+        text-format CheckpointState)."""
+        latest, kept = tf_checkpoint.read_checkpoint_state(save_dir)
+        if latest is not None:
+            kept = [os.path.basename(k) for k in kept] or [os.path.basename(latest)]
+            return kept, True
+        index = os.path.join(save_dir, "checkpoint")
+        if not os.path.exists(index):
+            return [], False
+        with open(index) as f:
+            return [l.strip() for l in f if l.strip()], False
+
     def save(self, save_dir, step):
         os.makedirs(save_dir, exist_ok=True)
-        path = self._ckpt_path(save_dir, step)
-        torch.save(self.state_dict(), path)
-        index = os.path.join(save_dir, "checkpoint")
-        kept = []
-        if os.path.exists(index):
-            with open(index) as f:
-                kept = [l.strip() for l in f if l.strip()]
-        base = os.path.basename(path)
+        kept, _ = self._kept(save_dir)
+        if self.ckpt_format == "tf":
+            base = "%s-%d" % (self.name, step)
+            path = os.path.join(save_dir, base)
+            tf_checkpoint.write_bundle(path, tf_checkpoint.state_to_tensors(self.state_dict()))
+        else:
+            path = self._ckpt_path(save_dir, step)
+            torch.save(self.state_dict(), path)
+            base = os.path.basename(path)
         kept = [k for k in kept if k != base] + [base]
         while len(kept) > 10:                       # tf.train.Saver(max_to_keep=10), :32
             old = kept.pop(0)
-            try:
-                os.remove(os.path.join(save_dir, old))
-            except OSError:
-                pass
-        with open(index, "w") as f:
-            f.write("\n".join(kept) + "\n")
+            for suffix in ("", ".index", ".data-00000-of-00001"):
+                try:
+                    os.remove(os.path.join(save_dir, old + suffix))
+                except OSError:
+                    pass
+        if self.ckpt_format == "tf":
+            tf_checkpoint.write_checkpoint_state(save_dir, base, kept)
+        else:
+            with open(os.path.join(save_dir, "checkpoint"), "w") as f:
+                f.write("\n".join(kept) + "\n")
         return path
 
     def load(self, save_dir, model_file=None, moving_average=False):
@@ -74,17 +98,20 @@ class Model(object):
             return False
         print("[*] Reading checkpoints...")
         if model_file is None:
-            index = os.path.join(save_dir, "checkpoint")
-            if not os.path.exists(index):
-                return False
-            with open(index) as f:
-                kept = [l.strip() for l in f if l.strip()]
+            kept, _ = self._kept(save_dir)
             if not kept:
                 return False
             ckpt_name = kept[-1]
         else:
             ckpt_name = model_file
-        sd = torch.load(os.path.join(save_dir, ckpt_name), map_location="cpu", weights_only=False)
+        path = os.path.join(save_dir, ckpt_name)
+        if os.path.exists(path + ".index"):         # a TensorFlow checkpoint-V2 bundle (the reference's own files)
+            sd = self.state_dict()
+            missing = tf_checkpoint.tensors_to_state(tf_checkpoint.read_bundle(path), sd)
+            if missing:
+                print("[*] %d optimizer / average variables not in the checkpoint, kept as initialised" % len(missing))
+        else:
+            sd = torch.load(path, map_location="cpu", weights_only=False)
         self.load_state_dict(sd, moving_average=moving_average)
         print("[*] Read {}".format(ckpt_name))
         return True
@@ -109,6 +136,7 @@ class GAN_RNN(Model):
         # averages of a batch-normalised GAN stay at their initial values -- reference behaviour, kept
         # (`update_bn_stats = True` opts out); DNNTrainer does run them.
         self.update_bn_stats = False
+        self.ckpt_format = _arg(args, "ckpt_format", "pt")   # "tf": TensorFlow checkpoint-V2 bundles (tf_checkpoint.py)
         self.batch_size = _arg(args, "batch_size", 8)
         self.devices = devices
         self.num_gpu = _arg(args, "num_gpu", 1)

@@ -304,6 +304,9 @@ def build_parser():
     p.add_argument("--gen_updates", type=int, default=2, help="Number of G step in a training iteration.")
     p.add_argument("--batch_norm", type=str2bool, nargs="?", default="false", help="Whether use batch normalization.")
     p.add_argument("--keep_prob", type=float, default=1.0, help="The probability that each element is kept for dropout.")
+    p.add_argument("--ckpt_format", type=str, default="pt", choices=["pt", "tf"],
+                   help="Checkpoint container: torch state dict, or TensorFlow checkpoint-V2 bundles as the reference's "
+                        "Saver writes them (either kind is read on resume / decode).")
     p.add_argument("--init_disc_noise_std", type=float, default=0.0, help="Noise std for discriminator.")
     p.add_argument("--l2_scale", type=float, default=0.00001, help="Scale used for L2 regularizer.")
     p.add_argument("--num_gpu", type=int, default=1, help="Number of GPU to use (= WORLD_SIZE under torchrun).")
