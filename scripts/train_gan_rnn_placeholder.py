@@ -315,8 +315,11 @@ def build_parser():
     p.add_argument("--g_cell", type=int, default=None)
     p.add_argument("--g_proj", type=int, default=None)
     p.add_argument("--g_layers", type=int, default=None)
+    p.add_argument("--g_units", type=int, default=None, help="hidden width of the dnn generator (models/dnn.py:34)")
     p.add_argument("--d_cell", type=int, default=None)
+    p.add_argument("--d_proj", type=int, default=None)
     p.add_argument("--d_layers", type=int, default=None)
+    p.add_argument("--d_units", type=int, default=None, help="hidden width of discriminator_dnn (:23)")
     p.add_argument("--dtype", type=str, default="f16", help="tensor-core operand type: f16 | bf16")
     p.add_argument("--seed", type=int, default=1234)
     return p

@@ -51,13 +51,20 @@ def _run(args):
     return r.stdout
 
 
-def test_train_resume_decode(tmp_path):
+@pytest.mark.parametrize("extra", [[], ["--batch_norm", "true", "--keep_prob", "0.9", "--ckpt_format", "tf",
+                                        "--d_type", "dnn", "--d_units", "128"]],
+                         ids=["plain", "batch_norm-dropout-tf_checkpoints"])
+def test_train_resume_decode(tmp_path, extra):
+    """`extra`: the optional pieces of the same driver surface -- --batch_norm / --keep_prob (first-layer batch_norm and
+    DropoutWrapper in the lstm generator, batch_norm + dropout in discriminator_dnn) and TensorFlow checkpoint-V2
+    bundles as the container that is saved, resumed from and decoded from."""
     d = str(tmp_path)
     lens = _make_data(d)
     save = os.path.join(d, "exp")
     common = ["--data_dir", d, "--save_dir", save, "--batch_size", "4", "--left_context", "0", "--right_context", "0",
               "--g_type", "lstm", "--d_type", "lstm", "--g_cell", "256", "--g_proj", "64", "--g_layers", "1",
               "--init_mse_weight", "10.0", "--init_disc_noise_std", "0.05", "--num_threads", "2", "--l2_scale", "0"]
+    common += extra
     out = _run(common + ["--tr_list_file", os.path.join(d, "tr.list"), "--cv_list_file", os.path.join(d, "cv.list"),
                          "--min_epoches", "2", "--max_epoches", "2"])
     pat = re.compile(r"(\d+)/(\d+) \((TRAIN|CROSS) AVG\.LOSS\): d_rl_loss = ([-\d.e+]+), d_fk_loss = ([-\d.e+]+), "
@@ -69,6 +76,11 @@ def test_train_resume_decode(tmp_path):
         vals = [float(v) for v in l[3:]]
         assert all(np.isfinite(vals)) and vals[2] == pytest.approx(vals[0] + vals[1], rel=1e-3, abs=1e-4)
     assert os.path.exists(os.path.join(save, "checkpoint"))
+    if "tf" in extra:
+        from rsrgan_b200 import tf_checkpoint
+        latest, _ = tf_checkpoint.read_checkpoint_state(save)
+        names = tf_checkpoint.read_bundle(os.path.join(save, latest))
+        assert "g_model/fully_connected/BatchNorm/gamma" in names and "d_model/fully_connected/BatchNorm/moving_mean" in names
     # second invocation on the same save_dir resumes (run_gan_rnn_placeholder.sh runs the script twice, :117-168)
     out2 = _run(common + ["--tr_list_file", os.path.join(d, "tr.list"), "--cv_list_file", os.path.join(d, "cv.list"),
                           "--min_epoches", "1", "--max_epoches", "1", "--d_learning_rate", "0.0003"])
