@@ -373,10 +373,10 @@ class GAN_RNN(Model):
 
     def _update(self, net, gscale, adam):
         P, h = net.P, self.h
-        for n in (self.G, self.D):                         # next update draws new dropout masks in both networks
-            if n is not None:
-                n.tick()
         h.join()                                           # weight gradients computed on the side stream
+        for n in (self.G, self.D):                         # next update draws new dropout masks in both networks; only
+            if n is not None:                              # after the join: backward passes on the side stream regenerate
+                n.tick()                                   # their masks from the current tick
         if self.world > 1:
             # utils/ops.py:343-376 average_gradients: sum over ranks here, 1/N folded into the update kernel
             if self._cap is not None:
