@@ -34,6 +34,12 @@ MSE_CASES = {
     "mse_rced": ("rced", dict(), 6),
 }
 
+# the dnn generator as run_dnn_single_gpu.sh trains it (:129-145): batch_norm(renorm) + dropout + l2, UPDATE_OPS with
+# every step.  name -> (sizes, frames, keep_prob, dropout seed)
+BN_CASES = {
+    "mse_dnn_bn": (dict(g_units=64), 40, 0.8, 11),
+}
+
 
 def build(name):
     g_type, d_type, sz, B, T = CASES[name]
@@ -123,14 +129,49 @@ def compute_mse(name, l2_scale=1e-4, lr=1e-3, steps=2):
     return out
 
 
+def compute_mse_bn(name, l2_scale=1e-4, lr=1e-3, steps=3):
+    """Batch-normalised dnn generator: weights (gamma / beta perturbed), training-graph output / losses / raw gradients
+    of the first step (dropout tick 0), then `steps` Adam updates with the UPDATE_OPS on fresh minibatches: the
+    non-trainable batch_norm variables and the INFERENCE-graph output (moving averages, no dropout) afterwards."""
+    sz, N, keep, seed = BN_CASES[name]
+    rng = np.random.default_rng(sum(map(ord, name)))
+    gp = O.init_g_dnn(rng, units=sz["g_units"], batch_norm=True)
+    for k in gp:
+        if "bias" in k or "BatchNorm" in k:
+            gp[k] = gp[k] + rng.standard_normal(gp[k].shape) * 0.1
+    out = OrderedDict(x=rng.standard_normal((steps, N, 257)).astype(np.float32),
+                      y=rng.standard_normal((steps, N, 40)).astype(np.float32),
+                      l2_scale=np.float64(l2_scale), lr=np.float64(lr), steps=np.int32(steps),
+                      keep_prob=np.float64(keep), seed=np.int64(seed))
+    for k, v in gp.items():
+        out["G/" + k] = v.astype(np.float32)
+    st = O.MseState(OrderedDict((k, out["G/" + k].astype(np.float64)) for k in gp), "dnn")
+    bst = O.init_bn_state(st.g)
+    x64, y64 = out["x"].astype(np.float64), out["y"].astype(np.float64)
+    opts = lambda tick, update: dict(bn_state=bst, update=update, keep_prob=keep, rng=(seed, tick))
+    L, gr, g_out = O.mse_losses_and_grads(st.g, "dnn", x64[0], y64[0], l2_scale, opts(0, False))
+    out["g_out"] = g_out
+    for k, v in L.items():
+        out["loss/" + k] = np.float64(v)
+    for k, v in gr.items():
+        out["ggrad/" + k] = v.astype(np.float32)
+    for t in range(steps):
+        L, _ = O.mse_step(st, x64[t], y64[t], lr, l2_scale, opts(t, True))
+        out["loss_step%d/g_mse_loss" % t] = np.float64(L["g_mse_loss"])
+    for k, v in bst.items():
+        out["BN/" + k] = np.asarray(v, np.float64)
+    out["g_out_after"], _ = O.g_dnn_fwd(st.g, x64[0], None, opts=dict(bn_state=bst, train=False))
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     import sys
     only = sys.argv[1:]
-    for name in list(CASES) + list(MSE_CASES):
+    for name in list(CASES) + list(MSE_CASES) + list(BN_CASES):
         if only and name not in only:
             continue
-        d = compute(name) if name in CASES else compute_mse(name)
+        d = compute(name) if name in CASES else compute_mse(name) if name in MSE_CASES else compute_mse_bn(name)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
         print("wrote", name, os.path.getsize(os.path.join(OUT, name + ".npz")), "bytes")
 

@@ -333,3 +333,46 @@ def test_lstm_generator_dropout_wrapper(g_type, kw):
     go = dict(bn_state=O.init_bn_state(gp), keep_prob=0.8, rng=(5, n0 + 5))          # last G update of the 2nd schedule
     L2, _, _ = O.tower_losses_and_grads(st, x.astype(np.float64), y.astype(np.float64), ln, "g", g_opts=go)
     assert o2["g_mse_loss"] == pytest.approx(L2["g_mse_loss"], rel=3e-3)
+
+
+def _run_golden_mse_dnn_bn(handle, tol_w, tol_state, tol_out):
+    """tests/golden/mse_dnn_bn.npz (oracle/make_golden.py): batch-normalised dnn generator with dropout + l2 under
+    DNNTrainer, three Adam steps with the UPDATE_OPS, then the inference graph."""
+    import os
+    from rsrgan_b200.dnn_trainer import DNNTrainer
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mse_dnn_bn.npz"))
+    gp = OrderedDict((k[2:], z[k]) for k in z.files if k.startswith("G/"))
+    N = z["x"].shape[1]
+    args = Namespace(g_type="dnn", batch_size=N, g_units=64, batch_norm=True, keep_prob=float(z["keep_prob"]),
+                     l2_scale=float(z["l2_scale"]), g_learning_rate=float(z["lr"]), seed=int(z["seed"]), dtype="f16")
+    m = DNNTrainer(None, args, ["/gpu:0"], **({"handle": handle} if handle is not None else {}))
+    m.load_params(gp)
+    # raw gradients of the first step (learning rate 0 keeps the weights; the UPDATE_OPS are switched off so that
+    # the statistics stay at their initial values for the steps below)
+    m.g_learning_rate, m.update_bn_stats = 0.0, False
+    out = m.train_step(z["x"][0], z["y"][0])
+    assert out["g_mse_loss"] == pytest.approx(float(z["loss/g_mse_loss"]), rel=3e-3)
+    assert out["g_l2_loss"] == pytest.approx(float(z["loss/g_l2_loss"]), rel=1e-3)
+    gs = m._gscale(N)
+    mine = m.G.P.export_tf("grad")
+    for k in gp:
+        assert rel(mine[k] / gs, z["ggrad/" + k]) < 5e-2, k
+    # the same model again from tick 0: Adam state and dropout stream reset by a fresh trainer
+    m = DNNTrainer(None, args, ["/gpu:0"], **({"handle": handle} if handle is not None else {}))
+    m.load_params(gp)
+    for t in range(int(z["steps"])):
+        out = m.train_step(z["x"][t], z["y"][t])
+        assert out["g_mse_loss"] == pytest.approx(float(z["loss_step%d/g_mse_loss" % t]), rel=tol_w), t
+    st = m.G.bn_state_tf()
+    for k in st:
+        assert rel(np.asarray(st[k]) + 1.0, z["BN/" + k] + 1.0) < tol_state, k
+    cv = DNNTrainer(None, args, ["/gpu:0"], cross_validation=True, share=m)
+    g = cv.generate(z["x"][0])
+    g = g.cpu().numpy() if hasattr(g, "cpu") else np.asarray(g)
+    assert rel(g, z["g_out_after"]) < tol_out
+
+
+def test_golden_mse_dnn_bn():
+    # weights after three Adam steps carry the sign noise of near-zero gradients (see the reference-driver-shape test),
+    # hence the loose bar on the inference output; the statistics and the per-step losses are tight
+    _run_golden_mse_dnn_bn(None, 5e-3, 1e-3, 5e-2)

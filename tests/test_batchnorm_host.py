@@ -299,3 +299,44 @@ def test_lstm_generator_dropout_wrapper_matches_oracle(g_type):
 
 
 GEN_FWD = {k: v[0] for k, v in O.GENERATORS.items()}
+
+
+def _run_golden_mse_dnn_bn(handle, tol_w, tol_state, tol_out):
+    """tests/golden/mse_dnn_bn.npz (oracle/make_golden.py): batch-normalised dnn generator with dropout + l2 under
+    DNNTrainer, three Adam steps with the UPDATE_OPS, then the inference graph."""
+    import os
+    from rsrgan_b200.dnn_trainer import DNNTrainer
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mse_dnn_bn.npz"))
+    gp = OrderedDict((k[2:], z[k]) for k in z.files if k.startswith("G/"))
+    N = z["x"].shape[1]
+    args = Namespace(g_type="dnn", batch_size=N, g_units=64, batch_norm=True, keep_prob=float(z["keep_prob"]),
+                     l2_scale=float(z["l2_scale"]), g_learning_rate=float(z["lr"]), seed=int(z["seed"]), dtype="f16")
+    m = DNNTrainer(None, args, ["/gpu:0"], **({"handle": handle} if handle is not None else {}))
+    m.load_params(gp)
+    # raw gradients of the first step (learning rate 0 keeps the weights; the UPDATE_OPS are switched off so that
+    # the statistics stay at their initial values for the steps below)
+    m.g_learning_rate, m.update_bn_stats = 0.0, False
+    out = m.train_step(z["x"][0], z["y"][0])
+    assert out["g_mse_loss"] == pytest.approx(float(z["loss/g_mse_loss"]), rel=3e-3)
+    assert out["g_l2_loss"] == pytest.approx(float(z["loss/g_l2_loss"]), rel=1e-3)
+    gs = m._gscale(N)
+    mine = m.G.P.export_tf("grad")
+    for k in gp:
+        assert rel(mine[k] / gs, z["ggrad/" + k]) < 5e-2, k
+    # the same model again from tick 0: Adam state and dropout stream reset by a fresh trainer
+    m = DNNTrainer(None, args, ["/gpu:0"], **({"handle": handle} if handle is not None else {}))
+    m.load_params(gp)
+    for t in range(int(z["steps"])):
+        out = m.train_step(z["x"][t], z["y"][t])
+        assert out["g_mse_loss"] == pytest.approx(float(z["loss_step%d/g_mse_loss" % t]), rel=tol_w), t
+    st = m.G.bn_state_tf()
+    for k in st:
+        assert rel(np.asarray(st[k]) + 1.0, z["BN/" + k] + 1.0) < tol_state, k
+    cv = DNNTrainer(None, args, ["/gpu:0"], cross_validation=True, share=m)
+    g = cv.generate(z["x"][0])
+    g = g.cpu().numpy() if hasattr(g, "cpu") else np.asarray(g)
+    assert rel(g, z["g_out_after"]) < tol_out
+
+
+def test_golden_mse_dnn_bn_host_wiring():
+    _run_golden_mse_dnn_bn(FakeHandle("f16"), 5e-3, 1e-3, 5e-2)
