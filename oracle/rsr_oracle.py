@@ -851,27 +851,32 @@ class GanState(object):
         self.g_type, self.d_type = g_type, d_type
         z = lambda p: OrderedDict((k, np.zeros_like(v)) for k, v in p.items())
         self.adam_m, self.adam_v, self.adam_t = z(g_params), z(g_params), 0
+        self.d_adam_m, self.d_adam_v, self.d_adam_t = z(d_params), z(d_params), 0   # models/gan.py:125 (Adam for D)
         self.g_ema = OrderedDict((k, v.copy()) for k, v in g_params.items())
         self.d_ema = OrderedDict((k, v.copy()) for k, v in d_params.items())
 
 
 def tower_losses_and_grads(st, x, y, lengths, which, noise_rl=None, noise_fk=None,
-                           mse_lambda=10.0, d_real=1.0, d_fake=0.0, l2_scale=0.0, g_opts=None, d_opts=None):
+                           mse_lambda=10.0, d_real=1.0, d_fake=0.0, l2_scale=0.0, g_opts=None, d_opts=None,
+                           d_cat=None, l2_weights_only=False):
     """One tower of build_model_single_gpu (gan_rnn_placeholder.py:191-298) plus
     compute_gradients wrt d_vars (which='d') or g_vars (which='g')."""
     gf, gb = GENERATORS[st.g_type]
     df, db_ = DISCRIMINATORS[st.d_type]
     # g_opts / d_opts: batch_norm state, dropout stream (fc_block_fwd); salts: G layers 0.., D(labels) 256.., D(G(x)) 512..
     g_out, gc = gf(st.g, x, lengths) if g_opts is None else gf(st.g, x, lengths, opts=g_opts, salt0=0)
+    # d_cat = (c0, c1): the frame-level GAN of models/gan.py:159-174 feeds D tf.concat([inputs[..., c0:c1], .], -1)
+    d_in = (lambda v: v) if d_cat is None else (lambda v: np.concatenate([x[..., d_cat[0]:d_cat[1]], v], -1))
     if d_opts is None:
-        lr_, crl = df(st.d, y, lengths, noise_rl)
-        lf_, cfk = df(st.d, g_out, lengths, noise_fk)
+        lr_, crl = df(st.d, d_in(y), lengths, noise_rl)
+        lf_, cfk = df(st.d, d_in(g_out), lengths, noise_fk)
     else:
-        lr_, crl = df(st.d, y, lengths, noise_rl, opts=d_opts, salt0=256)
-        lf_, cfk = df(st.d, g_out, lengths, noise_fk, opts=d_opts, salt0=512)
+        lr_, crl = df(st.d, d_in(y), lengths, noise_rl, opts=d_opts, salt0=256)
+        lf_, cfk = df(st.d, d_in(g_out), lengths, noise_fk, opts=d_opts, salt0=512)
     losses = lsgan_mse_losses(lr_, lf_, g_out, y, d_real, d_fake, mse_lambda, y.shape[-1])
+    reg = (lambda k: k.endswith("weights")) if l2_weights_only else (lambda k: "bias" not in k)
     if l2_scale > 0.0:
-        losses["g_l2_loss"] = l2_loss_g(st.g, l2_scale)
+        losses["g_l2_loss"] = l2_scale * sum(0.5 * float((v * v).sum()) for k, v in st.g.items() if reg(k))
         losses["g_loss"] += losses["g_l2_loss"]
     n_logit = lr_.size
     if which == "d":
@@ -880,23 +885,30 @@ def tower_losses_and_grads(st, x, y, lengths, which, noise_rl=None, noise_fk=Non
         grads = OrderedDict((k, g_rl[k] + g_fk[k]) for k in st.d)
     else:
         dg_adv, _ = db_(st.d, 2.0 * (lf_ - d_real) / n_logit, cfk)
+        if d_cat is not None:
+            dg_adv = dg_adv[..., d_cat[1] - d_cat[0]:]          # the generator's block of the concatenated input
         dg = dg_adv + mse_lambda * 0.5 * y.shape[-1] * 2.0 * (g_out - y) / g_out.size
         _, gg = gb(st.g, dg, gc)
         grads = OrderedDict((k, gg[k]) for k in st.g)
         if l2_scale > 0.0:
             for k in grads:
-                if "bias" not in k:
+                if reg(k):
                     grads[k] = grads[k] + l2_scale * st.g[k]
     return losses, grads, g_out
 
 
-def d_step(st, towers, lr_d, max_norm=15.0, ema_decay=0.9999, **kw):
-    """towers: list of dicts(x, y, lengths, noise_rl, noise_fk). SGD on theta_D."""
+def d_step(st, towers, lr_d, max_norm=15.0, ema_decay=0.9999, adam=False, **kw):
+    """towers: list of dicts(x, y, lengths, noise_rl, noise_fk). SGD on theta_D (gan_rnn_placeholder.py:144), or Adam
+    (adam=True: models/gan.py:125)."""
     res = [tower_losses_and_grads(st, t["x"], t["y"], t["lengths"], "d",
                                   t.get("noise_rl"), t.get("noise_fk"), **kw) for t in towers]
     avg = average_gradients([r[1] for r in res])
     clipped = OrderedDict((k, clip_by_norm(v, max_norm)) for k, v in avg.items())
-    st.d = sgd_update(st.d, clipped, lr_d)
+    if adam:
+        st.d, st.d_adam_m, st.d_adam_v, st.d_adam_t = adam_update_tf(
+            st.d, clipped, st.d_adam_m, st.d_adam_v, st.d_adam_t, lr_d)
+    else:
+        st.d = sgd_update(st.d, clipped, lr_d)
     st.d_ema = ema_update(st.d_ema, st.d, ema_decay)
     return [r[0] for r in res], clipped
 

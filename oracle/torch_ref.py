@@ -177,15 +177,16 @@ DIS = {"lstm": d_lstm, "dnn": d_dnn}
 
 
 def losses(gp, dp, g_type, d_type, x, y, lengths, noise_rl=None, noise_fk=None,
-           mse_lambda=10.0, d_real=1.0, d_fake=0.0, g_opts=None, d_opts=None):
-    """models/gan_rnn_placeholder.py:196-260."""
+           mse_lambda=10.0, d_real=1.0, d_fake=0.0, g_opts=None, d_opts=None, d_cat=None):
+    """models/gan_rnn_placeholder.py:196-260; d_cat = (c0, c1): models/gan.py:159-174 (D sees concat([x[c0:c1], .]))."""
     g = GEN[g_type](gp, x, lengths) if g_opts is None else GEN[g_type](gp, x, lengths, opts=g_opts, salt0=0)
+    d_in = (lambda v: v) if d_cat is None else (lambda v: torch.cat([x[..., d_cat[0]:d_cat[1]], v], -1))
     if d_opts is None:
-        rl = DIS[d_type](dp, y, lengths, noise_rl)
-        fk = DIS[d_type](dp, g, lengths, noise_fk)
+        rl = DIS[d_type](dp, d_in(y), lengths, noise_rl)
+        fk = DIS[d_type](dp, d_in(g), lengths, noise_fk)
     else:
-        rl = DIS[d_type](dp, y, lengths, noise_rl, opts=d_opts, salt0=256)
-        fk = DIS[d_type](dp, g, lengths, noise_fk, opts=d_opts, salt0=512)
+        rl = DIS[d_type](dp, d_in(y), lengths, noise_rl, opts=d_opts, salt0=256)
+        fk = DIS[d_type](dp, d_in(g), lengths, noise_fk, opts=d_opts, salt0=512)
     d_rl = ((rl - d_real) ** 2).mean()
     d_fk = ((fk - d_fake) ** 2).mean()
     g_adv = ((fk - d_real) ** 2).mean()

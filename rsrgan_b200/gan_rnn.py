@@ -189,7 +189,10 @@ class GAN_RNN(Model):
             self.G = nets.Generator(self.h, self.g_type, **gk)
             self.D = None
             if not infer:
-                dk = dict(in_dim=self.output_dim, batch_norm=bool(self.batch_norm), keep_prob=self.keep_prob)
+                # d_cat_dim / d_adam: the frame-level GAN of models/gan.py (rsrgan_b200/gan.py) conditions
+                # discriminator_dnn on the centre LPS frame and trains it with Adam
+                dk = dict(in_dim=self.output_dim, batch_norm=bool(self.batch_norm), keep_prob=self.keep_prob,
+                          cat_dim=_arg(args, "d_cat_dim", 0), adam=bool(_arg(args, "d_adam", False)))
                 for k_arg, k in (("d_cell", "cell"), ("d_proj", "proj"), ("d_layers", "layers"), ("d_units", "units")):
                     v = _arg(args, k_arg, None)
                     if v is not None:
@@ -346,6 +349,14 @@ class GAN_RNN(Model):
             self.h.stage_input(y, B, T, self.output_dim, out32=y_tm)
         return x, y_tm, ln, B, T
 
+    def _cat(self, x):
+        """Conditioning block of the discriminator input (models/gan.py:159-160: tf.slice(inputs, [0, input_dim *
+        left_context], [-1, input_dim]) -- the centre frame of the spliced LPS input), as a view of the fed batch."""
+        if self.D is None or not self.D.cat_dim:
+            return None
+        c0 = self.input_dim * self.left_context
+        return x[:, :, c0:c0 + self.D.cat_dim]
+
     def _noise(self, B, given, slot="rl"):
         if self.d_type != "lstm":
             return None                                    # discriminator_dnn has no noise layer
@@ -434,16 +445,16 @@ class GAN_RNN(Model):
         # D(labels) does not depend on the generator: its forward, loss and backward run on the side stream
         # while the generator recurrences (which occupy only the SMs of their clusters) run on this one.
         with h.side_stream():
-            lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=n_rl)
+            lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=n_rl, cat_src=self._cat(x))
             h.lsgan_mse_losses(self._losses, rl=lg_rl, ld_logit=lg_rl.stride(0), d_rl_grad=d_rl16, **kw)
             D.bwd("rl", d_rl16)
         g32 = _g32 if _g32 is not None else G.fwd(x, B, T, ln, train=_g_train)
         self._last_g32 = g32
-        lg_fk = D.fwd("fk", g32, B, T, ln, noise=n_fk)
+        lg_fk = D.fwd("fk", g32, B, T, ln, noise=n_fk, cat_src=self._cat(x))
         h.lsgan_mse_losses(self._losses, fk=lg_fk, ld_logit=lg_fk.stride(0), g=g32, y=y_tm, n_frames=rows,
                            d_out=self.output_dim, d_fk_grad=d_fk16, **kw)
         D.bwd("fk", d_fk16)
-        self._update(D, gs, adam=False)
+        self._update(D, gs, adam=D.P.adam)
         return self._loss_dict(self._losses.tolist(), "d") if sync else self._losses
 
     def g_step(self, inputs, labels, lengths, noise_fk=None, sync=True, _feed=None, _g32=None, _x_staged=False):
@@ -454,9 +465,12 @@ class GAN_RNN(Model):
         self._mode(True)
         gs = self._gscale(rows)
         g32 = _g32 if _g32 is not None else G.fwd(x, B, T, ln, train=True, reuse_staged=_x_staged)
-        lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"))
+        lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"), cat_src=self._cat(x))
         g_adv16 = D.ws.get(("loss", "g_adv16"), rows, 8, h.h16)
-        dg32 = D.ws.get(("loss", "dg32"), rows, g32.shape[1], F32)
+        # d(lambda g_mse)/dg is added to the discriminator's input gradient by its last GEMM (resid): same width as
+        # that input -- the generator's columns come first, the conditioning columns of a conditioned D stay zero
+        dw = g32.shape[1] if not D.cat_dim else (D.in_dim + D.cat_dim + 7) // 8 * 8
+        dg32 = D.ws.get(("loss", "dg32"), rows, dw, F32)
         self._losses.zero_()
         h.lsgan_mse_losses(self._losses, fk=lg_fk, ld_logit=lg_fk.stride(0), n_logit=rows, clip=D.clip,
                            g=g32, y=y_tm, n_frames=rows, d_out=self.output_dim, d_real=self.d_real,
@@ -464,7 +478,7 @@ class GAN_RNN(Model):
                            ld_grad=8, dg_mse=dg32)
         dg16 = D.bwd("fk", g_adv16, want_dw=False, want_dx=True, resid32=dg32)
         h.fill32(G.P.grad, 0.0)
-        G.bwd(dg16)
+        G.bwd(dg16[:, :g32.shape[1]] if D.cat_dim else dg16)
         self._l2_loss()
         if self.l2_scale > 0.0:
             h.l2_grad(G.P.grad, G.P.theta, G.P.seg_id, G.P.seg_l2, self.l2_scale * gs)
@@ -640,8 +654,8 @@ class GAN_RNN(Model):
         h, G, D, rows = self.h, self.G, self.D, T * B
         self._mode(False)
         g32 = G.fwd(x, B, T, ln, train=False)
-        lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=self._noise(B, noise_rl), train=False)
-        lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"), train=False)
+        lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=self._noise(B, noise_rl), train=False, cat_src=self._cat(x))
+        lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"), train=False, cat_src=self._cat(x))
         self._losses.zero_()
         h.lsgan_mse_losses(self._losses, rl=lg_rl, fk=lg_fk, ld_logit=lg_rl.stride(0), n_logit=rows, clip=D.clip,
                            g=g32, y=y_tm, n_frames=rows, d_out=self.output_dim, d_real=self.d_real,

@@ -47,13 +47,19 @@ class FC(object):
     """tf.contrib.layers.fully_connected over the last axis (models/lstm.py:82-87,121-124;
     models/discriminator_dnn.py:61-93; models/discriminator_lstm.py:100-104; models/dnn.py:79-110)."""
 
-    def __init__(self, net, scope, n_in, n_out, act):
+    def __init__(self, net, scope, n_in, n_out, act, cat=None):
         self.net, self.scope, self.n_in, self.n_out, self.act = net, scope, n_in, n_out, act
         self.inp, self.outp = packing.round_up(n_in, 8), packing.round_up(n_out, 8)
         self.wname, self.bname = scope + "/weights", scope + "/biases"
+        self.cat = cat          # (n_a, n_b): the input is tf.concat([a, b], -1), stored [b | a] on the device
+
+    def _wseg(self):
+        if self.cat is not None:
+            return params.fc_w_cat(self.wname, self.cat[0], self.cat[1], self.n_out)
+        return params.fc_w(self.wname, self.n_in, self.n_out)
 
     def segs(self):
-        return [params.fc_w(self.wname, self.n_in, self.n_out), params.fc_b(self.bname, self.n_out)]
+        return [self._wseg(), params.fc_b(self.bname, self.n_out)]
 
     def refresh(self):
         pass
@@ -110,8 +116,8 @@ class FCBN(FC):
     STATE_KEYS = ("moving_mean", "moving_variance", "renorm_mean", "renorm_stddev", "renorm_mean_weight",
                   "renorm_stddev_weight")
 
-    def __init__(self, net, scope, n_in, n_out, act, bn, index, drop=True):
-        super(FCBN, self).__init__(net, scope, n_in, n_out, act)
+    def __init__(self, net, scope, n_in, n_out, act, bn, index, drop=True, cat=None):
+        super(FCBN, self).__init__(net, scope, n_in, n_out, act, cat=cat)
         self.bn, self.index, self.drop = bool(bn), index, drop
         self.betaname, self.gname = scope + "/BatchNorm/beta", scope + "/BatchNorm/gamma"
         self.state = None
@@ -124,8 +130,7 @@ class FCBN(FC):
     def segs(self):
         if not self.bn:
             return super(FCBN, self).segs()
-        return [params.fc_w(self.wname, self.n_in, self.n_out), params.fc_b(self.betaname, self.n_out),
-                params.fc_b(self.gname, self.n_out)]
+        return [self._wseg(), params.fc_b(self.betaname, self.n_out), params.fc_b(self.gname, self.n_out)]
 
     def _bufs(self, ctx, rows):
         ws = self.net.ws
@@ -702,8 +707,13 @@ class Generator(Net):
 
 class Discriminator(Net):
     def __init__(self, handle, d_type="lstm", in_dim=40, cell=256, proj=40, layers=None, units=1024,
-                 batch_norm=False, keep_prob=1.0):
-        self.d_type, self.in_dim = d_type, in_dim
+                 batch_norm=False, keep_prob=1.0, cat_dim=0, adam=False):
+        """cat_dim > 0 (discriminator_dnn only): the discriminator sees tf.concat([conditioning (cat_dim), x (in_dim)], -1)
+        as in the frame-level GAN (models/gan.py:159-174, conditioning = centre-frame LPS).  adam: Adam instead of SGD
+        for this network (models/gan.py:125 vs models/gan_rnn_placeholder.py:144)."""
+        self.d_type, self.in_dim, self.cat_dim = d_type, in_dim, int(cat_dim)
+        if cat_dim and d_type != "dnn":
+            raise ValueError("a conditioned discriminator input is only defined for discriminator_dnn (models/gan.py)")
         # discriminator_lstm builds normalizer_params / keep_prob but uses neither (models/discriminator_lstm.py:37-52,
         # 64): both are no-ops there, as in the reference
         self.keep_prob = float(keep_prob) if d_type == "dnn" else 1.0
@@ -722,27 +732,32 @@ class Discriminator(Net):
             L = 3 if layers is None else layers
 
             def mk(net):
-                dims = [in_dim] + [units] * (L + 1)
+                dims = [in_dim + self.cat_dim] + [units] * (L + 1)
                 name = lambda i: "d_model/fully_connected" + ("" if i == 0 else "_%d" % i)
+                cat = lambda i: (self.cat_dim, in_dim) if (i == 0 and self.cat_dim) else None
                 if special:
-                    ls = [FCBN(net, name(i), dims[i], dims[i + 1], ACT_RELU, batch_norm, i) for i in range(L + 1)]
+                    ls = [FCBN(net, name(i), dims[i], dims[i + 1], ACT_RELU, batch_norm, i, cat=cat(i))
+                          for i in range(L + 1)]
                 else:
-                    ls = [FC(net, name(i), dims[i], dims[i + 1], ACT_RELU) for i in range(L + 1)]
+                    ls = [FC(net, name(i), dims[i], dims[i + 1], ACT_RELU, cat=cat(i)) for i in range(L + 1)]
                 return ls + [FC(net, "d_model/fully_connected_%d" % (L + 1), units, 1, ACT_NONE)]
         else:
             raise ValueError("Unrecognized D type {}".format(d_type))
-        super(Discriminator, self).__init__(handle, mk, adam=False)
+        super(Discriminator, self).__init__(handle, mk, adam=adam)
         self.clip = d_type == "dnn"
         self._ctx = {}
 
-    def fwd(self, ctx, x32_tm, B, T, lengths, noise=None, train=True):
+    def fwd(self, ctx, x32_tm, B, T, lengths, noise=None, train=True, cat_src=None):
         """x32_tm fp32 [T*B, ld] time-major (labels or generator output); noise fp32 (B, in_dim) or None
-        (utils/ops.py:19-30: ONE draw per utterance broadcast over time).  Returns logits32 [T*B, 8]
-        (column 0; pre-clip for the DNN discriminator)."""
+        (utils/ops.py:19-30: ONE draw per utterance broadcast over time).  cat_src: the conditioning block of a
+        conditioned discriminator, an fp32 batch-major (B, T, cat_dim) VIEW of the generator's input (row pitch = its
+        stride).  Returns logits32 [T*B, 8] (column 0; pre-clip for the DNN discriminator)."""
         h, ws, rows = self.h, self.ws, T * B
-        ip = packing.round_up(self.in_dim, 8)
+        ip = packing.round_up(self.in_dim + self.cat_dim, 8)
         x16 = ws.get((ctx, "x16", B), rows, ip, h.h16)
         h.stage_input(x32_tm, B, T, self.in_dim, out16=x16, noise=noise, time_major_in=True)
+        if self.cat_dim:      # device column order [x | conditioning], see params.fc_w_cat
+            h.stage_input(cat_src, B, T, self.cat_dim, out16=x16[:, self.in_dim:], ldx=cat_src.stride(1))
         acts = [x16]
         a = x16
         if self.d_type == "lstm":

@@ -36,6 +36,14 @@ def fc_w(name, n_in, n_out):
     return Seg(name, "fc_w", (n_in, n_out), (packing.round_up(n_in, 8), packing.round_up(n_out, 8)))
 
 
+def fc_w_cat(name, n_a, n_b, n_out):
+    """First-layer weight of a fully_connected fed tf.concat([a, b], -1) (models/gan.py:159-174: a = centre-frame LPS,
+    b = MFCC).  TF rows are [a ; b]; the device rows are [b ; a ; zero pad] so that the b block -- the part of the data
+    gradient that continues into the generator -- starts at column 0 of the activation buffer (16-byte aligned for TMA)."""
+    return Seg(name, "fc_w_cat", (n_a + n_b, n_out), (packing.round_up(n_a + n_b, 8), packing.round_up(n_out, 8)),
+               dict(n_a=n_a, n_b=n_b))
+
+
 def fc_b(name, n_out):
     return Seg(name, "vec", (n_out,), (packing.round_up(n_out, 8),))
 
@@ -76,6 +84,10 @@ def to_dev_layout(seg, a):
     out = np.zeros(seg.dev_shape, dtype=np.float32)
     if seg.kind == "fc_w":
         out[:a.shape[0], :a.shape[1]] = a
+    elif seg.kind == "fc_w_cat":
+        n_a, n_b = seg.meta["n_a"], seg.meta["n_b"]
+        out[:n_b, :a.shape[1]] = a[n_a:]
+        out[n_b:n_b + n_a, :a.shape[1]] = a[:n_a]
     elif seg.kind in ("vec", "peep"):
         out[:a.shape[0]] = a
     elif seg.kind == "lstm_bias":
@@ -102,6 +114,9 @@ def from_dev_layout(seg, d):
     d = np.asarray(d).reshape(seg.dev_shape)
     if seg.kind == "fc_w":
         return d[:seg.tf_shape[0], :seg.tf_shape[1]].copy()
+    if seg.kind == "fc_w_cat":
+        n_a, n_b = seg.meta["n_a"], seg.meta["n_b"]
+        return np.concatenate([d[n_b:n_b + n_a, :seg.tf_shape[1]], d[:n_b, :seg.tf_shape[1]]], 0)
     if seg.kind in ("vec", "peep"):
         return d[:seg.tf_shape[0]].copy()
     if seg.kind == "lstm_bias":

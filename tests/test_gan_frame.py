@@ -1,0 +1,169 @@
+"""The frame-level GAN of models/gan.py (rsrgan_b200/gan.py): dnn generator, discriminator_dnn on
+concat([centre LPS frame, MFCC]), Adam for both networks, no gradient clipping, UPDATE_OPS with every step.
+CPU: oracle vs autograd, host wiring through the test double.  GPU (-m gpu): the same checks on the kernels."""
+import copy
+import os
+import sys
+from argparse import Namespace
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from fake_handle import FakeHandle  # noqa: E402
+
+from oracle import rsr_oracle as O  # noqa: E402
+from oracle import torch_ref as R  # noqa: E402
+from rsrgan_b200 import params  # noqa: E402
+from rsrgan_b200.gan import GAN  # noqa: E402
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.sqrt(((a - b) ** 2).mean()) / (np.sqrt((b ** 2).mean()) + 1e-30))
+
+
+def test_concat_weight_layout_roundtrip():
+    s = params.fc_w_cat("w", 257, 40, 64)
+    assert s.dev_shape == (304, 64)
+    t = np.random.default_rng(0).standard_normal((297, 64)).astype(np.float32)
+    d = params.to_dev_layout(s, t)
+    assert np.array_equal(d[:40], t[257:]) and np.array_equal(d[40:297], t[:257]) and not d[297:].any()
+    assert np.array_equal(params.from_dev_layout(s, d), t)
+
+
+@pytest.mark.parametrize("which", ["d", "g"])
+def test_oracle_conditioned_discriminator_matches_autograd(which):
+    rng = np.random.default_rng(2)
+    gp = O.init_g_dnn(rng, in_dim=3 * 12, out_dim=5, units=16, hidden=1)
+    dp = O.init_d_dnn(rng, in_dim=12 + 5, units=16, hidden=1)
+    x, y, ln = rng.standard_normal((7, 1, 36)), rng.standard_normal((7, 1, 5)), np.ones(7, int)
+    st = O.GanState(gp, dp, "dnn", "dnn")
+    L, G, _ = O.tower_losses_and_grads(st, x, y, ln, which, d_cat=(12, 24), l2_scale=1e-3, l2_weights_only=True)
+    Lt, Gt, _ = R.grads(R.to_torch(gp, requires_grad=True), R.to_torch(dp, requires_grad=True), "dnn", "dnn",
+                        torch.tensor(x), torch.tensor(y), ln, which, d_cat=(12, 24))
+    for k in ("d_rl_loss", "d_fk_loss", "g_adv_loss", "g_mse_loss"):
+        assert abs(L[k] - float(Lt[k].detach())) < 1e-12
+    for k in G:
+        extra = 1e-3 * st.g[k] if which == "g" and k.endswith("weights") else 0.0     # torch_ref has no l2 term
+        assert np.abs(G[k] - (Gt[k].numpy() + extra)).max() < 1e-10, k
+
+
+def build(handle=None, bn=False, keep=1.0, l2=0.0, lr=0.0, B=48, units=32, **kw):
+    a = dict(g_type="dnn", batch_size=B, input_dim=40, output_dim=8, left_context=1, right_context=1, g_units=units,
+             g_layers=1, d_units=units, d_layers=1, batch_norm=bn, keep_prob=keep, l2_scale=l2, init_mse_weight=10.0,
+             g_learning_rate=lr, d_learning_rate=lr, seed=4, dtype="f16")
+    a.update(kw)
+    return GAN(None, Namespace(**a), ["/gpu:0"], **({"handle": handle} if handle is not None else {}))
+
+
+def check_steps(m, bn, keep, l2, gtol):
+    """losses and raw gradients of one D and one G update (learning rates 0) against the oracle."""
+    rng = np.random.default_rng(6)
+    N, I, U = m.batch_size, 120, m.G.layers[0].n_out
+    assert m.D.cat_dim == 40 and m.D.P.adam and m.max_grad_norm > 1e20 and m.update_bn_stats
+    assert m.D.layers[0].n_in == 48 and list(m.D.P.segs)[0] == "d_model/fully_connected/weights"
+    gp = O.init_g_dnn(rng, in_dim=I, out_dim=8, units=U, hidden=1, batch_norm=bn)
+    dp = O.init_d_dnn(rng, in_dim=48, units=U, hidden=1, batch_norm=bn)
+    for p in (gp, dp):
+        for k in p:
+            if "BatchNorm" in k or "bias" in k:
+                p[k] = p[k] + 0.1 * rng.standard_normal(p[k].shape)
+    m.load_params(OrderedDict((k, v.astype(np.float32)) for k, v in gp.items()),
+                  OrderedDict((k, v.astype(np.float32)) for k, v in dp.items()))
+    x = rng.standard_normal((N, I)).astype(np.float32)
+    y = rng.standard_normal((N, 8)).astype(np.float32)
+    st = O.GanState(gp, dp, "dnn", "dnn")
+    gbs, dbs = O.init_bn_state(gp), O.init_bn_state(dp)
+    gs = m._gscale(N)
+    g_keep = keep if l2 > 0 else 1.0               # models/dnn.py:64-68
+    for tick, which in enumerate("dg"):
+        go = dict(bn_state=copy.deepcopy(gbs), keep_prob=g_keep, rng=(4, tick))
+        do = dict(bn_state=copy.deepcopy(dbs), keep_prob=keep, rng=(4, tick))
+        # frames are rows (B = N, T = 1): time-major == batch-major
+        L, G, _ = O.tower_losses_and_grads(st, x[:, None].astype(np.float64), y[:, None].astype(np.float64),
+                                           np.ones(N, int), which, mse_lambda=10.0, l2_scale=l2, g_opts=go, d_opts=do,
+                                           d_cat=(40, 80), l2_weights_only=True)
+        m.update_bn_stats = False                  # statistics stay at their initial values for the next comparison
+        out = (m.d_step if which == "d" else m.g_step)(x, y)
+        net, keys = (m.D, ("d_rl_loss", "d_fk_loss")) if which == "d" else (m.G, ("g_adv_loss", "g_mse_loss", "g_l2_loss"))
+        for k in keys:
+            assert out[k] == pytest.approx(L[k], rel=3e-3, abs=1e-5), k
+        mine = net.P.export_tf("grad")
+        for k in G:
+            assert rel(mine[k] / gs, G[k]) < gtol, (which, k)
+    return x, y, st
+
+
+@pytest.mark.parametrize("bn,keep,l2", [(False, 1.0, 0.0), (True, 0.8, 1e-4)])
+def test_frame_gan_host_wiring(bn, keep, l2):
+    check_steps(build(FakeHandle("f16"), bn=bn, keep=keep, l2=l2), bn, keep, l2, 2e-2)
+
+
+def test_frame_gan_adam_for_both_no_clip_host():
+    """Two schedules with real learning rates against the oracle's update rules: Adam on D and on G, gradients
+    applied unclipped, EMA shadows."""
+    m = build(FakeHandle("f16"), lr=1e-3, B=32)
+    rng = np.random.default_rng(1)
+    gp, dp = m.G.P.export_tf(dtype=np.float64), m.D.P.export_tf(dtype=np.float64)
+    st = O.GanState(OrderedDict(gp), OrderedDict(dp), "dnn", "dnn")
+    x = (5 * rng.standard_normal((32, 120))).astype(np.float32)      # large inputs: gradient norms well above 15
+    y = (5 * rng.standard_normal((32, 8))).astype(np.float32)
+    tower = dict(x=x[:, None].astype(np.float64), y=y[:, None].astype(np.float64), lengths=np.ones(32, int))
+    kw = dict(mse_lambda=10.0, d_cat=(40, 80), l2_weights_only=True)
+    for _ in range(2):
+        m.train_batch(x, y)
+        O.d_step(st, [tower], 1e-3, max_norm=1e30, adam=True, **kw)
+        O.g_step(st, [tower], 1e-3, max_norm=1e30, **kw)
+        _, clipped = O.g_step(st, [tower], 1e-3, max_norm=1e30, **kw)
+    assert max(float(np.sqrt((v ** 2).sum())) for v in clipped.values()) > 15.0      # clipping WOULD have changed this
+    for net, ref, ema in ((m.G, st.g, st.g_ema), (m.D, st.d, st.d_ema)):
+        th, sh = net.P.export_tf(), net.P.export_tf("ema")
+        for k in ref:
+            bar = 5e-3 if ref[k].size > 64 else 3e-2       # a lone zero-initialised bias is all update, no weight
+            assert rel(th[k], ref[k]) < bar, k
+            assert rel(sh[k], ema[k]) < bar, k
+    assert float(m.D.P.hyper[4]) == pytest.approx(0.9 ** 3, rel=1e-5)               # D took two Adam steps
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bn,keep,l2", [(False, 1.0, 0.0), (True, 0.8, 1e-4)])
+def test_frame_gan_gpu(bn, keep, l2):
+    """The same on the kernels, at the reference's layer width (1024 units, 2827-d spliced input, 297-d D input)."""
+    m = build(None, bn=bn, keep=keep, l2=l2, B=256, units=1024, input_dim=257, output_dim=40, left_context=5,
+              right_context=5)
+    rng = np.random.default_rng(6)
+    N, I = 256, 257 * 11
+    assert m.D.cat_dim == 257 and m.D.layers[0].inp == 304
+    gp = O.init_g_dnn(rng, in_dim=I, out_dim=40, units=1024, hidden=1, batch_norm=bn)
+    dp = O.init_d_dnn(rng, in_dim=297, units=1024, hidden=1, batch_norm=bn)
+    m.load_params(OrderedDict((k, v.astype(np.float32)) for k, v in gp.items()),
+                  OrderedDict((k, v.astype(np.float32)) for k, v in dp.items()))
+    x, y = rng.standard_normal((N, I)).astype(np.float32), rng.standard_normal((N, 40)).astype(np.float32)
+    st = O.GanState(gp, dp, "dnn", "dnn")
+    gbs, dbs = O.init_bn_state(gp), O.init_bn_state(dp)
+    gs = m._gscale(N)
+    n0 = m.h.launches
+    for tick, which in enumerate("dg"):
+        go = dict(bn_state=copy.deepcopy(gbs), keep_prob=keep if l2 > 0 else 1.0, rng=(4, tick))
+        do = dict(bn_state=copy.deepcopy(dbs), keep_prob=keep, rng=(4, tick))
+        L, G, _ = O.tower_losses_and_grads(st, x[:, None].astype(np.float64), y[:, None].astype(np.float64),
+                                           np.ones(N, int), which, mse_lambda=10.0, l2_scale=l2, g_opts=go, d_opts=do,
+                                           d_cat=(257 * 5, 257 * 6), l2_weights_only=True)
+        m.update_bn_stats = False
+        out = (m.d_step if which == "d" else m.g_step)(x, y)
+        net, keys = (m.D, ("d_rl_loss", "d_fk_loss")) if which == "d" else (m.G, ("g_adv_loss", "g_mse_loss"))
+        for k in keys:
+            assert out[k] == pytest.approx(L[k], rel=3e-3, abs=1e-5), k
+        mine = net.P.export_tf("grad")
+        for k in G:
+            assert rel(mine[k] / gs, G[k]) < 5e-2, (which, k)
+    assert m.h.launches > n0
+    m.update_bn_stats = True
+    m.g_learning_rate = m.d_learning_rate = 1e-4
+    outs = [m.train_batch(x, y) for _ in range(4)]                 # eager, eager, capture, replay
+    assert all(np.isfinite(v) for o in outs for v in o.values())
+    g = m.generate(x).cpu().numpy()
+    assert g.shape == (N, 40) and np.isfinite(g).all()
