@@ -53,3 +53,26 @@ with open(os.path.join(HERE, "global.cmvn"), "wb") as f:
 mean = stats[0, :D] / n
 np.savez(os.path.join(HERE, "global_cmvn_expected.npz"), mean=mean, std=np.sqrt(stats[1, :D] / n - mean ** 2))
 print("wrote", sorted(os.listdir(HERE)))
+
+# A full-utterance compressed matrix (500 frames x 257 bins): the archive bytes are regenerated from the seed by the
+# tests (tests/test_kaldi_io.py::cm_utterance_bytes), only the SHA-256 of the float64 matrix the REFERENCE reader
+# returns -- and a few of its rows -- are committed.
+import hashlib  # noqa: E402
+import sys  # noqa: E402
+
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from test_kaldi_io import cm_utterance_bytes  # noqa: E402
+
+body, (rows, cols) = cm_utterance_bytes()
+big = os.path.join(HERE, "_cm_utt.ark")
+with open(big, "wb") as f:
+    f.write(b"utt_big ")
+    pos = f.tell()
+    f.write(body)
+m = np.asarray(ref.ArkReader().read_ark(big, pos))
+os.remove(big)
+assert m.shape == (rows, cols) and m.dtype == np.float64
+np.savez(os.path.join(HERE, "kaldi_cm_utt_expected.npz"), sha256=np.frombuffer(hashlib.sha256(m.tobytes()).digest(), np.uint8),
+         rows_0_249_499=m[[0, 249, 499]], shape=np.array(m.shape))
+print("reference reader: utterance-sized CM matrix", m.shape, hashlib.sha256(m.tobytes()).hexdigest())

@@ -11,6 +11,16 @@ from rsrgan_b200 import kaldi_io
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
+def cm_utterance_bytes(seed=7, rows=500, cols=257):
+    """Archive body ('\\0BCM ' + GlobalHeader + PerColHeaders + bytes) of a full-utterance compressed matrix, rebuilt from
+    the seed (so the 130 KB archive need not be committed); every byte value and all three char_to_float branches occur."""
+    rng = np.random.default_rng(seed)
+    hdr = np.sort(rng.integers(0, 65536, size=(cols, 4)), axis=1).astype("<u2")
+    data = rng.integers(0, 256, size=(cols, rows)).astype(np.uint8)
+    data[0, :256] = np.arange(256, dtype=np.uint8)
+    return b"\0BCM " + struct.pack("<ffii", -17.3125, 40.75, rows, cols) + hdr.tobytes() + data.tobytes(), (rows, cols)
+
+
 def _entries():
     r = kaldi_io.ArkReader()
     cwd = os.getcwd()
@@ -93,3 +103,20 @@ def test_read_ark_device_host_double():
         assert kaldi_io.ArkReader.read_compressed_raw(*r.scp_data[r.utt_ids.index("utt_dm")]) is None
     finally:
         os.chdir(cwd)
+
+
+def test_compressed_utterance_matches_reference_reader_sha256(tmp_path):
+    """500 x 257 compressed matrix: our vectorised reader returns the very float64 bits the REFERENCE's per-element
+    reader returned for the same bytes (tests/golden/make_kaldi_golden.py computed the digest by importing it)."""
+    import hashlib
+    exp = np.load(os.path.join(GOLD, "kaldi_cm_utt_expected.npz"))
+    body, (rows, cols) = cm_utterance_bytes()
+    ark = str(tmp_path / "big.ark")
+    with open(ark, "wb") as f:
+        f.write(b"utt_big ")
+        pos = f.tell()
+        f.write(body)
+    m = kaldi_io.ArkReader().read_ark(ark, pos)
+    assert m.shape == tuple(exp["shape"]) == (rows, cols) and m.dtype == np.float64
+    assert np.array_equal(m[[0, 249, 499]], exp["rows_0_249_499"])
+    assert hashlib.sha256(m.tobytes()).digest() == exp["sha256"].tobytes()

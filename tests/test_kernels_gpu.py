@@ -455,3 +455,32 @@ def test_ark_decompress_bit_exact(h):
         assert np.array_equal(o64[:, :cols].cpu().numpy(), want), (rows, cols)
         assert np.array_equal(o32[:, :cols].cpu().numpy(), ((want - mean) / std).astype(np.float32)), (rows, cols)
         assert bool((o64[:, cols:] == 7.0).all()) and bool((o32[:, cols:] == 7.0).all())
+
+
+def test_ark_decompress_utterance_sha256_of_reference_reader(h):
+    """A 500 x 257 compressed utterance decoded on the device hashes to the SHA-256 of what the REFERENCE's reader
+    returned for the same bytes (tests/golden/kaldi_cm_utt_expected.npz, computed by importing io_funcs/kaldi_io.py);
+    the float64-CMVN'd float32 output equals the host expression bit for bit."""
+    import hashlib
+    import os
+    import struct
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_kaldi_io import cm_utterance_bytes
+    exp = np.load(os.path.join(os.path.dirname(__file__), "golden", "kaldi_cm_utt_expected.npz"))
+    body, (rows, cols) = cm_utterance_bytes()
+    mn, rg, r2, c2 = struct.unpack("<ffii", body[5:21])
+    assert (r2, c2) == (rows, cols)
+    hdr = np.frombuffer(body[21:21 + 8 * cols], dtype="<u2").reshape(cols, 4)
+    data = np.frombuffer(body[21 + 8 * cols:], dtype=np.uint8).reshape(cols, rows)
+    dev = h.device
+    out64 = torch.zeros(rows, cols, dtype=torch.float64, device=dev)
+    out32 = torch.zeros(rows, cols, dtype=torch.float32, device=dev)
+    mean, std = np.linspace(-3, 3, cols), np.linspace(0.5, 4, cols)
+    h.ark_decompress(torch.from_numpy(hdr.view(np.int16).copy()).to(dev), torch.from_numpy(data.copy()).to(dev), mn, rg,
+                     rows, cols, out64=out64, out32=out32, mean=torch.from_numpy(mean).to(dev),
+                     std=torch.from_numpy(std).to(dev))
+    m = out64.cpu().numpy()
+    assert np.array_equal(m[[0, 249, 499]], exp["rows_0_249_499"])
+    assert hashlib.sha256(m.tobytes()).digest() == exp["sha256"].tobytes()
+    assert np.array_equal(out32.cpu().numpy(), ((m - mean) / std).astype(np.float32))
