@@ -220,7 +220,9 @@ class GAN_RNN(Model):
         self.graph_ddp = os.environ.get("RSR_GRAPH_DDP", "1") != "0"
         self._cap = None
         self.g_outputs = None
-        self.summaries = None
+        # tf.summary.FileWriter(save_dir/train | eval) (:82-86); `summaries` = the tags of the merged scalar summary
+        # (:270-298).  Created on first use by write_summaries(); rank 0 only.
+        self.summaries = ("d_rl_loss", "d_fk_loss", "d_loss", "g_adv_loss", "g_mse_loss", "g_l2_loss", "g_loss")
         self.writer = None
 
     # ------------------------------------------------------------------ scalars on device
@@ -640,6 +642,17 @@ class GAN_RNN(Model):
         if g_all:
             out.update(self._loss_dict(g_all[-1].tolist(), "g"))
         return out
+
+    def write_summaries(self, losses, counter):
+        """`summary = sess.run(model.summaries); model.writer.add_summary(summary, counter)`
+        (scripts/train_gan_rnn_placeholder.py:117-122): the loss scalars as a TensorBoard event."""
+        if self.dist is not None and self.dist.get_rank() != 0:
+            return
+        if self.writer is None:
+            from .summary import FileWriter
+            self.writer = FileWriter(os.path.join(self.save_dir, "eval" if self.cross_validation else "train"))
+        self.writer.add_scalars({k: losses[k] for k in self.summaries if k in losses}, counter)
+        self.writer.flush()
 
     def last_update_losses(self):
         """Losses of EVERY update of the last train_batch() -- ([D-update dicts], [G-update dicts]) -- as the

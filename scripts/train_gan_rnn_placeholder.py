@@ -86,7 +86,7 @@ def _train_and_prefetch(model, cur, nxt):
 def train_one_iteration(model, batches, iteration):
     """scripts/train_gan_rnn_placeholder.py:48-133."""
     sums = np.zeros(7)
-    d_counter = g_counter = 0
+    d_counter = g_counter = batch_counter = 0
     model.d_real, model.d_fake = 1.0, 0.0
     # One call per minibatch runs the whole schedule of :72-101 (disc_updates x D, gen_updates x G on the same
     # batch) on the device; the next minibatch is uploaded meanwhile (GAN_RNN.prefetch).
@@ -105,6 +105,9 @@ def train_one_iteration(model, batches, iteration):
         for g in g_list:
             g_counter += 1
             sums[3:7] += world_mean(model, [g["g_adv_loss"], g["g_mse_loss"], g["g_l2_loss"], g["g_loss"]])
+        batch_counter += 1
+        if batch_counter % 100 == 0 and d_list and g_list:     # :117-122 summaries every 100 batches
+            model.write_summaries(dict(d_list[-1], **g_list[-1]), (d_counter + g_counter) * FLAGS.num_gpu)
         cur = nxt
     d_counter, g_counter = max(d_counter, 1), max(g_counter, 1)
     return tuple(sums[0:3] / d_counter) + tuple(sums[3:7] / g_counter)
