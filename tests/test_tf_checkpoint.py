@@ -171,3 +171,25 @@ def test_load_reference_style_checkpoint_with_weights_only(tmp_path):
     T.write_bundle(os.path.join(d, "GAN_RNN-8"), tensors)
     with pytest.raises(KeyError):
         model(batch_norm=False, ckpt_format="pt").load(d, model_file="GAN_RNN-8")
+
+
+def test_sub_messages_parse_with_tensorflows_own_protos():
+    """TensorBoard ships TensorFlow's compiled framework protos: the shape / version sub-messages we emit parse with
+    them, and the dtype numbers are TensorFlow's DataType enum."""
+    pb_shape = pytest.importorskip("tensorboard.compat.proto.tensor_shape_pb2")
+    from tensorboard.compat.proto import types_pb2, versions_pb2
+    e = T.encode_entry(1, (257, 3040), 4096, 257 * 3040 * 4, 0xdeadbeef)
+    fields = {num: v for num, _, v in T._parse(e)}
+    shape = pb_shape.TensorShapeProto.FromString(fields[2])
+    assert [d.size for d in shape.dim] == [257, 3040] and not shape.unknown_rank
+    assert pb_shape.TensorShapeProto.FromString({n: v for n, _, v in T._parse(T.encode_entry(1, (), 0, 4, 1))}[2]).dim == []
+    hdr = {num: v for num, _, v in T._parse(T.encode_header(1))}
+    assert versions_pb2.VersionDef.FromString(hdr[3]).producer == 1
+    for name, np_dt in (("DT_FLOAT", "<f4"), ("DT_DOUBLE", "<f8"), ("DT_INT32", "<i4"), ("DT_INT64", "<i8"),
+                        ("DT_BOOL", "bool"), ("DT_HALF", "<f2"), ("DT_UINT8", "u1"), ("DT_INT16", "<i2"), ("DT_INT8", "i1")):
+        assert T.DTYPES[getattr(types_pb2, name)] == np.dtype(np_dt), name
+    # and the other way round: a shape serialized by the real proto decodes through our parser
+    real = pb_shape.TensorShapeProto(dim=[pb_shape.TensorShapeProto.Dim(size=7), pb_shape.TensorShapeProto.Dim(size=1)])
+    entry = T._field(1, 0, T.put_varint(1)) + T._field(2, 2, T.put_varint(len(real.SerializeToString())) +
+                                                      real.SerializeToString())
+    assert T.decode_entry(entry)["shape"] == (7, 1)
