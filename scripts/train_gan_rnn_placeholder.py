@@ -83,7 +83,7 @@ def _train_and_prefetch(model, cur, nxt):
     return model.last_update_losses()
 
 
-def train_one_iteration(model, batches, iteration):
+def train_one_iteration(model, batches, iteration, tr_num_batch=0):
     """scripts/train_gan_rnn_placeholder.py:48-133."""
     sums = np.zeros(7)
     d_counter = g_counter = batch_counter = 0
@@ -105,9 +105,10 @@ def train_one_iteration(model, batches, iteration):
         for g in g_list:
             g_counter += 1
             sums[3:7] += world_mean(model, [g["g_adv_loss"], g["g_mse_loss"], g["g_l2_loss"], g["g_loss"]])
+        if batch_counter % 100 == 0 and d_list and g_list:
+            # `if batch % 100 == 0: ... add_summary(_summaries, iteration*tr_num_batch)` (:116-122): batches 0, 100, ...
+            model.write_summaries(dict(d_list[-1], **g_list[-1]), iteration * tr_num_batch)
         batch_counter += 1
-        if batch_counter % 100 == 0 and d_list and g_list:     # :117-122 summaries every 100 batches
-            model.write_summaries(dict(d_list[-1], **g_list[-1]), (d_counter + g_counter) * FLAGS.num_gpu)
         cur = nxt
     d_counter, g_counter = max(d_counter, 1), max(g_counter, 1)
     return tuple(sums[0:3] / d_counter) + tuple(sums[3:7] / g_counter)
@@ -241,7 +242,7 @@ def main():
                                                              FLAGS.left_context, FLAGS.right_context,
                                                              FLAGS.num_threads, 1, cmvn=cmvn, seed=7)))
         start = datetime.datetime.now()
-        tr = train_one_iteration(tr_model, tr_batches, iteration + 1)
+        tr = train_one_iteration(tr_model, tr_batches, iteration + 1, tr_num_batch)
         cv = eval_one_iteration(cv_model, cv_batches, iteration + 1)
         end = datetime.datetime.now()
         fmt = ("d_rl_loss = {:.5f}, d_fk_loss = {:.5f}, d_loss = {:.5f}, g_adv_loss = {:.5f}, "

@@ -76,6 +76,9 @@ def test_train_resume_decode(tmp_path, extra):
         vals = [float(v) for v in l[3:]]
         assert all(np.isfinite(vals)) and vals[2] == pytest.approx(vals[0] + vals[1], rel=1e-3, abs=1e-4)
     assert os.path.exists(os.path.join(save, "checkpoint"))
+    # TensorBoard scalars of the first batch of each iteration (train...py:116-122) in <save_dir>/train
+    ev = [f for f in os.listdir(os.path.join(save, "train")) if f.startswith("events.out.tfevents.")]
+    assert len(ev) == 1 and os.path.getsize(os.path.join(save, "train", ev[0])) > 200
     if "tf" in extra:
         from rsrgan_b200 import tf_checkpoint
         latest, _ = tf_checkpoint.read_checkpoint_state(save)
