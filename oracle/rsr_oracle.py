@@ -285,6 +285,63 @@ def conv1d_same_bwd(dy, cache):
     return dxp[:, w // 2:w // 2 + L], dW, du.sum((0, 1))
 
 
+def conv2d_same_fwd(x, W, b, act=ACT_RELU):
+    """tf.contrib.layers.conv2d(inputs, C_out, [splice, w], padding=SAME, relu) for ANY splice (models/rced.py:90-101):
+    x NHWC (N, H, L, C_in), W (kh, kw, C_in, C_out), stride 1, odd kh and kw (SAME pads kh//2 / kw//2 zeros per side).
+        u[n, h, p, :] = b + sum_{i, k} x[n, h - kh//2 + i, p - kw//2 + k, :] @ W[i, k]
+    The product path builds only splice = 1 (conv1d_same_fwd); this is the statement the 2-D case will be held to."""
+    kh, kw = W.shape[:2]
+    assert kh % 2 == 1 and kw % 2 == 1
+    N, H, L, _ = x.shape
+    xp = np.zeros((N, H + kh - 1, L + kw - 1, x.shape[3]), x.dtype)
+    xp[:, kh // 2:kh // 2 + H, kw // 2:kw // 2 + L] = x
+    u = np.zeros((N, H, L, W.shape[3]), np.result_type(x, W)) + b
+    for i in range(kh):
+        for k in range(kw):
+            u += xp[:, i:i + H, k:k + L] @ W[i, k]
+    return act_fwd(u, act), (xp, W, u, act)
+
+
+def conv2d_same_bwd(dy, cache):
+    xp, W, u, act = cache
+    N, H, L, _ = u.shape
+    kh, kw = W.shape[:2]
+    du = act_bwd(u, dy, act)
+    dW, dxp = np.zeros_like(W), np.zeros_like(xp)
+    for i in range(kh):
+        for k in range(kw):
+            dW[i, k] = np.einsum("nhlc,nhld->cd", xp[:, i:i + H, k:k + L], du)
+            dxp[:, i:i + H, k:k + L] += du @ W[i, k].T
+    return dxp[:, kh // 2:kh // 2 + H, kw // 2:kw // 2 + L], dW, du.sum((0, 1, 2))
+
+
+def toeplitz_taps(W, H):
+    """The [kh, kw] SAME convolution over H stacked lines as a 1-D convolution over positions whose channels are
+    (line, channel) pairs: W2[0, k, h_in * C_in + ci, h_out * C_out + co] = W[h_in - h_out + kh//2, k, ci, co] (zero where
+    that row index falls outside the filter).  DESIGN.md section 9 item 4: how the overlapped-view GEMM will run the
+    2-D RCED; the compact filter stays the parameter, the expansion is a derived operand."""
+    kh, kw, ci, co = W.shape
+    W2 = np.zeros((1, kw, H * ci, H * co), W.dtype)
+    for h_out in range(H):
+        for h_in in range(H):
+            i = h_in - h_out + kh // 2
+            if 0 <= i < kh:
+                W2[0, :, h_in * ci:(h_in + 1) * ci, h_out * co:(h_out + 1) * co] = W[i]
+    return W2
+
+
+def toeplitz_fold_grad(dW2, kh, ci, co):
+    """Gradient of the compact filter from the gradient of its Toeplitz expansion: the sum over the tied copies."""
+    H = dW2.shape[2] // ci
+    dW = np.zeros((kh, dW2.shape[1], ci, co), dW2.dtype)
+    for h_out in range(H):
+        for h_in in range(H):
+            i = h_in - h_out + kh // 2
+            if 0 <= i < kh:
+                dW[i] += dW2[0, :, h_in * ci:(h_in + 1) * ci, h_out * co:(h_out + 1) * co]
+    return dW
+
+
 # --------------------------------------------------------------------------
 # LSTMP cell with peepholes == tf.contrib.rnn.LSTMCell(use_peepholes=True,
 # num_proj=P, forget_bias=1.0) under tf.nn.dynamic_rnn(sequence_length=...)

@@ -522,10 +522,12 @@ class Generator(Net):
         self.g_type, self.in_dim, self.out_dim = g_type, in_dim, out_dim
         # dnn: tf.nn.dropout behind every hidden layer (FCBN); LSTM generators: DropoutWrapper(output_keep_prob) on every
         # LSTM layer's output (models/lstm.py:99-102, models/res_lstm_l.py:96-99) = _drop_fwd / _drop_bwd below
-        self.keep_prob = float(keep_prob)
+        # rced builds keep_prob but never applies a dropout op (models/rced.py:73-77,102-103): a no-op there
+        self.keep_prob = 1.0 if g_type == "rced" else float(keep_prob)
         self._dropping = False
-        if (batch_norm or keep_prob < 1.0) and g_type == "rced":
-            raise NotImplementedError("batch_norm / dropout on the rced generator are not implemented")
+        if batch_norm and g_type == "rced":
+            # normalizer_fn=batch_norm on the nine conv2d layers (models/rced.py:63-71,94-97): not on this path yet
+            raise NotImplementedError("batch_norm on the rced convolutions is not implemented")
         # res_lstm_l / res_lstm_base build normalizer_params but never pass them on (models/res_lstm_l.py:58-67,81-82):
         # batch_norm is a no-op there, exactly as in the reference
         special = g_type == "dnn" and (batch_norm or self.keep_prob < 1.0)

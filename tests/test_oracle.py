@@ -214,3 +214,40 @@ def test_mse_trainer_gradients_match_torch_autograd():
         assert L["g_mse_loss"] == pytest.approx(float(mse), rel=1e-12) and L["g_l2_loss"] == pytest.approx(float(l2), rel=1e-12)
         for k in gp:
             assert np.allclose(grads[k], tp[k].grad.numpy(), atol=1e-10, rtol=1e-8), k
+
+
+def test_conv2d_same_against_torch_and_toeplitz_equivalence():
+    """The [splice, w] convolution of models/rced.py:90-101 for splice > 1: (i) the numpy statement against
+    torch.nn.functional.conv2d (forward and autograd), (ii) the block-Toeplitz 1-D form the product's overlapped-view
+    GEMM will use gives the same output, input gradient and -- folded over the tied copies -- the
+    same filter gradient."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(4)
+    N, H, L, ci, co, kh, kw = 3, 5, 17, 2, 3, 5, 7
+    x, W, b = rng.standard_normal((N, H, L, ci)), rng.standard_normal((kh, kw, ci, co)) * 0.3, rng.standard_normal(co)
+    w_out = rng.standard_normal((N, H, L, co))
+    y, cache = O.conv2d_same_fwd(x, W, b)
+    dx, dW, db = O.conv2d_same_bwd(w_out, cache)
+    xt = torch.tensor(x, requires_grad=True)
+    Wt, bt = torch.tensor(W, requires_grad=True), torch.tensor(b, requires_grad=True)
+    yt = torch.relu(F.conv2d(xt.permute(0, 3, 1, 2), Wt.permute(3, 2, 0, 1), bt, padding=(kh // 2, kw // 2)))
+    yt = yt.permute(0, 2, 3, 1)
+    assert np.abs(y - yt.detach().numpy()).max() < 1e-12
+    gx, gW, gb = torch.autograd.grad((yt * torch.tensor(w_out)).sum(), (xt, Wt, bt))
+    assert np.abs(dx - gx.numpy()).max() < 1e-12 and np.abs(dW - gW.numpy()).max() < 1e-11
+    assert np.abs(db - gb.numpy()).max() < 1e-11
+    # splice = 1 is the 1-D statement the product runs today
+    y1, _ = O.conv1d_same_fwd(x[:, 0], W[kh // 2:kh // 2 + 1], b)
+    y1b, _ = O.conv2d_same_fwd(x[:, :1], W[kh // 2:kh // 2 + 1], b)
+    assert np.array_equal(y1, y1b[:, 0])
+    # Toeplitz form: lines as channels
+    x2 = x.transpose(0, 2, 1, 3).reshape(N, L, H * ci)                   # (n, p, (h, ci))
+    W2 = O.toeplitz_taps(W, H)
+    y2, c2 = O.conv1d_same_fwd(x2, W2, np.tile(b, H))
+    assert np.abs(y2.reshape(N, L, H, co).transpose(0, 2, 1, 3) - y).max() < 1e-12
+    dx2, dW2, db2 = O.conv1d_same_bwd(w_out.transpose(0, 2, 1, 3).reshape(N, L, H * co), c2)
+    assert np.abs(dx2.reshape(N, L, H, ci).transpose(0, 2, 1, 3) - dx).max() < 1e-12
+    assert np.abs(O.toeplitz_fold_grad(dW2, kh, ci, co) - dW).max() < 1e-11
+    assert np.abs(db2.reshape(H, co).sum(0) - db).max() < 1e-11
+    dense = (W2 != 0).mean()
+    assert 0.5 < dense < 1.0                                              # 19 of 25 line pairs at H = kh = 5
