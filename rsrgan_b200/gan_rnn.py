@@ -18,6 +18,7 @@ clip+optimizer kernel.  All arithmetic runs in librsrgan_sm100.so; there is no C
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 from collections import OrderedDict
@@ -446,7 +447,10 @@ class GAN_RNN(Model):
                   ld_grad=8)
         # D(labels) does not depend on the generator: its forward, loss and backward run on the side stream
         # while the generator recurrences (which occupy only the SMs of their clusters) run on this one.
-        with h.side_stream():
+        # (a batch-normalised D whose UPDATE_OPS run assigns its moving averages in both passes: those two then stay
+        # on one stream, D(labels) first, so that neither read-modify-write is lost)
+        serial = D.fcbn and self.update_bn_stats
+        with (contextlib.nullcontext() if serial else h.side_stream()):
             lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=n_rl, cat_src=self._cat(x))
             h.lsgan_mse_losses(self._losses, rl=lg_rl, ld_logit=lg_rl.stride(0), d_rl_grad=d_rl16, **kw)
             D.bwd("rl", d_rl16)
