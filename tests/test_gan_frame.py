@@ -167,3 +167,80 @@ def test_frame_gan_gpu(bn, keep, l2):
     assert all(np.isfinite(v) for o in outs for v in o.values())
     g = m.generate(x).cpu().numpy()
     assert g.shape == (N, 40) and np.isfinite(g).all()
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)                       # same stream on both ranks: identical weights and data pool
+    m = build(FakeHandle("f16"), bn=True, lr=1e-3, B=24, num_gpu=world)
+    gp, dp = _dp_params(rng)
+    m.load_params(OrderedDict((k, v.astype(np.float32)) for k, v in gp.items()),
+                  OrderedDict((k, v.astype(np.float32)) for k, v in dp.items()))
+    x, y = _dp_data(rng)
+    sl = slice(24 * rank, 24 * (rank + 1))
+    m.d_step(x[sl], y[sl])
+    m.g_step(x[sl], y[sl])
+    q.put((rank, m.D.P.export_tf(), m.G.P.export_tf(), m.D.bn_state_tf()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _dp_params(rng):
+    gp = O.init_g_dnn(rng, in_dim=120, out_dim=8, units=32, hidden=1, batch_norm=True)
+    dp = O.init_d_dnn(rng, in_dim=48, units=32, hidden=1, batch_norm=True)
+    for p in (gp, dp):
+        for k in p:
+            if "BatchNorm" in k:
+                p[k] = p[k] + 0.1 * rng.standard_normal(p[k].shape)
+    return gp, dp
+
+
+def _dp_data(rng):
+    return rng.standard_normal((48, 120)).astype(np.float32), rng.standard_normal((48, 8)).astype(np.float32)
+
+
+def test_frame_gan_two_ranks_gloo_per_tower_batch_norm():
+    """world_size 2 over gloo: every tower normalises with the statistics of ITS OWN slice (models/gan.py builds the
+    batch_norm layers once per tower), gamma / beta gradients ride the same all-reduce, Adam on both networks with the
+    tower-mean gradient: identical weights on both ranks, equal to the two-tower oracle; the moving averages are
+    per-rank state and differ."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for net in (1, 2):
+        for k in res[0][net]:
+            assert np.array_equal(res[0][net][k], res[1][net][k]), k
+    k = "d_model/fully_connected/BatchNorm/moving_mean"
+    assert not np.array_equal(res[0][3][k], res[1][3][k])
+    rng = np.random.default_rng(3)
+    gp, dp = _dp_params(rng)
+    x, y = _dp_data(rng)
+    st = O.GanState(OrderedDict(gp), OrderedDict(dp), "dnn", "dnn")
+    towers = []
+    for r in range(2):
+        sl = slice(24 * r, 24 * (r + 1))
+        towers.append(dict(x=x[sl, None].astype(np.float64), y=y[sl, None].astype(np.float64), lengths=np.ones(24, int)))
+    kw = dict(mse_lambda=10.0, d_cat=(40, 80), l2_weights_only=True)
+    # per-tower statistics: each tower call gets its own (fresh) batch_norm state
+    mk = lambda: dict(g_opts=dict(bn_state=O.init_bn_state(gp)), d_opts=dict(bn_state=O.init_bn_state(dp)))
+
+    def both(which):
+        return [O.tower_losses_and_grads(st, t["x"], t["y"], t["lengths"], which, **kw, **mk())[1] for t in towers]
+    avg = O.average_gradients(both("d"))
+    st.d, st.d_adam_m, st.d_adam_v, st.d_adam_t = O.adam_update_tf(st.d, avg, st.d_adam_m, st.d_adam_v, st.d_adam_t, 1e-3)
+    avg = O.average_gradients(both("g"))
+    st.g, st.adam_m, st.adam_v, st.adam_t = O.adam_update_tf(st.g, avg, st.adam_m, st.adam_v, st.adam_t, 1e-3)
+    for mine, ref, start in ((res[0][1], st.d, dp), (res[0][2], st.g, gp)):
+        for k2 in ref:
+            # one Adam step moves every weight by ~lr: compare the UPDATE (sign noise on near-zero gradients aside)
+            assert rel(mine[k2] - start[k2], ref[k2] - start[k2]) < 0.15, k2
