@@ -193,3 +193,33 @@ def test_sub_messages_parse_with_tensorflows_own_protos():
     entry = T._field(1, 0, T.put_varint(1)) + T._field(2, 2, T.put_varint(len(real.SerializeToString())) +
                                                       real.SerializeToString())
     assert T.decode_entry(entry)["shape"] == (7, 1)
+
+
+def test_convert_checkpoint_script_both_directions(tmp_path, capsys):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "convert_checkpoint", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
+                                           "convert_checkpoint.py"))
+    conv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(conv)
+    m = model(ckpt_format="pt")
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal((2, 5, 257)).astype(np.float32), rng.standard_normal((2, 5, 40)).astype(np.float32)
+    m.train_batch(x, y, np.array([5, 4]))
+    d = str(tmp_path / "exp")
+    pt = m.save(d, 4)
+    assert conv.main(["--to", "tf", pt]) == 0
+    prefix = pt[:-3]
+    assert os.path.exists(prefix + ".index") and os.path.exists(prefix + ".data-00000-of-00001")
+    assert conv.main(["--list", prefix]) == 0
+    assert "g_model/fully_connected/BatchNorm/gamma" in capsys.readouterr().out
+    other = model(ckpt_format="pt", seed=77)
+    like = other.save(str(tmp_path / "other"), 1)
+    back = str(tmp_path / "back.pt")
+    assert conv.main(["--to", "pt", prefix, "--like", like, "--out", back]) == 0
+    import torch
+    a, b = torch.load(pt, weights_only=False), torch.load(back, weights_only=False)
+    for key in ("G", "D"):
+        for buf in ("theta", "ema", "m", "v", "bn_state"):
+            for n in a[key].get(buf, {}):
+                assert np.array_equal(np.asarray(a[key][buf][n]), np.asarray(b[key][buf][n])), (key, buf, n)
