@@ -1,7 +1,6 @@
 """Property tests (hypothesis) of the byte-level host formats: Kaldi ark write -> read, compressed-matrix decode
 structure, TensorFlow bundle write -> read, device parameter layouts.  CPU only."""
 import io
-import os
 import struct
 
 import numpy as np
