@@ -915,11 +915,21 @@ class GanState(object):
 
 def tower_losses_and_grads(st, x, y, lengths, which, noise_rl=None, noise_fk=None,
                            mse_lambda=10.0, d_real=1.0, d_fake=0.0, l2_scale=0.0, g_opts=None, d_opts=None,
-                           d_cat=None, l2_weights_only=False):
+                           d_cat=None, l2_weights_only=False, update_ops=None):
     """One tower of build_model_single_gpu (gan_rnn_placeholder.py:191-298) plus
-    compute_gradients wrt d_vars (which='d') or g_vars (which='g')."""
+    compute_gradients wrt d_vars (which='d') or g_vars (which='g').
+    update_ops: which batch_norm UPDATE_OPS the optimizer op depends on (they mutate opts['bn_state'] in place):
+      'own' -- gan_rnn_placeholder.py:163-175: d_opt runs the d_model updates (both discriminator passes), g_opt the
+               g_model ones;
+      'all' -- models/gan.py:139-143: both optimizers depend on the whole collection;
+      None  -- whatever the caller put into the opts dicts ('update' key, default off)."""
     gf, gb = GENERATORS[st.g_type]
     df, db_ = DISCRIMINATORS[st.d_type]
+    if update_ops is not None:
+        if g_opts is not None:
+            g_opts = dict(g_opts, update=update_ops == "all" or which == "g")     # bn_state stays the caller's object
+        if d_opts is not None:
+            d_opts = dict(d_opts, update=update_ops == "all" or which == "d")
     # g_opts / d_opts: batch_norm state, dropout stream (fc_block_fwd); salts: G layers 0.., D(labels) 256.., D(G(x)) 512..
     g_out, gc = gf(st.g, x, lengths) if g_opts is None else gf(st.g, x, lengths, opts=g_opts, salt0=0)
     # d_cat = (c0, c1): the frame-level GAN of models/gan.py:159-174 feeds D tf.concat([inputs[..., c0:c1], .], -1)

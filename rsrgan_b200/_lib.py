@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librsrgan_sm100.so")
+# RSR_LIB: another build of the same library (e.g. the -DRSR_TRACE phase-timing build used by scripts/gpu_trace_rec.py)
+LIB_PATH = os.environ.get("RSR_LIB") or os.path.join(_HERE, "librsrgan_sm100.so")
 
 RSR_DTYPE_F16, RSR_DTYPE_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_CLIP = 0, 1, 2, 3

@@ -49,6 +49,8 @@ struct rsr_handle {
     // co-resident clusters of the cluster recurrence kernels: [fwd|bwd][Cp/256 - 1][NB 16|32]; -1 = not queried yet
     int gemm2_pairs = -1;            // co-resident CTA pairs of the two-CTA GEMM (-1 = not queried yet)
     int fused_ik[2] = {-1, -1};      // Ik the fused-forward capacity entry was computed for
+    int pair_cap[2][2] = {{-1, -1}, {-1, -1}};   // CTA-pair kernels (lstmp_pair_sm100.cu): [fwd|bwd][Cp/256 - 1]
+    int pair_ik[2] = {-1, -1};
     int cluster_cap[3][2][2] = {{{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}};   // [2] = fused fwd
 };
 
@@ -78,6 +80,11 @@ int rsr_lstmp_fused_fwd_cluster(rsr_handle* h, void* stream, int B, int T, int I
                                 const void* kxT, const float* bias, const void* wcT, const float* w_i,
                                 const float* w_f, const float* w_o, float forget_bias, const int* lengths,
                                 void* mt_seq, float* save);
+// CTA-pair (cta_group::2) variants, lstmp_pair_sm100.cu; RSR_E_RESIDENT = not applicable
+int rsr_lstmp_fused_fwd_pair(rsr_handle* h, void* stream, int B, int T, int I, int Cp, const void* x16, int ldx,
+                             const void* kxT, const float* bias, const void* wcT, const float* w_i,
+                             const float* w_f, const float* w_o, float forget_bias, const int* lengths,
+                             void* mt_seq, float* save);
 int rsr_lstmp_bwd_cluster(rsr_handle* h, void* stream, int B, int T, int Cp, const float* dmt, const void* wc,
                           const float* w_i, const float* w_f, const float* w_o, const int* lengths,
                           const float* save, void* dz16, float* dbias, float* dw_i, float* dw_f, float* dw_o);

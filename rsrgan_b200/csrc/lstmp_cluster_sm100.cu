@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "handle.h"
+#include "cluster_util.h"
 
 using namespace rsr;
 
@@ -605,41 +606,6 @@ size_t cfwd_smem(int Cp, int nhalf, int Ik = 0) {
 size_t cbwd_smem(int Cp, int nhalf) {
     const size_t need = 1024 + (size_t)nhalf * (2 * (size_t)NB * 128 + 2 * (size_t)(Cp / 32) * NB * 64) + (size_t)nhalf * 32 + 64;
     return need < RSR_EXCLUSIVE_SMEM_REC ? RSR_EXCLUSIVE_SMEM_REC : need;
-}
-
-// Launch geometry of one cluster kernel variant, decided once per (kernel, Cp): does a cluster of
-// G CTAs with this much shared memory fit, and how many can be co-resident.
-template <typename K>
-int cluster_capacity(K kernel, int G, int threads, size_t smem) {
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-    if (G > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(G, 1, 1);
-    cfg.blockDim = dim3(threads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return n;
-}
-
-template <typename K, typename... Args>
-int cluster_launch(K kernel, int groups, int G, int threads, size_t smem, cudaStream_t stream, const Args&... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(groups * G, 1, 1);
-    cfg.blockDim = dim3(threads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
-    if (e != cudaSuccess) return (int)e;
-    return 0;
 }
 
 // halves (independent 16-utterance recurrences) per cluster: 1 when that many clusters run concurrently

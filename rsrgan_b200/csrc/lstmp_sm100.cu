@@ -468,6 +468,11 @@ extern "C" int rsr_lstmp_fused_fwd(rsr_handle* h, void* stream, int B, int T, in
          (uintptr_t)mt_seq | (uintptr_t)save) & 15)
         return RSR_E_ARG;
     if (getenv("RSR_NO_CLUSTER") || getenv("RSR_NO_FUSEX")) return RSR_E_RESIDENT;
+    if (!getenv("RSR_NO_PAIR")) {   // CTA-pair kernel first (half the exchange traffic and MMA issues per utterance)
+        const int rcp = rsr_lstmp_fused_fwd_pair(h, stream, B, T, I, Cp, x16, ldx, kxT, bias, wcT, w_i, w_f, w_o, forget_bias,
+                                                 lengths, mt_seq, save);
+        if (rcp != RSR_E_RESIDENT) return rcp;
+    }
     return rsr_lstmp_fused_fwd_cluster(h, stream, B, T, I, Cp, x16, ldx, kxT, bias, wcT, w_i, w_f, w_o, forget_bias,
                                        lengths, mt_seq, save);
 }

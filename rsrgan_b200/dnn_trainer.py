@@ -64,7 +64,7 @@ class DNNTrainer(GAN_RNN):
         B, T = int(x3.shape[0]), int(x3.shape[1])
         x, y_tm, ln, B, T = self._feed(x3, y3, np.full(B, T, np.int32))
         h, G, rows = self.h, self.G, T * B
-        self._mode(train)
+        self._mode(train, g_update=train)     # UPDATE_OPS run with every training step (dnn_trainer_single_gpu.py:101-104)
         gs = self._gscale(rows) if want_grad else 1.0
         g32 = G.fwd(x, B, T, ln, train=train)
         dg32 = G.ws.get(("loss", "dg32"), rows, g32.shape[1], F32) if want_grad else None

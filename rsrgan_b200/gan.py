@@ -33,7 +33,8 @@ class GAN(GAN_RNN):
         super(GAN, self).__init__(sess, Namespace(**a), devices, cross_validation=cross_validation, infer=False,
                                   name=name, handle=handle, share=share)
         self.max_grad_norm = 1e30            # apply_gradients(avg_grads) with no clip_by_norm (:146-151)
-        self.update_bn_stats = True          # control_dependencies(UPDATE_OPS) around compute_gradients (:139-143)
+        self.update_bn_stats = True          # control_dependencies(UPDATE_OPS) around compute_gradients (:139-143):
+        self.bn_update_scope = "all"         # ... the WHOLE collection, for both optimizers
         self.d_real, self.d_fake = 1.0, 0.0  # squared_difference(logits, 1.) / (logits, 0.) (:200-202)
         self.disc_noise_std = 0.0            # the noise layer is commented out in discriminator_dnn (:58)
         if share is None:

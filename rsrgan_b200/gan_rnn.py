@@ -133,10 +133,13 @@ class GAN_RNN(Model):
         self.batch_norm = _arg(args, "batch_norm", False)
         # contrib batch_norm(renorm) on the fully_connected layers and tf.nn.dropout behind them are nets.FCBN
         # (csrc/batchnorm.cu); DropoutWrapper on the LSTM generators is nets.Generator._drop_fwd / _drop_bwd.
-        # This trainer never runs the UPDATE_OPS (:169-175 has no control dependency on them), so the moving
-        # averages of a batch-normalised GAN stay at their initial values -- reference behaviour, kept
-        # (`update_bn_stats = True` opts out); DNNTrainer does run them.
-        self.update_bn_stats = False
+        # UPDATE_OPS (moving mean / variance and the renorm statistics of every batch-normalised layer): :163-175
+        # collects the g_model and the d_model update ops separately and makes d_opt's compute_gradients depend on the
+        # d_model ones, g_opt's on the g_model ones.  So a D update assigns D's statistics (both passes, D(labels) and
+        # D(G(x))) and leaves G's alone; a G update assigns G's and leaves D's alone.  `bn_update_scope = "all"` is the
+        # frame-level GAN of models/gan.py:139-143, whose two optimizers both depend on the WHOLE collection.
+        self.update_bn_stats = True
+        self.bn_update_scope = "own"
         self.ckpt_format = _arg(args, "ckpt_format", "pt")   # "tf": TensorFlow checkpoint-V2 bundles (tf_checkpoint.py)
         self.batch_size = _arg(args, "batch_size", 8)
         self.devices = devices
@@ -213,7 +216,7 @@ class GAN_RNN(Model):
         # RSR_NO_GRAPH=1 or use_graph=False runs every kernel eagerly
         self.use_graph = (_arg(args, "use_graph", True) and os.environ.get("RSR_NO_GRAPH", "0") != "1"
                           and dev.type == "cuda")
-        self._graphs = {}
+        self._graphs, self._graphs_gen = {}, None
         self._copy_stream, self._prefetched, self._prefetch_bufs = None, None, {}
         # With several ranks the schedule is captured as one graph SEGMENT per update; the NCCL all-reduce of the
         # flat gradient buffer runs eagerly between segments (capturing NCCL itself hung on 2 x B200 with
@@ -377,13 +380,15 @@ class GAN_RNN(Model):
         return float(2.0 ** round(math.log2(max(rows / max(self.mse_lambda, 1.0), 1.0))))
 
     # ------------------------------------------------------------------ updates
-    def _mode(self, training):
+    def _mode(self, training, g_update=False, d_update=False):
         """is_training of the graph about to run (batch_norm statistics, dropout): False on the cross-validation /
-        inference models (models/dnn.py:50, models/discriminator_dnn.py:30)."""
-        for net in (self.G, self.D):
+        inference models (models/dnn.py:50, models/discriminator_dnn.py:30).  g_update / d_update: which network's
+        UPDATE_OPS the optimizer op about to run depends on (see __init__)."""
+        every = self.bn_update_scope == "all" and (g_update or d_update)
+        for net, upd in ((self.G, g_update), (self.D, d_update)):
             if net is not None:
                 net.training = bool(training) and not self.cross_validation
-                net.bn_update = bool(self.update_bn_stats)
+                net.bn_update = bool(self.update_bn_stats) and net.training and (upd or every)
 
     def _update(self, net, gscale, adam):
         P, h = net.P, self.h
@@ -431,12 +436,14 @@ class GAN_RNN(Model):
         self._losses[4:5] = 0.5 * self.l2_scale * (P.sumsq * P.seg_l2.to(F32)).sum()
 
     def d_step(self, inputs, labels, lengths, noise_rl=None, noise_fk=None, sync=True, _feed=None, _g32=None,
-               _g_train=False):
+               _g_train=False, _g_reuse=False):
         """One discriminator update: L_D = mean((D(y)-d_real)^2) + mean((D(G(x))-d_fake)^2),
         gradients wrt theta_D only, tower mean, per-tensor clip 15, SGD(lr_d), EMA."""
         x, y_tm, ln, B, T = _feed if _feed is not None else self._feed(inputs, labels, lengths)
         h, G, D, rows = self.h, self.G, self.D, T * B
-        self._mode(True)
+        # _g_reuse: the generator forward computed here is the one the first G update of the schedule reuses, so it is
+        # the forward that G update's UPDATE_OPS belong to
+        self._mode(True, g_update=_g_reuse and _g32 is None, d_update=True)
         gs = self._gscale(rows)
         d_rl16 = D.ws.get(("loss", "d_rl16"), rows, 8, h.h16)
         d_fk16 = D.ws.get(("loss", "d_fk16"), rows, 8, h.h16)
@@ -447,9 +454,9 @@ class GAN_RNN(Model):
                   ld_grad=8)
         # D(labels) does not depend on the generator: its forward, loss and backward run on the side stream
         # while the generator recurrences (which occupy only the SMs of their clusters) run on this one.
-        # (a batch-normalised D whose UPDATE_OPS run assigns its moving averages in both passes: those two then stay
-        # on one stream, D(labels) first, so that neither read-modify-write is lost)
-        serial = D.fcbn and self.update_bn_stats
+        # (a batch-normalised D assigns its moving averages in both passes: those two then stay on one stream,
+        # D(labels) first, so that neither read-modify-write is lost)
+        serial = D.fcbn and D.bn_update
         with (contextlib.nullcontext() if serial else h.side_stream()):
             lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=n_rl, cat_src=self._cat(x))
             h.lsgan_mse_losses(self._losses, rl=lg_rl, ld_logit=lg_rl.stride(0), d_rl_grad=d_rl16, **kw)
@@ -468,9 +475,13 @@ class GAN_RNN(Model):
         gradients wrt theta_G only (through D, D frozen), tower mean, clip 15, Adam(lr_g), EMA."""
         x, y_tm, ln, B, T = _feed if _feed is not None else self._feed(inputs, labels, lengths)
         h, G, D, rows = self.h, self.G, self.D, T * B
-        self._mode(True)
+        self._mode(True, g_update=_g32 is None, d_update=False)
         gs = self._gscale(rows)
         g32 = _g32 if _g32 is not None else G.fwd(x, B, T, ln, train=True, reuse_staged=_x_staged)
+        if D.fcbn and D.bn_update:
+            # frame-level GAN: g_opt depends on the whole UPDATE_OPS collection (models/gan.py:139-143), which holds the
+            # assignments of the D(labels) pass too -- run that pass for its statistics (its output is not needed)
+            D.fwd("rl", y_tm, B, T, ln, noise=self._noise(B, None), cat_src=self._cat(x))
         lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"), cat_src=self._cat(x))
         g_adv16 = D.ws.get(("loss", "g_adv16"), rows, 8, h.h16)
         # d(lambda g_mse)/dg is added to the discriminator's input gradient by its last GEMM (resid): same width as
@@ -502,7 +513,8 @@ class GAN_RNN(Model):
         d_all, g_all = [], []
         share = self.G.keep_prob >= 1.0                    # a generator with dropout draws a new mask per sess.run
         for _ in range(self.disc_updates):
-            d = self.d_step(None, None, None, sync=False, _feed=feed, _g32=g32, _g_train=self.gen_updates > 0)
+            d = self.d_step(None, None, None, sync=False, _feed=feed, _g32=g32, _g_train=self.gen_updates > 0,
+                            _g_reuse=share and self.gen_updates > 0)
             g32 = self._last_g32 if share else None
             d_all.append(d[:2].clone())
         for k in range(self.gen_updates):
@@ -557,11 +569,24 @@ class GAN_RNN(Model):
         x, y, ln = self._prefetch_bufs["sets"][pf[1]]
         return x, y, ln, pf[1]
 
+    def _ws_generation(self):
+        """Replacement counters of the workspaces a captured schedule addresses (nets.Workspace.generation)."""
+        return (self.G.ws.generation, self.D.ws.generation if self.D is not None else 0)
+
     def _schedule_graphed(self, inputs, labels, lengths):
         """Copies the minibatch into static device buffers and replays the captured schedule.  The first two
-        calls for a given shape / scalar set run eagerly (they allocate the workspace), the third captures."""
+        calls for a given shape / scalar set run eagerly (they allocate the workspace), the third captures.
+        A graph holds raw workspace addresses: when a workspace buffer has been replaced since the capture (a longer
+        batch, or the cross-validation model running a longer utterance on the shared workspace) every captured
+        schedule is dropped and captured again after one eager call."""
         B, T = int(inputs.shape[0]), int(inputs.shape[1])
         key = self._graph_key(B, T)
+        gen = self._ws_generation()
+        if self._graphs and self._graphs_gen != gen:
+            for other in self._graphs.values():
+                if other["graph"] is not None:
+                    other["graph"], other["calls"] = None, 1
+        self._graphs_gen = gen
         st = self._graphs.get(key)
         if st is None:
             dev = self.h.device
@@ -581,6 +606,11 @@ class GAN_RNN(Model):
             return self._schedule(feed)
         if st["graph"] is None:
             self._capture(st)
+            if self._ws_generation() != gen:                # (not expected: the eager calls above sized every buffer)
+                for other in self._graphs.values():
+                    if other is not st and other["graph"] is not None:
+                        other["graph"], other["calls"] = None, 1
+                self._graphs_gen = self._ws_generation()
         for g, ar in st["graph"]:
             g.replay()
             if ar is not None:

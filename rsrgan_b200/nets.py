@@ -26,16 +26,27 @@ F32 = torch.float32
 
 
 class Workspace(object):
-    """Named device buffers, zero-filled at allocation, grown on demand (rows only)."""
+    """Named device buffers, zero-filled at allocation, grown on demand (rows only).
+
+    `generation` counts REPLACEMENTS of an existing buffer (a longer batch needed more rows): the old tensor is
+    freed, so anything that recorded its address -- the CUDA graphs GAN_RNN captures per batch shape -- is stale
+    from then on.  GAN_RNN compares generations before every replay and re-captures (gan_rnn._schedule_graphed).
+    Growth is geometric so that a stream of slowly lengthening batches settles after a few replacements."""
 
     def __init__(self, handle):
         self.h = handle
         self.bufs = {}
+        self.generation = 0
 
     def get(self, key, rows, cols, dtype):
         t = self.bufs.get(key)
         if t is None or t.shape[0] < rows or t.shape[1] != cols or t.dtype != dtype:
-            t = torch.zeros(rows, cols, dtype=dtype, device=self.h.device)
+            alloc = rows
+            if t is not None:
+                self.generation += 1
+                if t.shape[1] == cols and t.dtype == dtype:
+                    alloc = max(rows, t.shape[0] + t.shape[0] // 4)
+            t = torch.zeros(alloc, cols, dtype=dtype, device=self.h.device)
             self.bufs[key] = t
         return t[:rows]
 
@@ -458,8 +469,9 @@ class Net(object):
         self.h = handle
         self.ws = Workspace(handle)
         # batch_norm / dropout mode (FCBN layers): `training` = is_training of the graph being run (False for the
-        # cross-validation / inference models), `bn_update` = whether the UPDATE_OPS run with the step
-        # (models/dnn_trainer_single_gpu.py:101-104 yes; models/gan_rnn_placeholder.py:169-175 no), `rng` = device
+        # cross-validation / inference models), `bn_update` = whether THIS network's UPDATE_OPS run with the step
+        # about to be taken (models/dnn_trainer_single_gpu.py:101-104; models/gan_rnn_placeholder.py:163-175: d_opt runs
+        # the d_model ones, g_opt the g_model ones -- set per step by GAN_RNN._mode), `rng` = device
         # {seed, tick} of the dropout stream (rsr_affine_act_drop)
         self.training, self.bn_update = True, False
         self.keep_prob = getattr(self, "keep_prob", 1.0)

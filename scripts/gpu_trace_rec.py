@@ -24,7 +24,14 @@ ln = torch.full((B,), T, dtype=torch.int32, device=dev)
 mt = torch.zeros(rows + B, Cp, dtype=h.h16, device=dev)
 save = torch.zeros(rows, 5 * Cp, device=dev)
 h.lstmp_rec_fwd(B, T, Cp, zx, wcT, w[0], w[1], w[2], ln, mt, save)
-if which == "bwd":
+if which == "pfwd":      # fused forward, CTA-pair kernel (lstmp_pair_sm100.cu)
+    I = 256
+    x16 = (torch.randn(rows, I, device=dev) * 0.5).to(h.h16)
+    kxT = (torch.randn(4 * Cp, I, device=dev) * 0.03).to(h.h16)
+    bias = torch.randn(4 * Cp, device=dev) * 0.1
+    for _ in range(3):
+        assert h.lstmp_fused_fwd(B, T, I, Cp, x16, kxT, bias, wcT, w[0], w[1], w[2], ln, mt, save)
+elif which == "bwd":
     wc = wcT.t().contiguous()
     dmt = torch.randn(rows, Cp, device=dev) * 0.01
     dz = torch.zeros(rows + B, 4 * Cp, dtype=h.h16, device=dev)
@@ -37,10 +44,11 @@ else:
         h.lstmp_rec_fwd(B, T, Cp, zx, wcT, w[0], w[1], w[2], ln, mt, save)
 torch.cuda.synchronize()
 buf = (C.c_ulonglong * (64 * 8))()
-h.lib.rsr_debug_trace.argtypes = [C.c_void_p, C.c_int]
-rc = h.lib.rsr_debug_trace(buf, 64 * 8)
+fn = h.lib.rsr_debug_trace_pair if which.startswith("p") else h.lib.rsr_debug_trace
+fn.argtypes = [C.c_void_p, C.c_int]
+rc = fn(buf, 64 * 8)
 tr = np.array(buf[:], dtype=np.int64).reshape(64, 8)[:T]
-names = (["top", "full-wait done", "mma issued", "mma done", "xchg+sync", "gate math", "st.async sends", "global stores"] if which == "fwd" else
+names = (["top", "full-wait done", "mma issued", "mma done", "xchg+sync", "gate math", "st.async sends", "global stores"] if which in ("fwd", "pfwd") else
          ["top", "partials landed", "summed", "gate math", "dz stores", "bar+mma issued", "mma done", "ld+send"])
 print(which, "B %d Cp %d rc %d; cycles between trace points (median over steps 5..%d)" % (B, Cp, rc, T - 2))
 nt = len(names)

@@ -196,10 +196,11 @@ def test_dnn_trainer_batch_norm_steps_match_oracle():
 
 
 def test_gan_with_batch_norm_discriminator_matches_oracle():
-    """dnn generator + discriminator_dnn, both batch-normalised, dropout in D: gradients of one D and one G update;
-    the placeholder GAN never runs the UPDATE_OPS, so the moving averages stay put."""
-    rng = np.random.default_rng(6)
-    B, T, I, U = 3, 6, 40, 32
+    """dnn generator + discriminator_dnn, both batch-normalised, dropout in D: gradients of one D and one G update.
+    UPDATE_OPS as models/gan_rnn_placeholder.py:163-175 wires them: the D update assigns the discriminator's statistics
+    (both passes) and leaves the generator's alone, the G update the other way round."""
+    rng = np.random.default_rng(8)
+    B, T, I, U = 6, 16, 40, 64            # enough rows that a single relu' sign flip of a near-zero pre-activation stays below the bar
     args = Namespace(g_type="dnn", d_type="dnn", batch_size=B, input_dim=I, output_dim=8, g_units=U, g_layers=1,
                      d_units=U, d_layers=1, batch_norm=True, keep_prob=0.75, init_mse_weight=10.0, l2_scale=0.0,
                      g_learning_rate=0.0, d_learning_rate=0.0, seed=4)
@@ -221,22 +222,32 @@ def test_gan_with_batch_norm_discriminator_matches_oracle():
     st = O.GanState(gp, dp, "dnn", "dnn")
     seed = int(m.D.rng[0])
     gs = m._gscale(B * T)
+    assert m.update_bn_stats and m.bn_update_scope == "own"
+    g_run, d_run = copy.deepcopy(gbs), copy.deepcopy(dbs)      # the oracle's running statistics
     for tick, which in enumerate("dg"):
-        go = dict(bn_state=copy.deepcopy(gbs))
-        do = dict(bn_state=copy.deepcopy(dbs), keep_prob=0.75, rng=(seed, tick))
+        go = dict(bn_state=g_run)
+        do = dict(bn_state=d_run, keep_prob=0.75, rng=(seed, tick))
         # time-major rows inside the library: the oracle must draw its mask over the same (t, b) row order
         xt, yt = x.transpose(1, 0, 2).astype(np.float64), y.transpose(1, 0, 2).astype(np.float64)
-        L, G, _ = O.tower_losses_and_grads(st, xt, yt, ln, which, g_opts=go, d_opts=do)
+        L, G, _ = O.tower_losses_and_grads(st, xt, yt, ln, which, g_opts=go, d_opts=do, update_ops="own")
         out = (m.d_step if which == "d" else m.g_step)(x, y, ln)
+        if which == "d":        # the generator's statistics did not move during the D update
+            for k, v in m.G.bn_state_tf().items():
+                assert np.allclose(v, gbs[k], rtol=1e-6), k
         net, keys = (m.D, ("d_rl_loss", "d_fk_loss")) if which == "d" else (m.G, ("g_adv_loss", "g_mse_loss"))
         for k in keys:
             assert out[k] == pytest.approx(L[k], rel=3e-3, abs=1e-5), k
         mine = net.P.export_tf("grad")
         for k in G:
-            assert rel(mine[k] / gs, G[k]) < 2e-2, (which, k)
-    for net, ref in ((m.G, gbs), (m.D, dbs)):               # UPDATE_OPS not run by this trainer
+            # (relu' and the output clip are step functions: one near-zero pre-activation that rounds to the other side
+            #  in 16-bit moves a per-column gradient of this small network by a few per cent)
+            assert rel(mine[k] / gs, G[k]) < 3e-2, (which, k)
+    moved = 0
+    for net, ref, init in ((m.G, g_run, gbs), (m.D, d_run, dbs)):
         for k, v in net.bn_state_tf().items():
-            assert np.allclose(v, ref[k], rtol=1e-6), k
+            assert np.allclose(v, ref[k], rtol=2e-3, atol=2e-5), k
+            moved += int(not np.allclose(ref[k], init[k], rtol=1e-6))
+    assert moved >= 8                                        # ... and they did move in the update that owns them
 
 
 def test_lstm_generator_first_layer_batch_norm_and_noops():
