@@ -190,16 +190,19 @@ int rsr_colsum32(rsr_handle* h, void* stream, const float* x32, int ld, long lon
  *           EMA : ema -= (1 - decay) * (ema - theta_new)                        (:149-150,185-189; ema NULL = skip)
  *           theta16 = h16(theta_new)      operand copy for the tensor cores (NULL = skip)
  * hyper (device fp32[8]): [0]=lr [1]=beta1 [2]=beta2 [3]=eps [4]=beta1_power [5]=beta2_power
- * [6]=lr_t scratch.  Learning rates live on the device so a captured CUDA graph stays valid when
+ * [6]=lr_t scratch [7]=number of updates SKIPPED because a gradient norm was not finite (overflow
+ * guard of the 16-bit backward pass: with n_seg > 0 both calls scan sumsq[0..n_seg) first and leave
+ * theta / m / v / ema / theta16 / the beta powers untouched when any entry is inf or NaN; n_seg = 0
+ * switches the guard off).  Learning rates live on the device so a captured CUDA graph stays valid when
  * the host decays them (scripts/train_gan_rnn_placeholder.py:525-533).  The Adam call advances
  * the beta powers exactly as TF's _finish does (initialise [4]=beta1, [5]=beta2). */
 int rsr_seg_sumsq(rsr_handle* h, void* stream, const float* grad, float gmul, const int* seg_id,
                   long long n_elems, int n_seg, float* sumsq);
 int rsr_clip_sgd_ema(rsr_handle* h, void* stream, const float* grad, float gmul, const int* seg_id,
-                     const float* sumsq, float max_norm, const float* hyper, float ema_decay,
+                     const float* sumsq, int n_seg, float max_norm, float* hyper, float ema_decay,
                      long long n_elems, float* theta, float* ema, void* theta16);
 int rsr_clip_adam_ema(rsr_handle* h, void* stream, const float* grad, float gmul, const int* seg_id,
-                      const float* sumsq, float max_norm, float* hyper, float ema_decay,
+                      const float* sumsq, int n_seg, float max_norm, float* hyper, float ema_decay,
                       long long n_elems, float* theta, float* m, float* v, float* ema, void* theta16);
 
 /* L2 regulariser of G (models/gan_rnn_placeholder.py:253-258): grad += scale * theta on every

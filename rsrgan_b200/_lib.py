@@ -54,8 +54,8 @@ SIGNATURES = {
     "rsr_colsum16": [vp, vp, vp, ci, cll, ci, vp, ci],
     "rsr_colsum32": [vp, vp, vp, ci, cll, ci, vp, ci],
     "rsr_seg_sumsq": [vp, vp, vp, cf, vp, cll, ci, vp],
-    "rsr_clip_sgd_ema": [vp, vp, vp, cf, vp, vp, cf, vp, cf, cll, vp, vp, vp],
-    "rsr_clip_adam_ema": [vp, vp, vp, cf, vp, vp, cf, vp, cf, cll, vp, vp, vp, vp, vp],
+    "rsr_clip_sgd_ema": [vp, vp, vp, cf, vp, vp, ci, cf, vp, cf, cll, vp, vp, vp],
+    "rsr_clip_adam_ema": [vp, vp, vp, cf, vp, vp, ci, cf, vp, cf, cll, vp, vp, vp, vp, vp],
     "rsr_l2_grad": [vp, vp, vp, vp, vp, vp, cf, cll],
     "rsr_add_cast": [vp, vp, vp, vp, cll, vp, vp],
     "rsr_cast16": [vp, vp, vp, cll, vp],

@@ -384,6 +384,9 @@ __device__ __forceinline__ void tc_commit_2cta_mc(uint32_t bar, uint16_t mask) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// (explicit .release.cluster / .acquire.cluster forms of arrive / try_wait cost ~1000 cycles each on B200 -- ptxas emits
+//  a cluster-scope fence that invalidates L1 -- and are not needed here: the data the peers publish is shared memory
+//  consumed by the tensor core / async proxy after a proxy fence, not L1-cached global memory)
 
 // ---------------------------------------------------------------------------
 // cross-CTA flag helpers (group barriers of the persistent recurrent kernels)

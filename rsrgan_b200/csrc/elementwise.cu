@@ -302,7 +302,19 @@ __global__ void __launch_bounds__(256) seg_sumsq_finish_kernel(const float* __re
     if (threadIdx.x == 0) sumsq[seg] = sh[0];
 }
 
-__global__ void adam_tock_kernel(float* hyper) {
+// Overflow guard of the 16-bit backward pass (fp16 operands under a static loss scale): a gradient tensor that picked
+// up an inf / NaN has a non-finite norm.  The update sweep and the Adam tick then leave EVERYTHING untouched (weights,
+// slots, shadows, beta powers -- the fp32 reference would have taken a finite, clipped step; skipping one update is the
+// closest finite behaviour) and count the event in hyper[7]; the host halves the loss scale when the counter moves.
+__device__ __forceinline__ bool any_nonfinite_norm(const float* __restrict__ sumsq, int n_seg) {
+    bool bad = false;
+    for (int s = (int)(threadIdx.x & 31); s < n_seg; s += 32) bad |= !isfinite(sumsq[s]);
+    return __any_sync(0xffffffffu, bad);
+}
+
+__global__ void adam_tock_kernel(float* hyper, const float* __restrict__ sumsq, int n_seg) {
+    if (any_nonfinite_norm(sumsq, n_seg)) return;
+    if (threadIdx.x) return;
     hyper[6] = hyper[0] * sqrtf(1.f - hyper[5]) / (1.f - hyper[4]);   // lr_t of the step just applied (diagnostic)
     hyper[4] *= hyper[1];
     hyper[5] *= hyper[2];
@@ -312,10 +324,14 @@ template <int ADAM>
 __global__ void __launch_bounds__(256) clip_update_kernel(const float* __restrict__ g, float gmul,
                                                           const int* __restrict__ seg_id,
                                                           const float* __restrict__ sumsq, float max_norm,
-                                                          const float* __restrict__ hyper, float ema_decay,
+                                                          float* __restrict__ hyper, float ema_decay,
                                                           float* __restrict__ theta, float* __restrict__ m,
                                                           float* __restrict__ v, float* __restrict__ ema,
-                                                          uint16_t* __restrict__ theta16, int bf) {
+                                                          uint16_t* __restrict__ theta16, int bf, int n_seg) {
+    if (any_nonfinite_norm(sumsq, n_seg)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) hyper[7] += 1.0f;
+        return;
+    }
     const long long base = (long long)blockIdx.x * 1024 + threadIdx.x * 4;
     const float nrm = sqrtf(sumsq[seg_id[blockIdx.x]]);
     const float sc = gmul * (max_norm / fmaxf(nrm, max_norm));   // tf.clip_by_norm: g * clip / max(norm, clip)
@@ -596,24 +612,25 @@ extern "C" int rsr_seg_sumsq(rsr_handle* h, void* stream, const float* grad, flo
 }
 
 extern "C" int rsr_clip_sgd_ema(rsr_handle* h, void* stream, const float* grad, float gmul, const int* seg_id,
-                                const float* sumsq, float max_norm, const float* hyper, float ema_decay,
+                                const float* sumsq, int n_seg, float max_norm, float* hyper, float ema_decay,
                                 long long n_elems, float* theta, float* ema, void* theta16) {
-    if (!h || !grad || !seg_id || !sumsq || !hyper || !theta || n_elems <= 0 || (n_elems & 1023)) return RSR_E_ARG;
+    if (!h || !grad || !seg_id || !sumsq || !hyper || !theta || n_elems <= 0 || (n_elems & 1023) || n_seg < 0) return RSR_E_ARG;
     clip_update_kernel<0><<<(unsigned)(n_elems / 1024), 256, 0, (cudaStream_t)stream>>>(
         grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, nullptr, nullptr, ema, (uint16_t*)theta16,
-        h->dtype == RSR_DTYPE_BF16);
+        h->dtype == RSR_DTYPE_BF16, n_seg);
     RSR_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int rsr_clip_adam_ema(rsr_handle* h, void* stream, const float* grad, float gmul, const int* seg_id,
-                                 const float* sumsq, float max_norm, float* hyper, float ema_decay,
+                                 const float* sumsq, int n_seg, float max_norm, float* hyper, float ema_decay,
                                  long long n_elems, float* theta, float* m, float* v, float* ema, void* theta16) {
-    if (!h || !grad || !seg_id || !sumsq || !hyper || !theta || !m || !v || n_elems <= 0 || (n_elems & 1023)) return RSR_E_ARG;
+    if (!h || !grad || !seg_id || !sumsq || !hyper || !theta || !m || !v || n_elems <= 0 || (n_elems & 1023) || n_seg < 0)
+        return RSR_E_ARG;
     clip_update_kernel<1><<<(unsigned)(n_elems / 1024), 256, 0, (cudaStream_t)stream>>>(
         grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, m, v, ema, (uint16_t*)theta16,
-        h->dtype == RSR_DTYPE_BF16);
-    adam_tock_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper);
+        h->dtype == RSR_DTYPE_BF16, n_seg);
+    adam_tock_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(hyper, sumsq, n_seg);
     RSR_LAUNCH_CHECK();
     return 0;
 }

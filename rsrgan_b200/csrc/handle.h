@@ -85,6 +85,9 @@ int rsr_lstmp_fused_fwd_pair(rsr_handle* h, void* stream, int B, int T, int I, i
                              const void* kxT, const float* bias, const void* wcT, const float* w_i,
                              const float* w_f, const float* w_o, float forget_bias, const int* lengths,
                              void* mt_seq, float* save);
+int rsr_lstmp_bwd_pair(rsr_handle* h, void* stream, int B, int T, int Cp, const float* dmt, const void* wc,
+                       const float* w_i, const float* w_f, const float* w_o, const int* lengths,
+                       const float* save, void* dz16, float* dbias, float* dw_i, float* dw_f, float* dw_o);
 int rsr_lstmp_bwd_cluster(rsr_handle* h, void* stream, int B, int T, int Cp, const float* dmt, const void* wc,
                           const float* w_i, const float* w_f, const float* w_o, const int* lengths,
                           const float* save, void* dz16, float* dbias, float* dw_i, float* dw_f, float* dw_o);

@@ -35,6 +35,19 @@ constexpr int NBP = 32;         // utterances per cluster
 constexpr int GATE_THREADS = 256;
 constexpr int PAIR_THREADS = GATE_THREADS + 32;   // + the issuer / relay warp
 
+// MUFU.TANH forms of the gate non-linearities (default; RSR_FAST_GATES=0 selects the ex2 + rcp forms of common.cuh):
+// one special-function instruction per gate instead of two and ~6 FP32 instructions.  Relative error 2^-11 -- the size
+// of the rounding every 16-bit MMA operand already carries -- and no measurable effect on parity at the benchmarked
+// lengths (profiles/r2_parity_measured_v0.jsonl: generator output RMS vs the float64 oracle at B = 128, T = 100
+// 5.79e-5 with, 5.84e-5 without; gradients and post-schedule output likewise), for a gate phase of 582 instead of 976
+// cycles per step (profiles/r2_pair_kernels_v6.txt)
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
 __device__ __forceinline__ void tc_mma_f16_ts_2cta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -69,7 +82,7 @@ struct PFwdParams {
 // math + sends instead of 927 + 1093) or with 256-byte bulk copies from a sender warp (per-copy overhead and a proxy
 // fence per chunk: 5579 cycles per step instead of 3763); sharing reciprocals between gates (7 MUFU operations per cell
 // instead of 10: the gate phase is latency-, not MUFU-bound).
-template <int NCH>
+template <int NCH, int BF, int FAST>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 lstmp_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const PFwdParams p) {
     constexpr int NBC = NBP / NCH;              // utterances per chain = UMMA N
@@ -168,7 +181,7 @@ lstmp_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const PFwdParams 
                     tma_load_2d_2cta(sXt(hc, 0) + (uint32_t)kb * (NBR * 128u), &tmX, xfull(hc, 0) + lead, kb * 64,
                                      b0 + hc * NBC + (int)e * NBR);
             }
-            const uint32_t idesc = umma_idesc(256, NBC, p.bf, 0, 0);
+            const uint32_t idesc = umma_idesc(256, NBC, BF, 0, 0);
             const uint16_t pair_mask = (uint16_t)(3u << (j & ~1u));
             for (int t = 0; t < p.T; ++t) {
                 const int buf = t & 1;
@@ -193,7 +206,7 @@ lstmp_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const PFwdParams 
                         if (t > 0) {
                             const uint32_t ph = (uint32_t)(((t - 1) >> 1) & 1);
                             mbar_wait(full(hc, buf), ph);            // my rows of mt_{t-1}: all G slices have landed
-                            mbar_wait(peer(hc, buf), ph);            // ... and the odd CTA's rows
+                            mbar_wait(peer(hc, buf), ph);   // ... and the odd CTA's rows
                         }
                         PTRACE(hc == 0, t, 1);
                         fence_proxy_async_smem();
@@ -272,17 +285,17 @@ lstmp_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const PFwdParams 
                 const float zf = xchg[(2 * 32 + cl) * XP + nl];
                 const float zo = xchg[(3 * 32 + cl) * XP + nl];
                 const float cp = creg[c];
-                const float ig = sigmoidf_(zi + wi[c] * cp);
-                const float fg = sigmoidf_(zf + p.forget_bias + wf[c] * cp);
-                const float jg = tanhf_(zj);
+                const float ig = FAST ? sigmoid_fast(zi + wi[c] * cp) : sigmoidf_(zi + wi[c] * cp);
+                const float fg = FAST ? sigmoid_fast(zf + p.forget_bias + wf[c] * cp) : sigmoidf_(zf + p.forget_bias + wf[c] * cp);
+                const float jg = FAST ? tanh_fast(zj) : tanhf_(zj);
                 const float cn = fg * cp + ig * jg;
-                const float og = sigmoidf_(zo + wo[c] * cn);
-                const float mt = og * tanhf_(cn);
+                const float og = FAST ? sigmoid_fast(zo + wo[c] * cn) : sigmoidf_(zo + wo[c] * cn);
+                const float mt = og * (FAST ? tanh_fast(cn) : tanhf_(cn));
                 sv[0][c] = ig; sv[1][c] = fg; sv[2][c] = og; sv[3][c] = jg; sv[4][c] = cn;
                 mtv[c] = active ? mt : 0.f;
                 if (active) creg[c] = cn;
             }
-            const uint32_t lo = pack2(mtv[0], mtv[1], p.bf), hi = pack2(mtv[2], mtv[3], p.bf);
+            const uint32_t lo = pack2(mtv[0], mtv[1], BF), hi = pack2(mtv[2], mtv[3], BF);
             PTRACE(tid == 0, t, 5);
             // (the exchange buffer is rewritten at step t+1 only after the NEXT barM, which needs every warp's sends below)
             if (t + 1 < p.T) {
@@ -345,26 +358,358 @@ int rsr_lstmp_fused_fwd_pair(rsr_handle* h, void* stream, int B, int T, int I, i
     const int nch = pair_chains();
     const size_t smem = pfwd_smem(Cp, Ik, nch);
     if (smem > (size_t)h->max_smem) return RSR_E_RESIDENT;
-    int& cap = h->pair_cap[0][Cp / 256 - 1];
-    if (cap < 0 || h->pair_ik[Cp / 256 - 1] != Ik * 4 + nch) {
+    const int bf = h->dtype == RSR_DTYPE_BF16;
+    static const int fast = getenv("RSR_FAST_GATES") ? (atoi(getenv("RSR_FAST_GATES")) ? 1 : 0) : 1;
+    auto run = [&](auto kernel) -> int {
+        int& cap = h->pair_cap[0][Cp / 256 - 1];
+        const int key = ((Ik * 4 + nch) * 2 + bf) * 2 + fast;
+        if (cap < 0 || h->pair_ik[Cp / 256 - 1] != key) {
+            std::lock_guard<std::mutex> g(h->mu);
+            cap = cluster_capacity(kernel, G, PAIR_THREADS, smem);
+            h->pair_ik[Cp / 256 - 1] = key;
+            if (getenv("RSR_DEBUG")) fprintf(stderr, "[rsr] fused fwd pair kernel Cp=%d Ik=%d: %d-CTA clusters co-resident: %d\n", Cp, Ik, G, cap);
+        }
+        if (cap <= 0) return RSR_E_RESIDENT;
+        const int groups = (B + NBP - 1) / NBP;
+        CUtensorMap tmX;
+        int rc = rsr_get_tmap(h, x16, (uint64_t)ldx, (uint64_t)T * B, (uint64_t)ldx, 64, (uint32_t)(NBP / nch / 2), &tmX);
+        if (rc) return rc;
+        PFwdParams p;
+        p.B = B; p.T = T; p.Cp = Cp; p.bf = bf; p.forget_bias = forget_bias;
+        p.wcT = (const uint16_t*)wcT; p.kxT = (const uint16_t*)kxT; p.bias = bias;
+        p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths;
+        p.mt_seq = (uint16_t*)mt_seq; p.save = save; p.Ik = Ik;
+        return cluster_launch(kernel, groups, G, PAIR_THREADS, smem, (cudaStream_t)stream, tmX, p);
+    };
+    if (nch == 2) return bf ? run(lstmp_fwd_pair_kernel<2, 1, 0>) : run(lstmp_fwd_pair_kernel<2, 0, 0>);
+    if (fast) return bf ? run(lstmp_fwd_pair_kernel<1, 1, 1>) : run(lstmp_fwd_pair_kernel<1, 0, 1>);
+    return bf ? run(lstmp_fwd_pair_kernel<1, 1, 0>) : run(lstmp_fwd_pair_kernel<1, 0, 0>);
+}
+
+// =========================================================================================
+// backward, CTA-pair variant
+// =========================================================================================
+namespace {
+
+struct PBwdParams {
+    int B, T, Cp, bf;
+    const float* dmt;           // [T*B, Cp] dOut W_p^T (read only)
+    const uint16_t* wc;         // [Cp, 4Cp] packed gate columns
+    const float* w_i; const float* w_f; const float* w_o;
+    const int* lengths;
+    const float* save;          // [T*B, 5, Cp]
+    uint16_t* dz16;             // [T*B, 4Cp] packed
+    float* dbias; float* dw_i; float* dw_f; float* dw_o;
+};
+
+// dmt_{t-1} = dOut_{t-1} W_p^T + dz_t Wc^T, split along K over the G/2 PAIRS of the cluster: pair p owns the four gates
+// of cells [64p, 64p+64) (256 packed gate columns) for the 32 utterances of the group -- CTA (p, e) computes dz_t of those
+// cells for utterances [16e, 16e+16) (no exchange of the B operand: its 16 rows of the pair's B tile are produced
+// locally), the pair runs ONE tcgen05.mma.cta_group::2 per k-step (M = 256 output cells: 128 per CTA, N = 32, K = 256;
+// Wc slices resident in TMEM) and every CTA reduce-scatters its partial rows, 16-bit, to the CTA that owns (cell block,
+// utterance half).  Per SM and step 16 KB leave for 32 utterances (the single-CTA kernel ships 16 KB per 16), and one
+// CTA issues the MMAs of two.  Warps 0-7: gate backward (thread <-> one cell x 4 utterances) and the sends; warp 8 of the
+// even CTA: MMA issuer.
+template <int BF, int FAST>
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+lstmp_bwd_pair_kernel(const PBwdParams p) {
+    constexpr int NBR = 16;                     // B-operand rows (utterances) per CTA
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = p.Cp / 32, NP = G / 2;        // cluster size, pairs
+    const int MT2 = p.Cp / 256;                 // 256-row output tiles of the pair product: 1 or 2
+    const uint32_t j = cluster_ctarank();
+    const uint32_t e = j & 1u, pr = j >> 1;     // utterance half, pair index
+    const int grp = blockIdx.x / G;
+    const int b0 = grp * NBP + (int)e * NBR;    // first utterance this CTA differentiates
+
+    constexpr uint32_t SLOT = 2048u;                                 // bytes one source pair sends per step: [2][64 cells][8 utt] 16-bit
+    const uint32_t sR_bytes = (uint32_t)NP * SLOT;
+    const uint32_t sBt = base;                                       // dz tile: 4 k-subtiles [16 rows x 64 k] 16-bit, SW128
+    const uint32_t sR0 = sBt + 4u * NBR * 128u;                      // two receive buffers
+    const uint32_t sBar = sR0 + 2u * sR_bytes;
+    const uint32_t barM = sBar, full0 = sBar + 8, full1 = sBar + 16, dzr = sBar + 24;
+    const uint32_t tslot = sBar + 32;
+    uint8_t* sB_ptr = base_ptr + (sBt - base);
+
+    // TMEM: tile mt of the A operand (rows = output cells 256 mt + 128 e + lane, K = the pair's 256 gate columns) at columns
+    //       [128 mt, 128 mt + 128); accumulator of tile mt at columns 128 MT2 + 32 mt
+    const uint32_t a_cols = 128u * (uint32_t)MT2;
+    uint32_t tcols = 32;
+    while (tcols < a_cols + (uint32_t)(MT2 * NBP)) tcols <<= 1;
+    if (tid == GATE_THREADS) {
+        mbar_init(barM, 1); mbar_init(full0, 1); mbar_init(full1, 1); mbar_init(dzr, 2);
+        fence_mbar_init();
+        mbar_expect_tx(full1, sR_bytes);
+        mbar_expect_tx(full0, sR_bytes);
+    }
+    if (warp == 8) tmem_alloc_2cta(tslot, tcols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
+    const uint32_t tmem_acc = tmem + a_cols;
+
+    if (warp < 8) {   // weight slab -> TMEM: thread <-> output row, 64 k (32 columns) per store
+        const int q = warp & 3;
+        for (int it = warp >> 2; it < 4 * MT2; it += 2) {
+            const int mt = it >> 2, kq = it & 3;
+            const uint16_t* wrow = p.wc + (size_t)(256 * mt + 128 * (int)e + 32 * q + lane) * 4 * p.Cp + 256 * pr + 64 * kq;
+            uint32_t r[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(wrow) + c);
+                r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+            }
+            tmem_st32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 * mt + 32 * kq), r);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+
+    const uint32_t lead = mapa_u32(base, j & ~1u) - base;
+
+    if (warp == 8) {
+        if (e == 0 && elect_one_sync()) {
+            const uint32_t idesc = umma_idesc(256, NBP, BF, 0, 0);
+            const uint16_t pair_mask = (uint16_t)(3u << (j & ~1u));
+            for (int step = 0; step + 1 < p.T; ++step) {
+                mbar_wait(dzr, (uint32_t)(step & 1));      // both CTAs' rows of the dz tile are written
+                tc_fence_after();
+                for (int mt = 0; mt < MT2; ++mt) {
+#pragma unroll
+                    for (int kk = 0; kk < 16; ++kk) {
+                        const uint64_t db = umma_desc_sw128(sBt + (uint32_t)(kk >> 2) * (NBR * 128u) + (uint32_t)(kk & 3) * 32u, 16, 1024);
+                        tc_mma_f16_ts_2cta(tmem_acc + (uint32_t)(mt * NBP), tmem + (uint32_t)(128 * mt + 8 * kk), db, idesc, kk ? 1u : 0u);
+                    }
+                }
+                tc_commit_2cta_mc(barM, pair_mask);
+                PTRACE(true, step, 5);
+            }
+        }
+        __syncwarp();
+    } else {
+        // gate-backward ownership: thread <-> (cell 64 pr + cc, utterances 4 uq + u of this CTA's 16); a warp holds 16
+        // cells x 2 utterance quads so that its reads of a received slot are 256 contiguous bytes (no bank conflicts)
+        constexpr int UPT = 4;
+        const int cc = 16 * (warp & 3) + (lane & 15), uq = 2 * (warp >> 2) + (lane >> 4);
+        const int cl = cc & 31;                     // column of this cell inside a 32-wide gate block
+        const int cell = 64 * (int)pr + cc;
+        const float wi = p.w_i[cell], wf = p.w_f[cell], wo = p.w_o[cell];
+        float dcar[UPT];
+        int len[UPT];
+#pragma unroll
+        for (int u = 0; u < UPT; ++u) {
+            dcar[u] = 0.f;
+            const int b = b0 + UPT * uq + u;
+            len[u] = b < p.B ? p.lengths[b] : 0;
+        }
+        float a_dwi = 0.f, a_dwf = 0.f, a_dwo = 0.f, a_db[4] = {0.f, 0.f, 0.f, 0.f};
+        // sends: this thread drains accumulator rows 32 q + lane, columns [16 ch, +16) of every tile; row 256 mt + 128 e + 32 q +
+        // lane is cell 32 (q & 1) + lane of pair 4 mt + 2 e + q / 2; the 16 utterances belong to the CTA of parity ch
+        const int q = warp & 3, ch = warp >> 2;
+        uint32_t rd[2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+            rd[mt] = mt < MT2 ? mapa_u32(base, (uint32_t)(2 * (4 * mt + 2 * (int)e + (q >> 1)) + ch)) - base : 0u;
+        const uint32_t soff = pr * SLOT + (uint32_t)(32 * (q & 1) + lane) * 16u;
+        const size_t Cp = (size_t)p.Cp;
+        // my 4 utterances inside the 16-byte chunk [h][cell][8 utterances] of a source slot
+        const uint32_t roff = (uint32_t)(uq >> 1) * 1024u + (uint32_t)cc * 16u + (uint32_t)(uq & 1) * 8u;
+        // dz tile: row n, pair-local packed gate column 128 (cc / 32) + 32 g + cc % 32 -> k-subtile 2 (cc / 32) + g / 2
+        const uint32_t zoff = (uint32_t)(2 * (cc >> 5)) * (NBR * 128u);
+        uint16_t* dzg = p.dz16 + 256 * pr + 128 * (cc >> 5) + (cc & 31);
+
+        // saved activations / dmt of step t-1 are loaded one step ahead (see lstmp_bwd_cluster_kernel)
+        float s_i[UPT], s_f[UPT], s_o[UPT], s_j[UPT], s_c[UPT], s_cp[UPT], dm[UPT];
+        float n_i[UPT], n_f[UPT], n_o[UPT], n_j[UPT], n_cp[UPT], n_dm[UPT];
+#pragma unroll
+        for (int u = 0; u < UPT; ++u) {
+            const int b = b0 + UPT * uq + u;
+            s_i[u] = s_f[u] = s_o[u] = s_j[u] = s_c[u] = s_cp[u] = dm[u] = 0.f;
+            if (b < p.B) {
+                const size_t row = (size_t)(p.T - 1) * p.B + b;
+                const float* s = p.save + row * 5 * Cp + cell;
+                s_i[u] = __ldg(s); s_f[u] = __ldg(s + Cp); s_o[u] = __ldg(s + 2 * Cp); s_j[u] = __ldg(s + 3 * Cp);
+                s_c[u] = __ldg(s + 4 * Cp);
+                if (p.T > 1) s_cp[u] = __ldg(s - (size_t)p.B * 5 * Cp + 4 * Cp);
+                dm[u] = __ldg(p.dmt + row * Cp + cell);
+            }
+        }
+
+        for (int step = 0; step < p.T; ++step) {
+            const int t = p.T - 1 - step;
+            const int buf = step & 1;
+            PTRACE(tid == 0, step, 0);
+#pragma unroll
+            for (int u = 0; u < UPT; ++u) {            // operands of step t-1 (and c_{t-2}): in flight during this step
+                const int b = b0 + UPT * uq + u;
+                n_i[u] = n_f[u] = n_o[u] = n_j[u] = n_cp[u] = n_dm[u] = 0.f;
+                if (b < p.B && t > 0) {
+                    const size_t row = (size_t)(t - 1) * p.B + b;
+                    const float* s = p.save + row * 5 * Cp + cell;
+                    n_i[u] = __ldg(s); n_f[u] = __ldg(s + Cp); n_o[u] = __ldg(s + 2 * Cp); n_j[u] = __ldg(s + 3 * Cp);
+                    if (t > 1) n_cp[u] = __ldg(s - (size_t)p.B * 5 * Cp + 4 * Cp);
+                    n_dm[u] = __ldg(p.dmt + row * Cp + cell);
+                }
+            }
+            if (step > 0) {
+                const uint32_t fb = buf ? full1 : full0;
+                mbar_wait(fb, (uint32_t)(((step - 1) >> 1) & 1));   // partial rows of dz_{t+1} Wc^T from all NP pairs
+                PTRACE(tid == 0, step, 1);
+                const uint32_t rbase = sR0 + (uint32_t)buf * sR_bytes + roff;
+#pragma unroll
+                for (int s0 = 0; s0 < 8; s0 += 4) {
+                    if (s0 >= NP) break;
+                    uint32_t x[4], y[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x[k]), "=r"(y[k]) : "r"(rbase + (uint32_t)(s0 + k) * SLOT));
+                    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int k = 0; k < 4; k += 2) {
+                        a0[0] += h2f((uint16_t)(x[k] & 0xFFFFu), BF); a0[1] += h2f((uint16_t)(x[k] >> 16), BF);
+                        a0[2] += h2f((uint16_t)(y[k] & 0xFFFFu), BF); a0[3] += h2f((uint16_t)(y[k] >> 16), BF);
+                        a1[0] += h2f((uint16_t)(x[k + 1] & 0xFFFFu), BF); a1[1] += h2f((uint16_t)(x[k + 1] >> 16), BF);
+                        a1[2] += h2f((uint16_t)(y[k + 1] & 0xFFFFu), BF); a1[3] += h2f((uint16_t)(y[k + 1] >> 16), BF);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) dm[u] += a0[u] + a1[u];
+                }
+                __syncwarp();
+                if (tid == 0 && step + 2 < p.T) mbar_expect_tx(fb, sR_bytes);   // re-arm for step + 2
+            }
+            PTRACE(tid == 0, step, 2);
+            uint16_t hz[UPT][4];
+#pragma unroll
+            for (int u = 0; u < UPT; ++u) {
+                const int b = b0 + UPT * uq + u;
+                // branch-free: frozen steps and rows past the batch contribute exact zeros through the mask
+                const float m = ((b < p.B) && (t < len[u])) ? 1.f : 0.f;
+                const float tc = FAST ? tanh_fast(s_c[u]) : tanhf_(s_c[u]);
+                const float dz_o = m * dm[u] * tc * s_o[u] * (1.f - s_o[u]);
+                const float dc = dcar[u] + dm[u] * s_o[u] * (1.f - tc * tc) + dz_o * wo;
+                const float dz_f = m * dc * s_cp[u] * s_f[u] * (1.f - s_f[u]);
+                const float dz_i = m * dc * s_j[u] * s_i[u] * (1.f - s_i[u]);
+                const float dz_j = m * dc * s_i[u] * (1.f - s_j[u] * s_j[u]);
+                dcar[u] = m * (dc * s_f[u] + dz_f * wf + dz_i * wi);
+                a_dwo += dz_o * s_c[u]; a_dwf += dz_f * s_cp[u]; a_dwi += dz_i * s_cp[u];
+                a_db[0] += dz_i; a_db[1] += dz_j; a_db[2] += dz_f; a_db[3] += dz_o;
+                hz[u][0] = f2h(dz_i, BF); hz[u][1] = f2h(dz_j, BF); hz[u][2] = f2h(dz_f, BF); hz[u][3] = f2h(dz_o, BF);
+            }
+            PTRACE(tid == 0, step, 3);
+            if (t > 0) {
+                // B operand of the recurrent product first (it is what the next MMA waits for), the global copy after
+#pragma unroll
+                for (int u = 0; u < UPT; ++u) {
+                    const int n = UPT * uq + u;
+                    *reinterpret_cast<uint16_t*>(sB_ptr + zoff + sw128_off(n, cl)) = hz[u][0];                        // g = 0
+                    *reinterpret_cast<uint16_t*>(sB_ptr + zoff + sw128_off(n, 32 + cl)) = hz[u][1];                   // g = 1
+                    *reinterpret_cast<uint16_t*>(sB_ptr + zoff + NBR * 128 + sw128_off(n, cl)) = hz[u][2];            // g = 2
+                    *reinterpret_cast<uint16_t*>(sB_ptr + zoff + NBR * 128 + sw128_off(n, 32 + cl)) = hz[u][3];       // g = 3
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, GATE_THREADS);
+                if (tid == 0) mbar_arrive_cluster(dzr + lead);
+                PTRACE(tid == 0, step, 4);
+            }
+            // global copy of dz (operand of the weight-gradient GEMMs): off the dependent chain, behind the MMAs
+#pragma unroll
+            for (int u = 0; u < UPT; ++u) {
+                const int b = b0 + UPT * uq + u;
+                if (b < p.B) {
+                    uint16_t* d = dzg + ((size_t)t * p.B + b) * 4 * Cp;
+                    d[0] = hz[u][0]; d[32] = hz[u][1]; d[64] = hz[u][2]; d[96] = hz[u][3];
+                }
+            }
+            if (t == 0) break;                     // no earlier step to feed
+            mbar_wait(barM, (uint32_t)(step & 1));
+            tc_fence_after();
+            PTRACE(tid == 0, step, 6);
+            const uint32_t dst0 = sR0 + (uint32_t)(buf ^ 1) * sR_bytes + soff;
+            const uint32_t dbar = buf ? full0 : full1;
+            uint32_t acc[2][16];                   // both tiles in flight, one wait
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+                if (mt < MT2) tmem_ld16_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NBP + ch * 16), acc[mt]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                if (mt < MT2) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const uint32_t* a = acc[mt] + 8 * c;
+                        st_async_v4(dst0 + (uint32_t)c * 1024u + rd[mt],
+                                    pack2(__uint_as_float(a[0]), __uint_as_float(a[1]), BF),
+                                    pack2(__uint_as_float(a[2]), __uint_as_float(a[3]), BF),
+                                    pack2(__uint_as_float(a[4]), __uint_as_float(a[5]), BF),
+                                    pack2(__uint_as_float(a[6]), __uint_as_float(a[7]), BF), dbar + rd[mt]);
+                    }
+                }
+            }
+            tc_fence_before();
+#pragma unroll
+            for (int u = 0; u < UPT; ++u) {
+                s_c[u] = s_cp[u]; s_cp[u] = n_cp[u];
+                s_i[u] = n_i[u]; s_f[u] = n_f[u]; s_o[u] = n_o[u]; s_j[u] = n_j[u]; dm[u] = n_dm[u];
+            }
+            PTRACE(tid == 0, step, 7);
+        }
+        atomicAdd(p.dw_i + cell, a_dwi); atomicAdd(p.dw_f + cell, a_dwf); atomicAdd(p.dw_o + cell, a_dwo);
+        {
+            float* db = p.dbias + 256 * pr + 128 * (cc >> 5) + (cc & 31);
+            atomicAdd(db, a_db[0]); atomicAdd(db + 32, a_db[1]); atomicAdd(db + 64, a_db[2]); atomicAdd(db + 96, a_db[3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 8) tmem_dealloc_2cta(tmem, tcols);
+}
+
+size_t pbwd_smem(int Cp) {
+    const size_t need = 1024 + 4 * 16 * 128 + 2 * (size_t)(Cp / 64) * 2048 + 64;
+    return need < RSR_EXCLUSIVE_SMEM_REC ? RSR_EXCLUSIVE_SMEM_REC : need;
+}
+
+}  // namespace
+
+int rsr_lstmp_bwd_pair(rsr_handle* h, void* stream, int B, int T, int Cp, const float* dmt, const void* wc,
+                       const float* w_i, const float* w_f, const float* w_o, const int* lengths,
+                       const float* save, void* dz16, float* dbias, float* dw_i, float* dw_f, float* dw_o) {
+    if (Cp > 512) return RSR_E_RESIDENT;
+    const int G = Cp / 32;
+    const size_t smem = pbwd_smem(Cp);
+    int& cap = h->pair_cap[1][Cp / 256 - 1];
+    if (cap < 0) {
         std::lock_guard<std::mutex> g(h->mu);
-        cap = nch == 1 ? cluster_capacity(lstmp_fwd_pair_kernel<1>, G, PAIR_THREADS, smem)
-                       : cluster_capacity(lstmp_fwd_pair_kernel<2>, G, PAIR_THREADS, smem);
-        h->pair_ik[Cp / 256 - 1] = Ik * 4 + nch;
-        if (getenv("RSR_DEBUG")) fprintf(stderr, "[rsr] fused fwd pair kernel Cp=%d Ik=%d: %d-CTA clusters co-resident: %d\n", Cp, Ik, G, cap);
+        cap = cluster_capacity(lstmp_bwd_pair_kernel<0, 0>, G, PAIR_THREADS, smem);
+        if (cap > 0) {   // sets the launch attributes of the other instances
+            cluster_capacity(lstmp_bwd_pair_kernel<1, 0>, G, PAIR_THREADS, smem);
+            cluster_capacity(lstmp_bwd_pair_kernel<0, 1>, G, PAIR_THREADS, smem);
+            cluster_capacity(lstmp_bwd_pair_kernel<1, 1>, G, PAIR_THREADS, smem);
+        }
+        if (getenv("RSR_DEBUG")) fprintf(stderr, "[rsr] bwd pair kernel Cp=%d: %d-CTA clusters co-resident: %d\n", Cp, G, cap);
     }
     if (cap <= 0) return RSR_E_RESIDENT;
     const int groups = (B + NBP - 1) / NBP;
-    CUtensorMap tmX;
-    int rc = rsr_get_tmap(h, x16, (uint64_t)ldx, (uint64_t)T * B, (uint64_t)ldx, 64, (uint32_t)(NBP / nch / 2), &tmX);
-    if (rc) return rc;
-    PFwdParams p;
-    p.B = B; p.T = T; p.Cp = Cp; p.bf = h->dtype == RSR_DTYPE_BF16; p.forget_bias = forget_bias;
-    p.wcT = (const uint16_t*)wcT; p.kxT = (const uint16_t*)kxT; p.bias = bias;
-    p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths;
-    p.mt_seq = (uint16_t*)mt_seq; p.save = save; p.Ik = Ik;
-    if (nch == 1) return cluster_launch(lstmp_fwd_pair_kernel<1>, groups, G, PAIR_THREADS, smem, (cudaStream_t)stream, tmX, p);
-    return cluster_launch(lstmp_fwd_pair_kernel<2>, groups, G, PAIR_THREADS, smem, (cudaStream_t)stream, tmX, p);
+    PBwdParams p;
+    p.wc = (const uint16_t*)wc;
+    p.B = B; p.T = T; p.Cp = Cp; p.bf = h->dtype == RSR_DTYPE_BF16;
+    p.dmt = dmt; p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths; p.save = save;
+    p.dz16 = (uint16_t*)dz16; p.dbias = dbias; p.dw_i = dw_i; p.dw_f = dw_f; p.dw_o = dw_o;
+    static const int fast = getenv("RSR_FAST_GATES") ? (atoi(getenv("RSR_FAST_GATES")) ? 1 : 0) : 1;
+    if (fast) {
+        if (p.bf) return cluster_launch(lstmp_bwd_pair_kernel<1, 1>, groups, G, PAIR_THREADS, smem, (cudaStream_t)stream, p);
+        return cluster_launch(lstmp_bwd_pair_kernel<0, 1>, groups, G, PAIR_THREADS, smem, (cudaStream_t)stream, p);
+    }
+    if (p.bf) return cluster_launch(lstmp_bwd_pair_kernel<1, 0>, groups, G, PAIR_THREADS, smem, (cudaStream_t)stream, p);
+    return cluster_launch(lstmp_bwd_pair_kernel<0, 0>, groups, G, PAIR_THREADS, smem, (cudaStream_t)stream, p);
 }
 
 // debug: copies the phase-timing trace of the pair kernels (all zeros unless built with -DRSR_TRACE) to the host

@@ -485,6 +485,11 @@ extern "C" int rsr_lstmp_rec_bwd(rsr_handle* h, void* stream, int B, int T, int 
         return RSR_E_ARG;
     if (B <= 0 || T <= 0 || Cp <= 0 || (Cp & 255)) return RSR_E_SHAPE;
     if (((uintptr_t)dmt | (uintptr_t)wc | (uintptr_t)save | (uintptr_t)dz16) & 15) return RSR_E_ARG;
+    if (!getenv("RSR_NO_CLUSTER") && !getenv("RSR_NO_PAIR") && B > 16) {   // CTA-pair kernel (32 utterances per cluster)
+        const int rcp = rsr_lstmp_bwd_pair(h, stream, B, T, Cp, dmt, wc, w_i, w_f, w_o, lengths, save, dz16,
+                                           dbias, dw_i, dw_f, dw_o);
+        if (rcp != RSR_E_RESIDENT) return rcp;
+    }
     if (!getenv("RSR_NO_CLUSTER")) {
         const int rcc = rsr_lstmp_bwd_cluster(h, stream, B, T, Cp, dmt, wc, w_i, w_f, w_o, lengths, save, dz16,
                                               dbias, dw_i, dw_f, dw_o);

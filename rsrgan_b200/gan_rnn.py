@@ -177,6 +177,13 @@ class GAN_RNN(Model):
                 d0 = str(devices[0])
                 dev = int(d0.split(":")[-1]) if ":" in d0 else 0
             self.h = handle if handle is not None else ops.Handle(dev, _arg(args, "dtype", "f16"))
+            if _arg(args, "dtype", "f16") == "bf16":
+                # fp16 operands are the product dtype: 8 more mantissa bits keep the generator output within 1e-3 RMS of the
+                # fp32 reference at every benchmarked length; bf16 does not (profiles/r2_parity_measured_v0.jsonl)
+                import warnings
+                warnings.warn("rsrgan_b200: bf16 operands deviate from the fp32 reference by up to 3.5e-3 RMS in the "
+                              "generator output (4 x 1024 res_lstm_l, T = 200) -- outside the 1e-3 parity bar that "
+                              "dtype='f16' (the default) meets", stacklevel=2)
             in_dim = self.input_dim * (self.left_context + 1 + self.right_context)
             # models/dnn.py:64-68: the dnn generator drops out only when it is also regularised (else keep_prob = 1)
             g_keep = self.keep_prob
@@ -216,6 +223,7 @@ class GAN_RNN(Model):
         # RSR_NO_GRAPH=1 or use_graph=False runs every kernel eagerly
         self.use_graph = (_arg(args, "use_graph", True) and os.environ.get("RSR_NO_GRAPH", "0") != "1"
                           and dev.type == "cuda")
+        self.scale_backoff, self._skipped_seen = 0, 0       # fp16 loss-scale back-off (check_overflow)
         self._graphs, self._graphs_gen = {}, None
         self._copy_stream, self._prefetched, self._prefetch_bufs = None, None, {}
         # With several ranks the schedule is captured as one graph SEGMENT per update; the NCCL all-reduce of the
@@ -374,10 +382,34 @@ class GAN_RNN(Model):
         return torch.randn(B, self.output_dim, dtype=F32, device=self.h.device) * self.disc_noise_std
 
     def _gscale(self, rows):
-        """static loss scale keeping 16-bit gradient tensors in range (fp16 operands)"""
+        """Loss scale keeping the 16-bit gradient tensors of the backward pass in range (fp16 operands): the gradients
+        of a mean over `rows` frames are O(1 / rows), so they are multiplied by ~rows / lambda (a power of two) on the
+        way down and divided again inside the update sweep.  `scale_backoff` halves it once per overflow the update
+        kernels reported (check_overflow)."""
         if self.h.dtype_id == ops._lib.RSR_DTYPE_BF16:
             return 1.0
-        return float(2.0 ** round(math.log2(max(rows / max(self.mse_lambda, 1.0), 1.0))))
+        return float(2.0 ** (round(math.log2(max(rows / max(self.mse_lambda, 1.0), 1.0))) - self.scale_backoff))
+
+    def skipped_updates(self):
+        """(G, D) numbers of updates the overflow guard skipped so far (device counters hyper[7]; synchronises)."""
+        return tuple(int(n.P.hyper[7].item()) if n is not None else 0 for n in (self.G, self.D))
+
+    def check_overflow(self):
+        """fp16 overflow handling, host half: when the update kernels skipped an update since the last call (a gradient
+        norm was inf / NaN: include/rsrgan_b200.h, rsr_clip_adam_ema) the loss scale is halved for the following
+        batches -- skip-and-back-off as in mixed-precision training practice; the fp32 reference has no counterpart
+        because it cannot overflow there.  Returns the number of newly skipped updates.  Synchronises; the trainer
+        calls it where it reads the losses anyway."""
+        if self.h.dtype_id == ops._lib.RSR_DTYPE_BF16:
+            return 0
+        now = sum(self.skipped_updates())
+        new = now - self._skipped_seen
+        if new > 0:
+            self._skipped_seen = now
+            self.scale_backoff += 1
+            print("[!] %d update(s) skipped: non-finite 16-bit gradients; loss scale halved (back-off %d)"
+                  % (new, self.scale_backoff))
+        return new
 
     # ------------------------------------------------------------------ updates
     def _mode(self, training, g_update=False, d_update=False):
@@ -410,10 +442,10 @@ class GAN_RNN(Model):
         h.seg_sumsq(P.grad, gmul, P.seg_id, len(P.segs), P.sumsq)
         if adam:
             h.clip_adam_ema(P.grad, gmul, P.seg_id, P.sumsq, float(self.max_grad_norm), P.hyper,
-                            self.MOVING_AVERAGE_DECAY, P.theta, P.m, P.v, P.ema, P.theta16)
+                            self.MOVING_AVERAGE_DECAY, P.theta, P.m, P.v, P.ema, P.theta16, n_seg=len(P.segs))
         else:
             h.clip_sgd_ema(P.grad, gmul, P.seg_id, P.sumsq, float(self.max_grad_norm), P.hyper,
-                           self.MOVING_AVERAGE_DECAY, P.theta, P.ema, P.theta16)
+                           self.MOVING_AVERAGE_DECAY, P.theta, P.ema, P.theta16, n_seg=len(P.segs))
         net.refresh()
 
     def _loss_dict(self, vals, which):
@@ -527,7 +559,7 @@ class GAN_RNN(Model):
     def _graph_key(self, B, T):
         # everything a captured kernel receives BY VALUE; learning rates and Adam powers live on the device
         return (B, T, self.disc_updates, self.gen_updates, self.d_real, self.d_fake, self.mse_lambda,
-                self.disc_noise_std, self.l2_scale, self.world)
+                self.disc_noise_std, self.l2_scale, self.world, self.scale_backoff)
 
     def prefetch(self, inputs, labels, lengths):
         """Starts the host->device copy of the NEXT minibatch on a copy stream, so that it overlaps the batch

@@ -212,12 +212,13 @@ class Handle(object):
         self._call("rsr_seg_sumsq", 1, self.h, _stream(), _p(grad), gmul, _p(seg_id), grad.numel(), n_seg,
                                      _p(sumsq))
 
-    def clip_sgd_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, ema, theta16):
-        self._call("rsr_clip_sgd_ema", 1, self.h, _stream(), _p(grad), gmul, _p(seg_id), _p(sumsq), max_norm,
+    def clip_sgd_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, ema, theta16, n_seg=0):
+        """n_seg > 0: the update is skipped (and hyper[7] counts it) when any of sumsq[0..n_seg) is not finite"""
+        self._call("rsr_clip_sgd_ema", 1, self.h, _stream(), _p(grad), gmul, _p(seg_id), _p(sumsq), int(n_seg), max_norm,
                                         _p(hyper), ema_decay, theta.numel(), _p(theta), _p(ema), _p(theta16))
 
-    def clip_adam_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, m, v, ema, theta16):
-        self._call("rsr_clip_adam_ema", 3, self.h, _stream(), _p(grad), gmul, _p(seg_id), _p(sumsq), max_norm,
+    def clip_adam_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, m, v, ema, theta16, n_seg=0):
+        self._call("rsr_clip_adam_ema", 3, self.h, _stream(), _p(grad), gmul, _p(seg_id), _p(sumsq), int(n_seg), max_norm,
                                          _p(hyper), ema_decay, theta.numel(), _p(theta), _p(m), _p(v), _p(ema),
                                          _p(theta16))
 

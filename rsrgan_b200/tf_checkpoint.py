@@ -350,6 +350,7 @@ def state_to_tensors(sd):
     their names, Adam slots `<var>/Adam`, `<var>/Adam_1`, `beta{1,2}_power`, EMA shadows
     `<var>/ExponentialMovingAverage`, batch_norm statistics, and the six scalar variables."""
     out = OrderedDict()
+    both_adam = all(k in sd and "m" in sd[k] for k in ("G", "D"))
     for key in ("G", "D"):
         if key not in sd:
             continue
@@ -361,9 +362,13 @@ def state_to_tensors(sd):
                 out[n + suffix] = np.asarray(a, np.float32)
         for n, a in net.get("bn_state", {}).items():
             out[n] = np.asarray(a, np.float32)
-        if "m" in net:                                         # the Adam-optimised network owns the beta powers
-            out["model/beta1_power"] = np.float32(net["hyper"][4])
-            out["model/beta2_power"] = np.float32(net["hyper"][5])
+        if "m" in net:
+            # every AdamOptimizer creates its own beta powers when apply_gradients runs: with one Adam network (the
+            # placeholder GAN, G only) they are beta{1,2}_power; with two (models/gan.py:148-151 applies d_opt first, then
+            # g_opt) TensorFlow uniquifies the second pair to beta{1,2}_power_1
+            sfx = "_1" if (both_adam and key == "G") else ""
+            out["model/beta1_power" + sfx] = np.float32(net["hyper"][4])
+            out["model/beta2_power" + sfx] = np.float32(net["hyper"][5])
     for i, k in enumerate(SCALARS):
         if k in sd.get("scalars", {}):
             out["model/Variable" + ("_%d" % i if i else "")] = np.float32(sd["scalars"][k])
@@ -376,6 +381,7 @@ def tensors_to_state(tensors, sd):
     (matched by suffix, so a name-scope prefix TensorFlow may have added does not matter) and left as they are
     otherwise.  Returns the names that were missing."""
     missing = []
+    both_adam = all(k in sd and "m" in sd[k] for k in ("G", "D"))
 
     def find(name):
         if name in tensors:
@@ -408,7 +414,8 @@ def tensors_to_state(tensors, sd):
                 net["bn_state"][n] = np.asarray(a, np.float32).reshape(np.shape(net["bn_state"][n]))
         if "m" in net:
             hyper = np.array(net["hyper"], np.float32)
-            for idx, name in ((4, "beta1_power"), (5, "beta2_power")):
+            sfx = "_1" if (both_adam and key == "G") else ""
+            for idx, name in ((4, "beta1_power" + sfx), (5, "beta2_power" + sfx)):
                 a = find(name)
                 if a is None:
                     missing.append(name)

@@ -42,8 +42,11 @@ def main(argv=None):
         prefix = a.out or a.path[:-3] if a.path.endswith(".pt") else (a.out or a.path + ".tf")
         tensors = T.state_to_tensors(sd)
         T.write_bundle(prefix, tensors)
-        T.write_checkpoint_state(os.path.dirname(os.path.abspath(prefix)), os.path.basename(prefix),
-                                 [os.path.basename(prefix)])
+        # a directory that already has a `checkpoint` index (the trainer's max_to_keep rotation list, in either
+        # container) keeps it: the converted bundle is an extra file, not the new "latest"
+        d = os.path.dirname(os.path.abspath(prefix))
+        if not os.path.exists(os.path.join(d, "checkpoint")):
+            T.write_checkpoint_state(d, os.path.basename(prefix), [os.path.basename(prefix)])
         print("wrote %s.index / .data-00000-of-00001 (%d variables)" % (prefix, len(tensors)))
         return 0
     if a.to == "pt":

@@ -44,7 +44,7 @@ else:
         h.lstmp_rec_fwd(B, T, Cp, zx, wcT, w[0], w[1], w[2], ln, mt, save)
 torch.cuda.synchronize()
 buf = (C.c_ulonglong * (64 * 8))()
-fn = h.lib.rsr_debug_trace_pair if which.startswith("p") else h.lib.rsr_debug_trace
+fn = h.lib.rsr_debug_trace_pair if (which.startswith("p") or (which == "bwd" and B > 16 and not os.environ.get("RSR_NO_PAIR"))) else h.lib.rsr_debug_trace
 fn.argtypes = [C.c_void_p, C.c_int]
 rc = fn(buf, 64 * 8)
 tr = np.array(buf[:], dtype=np.int64).reshape(64, 8)[:T]

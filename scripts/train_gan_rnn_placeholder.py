@@ -108,8 +108,11 @@ def train_one_iteration(model, batches, iteration, tr_num_batch=0):
         if batch_counter % 100 == 0 and d_list and g_list:
             # `if batch % 100 == 0: ... add_summary(_summaries, iteration*tr_num_batch)` (:116-122): batches 0, 100, ...
             model.write_summaries(dict(d_list[-1], **g_list[-1]), iteration * tr_num_batch)
+        if batch_counter % 100 == 99:
+            model.check_overflow()       # fp16 operands: skipped updates -> halve the loss scale (no reference counterpart)
         batch_counter += 1
         cur = nxt
+    model.check_overflow()
     d_counter, g_counter = max(d_counter, 1), max(g_counter, 1)
     return tuple(sums[0:3] / d_counter) + tuple(sums[3:7] / g_counter)
 

@@ -253,16 +253,27 @@ class FakeHandle(object):
         sc = gmul * (max_norm / torch.clamp_min(nrm, max_norm))
         return (grad.reshape(-1, 1024) * sc[:, None]).reshape(-1)
 
-    def clip_sgd_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, ema, theta16):
+    @staticmethod
+    def _skip(sumsq, n_seg, hyper):
+        if n_seg and not bool(torch.isfinite(sumsq[:n_seg]).all()):
+            hyper[7] += 1.0
+            return True
+        return False
+
+    def clip_sgd_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, ema, theta16, n_seg=0):
         self.launches += 1
+        if self._skip(sumsq, n_seg, hyper):
+            return
         theta -= hyper[0] * self._clipped(grad, gmul, seg_id, sumsq, max_norm)
         if ema is not None:
             ema -= (1 - ema_decay) * (ema - theta)
         if theta16 is not None:
             theta16.copy_(theta.to(self.h16))
 
-    def clip_adam_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, m, v, ema, theta16):
+    def clip_adam_ema(self, grad, gmul, seg_id, sumsq, max_norm, hyper, ema_decay, theta, m, v, ema, theta16, n_seg=0):
         self.launches += 1
+        if self._skip(sumsq, n_seg, hyper):
+            return
         g = self._clipped(grad, gmul, seg_id, sumsq, max_norm)
         lr, b1, b2, eps, b1p, b2p = (float(hyper[i]) for i in range(6))
         lr_t = lr * (1 - b2p) ** 0.5 / (1 - b1p)

@@ -1,11 +1,16 @@
 """End-to-end parity of the CUDA GAN step (GAN_RNN over librsrgan_sm100.so) with the oracle and the
 committed golden vectors, plus size-independent properties at BASELINE.json's full batch size.
 
-Tolerances (fp16 tensor-core operands, fp32 accumulate / cell state; north_star bar: generator
-output within 1e-3 RMS of the reference):
-    generator output  : absolute RMS < 1e-3  AND relative RMS < 3e-3
-    losses            : relative 2e-3
-    raw gradients     : relative RMS 5e-2 per tensor (16-bit backprop), weight deltas likewise
+Tolerances (fp16 tensor-core operands -- the PRODUCT dtype --, fp32 accumulate / cell state; north_star bar:
+generator output within 1e-3 RMS of the reference).  The bars below are 2x what scripts/gpu_measure_parity.py measured
+on a B200 (profiles/r2_parity_measured_v0.jsonl), never looser than that:
+    generator output  : absolute RMS < 1e-3 (north_star) at every size incl. the benchmarked T = 100 / T = 200
+                        (measured 5.8e-5 at cfg-2 B = 128 x T = 100, 4.3e-4 at cfg-5 T = 200)
+    losses            : relative 2e-3 (measured 3e-6)
+    raw gradients     : relative RMS per tensor 2e-2 (measured worst tensor 9.7e-3: the first fully_connected of a
+                        network, whose input is the 16-bit rounded feature itself; median 1e-3), weight deltas likewise
+bf16 operands (BASELINE.json configs[4] names bf16) are supported but do NOT meet the 1e-3 bar at cfg-5 (3.5e-3 at
+T = 200; 4.6e-4 at cfg-2): test_cfg5_T200_against_oracle[bf16] records that as an expected failure.
 """
 import os
 from argparse import Namespace
@@ -19,6 +24,7 @@ from oracle import rsr_oracle as O
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+GRAD_BAR = 2e-2            # per-tensor relative RMS of raw gradients / weight deltas, fp16 operands (2x measured)
 
 
 def make_model(g_type, d_type, B, **kw):
@@ -63,11 +69,11 @@ def test_golden_vectors(name, kw):
     m.d_step(z["x"], z["y"], z["lengths"], **nz)
     dg = m.D.P.export_tf("grad")
     for k in dp:
-        assert rms(dg[k] / gs, z["dgrad/" + k])[1] < 5e-2, k
+        assert rms(dg[k] / gs, z["dgrad/" + k])[1] < GRAD_BAR, k
     m.g_step(z["x"], z["y"], z["lengths"], noise_fk=nz.get("noise_fk"))
     gg = m.G.P.export_tf("grad")
     for k in gp:
-        assert rms(gg[k] / gs, z["ggrad/" + k])[1] < 5e-2, k
+        assert rms(gg[k] / gs, z["ggrad/" + k])[1] < GRAD_BAR, k
     # the whole batch schedule with the reference learning rates
     m.load_params(gp, dp)
     m.G.P.m.zero_(); m.G.P.v.zero_(); m.G.P.hyper[4:6] = torch.tensor([0.9, 0.999], device=m.h.device)
@@ -106,7 +112,7 @@ def test_reference_native_sizes_against_oracle(g_type, d_type, B, T):
     assert ours["d_loss"] == pytest.approx(ref_losses[0]["d_loss"], rel=2e-3)
     d1 = m.D.P.export_tf()
     for k in d0:
-        assert rms(d1[k] - d0[k], st.d[k] - d0[k].astype(np.float64))[1] < 5e-2, k
+        assert rms(d1[k] - d0[k], st.d[k] - d0[k].astype(np.float64))[1] < GRAD_BAR, k
     ours = m.g_step(x, y, lengths, noise_fk=n_fk)
     ref_losses, _ = O.g_step(st, [tower], 8e-5)
     assert ours["g_loss"] == pytest.approx(ref_losses[0]["g_loss"], rel=2e-3)
@@ -243,3 +249,131 @@ def test_cfg5_res_lstm_l_1024_against_oracle(dtype, abs_bar, rel_bar):
     ours = m.g_step(x, y, lengths, noise_fk=n_fk)
     ref, grads = O.g_step(st, [tower], 8e-5)
     assert ours["g_loss"] == pytest.approx(ref[0]["g_loss"], rel=2e-3 if dtype == "f16" else 2e-2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# parity at the BENCHMARKED sequence lengths (the float64 oracle on a slice of the utterances: the generator treats
+# utterances independently; one whole update schedule at a batch the oracle finishes in seconds)
+# ---------------------------------------------------------------------------------------------------------------------
+def _oracle_state(m, g_type, d_type):
+    return O.GanState(OrderedDict((k, v.astype(np.float64)) for k, v in m.G.P.export_tf().items()),
+                      OrderedDict((k, v.astype(np.float64)) for k, v in m.D.P.export_tf().items()), g_type, d_type)
+
+
+def _g_slice(g_type, d_type, B, T, idx, dtype, kw):
+    m = make_model(g_type, d_type, B, dtype=dtype, **kw)
+    rng = np.random.default_rng(B + T)
+    x = rng.standard_normal((B, T, 257)).astype(np.float32)
+    lengths = rng.integers(T // 2, T + 1, size=B)
+    lengths[idx[0]] = T
+    g = m.generate(x, lengths).cpu().numpy()
+    gf, _ = O.GENERATORS[g_type]
+    g_ref, _ = gf(_oracle_state(m, g_type, d_type).g, x[idx].astype(np.float64), lengths[idx])
+    return rms(g[idx], g_ref)
+
+
+def _schedule(g_type, d_type, B, T, dtype, kw, grad_bar, out_bar):
+    m = make_model(g_type, d_type, B, dtype=dtype, use_graph=False, **kw)
+    rng = np.random.default_rng(B * T)
+    x, y = rng.standard_normal((B, T, 257)).astype(np.float32), rng.standard_normal((B, T, 40)).astype(np.float32)
+    lengths = rng.integers(T // 2, T + 1, size=B)
+    lengths[0] = T
+    lstm_d = d_type == "lstm"
+    n_rl = (rng.standard_normal((B, 1, 40)) * 0.05).astype(np.float32) if lstm_d else None
+    n_fk = (rng.standard_normal((B, 1, 40)) * 0.05).astype(np.float32) if lstm_d else None
+    f64 = lambda v: None if v is None else v.astype(np.float64)
+    st = _oracle_state(m, g_type, d_type)
+    tower = dict(x=f64(x), y=f64(y), lengths=lengths, noise_rl=f64(n_rl), noise_fk=f64(n_fk))
+    gs = m._gscale(B * T)
+    m.d_learning_rate, m.g_learning_rate = 0.0, 0.0           # raw gradients of one D and one G update
+    ours = m.d_step(x, y, lengths, noise_rl=n_rl, noise_fk=n_fk)
+    L, G, _ = O.tower_losses_and_grads(st, tower["x"], tower["y"], lengths, "d", tower["noise_rl"], tower["noise_fk"])
+    assert ours["d_loss"] == pytest.approx(L["d_loss"], rel=2e-3)
+    mine = m.D.P.export_tf("grad")
+    for k in G:
+        assert rms(mine[k] / gs, G[k])[1] < grad_bar, ("d", k)
+    ours = m.g_step(x, y, lengths, noise_fk=n_fk)
+    L, G, _ = O.tower_losses_and_grads(st, tower["x"], tower["y"], lengths, "g", tower["noise_rl"], tower["noise_fk"])
+    assert ours["g_loss"] == pytest.approx(L["g_loss"], rel=2e-3)
+    mine = m.G.P.export_tf("grad")
+    for k in G:
+        assert rms(mine[k] / gs, G[k])[1] < grad_bar, ("g", k)
+    # the whole schedule (1 D + 2 G updates) with the reference learning rates, then the generator again
+    m.d_learning_rate, m.g_learning_rate = 1e-3, 8e-5
+    m.G.P.m.zero_(); m.G.P.v.zero_(); m.G.P.hyper[4:6] = torch.tensor([0.9, 0.999], device=m.h.device)
+    m.d_step(x, y, lengths, noise_rl=n_rl, noise_fk=n_fk)
+    O.d_step(st, [tower], 1e-3)
+    for _ in range(2):
+        m.g_step(x, y, lengths, noise_fk=n_fk)
+        O.g_step(st, [tower], 8e-5)
+    gf, _ = O.GENERATORS[g_type]
+    g_ref, _ = gf(st.g, tower["x"], lengths)
+    a, r = rms(m.generate(x, lengths).cpu().numpy(), g_ref)
+    assert a < out_bar, (a, r)
+    assert m.skipped_updates() == (0, 0)
+
+
+CFG2 = dict(g_cell=512, g_proj=256, g_layers=2)
+CFG5 = dict(g_cell=1024, g_layers=4)
+
+
+@pytest.mark.parametrize("dtype,out_bar,grad_bar", [("f16", 1.2e-4, 2e-2), ("bf16", 1e-3, 6e-2)])
+def test_cfg2_T100_against_oracle(dtype, out_bar, grad_bar):
+    """BASELINE.json configs[1] at the benchmarked shape (B = 128 x T = 100, ragged lengths): generator output of eight
+    utterances spread over the four utterance groups against the float64 oracle; then one D update, one G update (raw
+    gradients per tensor) and a whole schedule at B = 24 x T = 100.  out_bar: 2x the measured RMS for fp16 (5.8e-5), the
+    north_star bar 1e-3 for bf16 (measured 4.6e-4)."""
+    a, r = _g_slice("lstm", "dnn", 128, 100, [0, 17, 31, 32, 63, 64, 100, 127], dtype, CFG2)
+    assert a < out_bar <= 1e-3, (a, r)
+    _schedule("lstm", "dnn", 24, 100, dtype, CFG2, grad_bar, out_bar)
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+def test_cfg5_T200_against_oracle(dtype):
+    """BASELINE.json configs[4] at its sequence length (res_lstm_l 4 x 1024, T = 200, B = 64 per GPU): generator output
+    of four utterances against the float64 oracle, one D / G update and a whole schedule at B = 4.  fp16 (the product
+    dtype) meets the 1e-3 north_star bar (measured 4.3e-4); bf16, which configs[4] names, does NOT (measured 3.5e-3):
+    that arm checks its own regression bound and then reports the miss as an expected failure."""
+    a, r = _g_slice("res_lstm_l", "lstm", 64, 200, [0, 21, 42, 63], dtype, CFG5)
+    if dtype == "f16":
+        assert a < 9e-4, (a, r)
+        _schedule("res_lstm_l", "lstm", 4, 200, dtype, CFG5, 2e-3, 1e-3)
+        return
+    assert a < 7e-3, (a, r)
+    _schedule("res_lstm_l", "lstm", 4, 200, dtype, CFG5, 1.2e-2, 7e-3)
+    if a >= 1e-3:
+        pytest.xfail("bf16 operands: generator output RMS %.1e at cfg-5 T = 200 is above the 1e-3 parity bar "
+                     "(fp16 is the product dtype; DESIGN.md section 2)" % a)
+
+
+def test_graph_replay_survives_workspace_growth():
+    """A captured schedule holds raw workspace addresses.  A longer batch (train_batch) or a longer cross-validation
+    utterance (eval_losses on the model that shares the workspace) replaces workspace buffers: the graphs captured
+    before must be dropped and re-captured, never replayed on freed memory.  Twin model, eager, same sequence."""
+    from rsrgan_b200.gan_rnn import GAN_RNN
+    kw = dict(g_cell=256, g_proj=64, g_layers=1, init_disc_noise_std=0.0)
+    ma = make_model("lstm", "dnn", 16, **kw)
+    mb = make_model("lstm", "dnn", 16, use_graph=False, **kw)
+    cv = GAN_RNN(None, Namespace(g_type="lstm", d_type="dnn", batch_size=16, init_mse_weight=10.0, dtype="f16"), ["/gpu:0"],
+                 cross_validation=True, share=ma)
+    rng = np.random.default_rng(2)
+
+    def batch(T):
+        return (rng.standard_normal((16, T, 257)).astype(np.float32), rng.standard_normal((16, T, 40)).astype(np.float32),
+                rng.integers(T // 2, T + 1, size=16))
+    b12, b20, b36 = batch(12), batch(20), batch(36)
+    for _ in range(4):                                   # capture at T = 12
+        ma.train_batch(*b12); mb.train_batch(*b12)
+    assert any(st["graph"] is not None for st in ma._graphs.values())
+    gen0 = ma._ws_generation()
+    for _ in range(4):                                   # a longer batch grows the workspace and gets its own graph
+        ma.train_batch(*b20); mb.train_batch(*b20)
+    cv.eval_losses(*b36)                                 # longer still, eager, on the SHARED workspace
+    assert ma._ws_generation() != gen0
+    for b in (b12, b20, b12, b12, b12, b20):             # back to the shapes whose graphs are stale now
+        oa, ob = ma.train_batch(*b), mb.train_batch(*b)
+        for k in ob:
+            assert oa[k] == pytest.approx(ob[k], rel=2e-3, abs=1e-6), k
+    assert any(st["graph"] is not None for st in ma._graphs.values())      # ... and they were captured again
+    for na, nb in ((ma.G, mb.G), (ma.D, mb.D)):
+        assert rms(na.P.theta.cpu().numpy(), nb.P.theta.cpu().numpy())[1] < 1e-4

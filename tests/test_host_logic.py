@@ -225,3 +225,40 @@ def test_dnn_trainer_wiring_matches_golden(name, kw):
     assert ev["g_mse_loss"] == pytest.approx(float(z["loss_after/g_mse_loss"]), rel=5e-3)
     with pytest.raises(AttributeError):
         m.d_step(z["x"], z["y"], None)
+
+
+def test_overflow_guard_skips_the_update_and_backs_the_loss_scale_off():
+    """fp16 loss scale: a non-finite gradient norm makes both update kernels leave weights, slots, shadows and the Adam
+    powers untouched and count the event; GAN_RNN.check_overflow then halves the scale (and re-keys the CUDA graphs)."""
+    from argparse import Namespace
+    from fake_handle import FakeHandle
+    from rsrgan_b200.gan_rnn import GAN_RNN
+    a = Namespace(g_type="lstm", d_type="lstm", batch_size=2, g_cell=40, g_proj=24, g_layers=1, d_cell=32, seed=2,
+                  init_mse_weight=10.0)
+    m = GAN_RNN(None, a, ["/gpu:0"], handle=FakeHandle("f16"))
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal((2, 5, 257)).astype(np.float32), rng.standard_normal((2, 5, 40)).astype(np.float32)
+    ln = np.array([5, 4])
+    m.train_batch(x, y, ln)
+    assert m.skipped_updates() == (0, 0) and m.check_overflow() == 0
+    before = {k: v.clone() for k, v in (("theta", m.G.P.theta), ("m", m.G.P.m), ("v", m.G.P.v), ("ema", m.G.P.ema))}
+    hyper = m.G.P.hyper.clone()
+    gs0, key0 = m._gscale(10), m._graph_key(2, 5)
+    # poison the generator's gradient path: an inf where the backward pass accumulates
+    orig = m.h.seg_sumsq
+
+    def poisoned(grad, gmul, seg_id, n_seg, sumsq):
+        orig(grad, gmul, seg_id, n_seg, sumsq)
+        if grad.data_ptr() == m.G.P.grad.data_ptr():
+            sumsq[1] = float("inf")
+    m.h.seg_sumsq = poisoned
+    m.g_step(x, y, ln)
+    m.h.seg_sumsq = orig
+    for k, v in before.items():
+        assert torch.equal(getattr(m.G.P, k), v), k
+    assert torch.equal(m.G.P.hyper[:6], hyper[:6])
+    assert m.skipped_updates() == (1, 0)
+    assert m.check_overflow() == 1 and m.scale_backoff == 1 and m.check_overflow() == 0
+    assert m._gscale(10) == gs0 / 2 and m._graph_key(2, 5) != key0
+    m.g_step(x, y, ln)                                   # and training goes on
+    assert not torch.equal(m.G.P.theta, before["theta"])

@@ -312,6 +312,35 @@ def test_fused_clip_update_sweep(h):
     assert np.abs(d_theta2.cpu().numpy() - ref).max() < 1e-6
 
 
+def test_update_sweep_overflow_guard(h):
+    """n_seg > 0: a non-finite per-tensor norm (an fp16 overflow somewhere in the backward pass) leaves weights, Adam
+    slots, shadows, the 16-bit copy and the beta powers untouched and counts the skipped update in hyper[7]."""
+    dev = h.device
+    n = 4 * 1024
+    seg = torch.tensor([0, 0, 1, 2], dtype=torch.int32, device=dev)
+    grad = torch.randn(n, device=dev)
+    theta, m, v, ema = (torch.randn(n, device=dev) for _ in range(4))
+    v.abs_()
+    th16 = theta.to(h.h16)
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.9, 0.999, 0.0, 0.0], device=dev)
+    sumsq = torch.zeros(3, device=dev)
+    keep = [t.clone() for t in (theta, m, v, ema, th16, hyper)]
+    grad[2048 + 7] = float("inf")
+    h.seg_sumsq(grad, 1.0, seg, 3, sumsq)
+    h.clip_adam_ema(grad, 1.0, seg, sumsq, 15.0, hyper, 0.9999, theta, m, v, ema, th16, n_seg=3)
+    h.clip_sgd_ema(grad, 1.0, seg, sumsq, 15.0, hyper, 0.9999, theta, ema, th16, n_seg=3)
+    torch.cuda.synchronize()
+    assert not bool(torch.isfinite(sumsq).all())
+    for t, k in zip((theta, m, v, ema, th16), keep):
+        assert torch.equal(t, k)
+    assert torch.equal(hyper[:7], keep[5][:7]) and float(hyper[7]) == 2.0
+    grad[2048 + 7] = 0.5                                 # finite again: the update goes through
+    h.seg_sumsq(grad, 1.0, seg, 3, sumsq)
+    h.clip_adam_ema(grad, 1.0, seg, sumsq, 15.0, hyper, 0.9999, theta, m, v, ema, th16, n_seg=3)
+    torch.cuda.synchronize()
+    assert not torch.equal(theta, keep[0]) and float(hyper[7]) == 2.0 and float(hyper[4]) == pytest.approx(0.81)
+
+
 @pytest.mark.parametrize("N,w,cin,cout", [(5, 13, 1, 12), (64, 11, 12, 16), (37, 9, 16, 20), (256, 7, 24, 32),
                                           (256, 9, 24, 20), (3, 13, 16, 12)])
 def test_conv1d_same_overlapped_view_gemm(h, N, w, cin, cout):

@@ -223,3 +223,32 @@ def test_convert_checkpoint_script_both_directions(tmp_path, capsys):
         for buf in ("theta", "ema", "m", "v", "bn_state"):
             for n in a[key].get(buf, {}):
                 assert np.array_equal(np.asarray(a[key][buf][n]), np.asarray(b[key][buf][n])), (key, buf, n)
+
+
+def test_two_adam_networks_keep_their_own_beta_powers(tmp_path):
+    """Frame-level GAN (models/gan.py:125-126,148-151): Adam for D and for G.  D is applied first, so TensorFlow names
+    its accumulators beta{1,2}_power and G's beta{1,2}_power_1; the two networks take different numbers of steps
+    (disc_updates = 1, gen_updates = 2), so after a save / resume each must get its own bias correction back."""
+    from rsrgan_b200.gan import GAN
+    a = Namespace(batch_size=4, input_dim=24, output_dim=8, left_context=0, right_context=0, g_units=16, g_layers=1,
+                  d_units=16, d_layers=1, batch_norm=False, init_mse_weight=10.0, seed=2, ckpt_format="tf",
+                  disc_updates=1, gen_updates=2)
+    m = GAN(None, a, ["/gpu:0"], handle=FakeHandle("f16"))
+    rng = np.random.default_rng(1)
+    x, y = rng.standard_normal((4, 24)).astype(np.float32), rng.standard_normal((4, 8)).astype(np.float32)
+    m.train_batch(x, y)
+    m.train_batch(x, y)
+    d = str(tmp_path / "exp")
+    m.save(d, 2)
+    names = T.read_bundle(os.path.join(d, "GAN-2"))
+    assert float(names["model/beta1_power"]) == pytest.approx(0.9 ** 3, rel=1e-5)        # D: 2 steps
+    assert float(names["model/beta1_power_1"]) == pytest.approx(0.9 ** 5, rel=1e-5)      # G: 4 steps
+    m2 = GAN(None, Namespace(**dict(vars(a), seed=7)), ["/gpu:0"], handle=FakeHandle("f16"))
+    assert m2.load(d)
+    for net, net2 in ((m.G, m2.G), (m.D, m2.D)):
+        assert np.allclose(net.P.hyper[4:6].numpy(), net2.P.hyper[4:6].numpy())
+    assert float(m2.G.P.hyper[4]) != float(m2.D.P.hyper[4])
+    # a bundle written by the reference's placeholder GAN (one Adam network) still feeds G from beta{1,2}_power
+    sd = model(batch_norm=False, ckpt_format="pt").state_dict()
+    t = T.state_to_tensors(sd)
+    assert "model/beta1_power" in t and "model/beta1_power_1" not in t
