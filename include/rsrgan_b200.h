@@ -97,11 +97,18 @@ int rsr_stage_input(rsr_handle* h, void* stream, const float* x, int ldx, int ti
 int rsr_unstage_output(rsr_handle* h, void* stream, const float* y_tm, int ld, int B, int T, int D,
                        const float* mean, const float* std, float* out_bm);
 /* CMVN on flat (N, D) matrices: out = (x - mean) / std, io_funcs/make_tfrecords.py:84-87;
- * inverse: out = y * std + mean, scripts/train_gan_rnn_placeholder.py:286-287. */
+ * inverse: out = y * std + mean, scripts/train_gan_rnn_placeholder.py:286-287.  x and out 16-byte aligned
+ * (the kernel streams 16-byte vectors of the flat array), D <= 4096. */
 int rsr_cmvn_apply(rsr_handle* h, void* stream, const float* x, const float* mean, const float* std,
                    long long N, int D, float* out);
 int rsr_cmvn_invert(rsr_handle* h, void* stream, const float* y, const float* mean, const float* std,
                     long long N, int D, float* out);
+/* The loader's CMVN on a zero-padded minibatch (B, T, D) fp32 with per-utterance lengths: frames t < lengths[b] become
+ * float((double)x - mean[d]) / std[d]) -- float64 arithmetic on the float64 statistics of train_cmvn.npz, bit-identical
+ * to io_funcs/make_tfrecords.py:84-87 -- and frames past the length are exact zeros, which is what padding AFTER the
+ * normalisation gives (io_funcs/tfrecords_dataset.py:149-152).  out may alias x. */
+int rsr_cmvn_apply_padded(rsr_handle* h, void* stream, const float* x, const int* lengths, const double* mean,
+                          const double* std, int B, int T, int D, float* out);
 
 /* LSTMP (tf.contrib.rnn.LSTMCell(use_peepholes, num_proj, forget_bias=1) under
  * tf.nn.dynamic_rnn(sequence_length)) ------------------------------------------------- */

@@ -45,6 +45,7 @@ SIGNATURES = {
     "rsr_unstage_output": [vp, vp, vp, ci, ci, ci, ci, vp, vp, vp],
     "rsr_cmvn_apply": [vp, vp, vp, vp, vp, cll, ci, vp],
     "rsr_cmvn_invert": [vp, vp, vp, vp, vp, cll, ci, vp],
+    "rsr_cmvn_apply_padded": [vp, vp, vp, vp, vp, vp, ci, ci, ci, vp],
     "rsr_lstmp_rec_fwd": [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, cf, vp, vp, vp],
     "rsr_lstmp_fused_fwd": [vp, vp, ci, ci, ci, ci, vp, ci, vp, vp, vp, vp, vp, vp, cf, vp, vp, vp],
     "rsr_transpose16": [vp, vp, vp, ci, ci, ci, vp, ci],

@@ -62,15 +62,81 @@ __global__ void unstage_output_kernel(const float* __restrict__ y, int ld, int B
     }
 }
 
-// CMVN on (N, D) fp32: mode 0: (x - mean) / std ; mode 1: y * std + mean
-__global__ void cmvn_kernel(const float* __restrict__ x, const float* __restrict__ mean,
-                            const float* __restrict__ std, long long n, int D, int mode, float* __restrict__ out) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int d = (int)(i % D);
-        const float v = x[i];
-        out[i] = mode ? fmaf(v, std[d], mean[d]) : (v - mean[d]) / std[d];
+// CMVN on (N, D) fp32: mode 0: (x - mean) / std ; mode 1: y * std + mean.  An HBM stream: the matrix is read and written
+// as 16-byte vectors of the FLAT array (D = 257 or 40: rows are not 16-byte aligned, the flat array is), the feature
+// index of a vector's first element comes from one division and is carried with a wrap for the other three, and the
+// statistics sit in shared memory.  The tail (n % 4 elements) is handled by the last thread.
+__global__ void __launch_bounds__(256) cmvn_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                   const float* __restrict__ std, long long n, int D, int mode,
+                                                   float* __restrict__ out) {
+    extern __shared__ float cm_sh[];
+    float* s_mean = cm_sh;
+    float* s_std = cm_sh + D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) { s_mean[d] = mean[d]; s_std[d] = std[d]; }
+    __syncthreads();
+    const long long nv = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    float4* ov = reinterpret_cast<float4*>(out);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const float4 v = xv[i];
+        int d = (int)((i << 2) % D);
+        float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            r[k] = mode ? fmaf(r[k], s_std[d], s_mean[d]) : (r[k] - s_mean[d]) / s_std[d];
+            if (++d == D) d = 0;
+        }
+        ov[i] = make_float4(r[0], r[1], r[2], r[3]);
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long long i = nv << 2; i < n; ++i) {
+            const int d = (int)(i % D);
+            out[i] = mode ? fmaf(x[i], s_std[d], s_mean[d]) : (x[i] - s_mean[d]) / s_std[d];
+        }
+}
+
+// The loader's CMVN on a PADDED minibatch (B, T, D) fp32, as the reference applies it per utterance BEFORE padding
+// (io_funcs/make_tfrecords.py:84-87: float64 (x - mean) / stddev, then astype(float32); the zero padding of
+// io_funcs/tfrecords_dataset.py:149-152 comes after, so padded frames are exact zeros of the NORMALISED domain):
+//   out[b, t, d] = t < length[b] ? float((double) x[b, t, d] - mean[d]) / std[d]) : 0
+// float64 arithmetic with the float64 statistics of train_cmvn.npz: bit-identical to the reference's numpy.  Same
+// vector stream as above.
+__global__ void __launch_bounds__(256) cmvn_padded_kernel(const float* __restrict__ x, const int* __restrict__ lengths,
+                                                          const double* __restrict__ mean, const double* __restrict__ std,
+                                                          long long n, int T, int D, float* __restrict__ out) {
+    extern __shared__ double cmd_sh[];
+    double* s_mean = cmd_sh;
+    double* s_std = cmd_sh + D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) { s_mean[d] = mean[d]; s_std[d] = std[d]; }
+    __syncthreads();
+    const long long nv = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    float4* ov = reinterpret_cast<float4*>(out);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const float4 v = xv[i];
+        long long row = (i << 2) / D;                  // b * T + t
+        int d = (int)((i << 2) - row * D);
+        int t = (int)(row % T);
+        int len = lengths[row / T];
+        float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            r[k] = t < len ? (float)(((double)r[k] - s_mean[d]) / s_std[d]) : 0.0f;
+            if (++d == D) {
+                d = 0; ++row;
+                if (++t == T) { t = 0; if (row < n / D) len = lengths[row / T]; }
+            }
+        }
+        ov[i] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long long i = nv << 2; i < n; ++i) {
+            const long long row = i / D;
+            const int d = (int)(i - row * D);
+            out[i] = (int)(row % T) < lengths[row / T] ? (float)(((double)x[i] - s_mean[d]) / s_std[d]) : 0.0f;
+        }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -534,7 +600,20 @@ static int cmvn_launch(rsr_handle* h, void* stream, const float* x, const float*
     if (!h || !x || !mean || !std || !out || N < 0 || D <= 0) return RSR_E_ARG;
     if (N == 0) return 0;
     const long long total = N * D;
-    cmvn_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(x, mean, std, total, D, mode, out);
+    if (D > 4096 || (((uintptr_t)x | (uintptr_t)out) & 15)) return RSR_E_ARG;
+    cmvn_kernel<<<grid_for((total + 3) / 4, 256, h->num_sms), 256, 2 * D * sizeof(float), (cudaStream_t)stream>>>(
+        x, mean, std, total, D, mode, out);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int rsr_cmvn_apply_padded(rsr_handle* h, void* stream, const float* x, const int* lengths, const double* mean,
+                                     const double* std, int B, int T, int D, float* out) {
+    if (!h || !x || !lengths || !mean || !std || !out || B < 0 || T <= 0 || D <= 0 || D > 2048) return RSR_E_ARG;
+    if (((uintptr_t)x | (uintptr_t)out) & 15) return RSR_E_ARG;
+    if (B == 0) return 0;
+    const long long total = (long long)B * T * D;
+    cmvn_padded_kernel<<<grid_for((total + 3) / 4, 256, h->num_sms), 256, 2 * D * sizeof(double), (cudaStream_t)stream>>>(
+        x, lengths, mean, std, total, T, D, out);
     RSR_LAUNCH_CHECK();
     return 0;
 }

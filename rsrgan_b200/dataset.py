@@ -10,7 +10,10 @@ make_tfrecords.py consumes (:62-69):
     <utt_id> <inputs.ark>:<offset>                                (test)
 
 and the loader applies, per utterance, (x - mean) / stddev in float64 -> float32
-(make_tfrecords.py:84-87), frame splicing with edge replication (tfrecords_dataset.py:76-99),
+(make_tfrecords.py:84-87) -- or, with cmvn_on_device=True, leaves the features RAW and the trainer object
+normalises the padded minibatch on the GPU (GAN_RNN.set_cmvn -> rsr_cmvn_apply_padded: the same float64
+arithmetic, bit-identical, padded frames exact zeros) --, frame splicing with edge replication
+(tfrecords_dataset.py:76-99),
 then the batching semantics of get_padded_batch:
 
   * shuffle buffer of 10 000 utterances (:128,151);
@@ -69,7 +72,7 @@ class PaddedBatches(object):
 
     def __init__(self, scp_files, batch_size, input_size, output_size, left_context=0, right_context=0,
                  num_threads=4, num_epochs=1, num_buckets=20, cmvn=None, shuffle=True, infer=False, seed=None,
-                 buffer_size=10000):
+                 buffer_size=10000, cmvn_on_device=False):
         self.items = read_pair_scp(scp_files)
         self.batch_size, self.num_epochs, self.num_buckets = batch_size, num_epochs, num_buckets
         self.left, self.right = left_context, right_context
@@ -78,6 +81,8 @@ class PaddedBatches(object):
         self.cmvn = None if cmvn is None else {k: np.asarray(cmvn[k], np.float64) for k in
                                                ("mean_inputs", "stddev_inputs", "mean_labels", "stddev_labels")
                                                if k in cmvn}
+        if cmvn_on_device:
+            self.cmvn = None              # raw features out; GAN_RNN.set_cmvn(cmvn) normalises the fed batch on the GPU
         self.shuffle, self.infer = shuffle and not infer, infer
         self.buffer_size = buffer_size
         self.rng = random.Random(seed)
@@ -172,18 +177,18 @@ class PaddedBatches(object):
 
 
 def get_padded_batch(filenames, batch_size, input_size, output_size, left_context, right_context,
-                     num_threads=4, num_epochs=1, num_buckets=20, cmvn=None, seed=None):
-    """Same argument list as io_funcs/tfrecords_dataset.py:53-55 (+ cmvn, seed); returns an iterable."""
+                     num_threads=4, num_epochs=1, num_buckets=20, cmvn=None, seed=None, cmvn_on_device=False):
+    """Same argument list as io_funcs/tfrecords_dataset.py:53-55 (+ cmvn, seed, cmvn_on_device); returns an iterable."""
     return PaddedBatches(filenames, batch_size, input_size, output_size, left_context, right_context,
-                         num_threads, num_epochs, num_buckets, cmvn=cmvn, seed=seed)
+                         num_threads, num_epochs, num_buckets, cmvn=cmvn, seed=seed, cmvn_on_device=cmvn_on_device)
 
 
 def get_batch(filenames, batch_size, input_size, output_size, left_context, right_context, num_threads=4,
-              num_epochs=1, infer=False, cmvn=None):
+              num_epochs=1, infer=False, cmvn=None, cmvn_on_device=False):
     """Decode-time reader (io_funcs/tfrecords_dataset.py:183-293 with infer=True): file order, no shuffle,
     no buckets; the trainer uses batch_size=1 (scripts/train_gan_rnn_placeholder.py:214-223)."""
     return PaddedBatches(filenames, batch_size, input_size, output_size, left_context, right_context,
-                         num_threads, num_epochs, 1, cmvn=cmvn, shuffle=False, infer=infer)
+                         num_threads, num_epochs, 1, cmvn=cmvn, shuffle=False, infer=infer, cmvn_on_device=cmvn_on_device)
 
 
 class Prefetcher(object):

@@ -224,6 +224,7 @@ class GAN_RNN(Model):
         self.use_graph = (_arg(args, "use_graph", True) and os.environ.get("RSR_NO_GRAPH", "0") != "1"
                           and dev.type == "cuda")
         self.scale_backoff, self._skipped_seen = 0, 0       # fp16 loss-scale back-off (check_overflow)
+        self._cmvn = None                                   # device CMVN of the fed minibatches (set_cmvn)
         self._graphs, self._graphs_gen = {}, None
         self._copy_stream, self._prefetched, self._prefetch_bufs = None, None, {}
         # With several ranks the schedule is captured as one graph SEGMENT per update; the NCCL all-reduce of the
@@ -351,14 +352,38 @@ class GAN_RNN(Model):
             dev.copy_(pin, non_blocking=True)
         return dev
 
+    def set_cmvn(self, cmvn):
+        """Global CMVN of the loader (io_funcs/make_tfrecords.py:84-87), applied ON THE DEVICE to every fed minibatch
+        instead of per utterance on the host: `cmvn` holds mean_inputs / stddev_inputs / mean_labels / stddev_labels
+        (train_cmvn.npz, io_funcs/convert_cmvn_to_numpy.py:43-47); inputs spliced with left / right context see the
+        statistics tiled per context frame.  The feeds must then be RAW features, zero-padded (dataset.get_padded_batch
+        with cmvn_on_device=True).  None switches it off."""
+        if cmvn is None:
+            self._cmvn = None
+            return
+        dev, ctx = self.h.device, self.left_context + 1 + self.right_context
+        t64 = lambda k, rep: torch.as_tensor(np.tile(np.asarray(cmvn[k], np.float64).reshape(-1), rep), device=dev)
+        self._cmvn = dict(mx=t64("mean_inputs", ctx), sx=t64("stddev_inputs", ctx),
+                          my=t64("mean_labels", 1), sy=t64("stddev_labels", 1))
+
+    def _normalise(self, name, a, ln, mean, std):
+        B, T, D = a.shape
+        out = self.G.ws.get(("feed", name, B), B * T, D, F32).view(B, T, D)
+        self.h.cmvn_apply_padded(a, ln, mean, std, out)
+        return out
+
     def _feed(self, inputs, labels, lengths):
         x = self._to_dev("x", inputs, F32)
         B, T = int(x.shape[0]), int(x.shape[1])
         # lengths are fed as float32 and cast to int32 (gan_rnn_placeholder.py:102-104)
         ln = self._to_dev("len", lengths, torch.int32)
+        if self._cmvn is not None:
+            x = self._normalise("x_cmvn", x, ln, self._cmvn["mx"], self._cmvn["sx"])
         y_tm = None
         if labels is not None:
             y = self._to_dev("y", labels, F32)
+            if self._cmvn is not None:
+                y = self._normalise("y_cmvn", y, ln, self._cmvn["my"], self._cmvn["sy"])
             y_tm = self.G.ws.get(("feed", "y_tm", B), T * B, self.output_dim, F32)
             self.h.stage_input(y, B, T, self.output_dim, out32=y_tm)
         return x, y_tm, ln, B, T

@@ -147,6 +147,11 @@ class Handle(object):
         n, d = x.shape
         self._call("rsr_cmvn_apply", 1, self.h, _stream(), _p(x), _p(mean), _p(std), n, d, _p(out))
 
+    def cmvn_apply_padded(self, x, lengths, mean64, std64, out):
+        """x, out (B, T, D) fp32; lengths (B,) int32; mean64 / std64 (D,) float64 (see include/rsrgan_b200.h)"""
+        B, T, D = x.shape
+        self._call("rsr_cmvn_apply_padded", 1, self.h, _stream(), _p(x), _p(lengths), _p(mean64), _p(std64), B, T, D, _p(out))
+
     def cmvn_invert(self, y, mean, std, out):
         n, d = y.shape
         self._call("rsr_cmvn_invert", 1, self.h, _stream(), _p(y), _p(mean), _p(std), n, d, _p(out))

@@ -166,8 +166,11 @@ def decode():
     if os.path.exists(write_ark_path):
         os.remove(write_ark_path)
     writer = ArkWriter(write_scp_path)
+    dev_cmvn = FLAGS.device_cmvn
+    if dev_cmvn:
+        model.set_cmvn(cmvn)          # (x - mean) / stddev of make_tfrecords.py:84-87 on the GPU, per fed utterance
     batches = list(get_batch(data_list, 1, FLAGS.input_dim, FLAGS.output_dim, FLAGS.left_context,
-                             FLAGS.right_context, FLAGS.num_threads, 1, infer=True, cmvn=cmvn))
+                             FLAGS.right_context, FLAGS.num_threads, 1, infer=True, cmvn=cmvn, cmvn_on_device=dev_cmvn))
     start = datetime.datetime.now()
     mean, std = cmvn["mean_labels"], cmvn["stddev_labels"]
     for i, (ids, inputs, _, lengths) in enumerate(batches):
@@ -232,6 +235,10 @@ def main():
         log("[*] Load SUCCESS")
     else:
         log("[!] Begin a new model.")
+    dev_cmvn = FLAGS.device_cmvn
+    if dev_cmvn:                      # the loader hands out raw features; the fed minibatch is normalised on the GPU
+        tr_model.set_cmvn(cmvn)
+        cv_model.set_cmvn(cmvn)
     g_loss_prev, g_rel_impr, check_interval, windows_g_loss = 10000.0, 1.0, 1, []
     tr_model.g_learning_rate = FLAGS.num_gpu * FLAGS.g_learning_rate       # :458-461
     tr_model.d_learning_rate = FLAGS.num_gpu * FLAGS.d_learning_rate
@@ -240,10 +247,12 @@ def main():
         gB = FLAGS.batch_size * FLAGS.num_gpu                     # :395 batch = batch_size * num_gpu
         tr_batches = Prefetcher(tower_slice(get_padded_batch(tr_files, gB, FLAGS.input_dim, FLAGS.output_dim,
                                                              FLAGS.left_context, FLAGS.right_context,
-                                                             FLAGS.num_threads, 1, cmvn=cmvn, seed=1000 + iteration)))
+                                                             FLAGS.num_threads, 1, cmvn=cmvn, seed=1000 + iteration,
+                                                             cmvn_on_device=dev_cmvn)))
         cv_batches = Prefetcher(tower_slice(get_padded_batch(cv_files, gB, FLAGS.input_dim, FLAGS.output_dim,
                                                              FLAGS.left_context, FLAGS.right_context,
-                                                             FLAGS.num_threads, 1, cmvn=cmvn, seed=7)))
+                                                             FLAGS.num_threads, 1, cmvn=cmvn, seed=7,
+                                                             cmvn_on_device=dev_cmvn)))
         start = datetime.datetime.now()
         tr = train_one_iteration(tr_model, tr_batches, iteration + 1, tr_num_batch)
         cv = eval_one_iteration(cv_model, cv_batches, iteration + 1)
@@ -328,6 +337,8 @@ def build_parser():
     p.add_argument("--d_layers", type=int, default=None)
     p.add_argument("--d_units", type=int, default=None, help="hidden width of discriminator_dnn (:23)")
     p.add_argument("--dtype", type=str, default="f16", help="tensor-core operand type: f16 | bf16")
+    p.add_argument("--device_cmvn", type=str2bool, nargs="?", default="true",
+                   help="apply the global CMVN to the fed minibatch on the GPU (bit-identical to the host loader's)")
     p.add_argument("--seed", type=int, default=1234)
     return p
 

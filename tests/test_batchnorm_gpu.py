@@ -270,11 +270,14 @@ def test_gan_batch_norm_and_dropout(graph):
     xt, yt = x.transpose(1, 0, 2).astype(np.float64), y.transpose(1, 0, 2).astype(np.float64)   # library rows = t*B + b
     st = O.GanState(gp, dp, "dnn", "dnn")
     gbs, dbs = O.init_bn_state(gp), O.init_bn_state(dp)
+    # UPDATE_OPS as models/gan_rnn_placeholder.py:163-175 wires them: the D update assigns the discriminator's statistics
+    # (both passes), the G update the generator's -- the oracle's running statistics follow the same rule
+    g_run, d_run = copy.deepcopy(gbs), copy.deepcopy(dbs)
     if not graph:
         gs = m._gscale(B * T)
         for tick, which in enumerate("dg"):
-            go, do = dict(bn_state=copy.deepcopy(gbs)), dict(bn_state=copy.deepcopy(dbs), keep_prob=0.75, rng=(4, tick))
-            L, G, _ = O.tower_losses_and_grads(st, xt, yt, ln, which, g_opts=go, d_opts=do)
+            go, do = dict(bn_state=g_run), dict(bn_state=d_run, keep_prob=0.75, rng=(4, tick))
+            L, G, _ = O.tower_losses_and_grads(st, xt, yt, ln, which, g_opts=go, d_opts=do, update_ops="own")
             out = (m.d_step if which == "d" else m.g_step)(x, y, ln)
             net, keys = (m.D, ("d_rl_loss", "d_fk_loss")) if which == "d" else (m.G, ("g_adv_loss", "g_mse_loss"))
             for k in keys:
@@ -282,6 +285,9 @@ def test_gan_batch_norm_and_dropout(graph):
             mine = net.P.export_tf("grad")
             for k in G:
                 assert rel(mine[k] / gs, G[k]) < 5e-2, (which, k)
+        for net, ref in ((m.G, g_run), (m.D, d_run)):          # ... and the statistics moved exactly as the oracle's
+            for k, v in net.bn_state_tf().items():
+                assert np.allclose(v, ref[k], rtol=2e-3, atol=2e-5), k
         return
     # three schedules through train_batch: the third replays the captured graph; the dropout stream advances 3 per schedule
     outs = [m.train_batch(x, y, ln) for _ in range(4)]
@@ -291,10 +297,16 @@ def test_gan_batch_norm_and_dropout(graph):
     vals = [o["d_fk_loss"] for o in outs]
     assert all(np.isfinite(v) for v in vals) and len(set(vals)) == len(vals)
     for tick0, o in zip((0, 3, 6, 9), outs):
-        do = dict(bn_state=copy.deepcopy(dbs), keep_prob=0.75, rng=(4, tick0))
-        L, _, _ = O.tower_losses_and_grads(st, xt, yt, ln, "d", g_opts=dict(bn_state=copy.deepcopy(gbs)), d_opts=do)
-        assert o["d_rl_loss"] == pytest.approx(L["d_rl_loss"], rel=3e-3) and \
-            o["d_fk_loss"] == pytest.approx(L["d_fk_loss"], rel=3e-3, abs=1e-5)
+        for k, which in enumerate("dgg"):                      # the schedule: one D update, two G updates
+            do = dict(bn_state=d_run, keep_prob=0.75, rng=(4, tick0 + k))
+            L, _, _ = O.tower_losses_and_grads(st, xt, yt, ln, which, g_opts=dict(bn_state=g_run), d_opts=do,
+                                               update_ops="own")
+            if which == "d":
+                assert o["d_rl_loss"] == pytest.approx(L["d_rl_loss"], rel=3e-3) and \
+                    o["d_fk_loss"] == pytest.approx(L["d_fk_loss"], rel=3e-3, abs=1e-5)
+    for net, ref in ((m.G, g_run), (m.D, d_run)):
+        for k, v in net.bn_state_tf().items():
+            assert np.allclose(v, ref[k], rtol=5e-3, atol=5e-5), k
 
 
 @pytest.mark.parametrize("g_type,kw", [("lstm", dict(g_cell=128, g_proj=64, g_layers=2, batch_norm=True)),

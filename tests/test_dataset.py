@@ -55,3 +55,35 @@ def test_loader_errors_reach_the_consumer(tmp_path):
         f.write(os.path.join(d, "bad.scp") + "\n")
     with pytest.raises(RuntimeError, match="uttX"):
         list(Prefetcher(get_padded_batch(read_list(os.path.join(d, "bad.list")), 4, 257, 40, 0, 0, 2, 1)))
+
+
+def test_device_cmvn_of_the_fed_minibatch_is_bit_identical_to_the_host_loader(tmp_path):
+    """cmvn_on_device=True: the loader hands out RAW zero-padded features and GAN_RNN.set_cmvn normalises the fed batch
+    through rsr_cmvn_apply_padded (float64, masked by the lengths) -- same bits as the host path, which follows
+    io_funcs/make_tfrecords.py:84-87, and padded frames stay exact zeros.  (FakeHandle here; the CUDA kernel is held
+    to the same statement in tests/test_kernels_gpu.py::test_cmvn_kernels.)"""
+    from argparse import Namespace
+    import torch
+    from fake_handle import FakeHandle
+    from rsrgan_b200.gan_rnn import GAN_RNN
+    d = str(tmp_path)
+    _make_data(d, n_utt=12)
+    lst = _all_list(d)
+    cm = {k: v for k, v in np.load(os.path.join(d, "train_cmvn.npz")).items()}
+    host = list(get_padded_batch(read_list(lst), 4, 257, 40, 1, 1, 2, 1, cmvn=cm, seed=3))
+    raw = list(get_padded_batch(read_list(lst), 4, 257, 40, 1, 1, 2, 1, cmvn=cm, seed=3, cmvn_on_device=True))
+    a = Namespace(g_type="lstm", d_type="lstm", batch_size=4, g_cell=40, g_proj=24, g_layers=1, d_cell=32, seed=2,
+                  left_context=1, right_context=1)
+    m = GAN_RNN(None, a, ["/gpu:0"], handle=FakeHandle("f16"))
+    m.set_cmvn(cm)
+    n = 0
+    for (ids_h, xh, yh, lh), (ids_r, xr, yr, lr) in zip(host, raw):
+        assert ids_h == ids_r and not np.array_equal(xh, xr)
+        x, y_tm, ln, B, T = m._feed(xr, yr, lr)
+        assert np.array_equal(x.numpy(), xh)
+        y = y_tm.numpy().reshape(T, B, 40).transpose(1, 0, 2)          # staged time-major
+        assert np.array_equal(y, yh)
+        for b in range(B):
+            assert not x.numpy()[b, int(lh[b]):].any()
+        n += 1
+    assert n >= 2

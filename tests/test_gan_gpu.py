@@ -24,7 +24,11 @@ from oracle import rsr_oracle as O
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-GRAD_BAR = 2e-2            # per-tensor relative RMS of raw gradients / weight deltas, fp16 operands (2x measured)
+GRAD_BAR = 2e-2            # per-tensor relative RMS of raw gradients, fp16 operands (2x measured)
+# weight DELTAS of one SGD step (theta_after - theta_before in fp32): lr * g is ~1e-6 against weights of ~1e-1, so the
+# difference of two fp32 weights carries their storage rounding (6e-9 / 1e-6 = a per cent or two) on top of the
+# gradient error: measured up to 3.7e-2
+DELTA_BAR = 6e-2
 
 
 def make_model(g_type, d_type, B, **kw):
@@ -112,7 +116,7 @@ def test_reference_native_sizes_against_oracle(g_type, d_type, B, T):
     assert ours["d_loss"] == pytest.approx(ref_losses[0]["d_loss"], rel=2e-3)
     d1 = m.D.P.export_tf()
     for k in d0:
-        assert rms(d1[k] - d0[k], st.d[k] - d0[k].astype(np.float64))[1] < GRAD_BAR, k
+        assert rms(d1[k] - d0[k], st.d[k] - d0[k].astype(np.float64))[1] < DELTA_BAR, k
     ours = m.g_step(x, y, lengths, noise_fk=n_fk)
     ref_losses, _ = O.g_step(st, [tower], 8e-5)
     assert ours["g_loss"] == pytest.approx(ref_losses[0]["g_loss"], rel=2e-3)

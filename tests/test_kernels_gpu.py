@@ -312,6 +312,36 @@ def test_fused_clip_update_sweep(h):
     assert np.abs(d_theta2.cpu().numpy() - ref).max() < 1e-6
 
 
+@pytest.mark.parametrize("B,T,D", [(3, 7, 257), (5, 11, 40), (2, 9, 771)])
+def test_cmvn_kernels(h, B, T, D):
+    """rsr_cmvn_apply / _invert (fp32 vector stream over the flat matrix; D = 257 rows are not 16-byte aligned, totals not
+    a multiple of 4) against numpy, and rsr_cmvn_apply_padded bit for bit against the loader's float64 statement of
+    io_funcs/make_tfrecords.py:84-87 with zero padding after the normalisation (tfrecords_dataset.py:149-152)."""
+    dev, rng = h.device, np.random.default_rng(B * T + D)
+    x = (rng.standard_normal((B, T, D)) * 3 + 1).astype(np.float32)
+    mean, std = rng.standard_normal(D), rng.uniform(0.5, 2.0, D)
+    xd = torch.tensor(x.reshape(B * T, D), device=dev)
+    out = torch.empty_like(xd)
+    m32, s32 = torch.tensor(mean.astype(np.float32), device=dev), torch.tensor(std.astype(np.float32), device=dev)
+    h.cmvn_apply(xd, m32, s32, out)
+    ref = (x.reshape(B * T, D) - mean.astype(np.float32)) / std.astype(np.float32)
+    assert np.allclose(out.cpu().numpy(), ref, rtol=2e-6, atol=1e-6)
+    back = torch.empty_like(xd)
+    h.cmvn_invert(out, m32, s32, back)
+    assert np.allclose(back.cpu().numpy(), x.reshape(B * T, D), rtol=1e-5, atol=1e-5)
+    lengths = rng.integers(1, T + 1, size=B).astype(np.int32)
+    lengths[0] = T
+    x3 = torch.tensor(x, device=dev)
+    o3 = torch.empty_like(x3)
+    h.cmvn_apply_padded(x3, torch.tensor(lengths, device=dev), torch.tensor(mean, device=dev), torch.tensor(std, device=dev), o3)
+    want = ((x.astype(np.float64) - mean) / std).astype(np.float32)
+    for b in range(B):
+        want[b, lengths[b]:] = 0.0
+    assert np.array_equal(o3.cpu().numpy(), want)
+    h.cmvn_apply_padded(x3, torch.tensor(lengths, device=dev), torch.tensor(mean, device=dev), torch.tensor(std, device=dev), x3)
+    assert np.array_equal(x3.cpu().numpy(), want)                  # in place
+
+
 def test_update_sweep_overflow_guard(h):
     """n_seg > 0: a non-finite per-tensor norm (an fp16 overflow somewhere in the backward pass) leaves weights, Adam
     slots, shadows, the 16-bit copy and the beta powers untouched and counts the skipped update in hyper[7]."""
