@@ -245,6 +245,34 @@ int rsr_conv_mask_rows(rsr_handle* h, void* stream, void* buf16, long long frame
 /* out[k][co][ci] = w[W-1-k][ci][co]: taps of the transposed convolution (tf.gradients of conv2d wrt its input). */
 int rsr_conv_w_flip(rsr_handle* h, void* stream, const void* w16, int W, int Cin_p, int Cout_p, void* out16);
 
+/* Strided members of the family (utils/ops.py:78-98 `downconv`: conv2d, strides [1, 2, 1, 1], SAME, kwidth 31;
+ * utils/ops.py:277-310 `deconv`: conv2d_transpose with the same geometry; consumer models/discriminator.py:38-90).
+ * Same channels-last sequence layout, sequence pitch S even, pl = SAME pad before (oracle/rsr_oracle.py same_pad):
+ *   downconv forward   Y[o] = sum_k X[2o + k - pl] W[k]: rsr_gemm over the view A[m, k*Cp + c] = x[2m - pl + k, c]
+ *                      (pointer x - pl*Cp, lda = 2*Cp, K = kwidth*Cp): TMA reads every second window
+ *   weight gradient    dW += A(X)^T dY  (a_mn = 1) over the same view
+ *   data gradient      dX[2u + r] = sum_j dY[u + e - j] W[2j + c]^T, one rsr_gemm per output parity r over a stride-1
+ *                      window of dY with the taps of that phase (rsr_conv_w_phase), rows written with ldc = 2*Cp
+ *   deconv             forward = that two-phase product, its gradients = the strided-window products.
+ * rsr_conv_w_phase: out[q][b][a] = w[step*(nj-1-q) + phase][a][b] for the nj taps of index = phase mod step
+ * (w16 [W, Ap, Bp] -> out16 [nj, Bp, Ap]). */
+int rsr_conv_w_phase(rsr_handle* h, void* stream, const void* w16, int W, int Ap, int Bp, int step, int phase,
+                     void* out16);
+
+/* Virtual batch normalisation (utils/bnorm.py:11-69) on an fp32 pre-activation z [rows, N] (rows = batch x time):
+ *   mean = w mean_B + (1-w) mean_ref, mean_sq likewise, std = sqrt(eps + mean_sq - mean^2), y = (z-mean)/std*gamma+beta
+ * rsr_vbn_stats fills coef [8, N] like rsr_bn_train_stats (rows 0-3: A, B, mean, 1/std; then apply with
+ * rsr_affine_act_drop).  ref_stats NULL (batch_weight 1) = the reference pass (:31-35); stats_out [2, N] (optional)
+ * receives (mean_B, mean_sq_B), the reference statistics of later live passes (batch_weight = 1 / (batch + 1), :42-47).
+ * rsr_vbn_bwd = rsr_bn_bwd through those statistics, the batch counted with batch_weight:
+ *   dz = A (g - w mean(g) - w x_hat mean(g x_hat)), dgamma += sum g x_hat, dbeta += sum g,  g = da act'(y). */
+int rsr_vbn_stats(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N, const float* gamma,
+                  const float* beta, float eps, float batch_weight, const float* ref_stats, float* stats_out,
+                  float* coef, float* scratch);
+int rsr_vbn_bwd(rsr_handle* h, void* stream, const void* da16, int ldda, const float* z, int ldz, long long rows, int N,
+                int act, float batch_weight, float* coef, float* dgamma, float* dbeta, void* dz16, int lddz,
+                float* dz32, int lddz32, float* scratch);
+
 /* batch_norm(renorm) / dropout behind a fully_connected ----------------------------------- */
 /* tf.contrib.layers.fully_connected(..., normalizer_fn=batch_norm, normalizer_params={is_training, scale=True,
  * renorm=True}) followed by tf.nn.dropout -- models/dnn.py:56-62,79-94, models/discriminator_dnn.py:36-46,61-83,

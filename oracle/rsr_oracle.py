@@ -285,6 +285,104 @@ def conv1d_same_bwd(dy, cache):
     return dxp[:, w // 2:w // 2 + L], dW, du.sum((0, 1))
 
 
+# --------------------------------------------------------------------------
+# the 1-D convolution family of utils/ops.py (strided downconv, transposed deconv) and virtual batch norm
+# (utils/bnorm.py): consumers models/discriminator.py:38-90 (SEGAN-style waveform discriminator)
+# --------------------------------------------------------------------------
+def same_pad(L, k, stride):
+    """TensorFlow SAME padding along one axis: (output length, pad before, pad after)."""
+    out = -(-L // stride)
+    total = max((out - 1) * stride + k - L, 0)
+    return out, total // 2, total - total // 2
+
+
+def downconv_fwd(x, W, b=None, pool=2):
+    """utils/ops.py:78-98 `downconv`: tf.nn.conv2d(x[:, :, None, :], W[k, 1, C_in, C_out], strides=[1, pool, 1, 1],
+    padding='SAME') (+ bias_add), reshaped back to (B, ceil(L / pool), C_out).  x (B, L, C_in); W (k, C_in, C_out)
+    (the singleton filter axis dropped)."""
+    B, L, _ = x.shape
+    k = W.shape[0]
+    out, pl, pr = same_pad(L, k, pool)
+    xp = np.pad(x, ((0, 0), (pl, pr), (0, 0)))
+    cols = np.stack([xp[:, j:j + pool * out:pool] for j in range(k)], 2)           # (B, out, k, C_in)
+    y = np.einsum("bokc,kcd->bod", cols, W)
+    if b is not None:
+        y = y + b
+    return y, (cols, W, x.shape, pool, pl, b is not None)
+
+
+def downconv_bwd(dy, cache):
+    cols, W, xshape, pool, pl, has_b = cache
+    B, L, C = xshape
+    k, out = W.shape[0], dy.shape[1]
+    dW = np.einsum("bokc,bod->kcd", cols, dy)
+    dcols = np.einsum("bod,kcd->bokc", dy, W)
+    dxp = np.zeros((B, max((out - 1) * pool + k, L + pl), C), dy.dtype)
+    for j in range(k):
+        dxp[:, j:j + pool * out:pool] += dcols[:, :, j]
+    return dxp[:, pl:pl + L], dW, (dy.sum((0, 1)) if has_b else None)
+
+
+def deconv_fwd(x, W, b=None, dilation=2):
+    """utils/ops.py:277-310 `deconv`: tf.nn.conv2d_transpose(x[:, :, None, :], W[k, 1, C_out, C_in], output_shape =
+    (B, dilation * L, 1, C_out), strides=[1, dilation, 1, 1]) (padding defaults to SAME) (+ bias): the gradient of the
+    SAME strided convolution C_out -> C_in with that filter.  x (B, L, C_in); W (k, C_out, C_in) -> (B, dilation*L, C_out)."""
+    B, L, _ = x.shape
+    k = W.shape[0]
+    Lo = dilation * L
+    _, pl, _ = same_pad(Lo, k, dilation)
+    yp = np.zeros((B, (L - 1) * dilation + k, W.shape[1]), x.dtype)
+    contrib = np.einsum("boi,kci->bokc", x, W)                                     # (B, L, k, C_out)
+    for j in range(k):
+        yp[:, j:j + dilation * L:dilation] += contrib[:, :, j]
+    y = yp[:, pl:pl + Lo]
+    if y.shape[1] < Lo:                                                            # k < dilation never happens here
+        y = np.pad(y, ((0, 0), (0, Lo - y.shape[1]), (0, 0)))
+    if b is not None:
+        y = y + b
+    return y, (x, W, dilation, pl, b is not None)
+
+
+def deconv_bwd(dy, cache):
+    x, W, dilation, pl, has_b = cache
+    B, L, _ = x.shape
+    k = W.shape[0]
+    dyp = np.zeros((B, (L - 1) * dilation + k + pl, dy.shape[2]), dy.dtype)
+    dyp[:, pl:pl + dy.shape[1]] = dy
+    cols = np.stack([dyp[:, j:j + dilation * L:dilation] for j in range(k)], 2)    # (B, L, k, C_out)
+    dx = np.einsum("bokc,kci->boi", cols, W)
+    dW = np.einsum("bokc,boi->kci", cols, x)
+    return dx, dW, (dy.sum((0, 1)) if has_b else None)
+
+
+def vbn_reference(x_ref, eps=1e-5):
+    """utils/bnorm.py:17-37: statistics of the reference batch, (mean, mean of squares) per channel over (batch, time)."""
+    return x_ref.mean((0, 1)), (x_ref ** 2).mean((0, 1)), x_ref.shape[0]
+
+
+def vbn_fwd(x, gamma, beta, ref=None, eps=1e-5):
+    """utils/bnorm.py:39-69.  ref None: the reference pass itself (statistics of x, :31-35); else ref = (mean, mean_sq,
+    batch_size) of the reference batch and the live statistics are blended with weight 1 / (batch_size + 1) (:42-49)."""
+    m_b, q_b = x.mean((0, 1)), (x ** 2).mean((0, 1))
+    if ref is None:
+        a, m, q = 1.0, m_b, q_b
+    else:
+        a = 1.0 / (ref[2] + 1.0)
+        m, q = a * m_b + (1.0 - a) * ref[0], a * q_b + (1.0 - a) * ref[1]
+    std = np.sqrt(eps + q - m ** 2)
+    xhat = (x - m) / std
+    return xhat * gamma + beta, (xhat, std, gamma, a)
+
+
+def vbn_bwd(dy, cache):
+    """d/dx through the batch statistics (weight a of the live batch), d/dgamma, d/dbeta."""
+    xhat, std, gamma, a = cache
+    n = dy.shape[0] * dy.shape[1]
+    s1, s2 = dy.sum((0, 1)), (dy * xhat).sum((0, 1))
+    dx = (gamma / std) * (dy - a * s1 / n - a * xhat * (s2 / n))
+    return dx, s2, s1
+
+
 def conv2d_same_fwd(x, W, b, act=ACT_RELU):
     """tf.contrib.layers.conv2d(inputs, C_out, [splice, w], padding=SAME, relu) for ANY splice (models/rced.py:90-101):
     x NHWC (N, H, L, C_in), W (kh, kw, C_in, C_out), stride 1, odd kh and kw (SAME pads kh//2 / kw//2 zeros per side).

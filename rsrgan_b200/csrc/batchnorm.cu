@@ -322,6 +322,35 @@ __global__ void bn_finish_train_kernel(const float* __restrict__ partial, int sp
     }
 }
 
+// Virtual batch normalisation (utils/bnorm.py:11-69): statistics are the per-channel mean and mean of squares over
+// (batch, time).  Reference pass (ref NULL, weight 1): the batch's own; live pass: blended with the reference batch's,
+//   mean = w mean_B + (1 - w) mean_ref,  mean_sq = w msq_B + (1 - w) msq_ref,  w = 1 / (reference batch size + 1)
+//   std = sqrt(eps + mean_sq - mean^2),  y = (x - mean) / std * gamma + beta
+// coef rows as for batch_norm: A = gamma / std, B = beta - mean A, mean, 1 / std, r = 1, d = 0.  stats_out (optional)
+// receives (mean_B, msq_B) -- what a reference pass hands to the live passes.
+__global__ void vbn_finish_kernel(const float* __restrict__ partial, int splits, long long rows, int N,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float w,
+                                  const float* __restrict__ ref, float* __restrict__ stats_out, float* __restrict__ coef) {
+    const int c = blockIdx.x * FIN_COLS + threadIdx.x;
+    float na, ma, qa;
+    if (!merge_moments(partial, splits, N, c, na, ma, qa)) return;
+    const float mean_b = ma, msq_b = qa / (float)rows + ma * ma;
+    float mean = mean_b, msq = msq_b;
+    if (ref) {
+        mean = w * mean_b + (1.0f - w) * ref[c];
+        msq = w * msq_b + (1.0f - w) * ref[(long long)N + c];
+    }
+    const float stddev = sqrtf(eps + msq - mean * mean);
+    const float A = gamma[c] / stddev;
+    coef[0 * (long long)N + c] = A;
+    coef[1 * (long long)N + c] = beta[c] - mean * A;
+    coef[2 * (long long)N + c] = mean;
+    coef[3 * (long long)N + c] = 1.0f / stddev;
+    coef[4 * (long long)N + c] = 1.0f;
+    coef[5 * (long long)N + c] = 0.0f;
+    if (stats_out) { stats_out[c] = mean_b; stats_out[(long long)N + c] = msq_b; }
+}
+
 __global__ void bn_eval_coef_kernel(int N, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                     const float* __restrict__ state, float* __restrict__ coef) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,8 +407,11 @@ __global__ void __launch_bounds__(256) affine_act_drop_kernel(const float* __res
 }
 
 // column totals of the backward partials; parameter gradients; means for the dz kernel
+// stat_w: weight of THIS batch in the statistics the normalisation differentiates through (1 for batch_norm; the live
+// pass of virtual batch norm blends the batch with a fixed reference: utils/bnorm.py:42-47)
 __global__ void bn_bwd_finish_kernel(const float* __restrict__ partial, int splits, long long rows, int N, int bn,
-                                     float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                     float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     float stat_w) {
     const int c = blockIdx.x * FIN_COLS + threadIdx.x;
     float s1, s2;
     if (!merge_sums(partial, splits, N, c, s1, s2)) return;
@@ -387,8 +419,8 @@ __global__ void bn_bwd_finish_kernel(const float* __restrict__ partial, int spli
         // y = (x_hat r + d) gamma + beta with r, d under stop_gradient
         // atomics: the D(labels) and D(G(x)) backward passes of one update run on two streams (two addends: order-free)
         if (dgamma) atomicAdd(dgamma + c, coef[4 * (long long)N + c] * s2 + coef[5 * (long long)N + c] * s1);
-        coef[6 * (long long)N + c] = s1 / (float)rows;
-        coef[7 * (long long)N + c] = s2 / (float)rows;
+        coef[6 * (long long)N + c] = stat_w * s1 / (float)rows;
+        coef[7 * (long long)N + c] = stat_w * s2 / (float)rows;
     }
     if (dbeta) atomicAdd(dbeta + c, s1);
 }
@@ -510,10 +542,10 @@ extern "C" int rsr_affine_act_drop(rsr_handle* h, void* stream, const float* z, 
     return 0;
 }
 
-extern "C" int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldda, const float* z, int ldz,
-                          long long rows, int N, int act, float keep_prob, const unsigned long long* rng, unsigned salt,
-                          int bn, float* coef, const float* bias, float* dgamma, float* dbeta, void* dz16, int lddz,
-                          float* dz32, int lddz32, float* scratch) {
+static int bn_bwd_impl(rsr_handle* h, void* stream, const void* da16, int ldda, const float* z, int ldz,
+                       long long rows, int N, int act, float keep_prob, const unsigned long long* rng, unsigned salt,
+                       int bn, float* coef, const float* bias, float* dgamma, float* dbeta, void* dz16, int lddz,
+                       float* dz32, int lddz32, float* scratch, float stat_w) {
     if (!h || !da16 || !z || !scratch || rows <= 0 || N <= 0) return RSR_E_ARG;
     if (bn ? !coef : !bias) return RSR_E_ARG;
     if ((N & 3) || (ldz & 3) || (ldda & 3) || (dz16 && (lddz & 3)) || (dz32 && (lddz32 & 3))) return RSR_E_SHAPE;
@@ -531,7 +563,7 @@ extern "C" int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldd
     if (bn || dbeta) {
         launch_partial<1>(bn_tx(N), splits, st, z, ldz, rows, N, p, scratch);
         RSR_LAUNCH_CHECK();
-        bn_bwd_finish_kernel<<<(N + FIN_COLS - 1) / FIN_COLS, dim3(FIN_COLS, FIN_LANES), 0, st>>>(scratch, splits, rows, N, bn, coef, dgamma, dbeta);
+        bn_bwd_finish_kernel<<<(N + FIN_COLS - 1) / FIN_COLS, dim3(FIN_COLS, FIN_LANES), 0, st>>>(scratch, splits, rows, N, bn, coef, dgamma, dbeta, stat_w);
         RSR_LAUNCH_CHECK();
     }
     if (dz16 || dz32) {
@@ -546,6 +578,37 @@ extern "C" int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldd
         RSR_LAUNCH_CHECK();
     }
     return 0;
+}
+
+extern "C" int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldda, const float* z, int ldz,
+                          long long rows, int N, int act, float keep_prob, const unsigned long long* rng, unsigned salt,
+                          int bn, float* coef, const float* bias, float* dgamma, float* dbeta, void* dz16, int lddz,
+                          float* dz32, int lddz32, float* scratch) {
+    return bn_bwd_impl(h, stream, da16, ldda, z, ldz, rows, N, act, keep_prob, rng, salt, bn, coef, bias, dgamma, dbeta, dz16,
+                       lddz, dz32, lddz32, scratch, 1.0f);
+}
+
+extern "C" int rsr_vbn_stats(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,
+                             const float* gamma, const float* beta, float eps, float batch_weight, const float* ref_stats,
+                             float* stats_out, float* coef, float* scratch) {
+    if (!h || !z || !gamma || !beta || !coef || !scratch || rows <= 0 || N <= 0) return RSR_E_ARG;
+    if ((N & 3) || (ldz & 3)) return RSR_E_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int splits = bn_splits(rows, N, h->num_sms);
+    BnBwdIn none = {};
+    launch_partial<0>(bn_tx(N), splits, st, z, ldz, rows, N, none, scratch);
+    RSR_LAUNCH_CHECK();
+    vbn_finish_kernel<<<(N + FIN_COLS - 1) / FIN_COLS, dim3(FIN_COLS, FIN_LANES), 0, st>>>(scratch, splits, rows, N, gamma, beta, eps,
+                                                                                         batch_weight, ref_stats, stats_out, coef);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_vbn_bwd(rsr_handle* h, void* stream, const void* da16, int ldda, const float* z, int ldz,
+                           long long rows, int N, int act, float batch_weight, float* coef, float* dgamma, float* dbeta,
+                           void* dz16, int lddz, float* dz32, int lddz32, float* scratch) {
+    return bn_bwd_impl(h, stream, da16, ldda, z, ldz, rows, N, act, 1.0f, nullptr, 0u, 1, coef, nullptr, dgamma, dbeta, dz16,
+                       lddz, dz32, lddz32, scratch, batch_weight);
 }
 
 extern "C" int rsr_rng_tick(rsr_handle* h, void* stream, unsigned long long* rng) {

@@ -195,6 +195,21 @@ __global__ void __launch_bounds__(256) lsgan_mse_kernel(const LossParams p) {
         // g_mse = 0.5 * D * mean((g-y)^2)  ->  d/dg = lambda * 0.5 * D * 2 (g-y) / (n_frames*D) = lambda (g-y)/n_frames
         const long long total = p.n_frames * p.D;
         const float cg = p.gscale * p.lambda / (float)p.n_frames;
+        const bool flat = p.ldg == p.D && p.ldy == p.D && (!p.dg_mse || p.lddg == p.D) && (total & 3) == 0 &&
+                          (((uintptr_t)p.g | (uintptr_t)p.y | (uintptr_t)p.dg_mse) & 15) == 0;
+        if (flat) {
+            // dense rows (the generator output is stored at its own width): one 16-byte vector stream over g, y and dg,
+            // no index arithmetic per element
+            const float4* gv = reinterpret_cast<const float4*>(p.g);
+            const float4* yv = reinterpret_cast<const float4*>(p.y);
+            float4* dv = reinterpret_cast<float4*>(p.dg_mse);
+            for (long long i = tid; i < (total >> 2); i += nth) {
+                const float4 a = gv[i], b = yv[i];
+                const float e0 = a.x - b.x, e1 = a.y - b.y, e2 = a.z - b.z, e3 = a.w - b.w;
+                s_mse += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+                if (dv) dv[i] = make_float4(cg * e0, cg * e1, cg * e2, cg * e3);
+            }
+        } else
         for (long long i = tid; i < total; i += nth) {
             const int d = (int)(i % p.D);
             const long long r = i / p.D;
@@ -501,6 +516,19 @@ __global__ void conv_w_flip_kernel(const uint16_t* __restrict__ w, int W, int Ci
     }
 }
 
+// Taps of one PHASE of a stride-`step` transposed convolution (data gradient of utils/ops.py `downconv`, forward of
+// `deconv`): out[q][b][a] = w[step * (nj - 1 - q) + c][a][b]   (w: [W, Ap, Bp], out: [nj, Bp, Ap]; taps with
+// index = c mod step, in reverse order, channel axes transposed).  step = 1, c = 0, nj = W is conv_w_flip.
+__global__ void conv_w_phase_kernel(const uint16_t* __restrict__ w, int Ap, int Bp, int step, int c, int nj,
+                                    uint16_t* __restrict__ out) {
+    const int total = nj * Ap * Bp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int a = i % Ap;
+        const int b = (i / Ap) % Bp;
+        const int q = i / (Ap * Bp);
+        out[i] = w[((step * (nj - 1 - q) + c) * Ap + a) * Bp + b];
+    }
+}
 
 // ---------------------------------------------------------------------------------------
 // fully_connected with ONE output unit (the discriminator heads, models/discriminator_dnn.py:90-92,
@@ -518,20 +546,32 @@ __global__ void __launch_bounds__(256) fc1_fwd_kernel(const uint16_t* __restrict
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const float b0 = bias ? bias[0] : 0.f;
-    for (long long r = warp0; r < rows; r += nwarps) {
-        const uint16_t* xr = x + r * ldx;
-        float acc = 0.f;
+    // two rows per warp and iteration: twice the loads in flight (a 1024-wide row is only four 16-byte loads per lane)
+    for (long long r = warp0; r < rows; r += 2 * nwarps) {
+        const long long r2 = r + nwarps;
+        const bool two = r2 < rows;
+        const uint16_t* xa = x + r * ldx;
+        const uint16_t* xb = x + (two ? r2 : r) * ldx;
+        float acc = 0.f, acc2 = 0.f;
         for (int k0 = lane * 8; k0 < K; k0 += 256) {       // K is a multiple of 8 (zero-padded activations)
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(xr + k0));
-            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(xa + k0));
+            const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(xb + k0));
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w}, u2[4] = {q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                acc = fmaf(h2f((uint16_t)(u[i] & 0xFFFFu), bf), fc1_w[k0 + 2 * i], acc);
-                acc = fmaf(h2f((uint16_t)(u[i] >> 16), bf), fc1_w[k0 + 2 * i + 1], acc);
+                const float w0 = fc1_w[k0 + 2 * i], w1 = fc1_w[k0 + 2 * i + 1];
+                acc = fmaf(h2f((uint16_t)(u[i] & 0xFFFFu), bf), w0, acc);
+                acc = fmaf(h2f((uint16_t)(u[i] >> 16), bf), w1, acc);
+                acc2 = fmaf(h2f((uint16_t)(u2[i] & 0xFFFFu), bf), w0, acc2);
+                acc2 = fmaf(h2f((uint16_t)(u2[i] >> 16), bf), w1, acc2);
             }
         }
         acc = warp_sum(acc);
-        if (lane == 0) out[r * ldo] = acc + b0;
+        acc2 = warp_sum(acc2);
+        if (lane == 0) {
+            out[r * ldo] = acc + b0;
+            if (two) out[r2 * ldo] = acc2 + b0;
+        }
     }
 }
 
@@ -789,12 +829,23 @@ extern "C" int rsr_conv_w_flip(rsr_handle* h, void* stream, const void* w16, int
     return 0;
 }
 
+extern "C" int rsr_conv_w_phase(rsr_handle* h, void* stream, const void* w16, int W, int Ap, int Bp, int step, int phase,
+                                void* out16) {
+    if (!h || !w16 || !out16 || W <= 0 || Ap <= 0 || Bp <= 0 || step <= 0 || phase < 0 || phase >= step) return RSR_E_ARG;
+    const int nj = (W - phase + step - 1) / step;          // taps with index = phase mod step
+    if (nj <= 0) return RSR_E_ARG;
+    conv_w_phase_kernel<<<grid_for((long long)nj * Ap * Bp, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        (const uint16_t*)w16, Ap, Bp, step, phase, nj, (uint16_t*)out16);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int rsr_fc1_fwd(rsr_handle* h, void* stream, const void* x16, int ldx, long long rows, int K,
                            const void* w16, int ldw, const float* bias, float* out32, int ldo) {
     if (!h || !x16 || !w16 || !out32 || rows <= 0 || K <= 0 || ldo <= 0 || ldw <= 0) return RSR_E_ARG;
     if ((K & 7) || (ldx & 7) || ldx < K || ((uintptr_t)x16 & 15) || K > 8192) return RSR_E_SHAPE;
     // few, long-lived blocks: every block stages the strided weight column once
-    fc1_fwd_kernel<<<grid_for(rows * 32, 256, h->num_sms, 2), 256, (size_t)K * 4, (cudaStream_t)stream>>>(
+    fc1_fwd_kernel<<<grid_for(rows * 16, 256, h->num_sms, 4), 256, (size_t)K * 4, (cudaStream_t)stream>>>(
         (const uint16_t*)x16, ldx, rows, K, (const uint16_t*)w16, ldw, bias, out32, ldo, h->dtype == RSR_DTYPE_BF16);
     RSR_LAUNCH_CHECK();
     return 0;

@@ -231,6 +231,8 @@ class GAN_RNN(Model):
         # flat gradient buffer runs eagerly between segments (capturing NCCL itself hung on 2 x B200 with
         # torch 2.11 / NCCL 2.28.9).  RSR_GRAPH_DDP=0: fully eager with several ranks.
         self.graph_ddp = os.environ.get("RSR_GRAPH_DDP", "1") != "0"
+        # RSR_GRAPH_NCCL=1: capture the all-reduces INTO the graph (one graph per schedule, no segment cuts)
+        self.graph_nccl = os.environ.get("RSR_GRAPH_NCCL", "0") == "1"
         self._cap = None
         self.g_outputs = None
         # tf.summary.FileWriter(save_dir/train | eval) (:82-86); `summaries` = the tags of the merged scalar summary
@@ -455,14 +457,14 @@ class GAN_RNN(Model):
                 n.tick()                                   # their masks from the current tick
         if self.world > 1:
             # utils/ops.py:343-376 average_gradients: sum over ranks here, 1/N folded into the update kernel
-            if self._cap is not None:
+            if self._cap is not None and not self.graph_nccl:
                 # graph capture in progress: the collective stays OUTSIDE the graphs -- close the segment, run the
                 # all-reduce eagerly (keeps every rank's collective sequence aligned), open the next segment
                 self._cap_end(P.grad)
                 self.dist.all_reduce(P.grad)
                 self._cap_begin()
             else:
-                self.dist.all_reduce(P.grad)
+                self.dist.all_reduce(P.grad)     # eager, or captured into the one graph of the schedule (graph_nccl)
         gmul = 1.0 / (self.world * gscale)
         h.seg_sumsq(P.grad, gmul, P.seg_id, len(P.segs), P.sumsq)
         if adam:

@@ -252,6 +252,21 @@ class Handle(object):
     def conv_w_flip(self, w16, W, cin_p, cout_p, out16):
         self._call("rsr_conv_w_flip", 1, self.h, _stream(), _p(w16), W, cin_p, cout_p, _p(out16))
 
+    def conv_w_phase(self, w16, W, ap, bp, step, phase, out16):
+        self._call("rsr_conv_w_phase", 1, self.h, _stream(), _p(w16), W, ap, bp, step, phase, _p(out16))
+
+    # ------------------------------------------------- virtual batch norm (utils/bnorm.py)
+    def vbn_stats(self, z32, rows, N, gamma, beta, coef, scratch, eps=1e-5, batch_weight=1.0, ref_stats=None,
+                  stats_out=None):
+        self._call("rsr_vbn_stats", 2, self.h, _stream(), _p(z32), z32.stride(0), rows, N, _p(gamma), _p(beta), eps,
+                   float(batch_weight), _p(ref_stats), _p(stats_out), _p(coef), _p(scratch))
+
+    def vbn_bwd(self, da16, z32, rows, N, act, batch_weight, coef, dgamma, dbeta, dz16, scratch, dz32=None):
+        self._call("rsr_vbn_bwd", 3, self.h, _stream(), _p(da16), da16.stride(0), _p(z32), z32.stride(0), rows, N, act,
+                   float(batch_weight), _p(coef), _p(dgamma), _p(dbeta), _p(dz16),
+                   dz16.stride(0) if dz16 is not None else 0, _p(dz32), dz32.stride(0) if dz32 is not None else 0,
+                   _p(scratch))
+
     # ------------------------------------------------- one-output fully_connected (discriminator heads)
     def fc1_fwd(self, x16, rows, K, w16, bias, out32):
         self._call("rsr_fc1_fwd", 1, self.h, _stream(), _p(x16), x16.stride(0), rows, K, _p(w16), w16.stride(0),

@@ -251,3 +251,61 @@ def test_conv2d_same_against_torch_and_toeplitz_equivalence():
     assert np.abs(db2.reshape(H, co).sum(0) - db).max() < 1e-11
     dense = (W2 != 0).mean()
     assert 0.5 < dense < 1.0                                              # 19 of 25 line pairs at H = kh = 5
+
+
+@pytest.mark.parametrize("B,L,ci,co,k", [(2, 64, 3, 5, 31), (3, 17, 4, 2, 5), (1, 32, 1, 16, 31)])
+def test_strided_conv_family_against_torch(B, L, ci, co, k):
+    """utils/ops.py `downconv` (conv2d, stride 2, SAME) and `deconv` (conv2d_transpose, stride 2): the oracle's statement
+    against torch.nn.functional.conv1d / conv_transpose1d on the explicitly SAME-padded tensors, values and gradients."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(L)
+    x, W, b = rng.standard_normal((B, L, ci)), rng.standard_normal((k, ci, co)) * 0.1, rng.standard_normal(co)
+    y, c = O.downconv_fwd(x, W, b)
+    _, pl, pr = O.same_pad(L, k, 2)
+    xt, Wt, bt = (torch.tensor(v, requires_grad=True) for v in (x, W, b))
+    yt = F.conv1d(F.pad(xt.permute(0, 2, 1), (pl, pr)), Wt.permute(2, 1, 0), bt, stride=2).permute(0, 2, 1)
+    dy = rng.standard_normal(y.shape)
+    yt.backward(torch.tensor(dy))
+    dx, dW, db = O.downconv_bwd(dy, c)
+    for a, r in ((y, yt.detach()), (dx, xt.grad), (dW, Wt.grad), (db, bt.grad)):
+        assert np.abs(a - r.numpy()).max() < 1e-11
+    x2, W2, b2 = rng.standard_normal((B, L, co)), rng.standard_normal((k, ci, co)) * 0.1, rng.standard_normal(ci)
+    y2, c2 = O.deconv_fwd(x2, W2, b2)
+    assert y2.shape == (B, 2 * L, ci)
+    x2t, W2t, b2t = (torch.tensor(v, requires_grad=True) for v in (x2, W2, b2))
+    _, pl2, _ = O.same_pad(2 * L, k, 2)
+    full = F.conv_transpose1d(x2t.permute(0, 2, 1), W2t.permute(2, 1, 0), None, stride=2)
+    full = F.pad(full, (0, max(0, pl2 + 2 * L - full.shape[2])))
+    y2t = (full[:, :, pl2:pl2 + 2 * L] + b2t[None, :, None]).permute(0, 2, 1)
+    dy2 = rng.standard_normal(y2.shape)
+    y2t.backward(torch.tensor(dy2))
+    dx2, dW2, db2 = O.deconv_bwd(dy2, c2)
+    for a, r in ((y2, y2t.detach()), (dx2, x2t.grad), (dW2, W2t.grad), (db2, b2t.grad)):
+        assert np.abs(a - r.numpy()).max() < 1e-11
+
+
+def test_virtual_batch_norm_against_autograd():
+    """utils/bnorm.py: reference pass and live pass (statistics blended with weight 1 / (batch + 1)) against an
+    independent torch statement differentiated by autograd."""
+    rng = np.random.default_rng(9)
+    B, L, C = 5, 12, 7
+    xr, xl = rng.standard_normal((B, L, C)), rng.standard_normal((B, L, C)) * 2 + 1
+    gamma, beta = 1 + 0.1 * rng.standard_normal(C), rng.standard_normal(C)
+    y_ref, _ = O.vbn_fwd(xr, gamma, beta)
+    ref = O.vbn_reference(xr)
+    y, cache = O.vbn_fwd(xl, gamma, beta, ref=ref)
+    dy = rng.standard_normal(y.shape)
+    dx, dg, db = O.vbn_bwd(dy, cache)
+
+    def torch_vbn(x, g, b_, m_ref=None, q_ref=None):
+        m, q = x.mean((0, 1)), (x ** 2).mean((0, 1))
+        if m_ref is not None:
+            w = 1.0 / (B + 1.0)
+            m, q = w * m + (1 - w) * m_ref, w * q + (1 - w) * q_ref
+        return (x - m) / torch.sqrt(1e-5 + q - m ** 2) * g + b_
+    assert np.abs(y_ref - torch_vbn(torch.tensor(xr), torch.tensor(gamma), torch.tensor(beta)).numpy()).max() < 1e-12
+    xt, gt, bt = (torch.tensor(v, requires_grad=True) for v in (xl, gamma, beta))
+    yt = torch_vbn(xt, gt, bt, torch.tensor(ref[0]), torch.tensor(ref[1]))
+    yt.backward(torch.tensor(dy))
+    for a, r in ((y, yt.detach()), (dx, xt.grad), (dg, gt.grad), (db, bt.grad)):
+        assert np.abs(a - r.numpy()).max() < 1e-11
