@@ -126,9 +126,9 @@ def peaks():
 
 NCU_SUMMARY = {   # C-ABI call -> committed `ncu --set full` summary of its kernel (profiles/, made by scripts in DESIGN.md 6)
     "rsr_gemm": "r1_gemm_full_summary.csv",
-    "rsr_lstmp_rec_bwd": "r1_recbwd_full_summary.csv",
+    "rsr_lstmp_rec_bwd": "r2_recbwd_pair_full_summary.csv",       # CTA-pair kernels (cfg-2: Cp = 512)
     "rsr_lstmp_rec_fwd": "r1_recfwd_full_summary.csv",
-    "rsr_lstmp_fused_fwd": "r1_recfwd_full_summary.csv",
+    "rsr_lstmp_fused_fwd": "r2_recfwd_pair_full_summary.csv",
 }
 
 

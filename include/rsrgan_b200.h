@@ -245,6 +245,24 @@ int rsr_conv_mask_rows(rsr_handle* h, void* stream, void* buf16, long long frame
 /* out[k][co][ci] = w[W-1-k][ci][co]: taps of the transposed convolution (tf.gradients of conv2d wrt its input). */
 int rsr_conv_w_flip(rsr_handle* h, void* stream, const void* w16, int W, int Cin_p, int Cout_p, void* out16);
 
+/* [splice, w] convolutions (models/rced.py:94-101 with splice = left_context + 1 + right_context > 1, the shape
+ * run_dnn.sh:129-140 trains: 40 bins x 11 lines): the H = splice lines of a frame are stored as CHANNELS of one position
+ * (channel = line * C + c), so the 2-D SAME convolution IS the 1-D overlapped-view GEMM above with the block-Toeplitz
+ * taps  W2[k][h_in*ci + a][h_out*co + b] = w[h_in - h_out + kh/2][k][a][b]  (zero outside the filter: the SAME padding
+ * along the lines).  The parameter stays TensorFlow's compact filter [kh, W, ci, co]:
+ *   rsr_conv_toeplitz_expand   compact 16-bit filter -> taps16 [W*cip, cop]  (after every update, like Wc)
+ *   rsr_conv_toeplitz_fold     grad[kh, W, ci, co] += sum over the tied copies of dW2 [W*cip, cop] (fixed order)
+ *   rsr_vec_tile / _fold       per-channel bias <-> its per-(line, channel) tiling and the gradient back
+ *   rsr_conv_stage_lines       fp32 frames (.., H*L) -> channels-last 16-bit rows [frames*S, Cp], channel h = line h */
+int rsr_conv_toeplitz_expand(rsr_handle* h, void* stream, const void* w16, int kh, int W, int ci, int co, int H,
+                             int cip, int cop, void* out16);
+int rsr_conv_toeplitz_fold(rsr_handle* h, void* stream, const float* dw2, int kh, int W, int ci, int co, int H,
+                           int cip, int cop, float* grad);
+int rsr_vec_tile(rsr_handle* h, void* stream, const float* v, int co, int H, int cop, float* out);
+int rsr_vec_fold(rsr_handle* h, void* stream, const float* t, int co, int H, float* grad);
+int rsr_conv_stage_lines(rsr_handle* h, void* stream, const float* x, int ldx, int time_major_in, int B, int T,
+                         int H, int L, int S, int Cp, const float* mean, const float* istd, void* out16);
+
 /* Strided members of the family (utils/ops.py:78-98 `downconv`: conv2d, strides [1, 2, 1, 1], SAME, kwidth 31;
  * utils/ops.py:277-310 `deconv`: conv2d_transpose with the same geometry; consumer models/discriminator.py:38-90).
  * Same channels-last sequence layout, sequence pitch S even, pl = SAME pad before (oracle/rsr_oracle.py same_pad):

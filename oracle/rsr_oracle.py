@@ -616,17 +616,17 @@ RCED_FILTERS = (12, 16, 20, 24, 32, 24, 20, 16, 12)      # models/rced.py:92
 RCED_WIDTHS = (13, 11, 9, 7, 7, 7, 9, 11, 13)            # models/rced.py:93
 
 
-def init_g_rced(rng, in_dim=257, out_dim=40, filters=RCED_FILTERS, widths=RCED_WIDTHS, dtype=np.float64):
-    """models/rced.py:90-114 with splice = 1: nine conv2d [1, w] (xavier, zero bias; contrib default scopes
-    Conv, Conv_1, ...), then FC (in_dim * filters[-1]) -> out_dim with bias 0.1 (:108-113)."""
+def init_g_rced(rng, in_dim=257, out_dim=40, filters=RCED_FILTERS, widths=RCED_WIDTHS, dtype=np.float64, splice=1):
+    """models/rced.py:90-114: nine conv2d [splice, w] (xavier, zero bias; contrib default scopes Conv, Conv_1, ...), then
+    FC (splice * in_dim * filters[-1]) -> out_dim with bias 0.1 (:108-113)."""
     p = OrderedDict()
     cin = 1
     for l, (c, w) in enumerate(zip(filters, widths)):
         name = "g_model/Conv" + ("" if l == 0 else "_%d" % l)
-        p[name + "/weights"] = xavier(rng, (1, w, cin, c), dtype)
+        p[name + "/weights"] = xavier(rng, (splice, w, cin, c), dtype)
         p[name + "/biases"] = np.zeros(c, dtype)
         cin = c
-    p["g_model/fully_connected/weights"] = xavier(rng, (in_dim * cin, out_dim), dtype)
+    p["g_model/fully_connected/weights"] = xavier(rng, (splice * in_dim * cin, out_dim), dtype)
     p["g_model/fully_connected/biases"] = np.full(out_dim, 0.1, dtype)
     return p
 
@@ -849,14 +849,21 @@ def _conv_names(p):
 
 
 def g_rced_fwd(p, x, lengths=None):
-    """models/rced.py:46-57,90-114, splice = 1: every frame (leading dims flattened) is a length-257 signal with
-    one channel; nine ReLU convs; the NHWC tensor (N, 1, 257, 12) is flattened position-major / channel-minor
-    (tf.reshape, :106) into the linear output layer."""
-    lead, L = x.shape[:-1], x.shape[-1]
-    h = x.reshape(-1, L, 1)
+    """models/rced.py:46-57,90-114: every frame (leading dims flattened) is `splice` stacked lines of `input_dim` bins
+    with one channel, NHWC (N, splice, input_dim, 1) (:46-57; splice = the filter height of the first convolution, 1 in
+    BASELINE configs[3], 11 in run_dnn.sh:129-140); nine ReLU conv2d [splice, w]; the NHWC tensor is flattened
+    line-major / position / channel-minor (tf.reshape, :106) into the linear output layer."""
+    names = _conv_names(p)
+    H = p[names[0] + "/weights"].shape[0]
+    lead, L = x.shape[:-1], x.shape[-1] // H
+    h = x.reshape(-1, H, L, 1)
     caches = []
-    for n in _conv_names(p):
-        h, c = conv1d_same_fwd(h, p[n + "/weights"], p[n + "/biases"], ACT_RELU)
+    for n in names:
+        if H == 1:
+            h1, c = conv1d_same_fwd(h[:, 0], p[n + "/weights"], p[n + "/biases"], ACT_RELU)
+            h = h1[:, None]
+        else:
+            h, c = conv2d_same_fwd(h, p[n + "/weights"], p[n + "/biases"], ACT_RELU)
         caches.append(c)
     flat = h.reshape(h.shape[0], -1)
     y, c = linear_fwd(flat, p["g_model/fully_connected/weights"], p["g_model/fully_connected/biases"], ACT_NONE)
@@ -867,12 +874,17 @@ def g_rced_fwd(p, x, lengths=None):
 def g_rced_bwd(p, dy, caches):
     g = OrderedDict()
     c, hshape = caches[-1]
+    H = hshape[1]
     dh, dW, db = linear_bwd(dy.reshape(-1, dy.shape[-1]), c)
     g["g_model/fully_connected/weights"] = dW
     g["g_model/fully_connected/biases"] = db
     dh = dh.reshape(hshape)
     for n, cc in zip(reversed(_conv_names(p)), reversed(caches[:-1])):
-        dh, dW, db = conv1d_same_bwd(dh, cc)
+        if H == 1:
+            d1, dW, db = conv1d_same_bwd(dh[:, 0], cc)
+            dh = d1[:, None]
+        else:
+            dh, dW, db = conv2d_same_bwd(dh, cc)
         g[n + "/weights"] = dW
         g[n + "/biases"] = db
     return dh[..., 0].reshape(dy.shape[:-1] + (-1,)), g

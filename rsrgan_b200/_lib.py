@@ -67,6 +67,11 @@ SIGNATURES = {
     "rsr_conv_mask_rows": [vp, vp, vp, cll, ci, ci, ci],
     "rsr_conv_w_flip": [vp, vp, vp, ci, ci, ci, vp],
     "rsr_conv_w_phase": [vp, vp, vp, ci, ci, ci, ci, ci, vp],
+    "rsr_conv_toeplitz_expand": [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp],
+    "rsr_conv_toeplitz_fold": [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp],
+    "rsr_vec_tile": [vp, vp, vp, ci, ci, ci, vp],
+    "rsr_vec_fold": [vp, vp, vp, ci, ci, vp],
+    "rsr_conv_stage_lines": [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp],
     "rsr_vbn_stats": [vp, vp, vp, ci, cll, ci, vp, vp, cf, cf, vp, vp, vp, vp],
     "rsr_vbn_bwd": [vp, vp, vp, ci, vp, ci, cll, ci, ci, cf, vp, vp, vp, vp, ci, vp, ci, vp],
     "rsr_bn_train_stats": [vp, vp, vp, ci, cll, ci, vp, vp, cf, vp, cf, cf, ci, vp, vp],

@@ -516,6 +516,85 @@ __global__ void conv_w_flip_kernel(const uint16_t* __restrict__ w, int W, int Ci
     }
 }
 
+// [splice, w] SAME convolution over H stacked lines (models/rced.py:94-101 with splice > 1) as the 1-D overlapped-view
+// GEMM: the H lines of a frame are CHANNELS of one position (channel = line * C + c), and the compact TensorFlow filter
+// w[kh][W][ci][co] expands to block-Toeplitz taps
+//   out[k][h_in * ci + a][h_out * co + b] = w[h_in - h_out + kh / 2][k][a][b]      (zero outside the filter / the padding)
+// (out: [W, cip, cop], cip / cop = H * ci / H * co padded to multiples of 8).  The expansion is a derived operand,
+// rebuilt after every update like Wc; conv_toeplitz_fold_kernel sums the gradient of the expansion over the tied copies,
+// one thread per compact element in a fixed order (deterministic).
+__global__ void conv_toeplitz_expand_kernel(const uint16_t* __restrict__ w, int kh, int W, int ci, int co, int H,
+                                            int cip, int cop, uint16_t* __restrict__ out) {
+    const long long total = (long long)W * cip * cop;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % cop);
+        const int a = (int)((i / cop) % cip);
+        const int k = (int)(i / ((long long)cop * cip));
+        uint16_t v = 0;
+        if (a < H * ci && col < H * co) {
+            const int h_in = a / ci, h_out = col / co;
+            const int r = h_in - h_out + kh / 2;
+            if (r >= 0 && r < kh) v = w[(((long long)r * W + k) * ci + (a - h_in * ci)) * co + (col - h_out * co)];
+        }
+        out[i] = v;
+    }
+}
+
+__global__ void conv_toeplitz_fold_kernel(const float* __restrict__ dw2, int kh, int W, int ci, int co, int H, int cip,
+                                          int cop, float* __restrict__ grad) {
+    const long long total = (long long)kh * W * ci * co;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i % co);
+        const int a = (int)((i / co) % ci);
+        const int k = (int)((i / ((long long)co * ci)) % W);
+        const int r = (int)(i / ((long long)co * ci * W));
+        float s = 0.f;
+        for (int h_out = 0; h_out < H; ++h_out) {
+            const int h_in = h_out + r - kh / 2;
+            if (h_in >= 0 && h_in < H) s += dw2[((long long)k * cip + h_in * ci + a) * cop + h_out * co + b];
+        }
+        grad[i] += s;
+    }
+}
+
+// per-channel vectors of those layers (bias): tile[h * co + b] = v[b]; fold: grad[b] += sum_h t[h * co + b]
+__global__ void vec_tile_kernel(const float* __restrict__ v, int co, int H, int cop, float* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cop; i += gridDim.x * blockDim.x)
+        out[i] = i < H * co ? v[i % co] : 0.f;
+}
+__global__ void vec_fold_kernel(const float* __restrict__ t, int co, int H, float* __restrict__ grad) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < co; b += gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int h = 0; h < H; ++h) s += t[h * co + b];
+        grad[b] += s;
+    }
+}
+
+// x fp32 frames of H stacked lines ((B, T, H*L) batch-major or [T*B, ldx] time-major) -> out16 [T*B*S, Cp]:
+// row (t*B+b)*S + p, channel h = (x[.., h*L + p] - mean[h*L + p]) * istd[h*L + p]; channels >= H and rows p >= L zero.
+__global__ void conv_stage_lines_kernel(const float* __restrict__ x, int ldx, int time_major_in, int B, int T, int H,
+                                        int L, int S, int Cp, const float* __restrict__ mean,
+                                        const float* __restrict__ istd, uint16_t* __restrict__ out, int bf) {
+    const long long total = (long long)B * T * S * Cp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cp);
+        const long long row = i / Cp;
+        const int p = (int)(row % S);
+        const long long r = row / S;
+        float v = 0.f;
+        if (c < H && p < L) {
+            const int b = (int)(r % B), t = (int)(r / B);
+            const int f = c * L + p;
+            v = time_major_in ? x[r * ldx + f] : x[((long long)b * T + t) * ldx + f];
+            if (mean) v = (v - mean[f]) * istd[f];
+        }
+        out[i] = f2h(v, bf);
+    }
+}
+
 // Taps of one PHASE of a stride-`step` transposed convolution (data gradient of utils/ops.py `downconv`, forward of
 // `deconv`): out[q][b][a] = w[step * (nj - 1 - q) + c][a][b]   (w: [W, Ap, Bp], out: [nj, Bp, Ap]; taps with
 // index = c mod step, in reverse order, channel axes transposed).  step = 1, c = 0, nj = W is conv_w_flip.
@@ -825,6 +904,52 @@ extern "C" int rsr_conv_w_flip(rsr_handle* h, void* stream, const void* w16, int
     if (!h || !w16 || !out16 || W <= 0 || Cin_p <= 0 || Cout_p <= 0) return RSR_E_ARG;
     conv_w_flip_kernel<<<grid_for((long long)W * Cin_p * Cout_p, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
         (const uint16_t*)w16, W, Cin_p, Cout_p, (uint16_t*)out16);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_conv_toeplitz_expand(rsr_handle* h, void* stream, const void* w16, int kh, int W, int ci, int co, int H,
+                                        int cip, int cop, void* out16) {
+    if (!h || !w16 || !out16 || kh <= 0 || !(kh & 1) || W <= 0 || ci <= 0 || co <= 0 || H <= 0) return RSR_E_ARG;
+    if (cip < H * ci || cop < H * co || (cip & 7) || (cop & 7)) return RSR_E_SHAPE;
+    conv_toeplitz_expand_kernel<<<grid_for((long long)W * cip * cop, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        (const uint16_t*)w16, kh, W, ci, co, H, cip, cop, (uint16_t*)out16);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_conv_toeplitz_fold(rsr_handle* h, void* stream, const float* dw2, int kh, int W, int ci, int co, int H,
+                                      int cip, int cop, float* grad) {
+    if (!h || !dw2 || !grad || kh <= 0 || !(kh & 1) || W <= 0 || ci <= 0 || co <= 0 || H <= 0) return RSR_E_ARG;
+    if (cip < H * ci || cop < H * co) return RSR_E_SHAPE;
+    conv_toeplitz_fold_kernel<<<grid_for((long long)kh * W * ci * co, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        dw2, kh, W, ci, co, H, cip, cop, grad);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_vec_tile(rsr_handle* h, void* stream, const float* v, int co, int H, int cop, float* out) {
+    if (!h || !v || !out || co <= 0 || H <= 0 || cop < H * co) return RSR_E_ARG;
+    vec_tile_kernel<<<(cop + 255) / 256, 256, 0, (cudaStream_t)stream>>>(v, co, H, cop, out);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_vec_fold(rsr_handle* h, void* stream, const float* t, int co, int H, float* grad) {
+    if (!h || !t || !grad || co <= 0 || H <= 0) return RSR_E_ARG;
+    vec_fold_kernel<<<(co + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, co, H, grad);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_conv_stage_lines(rsr_handle* h, void* stream, const float* x, int ldx, int time_major_in, int B, int T,
+                                    int H, int L, int S, int Cp, const float* mean, const float* istd, void* out16) {
+    if (!h || !x || !out16 || B <= 0 || T <= 0 || H <= 0 || L <= 0) return RSR_E_ARG;
+    if ((mean == nullptr) != (istd == nullptr)) return RSR_E_ARG;
+    if (S < L || Cp < H || (Cp & 7) || ldx < H * L || ((uintptr_t)out16 & 15)) return RSR_E_SHAPE;
+    const long long total = (long long)B * T * S * Cp;
+    conv_stage_lines_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, time_major_in, B, T, H, L, S, Cp, mean, istd, (uint16_t*)out16, h->dtype == RSR_DTYPE_BF16);
     RSR_LAUNCH_CHECK();
     return 0;
 }

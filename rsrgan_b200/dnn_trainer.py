@@ -34,8 +34,6 @@ class DNNTrainer(GAN_RNN):
         if g_type not in ("dnn", "rced"):
             # dnn_trainer_single_gpu.py:86-89 / dnn_trainer.py:94-101 (`cnn` = models/cnn.py is not on this path)
             raise ValueError("Unrecognized G type {}".format(g_type))
-        if g_type == "rced" and (_arg(args, "left_context", 0) or _arg(args, "right_context", 0)):
-            raise NotImplementedError("rced is implemented for splice = 1 (left_context = right_context = 0)")
         if not hasattr(args, "g_type"):          # GAN_RNN's default g_type is "lstm"; this trainer's is "dnn"
             from argparse import Namespace
             args = Namespace(**dict(vars(args) if args is not None else {}, g_type=g_type))

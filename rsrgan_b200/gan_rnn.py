@@ -197,6 +197,8 @@ class GAN_RNN(Model):
             if self.g_type in ("res_lstm_l", "res_lstm_base"):
                 gk.pop("proj", None)
                 gk.pop("units", None)
+            if self.g_type == "rced":              # models/rced.py:46-57: (batch, splice, input_dim, 1) frames
+                gk["splice"] = self.left_context + 1 + self.right_context
             self.G = nets.Generator(self.h, self.g_type, **gk)
             self.D = None
             if not infer:

@@ -420,17 +420,81 @@ class Conv1dSame(object):
         return dx_whole
 
 
+class Conv2dLines(Conv1dSame):
+    """tf.contrib.layers.conv2d(inputs, C_out, [splice, w], padding=SAME, relu) over frames of H = splice stacked lines
+    (models/rced.py:46-57,94-101; run_dnn.sh:129-140 trains 40 bins x 11 lines).  The lines are CHANNELS of one position
+    (channel = line * C + c), so the layer is Conv1dSame with block-Toeplitz taps (include/rsrgan_b200.h, "[splice, w]
+    convolutions"): the flat parameter buffer holds TensorFlow's compact filter (kh, w, C_in, C_out) and per-channel bias,
+    the GEMM operands (taps, flipped taps, tiled bias) are derived after every update, and the gradient of the expansion is
+    folded back over the tied copies in a fixed order."""
+
+    def __init__(self, net, scope, fl, kh, width, c_in, c_out, lines):
+        self.net, self.scope, self.fl, self.W, self.c_in, self.c_out = net, scope, fl, width, c_in, c_out
+        self.kh, self.H = kh, lines
+        self.cip, self.cop = packing.round_up(lines * c_in, 8), packing.round_up(lines * c_out, 8)
+        self.wname, self.bname = scope + "/weights", scope + "/biases"
+        h = net.h
+        self.taps16 = torch.zeros(width * self.cip, self.cop, dtype=h.h16, device=h.device)
+        self.wflip16 = torch.zeros(width * self.cop, self.cip, dtype=h.h16, device=h.device)
+        self.dw2 = torch.zeros(width * self.cip, self.cop, dtype=F32, device=h.device)
+        self.bias_t = torch.zeros(self.cop, dtype=F32, device=h.device)
+        self.db_t = torch.zeros(self.cop, dtype=F32, device=h.device)
+
+    def segs(self):
+        return [params.conv_w2d(self.wname, self.kh, self.W, self.c_in, self.c_out), params.fc_b(self.bname, self.c_out)]
+
+    def refresh(self):
+        h, P = self.net.h, self.net.P
+        h.conv_toeplitz_expand(P.view(self.wname, "theta16"), self.kh, self.W, self.c_in, self.c_out, self.H, self.cip,
+                               self.cop, self.taps16)
+        h.conv_w_flip(self.taps16, self.W, self.cip, self.cop, self.wflip16)
+        h.vec_tile(P.view(self.bname), self.c_out, self.H, self.cop, self.bias_t)
+
+    def fwd(self, ctx, x_whole, frames):
+        net, h, fl = self.net, self.net.h, self.fl
+        y_whole, y = fl.buf(net, (ctx, self.scope, "y16", frames), frames, self.cop)
+        rows = frames * fl.S
+        h.gemm(fl.window(x_whole, frames, self.cip, self.W), self.taps16, rows, self.cop, self.W * self.cip, b_mn=True,
+               bias=self.bias_t, act=ACT_RELU, out16=y)
+        h.conv_mask_rows(y, frames, fl.S, fl.L, self.cop)
+        return y_whole
+
+    def bwd(self, ctx, x_whole, dy_whole, frames, want_dx=True):
+        net, h, fl, P = self.net, self.net.h, self.fl, self.net.P
+        rows = frames * fl.S
+        G = fl.GUARD
+        dy = dy_whole[G:G + rows]
+        dx_whole = None
+        if want_dx:
+            dx_whole, dx = fl.buf(net, (ctx, self.scope, "dx16", frames), frames, self.cip)
+            h.gemm(fl.window(dy_whole, frames, self.cop, self.W), self.wflip16, rows, self.cip, self.W * self.cop,
+                   b_mn=True, dact_src=x_whole[G:G + rows], dact=ACT_RELU, out16=dx)
+        with h.side_stream():
+            h.fill32(self.dw2, 0.0)
+            h.gemm(fl.window(x_whole, frames, self.cip, self.W), dy, self.W * self.cip, self.cop, rows, a_mn=True,
+                   b_mn=True, beta=1.0, out32=self.dw2)
+            h.conv_toeplitz_fold(self.dw2, self.kh, self.W, self.c_in, self.c_out, self.H, self.cip, self.cop,
+                                 P.view(self.wname, "grad"))
+            h.fill32(self.db_t, 0.0)
+            h.colsum16(dy, rows, self.cop, self.db_t, accumulate=True)
+            h.vec_fold(self.db_t, self.c_out, self.H, P.view(self.bname, "grad"))
+        return dx_whole
+
+
 class FCFrames(object):
     """fully_connected over the flattened NHWC frame (models/rced.py:106-113): one GEMM whose A rows are whole
-    frames of the channels-last buffer (row pitch S*Cp, K = L*Cp; padded channels meet zero weight rows)."""
+    frames of the channels-last buffer (row pitch S*Cp, K = L*Cp; padded channels meet zero weight rows).  lines > 1:
+    the frame is `lines` stacked lines stored as channels (Conv2dLines); the weight rows are re-indexed accordingly."""
 
-    def __init__(self, net, scope, fl, chans, n_out):
-        self.net, self.scope, self.fl, self.chans, self.n_out = net, scope, fl, chans, n_out
-        self.cp, self.outp = packing.round_up(chans, 8), packing.round_up(n_out, 8)
+    def __init__(self, net, scope, fl, chans, n_out, lines=1):
+        self.net, self.scope, self.fl, self.chans, self.n_out, self.H = net, scope, fl, chans, n_out, lines
+        self.cp, self.outp = packing.round_up(lines * chans, 8), packing.round_up(n_out, 8)
         self.wname, self.bname = scope + "/weights", scope + "/biases"
 
     def segs(self):
-        return [params.fc_w_frames(self.wname, self.fl.L, self.chans, self.n_out), params.fc_b(self.bname, self.n_out)]
+        w = (params.fc_w_frames(self.wname, self.fl.L, self.chans, self.n_out) if self.H == 1 else
+             params.fc_w_lines(self.wname, self.H, self.fl.L, self.chans, self.n_out))
+        return [w, params.fc_b(self.bname, self.n_out)]
 
     def refresh(self):
         pass
@@ -530,8 +594,10 @@ RCED_WIDTHS = (13, 11, 9, 7, 7, 7, 9, 11, 13)            # models/rced.py:93
 
 class Generator(Net):
     def __init__(self, handle, g_type="lstm", in_dim=257, out_dim=40, cell=760, proj=280, layers=None,
-                 units=1024, batch_norm=False, keep_prob=1.0):
+                 units=1024, batch_norm=False, keep_prob=1.0, splice=1):
+        """splice (rced only): the input frame is `splice` stacked lines of in_dim / splice bins (models/rced.py:46-57)."""
         self.g_type, self.in_dim, self.out_dim = g_type, in_dim, out_dim
+        self.splice = int(splice) if g_type == "rced" else 1
         # dnn: tf.nn.dropout behind every hidden layer (FCBN); LSTM generators: DropoutWrapper(output_keep_prob) on every
         # LSTM layer's output (models/lstm.py:99-102, models/res_lstm_l.py:96-99) = _drop_fwd / _drop_bwd below
         # rced builds keep_prob but never applies a dropout op (models/rced.py:73-77,102-103): a no-op there
@@ -575,15 +641,21 @@ class Generator(Net):
                 return ls + [FC(net, "g_model/fully_connected_%d" % (L + 1), units, out_dim, ACT_NONE)]
         elif g_type == "rced":
             # models/rced.py:92-101: nine [1, w] ReLU convolutions over the spectrum bins of each frame, then
-            # FC (in_dim * 12) -> out_dim.  splice = 1 only (the [splice, w] 2-D case is not on this path).
+            # FC (splice * bins * 12) -> out_dim.  splice = 1: 1-D convolutions (Conv1dSame); splice > 1: the [splice, w]
+            # 2-D convolutions over the stacked lines (Conv2dLines).
             filt, wid = RCED_FILTERS, RCED_WIDTHS
-            self.frames = ConvFrames(in_dim, max(wid))
+            H = self.splice
+            assert in_dim % H == 0, "rced input width must be splice * bins"
+            self.frames = ConvFrames(in_dim // H, max(wid))
 
             def mk(net):
                 ch = (1,) + filt
-                ls = [Conv1dSame(net, "g_model/Conv" + ("" if i == 0 else "_%d" % i), self.frames, wid[i], ch[i],
-                                 ch[i + 1]) for i in range(len(filt))]
-                return ls + [FCFrames(net, "g_model/fully_connected", self.frames, filt[-1], out_dim)]
+                name = lambda i: "g_model/Conv" + ("" if i == 0 else "_%d" % i)
+                if H == 1:
+                    ls = [Conv1dSame(net, name(i), self.frames, wid[i], ch[i], ch[i + 1]) for i in range(len(filt))]
+                else:
+                    ls = [Conv2dLines(net, name(i), self.frames, H, wid[i], ch[i], ch[i + 1], H) for i in range(len(filt))]
+                return ls + [FCFrames(net, "g_model/fully_connected", self.frames, filt[-1], out_dim, lines=H)]
         else:
             raise ValueError("Unrecognized G type {}".format(g_type))   # models/gan_rnn_placeholder.py:131-132
         super(Generator, self).__init__(handle, mk, adam=True)
@@ -618,7 +690,11 @@ class Generator(Net):
             fl, Ls = self.frames, self.layers
             a, _ = fl.buf(self, ("g", "x16", rows), rows, Ls[0].cip)
             if not reuse_staged:
-                h.conv_stage_frames(x, B, T, self.in_dim, fl.S, Ls[0].cip, a[fl.GUARD:], time_major_in=x_time_major)
+                if self.splice == 1:
+                    h.conv_stage_frames(x, B, T, self.in_dim, fl.S, Ls[0].cip, a[fl.GUARD:], time_major_in=x_time_major)
+                else:
+                    h.conv_stage_lines(x, B, T, self.splice, fl.L, fl.S, Ls[0].cip, a[fl.GUARD:],
+                                       time_major_in=x_time_major)
             self._acts = [a]
             for l in Ls[:-1]:
                 a = l.fwd("g", a, rows)

@@ -252,6 +252,23 @@ class Handle(object):
     def conv_w_flip(self, w16, W, cin_p, cout_p, out16):
         self._call("rsr_conv_w_flip", 1, self.h, _stream(), _p(w16), W, cin_p, cout_p, _p(out16))
 
+    def conv_toeplitz_expand(self, w16, kh, W, ci, co, H, cip, cop, out16):
+        self._call("rsr_conv_toeplitz_expand", 1, self.h, _stream(), _p(w16), kh, W, ci, co, H, cip, cop, _p(out16))
+
+    def conv_toeplitz_fold(self, dw2, kh, W, ci, co, H, cip, cop, grad):
+        self._call("rsr_conv_toeplitz_fold", 1, self.h, _stream(), _p(dw2), kh, W, ci, co, H, cip, cop, _p(grad))
+
+    def vec_tile(self, v, co, H, cop, out):
+        self._call("rsr_vec_tile", 1, self.h, _stream(), _p(v), co, H, cop, _p(out))
+
+    def vec_fold(self, t, co, H, grad):
+        self._call("rsr_vec_fold", 1, self.h, _stream(), _p(t), co, H, _p(grad))
+
+    def conv_stage_lines(self, x, B, T, H, L, S, Cp, out16, mean=None, istd=None, time_major_in=False, ldx=None):
+        self._call("rsr_conv_stage_lines", 1, self.h, _stream(), _p(x),
+                   ldx if ldx is not None else (x.stride(0) if time_major_in else H * L), int(time_major_in), B, T, H, L, S,
+                   Cp, _p(mean), _p(istd), _p(out16))
+
     def conv_w_phase(self, w16, W, ap, bp, step, phase, out16):
         self._call("rsr_conv_w_phase", 1, self.h, _stream(), _p(w16), W, ap, bp, step, phase, _p(out16))
 

@@ -55,6 +55,21 @@ def conv_w(name, width, c_in, c_out):
     return Seg(name, "conv_w", (1, width, c_in, c_out), (width * cip, cop), dict(W=width, Cin_p=cip, Cout_p=cop))
 
 
+def conv_w2d(name, kh, width, c_in, c_out):
+    """tf.contrib.layers.conv2d filter (kh, w, C_in, C_out) of the [splice, w] convolutions (models/rced.py:94-101,
+    splice > 1), stored COMPACT exactly as TensorFlow holds it; the GEMM operand -- its block-Toeplitz expansion over
+    the stacked lines -- is derived after every update (rsr_conv_toeplitz_expand)."""
+    return Seg(name, "conv_w2d", (kh, width, c_in, c_out), (kh * width * c_in, c_out), dict(kh=kh, W=width, Ci=c_in, Co=c_out))
+
+
+def fc_w_lines(name, lines, positions, chans, n_out):
+    """FC over a flattened NHWC frame of `lines` stacked lines (models/rced.py:106-113): TF rows = (h * L + pos) * chans
+    + ch; device rows = pos * Cp + h * chans + ch, Cp = lines * chans padded to a multiple of 8 (zero rows)."""
+    cp = packing.round_up(lines * chans, 8)
+    return Seg(name, "fc_w_lines", (lines * positions * chans, n_out), (positions * cp, packing.round_up(n_out, 8)),
+               dict(H=lines, L=positions, C=chans, Cp=cp))
+
+
 def fc_w_frames(name, positions, chans, n_out):
     """FC over a flattened channels-last frame (models/rced.py:106-113): TF rows = pos * chans + ch; device rows =
     pos * Cp + ch with zero rows for the padded channels."""
@@ -100,6 +115,12 @@ def to_dev_layout(seg, a):
     elif seg.kind == "fc_w_frames":
         m = seg.meta
         out.reshape(m["L"], m["Cp"], -1)[:, :m["C"], :a.shape[1]] = a.reshape(m["L"], m["C"], -1)
+    elif seg.kind == "conv_w2d":
+        out[:] = a.reshape(seg.dev_shape)
+    elif seg.kind == "fc_w_lines":
+        m = seg.meta
+        t = a.reshape(m["H"], m["L"], m["C"], -1).transpose(1, 0, 2, 3).reshape(m["L"], m["H"] * m["C"], -1)
+        out.reshape(m["L"], m["Cp"], -1)[:, :m["H"] * m["C"], :a.shape[1]] = t
     elif seg.kind == "lstm_kernel":
         m = seg.meta
         p = packing.pack_cols(a, m["C"])
@@ -129,6 +150,12 @@ def from_dev_layout(seg, d):
     if seg.kind == "fc_w_frames":
         m = seg.meta
         return d.reshape(m["L"], m["Cp"], -1)[:, :m["C"], :seg.tf_shape[1]].reshape(seg.tf_shape).copy()
+    if seg.kind == "conv_w2d":
+        return d.reshape(seg.tf_shape).copy()
+    if seg.kind == "fc_w_lines":
+        m = seg.meta
+        t = d.reshape(m["L"], m["Cp"], -1)[:, :m["H"] * m["C"], :seg.tf_shape[1]]
+        return t.reshape(m["L"], m["H"], m["C"], -1).transpose(1, 0, 2, 3).reshape(seg.tf_shape).copy()
     if seg.kind == "lstm_kernel":
         m = seg.meta
         u = packing.unpack_cols(d, m["C"])

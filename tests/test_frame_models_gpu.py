@@ -165,3 +165,40 @@ def test_cfg4_rced_gan_batch256_against_oracle():
     g1 = m.generate(x, lengths).cpu().numpy()
     g2 = m.generate(x[perm], lengths).cpu().numpy()
     assert np.abs(g2 - g1[perm]).max() < 1e-6
+
+
+def test_rced_splice11_2d_convolutions_against_oracle():
+    """models/rced.py with splice > 1 -- the shape run_dnn.sh:129-140 trains: 40 bins x 11 spliced lines, nine conv2d
+    [11, w] -- under DNNTrainer: generator output, MSE loss, every raw gradient (compact TF filters: the block-Toeplitz
+    expansion is folded back over its tied copies) and two Adam steps against the float64 oracle (conv2d_same_fwd/_bwd,
+    pinned to torch.nn.functional.conv2d in tests/test_oracle.py)."""
+    N, bins, H = 48, 40, 11
+    m = trainer(g_type="rced", batch_size=N, input_dim=bins, output_dim=40, left_context=5, right_context=5,
+                g_learning_rate=1e-3)
+    assert m.G.splice == H and m.G.frames.L == bins
+    gp = OrderedDict((k, v.astype(np.float64)) for k, v in m.G.P.export_tf().items())
+    assert gp["g_model/Conv/weights"].shape == (H, 13, 1, 12) and gp["g_model/Conv_4/weights"].shape == (H, 7, 24, 32)
+    assert gp["g_model/fully_connected/weights"].shape == (H * bins * 12, 40)
+    rng = np.random.default_rng(7)
+    x, y = rng.standard_normal((N, H * bins)).astype(np.float32), rng.standard_normal((N, 40)).astype(np.float32)
+    g_ref, _ = O.g_rced_fwd(gp, x.astype(np.float64))
+    a, r = rms(m.generate(x).cpu().numpy(), g_ref)
+    assert a < 1e-3 and r < 3e-3, (a, r)
+    L, G, _ = O.mse_losses_and_grads(gp, "rced", x.astype(np.float64), y.astype(np.float64))
+    m.g_learning_rate = 0.0
+    out = m.train_step(x, y)
+    assert out["g_mse_loss"] == pytest.approx(L["g_mse_loss"], rel=2e-3)
+    gs = m._gscale(N)
+    gg = m.G.P.export_tf("grad")
+    for k in G:
+        assert rms(gg[k] / gs, G[k])[1] < 1e-1, k          # same bar as the splice = 1 golden (nine stacked ReLU layers)
+    m.load_params(gp)                                     # fresh Adam state for the real steps (the lr = 0 step moved m, v)
+    m.G.P.m.zero_(); m.G.P.v.zero_(); m.G.P.hyper[4:6] = torch.tensor([0.9, 0.999], device=m.h.device)
+    m.g_learning_rate = 1e-3
+    st = O.MseState(gp, "rced")
+    for _ in range(2):
+        m.train_step(x, y)
+        O.mse_step(st, x.astype(np.float64), y.astype(np.float64), 1e-3)
+    g_ref2, _ = O.g_rced_fwd(st.g, x.astype(np.float64))
+    a, r = rms(m.generate(x).cpu().numpy(), g_ref2)
+    assert a < 2e-3 and r < 1e-2, (a, r)
