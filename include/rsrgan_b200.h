@@ -339,6 +339,28 @@ int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldda, const fl
                float* dz32, int lddz32, float* scratch);
 int rsr_rng_tick(rsr_handle* h, void* stream, unsigned long long* rng);
 
+/* batch_norm behind the convolutions -- tf.contrib.layers.conv2d(..., normalizer_fn=batch_norm, normalizer_params=
+ * {is_training, scale=True, renorm=True}), models/rced.py:63-71,94-97: no bias, the normalised axis is the conv2d
+ * channel and the moments pool every (frame, line, position).  In the frame layout of the convolution family the
+ * pre-activation z is [frames * S, N] fp32 with channel ch of line l in column l * C + ch (l < H; H = 1 for the
+ * [1, w] convolutions) and only rows r % S < L are data; gamma, beta [C] and state [6, lds >= C] are per channel,
+ * coef [8, N] is per column (the H columns of a channel hold the same values, columns >= H * C hold zeros) so the
+ * apply kernels stay per column.  Same arithmetic as the fully-connected entries above; count = frames * H * L.
+ *   rsr_bn_train_stats_lines / rsr_bn_eval_coef_lines   coefficients (+ UPDATE_OPS)
+ *   rsr_affine_act_lines   out16 = act(z A + B) on data rows, 0 on the padding rows (replaces rsr_conv_mask_rows)
+ *   rsr_bn_bwd_lines       da16 = gradient wrt the layer OUTPUT (any values on padding rows); dz16 = gradient wrt z,
+ *                          0 on padding rows; dgamma, dbeta [C] accumulate */
+int rsr_bn_train_stats_lines(rsr_handle* h, void* stream, const float* z, int ldz, long long frames, int S, int L, int H,
+                             int C, int N, const float* gamma, const float* beta, float eps, float* state, int lds,
+                             float momentum, float renorm_momentum, int update_state, float* coef, float* scratch);
+int rsr_bn_eval_coef_lines(rsr_handle* h, void* stream, int N, int H, int C, const float* gamma, const float* beta,
+                           float eps, const float* state, int lds, float* coef);
+int rsr_affine_act_lines(rsr_handle* h, void* stream, const float* z, int ldz, long long frames, int S, int L, int N,
+                         const float* A, const float* Bc, int act, void* out16, int ld16);
+int rsr_bn_bwd_lines(rsr_handle* h, void* stream, const void* da16, int ldda, const float* z, int ldz, long long frames,
+                     int S, int L, int H, int C, int N, int act, float* coef, float* dgamma, float* dbeta, void* dz16,
+                     int lddz, float* scratch);
+
 /* Kaldi compressed matrix ("CM" ark entries) decoded on the device -- io_funcs/kaldi_io.py:121-161 (uint16_to_float,
  * char_to_float, read_compress) fused with the CMVN of io_funcs/make_tfrecords.py:84-87.
  *   col_hdr  u16 [cols, 4]    PerColHeader percentiles (0, 25, 75, 100), as on disk (little endian)

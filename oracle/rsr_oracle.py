@@ -616,15 +616,20 @@ RCED_FILTERS = (12, 16, 20, 24, 32, 24, 20, 16, 12)      # models/rced.py:92
 RCED_WIDTHS = (13, 11, 9, 7, 7, 7, 9, 11, 13)            # models/rced.py:93
 
 
-def init_g_rced(rng, in_dim=257, out_dim=40, filters=RCED_FILTERS, widths=RCED_WIDTHS, dtype=np.float64, splice=1):
+def init_g_rced(rng, in_dim=257, out_dim=40, filters=RCED_FILTERS, widths=RCED_WIDTHS, dtype=np.float64, splice=1,
+                batch_norm=False):
     """models/rced.py:90-114: nine conv2d [splice, w] (xavier, zero bias; contrib default scopes Conv, Conv_1, ...), then
-    FC (splice * in_dim * filters[-1]) -> out_dim with bias 0.1 (:108-113)."""
+    FC (splice * in_dim * filters[-1]) -> out_dim with bias 0.1 (:108-113).  batch_norm (:63-71,97): the convolutions
+    have BatchNorm beta / gamma instead of biases, the output layer keeps its bias."""
     p = OrderedDict()
     cin = 1
     for l, (c, w) in enumerate(zip(filters, widths)):
         name = "g_model/Conv" + ("" if l == 0 else "_%d" % l)
         p[name + "/weights"] = xavier(rng, (splice, w, cin, c), dtype)
-        p[name + "/biases"] = np.zeros(c, dtype)
+        if batch_norm:
+            _bn_vars(p, name, c, dtype)
+        else:
+            p[name + "/biases"] = np.zeros(c, dtype)
         cin = c
     p["g_model/fully_connected/weights"] = xavier(rng, (splice * in_dim * cin, out_dim), dtype)
     p["g_model/fully_connected/biases"] = np.full(out_dim, 0.1, dtype)
@@ -844,27 +849,47 @@ def g_dnn_bwd(p, dy, caches):
 
 
 def _conv_names(p):
-    return sorted({k.rsplit("/", 1)[0] for k in p if k.startswith("g_model/Conv")},
+    return sorted({k.rsplit("/", 1)[0] for k in p if k.startswith("g_model/Conv") and k.endswith("/weights")},
                   key=lambda s: int(s.split("_")[-1]) if s[-1].isdigit() else 0)
 
 
-def g_rced_fwd(p, x, lengths=None):
+def g_rced_fwd(p, x, lengths=None, opts=None, salt0=0):
     """models/rced.py:46-57,90-114: every frame (leading dims flattened) is `splice` stacked lines of `input_dim` bins
     with one channel, NHWC (N, splice, input_dim, 1) (:46-57; splice = the filter height of the first convolution, 1 in
     BASELINE configs[3], 11 in run_dnn.sh:129-140); nine ReLU conv2d [splice, w]; the NHWC tensor is flattened
-    line-major / position / channel-minor (tf.reshape, :106) into the linear output layer."""
+    line-major / position / channel-minor (tf.reshape, :106) into the linear output layer.
+    With BatchNorm variables in p (:63-71,97): conv2d without bias -> batch_norm(renorm) over (N, H, W) per channel ->
+    relu; opts as in fc_block_fwd (bn_state, train, update)."""
+    opts = opts or {}
+    train = opts.get("train", True)
     names = _conv_names(p)
     H = p[names[0] + "/weights"].shape[0]
     lead, L = x.shape[:-1], x.shape[-1] // H
     h = x.reshape(-1, H, L, 1)
     caches = []
     for n in names:
+        bn = (n + "/BatchNorm/gamma") in p
+        W = p[n + "/weights"]
+        b = np.zeros(W.shape[-1], W.dtype) if bn else p[n + "/biases"]
+        act = ACT_NONE if bn else ACT_RELU
         if H == 1:
-            h1, c = conv1d_same_fwd(h[:, 0], p[n + "/weights"], p[n + "/biases"], ACT_RELU)
+            h1, c = conv1d_same_fwd(h[:, 0], W, b, act)
             h = h1[:, None]
         else:
-            h, c = conv2d_same_fwd(h, p[n + "/weights"], p[n + "/biases"], ACT_RELU)
-        caches.append(c)
+            h, c = conv2d_same_fwd(h, W, b, act)
+        bc = None
+        if bn:
+            gamma, beta = p[n + "/BatchNorm/gamma"], p[n + "/BatchNorm/beta"]
+            st = OrderedDict((k, opts["bn_state"][n + "/BatchNorm/" + k]) for k in BN_STATE_KEYS)
+            if train:
+                y, bc = bn_renorm_train_fwd(h, gamma, beta, st, update=opts.get("update", False))
+                for k in BN_STATE_KEYS:
+                    opts["bn_state"][n + "/BatchNorm/" + k] = st[k]
+            else:
+                y = bn_eval_fwd(h, gamma, beta, st)
+            h = act_fwd(y, ACT_RELU)
+            bc = (bc, y)
+        caches.append((c, bc))
     flat = h.reshape(h.shape[0], -1)
     y, c = linear_fwd(flat, p["g_model/fully_connected/weights"], p["g_model/fully_connected/biases"], ACT_NONE)
     caches.append((c, h.shape))
@@ -879,14 +904,18 @@ def g_rced_bwd(p, dy, caches):
     g["g_model/fully_connected/weights"] = dW
     g["g_model/fully_connected/biases"] = db
     dh = dh.reshape(hshape)
-    for n, cc in zip(reversed(_conv_names(p)), reversed(caches[:-1])):
+    for n, (cc, bc) in zip(reversed(_conv_names(p)), reversed(caches[:-1])):
+        if bc is not None:
+            bn_cache, y = bc
+            dh, g[n + "/BatchNorm/gamma"], g[n + "/BatchNorm/beta"] = bn_renorm_train_bwd(act_bwd(y, dh, ACT_RELU), bn_cache)
         if H == 1:
             d1, dW, db = conv1d_same_bwd(dh[:, 0], cc)
             dh = d1[:, None]
         else:
             dh, dW, db = conv2d_same_bwd(dh, cc)
         g[n + "/weights"] = dW
-        g[n + "/biases"] = db
+        if bc is None:
+            g[n + "/biases"] = db
     return dh[..., 0].reshape(dy.shape[:-1] + (-1,)), g
 
 

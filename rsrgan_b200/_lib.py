@@ -76,6 +76,10 @@ SIGNATURES = {
     "rsr_vbn_bwd": [vp, vp, vp, ci, vp, ci, cll, ci, ci, cf, vp, vp, vp, vp, ci, vp, ci, vp],
     "rsr_bn_train_stats": [vp, vp, vp, ci, cll, ci, vp, vp, cf, vp, cf, cf, ci, vp, vp],
     "rsr_bn_eval_coef": [vp, vp, ci, vp, vp, cf, vp, vp],
+    "rsr_bn_train_stats_lines": [vp, vp, vp, ci, cll, ci, ci, ci, ci, ci, vp, vp, cf, vp, ci, cf, cf, ci, vp, vp],
+    "rsr_bn_eval_coef_lines": [vp, vp, ci, ci, ci, vp, vp, cf, vp, ci, vp],
+    "rsr_affine_act_lines": [vp, vp, vp, ci, cll, ci, ci, ci, vp, vp, ci, vp, ci],
+    "rsr_bn_bwd_lines": [vp, vp, vp, ci, vp, ci, cll, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, ci, vp],
     "rsr_affine_act_drop": [vp, vp, vp, ci, cll, ci, vp, vp, ci, cf, vp, C.c_uint, vp, ci, vp, ci],
     "rsr_bn_bwd": [vp, vp, vp, ci, vp, ci, cll, ci, ci, cf, vp, C.c_uint, ci, vp, vp, vp, vp, vp, ci, vp, ci, vp],
     "rsr_rng_tick": [vp, vp, vp],

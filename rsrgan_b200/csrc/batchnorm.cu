@@ -73,7 +73,13 @@ struct BnBwdIn {
     const uint16_t* da; int ldda;   // gradient wrt the layer output (after activation and dropout)
     const float* A; const float* Bc; const float* mean; const float* inv_std;
     int act; uint32_t thr24; float inv_keep; const unsigned long long* rng; unsigned salt; int bf;
+    int S, L;                       // frame layout of the convolutional generator (S = 0: every row counts): row r is data
+                                    // iff r % S < L; the rows behind are the SAME padding shared with the next frame
 };
+// (the frame layout has fewer than 2^31 rows -- lines_check -- so the remainder is a 32-bit one)
+__device__ __forceinline__ bool row_live(long long r, int S, int L) {
+    return S == 0 || (unsigned)r % (unsigned)S < (unsigned)L;
+}
 
 // per-thread column coefficients (4 consecutive columns), loaded once
 struct Col4 { float A[4], B[4], mean[4], istd[4]; };
@@ -150,9 +156,11 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict
 #pragma unroll
                 for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(z + (r + u * BN_LANES) * ldz + c);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) acc(v[u]);
+                for (int u = 0; u < 4; ++u)
+                    if (row_live(r + u * BN_LANES, p.S, p.L)) acc(v[u]);
             }
-            for (; r < r1; r += BN_LANES) acc(*reinterpret_cast<const float4*>(z + r * ldz + c));
+            for (; r < r1; r += BN_LANES)
+                if (row_live(r, p.S, p.L)) acc(*reinterpret_cast<const float4*>(z + r * ldz + c));
             if (n > 0.f) {
                 const float inv_n = 1.0f / n;
 #pragma unroll
@@ -177,6 +185,7 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
+                    if (!row_live(r + u * BN_LANES, p.S, p.L)) continue;
                     float g[4], xh[4];
                     bwd_elem4(p, k4, v[u], raw[u], r + u * BN_LANES, c, N, key, g, xh);
 #pragma unroll
@@ -184,6 +193,7 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict
                 }
             }
             for (; r < r1; r += BN_LANES) {
+                if (!row_live(r, p.S, p.L)) continue;
                 const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + c);
                 const uint2 raw = *reinterpret_cast<const uint2*>(p.da + r * p.ldda + c);
                 float g[4], xh[4];
@@ -285,31 +295,24 @@ __device__ __forceinline__ bool merge_sums(const float* __restrict__ partial, in
 
 // state rows: 0 moving_mean 1 moving_variance 2 renorm_mean 3 renorm_stddev 4 renorm_mean_weight 5 renorm_stddev_weight
 // coef  rows: 0 A = scale / stddev  1 B = offset - mean A  2 mean  3 1 / stddev  4 r  5 d  6 mean(g)  7 mean(g x_hat)
-__global__ void bn_finish_train_kernel(const float* __restrict__ partial, int splits, long long rows, int N,
-                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                       float* __restrict__ state, float momentum, float renorm_momentum,
-                                       int update_state, float* __restrict__ coef) {
-    const int c = blockIdx.x * FIN_COLS + threadIdx.x;
-    float na, ma, qa;
-    if (!merge_moments(partial, splits, N, c, na, ma, qa)) return;
-    const float mean = ma, var = qa / (float)rows;
+// Renorm corrections, coefficients and (optionally) the UPDATE_OPS of ONE channel from its batch moments.  `sc` = the
+// channel's index in the state rows (pitch lds); returns coef rows 0-5 in k[6].
+__device__ __forceinline__ void renorm_channel(float mean, float var, float gamma, float beta, float eps,
+                                               float* __restrict__ state, long long lds, int sc, float momentum,
+                                               float renorm_momentum, int update_state, float k6[6]) {
     const float stddev = sqrtf(var + eps);
-    float* mm = state + 0 * (long long)N; float* mv = state + 1 * (long long)N;
-    float* rm = state + 2 * (long long)N; float* rs = state + 3 * (long long)N;
-    float* rmw = state + 4 * (long long)N; float* rsw = state + 5 * (long long)N;
+    float* mm = state + 0 * lds; float* mv = state + 1 * lds;
+    float* rm = state + 2 * lds; float* rs = state + 3 * lds;
+    float* rmw = state + 4 * lds; float* rsw = state + 5 * lds;
+    const int c = sc;
     // corrections from the PRE-update renorm averages, "as if they were initialised with this batch's moments"
     const float mixed_mean = rm[c] + (1.0f - rmw[c]) * mean;
     const float mixed_std = rs[c] + (1.0f - rsw[c]) * stddev;
     const float r = stddev / mixed_std;
     const float d = (mean - mixed_mean) / mixed_std;
-    const float scale = r * gamma[c], offset = fmaf(d, gamma[c], beta[c]);
+    const float scale = r * gamma, offset = fmaf(d, gamma, beta);
     const float A = scale / stddev;
-    coef[0 * (long long)N + c] = A;
-    coef[1 * (long long)N + c] = offset - mean * A;
-    coef[2 * (long long)N + c] = mean;
-    coef[3 * (long long)N + c] = 1.0f / stddev;
-    coef[4 * (long long)N + c] = r;
-    coef[5 * (long long)N + c] = d;
+    k6[0] = A; k6[1] = offset - mean * A; k6[2] = mean; k6[3] = 1.0f / stddev; k6[4] = r; k6[5] = d;
     if (update_state) {
         const float k = 1.0f - renorm_momentum;
         const float rm_n = rm[c] - (rm[c] - mean) * k, rmw_n = rmw[c] - (rmw[c] - 1.0f) * k;
@@ -319,6 +322,107 @@ __global__ void bn_finish_train_kernel(const float* __restrict__ partial, int sp
         rm[c] = rm_n; rmw[c] = rmw_n; rs[c] = rs_n; rsw[c] = rsw_n;
         mm[c] -= (mm[c] - new_mean) * (1.0f - momentum);
         mv[c] -= (mv[c] - new_var) * (1.0f - momentum);
+    }
+}
+
+__global__ void bn_finish_train_kernel(const float* __restrict__ partial, int splits, long long rows, int N,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                       float* __restrict__ state, float momentum, float renorm_momentum,
+                                       int update_state, float* __restrict__ coef) {
+    const int c = blockIdx.x * FIN_COLS + threadIdx.x;
+    float na, ma, qa;
+    if (!merge_moments(partial, splits, N, c, na, ma, qa)) return;
+    float k6[6];
+    renorm_channel(ma, qa / (float)rows, gamma[c], beta[c], eps, state, N, c, momentum, renorm_momentum, update_state, k6);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) coef[j * (long long)N + c] = k6[j];
+}
+
+// batch_norm behind a [splice, w] convolution (models/rced.py:63-71,94-97): the normalised axis is the conv2d channel,
+// pooled over (frame, line, position).  In the channels-last frame buffer the H lines of channel ch are the columns
+// line * C + ch, and only rows r % S < L are data (the partial kernels skip the rest): one block per channel merges the
+// splits * H column partials -- thread-strided in order, then a fixed binary tree -- and writes the channel's
+// coefficients to its H columns, so the normalise / backward kernels stay per-column.  Columns >= H * C (padding of the
+// GEMM N) get zero coefficients.  state rows have pitch lds (>= C).
+constexpr int LINES_THREADS = 256;
+__global__ void __launch_bounds__(LINES_THREADS) bn_finish_train_lines_kernel(
+    const float* __restrict__ partial, int splits, float count, int N, int H, int C, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float eps, float* __restrict__ state, int lds, float momentum, float renorm_momentum,
+    int update_state, float* __restrict__ coef) {
+    __shared__ float sn[LINES_THREADS], smn[LINES_THREADS], sq[LINES_THREADS];
+    __shared__ float k6s[6];
+    const int ch = blockIdx.x, t = threadIdx.x;
+    float na = 0.f, ma = 0.f, qa = 0.f;
+    for (int i = t; i < splits * H; i += LINES_THREADS) {
+        const int split = i / H, col = (i % H) * C + ch;
+        chan_merge(na, ma, qa, partial[((long long)split * 3 + 0) * N + col], partial[((long long)split * 3 + 1) * N + col],
+                   partial[((long long)split * 3 + 2) * N + col]);
+    }
+    sn[t] = na; smn[t] = ma; sq[t] = qa;
+    __syncthreads();
+    for (int s = LINES_THREADS / 2; s > 0; s >>= 1) {
+        if (t < s) {
+            chan_merge(na, ma, qa, sn[t + s], smn[t + s], sq[t + s]);
+            sn[t] = na; smn[t] = ma; sq[t] = qa;
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        float k6[6];
+        renorm_channel(ma, qa / count, gamma[ch], beta[ch], eps, state, lds, ch, momentum, renorm_momentum, update_state,
+                       k6);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) k6s[j] = k6[j];
+    }
+    __syncthreads();
+    for (int i = t; i < H * 6; i += LINES_THREADS) coef[(i % 6) * (long long)N + (i / 6) * C + ch] = k6s[i % 6];
+    if (ch == 0)
+        for (int i = t; i < (N - H * C) * 8; i += LINES_THREADS) coef[(i % 8) * (long long)N + H * C + i / 8] = 0.0f;
+}
+
+__global__ void bn_eval_coef_lines_kernel(int N, int H, int C, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, float eps, const float* __restrict__ state,
+                                          int lds, float* __restrict__ coef) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= N) return;
+    const bool live = col < H * C;
+    const int ch = col % C;
+    const float inv = live ? rsqrtf(state[1 * (long long)lds + ch] + eps) : 0.0f;
+    const float A = live ? gamma[ch] * inv : 0.0f;
+    coef[0 * (long long)N + col] = A;
+    coef[1 * (long long)N + col] = live ? beta[ch] - state[ch] * A : 0.0f;
+    coef[2 * (long long)N + col] = live ? state[ch] : 0.0f;
+    coef[3 * (long long)N + col] = inv;
+    coef[4 * (long long)N + col] = live ? 1.0f : 0.0f;
+    coef[5 * (long long)N + col] = 0.0f;
+}
+
+// backward totals of one channel over its H columns: dgamma, dbeta (per channel) and the two means of the dz kernel
+__global__ void __launch_bounds__(LINES_THREADS) bn_bwd_finish_lines_kernel(
+    const float* __restrict__ partial, int splits, float count, int N, int H, int C, float* __restrict__ coef,
+    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float s1s[LINES_THREADS], s2s[LINES_THREADS];
+    const int ch = blockIdx.x, t = threadIdx.x;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = t; i < splits * H; i += LINES_THREADS) {
+        const int split = i / H, col = (i % H) * C + ch;
+        s1 += partial[((long long)split * 2 + 0) * N + col];
+        s2 += partial[((long long)split * 2 + 1) * N + col];
+    }
+    s1s[t] = s1; s2s[t] = s2;
+    __syncthreads();
+    for (int s = LINES_THREADS / 2; s > 0; s >>= 1) {
+        if (t < s) { s1s[t] += s1s[t + s]; s2s[t] += s2s[t + s]; }
+        __syncthreads();
+    }
+    s1 = s1s[0]; s2 = s2s[0];
+    if (t == 0) {
+        if (dgamma) atomicAdd(dgamma + ch, coef[4 * (long long)N + ch] * s2 + coef[5 * (long long)N + ch] * s1);
+        if (dbeta) atomicAdd(dbeta + ch, s1);
+    }
+    for (int i = t; i < H; i += LINES_THREADS) {
+        coef[6 * (long long)N + i * C + ch] = s1 / count;
+        coef[7 * (long long)N + i * C + ch] = s2 / count;
     }
 }
 
@@ -373,7 +477,8 @@ __global__ void __launch_bounds__(256) affine_act_drop_kernel(const float* __res
                                                               const float* __restrict__ Bc, int act, uint32_t thr24,
                                                               float inv_keep, const unsigned long long* __restrict__ rng,
                                                               unsigned salt, uint16_t* __restrict__ out, int ldo,
-                                                              float* __restrict__ out32, int ldo32, int bf) {
+                                                              float* __restrict__ out32, int ldo32, int bf, int S,
+                                                              int L) {
     const int n4 = N >> 2;
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long rstep = ((long long)gridDim.x * blockDim.x) / n4;
@@ -387,7 +492,7 @@ __global__ void __launch_bounds__(256) affine_act_drop_kernel(const float* __res
         const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + c);
         float y[4] = {fmaf(v.x, a.x, b.x), fmaf(v.y, a.y, b.y), fmaf(v.z, a.z, b.z), fmaf(v.w, a.w, b.w)};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) y[k] = act_apply(y[k], act);
+        for (int k = 0; k < 4; ++k) y[k] = row_live(r, S, L) ? act_apply(y[k], act) : 0.0f;
         if (thr24 < (1u << 24)) {
             bool keep[4];
             const uint64_t idx = (uint64_t)r * (uint64_t)N + (uint64_t)c;
@@ -452,6 +557,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 #pragma unroll
             for (int k = 0; k < 4; ++k) g[k] = k4.A[k] * (g[k] - u1[k] - xh[k] * u2[k]);
         }
+        if (!row_live(r, p.S, p.L)) g[0] = g[1] = g[2] = g[3] = 0.0f;
         if (O16) {
             uint2 o;
             o.x = pack2(g[0], g[1], p.bf);
@@ -519,10 +625,9 @@ extern "C" int rsr_bn_eval_coef(rsr_handle* h, void* stream, int N, const float*
     return 0;
 }
 
-extern "C" int rsr_affine_act_drop(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,
-                                   const float* A, const float* Bc, int act, float keep_prob,
-                                   const unsigned long long* rng, unsigned salt, void* out16, int ld16, float* out32,
-                                   int ld32) {
+static int affine_impl(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N, const float* A,
+                       const float* Bc, int act, float keep_prob, const unsigned long long* rng, unsigned salt, void* out16,
+                       int ld16, float* out32, int ld32, int S, int L) {
     if (!h || !z || !Bc || (!out16 && !out32) || rows <= 0 || N <= 0) return RSR_E_ARG;
     if ((N & 3) || (ldz & 3) || (out16 && (ld16 & 3)) || (out32 && (ld32 & 3))) return RSR_E_SHAPE;
     if (act != RSR_ACT_NONE && act != RSR_ACT_RELU && act != RSR_ACT_LRELU) return RSR_E_SHAPE;
@@ -533,7 +638,7 @@ extern "C" int rsr_affine_act_drop(rsr_handle* h, void* stream, const float* z, 
     const int bf = h->dtype == RSR_DTYPE_BF16;
     cudaStream_t st = (cudaStream_t)stream;
 #define RSR_AFFINE(O16, O32) affine_act_drop_kernel<O16, O32><<<grid, 256, 0, st>>>( \
-        z, ldz, rows, N, A, Bc, act, thr, ik, rng, salt, (uint16_t*)out16, ld16, out32, ld32, bf)
+        z, ldz, rows, N, A, Bc, act, thr, ik, rng, salt, (uint16_t*)out16, ld16, out32, ld32, bf, S, L)
     if (out16 && out32) RSR_AFFINE(true, true);
     else if (out16) RSR_AFFINE(true, false);
     else RSR_AFFINE(false, true);
@@ -542,10 +647,17 @@ extern "C" int rsr_affine_act_drop(rsr_handle* h, void* stream, const float* z, 
     return 0;
 }
 
+extern "C" int rsr_affine_act_drop(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,
+                                   const float* A, const float* Bc, int act, float keep_prob,
+                                   const unsigned long long* rng, unsigned salt, void* out16, int ld16, float* out32,
+                                   int ld32) {
+    return affine_impl(h, stream, z, ldz, rows, N, A, Bc, act, keep_prob, rng, salt, out16, ld16, out32, ld32, 0, 0);
+}
+
 static int bn_bwd_impl(rsr_handle* h, void* stream, const void* da16, int ldda, const float* z, int ldz,
                        long long rows, int N, int act, float keep_prob, const unsigned long long* rng, unsigned salt,
                        int bn, float* coef, const float* bias, float* dgamma, float* dbeta, void* dz16, int lddz,
-                       float* dz32, int lddz32, float* scratch, float stat_w) {
+                       float* dz32, int lddz32, float* scratch, float stat_w, int S = 0, int L = 0, int H = 0, int C = 0) {
     if (!h || !da16 || !z || !scratch || rows <= 0 || N <= 0) return RSR_E_ARG;
     if (bn ? !coef : !bias) return RSR_E_ARG;
     if ((N & 3) || (ldz & 3) || (ldda & 3) || (dz16 && (lddz & 3)) || (dz32 && (lddz32 & 3))) return RSR_E_SHAPE;
@@ -559,11 +671,16 @@ static int bn_bwd_impl(rsr_handle* h, void* stream, const void* da16, int ldda, 
     else { p.A = nullptr; p.Bc = bias; p.mean = nullptr; p.inv_std = nullptr; }
     p.act = act; p.thr24 = thr; p.inv_keep = thr < (1u << 24) ? 1.0f / keep_prob : 1.0f; p.rng = rng; p.salt = salt;
     p.bf = h->dtype == RSR_DTYPE_BF16;
+    p.S = S; p.L = L;
     const int splits = bn_splits(rows, N, h->num_sms);
     if (bn || dbeta) {
         launch_partial<1>(bn_tx(N), splits, st, z, ldz, rows, N, p, scratch);
         RSR_LAUNCH_CHECK();
-        bn_bwd_finish_kernel<<<(N + FIN_COLS - 1) / FIN_COLS, dim3(FIN_COLS, FIN_LANES), 0, st>>>(scratch, splits, rows, N, bn, coef, dgamma, dbeta, stat_w);
+        if (H > 0)
+            bn_bwd_finish_lines_kernel<<<C, LINES_THREADS, 0, st>>>(scratch, splits, (float)(rows / S) * (float)(L * H), N, H, C,
+                                                                    coef, dgamma, dbeta);
+        else
+            bn_bwd_finish_kernel<<<(N + FIN_COLS - 1) / FIN_COLS, dim3(FIN_COLS, FIN_LANES), 0, st>>>(scratch, splits, rows, N, bn, coef, dgamma, dbeta, stat_w);
         RSR_LAUNCH_CHECK();
     }
     if (dz16 || dz32) {
@@ -586,6 +703,58 @@ extern "C" int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldd
                           float* dz32, int lddz32, float* scratch) {
     return bn_bwd_impl(h, stream, da16, ldda, z, ldz, rows, N, act, keep_prob, rng, salt, bn, coef, bias, dgamma, dbeta, dz16,
                        lddz, dz32, lddz32, scratch, 1.0f);
+}
+
+// ---- batch_norm behind the convolutions of the frame layout (see bn_finish_train_lines_kernel) ----
+static int lines_check(long long frames, int S, int L, int H, int C, int N) {
+    if (frames <= 0 || S <= 0 || L <= 0 || H <= 0 || C <= 0) return RSR_E_ARG;
+    if (S < L || N < H * C || (N & 3) || frames * S >= (1LL << 31)) return RSR_E_SHAPE;
+    return 0;
+}
+
+extern "C" int rsr_bn_train_stats_lines(rsr_handle* h, void* stream, const float* z, int ldz, long long frames, int S, int L,
+                                        int H, int C, int N, const float* gamma, const float* beta, float eps, float* state,
+                                        int lds, float momentum, float renorm_momentum, int update_state, float* coef,
+                                        float* scratch) {
+    if (!h || !z || !gamma || !beta || !state || !coef || !scratch) return RSR_E_ARG;
+    if (int e = lines_check(frames, S, L, H, C, N)) return e;
+    if ((ldz & 3) || lds < C) return RSR_E_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = frames * S;
+    const int splits = bn_splits(rows, N, h->num_sms);
+    BnBwdIn rows_only = {};
+    rows_only.S = S; rows_only.L = L;
+    launch_partial<0>(bn_tx(N), splits, st, z, ldz, rows, N, rows_only, scratch);
+    RSR_LAUNCH_CHECK();
+    bn_finish_train_lines_kernel<<<C, LINES_THREADS, 0, st>>>(scratch, splits, (float)frames * (float)(L * H), N, H, C, gamma,
+                                                              beta, eps, state, lds, momentum, renorm_momentum, update_state,
+                                                              coef);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_bn_eval_coef_lines(rsr_handle* h, void* stream, int N, int H, int C, const float* gamma, const float* beta,
+                                      float eps, const float* state, int lds, float* coef) {
+    if (!h || !gamma || !beta || !state || !coef || N <= 0 || H <= 0 || C <= 0) return RSR_E_ARG;
+    if (N < H * C || lds < C) return RSR_E_SHAPE;
+    bn_eval_coef_lines_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, H, C, gamma, beta, eps, state, lds, coef);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_affine_act_lines(rsr_handle* h, void* stream, const float* z, int ldz, long long frames, int S, int L,
+                                    int N, const float* A, const float* Bc, int act, void* out16, int ld16) {
+    if (frames <= 0 || S <= 0 || L <= 0 || S < L || frames * S >= (1LL << 31)) return RSR_E_ARG;
+    return affine_impl(h, stream, z, ldz, frames * S, N, A, Bc, act, 1.0f, nullptr, 0u, out16, ld16, nullptr, 0, S, L);
+}
+
+extern "C" int rsr_bn_bwd_lines(rsr_handle* h, void* stream, const void* da16, int ldda, const float* z, int ldz,
+                                long long frames, int S, int L, int H, int C, int N, int act, float* coef, float* dgamma,
+                                float* dbeta, void* dz16, int lddz, float* scratch) {
+    if (int e = lines_check(frames, S, L, H, C, N)) return e;
+    if (!dz16) return RSR_E_ARG;
+    return bn_bwd_impl(h, stream, da16, ldda, z, ldz, frames * S, N, act, 1.0f, nullptr, 0u, 1, coef, nullptr, dgamma, dbeta,
+                       dz16, lddz, nullptr, 0, scratch, 1.0f, S, L, H, C);
 }
 
 extern "C" int rsr_vbn_stats(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,

@@ -312,7 +312,7 @@ class GAN_RNN(Model):
         if self.D is not None:
             sd["D"] = self.D.P.state_dict()
         for net, key in ((self.G, "G"), (self.D, "D")):
-            if net is not None and net.fcbn:             # non-trainable batch_norm variables + dropout stream
+            if net is not None and net.has_bn_state:     # non-trainable batch_norm variables + dropout stream
                 sd[key]["bn_state"] = net.bn_state_tf()
                 sd[key]["rng"] = net.rng.cpu().numpy()
         sd["scalars"] = dict(mse_lambda=self.mse_lambda, disc_noise_std=self.disc_noise_std,

@@ -351,6 +351,73 @@ class LSTMP(object):
                    out32=P.view(self.prefix + "projection/kernel", "grad"))
 
 
+class ConvBN(object):
+    """normalizer_fn=batch_norm on a convolution of the frame layout (models/rced.py:63-71,94-97: {is_training,
+    scale=True, renorm=True} on all nine conv2d, which then have BatchNorm/beta and BatchNorm/gamma instead of a bias).
+    The GEMM writes the fp32 pre-activation; moments pool every (frame, line, position) of a channel
+    (rsr_bn_train_stats_lines), the normalise kernel also zeroes the padding rows, and the backward kernel takes the
+    gradient wrt the layer OUTPUT (include/rsrgan_b200.h, "batch_norm behind the convolutions")."""
+
+    STATE_KEYS = FCBN.STATE_KEYS
+
+    def _bn_init(self, bn, lines, chans):
+        self.bn, self.bn_H, self.bn_C = bool(bn), lines, chans
+        self.betaname, self.gname = self.scope + "/BatchNorm/beta", self.scope + "/BatchNorm/gamma"
+        self.state = None
+        if self.bn:
+            self.state = torch.zeros(6, packing.round_up(chans, 8), dtype=F32, device=self.net.h.device)
+            self.state[1].fill_(1.0)
+
+    def _bn_bufs(self, ctx, frames):
+        ws, rows = self.net.ws, frames * self.fl.S
+        return (ws.get((ctx, self.scope, "z32", frames), rows, self.cop, F32),
+                ws.get((ctx, self.scope, "bn_coef"), 8, self.cop, F32),
+                ws.get((ctx, self.scope, "bn_scratch"), 768, self.cop, F32))
+
+    def _bn_fwd(self, ctx, x_whole, taps16, frames):
+        net, h, fl = self.net, self.net.h, self.fl
+        y_whole, y = fl.buf(net, (ctx, self.scope, "y16", frames), frames, self.cop)
+        z32, coef, scratch = self._bn_bufs(ctx, frames)
+        h.gemm(fl.window(x_whole, frames, self.cip, self.W), taps16, frames * fl.S, self.cop, self.W * self.cip, b_mn=True,
+               out32=z32)
+        gamma, beta = net.P.view(self.gname), net.P.view(self.betaname)
+        if net.training:
+            h.bn_train_stats_lines(z32, frames, fl.S, fl.L, self.bn_H, self.bn_C, self.cop, gamma, beta, self.state, coef,
+                                   scratch, update_state=net.bn_update)
+        else:
+            h.bn_eval_coef_lines(self.cop, self.bn_H, self.bn_C, gamma, beta, self.state, coef)
+        h.affine_act_lines(z32, frames, fl.S, fl.L, self.cop, coef[0], coef[1], ACT_RELU, y)
+        return y_whole
+
+    def _bn_bwd(self, ctx, da_whole, frames):
+        """da_whole: gradient wrt this layer's OUTPUT -> (whole, data rows) of the gradient wrt its pre-activation"""
+        net, h, fl, P = self.net, self.net.h, self.fl, self.net.P
+        z32, coef, scratch = self._bn_bufs(ctx, frames)
+        dz_whole, dz = fl.buf(net, (ctx, self.scope, "dz16", frames), frames, self.cop)
+        h.bn_bwd_lines(da_whole[fl.GUARD:fl.GUARD + frames * fl.S], z32, frames, fl.S, fl.L, self.bn_H, self.bn_C, self.cop,
+                       ACT_RELU, coef, P.view(self.gname, "grad"), P.view(self.betaname, "grad"), dz, scratch)
+        return dz_whole, dz
+
+    def export_state(self):
+        out = {}
+        if self.bn:
+            st = self.state.detach().cpu().numpy()
+            for i, k in enumerate(self.STATE_KEYS):
+                out[self.scope + "/BatchNorm/" + k] = st[i, :self.bn_C].copy() if i < 4 else st[i, 0].copy()
+        return out
+
+    def load_state(self, d):
+        if self.bn:
+            for i, k in enumerate(self.STATE_KEYS):
+                v = torch.as_tensor(d[self.scope + "/BatchNorm/" + k], dtype=F32)
+                if i < 4:
+                    self.state[i].zero_()
+                    self.state[i, :self.bn_C] = v.to(self.state.device)
+                else:
+                    self.state[i].fill_(float(v))
+            self.state[1, self.bn_C:] = 1.0
+
+
 class ConvFrames(object):
     """The frame layout shared by the layers of the convolutional generator (models/rced.py:46-57, splice = 1):
     frame r = rows [r*S, r*S+S) of a channels-last 16-bit buffer, positions 0..L-1 data, rows L..S-1 zero (the
@@ -374,19 +441,27 @@ class ConvFrames(object):
                                 whole.storage_offset() + (self.GUARD - width // 2) * cp)
 
 
-class Conv1dSame(object):
+class Conv1dSame(ConvBN):
     """tf.contrib.layers.conv2d(inputs, C_out, [1, w], padding=SAME, activation_fn=relu) -- models/rced.py:94-101 with
-    splice = 1.  Forward, data gradient and weight gradient are rsr_gemm calls over overlapped views."""
+    splice = 1.  Forward, data gradient and weight gradient are rsr_gemm calls over overlapped views.
+    Without a normalizer `bwd` takes the gradient wrt this layer's PRE-activation and hands the producer the same; with
+    batch_norm (ConvBN) both are gradients wrt the layer OUTPUT."""
 
-    def __init__(self, net, scope, fl, width, c_in, c_out):
+    def __init__(self, net, scope, fl, width, c_in, c_out, bn=False):
         self.net, self.scope, self.fl, self.W, self.c_in, self.c_out = net, scope, fl, width, c_in, c_out
         self.cip, self.cop = packing.round_up(c_in, 8), packing.round_up(c_out, 8)
         self.wname, self.bname = scope + "/weights", scope + "/biases"
         h = net.h
         self.wflip16 = torch.zeros(width * self.cop, self.cip, dtype=h.h16, device=h.device)
+        self._bn_init(bn, 1, c_out)
+
+    def _tail_segs(self):
+        if self.bn:
+            return [params.fc_b(self.betaname, self.c_out), params.fc_b(self.gname, self.c_out)]
+        return [params.fc_b(self.bname, self.c_out)]
 
     def segs(self):
-        return [params.conv_w(self.wname, self.W, self.c_in, self.c_out), params.fc_b(self.bname, self.c_out)]
+        return [params.conv_w(self.wname, self.W, self.c_in, self.c_out)] + self._tail_segs()
 
     def refresh(self):
         """taps of the transposed convolution (data gradient) after every weight update"""
@@ -394,6 +469,8 @@ class Conv1dSame(object):
 
     def fwd(self, ctx, x_whole, frames):
         net, h, fl = self.net, self.net.h, self.fl
+        if self.bn:
+            return self._bn_fwd(ctx, x_whole, net.P.view(self.wname, "theta16"), frames)
         y_whole, y = fl.buf(net, (ctx, self.scope, "y16", frames), frames, self.cop)
         rows = frames * fl.S
         h.gemm(fl.window(x_whole, frames, self.cip, self.W), net.P.view(self.wname, "theta16"), rows, self.cop,
@@ -407,16 +484,21 @@ class Conv1dSame(object):
         net, h, fl = self.net, self.net.h, self.fl
         rows = frames * fl.S
         G = fl.GUARD
-        dy = dy_whole[G:G + rows]
+        if self.bn:
+            dy_whole, dy = self._bn_bwd(ctx, dy_whole, frames)
+        else:
+            dy = dy_whole[G:G + rows]
         dx_whole = None
         if want_dx:
             dx_whole, dx = fl.buf(net, (ctx, self.scope, "dx16", frames), frames, self.cip)
             h.gemm(fl.window(dy_whole, frames, self.cop, self.W), self.wflip16, rows, self.cip, self.W * self.cop,
-                   b_mn=True, dact_src=x_whole[G:G + rows], dact=ACT_RELU, out16=dx)
+                   b_mn=True, dact_src=None if self.bn else x_whole[G:G + rows],
+                   dact=ACT_NONE if self.bn else ACT_RELU, out16=dx)
         with h.side_stream():
             h.gemm(fl.window(x_whole, frames, self.cip, self.W), dy, self.W * self.cip, self.cop, rows, a_mn=True,
                    b_mn=True, beta=1.0, out32=net.P.view(self.wname, "grad"))
-            h.colsum16(dy, rows, self.cop, net.P.view(self.bname, "grad"), accumulate=True)
+            if not self.bn:
+                h.colsum16(dy, rows, self.cop, net.P.view(self.bname, "grad"), accumulate=True)
         return dx_whole
 
 
@@ -428,7 +510,7 @@ class Conv2dLines(Conv1dSame):
     the GEMM operands (taps, flipped taps, tiled bias) are derived after every update, and the gradient of the expansion is
     folded back over the tied copies in a fixed order."""
 
-    def __init__(self, net, scope, fl, kh, width, c_in, c_out, lines):
+    def __init__(self, net, scope, fl, kh, width, c_in, c_out, lines, bn=False):
         self.net, self.scope, self.fl, self.W, self.c_in, self.c_out = net, scope, fl, width, c_in, c_out
         self.kh, self.H = kh, lines
         self.cip, self.cop = packing.round_up(lines * c_in, 8), packing.round_up(lines * c_out, 8)
@@ -439,19 +521,23 @@ class Conv2dLines(Conv1dSame):
         self.dw2 = torch.zeros(width * self.cip, self.cop, dtype=F32, device=h.device)
         self.bias_t = torch.zeros(self.cop, dtype=F32, device=h.device)
         self.db_t = torch.zeros(self.cop, dtype=F32, device=h.device)
+        self._bn_init(bn, lines, c_out)
 
     def segs(self):
-        return [params.conv_w2d(self.wname, self.kh, self.W, self.c_in, self.c_out), params.fc_b(self.bname, self.c_out)]
+        return [params.conv_w2d(self.wname, self.kh, self.W, self.c_in, self.c_out)] + self._tail_segs()
 
     def refresh(self):
         h, P = self.net.h, self.net.P
         h.conv_toeplitz_expand(P.view(self.wname, "theta16"), self.kh, self.W, self.c_in, self.c_out, self.H, self.cip,
                                self.cop, self.taps16)
         h.conv_w_flip(self.taps16, self.W, self.cip, self.cop, self.wflip16)
-        h.vec_tile(P.view(self.bname), self.c_out, self.H, self.cop, self.bias_t)
+        if not self.bn:
+            h.vec_tile(P.view(self.bname), self.c_out, self.H, self.cop, self.bias_t)
 
     def fwd(self, ctx, x_whole, frames):
         net, h, fl = self.net, self.net.h, self.fl
+        if self.bn:
+            return self._bn_fwd(ctx, x_whole, self.taps16, frames)
         y_whole, y = fl.buf(net, (ctx, self.scope, "y16", frames), frames, self.cop)
         rows = frames * fl.S
         h.gemm(fl.window(x_whole, frames, self.cip, self.W), self.taps16, rows, self.cop, self.W * self.cip, b_mn=True,
@@ -463,21 +549,26 @@ class Conv2dLines(Conv1dSame):
         net, h, fl, P = self.net, self.net.h, self.fl, self.net.P
         rows = frames * fl.S
         G = fl.GUARD
-        dy = dy_whole[G:G + rows]
+        if self.bn:
+            dy_whole, dy = self._bn_bwd(ctx, dy_whole, frames)
+        else:
+            dy = dy_whole[G:G + rows]
         dx_whole = None
         if want_dx:
             dx_whole, dx = fl.buf(net, (ctx, self.scope, "dx16", frames), frames, self.cip)
             h.gemm(fl.window(dy_whole, frames, self.cop, self.W), self.wflip16, rows, self.cip, self.W * self.cop,
-                   b_mn=True, dact_src=x_whole[G:G + rows], dact=ACT_RELU, out16=dx)
+                   b_mn=True, dact_src=None if self.bn else x_whole[G:G + rows],
+                   dact=ACT_NONE if self.bn else ACT_RELU, out16=dx)
         with h.side_stream():
             h.fill32(self.dw2, 0.0)
             h.gemm(fl.window(x_whole, frames, self.cip, self.W), dy, self.W * self.cip, self.cop, rows, a_mn=True,
                    b_mn=True, beta=1.0, out32=self.dw2)
             h.conv_toeplitz_fold(self.dw2, self.kh, self.W, self.c_in, self.c_out, self.H, self.cip, self.cop,
                                  P.view(self.wname, "grad"))
-            h.fill32(self.db_t, 0.0)
-            h.colsum16(dy, rows, self.cop, self.db_t, accumulate=True)
-            h.vec_fold(self.db_t, self.c_out, self.H, P.view(self.bname, "grad"))
+            if not self.bn:
+                h.fill32(self.db_t, 0.0)
+                h.colsum16(dy, rows, self.cop, self.db_t, accumulate=True)
+                h.vec_fold(self.db_t, self.c_out, self.H, P.view(self.bname, "grad"))
         return dx_whole
 
 
@@ -486,8 +577,11 @@ class FCFrames(object):
     frames of the channels-last buffer (row pitch S*Cp, K = L*Cp; padded channels meet zero weight rows).  lines > 1:
     the frame is `lines` stacked lines stored as channels (Conv2dLines); the weight rows are re-indexed accordingly."""
 
-    def __init__(self, net, scope, fl, chans, n_out, lines=1):
+    def __init__(self, net, scope, fl, chans, n_out, lines=1, x_act=True):
+        """x_act: apply relu'(x) to the returned gradient (the producer wants the gradient wrt its pre-activation);
+        False when the producer is normalised and takes the gradient wrt its output (ConvBN)."""
         self.net, self.scope, self.fl, self.chans, self.n_out, self.H = net, scope, fl, chans, n_out, lines
+        self.x_act = x_act
         self.cp, self.outp = packing.round_up(lines * chans, 8), packing.round_up(n_out, 8)
         self.wname, self.bname = scope + "/weights", scope + "/biases"
 
@@ -517,8 +611,8 @@ class FCFrames(object):
         K = fl.L * self.cp
         dx_whole, _ = fl.buf(net, (ctx, self.scope, "dx16", frames), frames, self.cp)
         xf = self._frames(x_whole, frames)
-        h.gemm(dy16, net.P.view(self.wname, "theta16"), frames, K, self.outp, dact_src=xf, dact=ACT_RELU,
-               out16=self._frames(dx_whole, frames))
+        h.gemm(dy16, net.P.view(self.wname, "theta16"), frames, K, self.outp, dact_src=xf if self.x_act else None,
+               dact=ACT_RELU if self.x_act else ACT_NONE, out16=self._frames(dx_whole, frames))
         with h.side_stream():
             h.gemm(xf, dy16, K, self.outp, frames, a_mn=True, b_mn=True, beta=1.0,
                    out32=net.P.view(self.wname, "grad"))
@@ -555,18 +649,23 @@ class Net(object):
     def fcbn(self):
         return any(isinstance(l, FCBN) for l in self.layers)
 
+    @property
+    def has_bn_state(self):
+        """any layer with non-trainable batch_norm variables (FCBN, ConvBN) or a dropout stream to checkpoint"""
+        return self.fcbn or any(getattr(l, "bn", False) for l in self.layers)
+
     def bn_state_tf(self):
         """Non-trainable batch_norm variables keyed by their TF names (saved with the checkpoint, like tf.train.Saver
         saves every global variable, models/gan_rnn_placeholder.py:26-34)."""
         out = {}
         for l in self.layers:
-            if isinstance(l, FCBN):
+            if hasattr(l, "export_state"):
                 out.update(l.export_state())
         return out
 
     def load_bn_state_tf(self, d):
         for l in self.layers:
-            if isinstance(l, FCBN):
+            if hasattr(l, "load_state"):
                 l.load_state(d)
 
     def tick(self):
@@ -603,9 +702,6 @@ class Generator(Net):
         # rced builds keep_prob but never applies a dropout op (models/rced.py:73-77,102-103): a no-op there
         self.keep_prob = 1.0 if g_type == "rced" else float(keep_prob)
         self._dropping = False
-        if batch_norm and g_type == "rced":
-            # normalizer_fn=batch_norm on the nine conv2d layers (models/rced.py:63-71,94-97): not on this path yet
-            raise NotImplementedError("batch_norm on the rced convolutions is not implemented")
         # res_lstm_l / res_lstm_base build normalizer_params but never pass them on (models/res_lstm_l.py:58-67,81-82):
         # batch_norm is a no-op there, exactly as in the reference
         special = g_type == "dnn" and (batch_norm or self.keep_prob < 1.0)
@@ -651,11 +747,14 @@ class Generator(Net):
             def mk(net):
                 ch = (1,) + filt
                 name = lambda i: "g_model/Conv" + ("" if i == 0 else "_%d" % i)
+                bn = bool(batch_norm)       # normalizer_fn=batch_norm on the nine conv2d, not on the output layer (:94-113)
                 if H == 1:
-                    ls = [Conv1dSame(net, name(i), self.frames, wid[i], ch[i], ch[i + 1]) for i in range(len(filt))]
+                    ls = [Conv1dSame(net, name(i), self.frames, wid[i], ch[i], ch[i + 1], bn=bn) for i in range(len(filt))]
                 else:
-                    ls = [Conv2dLines(net, name(i), self.frames, H, wid[i], ch[i], ch[i + 1], H) for i in range(len(filt))]
-                return ls + [FCFrames(net, "g_model/fully_connected", self.frames, filt[-1], out_dim, lines=H)]
+                    ls = [Conv2dLines(net, name(i), self.frames, H, wid[i], ch[i], ch[i + 1], H, bn=bn)
+                          for i in range(len(filt))]
+                return ls + [FCFrames(net, "g_model/fully_connected", self.frames, filt[-1], out_dim, lines=H,
+                                      x_act=not bn)]
         else:
             raise ValueError("Unrecognized G type {}".format(g_type))   # models/gan_rnn_placeholder.py:131-132
         super(Generator, self).__init__(handle, mk, adam=True)

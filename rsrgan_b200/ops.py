@@ -318,6 +318,24 @@ class Handle(object):
                    _p(dz16), dz16.stride(0) if dz16 is not None else 0, _p(dz32),
                    dz32.stride(0) if dz32 is not None else 0, _p(scratch))
 
+    # batch_norm behind the convolutions of the frame layout (include/rsrgan_b200.h); state [6, lds] per channel
+    def bn_train_stats_lines(self, z32, frames, S, L, H, C, N, gamma, beta, state, coef, scratch, update_state=False):
+        self._call("rsr_bn_train_stats_lines", 2, self.h, _stream(), _p(z32), z32.stride(0), frames, S, L, H, C, N,
+                   _p(gamma), _p(beta), self.BN_EPS, _p(state), state.stride(0), self.BN_DECAY, self.BN_RENORM_DECAY,
+                   int(update_state), _p(coef), _p(scratch))
+
+    def bn_eval_coef_lines(self, N, H, C, gamma, beta, state, coef):
+        self._call("rsr_bn_eval_coef_lines", 1, self.h, _stream(), N, H, C, _p(gamma), _p(beta), self.BN_EPS, _p(state),
+                   state.stride(0), _p(coef))
+
+    def affine_act_lines(self, z32, frames, S, L, N, A, Bc, act, out16):
+        self._call("rsr_affine_act_lines", 1, self.h, _stream(), _p(z32), z32.stride(0), frames, S, L, N, _p(A), _p(Bc),
+                   act, _p(out16), out16.stride(0))
+
+    def bn_bwd_lines(self, da16, z32, frames, S, L, H, C, N, act, coef, dgamma, dbeta, dz16, scratch):
+        self._call("rsr_bn_bwd_lines", 3, self.h, _stream(), _p(da16), da16.stride(0), _p(z32), z32.stride(0), frames, S,
+                   L, H, C, N, act, _p(coef), _p(dgamma), _p(dbeta), _p(dz16), dz16.stride(0), _p(scratch))
+
     def rng_tick(self, rng):
         self._call("rsr_rng_tick", 1, self.h, _stream(), _p(rng))
 

@@ -396,6 +396,65 @@ class FakeHandle(object):
         if dz32 is not None:
             dz32[:rows, :N] = g
 
+    # batch_norm behind the convolutions of the frame layout: channel ch of line l = column l * C + ch, data rows r % S < L
+    def _live(self, frames, S, L):
+        return (torch.arange(frames * S) % S) < L
+
+    def bn_train_stats_lines(self, z32, frames, S, L, H, C, N, gamma, beta, state, coef, scratch, update_state=False):
+        self.launches += 2
+        z = z32[:frames * S, :H * C][self._live(frames, S, L)].reshape(-1, C)
+        mean = z.mean(0)
+        var = ((z - mean) ** 2).mean(0)
+        std = torch.sqrt(var + self.BN_EPS)
+        mm, mv, rm, rs, rmw, rsw = (state[i, :C] for i in range(6))
+        denom = rs + (1 - rsw) * std
+        r, d = std / denom, (mean - (rm + (1 - rmw) * mean)) / denom
+        A = r * gamma[:C] / std
+        k = torch.stack([A, d * gamma[:C] + beta[:C] - mean * A, mean, 1.0 / std, r, d])
+        coef[:, :N] = 0.0
+        coef[:6, :H * C] = k.repeat(1, H)
+        if update_state:
+            kk = 1 - self.BN_RENORM_DECAY
+            rm -= (rm - mean) * kk
+            rmw -= (rmw - 1) * kk
+            rs -= (rs - std) * kk
+            rsw -= (rsw - 1) * kk
+            mm -= (mm - rm / rmw) * (1 - self.BN_DECAY)
+            mv -= (mv - ((rs / rsw) ** 2 - self.BN_EPS)) * (1 - self.BN_DECAY)
+
+    def bn_eval_coef_lines(self, N, H, C, gamma, beta, state, coef):
+        self.launches += 1
+        inv = torch.rsqrt(state[1, :C] + self.BN_EPS)
+        k = torch.stack([gamma[:C] * inv, beta[:C] - state[0, :C] * gamma[:C] * inv, state[0, :C], inv,
+                         torch.ones_like(inv), torch.zeros_like(inv)])
+        coef[:, :N] = 0.0
+        coef[:6, :H * C] = k.repeat(1, H)
+
+    def affine_act_lines(self, z32, frames, S, L, N, A, Bc, act, out16):
+        self.launches += 1
+        rows = frames * S
+        a = _act(z32[:rows, :N] * (A[:N] if A is not None else 1.0) + Bc[:N], act)
+        out16[:rows, :N] = torch.where(self._live(frames, S, L)[:, None], a, torch.zeros_like(a)).to(self.h16)
+
+    def bn_bwd_lines(self, da16, z32, frames, S, L, H, C, N, act, coef, dgamma, dbeta, dz16, scratch):
+        self.launches += 3
+        rows, live = frames * S, self._live(frames, S, L)[:, None]
+        z = z32[:rows, :N]
+        g = da16[:rows, :N].float() * _dact(z * coef[0, :N] + coef[1, :N], act)
+        g = torch.where(live, g, torch.zeros_like(g))
+        xh = (z - coef[2, :N]) * coef[3, :N]
+        s1 = g[:, :H * C].sum(0).reshape(H, C).sum(0)
+        s2 = (g * xh)[:, :H * C].sum(0).reshape(H, C).sum(0)
+        if dbeta is not None:
+            dbeta[:C] += s1
+        if dgamma is not None:
+            dgamma[:C] += coef[4, :C] * s2 + coef[5, :C] * s1
+        n = float(frames * L * H)
+        m1, m2 = torch.zeros(N), torch.zeros(N)
+        m1[:H * C], m2[:H * C] = (s1 / n).repeat(H), (s2 / n).repeat(H)
+        g = coef[0, :N] * (g - m1 - xh * m2)
+        dz16[:rows, :N] = torch.where(live, g, torch.zeros_like(g)).to(self.h16)
+
     def rng_tick(self, rng):
         self.launches += 1
         rng[1] += 1

@@ -197,6 +197,84 @@ def test_bn_shape_errors(h):
                           torch.zeros(8, 8, dtype=h.h16, device=dev))
 
 
+# frame layout: (frames, S, L), H lines x C channels, N columns (>= H C: zero-coefficient padding columns)
+@pytest.mark.parametrize("frames,S,L,H,C,N", [(3, 8, 5, 1, 12, 16), (256, 264, 257, 1, 32, 32), (48, 48, 40, 11, 12, 136),
+                                              (700, 48, 40, 11, 20, 224), (1, 16, 16, 2, 4, 8)])
+@pytest.mark.parametrize("update", [False, True])
+def test_bn_lines_entries_against_oracle(h, frames, S, L, H, C, N, update):
+    """batch_norm behind the convolutions: channel ch of line l = column l * C + ch, data rows r % S < L.  Statistics,
+    UPDATE_OPS, normalise (+ zeroed padding rows), backward and the eval coefficients against the float64 oracle run on
+    the compacted (frames * L * H, C) matrix."""
+    dev, rng = h.device, np.random.default_rng(frames + S + H * C)
+    rows, HC = frames * S, H * C
+    z = (rng.standard_normal((rows, N)) * 0.7 + 2.0).astype(np.float32)          # padding rows / columns hold junk
+    z[:, :HC] = (rng.standard_normal((rows, HC)) * np.tile(0.5 + rng.random(C), H) + np.tile(rng.standard_normal(C), H))
+    live = (np.arange(rows) % S) < L
+    zc = z[live][:, :HC].astype(np.float64).reshape(-1, C)                        # (frame, position, line) x channel
+    gamma, beta = (1 + 0.2 * rng.standard_normal(C)).astype(np.float32), (0.3 * rng.standard_normal(C)).astype(np.float32)
+    st = warm(O.bn_init_state(C), rng)
+    Cs = -(-C // 8) * 8
+    state = torch.zeros(6, Cs, dtype=F32, device=dev)
+    state[:, :C] = torch.tensor(state_arrays(st, C), device=dev)
+    state0 = state.clone()
+    zt = torch.tensor(z, device=dev)
+    gam_t, bet_t = torch.tensor(gamma, device=dev), torch.tensor(beta, device=dev)
+    coef = torch.full((8, N), 7.0, dtype=F32, device=dev)
+    scratch = torch.zeros(768, N, dtype=F32, device=dev)
+    h.bn_train_stats_lines(zt, frames, S, L, H, C, N, gam_t, bet_t, state, coef, scratch, update_state=update)
+    st_ref = copy.deepcopy(st)
+    y_ref, cache = O.bn_renorm_train_fwd(zc, gamma.astype(np.float64), beta.astype(np.float64), st_ref, update=update)
+    c = coef.cpu().numpy().astype(np.float64)
+    for l in range(H):                                   # every line of a channel holds the channel's coefficients
+        assert np.array_equal(c[:6, l * C:(l + 1) * C], c[:6, :C])
+    assert np.all(c[:6, HC:] == 0.0)
+    assert rel(c[2, :C], zc.mean(0)) < 1e-5 and rel(c[4, :C], cache[1]) < 1e-5
+    assert rel(zc * c[0, :C] + c[1, :C], y_ref) < 2e-5
+    s = state.cpu().numpy()
+    for i, k in enumerate(O.BN_STATE_KEYS):
+        assert rel(s[i, :C] + 1.0, np.broadcast_to(st_ref[k], (C,)) + 1.0) < 1e-5, k
+    if not update:
+        assert torch.equal(state, state0)
+    # normalise + ReLU, padding rows zeroed
+    y16 = torch.full((rows, N), 3.0, dtype=h.h16, device=dev)
+    h.affine_act_lines(zt, frames, S, L, N, coef[0], coef[1], 1, y16)
+    y = y16.float().cpu().numpy()
+    assert np.all(y[~live] == 0.0) and np.all(y[:, HC:] == 0.0)
+    assert rel(y[live][:, :HC].reshape(-1, C), np.maximum(y_ref, 0.0)) < tol(h, 1e-3, 8e-3)
+    # backward: da holds junk on the padding rows
+    da = (rng.standard_normal((rows, N)) * 0.1).astype(np.float32)
+    da16 = torch.tensor(da, device=dev).to(h.h16)
+    dac = da16.double().cpu().numpy()[live][:, :HC].reshape(-1, C)
+    dgam = torch.full((Cs,), 0.5, dtype=F32, device=dev)
+    dbet = torch.full((Cs,), -0.25, dtype=F32, device=dev)
+    dz16 = torch.full((rows, N), 3.0, dtype=h.h16, device=dev)
+    h.bn_bwd_lines(da16, zt, frames, S, L, H, C, N, 1, coef, dgam, dbet, dz16, scratch)
+    torch.cuda.synchronize()
+    dz, dgamma, dbeta = O.bn_renorm_train_bwd(O.act_bwd(y_ref, dac, O.ACT_RELU), cache)
+    assert rel(dgam.cpu().numpy()[:C] - 0.5, dgamma) < 1e-4 and rel(dbet.cpu().numpy()[:C] + 0.25, dbeta) < 1e-4
+    got = dz16.float().cpu().numpy()
+    assert np.all(got[~live] == 0.0) and np.all(got[:, HC:] == 0.0)
+    assert rel(got[live][:, :HC].reshape(-1, C), dz) < tol(h, 1e-3, 8e-3)
+    # inference coefficients from the moving averages
+    h.bn_eval_coef_lines(N, H, C, gam_t, bet_t, state, coef)
+    c = coef.cpu().numpy().astype(np.float64)
+    st_now = OrderedDict((k, s[i, :C].astype(np.float64)) for i, k in enumerate(O.BN_STATE_KEYS))
+    assert rel(zc * c[0, :C] + c[1, :C], O.bn_eval_fwd(zc, gamma.astype(np.float64), beta.astype(np.float64), st_now)) < 1e-5
+    assert np.array_equal(c[:6, (H - 1) * C:HC], c[:6, :C]) and np.all(c[:6, HC:] == 0.0)
+
+
+def test_bn_lines_shape_errors(h):
+    from rsrgan_b200._lib import RsrError
+    dev = h.device
+    z = torch.zeros(16, 8, dtype=F32, device=dev)
+    v = torch.zeros(8, dtype=F32, device=dev)
+    st, coef, scr = torch.zeros(6, 8, device=dev), torch.zeros(8, 8, device=dev), torch.zeros(768, 8, device=dev)
+    with pytest.raises(RsrError, match="RSR_E_SHAPE"):           # fewer columns than H * C
+        h.bn_train_stats_lines(z, 2, 8, 5, 3, 4, 8, v, v, st, coef, scr)
+    with pytest.raises(RsrError, match="RSR_E_SHAPE"):           # S < L
+        h.bn_train_stats_lines(z, 2, 4, 5, 1, 8, 8, v, v, st, coef, scr)
+
+
 # ------------------------------------------------------------------ model level
 def tf32(p):
     return OrderedDict((k, np.asarray(v, np.float32)) for k, v in p.items())
@@ -388,3 +466,45 @@ def test_golden_mse_dnn_bn():
     # weights after three Adam steps carry the sign noise of near-zero gradients (see the reference-driver-shape test),
     # hence the loose bar on the inference output; the statistics and the per-step losses are tight
     _run_golden_mse_dnn_bn(None, 5e-3, 1e-3, 5e-2)
+
+
+@pytest.mark.parametrize("splice,N,bins", [(1, 256, 257), (11, 48, 40)])
+def test_rced_batch_norm_against_oracle(splice, N, bins):
+    """models/rced.py:63-71,94-97 under DNNTrainer (run_dnn.sh:129-140 shape for splice 11): batch_norm on the nine
+    convolutions.  Loss, UPDATE_OPS and the inference graph tightly; raw gradients at the bar measured for nine stacked
+    normalised layers with 16-bit operands (tests/test_batchnorm_host.py shows the wiring exact with fp32 operands)."""
+    from rsrgan_b200.dnn_trainer import DNNTrainer
+    rng = np.random.default_rng(31 + splice)
+    ctx = (splice - 1) // 2
+    args = Namespace(g_type="rced", batch_size=N, input_dim=bins, left_context=ctx, right_context=ctx, output_dim=40,
+                     batch_norm=True, g_learning_rate=0.0, seed=11, dtype="f16")
+    m = DNNTrainer(None, args, ["/gpu:0"])
+    gp = perturb_bn(O.init_g_rced(rng, in_dim=bins, out_dim=40, splice=splice, batch_norm=True), rng)
+    assert list(m.G.P.segs) == list(gp)
+    m.load_params(tf32(gp))
+    bst = O.init_bn_state(gp)
+    x = rng.standard_normal((N, splice * bins)).astype(np.float32)
+    y = rng.standard_normal((N, 40)).astype(np.float32)
+    # two steps with lr = 0: the second one sees warmed renorm averages (r != 1, d != 0)
+    for step in range(2):
+        L, G, _ = O.mse_losses_and_grads(gp, "rced", x.astype(np.float64), y.astype(np.float64),
+                                         g_opts=dict(bn_state=bst, update=True))
+        out = m.train_step(x, y)
+        assert out["g_mse_loss"] == pytest.approx(L["g_mse_loss"], rel=3e-3)
+    gs = m._gscale(N)
+    gg = m.G.P.export_tf("grad")
+    for k in G:
+        assert rel(gg[k] / gs, G[k]) < 2e-1, k
+    mine = m.G.bn_state_tf()
+    assert set(mine) == set(bst)
+    for k in bst:
+        assert rel(np.asarray(mine[k]) + 1.0, np.asarray(bst[k]) + 1.0) < 1e-3, k
+    cv = DNNTrainer(None, args, ["/gpu:0"], cross_validation=True, share=m)
+    g = cv.generate(x).cpu().numpy()
+    g_ref, _ = O.g_rced_fwd(gp, x.astype(np.float64), None, opts=dict(bn_state=bst, train=False))
+    d = float(np.sqrt(((g - g_ref) ** 2).mean()))
+    assert d < 1e-3 and rel(g, g_ref) < 5e-3, (d, rel(g, g_ref))
+    # a real Adam step moves the weights and lowers the loss
+    m.g_learning_rate = 1e-3
+    losses = [m.train_step(x, y)["g_mse_loss"] for _ in range(4)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0], losses

@@ -351,3 +351,53 @@ def _run_golden_mse_dnn_bn(handle, tol_w, tol_state, tol_out):
 
 def test_golden_mse_dnn_bn_host_wiring():
     _run_golden_mse_dnn_bn(FakeHandle("f16"), 5e-3, 1e-3, 5e-2)
+
+
+def _double(operands):
+    fh = FakeHandle("f16")
+    if operands == "f32":
+        fh.h16 = torch.float32        # the double with fp32 GEMM operands: isolates the wiring from 16-bit rounding
+    return fh
+
+
+@pytest.mark.parametrize("operands,gbar", [("f32", 1e-3), ("f16", 2e-1)])
+def test_rced_batch_norm_host_wiring_matches_oracle(operands, gbar):
+    """models/rced.py:63-71,94-97: normalizer_fn=batch_norm on the nine convolutions (no biases; moments pooled over
+    frames and positions of a channel).  nets.ConvBN through the CPU test double: loss, every raw gradient, the
+    UPDATE_OPS and the inference graph against the oracle.  The gradient of a normalised layer is orthogonal to (1, x_hat),
+    so the weight gradients behind it are sums with heavy cancellation: with 16-bit operands nine such layers measure
+    2e-2 (Conv_8) .. 1.6e-1 (Conv_1) relative, with fp32 operands the same wiring is exact to < 1e-4."""
+    rng = np.random.default_rng(9)
+    N, bins = 12, 24
+    args = Namespace(g_type="rced", batch_size=N, input_dim=bins, output_dim=8, batch_norm=True, g_learning_rate=0.0, seed=3)
+    m = DNNTrainer(None, args, ["/gpu:0"], handle=_double(operands))
+    assert m.G.has_bn_state and not m.G.fcbn
+    gp = O.init_g_rced(rng, in_dim=bins, out_dim=8, batch_norm=True)
+    for k in gp:
+        if "BatchNorm" in k:
+            gp[k] = gp[k] + 0.1 * rng.standard_normal(gp[k].shape)
+    assert list(m.G.P.segs) == list(gp) and "g_model/Conv/biases" not in gp
+    m.load_params(tf32(gp))
+    bst = warm_state(O.init_bn_state(gp), rng)
+    m.G.load_bn_state_tf(bst)
+    x, y = rng.standard_normal((N, bins)).astype(np.float32), rng.standard_normal((N, 8)).astype(np.float32)
+    opts = dict(bn_state=bst, update=True)
+    L, G, _ = O.mse_losses_and_grads(gp, "rced", x.astype(np.float64), y.astype(np.float64), g_opts=opts)
+    out = m.train_step(x, y)
+    assert out["g_mse_loss"] == pytest.approx(L["g_mse_loss"], rel=3e-3)
+    gs = m._gscale(N)
+    gg = m.G.P.export_tf("grad")
+    for k in G:
+        assert rel(gg[k] / gs, G[k]) < gbar, k
+    mine = m.G.bn_state_tf()
+    assert set(mine) == set(bst)
+    for k in bst:
+        assert rel(np.asarray(mine[k]) + 1.0, np.asarray(bst[k]) + 1.0) < 2e-3, k
+    cv = DNNTrainer(None, args, ["/gpu:0"], cross_validation=True, share=m)
+    g_ref, _ = O.g_rced_fwd(gp, x.astype(np.float64), None, opts=dict(bn_state=bst, train=False))
+    assert rel(cv.generate(x).numpy(), g_ref) < 5e-3
+    sd = m.state_dict()
+    m2 = DNNTrainer(None, args, ["/gpu:0"], handle=_double(operands))
+    m2.load_state_dict(sd)
+    for k, v in m2.G.bn_state_tf().items():
+        assert np.array_equal(v, mine[k]), k
