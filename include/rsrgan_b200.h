@@ -380,6 +380,30 @@ int rsr_ark_decompress(rsr_handle* h, void* stream, const void* col_hdr, const v
  * checkpoints (models/gan_rnn_placeholder.py:26-60).  Needs no device.  Returns the checksum (not a status). */
 unsigned int rsr_crc32c_host(const void* data_host, unsigned long long n, unsigned int crc);
 
+/* average_gradients over NVLink peer memory ------------------------------------------------
+ * utils/ops.py:343-376 (the tower mean behind both optimizers, models/gan_rnn_placeholder.py:144-160) for one rank per
+ * GPU on one node: the flat gradient buffers live in blocks the other ranks have opened through CUDA IPC, and ONE
+ * kernel per update sums them in place over NVLink -- rank r reads slice r of all `world` buffers, adds them in rank
+ * order 0..world-1 and stores the sum into all of them, between two flag barriers (csrc/peer_allreduce.cu).  The result
+ * is the SUM (the 1/world of the mean is the gmul of rsr_seg_sumsq / rsr_clip_*_ema) and is bit-identical on every rank.
+ * Stream-ordered like every other entry and capturable into a CUDA graph; every rank must issue the same calls in the
+ * same order.  A barrier that waits longer than ~2 s gives up and raises the block's error flag (rsr_peer_error).
+ *   rsr_peer_alloc   cudaMalloc of RSR_PEER_HEADER_BYTES + data_bytes (zeroed) + its 64-byte IPC handle
+ *   rsr_peer_open    maps another rank's block from its handle;  rsr_peer_close unmaps it;  rsr_peer_free releases one's own
+ *   rsr_peer_allreduce  blocks[world] = every rank's block (own at [rank]); the buffer is n_floats (multiple of 4) at byte
+ *                    offset data_off_bytes (multiple of 16, >= RSR_PEER_HEADER_BYTES) of EVERY block; world in {1, 2, 4, 8};
+ *                    max_blocks caps the grid (0 = 148; identical on all ranks) */
+#define RSR_PEER_MAX_RANKS 8
+#define RSR_PEER_HEADER_BYTES 16384
+#define RSR_PEER_IPC_HANDLE_BYTES 64
+int rsr_peer_alloc(rsr_handle* h, long long data_bytes, void** block, unsigned char* ipc_handle);
+int rsr_peer_open(rsr_handle* h, const unsigned char* ipc_handle, void** block);
+int rsr_peer_close(rsr_handle* h, void* block);
+int rsr_peer_free(rsr_handle* h, void* block);
+int rsr_peer_error(rsr_handle* h, const void* block, int* error);
+int rsr_peer_allreduce(rsr_handle* h, void* stream, void* const* blocks, int rank, int world, long long data_off_bytes,
+                       long long n_floats, int max_blocks);
+
 /* misc ---------------------------------------------------------------------------------- */
 /* dst[c, r] = src[r, c] for r < rows, c < cols (16-bit elements; other elements of dst untouched):
  * keeps the K_x^T operand of rsr_lstmp_fused_fwd in step with the updated weights. */
