@@ -336,6 +336,10 @@ def main():
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         out["ranks_in_sync"] = bool(torch.equal(lo, hi))
+        # gradient averaging: one kernel over NVLink peer memory inside the schedule's CUDA graph, or NCCL between segments
+        out["allreduce"] = "peer" if model.peer is not None else "nccl"
+        if model.peer is not None:
+            out["allreduce_error"] = int(model.peer.error())
     if rank == 0:
         out["clocks"] = sampler.summary()
         if world == 1 and not a.no_cpu_baseline:

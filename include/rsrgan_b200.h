@@ -387,7 +387,7 @@ unsigned int rsr_crc32c_host(const void* data_host, unsigned long long n, unsign
  * order 0..world-1 and stores the sum into all of them, between two flag barriers (csrc/peer_allreduce.cu).  The result
  * is the SUM (the 1/world of the mean is the gmul of rsr_seg_sumsq / rsr_clip_*_ema) and is bit-identical on every rank.
  * Stream-ordered like every other entry and capturable into a CUDA graph; every rank must issue the same calls in the
- * same order.  A barrier that waits longer than ~2 s gives up and raises the block's error flag (rsr_peer_error).
+ * same order.  A barrier that waits longer than ~30 s gives up and raises the block's error flag (rsr_peer_error).
  *   rsr_peer_alloc   cudaMalloc of RSR_PEER_HEADER_BYTES + data_bytes (zeroed) + its 64-byte IPC handle
  *   rsr_peer_open    maps another rank's block from its handle;  rsr_peer_close unmaps it;  rsr_peer_free releases one's own
  *   rsr_peer_allreduce  blocks[world] = every rank's block (own at [rank]); the buffer is n_floats (multiple of 4) at byte

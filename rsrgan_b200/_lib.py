@@ -49,6 +49,12 @@ SIGNATURES = {
     "rsr_lstmp_rec_fwd": [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, cf, vp, vp, vp],
     "rsr_lstmp_fused_fwd": [vp, vp, ci, ci, ci, ci, vp, ci, vp, vp, vp, vp, vp, vp, cf, vp, vp, vp],
     "rsr_transpose16": [vp, vp, vp, ci, ci, ci, vp, ci],
+    "rsr_peer_alloc": [vp, cll, C.POINTER(vp), vp],
+    "rsr_peer_open": [vp, vp, C.POINTER(vp)],
+    "rsr_peer_close": [vp, vp],
+    "rsr_peer_free": [vp, vp],
+    "rsr_peer_error": [vp, vp, C.POINTER(ci)],
+    "rsr_peer_allreduce": [vp, vp, C.POINTER(vp), ci, ci, cll, cll, ci],
     "rsr_lstmp_rec_bwd": [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "rsr_lsgan_mse_losses": [vp, vp, vp, vp, ci, cll, ci, vp, ci, vp, ci, cll, ci, cf, cf, cf, cf,
                              vp, vp, vp, vp, ci, vp, ci],

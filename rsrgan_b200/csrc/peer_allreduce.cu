@@ -27,7 +27,8 @@ namespace {
 constexpr int PEER_MAX = RSR_PEER_MAX_RANKS;
 constexpr int PEER_MAX_BLOCKS = 148;
 constexpr int PEER_THREADS = 512;
-constexpr long long PEER_TIMEOUT_CYCLES = 4000000000LL;     // ~2 s: a dead peer must not hang the GPU
+constexpr long long PEER_TIMEOUT_CYCLES = 60000000000LL;    // ~30 s (ranks may be seconds apart around a graph capture);
+                                                            // a dead peer must not hang the GPU for good
 
 struct PeerHeader {
     uint32_t flags[PEER_MAX_BLOCKS][PEER_MAX];

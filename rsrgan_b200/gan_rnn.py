@@ -215,6 +215,17 @@ class GAN_RNN(Model):
             for net in (self.G, self.D):
                 if net is not None:
                     net.rng[0] = int(_arg(args, "seed", 1234))
+        # average_gradients (utils/ops.py:343-376) over NVLink peer memory: the gradient stores move into a block the
+        # other ranks of the node have mapped, and the all-reduce is one kernel of the schedule (rsrgan_b200/peer.py);
+        # None -> torch.distributed.all_reduce (CPU test double, other world sizes, no peer access)
+        self.peer = share.peer if share is not None else None
+        if share is None and self.world > 1 and not cross_validation:
+            from . import peer
+            stores = [n.P for n in (self.G, self.D) if n is not None]
+            self.peer = peer.try_create(self.h, self.dist, [P.n for P in stores])
+            if self.peer is not None:
+                for i, P in enumerate(stores):
+                    P.grad = self.peer.buffer(i)
         self.g_learning_rate = float(_arg(args, "g_learning_rate", 0.0003))
         self.d_learning_rate = float(_arg(args, "d_learning_rate", 0.001))
         dev = self.h.device
@@ -429,6 +440,8 @@ class GAN_RNN(Model):
         batches -- skip-and-back-off as in mixed-precision training practice; the fp32 reference has no counterpart
         because it cannot overflow there.  Returns the number of newly skipped updates.  Synchronises; the trainer
         calls it where it reads the losses anyway."""
+        if self.peer is not None and self.peer.error():
+            raise RuntimeError("peer all-reduce: a barrier timed out (a rank died or issued a different call sequence)")
         if self.h.dtype_id == ops._lib.RSR_DTYPE_BF16:
             return 0
         now = sum(self.skipped_updates())
@@ -459,7 +472,9 @@ class GAN_RNN(Model):
                 n.tick()                                   # their masks from the current tick
         if self.world > 1:
             # utils/ops.py:343-376 average_gradients: sum over ranks here, 1/N folded into the update kernel
-            if self._cap is not None and not self.graph_nccl:
+            if self.peer is not None:
+                self.peer.all_reduce(P.grad)     # one kernel over peer memory; part of the captured schedule
+            elif self._cap is not None and not self.graph_nccl:
                 # graph capture in progress: the collective stays OUTSIDE the graphs -- close the segment, run the
                 # all-reduce eagerly (keeps every rank's collective sequence aligned), open the next segment
                 self._cap_end(P.grad)

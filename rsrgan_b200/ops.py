@@ -294,6 +294,37 @@ class Handle(object):
                    _p(dact_src), dact_src.stride(0) if dact_src is not None else 0, dact, _p(dx16), dx16.stride(0),
                    work=2.0 * rows * K)
 
+    # ------------------------------------------------------ gradient all-reduce over peer memory (rsrgan_b200/peer.py)
+    PEER_HEADER_BYTES, PEER_IPC_HANDLE_BYTES = 16384, 64
+
+    def peer_alloc(self, data_bytes):
+        """-> (block address, 64-byte IPC handle)"""
+        blk, hd = C.c_void_p(), C.create_string_buffer(self.PEER_IPC_HANDLE_BYTES)
+        check(self.lib.rsr_peer_alloc(self.h, int(data_bytes), C.byref(blk), C.cast(hd, C.c_void_p)), "rsr_peer_alloc")
+        return int(blk.value), hd.raw
+
+    def peer_open(self, ipc_handle):
+        blk = C.c_void_p()
+        hd = C.create_string_buffer(bytes(ipc_handle), self.PEER_IPC_HANDLE_BYTES)
+        check(self.lib.rsr_peer_open(self.h, C.cast(hd, C.c_void_p), C.byref(blk)), "rsr_peer_open")
+        return int(blk.value)
+
+    def peer_close(self, block):
+        check(self.lib.rsr_peer_close(self.h, C.c_void_p(block)), "rsr_peer_close")
+
+    def peer_free(self, block):
+        check(self.lib.rsr_peer_free(self.h, C.c_void_p(block)), "rsr_peer_free")
+
+    def peer_error(self, block):
+        e = C.c_int(0)
+        check(self.lib.rsr_peer_error(self.h, C.c_void_p(block), C.byref(e)), "rsr_peer_error")
+        return int(e.value)
+
+    def peer_allreduce(self, blocks, rank, data_off_bytes, n_floats, max_blocks=0):
+        arr = (C.c_void_p * len(blocks))(*blocks)
+        self._call("rsr_peer_allreduce", 1 if len(blocks) > 1 else 0, self.h, _stream(), arr, rank, len(blocks),
+                   int(data_off_bytes), int(n_floats), int(max_blocks))
+
     # ------------------------------------------------------ batch_norm(renorm) / dropout
     BN_EPS, BN_DECAY, BN_RENORM_DECAY = 1e-3, 0.999, 0.99     # contrib batch_norm defaults (TF 1.4)
 
