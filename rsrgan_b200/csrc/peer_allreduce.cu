@@ -64,13 +64,21 @@ __device__ __forceinline__ void st_peer(float4* p, const float4 v) {
                  : "memory");
 }
 
+// P.base[] indexed by a run-time value would put the parameter struct on the local stack: select with constant indices
 template <int N>
-__device__ __forceinline__ void peer_barrier(const PeerParams& P, uint32_t target) {
+__device__ __forceinline__ char* base_of(const PeerParams& P, int r) {
+    char* b = P.base[0];
+#pragma unroll
+    for (int q = 1; q < N; ++q) b = r == q ? P.base[q] : b;
+    return b;
+}
+
+template <int N>
+__device__ __forceinline__ void peer_barrier(const PeerParams& P, PeerHeader* mine, uint32_t target) {
     __syncthreads();                                   // this block's loads / stores precede the release below
     const int p = threadIdx.x;
     if (p < N) {
-        PeerHeader* theirs = reinterpret_cast<PeerHeader*>(P.base[p]);
-        PeerHeader* mine = reinterpret_cast<PeerHeader*>(P.base[P.rank]);
+        PeerHeader* theirs = reinterpret_cast<PeerHeader*>(base_of<N>(P, p));
         st_release_sys(&theirs->flags[blockIdx.x][P.rank], target);
         const uint32_t* w = &mine->flags[blockIdx.x][p];
         const long long t0 = clock64();
@@ -81,26 +89,38 @@ __device__ __forceinline__ void peer_barrier(const PeerParams& P, uint32_t targe
     __syncthreads();
 }
 
-template <int N>
+// U float4 per thread and pass, all N * U loads issued before the first add: the pass is one NVLink round trip deep
+// (N * U = 8 -> 64 KB in flight per SM, ~9 MB per GPU against the ~3 MB that 900 GB/s x 3 us need)
+template <int N, int U>
 __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(PeerParams P) {
-    PeerHeader* mine = reinterpret_cast<PeerHeader*>(P.base[P.rank]);
+    PeerHeader* mine = reinterpret_cast<PeerHeader*>(base_of<N>(P, P.rank));
     const uint32_t c0 = mine->count[blockIdx.x];
-    peer_barrier<N>(P, c0 + 1);                        // every rank's gradients are complete
+    peer_barrier<N>(P, mine, c0 + 1);                  // every rank's gradients are complete
     const long long per = (P.n4 + N - 1) / N;
     const long long lo = (long long)P.rank * per;
     const long long hi = lo + per < P.n4 ? lo + per : P.n4;
-    for (long long i = lo + (long long)blockIdx.x * PEER_THREADS + threadIdx.x; i < hi;
-         i += (long long)gridDim.x * PEER_THREADS) {
-        float4 v[N];
+    const long long stride = (long long)gridDim.x * PEER_THREADS;
+    for (long long i0 = lo + (long long)blockIdx.x * PEER_THREADS + threadIdx.x; i0 < hi; i0 += stride * U) {
+        float4 v[U][N];
 #pragma unroll
-        for (int p = 0; p < N; ++p) v[p] = ld_peer(reinterpret_cast<const float4*>(P.base[p] + P.data_off) + i);
-        float4 a = v[0];
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
 #pragma unroll
-        for (int p = 1; p < N; ++p) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
+            for (int p = 0; p < N; ++p)
+                if (i < hi) v[u][p] = ld_peer(reinterpret_cast<const float4*>(P.base[p] + P.data_off) + i);
+        }
 #pragma unroll
-        for (int p = 0; p < N; ++p) st_peer(reinterpret_cast<float4*>(P.base[p] + P.data_off) + i, a);
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= hi) break;
+            float4 a = v[u][0];
+#pragma unroll
+            for (int p = 1; p < N; ++p) { a.x += v[u][p].x; a.y += v[u][p].y; a.z += v[u][p].z; a.w += v[u][p].w; }
+#pragma unroll
+            for (int p = 0; p < N; ++p) st_peer(reinterpret_cast<float4*>(P.base[p] + P.data_off) + i, a);
+        }
     }
-    peer_barrier<N>(P, c0 + 2);                        // every rank's sums have landed in every buffer
+    peer_barrier<N>(P, mine, c0 + 2);                  // every rank's sums have landed in every buffer
     if (threadIdx.x == 0) mine->count[blockIdx.x] = c0 + 2;
 }
 
@@ -165,14 +185,15 @@ extern "C" int rsr_peer_allreduce(rsr_handle* h, void* stream, void* const* bloc
     P.data_off = data_off_bytes; P.n4 = n_floats / 4; P.rank = rank;
     // the SAME grid on every rank (flags are indexed by block): a function of the size and world only
     const long long per = (P.n4 + world - 1) / world;
-    long long grid = (per + PEER_THREADS - 1) / PEER_THREADS;
+    const int unroll = 8 / world;
+    long long grid = (per + (long long)PEER_THREADS * unroll - 1) / ((long long)PEER_THREADS * unroll);
     const int cap = max_blocks > 0 && max_blocks < PEER_MAX_BLOCKS ? max_blocks : PEER_MAX_BLOCKS;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (world == 2) peer_allreduce_kernel<2><<<(int)grid, PEER_THREADS, 0, st>>>(P);
-    else if (world == 4) peer_allreduce_kernel<4><<<(int)grid, PEER_THREADS, 0, st>>>(P);
-    else peer_allreduce_kernel<8><<<(int)grid, PEER_THREADS, 0, st>>>(P);
+    if (world == 2) peer_allreduce_kernel<2, 4><<<(int)grid, PEER_THREADS, 0, st>>>(P);
+    else if (world == 4) peer_allreduce_kernel<4, 2><<<(int)grid, PEER_THREADS, 0, st>>>(P);
+    else peer_allreduce_kernel<8, 1><<<(int)grid, PEER_THREADS, 0, st>>>(P);
     RSR_LAUNCH_CHECK();
     return 0;
 }

@@ -42,7 +42,7 @@ def test_emulated_ranks_sum_bit_exact_and_repeatable(h, world, n):
     streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
     try:
         for it in range(3):                                   # monotonic barrier counters: nothing is reset between calls
-            src = [torch.tensor(rng.standard_normal(n).astype(np.float32) * 10.0 ** rng.integers(-3, 3), device=dev)
+            src = [torch.tensor((rng.standard_normal(n) * 10.0 ** rng.integers(-3, 3)).astype(np.float32), device=dev)
                    for _ in range(world)]
             want = src[0].clone()
             for r in range(1, world):
