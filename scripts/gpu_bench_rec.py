@@ -54,7 +54,8 @@ def run(B, T, Cp):
 
 
 print("%5s %5s %5s | %10s %10s | %10s %10s | %10s %10s" % ("B", "T", "Cp", "fwd us", "us/step", "fused us", "us/step", "bwd us", "us/step"))
-for (B, T, Cp) in [(16, 100, 512), (32, 100, 512), (48, 100, 512), (64, 100, 512), (96, 100, 512), (112, 100, 512),
+shapes = os.environ.get("RSR_REC_SHAPES")          # "B,T,Cp;B,T,Cp;..." overrides the default sweep
+for (B, T, Cp) in [tuple(int(v) for v in s.split(",")) for s in shapes.split(";")] if shapes else [(16, 100, 512), (32, 100, 512), (48, 100, 512), (64, 100, 512), (96, 100, 512), (112, 100, 512),
                    (128, 100, 512), (128, 200, 512), (8, 100, 768), (64, 100, 1024), (8, 100, 256), (32, 100, 256),
                    (128, 100, 256)]:
     try:
