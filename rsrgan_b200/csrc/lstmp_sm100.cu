@@ -222,10 +222,14 @@ struct BwdParams {
 };
 
 // CTA (ks, ms): gate-column slice ks = 64 cells (256 packed gate columns), output rows
-// [256 ms, 256 ms + 256) as two UMMA M=128 tiles.
+// [256 ms, 256 ms + 256) as two UMMA M=128 tiles.  The block has 8 NB threads (128 for 16 utterances, 256 for 32): every
+// thread differentiates ONE cell for 8 utterances and issues 32 reductions per step whatever NB is -- with 128 threads
+// the NB = 32 slice (what Cp = 1024, B = 64 needs to stay co-resident) ran 7.7 us per step against 4.4 for NB = 16
+// (profiles/r2_rec_steps_big_v0.txt), all of it the doubled per-thread gate math and red.global issue.
 template <int NB>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(8 * NB, 1)
 lstmp_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const BwdParams p) {
+    constexpr int NPART = NB / 8;                   // utterance lanes of the gate math: threads / 64
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -264,7 +268,7 @@ lstmp_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const BwdParams p)
     }
 
     // gate-backward ownership: thread <-> (cell c of the slice, utterances n = half, half+2, ...)
-    constexpr int NH = NB / 2;
+    constexpr int NH = NB / NPART;                  // = 8
     const int c = tid & 63, half = tid >> 6;
     const int cell = 64 * ks + c;
     const int jl = c >> 5, c32 = c & 31;
@@ -274,7 +278,7 @@ lstmp_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const BwdParams p)
 #pragma unroll
     for (int i = 0; i < NH; ++i) {
         dcar[i] = 0.f;
-        const int b = b0 + half + 2 * i;
+        const int b = b0 + half + NPART * i;
         len[i] = b < p.B ? p.lengths[b] : 0;
     }
     float a_dwi = 0.f, a_dwf = 0.f, a_dwo = 0.f, a_db[4] = {0.f, 0.f, 0.f, 0.f};
@@ -289,7 +293,7 @@ lstmp_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const BwdParams p)
         float s_i[NH], s_f[NH], s_o[NH], s_j[NH], s_c[NH], s_cp[NH];
 #pragma unroll
         for (int i = 0; i < NH; ++i) {
-            const int b = b0 + half + 2 * i;
+            const int b = b0 + half + NPART * i;
             if (b < p.B) {
                 const float* s = p.save + ((size_t)t * p.B + b) * 5 * Cp + cell;
                 s_i[i] = __ldg(s); s_f[i] = __ldg(s + Cp); s_o[i] = __ldg(s + 2 * Cp); s_j[i] = __ldg(s + 3 * Cp);
@@ -311,12 +315,12 @@ lstmp_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const BwdParams p)
         float dmv[NH];
 #pragma unroll
         for (int i = 0; i < NH; ++i) {
-            const int b = b0 + half + 2 * i;
+            const int b = b0 + half + NPART * i;
             dmv[i] = b < p.B ? __ldcg(p.dmt + ((size_t)t * p.B + b) * Cp + cell) : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < NH; ++i) {
-            const int n = half + 2 * i;
+            const int n = half + NPART * i;
             const int b = b0 + n;
             const float m = ((b < p.B) && (t < len[i])) ? 1.f : 0.f;     // frozen steps / rows past the batch: exact zeros
             const float dm = dmv[i];
@@ -363,12 +367,15 @@ lstmp_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const BwdParams p)
         __syncwarp();
         mbar_wait(barM, (uint32_t)(step & 1));
         tc_fence_after();
+        // warp w reads TMEM lane quadrant w % 4: four warps drain both m-tiles (NB = 16), eight warps one tile each (NB = 32)
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mi = 0; mi < (NB == 16 ? 2 : 1); ++mi) {
+            const int mt = NB == 16 ? mi : (warp >> 2);
+            const int wq = warp & 3;
             float acc[NB];
-            if constexpr (NB == 16) tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NB), acc);
-            else tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NB), acc);
-            const int crow = 256 * ms + 128 * mt + warp * 32 + lane;
+            if constexpr (NB == 16) tmem_ld16(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(mt * NB), acc);
+            else tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(mt * NB), acc);
+            const int crow = 256 * ms + 128 * mt + wq * 32 + lane;
 #pragma unroll
             for (int n = 0; n < NB; ++n) {
                 const int b = b0 + n;
@@ -514,7 +521,7 @@ extern "C" int rsr_lstmp_rec_bwd(rsr_handle* h, void* stream, int B, int T, int 
         lstmp_rec_bwd_kernel<16><<<groups * per_grp, 128, smem, (cudaStream_t)stream>>>(tmW, p);
     } else {
         RSR_CHECK_CUDA(cudaFuncSetAttribute(lstmp_rec_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
-        lstmp_rec_bwd_kernel<32><<<groups * per_grp, 128, smem, (cudaStream_t)stream>>>(tmW, p);
+        lstmp_rec_bwd_kernel<32><<<groups * per_grp, 256, smem, (cudaStream_t)stream>>>(tmW, p);
     }
     RSR_LAUNCH_CHECK();
     return 0;

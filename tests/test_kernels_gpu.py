@@ -127,6 +127,7 @@ def _rec_case(h, B, T, I, C, P, ragged, seed):
     (3, 1, 40, 256, 40, False),          # a single frame
     (20, 7, 257, 1024, 257, True),       # BASELINE configs[4] layer (res_lstm_l, C = 1024): weight slab half in TMEM
     (64, 5, 257, 1000, 257, False),      # same family at the cfg-5 batch (two groups of 32 in the backward), C padded
+    (50, 6, 257, 1024, 257, True),       # ... ragged, second group partial (256-thread backward blocks)
 ])
 def test_lstmp_recurrence_fwd_bwd(h, B, T, I, C, P, ragged):
     r = _rec_case(h, B, T, I, C, P, ragged, seed=B + T)
