@@ -306,7 +306,8 @@ def main():
                 "algorithmic_flops_per_launch": work / cnt}
     roofline = roof(name, cnt, tms, work)
     # the fused LSTM-gate kernels named by north_star, reported whatever their share (latency / DSMEM bound)
-    lstm_roofs = [roof(k, *shares[k]) for k in ("rsr_lstmp_fused_fwd", "rsr_lstmp_rec_fwd", "rsr_lstmp_rec_bwd") if k in shares]
+    lstm_roofs = [roof(k, *shares[k]) for k in ("rsr_lstmp_wave_fwd", "rsr_lstmp_fused_fwd", "rsr_lstmp_rec_fwd", "rsr_lstmp_rec_bwd")
+                  if k in shares]
     fpf = flops_per_frame(cfg)
     step_tflops = value / world * fpf / 1e12
 

@@ -146,6 +146,32 @@ int rsr_lstmp_fused_fwd(rsr_handle* h, void* stream, int B, int T, int I, int Cp
                         const void* kxT, const float* bias, const void* wcT, const float* w_i,
                         const float* w_f, const float* w_o, float forget_bias, const int* lengths,
                         void* mt_seq, float* save);
+/* Layer wavefront: two stacked LSTMP layers of equal cell count (tf.contrib.rnn.MultiRNNCell under ONE dynamic_rnn,
+ * models/lstm.py:89-112 -- layer 2 consumes layer 1's output of the same time step) in one launch.  Layer 1's clusters,
+ * a projection stage (out1_t = mt1_t W_p1 per step, W_p1^T resident in TMEM) and layer 2's clusters run side by side,
+ * layer 2 a few steps behind, handing rows over through global memory with one release / acquire counter per group of
+ * utterances and step.  Same outputs as rsr_lstmp_fused_fwd(layer 1) + rsr_gemm(projection) + rsr_lstmp_fused_fwd
+ * (layer 2): mt1, save1, out1 (16-bit rows [B, (T+1) B) of the layer-1 output sequence), mt2, save2.
+ *   wpT1    h16 [Pp1, Cp]   W_p1^T (rows >= P1 zero); the other operands as for rsr_lstmp_fused_fwd, per layer;
+ *                           layer 2's input width is P1, its K_x^T is [4Cp, round_up(P1, 16)].
+ * Returns RSR_E_RESIDENT (nothing launched) when the shape does not apply: Cp > 512, the operands do not fit in TMEM,
+ * or the 2 * groups + 1 clusters are not co-resident -- the caller then runs the layers one after the other. */
+typedef struct rsr_wave_args {
+    int B, T, Cp;
+    int I1, P1;                   /* layer-1 input width and projection width (= layer-2 input width) */
+    float forget_bias;
+    const int* lengths;
+    const void* x16; int ldx;     /* layer-1 input, time-major [T*B, ldx] */
+    const void* kxT1; const float* bias1; const void* wcT1;
+    const float* w_i1; const float* w_f1; const float* w_o1;
+    void* mt1; float* save1;
+    const void* wpT1;
+    void* out1; int ldo1;         /* [(T+1)*B, ldo1]; rows [0, B) (initial state) are not written */
+    const void* kxT2; const float* bias2; const void* wcT2;
+    const float* w_i2; const float* w_f2; const float* w_o2;
+    void* mt2; float* save2;
+} rsr_wave_args;
+int rsr_lstmp_wave_fwd(rsr_handle* h, void* stream, const rsr_wave_args* a);
 /*   dmt     fp32 [T*B, Cp]    dOut_t * W_proj^T (from rsr_gemm); read only on the cluster path (Cp <= 512), the
  *                              L2-exchange path (Cp > 512) adds the recurrent term dz_{t+1} * Wc^T in place
  *   wc      h16  [Cp, 4Cp]    Wc, packed columns (backward MMA A operand)

@@ -34,6 +34,19 @@ class GemmArgs(C.Structure):
                 ("tile_n", ci), ("split_k", ci)]
 
 
+class WaveArgs(C.Structure):
+    """rsr_wave_args (include/rsrgan_b200.h)."""
+    _fields_ = [("B", ci), ("T", ci), ("Cp", ci), ("I1", ci), ("P1", ci), ("forget_bias", cf),
+                ("lengths", vp),
+                ("x16", vp), ("ldx", ci),
+                ("kxT1", vp), ("bias1", vp), ("wcT1", vp), ("w_i1", vp), ("w_f1", vp), ("w_o1", vp),
+                ("mt1", vp), ("save1", vp),
+                ("wpT1", vp),
+                ("out1", vp), ("ldo1", ci),
+                ("kxT2", vp), ("bias2", vp), ("wcT2", vp), ("w_i2", vp), ("w_f2", vp), ("w_o2", vp),
+                ("mt2", vp), ("save2", vp)]
+
+
 # name -> argtypes (every symbol include/rsrgan_b200.h declares)
 SIGNATURES = {
     "rsr_version": [],
@@ -48,6 +61,7 @@ SIGNATURES = {
     "rsr_cmvn_apply_padded": [vp, vp, vp, vp, vp, vp, ci, ci, ci, vp],
     "rsr_lstmp_rec_fwd": [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, cf, vp, vp, vp],
     "rsr_lstmp_fused_fwd": [vp, vp, ci, ci, ci, ci, vp, ci, vp, vp, vp, vp, vp, vp, cf, vp, vp, vp],
+    "rsr_lstmp_wave_fwd": [vp, vp, C.POINTER(WaveArgs)],
     "rsr_transpose16": [vp, vp, vp, ci, ci, ci, vp, ci],
     "rsr_peer_alloc": [vp, cll, C.POINTER(vp), vp],
     "rsr_peer_open": [vp, vp, C.POINTER(vp)],

@@ -51,11 +51,23 @@ struct rsr_handle {
     int fused_ik[2] = {-1, -1};      // Ik the fused-forward capacity entry was computed for
     int pair_cap[2][2] = {{-1, -1}, {-1, -1}};   // CTA-pair kernels (lstmp_pair_sm100.cu): [fwd|bwd][Cp/256 - 1]
     int pair_ik[2] = {-1, -1};
+    int wave_cap[2][2] = {{-1, -1}, {-1, -1}};   // layer-wavefront forward kernel: [NBP 32|48][Cp/256 - 1]
+    int wave_key[2][2] = {{-1, -1}, {-1, -1}};
     int cluster_cap[3][2][2] = {{{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}};   // [2] = fused fwd
 };
 
 #define RSR_FLAG_WORDS 4096
 #define RSR_PARTIAL_WORDS (1 << 17)   // 128 Mi parameters per network
+
+// `n` zero-initialised-by-the-caller counters of the group-barrier workspace (ring allocation: a launch's counters are
+// dead long before the cursor wraps)
+inline unsigned int* rsr_take_flags(rsr_handle* h, int n) {
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->flag_cursor + n > RSR_FLAG_WORDS) h->flag_cursor = 0;
+    unsigned int* f = h->flags + h->flag_cursor;
+    h->flag_cursor += n;
+    return f;
+}
 
 // Dynamic shared memory floors that keep TMEM owners apart when kernels of different streams overlap:
 // two recurrence CTAs (each allocates up to all 512 TMEM columns and waits on its cluster) must never share

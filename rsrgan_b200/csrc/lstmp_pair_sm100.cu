@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "handle.h"
 #include "cluster_util.h"
+#include <type_traits>
 
 using namespace rsr;
 
@@ -31,9 +32,20 @@ __device__ unsigned long long g_rsr_ptrace[8192];
 
 namespace {
 
-constexpr int NBP = 32;         // utterances per cluster
-constexpr int GATE_THREADS = 256;
-constexpr int PAIR_THREADS = GATE_THREADS + 32;   // + the issuer / relay warp
+constexpr int NBP_BWD = 32;     // utterances per cluster of the backward kernel
+constexpr int GATE_THREADS = 256;                 // backward kernel: gate-backward warps
+constexpr int PAIR_THREADS = GATE_THREADS + 32;   // + the issuer warp
+
+// Geometry of the forward kernel for NBP utterances per cluster (32: the default; 48: the layer-wavefront launch,
+// which has to seat two layers' clusters plus the projection cluster in the 7 sixteen-CTA clusters this part places).
+template <int NBP> struct PairGeom {
+    static constexpr int NBR = NBP / 2;                 // B-operand rows (utterances) per CTA
+    static constexpr int CW = NBP / 4;                  // gate warps: thread <-> 4 cells x 1 utterance
+    static constexpr int GT = 32 * CW;                  // gate threads
+    static constexpr int THREADS = GT + 64;             // + the issuer / relay warp + the poster warp (layer wavefront)
+    static constexpr int ACCS = NBP <= 32 ? 32 : 64;    // TMEM column stride between the two accumulators
+    static constexpr int XP = NBP + 1;                  // xchg pitch in floats
+};
 
 // MUFU.TANH forms of the gate non-linearities (default; RSR_FAST_GATES=0 selects the ex2 + rcp forms of common.cuh):
 // one special-function instruction per gate instead of two and ~6 FP32 instructions.  Relative error 2^-11 -- the size
@@ -56,6 +68,22 @@ __device__ __forceinline__ void tc_mma_f16_ts_2cta(uint32_t tmem_d, uint32_t tme
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {   // non-blocking arrival
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// monotonic step counter of another cluster (layer wavefront): returns the value seen once it is >= want; bounded
+__device__ __forceinline__ unsigned int spin_get_ge(const unsigned int* p, unsigned int want) {
+    unsigned int v = ld_acquire(p);
+    if (v >= want) return v;
+    const uint64_t t0 = global_ns();
+    uint32_t spins = 0;
+    while ((v = ld_acquire(p)) < want) {
+        if ((++spins & 1023u) == 0 && global_ns() - t0 > RSR_SPIN_LIMIT_NS) __trap();
+    }
+    return v;
+}
+
 struct PFwdParams {
     int B, T, Cp, bf;
     float forget_bias;
@@ -67,72 +95,67 @@ struct PFwdParams {
     uint16_t* mt_seq;           // [(T+1)*B, Cp]
     float* save;                // [T*B, 5, Cp] or null
     int Ik;
+    // layer wavefront (null / 0 otherwise): post[grp] += 1 per CTA once the CTA's rows of mt_t are in global memory;
+    // the x tile of step t may be fetched once wait[grp] >= wait_per_step * (t + 1)
+    unsigned int* post;
+    const unsigned int* wait;
+    unsigned int wait_per_step;
 };
 
-// One cluster (G = Cp/32 CTAs = G/2 pairs) = one group of 32 utterances, run as NCH independent recurrences
-// ("chains") of NBC = 32/NCH utterances: NCH = 1 -> one pair MMA of N = 32 per step (the one that is launched: two
-// N = 16 chains behind one issuer fall into lockstep and gain nothing, profiles/r2_pair_fwd_variants.txt).
+// One cluster (G = Cp/32 CTAs = G/2 pairs) = one group of NBP utterances: one pair MMA of N = NBP per k-step.
 // CTA j owns cells [32j, 32j+32): its 128 packed gate rows of Wc^T and K_x^T are resident in its TMEM (A operand) for
-// the whole sequence, and it holds the B-operand rows (mt_{t-1}, x_t) of NBR = NBC/2 utterances of every chain (the
-// even CTA of a pair the first half, the odd CTA the second).
-// Warps 0-7: gate math (thread <-> 4 cells x 1 utterance; 8/NCH warps per chain); warp 8: in the even CTA of each
-// pair the MMA issuer, in the odd CTA the relay that tells the issuer when the odd half of a B operand has landed.
+// the whole sequence, and it holds the B-operand rows (mt_{t-1}, x_t) of NBR = NBP/2 utterances (the even CTA of a
+// pair the first half, the odd CTA the second).
+// Warps 0..CW-1: gate math (thread <-> 4 cells x 1 utterance); warp CW: in the even CTA of each pair the MMA issuer,
+// in the odd CTA the relay that tells the issuer when the odd half of a B operand has landed; warp CW+1: the poster of
+// the layer wavefront (idle otherwise).
 // Tried and measured slower (profiles/r2_pair_fwd_variants_*.txt): shipping every 8-cell k-chunk as soon as its cell
 // index is done, either with st.async from the gate warps (they stall on the 15 B/clk DSMEM port: 2766 cycles for gate
 // math + sends instead of 927 + 1093) or with 256-byte bulk copies from a sender warp (per-copy overhead and a proxy
 // fence per chunk: 5579 cycles per step instead of 3763); sharing reciprocals between gates (7 MUFU operations per cell
-// instead of 10: the gate phase is latency-, not MUFU-bound).
-template <int NCH, int BF, int FAST>
-__global__ void __launch_bounds__(PAIR_THREADS, 1)
-lstmp_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const PFwdParams p) {
-    constexpr int NBC = NBP / NCH;              // utterances per chain = UMMA N
-    constexpr int NBR = NBC / 2;                // B-operand rows per CTA and chain
-    constexpr int CW = 8 / NCH;                 // gate warps per chain
-    constexpr int XP = NBC + 1;                 // xchg pitch in floats
+// instead of 10: the gate phase is latency-, not MUFU-bound); two N = 16 recurrences per cluster behind one issuer (they
+// fall into lockstep: 3959 vs 3763 cycles per step).
+template <int NBP, int BF, int FAST>
+__device__ __forceinline__ void pair_fwd_body(const CUtensorMap* tmX, const PFwdParams& p, const int grp) {
+    using GM = PairGeom<NBP>;
+    constexpr int NBR = GM::NBR, CW = GM::CW, GT = GM::GT, XP = GM::XP;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = p.Cp / 32;                    // cluster size
     const uint32_t j = cluster_ctarank();       // cell block
-    const uint32_t e = j & 1u;                  // which half of every chain's utterances this CTA holds
-    const int grp = blockIdx.x / G;
+    const uint32_t e = j & 1u;                  // which half of the group's utterances this CTA holds
     const int b0 = grp * NBP;
 
     const uint32_t sB_bytes = (uint32_t)p.Cp * NBR * 2u;             // one B-operand buffer [Cp/8][NBR][8] 16-bit
     const int KBX = (p.Ik + 63) / 64;                                // 64-wide k sub-tiles of the x_t tile
     const uint32_t xt_bytes = (uint32_t)KBX * NBR * 128u;            // this CTA's rows of one x_t tile, SW128 (1024-aligned)
-    const uint32_t chain_bytes = 2u * xt_bytes + 2u * sB_bytes;      // per chain: 2 x tiles | 2 B buffers
-    const uint32_t sX0 = base + (uint32_t)NCH * chain_bytes;         // float xchg[NCH][128][XP]
-    const uint32_t sBar0 = sX0 + (uint32_t)NCH * 128u * XP * 4u;     // per chain 64 B: barM, full0/1, xfull0/1, peer0/1
-    const uint32_t tslot = sBar0 + (uint32_t)NCH * 64u;
-    auto sXt = [&](int hc, int b) { return base + (uint32_t)hc * chain_bytes + (uint32_t)b * xt_bytes; };
-    auto sB = [&](int hc, int b) { return base + (uint32_t)hc * chain_bytes + 2u * xt_bytes + (uint32_t)b * sB_bytes; };
-    auto barM = [&](int hc) { return sBar0 + (uint32_t)hc * 64u; };
-    auto full = [&](int hc, int b) { return sBar0 + (uint32_t)hc * 64u + 8u + 8u * (uint32_t)b; };
-    auto xfull = [&](int hc, int b) { return sBar0 + (uint32_t)hc * 64u + 24u + 8u * (uint32_t)b; };
-    auto peer = [&](int hc, int b) { return sBar0 + (uint32_t)hc * 64u + 40u + 8u * (uint32_t)b; };
+    const uint32_t sX0 = base + 2u * xt_bytes + 2u * sB_bytes;       // float xchg[128][XP]
+    const uint32_t sBar0 = (sX0 + 128u * XP * 4u + 7u) & ~7u;        // barM, full0/1, xfull0/1, peer0/1
+    const uint32_t tslot = sBar0 + 64u;
+    auto sXt = [&](int b) { return base + (uint32_t)b * xt_bytes; };
+    auto sB = [&](int b) { return base + 2u * xt_bytes + (uint32_t)b * sB_bytes; };
+    const uint32_t barM = sBar0;
+    auto full = [&](int b) { return sBar0 + 8u + 8u * (uint32_t)b; };
+    auto xfull = [&](int b) { return sBar0 + 24u + 8u * (uint32_t)b; };
+    auto peer = [&](int b) { return sBar0 + 40u + 8u * (uint32_t)b; };
 
-    // TMEM: [0, Cp/2) Wc^T slice | [Cp/2, Cp/2 + Ik/2) K_x^T slice | accumulators [chain][step parity] of NBC columns
+    // TMEM: [0, Cp/2) Wc^T slice | [Cp/2, Cp/2 + Ik/2) K_x^T slice | two accumulators (step parity), ACCS columns apart
     const uint32_t a_cols = (uint32_t)p.Cp / 2u + (uint32_t)p.Ik / 2u;
     uint32_t tcols = 32;
-    while (tcols < a_cols + 2u * NBP) tcols <<= 1;
-    if (tid == GATE_THREADS) {
-        tma_prefetch_desc(&tmX);
-        for (int hc = 0; hc < NCH; ++hc) {
-            mbar_init(barM(hc), 1);
-            for (int b = 0; b < 2; ++b) { mbar_init(full(hc, b), 1); mbar_init(xfull(hc, b), 1); mbar_init(peer(hc, b), 1); }
-        }
+    while (tcols < a_cols + 2u * GM::ACCS) tcols <<= 1;
+    if (tid == GT) {
+        tma_prefetch_desc(tmX);
+        mbar_init(barM, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(full(b), 1); mbar_init(xfull(b), 1); mbar_init(peer(b), 1); }
         fence_mbar_init();
-        for (int hc = 0; hc < NCH; ++hc) {
-            mbar_expect_tx(full(hc, 1), sB_bytes);      // armed for step 1 (mt_0 from every CTA of the cluster)
-            mbar_expect_tx(full(hc, 0), sB_bytes);      // armed for step 2
-        }
+        mbar_expect_tx(full(1), sB_bytes);      // armed for step 1 (mt_0 from every CTA of the cluster)
+        mbar_expect_tx(full(0), sB_bytes);      // armed for step 2
     }
-    if (warp == 8) tmem_alloc_2cta(tslot, tcols);
-    if (tid < GATE_THREADS)                             // m_{-1} = 0
-        for (int hc = 0; hc < NCH; ++hc)
-            for (uint32_t i = tid; i < sB_bytes / 16u; i += GATE_THREADS) st_shared_v4(sB(hc, 0) + i * 16u, 0u, 0u, 0u, 0u);
+    if (warp == CW) tmem_alloc_2cta(tslot, tcols);
+    if (tid < GT)                               // m_{-1} = 0
+        for (uint32_t i = tid; i < sB_bytes / 16u; i += GT) st_shared_v4(sB(0) + i * 16u, 0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -169,77 +192,89 @@ lstmp_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const PFwdParams 
     const int KK = p.Cp / 16, KKX = p.Ik / 16;
     const uint32_t lead = mapa_u32(base, j & ~1u) - base;            // shared::cta -> shared::cluster offset of the pair's even CTA
 
-    if (warp == 8) {
+    if (warp == CW) {
         // ------------------------------------------------------------------------------------------------
         // issuer (even CTA) / relay (odd CTA): one elected lane
         // ------------------------------------------------------------------------------------------------
         if (elect_one_sync()) {
-            // x_0 tiles; both CTAs' rows complete on the issuer's barrier
-            for (int hc = 0; hc < NCH; ++hc) {
-                if (e == 0) mbar_expect_tx(xfull(hc, 0), 2u * xt_bytes);
-                for (int kb = 0; kb < KBX; ++kb)
-                    tma_load_2d_2cta(sXt(hc, 0) + (uint32_t)kb * (NBR * 128u), &tmX, xfull(hc, 0) + lead, kb * 64,
-                                     b0 + hc * NBC + (int)e * NBR);
-            }
-            const uint32_t idesc = umma_idesc(256, NBC, BF, 0, 0);
+            // layer wavefront: the rows of x_t come from another cluster of this grid; `seen` caches the producer's counter,
+            // so that a consumer that trails by several steps polls once per several steps
+            unsigned int seen = 0;
+            auto x_ready = [&](int t) {
+                if (p.wait) {
+                    const unsigned int need = p.wait_per_step * (unsigned int)(t + 1);
+                    if (seen < need) { seen = spin_get_ge(p.wait + grp, need); fence_proxy_async_all(); }
+                }
+            };
+            // x_0 tile; both CTAs' rows complete on the issuer's barrier
+            x_ready(0);
+            if (e == 0) mbar_expect_tx(xfull(0), 2u * xt_bytes);
+            for (int kb = 0; kb < KBX; ++kb)
+                tma_load_2d_2cta(sXt(0) + (uint32_t)kb * (NBR * 128u), tmX, xfull(0) + lead, kb * 64, b0 + (int)e * NBR);
+            const uint32_t idesc = umma_idesc(256, NBP, BF, 0, 0);
             const uint16_t pair_mask = (uint16_t)(3u << (j & ~1u));
             for (int t = 0; t < p.T; ++t) {
                 const int buf = t & 1;
-                for (int hc = 0; hc < NCH; ++hc) {
-                    if (t + 1 < p.T) {   // prefetch x_{t+1}; its buffer was last read by the MMAs of step t-1 (retired: barM)
-                        if (t > 0) mbar_wait(barM(hc), (uint32_t)((t - 1) & 1));
-                        if (e == 0) mbar_expect_tx(xfull(hc, buf ^ 1), 2u * xt_bytes);
-                        for (int kb = 0; kb < KBX; ++kb)
-                            tma_load_2d_2cta(sXt(hc, buf ^ 1) + (uint32_t)kb * (NBR * 128u), &tmX, xfull(hc, buf ^ 1) + lead, kb * 64,
-                                             (t + 1) * p.B + b0 + hc * NBC + (int)e * NBR);
+                if (t + 1 < p.T) {   // prefetch x_{t+1}; its buffer was last read by the MMAs of step t-1 (retired: barM)
+                    if (t > 0) mbar_wait(barM, (uint32_t)((t - 1) & 1));
+                    x_ready(t + 1);
+                    if (e == 0) mbar_expect_tx(xfull(buf ^ 1), 2u * xt_bytes);
+                    for (int kb = 0; kb < KBX; ++kb)
+                        tma_load_2d_2cta(sXt(buf ^ 1) + (uint32_t)kb * (NBR * 128u), tmX, xfull(buf ^ 1) + lead, kb * 64,
+                                         (t + 1) * p.B + b0 + (int)e * NBR);
+                }
+                if (e == 0) {
+                    const uint32_t acc = tmem_acc + (uint32_t)buf * GM::ACCS;
+                    // input half first: it does not depend on mt_{t-1}, so it runs while the exchange is still in flight
+                    mbar_wait(xfull(buf), (uint32_t)((t >> 1) & 1));
+                    tc_fence_after();
+                    const uint32_t sxt = sXt(buf);
+                    for (int kk = 0; kk < KKX; ++kk) {
+                        const uint64_t dx = umma_desc_sw128(sxt + (uint32_t)(kk >> 2) * (NBR * 128u) + (uint32_t)(kk & 3) * 32u, 16, 1024);
+                        tc_mma_f16_ts_2cta(acc, tmem + (uint32_t)p.Cp / 2u + (uint32_t)kk * 8u, dx, idesc, kk ? 1u : 0u);
                     }
-                    if (e == 0) {
-                        const uint32_t acc = tmem_acc + (uint32_t)(hc * 2 + buf) * NBC;
-                        // input half first: it does not depend on mt_{t-1}, so it runs while the exchange is still in flight
-                        mbar_wait(xfull(hc, buf), (uint32_t)((t >> 1) & 1));
-                        tc_fence_after();
-                        const uint32_t sxt = sXt(hc, buf);
-                        for (int kk = 0; kk < KKX; ++kk) {
-                            const uint64_t dx = umma_desc_sw128(sxt + (uint32_t)(kk >> 2) * (NBR * 128u) + (uint32_t)(kk & 3) * 32u, 16, 1024);
-                            tc_mma_f16_ts_2cta(acc, tmem + (uint32_t)p.Cp / 2u + (uint32_t)kk * 8u, dx, idesc, kk ? 1u : 0u);
-                        }
-                        if (t > 0) {
-                            const uint32_t ph = (uint32_t)(((t - 1) >> 1) & 1);
-                            mbar_wait(full(hc, buf), ph);            // my rows of mt_{t-1}: all G slices have landed
-                            mbar_wait(peer(hc, buf), ph);   // ... and the odd CTA's rows
-                        }
-                        PTRACE(hc == 0, t, 1);
-                        fence_proxy_async_smem();
-                        tc_fence_after();
-                        uint64_t db = umma_desc_nosw(sB(hc, buf), NBR * 16u, 128u);
-                        uint32_t ta = tmem;
+                    if (t > 0) {
+                        const uint32_t ph = (uint32_t)(((t - 1) >> 1) & 1);
+                        mbar_wait(full(buf), ph);            // my rows of mt_{t-1}: all G slices have landed
+                        mbar_wait(peer(buf), ph);            // ... and the odd CTA's rows
+                    }
+                    PTRACE(true, t, 1);
+                    fence_proxy_async_smem();
+                    tc_fence_after();
+                    uint64_t db = umma_desc_nosw(sB(buf), NBR * 16u, 128u);
+                    uint32_t ta = tmem;
 #pragma unroll 8
-                        for (int kk = 0; kk < KK; ++kk) {
-                            tc_mma_f16_ts_2cta(acc, ta, db, idesc, 1u);
-                            ta += 8u;                                    // 16 k = 8 columns
-                            db += (uint64_t)((2u * NBR * 16u) >> 4);     // two k-chunks of [NBR rows][16 B]
-                        }
-                        tc_commit_2cta_mc(barM(hc), pair_mask);
-                        if (t > 0 && t + 2 < p.T) mbar_expect_tx(full(hc, buf), sB_bytes);   // re-arm for step t + 2
-                        PTRACE(hc == 0, t, 2);
-                    } else if (t > 0) {
-                        mbar_wait(full(hc, buf), (uint32_t)(((t - 1) >> 1) & 1));
-                        fence_proxy_async_smem();
-                        mbar_arrive_cluster(peer(hc, buf) + lead);
-                        if (t + 2 < p.T) mbar_expect_tx(full(hc, buf), sB_bytes);
+                    for (int kk = 0; kk < KK; ++kk) {
+                        tc_mma_f16_ts_2cta(acc, ta, db, idesc, 1u);
+                        ta += 8u;                                    // 16 k = 8 columns
+                        db += (uint64_t)((2u * NBR * 16u) >> 4);     // two k-chunks of [NBR rows][16 B]
                     }
+                    tc_commit_2cta_mc(barM, pair_mask);
+                    if (t > 0 && t + 2 < p.T) mbar_expect_tx(full(buf), sB_bytes);   // re-arm for step t + 2
+                    PTRACE(true, t, 2);
+                } else if (t > 0) {
+                    mbar_wait(full(buf), (uint32_t)(((t - 1) >> 1) & 1));
+                    fence_proxy_async_smem();
+                    mbar_arrive_cluster(peer(buf) + lead);
+                    if (t + 2 < p.T) mbar_expect_tx(full(buf), sB_bytes);
                 }
             }
         }
         __syncwarp();
+    } else if (warp == CW + 1) {
+        // poster (layer wavefront): once every gate thread has stored its piece of mt_t, one release per CTA and step
+        if (p.post)
+            for (int t = 0; t < p.T; ++t) {
+                named_bar_sync((t & 1) ? 5u : 2u, GT + 32);
+                if (lane == 0) red_release_add(p.post + grp, 1u);
+            }
     } else {
         // ------------------------------------------------------------------------------------------------
-        // gate warps: thread <-> (cells 4a..4a+3 of the block, utterance nl of chain hc)
+        // gate warps: thread <-> (cells 4a..4a+3 of the block, utterance nl of the group)
         // ------------------------------------------------------------------------------------------------
-        const int hc = warp / CW, wc = warp % CW;
-        const int q = warp & 3, chh = wc >> 2;      // TMEM lane quadrant, 16-column half of the accumulator (NCH = 1)
+        const int q = warp & 3, chh = warp >> 2;    // TMEM lane quadrant, 16-column piece of the accumulator
         const int a = lane & 7;
-        const int nl = 4 * wc + (lane >> 3);        // utterance within the chain
+        const int nl = 4 * warp + (lane >> 3);      // utterance within the group
         const int cell0 = 32 * (int)j + 4 * a;
         const float4 wi4 = *reinterpret_cast<const float4*>(p.w_i + cell0);
         const float4 wf4 = *reinterpret_cast<const float4*>(p.w_f + cell0);
@@ -247,7 +282,7 @@ lstmp_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const PFwdParams 
         const float wi[4] = {wi4.x, wi4.y, wi4.z, wi4.w}, wf[4] = {wf4.x, wf4.y, wf4.z, wf4.w},
                     wo[4] = {wo4.x, wo4.y, wo4.z, wo4.w};
         float creg[4] = {0.f, 0.f, 0.f, 0.f};
-        const int b_own = b0 + hc * NBC + nl;
+        const int b_own = b0 + nl;
         const int len = b_own < p.B ? p.lengths[b_own] : 0;
         // destinations of this thread's remote stores: the G/2 CTAs that hold this utterance's row (parity nl / NBR); the
         // two lanes that build one 16-byte chunk (8 cells) split them
@@ -258,22 +293,21 @@ lstmp_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const PFwdParams 
             rdelta[i] = i < HD ? mapa_u32(base, (uint32_t)(2 * ((a & 1) * HD + i) + nl / NBR)) - base : 0u;
         const int grow = 32 * q + lane;             // gate row of this thread in the tile (TMEM lane)
         const float bias_r = __ldg(p.bias + 128 * j + grow);
-        float* xchg = reinterpret_cast<float*>(base_ptr + (sX0 - base)) + hc * 128 * XP;
-        const uint32_t my_barM = barM(hc);
+        float* xchg = reinterpret_cast<float*>(base_ptr + (sX0 - base));
         const uint32_t send_off = (uint32_t)(4 * j + (a >> 1)) * (NBR * 16u) + (uint32_t)(nl % NBR) * 16u;
 
         for (int t = 0; t < p.T; ++t) {
             const int buf = t & 1;
             PTRACE(tid == 0, t, 0);
-            mbar_wait(my_barM, (uint32_t)(t & 1));
+            mbar_wait(barM, (uint32_t)(t & 1));
             tc_fence_after();
             PTRACE(tid == 0, t, 3);
             float acc[16];
-            tmem_ld16(tmem_acc + (uint32_t)(hc * 2 + buf) * NBC + ((uint32_t)(q * 32) << 16) + (uint32_t)chh * 16u, acc);
+            tmem_ld16(tmem_acc + (uint32_t)buf * GM::ACCS + ((uint32_t)(q * 32) << 16) + (uint32_t)chh * 16u, acc);
 #pragma unroll
             for (int k = 0; k < 16; ++k) xchg[grow * XP + chh * 16 + k] = acc[k] + bias_r;
             tc_fence_before();
-            named_bar_sync(1u + (uint32_t)hc, 32 * CW);
+            named_bar_sync(1u, GT);
             PTRACE(tid == 0, t, 4);
             const bool active = t < len;
             float mtv[4], sv[5][4];
@@ -303,8 +337,8 @@ lstmp_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const PFwdParams 
                 const uint32_t plo = __shfl_xor_sync(0xffffffffu, lo, 1), phi = __shfl_xor_sync(0xffffffffu, hi, 1);
                 const bool odd = a & 1;
                 const uint32_t w0 = odd ? plo : lo, w1 = odd ? phi : hi, w2 = odd ? lo : plo, w3 = odd ? hi : phi;
-                const uint32_t dst = sB(hc, buf ^ 1) + send_off;
-                const uint32_t dbar = full(hc, buf ^ 1);
+                const uint32_t dst = sB(buf ^ 1) + send_off;
+                const uint32_t dbar = full(buf ^ 1);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (k < HD) st_async_v4(dst + rdelta[k], w0, w1, w2, w3, dbar + rdelta[k]);
@@ -312,14 +346,15 @@ lstmp_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const PFwdParams 
             PTRACE(tid == 0, t, 6);
             // off the critical path: operand of the hoisted projection GEMM and of the backward pass
             const size_t row = (size_t)t * p.B + b_own;
-            if (b_own < p.B) {
-                *reinterpret_cast<uint2*>(p.mt_seq + (row + p.B) * p.Cp + cell0) = make_uint2(lo, hi);
-                if (p.save) {
-                    float* s = p.save + row * 5 * p.Cp + cell0;
+            if (b_own < p.B) *reinterpret_cast<uint2*>(p.mt_seq + (row + p.B) * p.Cp + cell0) = make_uint2(lo, hi);
+            // layer wavefront: this CTA's rows of mt_t are on their way; the poster warp releases them to the consumer (the
+            // gate warps only ARRIVE: a release fence here costs them ~0.5 us per step, profiles/r2_wave_steps_v0.txt)
+            if (p.post) named_bar_arrive((t & 1) ? 5u : 2u, GT + 32);
+            if (b_own < p.B && p.save) {
+                float* s = p.save + row * 5 * p.Cp + cell0;
 #pragma unroll
-                    for (int k = 0; k < 5; ++k)
-                        *reinterpret_cast<float4*>(s + (size_t)k * p.Cp) = make_float4(sv[k][0], sv[k][1], sv[k][2], sv[k][3]);
-                }
+                for (int k = 0; k < 5; ++k)
+                    *reinterpret_cast<float4*>(s + (size_t)k * p.Cp) = make_float4(sv[k][0], sv[k][1], sv[k][2], sv[k][3]);
             }
             PTRACE(tid == 0, t, 7);
         }
@@ -327,20 +362,184 @@ lstmp_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const PFwdParams 
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();   // nobody leaves (or frees TMEM the pair's MMAs address) while a peer may still use it
-    if (warp == 8) tmem_dealloc_2cta(tmem, tcols);
+    if (warp == CW) tmem_dealloc_2cta(tmem, tcols);
 }
 
-size_t pfwd_smem(int Cp, int Ik, int nch) {
-    const int nbc = NBP / nch, nbr = nbc / 2;
+template <int NBP, int BF, int FAST>
+__global__ void __launch_bounds__(PairGeom<NBP>::THREADS, 1)
+lstmp_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const PFwdParams p) {
+    pair_fwd_body<NBP, BF, FAST>(&tmX, p, (int)blockIdx.x / (p.Cp / 32));
+}
+
+// =========================================================================================
+// layer wavefront: two stacked LSTMP layers in ONE launch (models/lstm.py:89-112 builds them as a MultiRNNCell, i.e.
+// layer 2 consumes layer 1's output of the same time step).  Clusters [0, groups) run layer 1, clusters
+// [groups, 2 groups) layer 2 -- one to a few steps behind, gated by per-group counters in global memory -- and the
+// last cluster streams the projection out1_t = mt1_t W_p1 between them (a few of its CTAs; the others exit at once):
+//   layer 1, step t : mt1_t -> global, post flag1[g]            (16 CTAs -> 16 per step)
+//   projection      : wait flag1[g] >= 16 (t+1); TMA mt1_t (B operand, N = NBP), A = W_p1^T slice resident in TMEM
+//                     (128 features per CTA), D -> 16-bit rows of out1_t -> global, post flag2[g]
+//   layer 2, step t : its x tile is out1_t: wait flag2[g] >= NFT (t+1) before the TMA
+// Nobody waits on a LATER cluster of the grid, clusters are dispatched in index order, and the host launches only if
+// all 2 groups + 1 clusters are co-resident -- so the spins cannot deadlock; they are bounded anyway (RSR_SPIN_LIMIT_NS).
+// =========================================================================================
+struct WaveProj {
+    int groups, P, Pp, ldo;
+    const uint16_t* wpT;        // [Pp, Cp] = W_p1^T (16-bit, rows >= P zero)
+    uint16_t* out;              // [(T+1)*B, ldo] layer-1 output sequence (slot 0 = initial state, not written)
+    unsigned int* flag1;        // [groups] posted by layer 1
+    unsigned int* flag2;        // [groups] posted by the projection
+};
+
+template <int NBP, int BF>
+__device__ __forceinline__ void wave_proj_body(const CUtensorMap* tmM, const PFwdParams& p, const WaveProj& w) {
+    constexpr int ACCS = PairGeom<NBP>::ACCS;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NFT = (w.Pp + 127) / 128;
+    const int c = (int)cluster_ctarank();
+    if (c >= w.groups * NFT) return;            // whole CTA: nothing of this cluster is shared
+    const int g = c / NFT, ft = c % NFT;
+    const int b0 = g * NBP;
+    const int KB = p.Cp / 64;
+    const uint32_t bt_bytes = (uint32_t)KB * NBP * 128u;             // one mt1_t tile: KB sub-tiles [NBP rows x 64 k], SW128
+    const uint32_t sBar = base + 2u * bt_bytes;
+    auto sBt = [&](int b) { return base + (uint32_t)b * bt_bytes; };
+    auto fullB = [&](int b) { return sBar + 8u * (uint32_t)b; };
+    auto emptyB = [&](int b) { return sBar + 16u + 8u * (uint32_t)b; };
+    auto accfull = [&](int b) { return sBar + 32u + 8u * (uint32_t)b; };
+    auto accfree = [&](int b) { return sBar + 48u + 8u * (uint32_t)b; };
+    const uint32_t tslot = sBar + 64u;
+    const uint32_t a_cols = (uint32_t)p.Cp / 2u;
+    uint32_t tcols = 32;
+    while (tcols < a_cols + 2u * ACCS) tcols <<= 1;
+    if (tid == 0) {
+        tma_prefetch_desc(tmM);
+        for (int b = 0; b < 2; ++b) { mbar_init(fullB(b), 1); mbar_init(emptyB(b), 1); mbar_init(accfull(b), 1); mbar_init(accfree(b), 1); }
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tslot, tcols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
+    const uint32_t tmem_acc = tmem + a_cols;
+    if (warp < 4) {   // W_p1^T slice -> TMEM: thread <-> feature row, 64 k (32 columns) per store
+        const int f = 128 * ft + 32 * warp + lane;
+        const uint16_t* wrow = w.wpT + (size_t)f * p.Cp;
+        for (int cb = 0; cb < KB; ++cb) {
+            uint32_t r[32];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (f < w.Pp) v = __ldg(reinterpret_cast<const uint4*>(wrow + cb * 64) + k);
+                r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
+            }
+            tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb * 32u, r);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp >= 6) return;                      // (only mbarriers and named barriers 3, 4 below)
+
+    const int G = p.Cp / 32;
+    if (warp == 0) {
+        if (elect_one_sync()) {                 // producer: mt1_t tiles as layer 1 releases them
+            unsigned int seen = 0;
+            for (int t = 0; t < p.T; ++t) {
+                const int buf = t & 1;
+                if (t >= 2) mbar_wait(emptyB(buf), (uint32_t)(((t - 2) >> 1) & 1));
+                const unsigned int need = (unsigned int)G * (unsigned int)(t + 1);
+                if (seen < need) { seen = spin_get_ge(w.flag1 + g, need); fence_proxy_async_all(); }
+                mbar_expect_tx(fullB(buf), bt_bytes);
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(sBt(buf) + (uint32_t)kb * (NBP * 128u), tmM, fullB(buf), kb * 64, (t + 1) * p.B + b0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one_sync()) {                 // D[128 features, NBP utterances] = W_p1^T (TMEM) x mt1_t^T
+            const uint32_t idesc = umma_idesc(128, NBP, BF, 0, 0);
+            for (int t = 0; t < p.T; ++t) {
+                const int buf = t & 1;
+                mbar_wait(fullB(buf), (uint32_t)((t >> 1) & 1));
+                if (t >= 2) mbar_wait(accfree(buf), (uint32_t)(((t - 2) >> 1) & 1));
+                tc_fence_after();
+                const uint32_t sb = sBt(buf);
+                for (int kk = 0; kk < p.Cp / 16; ++kk) {
+                    const uint64_t db = umma_desc_sw128(sb + (uint32_t)(kk >> 2) * (NBP * 128u) + (uint32_t)(kk & 3) * 32u, 16, 1024);
+                    tc_mma_f16_ts(tmem_acc + (uint32_t)buf * ACCS, tmem + (uint32_t)kk * 8u, db, idesc, kk ? 1u : 0u);
+                }
+                tc_commit(emptyB(buf));
+                tc_commit(accfull(buf));
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;                 // warps 2..5 <-> TMEM lane quadrants 2, 3, 0, 1
+        const int f = 128 * ft + 32 * q + lane;
+        for (int t = 0; t < p.T; ++t) {
+            const int buf = t & 1;
+            mbar_wait(accfull(buf), (uint32_t)((t >> 1) & 1));
+            tc_fence_after();
+            uint16_t* orow = w.out + ((size_t)(t + 1) * p.B + b0) * w.ldo + f;
+#pragma unroll
+            for (int c16 = 0; c16 < NBP / 16; ++c16) {
+                float acc[16];
+                tmem_ld16(tmem_acc + (uint32_t)buf * ACCS + ((uint32_t)(q * 32) << 16) + (uint32_t)c16 * 16u, acc);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int n = c16 * 16 + k;
+                    if (b0 + n < p.B && f < w.Pp) orow[(size_t)n * w.ldo] = f2h(acc[k], BF);
+                }
+            }
+            tc_fence_before();
+            named_bar_sync(3u, 128);
+            if (warp == 2 && lane == 0) {
+                mbar_arrive(accfree(buf));
+                red_release_add(w.flag2 + g, 1u);
+            }
+        }
+    }
+    named_bar_sync(4u, 192);
+    if (warp == 0) tmem_dealloc(tmem, tcols);
+}
+
+template <int NBP, int BF, int FAST>
+__global__ void __launch_bounds__(PairGeom<NBP>::THREADS, 1)
+lstmp_wave_fwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+                      const __grid_constant__ CUtensorMap tmM, const PFwdParams p1, const PFwdParams p2, const WaveProj w) {
+    const int cid = (int)blockIdx.x / (p1.Cp / 32);
+    if (cid < w.groups) pair_fwd_body<NBP, BF, FAST>(&tmX1, p1, cid);
+    else if (cid < 2 * w.groups) pair_fwd_body<NBP, BF, FAST>(&tmX2, p2, cid - w.groups);
+    else wave_proj_body<NBP, BF>(&tmM, p1, w);
+}
+
+size_t pfwd_smem(int Cp, int Ik, int nbp) {
+    const int nbr = nbp / 2;
     const size_t xt = (size_t)((Ik + 63) / 64) * nbr * 128;
-    const size_t need = 1024 + (size_t)nch * (2 * xt + 2 * (size_t)Cp * nbr * 2 + 128 * (size_t)(nbc + 1) * 4 + 64) + 64;
+    const size_t need = 1024 + 2 * xt + 2 * (size_t)Cp * nbr * 2 + 128 * (size_t)(nbp + 1) * 4 + 8 + 64 + 16;
     return need < RSR_EXCLUSIVE_SMEM_REC ? RSR_EXCLUSIVE_SMEM_REC : need;
 }
+size_t wproj_smem(int Cp, int nbp) { return 1024 + 2 * (size_t)(Cp / 64) * nbp * 128 + 64 + 16; }
 
-// chains per cluster: 1 (RSR_PAIR_CHAINS=2 selects the two-chain experiment)
-int pair_chains() {
-    const char* ev = getenv("RSR_PAIR_CHAINS");
-    return (ev && ev[0] == '2') ? 2 : 1;
+bool fast_gates() {
+    static const int fast = getenv("RSR_FAST_GATES") ? (atoi(getenv("RSR_FAST_GATES")) ? 1 : 0) : 1;
+    return fast != 0;
+}
+
+void fill_fwd_params(PFwdParams& p, rsr_handle* h, int B, int T, int Cp, int Ik, const void* kxT, const float* bias,
+                     const void* wcT, const float* w_i, const float* w_f, const float* w_o, float forget_bias,
+                     const int* lengths, void* mt_seq, float* save) {
+    p.B = B; p.T = T; p.Cp = Cp; p.bf = h->dtype == RSR_DTYPE_BF16; p.forget_bias = forget_bias;
+    p.wcT = (const uint16_t*)wcT; p.kxT = (const uint16_t*)kxT; p.bias = bias;
+    p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths;
+    p.mt_seq = (uint16_t*)mt_seq; p.save = save; p.Ik = Ik;
+    p.post = nullptr; p.wait = nullptr; p.wait_per_step = 0;
 }
 
 }  // namespace
@@ -351,39 +550,110 @@ int rsr_lstmp_fused_fwd_pair(rsr_handle* h, void* stream, int B, int T, int I, i
                              const void* kxT, const float* bias, const void* wcT, const float* w_i,
                              const float* w_f, const float* w_o, float forget_bias, const int* lengths,
                              void* mt_seq, float* save) {
+    constexpr int NBP = 32;
     if (Cp > 512) return RSR_E_RESIDENT;
     const int Ik = (I + 15) & ~15;
-    if (Cp / 2 + Ik / 2 + 2 * NBP > 512) return RSR_E_RESIDENT;
+    if (Cp / 2 + Ik / 2 + 2 * PairGeom<NBP>::ACCS > 512) return RSR_E_RESIDENT;
     const int G = Cp / 32;
-    const int nch = pair_chains();
-    const size_t smem = pfwd_smem(Cp, Ik, nch);
+    const size_t smem = pfwd_smem(Cp, Ik, NBP);
     if (smem > (size_t)h->max_smem) return RSR_E_RESIDENT;
     const int bf = h->dtype == RSR_DTYPE_BF16;
-    static const int fast = getenv("RSR_FAST_GATES") ? (atoi(getenv("RSR_FAST_GATES")) ? 1 : 0) : 1;
+    const int fast = fast_gates();
     auto run = [&](auto kernel) -> int {
         int& cap = h->pair_cap[0][Cp / 256 - 1];
-        const int key = ((Ik * 4 + nch) * 2 + bf) * 2 + fast;
+        const int key = (Ik * 2 + bf) * 2 + fast;
         if (cap < 0 || h->pair_ik[Cp / 256 - 1] != key) {
             std::lock_guard<std::mutex> g(h->mu);
-            cap = cluster_capacity(kernel, G, PAIR_THREADS, smem);
+            cap = cluster_capacity(kernel, G, PairGeom<NBP>::THREADS, smem);
             h->pair_ik[Cp / 256 - 1] = key;
             if (getenv("RSR_DEBUG")) fprintf(stderr, "[rsr] fused fwd pair kernel Cp=%d Ik=%d: %d-CTA clusters co-resident: %d\n", Cp, Ik, G, cap);
         }
         if (cap <= 0) return RSR_E_RESIDENT;
         const int groups = (B + NBP - 1) / NBP;
         CUtensorMap tmX;
-        int rc = rsr_get_tmap(h, x16, (uint64_t)ldx, (uint64_t)T * B, (uint64_t)ldx, 64, (uint32_t)(NBP / nch / 2), &tmX);
+        int rc = rsr_get_tmap(h, x16, (uint64_t)ldx, (uint64_t)T * B, (uint64_t)ldx, 64, (uint32_t)(NBP / 2), &tmX);
         if (rc) return rc;
         PFwdParams p;
-        p.B = B; p.T = T; p.Cp = Cp; p.bf = bf; p.forget_bias = forget_bias;
-        p.wcT = (const uint16_t*)wcT; p.kxT = (const uint16_t*)kxT; p.bias = bias;
-        p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths;
-        p.mt_seq = (uint16_t*)mt_seq; p.save = save; p.Ik = Ik;
-        return cluster_launch(kernel, groups, G, PAIR_THREADS, smem, (cudaStream_t)stream, tmX, p);
+        fill_fwd_params(p, h, B, T, Cp, Ik, kxT, bias, wcT, w_i, w_f, w_o, forget_bias, lengths, mt_seq, save);
+        return cluster_launch(kernel, groups, G, PairGeom<NBP>::THREADS, smem, (cudaStream_t)stream, tmX, p);
     };
-    if (nch == 2) return bf ? run(lstmp_fwd_pair_kernel<2, 1, 0>) : run(lstmp_fwd_pair_kernel<2, 0, 0>);
-    if (fast) return bf ? run(lstmp_fwd_pair_kernel<1, 1, 1>) : run(lstmp_fwd_pair_kernel<1, 0, 1>);
-    return bf ? run(lstmp_fwd_pair_kernel<1, 1, 0>) : run(lstmp_fwd_pair_kernel<1, 0, 0>);
+    if (fast) return bf ? run(lstmp_fwd_pair_kernel<NBP, 1, 1>) : run(lstmp_fwd_pair_kernel<NBP, 0, 1>);
+    return bf ? run(lstmp_fwd_pair_kernel<NBP, 1, 0>) : run(lstmp_fwd_pair_kernel<NBP, 0, 0>);
+}
+
+// Two stacked LSTMP layers of equal cell count as one wavefront launch (see lstmp_wave_fwd_kernel).  Layer 2's input
+// is layer 1's projected output: I2 = P1, x2 rows = out1 rows.  Returns RSR_E_RESIDENT when the shape does not fit
+// (the caller then runs the layers one after the other).
+extern "C" int rsr_lstmp_wave_fwd(rsr_handle* h, void* stream, const rsr_wave_args* a) {
+    if (!h || !a) return RSR_E_ARG;
+    const int B = a->B, T = a->T, Cp = a->Cp, I1 = a->I1, P1 = a->P1;
+    if (!a->x16 || !a->kxT1 || !a->bias1 || !a->wcT1 || !a->w_i1 || !a->w_f1 || !a->w_o1 || !a->mt1 || !a->wpT1 || !a->out1 ||
+        !a->kxT2 || !a->bias2 || !a->wcT2 || !a->w_i2 || !a->w_f2 || !a->w_o2 || !a->mt2 || !a->lengths)
+        return RSR_E_ARG;
+    if (B <= 0 || T <= 0 || I1 <= 0 || P1 <= 0 || Cp <= 0 || (Cp & 255) || a->ldx < I1 || (a->ldx & 7) || a->ldo1 < P1 || (a->ldo1 & 7))
+        return RSR_E_SHAPE;
+    if (((uintptr_t)a->x16 | (uintptr_t)a->kxT1 | (uintptr_t)a->wcT1 | (uintptr_t)a->mt1 | (uintptr_t)a->save1 | (uintptr_t)a->wpT1 |
+         (uintptr_t)a->out1 | (uintptr_t)a->kxT2 | (uintptr_t)a->wcT2 | (uintptr_t)a->mt2 | (uintptr_t)a->save2) & 15)
+        return RSR_E_ARG;
+    if (getenv("RSR_NO_CLUSTER") || getenv("RSR_NO_PAIR") || getenv("RSR_NO_WAVE") || Cp > 512) return RSR_E_RESIDENT;
+    const int Ik1 = (I1 + 15) & ~15, Ik2 = (P1 + 15) & ~15, Ikm = Ik1 > Ik2 ? Ik1 : Ik2;
+    const int Pp = (P1 + 7) & ~7;
+    const int G = Cp / 32, NFT = (Pp + 127) / 128;
+    const int bf = h->dtype == RSR_DTYPE_BF16, fast = fast_gates();
+    auto run = [&](auto kernel, auto nbp_tag) -> int {
+        constexpr int NBP = decltype(nbp_tag)::value;
+        using GM = PairGeom<NBP>;
+        const int groups = (B + NBP - 1) / NBP;
+        if (Cp / 2 + Ikm / 2 + 2 * GM::ACCS > 512 || groups * NFT > G) return RSR_E_RESIDENT;
+        size_t smem = pfwd_smem(Cp, Ikm, NBP);
+        if (wproj_smem(Cp, NBP) > smem) smem = wproj_smem(Cp, NBP);
+        if (smem > (size_t)h->max_smem) return RSR_E_RESIDENT;
+        int cap;
+        {
+            std::lock_guard<std::mutex> g(h->mu);
+            int& c = h->wave_cap[NBP == 32 ? 0 : 1][Cp / 256 - 1];
+            const int key = ((Ikm * 2 + bf) * 2 + fast);
+            if (c < 0 || h->wave_key[NBP == 32 ? 0 : 1][Cp / 256 - 1] != key) {
+                c = cluster_capacity(kernel, G, GM::THREADS, smem);
+                h->wave_key[NBP == 32 ? 0 : 1][Cp / 256 - 1] = key;
+                if (getenv("RSR_DEBUG")) fprintf(stderr, "[rsr] wave fwd kernel Cp=%d NBP=%d: %d-CTA clusters co-resident: %d\n", Cp, NBP, G, c);
+            }
+            cap = c;
+        }
+        if (cap < 2 * groups + 1) return RSR_E_RESIDENT;
+        CUtensorMap tmX1, tmX2, tmM;
+        int rc = rsr_get_tmap(h, a->x16, (uint64_t)a->ldx, (uint64_t)T * B, (uint64_t)a->ldx, 64, (uint32_t)(NBP / 2), &tmX1);
+        if (rc) return rc;
+        // layer 2 reads rows [B, (T+1) B) of out1: its step t is out1 row (t+1) B + b
+        rc = rsr_get_tmap(h, (const uint16_t*)a->out1 + (size_t)B * a->ldo1, (uint64_t)a->ldo1, (uint64_t)T * B, (uint64_t)a->ldo1, 64,
+                          (uint32_t)(NBP / 2), &tmX2);
+        if (rc) return rc;
+        rc = rsr_get_tmap(h, a->mt1, (uint64_t)Cp, (uint64_t)(T + 1) * B, (uint64_t)Cp, 64, (uint32_t)NBP, &tmM);
+        if (rc) return rc;
+        unsigned int* flags = rsr_take_flags(h, 2 * groups);
+        RSR_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * 2 * groups, (cudaStream_t)stream));
+        PFwdParams p1, p2;
+        fill_fwd_params(p1, h, B, T, Cp, Ik1, a->kxT1, a->bias1, a->wcT1, a->w_i1, a->w_f1, a->w_o1, a->forget_bias, a->lengths, a->mt1, a->save1);
+        fill_fwd_params(p2, h, B, T, Cp, Ik2, a->kxT2, a->bias2, a->wcT2, a->w_i2, a->w_f2, a->w_o2, a->forget_bias, a->lengths, a->mt2, a->save2);
+        p1.post = flags;
+        p2.wait = flags + groups; p2.wait_per_step = (unsigned int)NFT;
+        WaveProj w;
+        w.groups = groups; w.P = P1; w.Pp = Pp; w.ldo = a->ldo1; w.wpT = (const uint16_t*)a->wpT1; w.out = (uint16_t*)a->out1;
+        w.flag1 = flags; w.flag2 = flags + groups;
+        return cluster_launch(kernel, 2 * groups + 1, G, GM::THREADS, smem, (cudaStream_t)stream, tmX1, tmX2, tmM, p1, p2, w);
+    };
+    auto pick = [&](auto nbp_tag) -> int {
+        constexpr int NBP = decltype(nbp_tag)::value;
+        if (fast) return bf ? run(lstmp_wave_fwd_kernel<NBP, 1, 1>, nbp_tag) : run(lstmp_wave_fwd_kernel<NBP, 0, 1>, nbp_tag);
+        return bf ? run(lstmp_wave_fwd_kernel<NBP, 1, 0>, nbp_tag) : run(lstmp_wave_fwd_kernel<NBP, 0, 0>, nbp_tag);
+    };
+    // 32 utterances per cluster when the batch seats that way (the faster step), else 48
+    const int force = getenv("RSR_WAVE_NBP") ? atoi(getenv("RSR_WAVE_NBP")) : 0;
+    if (force != 48) {
+        const int rc = pick(std::integral_constant<int, 32>());
+        if (rc != RSR_E_RESIDENT || force == 32) return rc;
+    }
+    return pick(std::integral_constant<int, 48>());
 }
 
 // =========================================================================================
@@ -423,7 +693,7 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
     const uint32_t j = cluster_ctarank();
     const uint32_t e = j & 1u, pr = j >> 1;     // utterance half, pair index
     const int grp = blockIdx.x / G;
-    const int b0 = grp * NBP + (int)e * NBR;    // first utterance this CTA differentiates
+    const int b0 = grp * NBP_BWD + (int)e * NBR;    // first utterance this CTA differentiates
 
     constexpr uint32_t SLOT = 2048u;                                 // bytes one source pair sends per step: [2][64 cells][8 utt] 16-bit
     const uint32_t sR_bytes = (uint32_t)NP * SLOT;
@@ -438,7 +708,7 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
     //       [128 mt, 128 mt + 128); accumulator of tile mt at columns 128 MT2 + 32 mt
     const uint32_t a_cols = 128u * (uint32_t)MT2;
     uint32_t tcols = 32;
-    while (tcols < a_cols + (uint32_t)(MT2 * NBP)) tcols <<= 1;
+    while (tcols < a_cols + (uint32_t)(MT2 * NBP_BWD)) tcols <<= 1;
     if (tid == GATE_THREADS) {
         mbar_init(barM, 1); mbar_init(full0, 1); mbar_init(full1, 1); mbar_init(dzr, 2);
         fence_mbar_init();
@@ -476,7 +746,7 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
 
     if (warp == 8) {
         if (e == 0 && elect_one_sync()) {
-            const uint32_t idesc = umma_idesc(256, NBP, BF, 0, 0);
+            const uint32_t idesc = umma_idesc(256, NBP_BWD, BF, 0, 0);
             const uint16_t pair_mask = (uint16_t)(3u << (j & ~1u));
             for (int step = 0; step + 1 < p.T; ++step) {
                 mbar_wait(dzr, (uint32_t)(step & 1));      // both CTAs' rows of the dz tile are written
@@ -485,7 +755,7 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
 #pragma unroll
                     for (int kk = 0; kk < 16; ++kk) {
                         const uint64_t db = umma_desc_sw128(sBt + (uint32_t)(kk >> 2) * (NBR * 128u) + (uint32_t)(kk & 3) * 32u, 16, 1024);
-                        tc_mma_f16_ts_2cta(tmem_acc + (uint32_t)(mt * NBP), tmem + (uint32_t)(128 * mt + 8 * kk), db, idesc, kk ? 1u : 0u);
+                        tc_mma_f16_ts_2cta(tmem_acc + (uint32_t)(mt * NBP_BWD), tmem + (uint32_t)(128 * mt + 8 * kk), db, idesc, kk ? 1u : 0u);
                     }
                 }
                 tc_commit_2cta_mc(barM, pair_mask);
@@ -636,7 +906,7 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
             uint32_t acc[2][16];                   // both tiles in flight, one wait
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
-                if (mt < MT2) tmem_ld16_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NBP + ch * 16), acc[mt]);
+                if (mt < MT2) tmem_ld16_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NBP_BWD + ch * 16), acc[mt]);
             tmem_ld_wait();
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
@@ -697,7 +967,7 @@ int rsr_lstmp_bwd_pair(rsr_handle* h, void* stream, int B, int T, int Cp, const 
         if (getenv("RSR_DEBUG")) fprintf(stderr, "[rsr] bwd pair kernel Cp=%d: %d-CTA clusters co-resident: %d\n", Cp, G, cap);
     }
     if (cap <= 0) return RSR_E_RESIDENT;
-    const int groups = (B + NBP - 1) / NBP;
+    const int groups = (B + NBP_BWD - 1) / NBP_BWD;
     PBwdParams p;
     p.wc = (const uint16_t*)wc;
     p.B = B; p.T = T; p.Cp = Cp; p.bf = h->dtype == RSR_DTYPE_BF16;

@@ -415,13 +415,7 @@ int pick_nb(int B, int ctas_per_group, int num_sms, int max_smem, int Cp, bool f
     return 0;
 }
 
-unsigned int* take_flags(rsr_handle* h, int n) {
-    std::lock_guard<std::mutex> g(h->mu);
-    if (h->flag_cursor + n > RSR_FLAG_WORDS) h->flag_cursor = 0;
-    unsigned int* f = h->flags + h->flag_cursor;
-    h->flag_cursor += n;
-    return f;
-}
+unsigned int* take_flags(rsr_handle* h, int n) { return rsr_take_flags(h, n); }
 
 }  // namespace
 

@@ -229,6 +229,9 @@ class LSTMP(object):
         self.Ik = packing.round_up(I, 16)
         self.kxT16 = torch.zeros(4 * self.Cp, self.Ik, dtype=h.h16, device=h.device)   # K_x^T (fused forward operand)
         self.fused = True            # cleared the first time the library says the fused variant does not apply
+        self.wpT16 = torch.zeros(self.Pp, self.Cp, dtype=h.h16, device=h.device)       # W_p^T (layer-wavefront operand)
+        self.wave = False            # set by the network on the first layer of a stacked pair (fwd_wave)
+        self.wave_declined = set()   # batch sizes the library declined the wavefront launch for
         if self.Cp > 512 and hasattr(h, "overlap"):
             # L2-exchange recurrence kernels (Cp > 512) spin on counters of co-resident CTAs: nothing else
             # may take SMs while they run, so the side stream is switched off for this model
@@ -257,6 +260,8 @@ class LSTMP(object):
         if self.fused:
             Kx16 = self._w()[0]
             h.transpose16(Kx16, self.Ip, 4 * self.Cp, self.kxT16)
+            if self.wave:
+                h.transpose16(Wp16, self.Cp, self.Pp, self.wpT16)
 
     def fwd(self, ctx, x16, B, T, lengths, save=True, want32=False):
         """x16 [T*B, Ip] -> out_seq16 [(T+1)*B, Pp] (slot 0 = zero initial state; rows B.. are
@@ -283,6 +288,36 @@ class LSTMP(object):
                             work=self.rec_flops(B, T))
         h.gemm(mt[B:], Wp16, rows, self.Pp, Cp, b_mn=True, out16=out[B:], out32=o32)
         return out, o32
+
+    def _fused_operands(self):
+        P = self.net.P
+        return (self.kxT16, P.view(self.prefix + "bias"), self.wcT16, P.view(self.prefix + "w_i_diag"),
+                P.view(self.prefix + "w_f_diag"), P.view(self.prefix + "w_o_diag"))
+
+    def fwd_wave(self, nxt, ctx, x16, B, T, lengths, save=True, want32=False):
+        """This layer and the one stacked on it (`nxt`) as ONE wavefront launch: layer 2 runs a few time steps behind
+        layer 1 instead of after it (rsr_lstmp_wave_fwd).  Returns (out_seq16 of this layer, out_seq16 of nxt, out32 of
+        nxt or None) -- or None when the launch does not apply (the caller then runs the two layers one by one)."""
+        net, h = self.net, self.net.h
+        if not (self.wave and self.fused and nxt.fused and self.Cp == nxt.Cp and nxt.I == self.P and nxt.Ip == self.Pp) \
+                or B in self.wave_declined:
+            return None
+        rows, Cp = T * B, self.Cp
+        k1, k2 = (ctx, self.prefix, B), (ctx, nxt.prefix, B)
+        mt1 = net.ws.get(k1 + ("mt",), rows + B, Cp, h.h16)
+        out1 = net.ws.get(k1 + ("out",), rows + B, self.Pp, h.h16)
+        sv1 = net.ws.get(k1 + ("save",), rows, 5 * Cp, F32) if save else None
+        mt2 = net.ws.get(k2 + ("mt",), rows + B, Cp, h.h16)
+        out2 = net.ws.get(k2 + ("out",), rows + B, nxt.Pp, h.h16)
+        sv2 = net.ws.get(k2 + ("save",), rows, 5 * Cp, F32) if save else None
+        o32 = net.ws.get(k2 + ("o32",), rows, nxt.Pp, F32) if want32 else None
+        work = (self.rec_flops(B, T) + nxt.rec_flops(B, T) + 2.0 * rows * (self.I + nxt.I) * 4 * self.C)
+        if not h.lstmp_wave_fwd(B, T, Cp, self.I, self.P, lengths, x16, self._fused_operands(), mt1, sv1, self.wpT16, out1,
+                                nxt._fused_operands(), mt2, sv2, work=work):
+            self.wave_declined.add(B)
+            return None
+        h.gemm(mt2[B:], nxt._w()[2], rows, nxt.Pp, Cp, b_mn=True, out16=out2[B:], out32=o32)
+        return out1, out2, o32
 
     def bwd(self, ctx, x16, dout16, dout32, B, T, lengths, want_dw=True, want_dx=True, prev_y16=None,
             prev_act=ACT_NONE, resid32=None, want32=False):
@@ -714,6 +749,8 @@ class Generator(Net):
                       FC(net, "g_model/fully_connected", in_dim, proj, ACT_LRELU)]
                 ls += [LSTMP(net, "g_model/rnn/multi_rnn_cell/cell_%d/lstm_cell/" % i, proj, cell, proj)
                        for i in range(L)]
+                for i in range(0, L - 1, 2):      # stacked pairs run as one wavefront launch (LSTMP.fwd_wave)
+                    ls[1 + i].wave = ls[1 + i].Cp <= 512 and float(keep_prob) >= 1.0
                 return ls + [FC(net, "g_model/fully_connected_1", proj, out_dim, ACT_NONE)]
         elif g_type in ("res_lstm_l", "res_lstm_base"):
             # models/res_lstm_l.py:101-138: four LSTMP(760 -> in_dim) layers (the `lstm_num_layer = 3` at :45 is unused)
@@ -779,10 +816,12 @@ class Generator(Net):
                  zeros, None, None, dd16, ws.get(("g", "drop_scratch"), 1, 8, F32), dz32=dd32)
         return dd16, dd32
 
-    def fwd(self, x, B, T, lengths, train=True, x_time_major=False, reuse_staged=False):
+    def fwd(self, x, B, T, lengths, train=True, x_time_major=False, reuse_staged=False, wave=True):
         """x fp32 (B, T, in_dim) batch-major on the device -> y32 [T*B, out_pad] time-major fp32.
         reuse_staged: the 16-bit time-major copy of this same x from the previous call is still valid (the second
-        generator forward of a batch schedule sees the same minibatch)."""
+        generator forward of a batch schedule sees the same minibatch).
+        wave: stacked LSTMP pairs may run as one layer-wavefront launch.  It takes 7 sixteen-CTA clusters (112 SMs) where
+        the layer-by-layer kernels take 4, so a caller that has other work for those SMs on the side stream says no."""
         h, ws, rows = self.h, self.ws, T * B
         if self.g_type == "rced":
             self._B, self._T, self._len = B, T, lengths
@@ -820,11 +859,23 @@ class Generator(Net):
             h0, _ = self.layers[0].fwd("g", x16, rows)
             self._acts = [x16, h0]
             a = h0
-            for li, l in enumerate(self.layers[1:-1]):
+            rec, li = self.layers[1:-1], 0
+            while li < len(rec):
+                l = rec[li]
+                # two stacked layers as one wavefront launch (no DropoutWrapper between them)
+                w = (l.fwd_wave(rec[li + 1], "g", a, B, T, lengths, save=train)
+                     if (wave and not drop and li + 1 < len(rec)) else None)
+                if w is not None:
+                    self._o32 += [None, None]
+                    self._acts += [w[0][B:], w[1][B:]]
+                    a = w[1][B:]
+                    li += 2
+                    continue
                 seq, o32 = l.fwd("g", a, B, T, lengths, save=train, want32=drop)
                 a = self._drop_fwd(li, o32, rows)[0] if drop else seq[B:]
                 self._o32.append(o32)
                 self._acts.append(a)
+                li += 1
             _, y32 = self.layers[-1].fwd("g", a, rows, want16=False, want32=True)
             return y32
         a16, a32 = x16, x32

@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT_CLIP, ACT_LRELU, ACT_NONE, ACT_RELU, GemmArgs, check  # noqa: F401
+from ._lib import ACT_CLIP, ACT_LRELU, ACT_NONE, ACT_RELU, GemmArgs, WaveArgs, check  # noqa: F401
 
 H16 = {0: torch.float16, 1: torch.bfloat16}
 
@@ -182,6 +182,38 @@ class Handle(object):
         if rc == _lib.RSR_E_RESIDENT:
             return False
         check(rc, "rsr_lstmp_fused_fwd")
+        self.launches += 1
+        return True
+
+    def lstmp_wave_fwd(self, B, T, Cp, I1, P1, lengths, x16, l1, mt1, save1, wpT1, out1, l2, mt2, save2,
+                       forget_bias=1.0, work=0.0):
+        """Two stacked LSTMP layers as one wavefront launch (rsr_lstmp_wave_fwd).  l1 / l2 = (kxT, bias, wcT, w_i, w_f,
+        w_o) of the layers.  Returns False (nothing launched) when the shape does not apply."""
+        a = WaveArgs()
+        a.B, a.T, a.Cp, a.I1, a.P1, a.forget_bias = B, T, Cp, I1, P1, forget_bias
+        a.lengths = _p(lengths)
+        a.x16, a.ldx = _p(x16), x16.stride(0)
+        a.kxT1, a.bias1, a.wcT1, a.w_i1, a.w_f1, a.w_o1 = (_p(t) for t in l1)
+        a.mt1, a.save1, a.wpT1 = _p(mt1), _p(save1), _p(wpT1)
+        a.out1, a.ldo1 = _p(out1), out1.stride(0)
+        a.kxT2, a.bias2, a.wcT2, a.w_i2, a.w_f2, a.w_o2 = (_p(t) for t in l2)
+        a.mt2, a.save2 = _p(mt2), _p(save2)
+        fn = self.lib.rsr_lstmp_wave_fwd
+        timed = self.timing is not None or self.timeline is not None
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        rc = fn(self.h, _stream(), C.byref(a))
+        if timed:
+            e1.record()
+            if rc == 0 and self.timing is not None:
+                self.timing.append(("rsr_lstmp_wave_fwd", e0, e1, work))
+            if rc == 0 and self.timeline is not None:
+                cur = torch.cuda.current_stream()
+                self.timeline.append(("rsr_lstmp_wave_fwd", "side" if cur == self._side else "main", e0, e1, work))
+        if rc == _lib.RSR_E_RESIDENT:
+            return False
+        check(rc, "rsr_lstmp_wave_fwd")
         self.launches += 1
         return True
 

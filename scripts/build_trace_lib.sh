@@ -8,7 +8,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -cudart static -DRSR_TRACE)
 mkdir -p "$C/build/trace"
 pids=()
-for f in gemm_sm100 elementwise batchnorm lstmp_sm100 lstmp_cluster_sm100 lstmp_pair_sm100; do
+for f in gemm_sm100 elementwise batchnorm lstmp_sm100 lstmp_cluster_sm100 lstmp_pair_sm100 peer_allreduce; do
   "$NVCC" "${FLAGS[@]}" -c "$C/$f.cu" -o "$C/build/trace/$f.o" > "$C/build/trace/$f.log" 2>&1 &
   pids+=($!)
 done

@@ -1,0 +1,63 @@
+"""Times rsr_lstmp_wave_fwd (two stacked LSTMP layers as one wavefront launch) against the same two layers run one
+after the other (fused forward, projection GEMM, fused forward).  usage: gpu_bench_wave.py [f16|bf16]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rsrgan_b200 import ops, packing  # noqa: E402
+
+h = ops.Handle(0, sys.argv[1] if len(sys.argv) > 1 else "f16")
+dev = h.device
+
+
+def layer(rng, I, Cp, P):
+    Ik, Pp = packing.round_up(I, 16), packing.round_up(P, 8)
+    r = lambda *s: torch.tensor(rng.standard_normal(s).astype(np.float32) * 0.05, device=dev)
+    return (r(4 * Cp, Ik).to(h.h16), r(4 * Cp), r(4 * Cp, Cp).to(h.h16), r(Cp), r(Cp), r(Cp)), r(Pp, Cp).to(h.h16)
+
+
+def timeit(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+print("%5s %5s %5s %5s | %10s %8s | %10s %8s | %s" % ("B", "T", "Cp", "nbp", "serial us", "us/step", "wave us", "us/step", "ok"))
+for (B, T, I, Cp, P, nbp) in [(128, 100, 256, 512, 256, 0), (96, 100, 256, 512, 256, 32), (96, 100, 256, 512, 256, 48),
+                              (64, 100, 256, 512, 256, 32), (128, 200, 256, 512, 256, 0), (64, 100, 40, 256, 40, 0)]:
+    if nbp:
+        os.environ["RSR_WAVE_NBP"] = str(nbp)
+    else:
+        os.environ.pop("RSR_WAVE_NBP", None)
+    rng = np.random.default_rng(1)
+    Ip, Pp = packing.round_up(I, 8), packing.round_up(P, 8)
+    (d1, wpT1), (d2, _) = layer(rng, I, Cp, P), layer(rng, P, Cp, P)
+    x16 = torch.tensor(rng.standard_normal((T * B, Ip)).astype(np.float32), device=dev).to(h.h16)
+    d_len = torch.full((B,), T, dtype=torch.int32, device=dev)
+    mk = lambda cols: torch.zeros((T + 1) * B, cols, dtype=h.h16, device=dev)
+    mt1, mt2, out1 = mk(Cp), mk(Cp), mk(Pp)
+    sv1, sv2 = (torch.zeros(T * B, 5 * Cp, dtype=torch.float32, device=dev) for _ in range(2))
+
+    def serial():
+        h.lstmp_fused_fwd(B, T, I, Cp, x16, *d1, d_len, mt1, sv1)
+        h.gemm(mt1[B:], wpT1, T * B, Pp, Cp, out16=out1[B:])
+        h.lstmp_fused_fwd(B, T, P, Cp, out1[B:], *d2, d_len, mt2, sv2)
+
+    ok = [True]
+
+    def wave():
+        ok[0] = h.lstmp_wave_fwd(B, T, Cp, I, P, d_len, x16, d1, mt1, sv1, wpT1, out1, d2, mt2, sv2) and ok[0]
+
+    ts = timeit(serial)
+    tw = timeit(wave)
+    print("%5d %5d %5d %5d | %10.1f %8.2f | %10.1f %8.2f | %s" % (B, T, Cp, nbp, ts, ts / (2 * T), tw, tw / T, ok[0]))

@@ -31,6 +31,15 @@ if which == "pfwd":      # fused forward, CTA-pair kernel (lstmp_pair_sm100.cu)
     bias = torch.randn(4 * Cp, device=dev) * 0.1
     for _ in range(3):
         assert h.lstmp_fused_fwd(B, T, I, Cp, x16, kxT, bias, wcT, w[0], w[1], w[2], ln, mt, save)
+elif which == "wave":    # two stacked layers as one wavefront launch; the trace is layer 1's first cluster
+    I = 256
+    x16 = (torch.randn(rows, I, device=dev) * 0.5).to(h.h16)
+    mk = lambda: ((torch.randn(4 * Cp, I, device=dev) * 0.03).to(h.h16), torch.randn(4 * Cp, device=dev) * 0.1, wcT, w[0], w[1], w[2])
+    wpT = (torch.randn(I, Cp, device=dev) * 0.03).to(h.h16)
+    mt2, out1, save2 = torch.zeros_like(mt), torch.zeros(rows + B, I, dtype=h.h16, device=dev), torch.zeros_like(save)
+    l1, l2 = mk(), mk()
+    for _ in range(3):
+        assert h.lstmp_wave_fwd(B, T, Cp, I, I, ln, x16, l1, mt, save, wpT, out1, l2, mt2, save2)
 elif which == "bwd":
     wc = wcT.t().contiguous()
     dmt = torch.randn(rows, Cp, device=dev) * 0.01
@@ -44,11 +53,11 @@ else:
         h.lstmp_rec_fwd(B, T, Cp, zx, wcT, w[0], w[1], w[2], ln, mt, save)
 torch.cuda.synchronize()
 buf = (C.c_ulonglong * (64 * 8))()
-fn = h.lib.rsr_debug_trace_pair if (which.startswith("p") or (which == "bwd" and B > 16 and not os.environ.get("RSR_NO_PAIR"))) else h.lib.rsr_debug_trace
+fn = h.lib.rsr_debug_trace_pair if (which.startswith("p") or which == "wave" or (which == "bwd" and B > 16 and not os.environ.get("RSR_NO_PAIR"))) else h.lib.rsr_debug_trace
 fn.argtypes = [C.c_void_p, C.c_int]
 rc = fn(buf, 64 * 8)
 tr = np.array(buf[:], dtype=np.int64).reshape(64, 8)[:T]
-names = (["top", "full-wait done", "mma issued", "mma done", "xchg+sync", "gate math", "st.async sends", "global stores"] if which in ("fwd", "pfwd") else
+names = (["top", "full-wait done", "mma issued", "mma done", "xchg+sync", "gate math", "st.async sends", "global stores"] if which in ("fwd", "pfwd", "wave") else
          ["top", "partials landed", "summed", "gate math", "dz stores", "bar+mma issued", "mma done", "ld+send"])
 print(which, "B %d Cp %d rc %d; cycles between trace points (median over steps 5..%d)" % (B, Cp, rc, T - 2))
 nt = len(names)

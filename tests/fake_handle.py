@@ -55,6 +55,9 @@ class FakeHandle(object):
     def lstmp_fused_fwd(self, *a, **k):      # the double has no fused variant: callers fall back to gemm + rec
         return False
 
+    def lstmp_wave_fwd(self, *a, **k):       # ... and no layer-wavefront launch: the layers run one after the other
+        return False
+
     def transpose16(self, src, rows, cols, dst):
         self.launches += 1
         dst[:cols, :rows] = src[:rows, :cols].t()

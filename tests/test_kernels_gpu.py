@@ -207,6 +207,75 @@ def test_lstmp_fused_forward(h, B, T, I, C, P, ragged):
     assert torch.equal(dst[:130, :70], src.t()) and float(dst[130:].abs().max()) == 0 and float(dst[:, 70:].abs().max()) == 0
 
 
+def _fused_operands(h, rng, I, C, P, Cp):
+    """Random LSTMP layer: oracle weights + the device operands of the fused forward kernels."""
+    dev = h.device
+    Ik = packing.round_up(I, 16)
+    K = O.xavier(rng, (I + P, 4 * C)) * 2.0
+    b = rng.standard_normal(4 * C) * 0.1
+    wi, wf, wo = (O.xavier(rng, (C,)) for _ in range(3))
+    Wp = O.xavier(rng, (C, P)) * 2.0
+    kxT = torch.zeros(4 * Cp, Ik, dtype=h.h16, device=dev)
+    kxT[:, :I] = torch.tensor(packing.pack_cols(K[:I], C).T.copy(), device=dev).to(h.h16)
+    wcT16 = torch.tensor(packing.pad_first(packing.pack_cols(Wp @ K[I:], C), Cp), device=dev).to(h.h16).t().contiguous()
+    pk = lambda v: torch.tensor(packing.pad_last(v, Cp).astype(np.float32), device=dev)
+    bias_p = torch.tensor(packing.pack_cols(b[None], C)[0].astype(np.float32), device=dev)
+    Pp = packing.round_up(P, 8)
+    wpT = torch.zeros(Pp, Cp, dtype=h.h16, device=dev)
+    wpT[:P, :C] = torch.tensor(Wp.T.copy(), device=dev).to(h.h16)
+    return (K, b, wi, wf, wo, Wp), (kxT, bias_p, wcT16, pk(wi), pk(wf), pk(wo)), wpT
+
+
+@pytest.mark.parametrize("B,T,I,C,P,ragged,nbp", [
+    (40, 10, 256, 512, 256, True, 0),       # BASELINE cfg-2 stack: 32 utterances per cluster, 2 + 2 + 1 clusters
+    (128, 12, 256, 512, 256, True, 0),      # ... at the benchmarked batch: 48 per cluster, 3 + 3 + 1 clusters (all that fit)
+    (100, 7, 256, 512, 256, False, 48),     # last group partial (4 of 48)
+    (8, 12, 40, 256, 40, True, 0),          # discriminator_lstm stack: 8-CTA clusters, one 40-wide feature tile
+    (70, 9, 257, 256, 257, True, 0),        # 257-wide projection: three feature tiles, ldo = 264, Ik = 272
+    (3, 1, 40, 256, 40, False, 32),         # a single frame
+])
+def test_lstmp_wave_forward(h, monkeypatch, B, T, I, C, P, ragged, nbp):
+    """rsr_lstmp_wave_fwd (two stacked LSTMP layers, layer 2 a few steps behind layer 1 in the same launch) == the oracle's
+    two dynamic_rnn layers, and == the one-after-the-other kernels bit for bit."""
+    if nbp:
+        monkeypatch.setenv("RSR_WAVE_NBP", str(nbp))
+    dev, rng = h.device, np.random.default_rng(B + I + T)
+    Cp, Ip, Pp = packing.cell_pad(C), packing.round_up(I, 8), packing.round_up(P, 8)
+    x = rng.standard_normal((B, T, I))
+    lengths = rng.integers(max(T // 2, 1), T + 1, size=B) if ragged else np.full(B, T)
+    (w1, d1, wpT1), (w2, d2, _) = _fused_operands(h, rng, I, C, P, Cp), _fused_operands(h, rng, P, C, P, Cp)
+    out1_ref, c1 = O.lstmp_fwd(x, lengths, *w1)
+    out2_ref, c2 = O.lstmp_fwd(out1_ref, lengths, *w2)
+    x16 = torch.zeros(T * B, Ip, dtype=h.h16, device=dev)
+    x16[:, :I] = torch.tensor(x.transpose(1, 0, 2).reshape(T * B, I), device=dev).to(h.h16)
+    d_len = torch.tensor(lengths.astype(np.int32), device=dev)
+    mk = lambda cols, dt: torch.zeros((T + 1) * B, cols, dtype=dt, device=dev)
+    mt1, mt2, out1 = mk(Cp, h.h16), mk(Cp, h.h16), mk(Pp, h.h16)
+    sv1, sv2 = (torch.zeros(T * B, 5 * Cp, dtype=torch.float32, device=dev) for _ in range(2))
+    ok = h.lstmp_wave_fwd(B, T, Cp, I, P, d_len, x16, d1, mt1, sv1, wpT1, out1, d2, mt2, sv2)
+    torch.cuda.synchronize()
+    assert ok
+    t16 = tol(h, 1.5e-3, 1e-2)
+    mref = lambda c: np.stack([np.where(c[-1][t][9], c[-1][t][8], 0.0) for t in range(T)])
+    got1 = mt1[B:].float().cpu().numpy().reshape(T, B, Cp)
+    got2 = mt2[B:].float().cpu().numpy().reshape(T, B, Cp)
+    o1 = out1[B:].float().cpu().numpy().reshape(T, B, Pp)
+    assert rel(got1[:, :, :C], mref(c1)) < t16
+    assert rel(o1[:, :, :P].transpose(1, 0, 2), out1_ref) < t16
+    assert rel(got2[:, :, :C], mref(c2)) < 2 * t16
+    assert float(out1[:B].abs().max()) == 0.0 and (Pp == P or float(np.abs(o1[:, :, P:]).max()) == 0.0)
+    # the same two layers one after the other (fused forward, projection GEMM, fused forward)
+    s_mt1, s_mt2, s_out1 = mk(Cp, h.h16), mk(Cp, h.h16), mk(Pp, h.h16)
+    s_sv1, s_sv2 = torch.zeros_like(sv1), torch.zeros_like(sv2)
+    assert h.lstmp_fused_fwd(B, T, I, Cp, x16, *d1, d_len, s_mt1, s_sv1)
+    h.gemm(s_mt1[B:], wpT1, T * B, Pp, Cp, out16=s_out1[B:])
+    assert h.lstmp_fused_fwd(B, T, P, Cp, s_out1[B:], *d2, d_len, s_mt2, s_sv2)
+    torch.cuda.synchronize()
+    assert torch.equal(mt1, s_mt1) and torch.equal(sv1, s_sv1)
+    assert float((out1.float() - s_out1.float()).abs().max()) <= 2e-3 * float(s_out1.float().abs().max())
+    assert rel(got2, s_mt2[B:].float().cpu().numpy().reshape(T, B, Cp)) < 2e-3
+
+
 def test_lstmp_shape_errors(h):
     z = torch.zeros(8, device=h.device)
     from rsrgan_b200 import _lib
