@@ -172,6 +172,27 @@ typedef struct rsr_wave_args {
     void* mt2; float* save2;
 } rsr_wave_args;
 int rsr_lstmp_wave_fwd(rsr_handle* h, void* stream, const rsr_wave_args* a);
+/* Layer wavefront, backward (tf.gradients through the MultiRNNCell while-loop of models/lstm.py:89-112): the reversed
+ * recurrences of layer 2 and layer 1 in one launch, layer 1 a few steps behind.  Between them a stage turns every dz2_t
+ * into layer 1's incoming gradient  dmt1_t = (dz2_t K_x2^T) W_p1^T = dz2_t F^T  with  F = W_p1 K_x2  resident in TMEM.
+ *   dmt2    fp32 [T*B, Cp]        dOut2 W_p2^T (from rsr_gemm), read only
+ *   fT      h16  [Cp, 4Cp]        F: row = layer-1 cell, columns = layer-2 packed gate columns (refreshed with the weights)
+ *   part    fp32 T*(B+48)*Cp      scratch for dmt1 (laid out per group of utterances): ALL ZEROS on entry, all zeros again
+ *                                 on return (the stage accumulates its four K-slice partial products into it, layer 1
+ *                                 resets every element as it reads it)
+ * Outputs as two rsr_lstmp_rec_bwd calls: dz2, dz1 (h16 [T*B, 4Cp]) and the bias / peephole gradients (accumulated).
+ * The gradient wrt layer 1's OUTPUT (dz2 K_x2^T), which the weight gradients of layer 1 need, stays an rsr_gemm.
+ * Returns RSR_E_RESIDENT (nothing launched) when the shape does not apply, as rsr_lstmp_wave_fwd. */
+typedef struct rsr_wave_bwd_args {
+    int B, T, Cp;
+    const int* lengths;
+    const float* dmt2; const void* wc2; const float* w_i2; const float* w_f2; const float* w_o2; const float* save2;
+    void* dz2; float* dbias2; float* dw_i2; float* dw_f2; float* dw_o2;
+    const void* fT; float* part;
+    const void* wc1; const float* w_i1; const float* w_f1; const float* w_o1; const float* save1;
+    void* dz1; float* dbias1; float* dw_i1; float* dw_f1; float* dw_o1;
+} rsr_wave_bwd_args;
+int rsr_lstmp_wave_bwd(rsr_handle* h, void* stream, const rsr_wave_bwd_args* a);
 /*   dmt     fp32 [T*B, Cp]    dOut_t * W_proj^T (from rsr_gemm); read only on the cluster path (Cp <= 512), the
  *                              L2-exchange path (Cp > 512) adds the recurrent term dz_{t+1} * Wc^T in place
  *   wc      h16  [Cp, 4Cp]    Wc, packed columns (backward MMA A operand)

@@ -47,6 +47,17 @@ class WaveArgs(C.Structure):
                 ("mt2", vp), ("save2", vp)]
 
 
+class WaveBwdArgs(C.Structure):
+    """rsr_wave_bwd_args (include/rsrgan_b200.h)."""
+    _fields_ = [("B", ci), ("T", ci), ("Cp", ci),
+                ("lengths", vp),
+                ("dmt2", vp), ("wc2", vp), ("w_i2", vp), ("w_f2", vp), ("w_o2", vp), ("save2", vp),
+                ("dz2", vp), ("dbias2", vp), ("dw_i2", vp), ("dw_f2", vp), ("dw_o2", vp),
+                ("fT", vp), ("part", vp),
+                ("wc1", vp), ("w_i1", vp), ("w_f1", vp), ("w_o1", vp), ("save1", vp),
+                ("dz1", vp), ("dbias1", vp), ("dw_i1", vp), ("dw_f1", vp), ("dw_o1", vp)]
+
+
 # name -> argtypes (every symbol include/rsrgan_b200.h declares)
 SIGNATURES = {
     "rsr_version": [],
@@ -62,6 +73,7 @@ SIGNATURES = {
     "rsr_lstmp_rec_fwd": [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, cf, vp, vp, vp],
     "rsr_lstmp_fused_fwd": [vp, vp, ci, ci, ci, ci, vp, ci, vp, vp, vp, vp, vp, vp, cf, vp, vp, vp],
     "rsr_lstmp_wave_fwd": [vp, vp, C.POINTER(WaveArgs)],
+    "rsr_lstmp_wave_bwd": [vp, vp, C.POINTER(WaveBwdArgs)],
     "rsr_transpose16": [vp, vp, vp, ci, ci, ci, vp, ci],
     "rsr_peer_alloc": [vp, cll, C.POINTER(vp), vp],
     "rsr_peer_open": [vp, vp, C.POINTER(vp)],

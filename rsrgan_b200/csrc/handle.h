@@ -51,8 +51,9 @@ struct rsr_handle {
     int fused_ik[2] = {-1, -1};      // Ik the fused-forward capacity entry was computed for
     int pair_cap[2][2] = {{-1, -1}, {-1, -1}};   // CTA-pair kernels (lstmp_pair_sm100.cu): [fwd|bwd][Cp/256 - 1]
     int pair_ik[2] = {-1, -1};
-    int wave_cap[2][2] = {{-1, -1}, {-1, -1}};   // layer-wavefront forward kernel: [NBP 32|48][Cp/256 - 1]
-    int wave_key[2][2] = {{-1, -1}, {-1, -1}};
+    // layer-wavefront kernels: [fwd NBP 32 | fwd 48 | bwd 32 | bwd 48][Cp/256 - 1]
+    int wave_cap[4][2] = {{-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
+    int wave_key[4][2] = {{-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
     int cluster_cap[3][2][2] = {{{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}};   // [2] = fused fwd
 };
 

@@ -72,6 +72,10 @@ __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads)
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// named barrier the gate threads ARRIVE at and the poster warp syncs on, step by step: four ids in rotation, so that
+// arrivals of a later step can only collide with an unconsumed earlier one if the poster fell four steps behind
+__device__ __forceinline__ uint32_t post_bar_id(int step) { return 2u + (uint32_t)(step & 3) + ((step & 3) ? 2u : 0u); }   // 2, 5, 6, 7
+
 // monotonic step counter of another cluster (layer wavefront): returns the value seen once it is >= want; bounded
 __device__ __forceinline__ unsigned int spin_get_ge(const unsigned int* p, unsigned int want) {
     unsigned int v = ld_acquire(p);
@@ -265,7 +269,7 @@ __device__ __forceinline__ void pair_fwd_body(const CUtensorMap* tmX, const PFwd
         // poster (layer wavefront): once every gate thread has stored its piece of mt_t, one release per CTA and step
         if (p.post)
             for (int t = 0; t < p.T; ++t) {
-                named_bar_sync((t & 1) ? 5u : 2u, GT + 32);
+                named_bar_sync(post_bar_id(t), GT + 32);
                 if (lane == 0) red_release_add(p.post + grp, 1u);
             }
     } else {
@@ -349,7 +353,7 @@ __device__ __forceinline__ void pair_fwd_body(const CUtensorMap* tmX, const PFwd
             if (b_own < p.B) *reinterpret_cast<uint2*>(p.mt_seq + (row + p.B) * p.Cp + cell0) = make_uint2(lo, hi);
             // layer wavefront: this CTA's rows of mt_t are on their way; the poster warp releases them to the consumer (the
             // gate warps only ARRIVE: a release fence here costs them ~0.5 us per step, profiles/r2_wave_steps_v0.txt)
-            if (p.post) named_bar_arrive((t & 1) ? 5u : 2u, GT + 32);
+            if (p.post) named_bar_arrive(post_bar_id(t), GT + 32);
             if (b_own < p.B && p.save) {
                 float* s = p.save + row * 5 * p.Cp + cell0;
 #pragma unroll
@@ -525,7 +529,7 @@ size_t pfwd_smem(int Cp, int Ik, int nbp) {
     const size_t need = 1024 + 2 * xt + 2 * (size_t)Cp * nbr * 2 + 128 * (size_t)(nbp + 1) * 4 + 8 + 64 + 16;
     return need < RSR_EXCLUSIVE_SMEM_REC ? RSR_EXCLUSIVE_SMEM_REC : need;
 }
-size_t wproj_smem(int Cp, int nbp) { return 1024 + 2 * (size_t)(Cp / 64) * nbp * 128 + 64 + 16; }
+size_t wproj_smem(int Cp, int nbp, int stages = 2) { return 1024 + (size_t)stages * (Cp / 64) * nbp * 128 + 128 + 16; }
 
 bool fast_gates() {
     static const int fast = getenv("RSR_FAST_GATES") ? (atoi(getenv("RSR_FAST_GATES")) ? 1 : 0) : 1;
@@ -661,29 +665,46 @@ extern "C" int rsr_lstmp_wave_fwd(rsr_handle* h, void* stream, const rsr_wave_ar
 // =========================================================================================
 namespace {
 
+template <int NBP> struct PairGeomB {
+    static constexpr int NBR = NBP / 2;                 // utterances this CTA differentiates (B-operand rows it produces)
+    static constexpr int GW = NBR / 2;                  // gate-backward warps: thread <-> one cell x 4 utterances
+    static constexpr int GT = 32 * GW;                  // 64 cells x NBR / 4 utterance quads
+    static constexpr int THREADS = GT + 64;             // + the issuer warp + the poster warp (layer wavefront)
+    static constexpr int ACCS = NBP <= 32 ? 32 : 64;    // TMEM column stride between the output tiles' accumulators
+    static constexpr uint32_t SLOT = NBR * 128u;        // bytes one source pair sends per step: [NBR/8][64 cells][8 utt] 16-bit
+};
+
 struct PBwdParams {
     int B, T, Cp, bf;
-    const float* dmt;           // [T*B, Cp] dOut W_p^T (read only)
+    const float* dmt;           // [T*B, Cp] dOut W_p^T, read only -- or, with `grouped`,
+    int grouped;                // layer wavefront: [T][groups][Cp][NBP] (utterances of a group contiguous), accumulated by the
+    int groups;                 //   producer stage; every element is reset to 0 once read
     const uint16_t* wc;         // [Cp, 4Cp] packed gate columns
     const float* w_i; const float* w_f; const float* w_o;
     const int* lengths;
     const float* save;          // [T*B, 5, Cp]
     uint16_t* dz16;             // [T*B, 4Cp] packed
     float* dbias; float* dw_i; float* dw_f; float* dw_o;
+    // layer wavefront (null / 0 otherwise): post[grp] += 1 per CTA once its piece of dz_t is in global memory; the dmt rows
+    // of step s (t = T-1-s) may be read once wait[grp] >= wait_per_step * (s + 1)
+    unsigned int* post;
+    const unsigned int* wait;
+    unsigned int wait_per_step;
 };
 
 // dmt_{t-1} = dOut_{t-1} W_p^T + dz_t Wc^T, split along K over the G/2 PAIRS of the cluster: pair p owns the four gates
-// of cells [64p, 64p+64) (256 packed gate columns) for the 32 utterances of the group -- CTA (p, e) computes dz_t of those
-// cells for utterances [16e, 16e+16) (no exchange of the B operand: its 16 rows of the pair's B tile are produced
-// locally), the pair runs ONE tcgen05.mma.cta_group::2 per k-step (M = 256 output cells: 128 per CTA, N = 32, K = 256;
-// Wc slices resident in TMEM) and every CTA reduce-scatters its partial rows, 16-bit, to the CTA that owns (cell block,
-// utterance half).  Per SM and step 16 KB leave for 32 utterances (the single-CTA kernel ships 16 KB per 16), and one
-// CTA issues the MMAs of two.  Warps 0-7: gate backward (thread <-> one cell x 4 utterances) and the sends; warp 8 of the
-// even CTA: MMA issuer.
-template <int BF, int FAST>
-__global__ void __launch_bounds__(PAIR_THREADS, 1)
-lstmp_bwd_pair_kernel(const PBwdParams p) {
-    constexpr int NBR = 16;                     // B-operand rows (utterances) per CTA
+// of cells [64p, 64p+64) (256 packed gate columns) for the NBP utterances of the group -- CTA (p, e) computes dz_t of
+// those cells for utterances [NBR e, NBR e + NBR) (no exchange of the B operand: its rows of the pair's B tile are
+// produced locally), the pair runs ONE tcgen05.mma.cta_group::2 per k-step (M = 256 output cells: 128 per CTA, N = NBP,
+// K = 256; Wc slices resident in TMEM) and every CTA reduce-scatters its partial rows, 16-bit, to the CTA that owns (cell
+// block, utterance half).  Per SM and step 16 KB leave for 32 utterances (the single-CTA kernel ships 16 KB per 16), and
+// one CTA issues the MMAs of two.  Warps 0..GW-1: gate backward (thread <-> one cell x 4 utterances) and the sends; warp
+// GW: MMA issuer (even CTA); warp GW+1: in the layer wavefront, the poster of this CTA's dz_t.
+template <int NBP, int BF, int FAST>
+__device__ __forceinline__ void pair_bwd_body(const PBwdParams& p, const int grp) {
+    using GM = PairGeomB<NBP>;
+    constexpr int NBR = GM::NBR, GW = GM::GW, GT = GM::GT, ACCS = GM::ACCS;
+    constexpr uint32_t SLOT = GM::SLOT;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -692,12 +713,10 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
     const int MT2 = p.Cp / 256;                 // 256-row output tiles of the pair product: 1 or 2
     const uint32_t j = cluster_ctarank();
     const uint32_t e = j & 1u, pr = j >> 1;     // utterance half, pair index
-    const int grp = blockIdx.x / G;
-    const int b0 = grp * NBP_BWD + (int)e * NBR;    // first utterance this CTA differentiates
+    const int b0 = grp * NBP + (int)e * NBR;    // first utterance this CTA differentiates
 
-    constexpr uint32_t SLOT = 2048u;                                 // bytes one source pair sends per step: [2][64 cells][8 utt] 16-bit
     const uint32_t sR_bytes = (uint32_t)NP * SLOT;
-    const uint32_t sBt = base;                                       // dz tile: 4 k-subtiles [16 rows x 64 k] 16-bit, SW128
+    const uint32_t sBt = base;                                       // dz tile: 4 k-subtiles [NBR rows x 64 k] 16-bit, SW128
     const uint32_t sR0 = sBt + 4u * NBR * 128u;                      // two receive buffers
     const uint32_t sBar = sR0 + 2u * sR_bytes;
     const uint32_t barM = sBar, full0 = sBar + 8, full1 = sBar + 16, dzr = sBar + 24;
@@ -705,17 +724,17 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
     uint8_t* sB_ptr = base_ptr + (sBt - base);
 
     // TMEM: tile mt of the A operand (rows = output cells 256 mt + 128 e + lane, K = the pair's 256 gate columns) at columns
-    //       [128 mt, 128 mt + 128); accumulator of tile mt at columns 128 MT2 + 32 mt
+    //       [128 mt, 128 mt + 128); accumulator of tile mt at columns 128 MT2 + ACCS mt
     const uint32_t a_cols = 128u * (uint32_t)MT2;
     uint32_t tcols = 32;
-    while (tcols < a_cols + (uint32_t)(MT2 * NBP_BWD)) tcols <<= 1;
-    if (tid == GATE_THREADS) {
+    while (tcols < a_cols + (uint32_t)(MT2 * ACCS)) tcols <<= 1;
+    if (tid == GT) {
         mbar_init(barM, 1); mbar_init(full0, 1); mbar_init(full1, 1); mbar_init(dzr, 2);
         fence_mbar_init();
         mbar_expect_tx(full1, sR_bytes);
         mbar_expect_tx(full0, sR_bytes);
     }
-    if (warp == 8) tmem_alloc_2cta(tslot, tcols);
+    if (warp == GW) tmem_alloc_2cta(tslot, tcols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -744,9 +763,9 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
 
     const uint32_t lead = mapa_u32(base, j & ~1u) - base;
 
-    if (warp == 8) {
+    if (warp == GW) {
         if (e == 0 && elect_one_sync()) {
-            const uint32_t idesc = umma_idesc(256, NBP_BWD, BF, 0, 0);
+            const uint32_t idesc = umma_idesc(256, NBP, BF, 0, 0);
             const uint16_t pair_mask = (uint16_t)(3u << (j & ~1u));
             for (int step = 0; step + 1 < p.T; ++step) {
                 mbar_wait(dzr, (uint32_t)(step & 1));      // both CTAs' rows of the dz tile are written
@@ -755,7 +774,7 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
 #pragma unroll
                     for (int kk = 0; kk < 16; ++kk) {
                         const uint64_t db = umma_desc_sw128(sBt + (uint32_t)(kk >> 2) * (NBR * 128u) + (uint32_t)(kk & 3) * 32u, 16, 1024);
-                        tc_mma_f16_ts_2cta(tmem_acc + (uint32_t)(mt * NBP_BWD), tmem + (uint32_t)(128 * mt + 8 * kk), db, idesc, kk ? 1u : 0u);
+                        tc_mma_f16_ts_2cta(tmem_acc + (uint32_t)(mt * ACCS), tmem + (uint32_t)(128 * mt + 8 * kk), db, idesc, kk ? 1u : 0u);
                     }
                 }
                 tc_commit_2cta_mc(barM, pair_mask);
@@ -763,8 +782,16 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
             }
         }
         __syncwarp();
+    } else if (warp == GW + 1) {
+        // poster (layer wavefront): every gate thread has stored its piece of dz_t (they only arrive); one release per CTA
+        // and step -- the fence behind it waits for those scattered 2-byte stores, which is why no busy warp does it
+        if (p.post)
+            for (int step = 0; step < p.T; ++step) {
+                named_bar_sync(post_bar_id(step), GT + 32);
+                if (lane == 0) red_release_add(p.post + grp, 1u);
+            }
     } else {
-        // gate-backward ownership: thread <-> (cell 64 pr + cc, utterances 4 uq + u of this CTA's 16); a warp holds 16
+        // gate-backward ownership: thread <-> (cell 64 pr + cc, utterances 4 uq + u of this CTA's NBR); a warp holds 16
         // cells x 2 utterance quads so that its reads of a received slot are 256 contiguous bytes (no bank conflicts)
         constexpr int UPT = 4;
         const int cc = 16 * (warp & 3) + (lane & 15), uq = 2 * (warp >> 2) + (lane >> 4);
@@ -780,14 +807,19 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
             len[u] = b < p.B ? p.lengths[b] : 0;
         }
         float a_dwi = 0.f, a_dwf = 0.f, a_dwo = 0.f, a_db[4] = {0.f, 0.f, 0.f, 0.f};
-        // sends: this thread drains accumulator rows 32 q + lane, columns [16 ch, +16) of every tile; row 256 mt + 128 e + 32 q +
-        // lane is cell 32 (q & 1) + lane of pair 4 mt + 2 e + q / 2; the 16 utterances belong to the CTA of parity ch
-        const int q = warp & 3, ch = warp >> 2;
-        uint32_t rd[2];
+        // sends: this thread drains accumulator rows 32 q + lane, columns [16 piece, +16) of every tile; row 256 mt + 128 e +
+        // 32 q + lane is cell 32 (q & 1) + lane of pair 4 mt + 2 e + q / 2; each 8-column unit (8 utterances) goes to the CTA
+        // of that pair which holds the unit's utterance half
+        const int q = warp & 3, piece = warp >> 2;
+        uint32_t rd[2][2], soff[2];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-            rd[mt] = mt < MT2 ? mapa_u32(base, (uint32_t)(2 * (4 * mt + 2 * (int)e + (q >> 1)) + ch)) - base : 0u;
-        const uint32_t soff = pr * SLOT + (uint32_t)(32 * (q & 1) + lane) * 16u;
+        for (int c = 0; c < 2; ++c) {
+            const int u8 = 2 * piece + c, par = u8 / (NBR / 8), hh = u8 % (NBR / 8);
+            soff[c] = pr * SLOT + (uint32_t)hh * 1024u + (uint32_t)(32 * (q & 1) + lane) * 16u;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+                rd[mt][c] = mt < MT2 ? mapa_u32(base, (uint32_t)(2 * (4 * mt + 2 * (int)e + (q >> 1)) + par)) - base : 0u;
+        }
         const size_t Cp = (size_t)p.Cp;
         // my 4 utterances inside the 16-byte chunk [h][cell][8 utterances] of a source slot
         const uint32_t roff = (uint32_t)(uq >> 1) * 1024u + (uint32_t)cc * 16u + (uint32_t)(uq & 1) * 8u;
@@ -795,9 +827,39 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
         const uint32_t zoff = (uint32_t)(2 * (cc >> 5)) * (NBR * 128u);
         uint16_t* dzg = p.dz16 + 256 * pr + 128 * (cc >> 5) + (cc & 31);
 
+        // layer wavefront: the dmt rows come from another cluster of this grid
+        unsigned int seen = 0;
+        auto dm_ready = [&](int s) {
+            if (p.wait) {
+                const unsigned int need = p.wait_per_step * (unsigned int)(s + 1);
+                if (seen < need) {
+                    unsigned int v = 0;
+                    if (lane == 0) v = spin_get_ge(p.wait + grp, need);
+                    seen = __shfl_sync(0xffffffffu, v, 0);
+                }
+            }
+        };
+        // dmt of time step t for this thread's four utterances
+        auto load_dm4 = [&](int t, float* out) {
+            if (p.grouped) {
+                float4* a = reinterpret_cast<float4*>(const_cast<float*>(p.dmt)) +
+                            ((((size_t)t * p.groups + grp) * Cp + cell) * NBP + e * NBR + UPT * uq) / 4;
+                const float4 v = __ldcg(a);
+                __stcg(a, make_float4(0.f, 0.f, 0.f, 0.f));
+                out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+            } else {
+#pragma unroll
+                for (int u = 0; u < UPT; ++u) {
+                    const int b = b0 + UPT * uq + u;
+                    out[u] = b < p.B ? __ldg(p.dmt + ((size_t)t * p.B + b) * Cp + cell) : 0.f;
+                }
+            }
+        };
+
         // saved activations / dmt of step t-1 are loaded one step ahead (see lstmp_bwd_cluster_kernel)
         float s_i[UPT], s_f[UPT], s_o[UPT], s_j[UPT], s_c[UPT], s_cp[UPT], dm[UPT];
         float n_i[UPT], n_f[UPT], n_o[UPT], n_j[UPT], n_cp[UPT], n_dm[UPT];
+        dm_ready(0);
 #pragma unroll
         for (int u = 0; u < UPT; ++u) {
             const int b = b0 + UPT * uq + u;
@@ -808,14 +870,15 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
                 s_i[u] = __ldg(s); s_f[u] = __ldg(s + Cp); s_o[u] = __ldg(s + 2 * Cp); s_j[u] = __ldg(s + 3 * Cp);
                 s_c[u] = __ldg(s + 4 * Cp);
                 if (p.T > 1) s_cp[u] = __ldg(s - (size_t)p.B * 5 * Cp + 4 * Cp);
-                dm[u] = __ldg(p.dmt + row * Cp + cell);
             }
         }
+        load_dm4(p.T - 1, dm);
 
         for (int step = 0; step < p.T; ++step) {
             const int t = p.T - 1 - step;
             const int buf = step & 1;
             PTRACE(tid == 0, step, 0);
+            if (t > 0) dm_ready(step + 1);
 #pragma unroll
             for (int u = 0; u < UPT; ++u) {            // operands of step t-1 (and c_{t-2}): in flight during this step
                 const int b = b0 + UPT * uq + u;
@@ -825,9 +888,9 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
                     const float* s = p.save + row * 5 * Cp + cell;
                     n_i[u] = __ldg(s); n_f[u] = __ldg(s + Cp); n_o[u] = __ldg(s + 2 * Cp); n_j[u] = __ldg(s + 3 * Cp);
                     if (t > 1) n_cp[u] = __ldg(s - (size_t)p.B * 5 * Cp + 4 * Cp);
-                    n_dm[u] = __ldg(p.dmt + row * Cp + cell);
                 }
             }
+            if (t > 0) load_dm4(t - 1, n_dm);
             if (step > 0) {
                 const uint32_t fb = buf ? full1 : full0;
                 mbar_wait(fb, (uint32_t)(((step - 1) >> 1) & 1));   // partial rows of dz_{t+1} Wc^T from all NP pairs
@@ -884,7 +947,7 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
                     *reinterpret_cast<uint16_t*>(sB_ptr + zoff + NBR * 128 + sw128_off(n, 32 + cl)) = hz[u][3];       // g = 3
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1, GATE_THREADS);
+                named_bar_sync(1, GT);
                 if (tid == 0) mbar_arrive_cluster(dzr + lead);
                 PTRACE(tid == 0, step, 4);
             }
@@ -897,16 +960,17 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
                     d[0] = hz[u][0]; d[32] = hz[u][1]; d[64] = hz[u][2]; d[96] = hz[u][3];
                 }
             }
+            if (p.post) named_bar_arrive(post_bar_id(step), GT + 32);
             if (t == 0) break;                     // no earlier step to feed
             mbar_wait(barM, (uint32_t)(step & 1));
             tc_fence_after();
             PTRACE(tid == 0, step, 6);
-            const uint32_t dst0 = sR0 + (uint32_t)(buf ^ 1) * sR_bytes + soff;
+            const uint32_t dst0 = sR0 + (uint32_t)(buf ^ 1) * sR_bytes;
             const uint32_t dbar = buf ? full0 : full1;
             uint32_t acc[2][16];                   // both tiles in flight, one wait
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
-                if (mt < MT2) tmem_ld16_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NBP_BWD + ch * 16), acc[mt]);
+                if (mt < MT2) tmem_ld16_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * ACCS + piece * 16), acc[mt]);
             tmem_ld_wait();
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
@@ -914,11 +978,11 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         const uint32_t* a = acc[mt] + 8 * c;
-                        st_async_v4(dst0 + (uint32_t)c * 1024u + rd[mt],
+                        st_async_v4(dst0 + soff[c] + rd[mt][c],
                                     pack2(__uint_as_float(a[0]), __uint_as_float(a[1]), BF),
                                     pack2(__uint_as_float(a[2]), __uint_as_float(a[3]), BF),
                                     pack2(__uint_as_float(a[4]), __uint_as_float(a[5]), BF),
-                                    pack2(__uint_as_float(a[6]), __uint_as_float(a[7]), BF), dbar + rd[mt]);
+                                    pack2(__uint_as_float(a[6]), __uint_as_float(a[7]), BF), dbar + rd[mt][c]);
                     }
                 }
             }
@@ -939,12 +1003,208 @@ lstmp_bwd_pair_kernel(const PBwdParams p) {
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 8) tmem_dealloc_2cta(tmem, tcols);
+    if (warp == GW) tmem_dealloc_2cta(tmem, tcols);
 }
 
-size_t pbwd_smem(int Cp) {
-    const size_t need = 1024 + 4 * 16 * 128 + 2 * (size_t)(Cp / 64) * 2048 + 64;
+template <int NBP, int BF, int FAST>
+__global__ void __launch_bounds__(PairGeomB<NBP>::THREADS, 1)
+lstmp_bwd_pair_kernel(const PBwdParams p) {
+    pair_bwd_body<NBP, BF, FAST>(p, (int)blockIdx.x / (p.Cp / 32));
+}
+
+// =========================================================================================
+// layer wavefront, backward: layer 2's clusters [0, groups), layer 1's [groups, 2 groups) -- one to a few steps behind --
+// and between them the last cluster, which turns every dz2_t into layer 1's incoming gradient
+//     dmt1_t = (dz2_t K_x2^T) W_p1^T = dz2_t F^T,   F = W_p1 K_x2  [Cp, 4Cp]  (refreshed with the weights, like Wc)
+// CTA (mi, ki) of that cluster keeps rows [128 mi, +128) x columns [Cp ki, +Cp) of F resident in TMEM (A operand, 4 K
+// slices) and per (group, step) runs D[128 cells, NBP utterances] = F slice x dz2_t slice^T (dz2_t by TMA from the global
+// copy layer 2 writes anyway) and adds its K-slice partial into the dmt1 scratch with fire-and-forget 16-byte fp32
+// reductions in L2 (the scratch is laid out [t][group][cell][utterance], so a CTA's tile is one contiguous stream and a
+// layer-1 thread reads its four utterances as one float4); layer 1 resets every element to zero as it reads it, so the
+// scratch is all zeros again when the launch ends (four separate partial buffers summed by the reader were measured
+// first: sixteen dependent L2 loads per thread and step, 7 us per step).  Counters as in the forward wavefront.
+// =========================================================================================
+struct WaveProjB {
+    int groups;
+    const uint16_t* fT;         // [Cp, 4Cp] F (16-bit)
+    float* part;                // dmt1 scratch [T][groups][Cp][NBP], all zeros on entry
+    unsigned int* flagA;        // [groups] posted by layer 2 (G per step)
+    unsigned int* flagB;        // [groups] posted by this stage (G per step)
+};
+
+template <int NBP, int BF>
+__device__ __forceinline__ void wave_projb_body(const CUtensorMap* tmZ, const PBwdParams& p, const WaveProjB& w) {
+    constexpr int ACCS = PairGeomB<NBP>::ACCS;
+    constexpr int MAXG = 8;
+    constexpr int NST = 4;                      // dz2 slices in flight: three groups per step, ~2 us of TMA latency each
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = p.Cp / 32, MT = p.Cp / 128;   // K slices = G / MT = 4, each Cp wide
+    const int c = (int)cluster_ctarank();
+    const int mi = c % MT, ki = c / MT;
+    const int KB = p.Cp / 64;
+    const uint32_t bt_bytes = (uint32_t)KB * NBP * 128u;             // one dz2_t slice: KB sub-tiles [NBP rows x 64 k], SW128
+    constexpr int SP = NBP + 4;                 // staging pitch in floats: 16-byte rows, conflict-free for v4 stores
+    const uint32_t sStage = base + (uint32_t)NST * bt_bytes;         // float stage[128][SP]: the D tile, cell-major
+    const uint32_t sBar = sStage + 128u * SP * 4u;
+    auto sBt = [&](int b) { return base + (uint32_t)b * bt_bytes; };
+    auto fullB = [&](int b) { return sBar + 8u * (uint32_t)b; };
+    auto emptyB = [&](int b) { return sBar + 32u + 8u * (uint32_t)b; };
+    auto accfull = [&](int b) { return sBar + 64u + 8u * (uint32_t)b; };
+    auto accfree = [&](int b) { return sBar + 80u + 8u * (uint32_t)b; };
+    auto done = [&](int b) { return sBar + 96u + 8u * (uint32_t)b; };
+    const uint32_t tslot = sBar + 112u;
+    const uint32_t a_cols = (uint32_t)p.Cp / 2u;
+    uint32_t tcols = 32;
+    while (tcols < a_cols + 2u * ACCS) tcols <<= 1;
+    if (tid == 0) {
+        tma_prefetch_desc(tmZ);
+        for (int b = 0; b < NST; ++b) { mbar_init(fullB(b), 1); mbar_init(emptyB(b), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(accfull(b), 1); mbar_init(accfree(b), 4); }
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(done(0)), "r"(0u) : "memory");
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tslot, tcols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
+    const uint32_t tmem_acc = tmem + a_cols;
+    if (warp < 4) {   // F slice -> TMEM: thread <-> layer-1 cell, 64 k (32 columns) per store
+        const uint16_t* wrow = w.fT + (size_t)(128 * mi + 32 * warp + lane) * 4 * p.Cp + (size_t)ki * p.Cp;
+        for (int cb = 0; cb < KB; ++cb) {
+            uint32_t r[32];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(wrow + cb * 64) + k);
+                r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
+            }
+            tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb * 32u, r);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp >= 7) return;                      // (only mbarriers and named barriers below)
+
+    const int items = p.T * w.groups;           // item = (step, group), step-major
+    if (warp == 0) {
+        if (elect_one_sync()) {                 // producer: dz2_t slices as layer 2 releases them
+            unsigned int seen[MAXG];
+#pragma unroll
+            for (int g = 0; g < MAXG; ++g) seen[g] = 0;
+            for (int it = 0; it < items; ++it) {
+                const int s = it / w.groups, g = it % w.groups, buf = it % NST;
+                if (it >= NST) mbar_wait(emptyB(buf), (uint32_t)((it / NST - 1) & 1));
+                const unsigned int need = (unsigned int)G * (unsigned int)(s + 1);
+                if (seen[g] < need) { seen[g] = spin_get_ge(w.flagA + g, need); fence_proxy_async_all(); }
+                mbar_expect_tx(fullB(buf), bt_bytes);
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(sBt(buf) + (uint32_t)kb * (NBP * 128u), tmZ, fullB(buf), ki * p.Cp + kb * 64,
+                                (p.T - 1 - s) * p.B + g * NBP);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            const uint32_t idesc = umma_idesc(128, NBP, BF, 0, 0);
+            for (int it = 0; it < items; ++it) {
+                const int buf = it % NST, ab = it & 1;
+                mbar_wait(fullB(buf), (uint32_t)((it / NST) & 1));
+                if (it >= 2) mbar_wait(accfree(ab), (uint32_t)(((it - 2) >> 1) & 1));
+                tc_fence_after();
+                const uint32_t sb = sBt(buf);
+                for (int kk = 0; kk < p.Cp / 16; ++kk) {
+                    const uint64_t db = umma_desc_sw128(sb + (uint32_t)(kk >> 2) * (NBP * 128u) + (uint32_t)(kk & 3) * 32u, 16, 1024);
+                    tc_mma_f16_ts(tmem_acc + (uint32_t)ab * ACCS, tmem + (uint32_t)kk * 8u, db, idesc, kk ? 1u : 0u);
+                }
+                tc_commit(emptyB(buf));
+                tc_commit(accfull(ab));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 6) {
+        // poster: releases a whole step's rows (all groups) with ONE fence -- a fence per group would cost more than the
+        // step.  `done` is a monotonic count of (epilogue warp, item) completions in shared memory (no phase to lap).
+        if (elect_one_sync()) {
+            for (int s1 = 1; s1 <= p.T; ++s1) {
+                const unsigned int need = 4u * (unsigned int)(s1 * w.groups);
+                unsigned int v;
+                do {
+                    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(done(0)) : "memory");
+                } while (v < need);
+                __threadfence();
+                for (int g = 0; g < w.groups; ++g)
+                    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(w.flagB + g), "r"(1u) : "memory");
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;                 // warps 2..5 <-> TMEM lane quadrants 2, 3, 0, 1
+        const int et = tid - 64;                // 0..127
+        const uint32_t srow = sStage + (uint32_t)(32 * q + lane) * (SP * 4u);
+        for (int it = 0; it < items; ++it) {
+            const int s = it / w.groups, g = it % w.groups, buf = it & 1;
+            mbar_wait(accfull(buf), (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            uint32_t acc[NBP];
+#pragma unroll
+            for (int c16 = 0; c16 < NBP / 16; ++c16)
+                tmem_ld16_nowait(tmem_acc + (uint32_t)buf * ACCS + ((uint32_t)(q * 32) << 16) + (uint32_t)c16 * 16u, acc + 16 * c16);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accfree(buf));           // this warp's quadrant of the accumulator is drained
+            // D tile -> staging (thread <-> cell row), then the tile leaves as one linear stream of 16-byte reductions:
+            // dmt1 scratch [t][group][cell][NBP], so the 128 x NBP tile of this CTA is NBP * 512 contiguous bytes
+#pragma unroll
+            for (int k = 0; k < NBP / 4; ++k)
+                st_shared_v4(srow + 16u * (uint32_t)k, acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+            named_bar_sync(3u, 128);
+            float* tile = w.part + ((((size_t)(p.T - 1 - s) * w.groups + g) * p.Cp) + 128 * mi) * NBP;
+#pragma unroll
+            for (int k = 0; k < NBP / 4; ++k) {
+                const int f = et + 128 * k, cell = f / (NBP / 4), part = f % (NBP / 4);
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                             : "r"(sStage + (uint32_t)cell * (SP * 4u) + 16u * (uint32_t)part));
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(tile + 4 * (size_t)f), "f"(v.x), "f"(v.y), "f"(v.z),
+                             "f"(v.w) : "memory");
+            }
+            named_bar_sync(5u, 128);                            // staging may be rewritten; all four warps' rows are on their way
+            if (lane == 0) asm volatile("red.release.cta.shared.add.u32 [%0], %1;" ::"r"(done(0)), "r"(1u) : "memory");
+        }
+    }
+    named_bar_sync(4u, 224);
+    if (warp == 0) tmem_dealloc(tmem, tcols);
+}
+
+template <int NBP, int BF, int FAST>
+__global__ void __launch_bounds__(PairGeomB<NBP>::THREADS, 1)
+lstmp_wave_bwd_kernel(const __grid_constant__ CUtensorMap tmZ, const PBwdParams p2, const PBwdParams p1, const WaveProjB w) {
+    const int cid = (int)blockIdx.x / (p2.Cp / 32);
+    if (cid < w.groups) pair_bwd_body<NBP, BF, FAST>(p2, cid);
+    else if (cid < 2 * w.groups) pair_bwd_body<NBP, BF, FAST>(p1, cid - w.groups);
+    else wave_projb_body<NBP, BF>(&tmZ, p2, w);
+}
+
+size_t pbwd_smem(int Cp, int nbp) {
+    const size_t need = 1024 + 4 * (size_t)(nbp / 2) * 128 + 2 * (size_t)(Cp / 64) * (nbp / 2) * 128 + 64;
     return need < RSR_EXCLUSIVE_SMEM_REC ? RSR_EXCLUSIVE_SMEM_REC : need;
+}
+
+void fill_bwd_params(PBwdParams& p, rsr_handle* h, int B, int T, int Cp, const float* dmt, const void* wc, const float* w_i,
+                     const float* w_f, const float* w_o, const int* lengths, const float* save, void* dz16, float* dbias,
+                     float* dw_i, float* dw_f, float* dw_o) {
+    p.wc = (const uint16_t*)wc;
+    p.B = B; p.T = T; p.Cp = Cp; p.bf = h->dtype == RSR_DTYPE_BF16;
+    p.dmt = dmt; p.grouped = 0; p.groups = 0;
+    p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths; p.save = save;
+    p.dz16 = (uint16_t*)dz16; p.dbias = dbias; p.dw_i = dw_i; p.dw_f = dw_f; p.dw_o = dw_o;
+    p.post = nullptr; p.wait = nullptr; p.wait_per_step = 0;
 }
 
 }  // namespace
@@ -952,34 +1212,101 @@ size_t pbwd_smem(int Cp) {
 int rsr_lstmp_bwd_pair(rsr_handle* h, void* stream, int B, int T, int Cp, const float* dmt, const void* wc,
                        const float* w_i, const float* w_f, const float* w_o, const int* lengths,
                        const float* save, void* dz16, float* dbias, float* dw_i, float* dw_f, float* dw_o) {
+    constexpr int NBP = 32;
+    using GM = PairGeomB<NBP>;
     if (Cp > 512) return RSR_E_RESIDENT;
     const int G = Cp / 32;
-    const size_t smem = pbwd_smem(Cp);
+    const size_t smem = pbwd_smem(Cp, NBP);
     int& cap = h->pair_cap[1][Cp / 256 - 1];
     if (cap < 0) {
         std::lock_guard<std::mutex> g(h->mu);
-        cap = cluster_capacity(lstmp_bwd_pair_kernel<0, 0>, G, PAIR_THREADS, smem);
+        cap = cluster_capacity(lstmp_bwd_pair_kernel<NBP, 0, 0>, G, GM::THREADS, smem);
         if (cap > 0) {   // sets the launch attributes of the other instances
-            cluster_capacity(lstmp_bwd_pair_kernel<1, 0>, G, PAIR_THREADS, smem);
-            cluster_capacity(lstmp_bwd_pair_kernel<0, 1>, G, PAIR_THREADS, smem);
-            cluster_capacity(lstmp_bwd_pair_kernel<1, 1>, G, PAIR_THREADS, smem);
+            cluster_capacity(lstmp_bwd_pair_kernel<NBP, 1, 0>, G, GM::THREADS, smem);
+            cluster_capacity(lstmp_bwd_pair_kernel<NBP, 0, 1>, G, GM::THREADS, smem);
+            cluster_capacity(lstmp_bwd_pair_kernel<NBP, 1, 1>, G, GM::THREADS, smem);
         }
         if (getenv("RSR_DEBUG")) fprintf(stderr, "[rsr] bwd pair kernel Cp=%d: %d-CTA clusters co-resident: %d\n", Cp, G, cap);
     }
     if (cap <= 0) return RSR_E_RESIDENT;
-    const int groups = (B + NBP_BWD - 1) / NBP_BWD;
+    const int groups = (B + NBP - 1) / NBP;
     PBwdParams p;
-    p.wc = (const uint16_t*)wc;
-    p.B = B; p.T = T; p.Cp = Cp; p.bf = h->dtype == RSR_DTYPE_BF16;
-    p.dmt = dmt; p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths; p.save = save;
-    p.dz16 = (uint16_t*)dz16; p.dbias = dbias; p.dw_i = dw_i; p.dw_f = dw_f; p.dw_o = dw_o;
-    static const int fast = getenv("RSR_FAST_GATES") ? (atoi(getenv("RSR_FAST_GATES")) ? 1 : 0) : 1;
-    if (fast) {
-        if (p.bf) return cluster_launch(lstmp_bwd_pair_kernel<1, 1>, groups, G, PAIR_THREADS, smem, (cudaStream_t)stream, p);
-        return cluster_launch(lstmp_bwd_pair_kernel<0, 1>, groups, G, PAIR_THREADS, smem, (cudaStream_t)stream, p);
+    fill_bwd_params(p, h, B, T, Cp, dmt, wc, w_i, w_f, w_o, lengths, save, dz16, dbias, dw_i, dw_f, dw_o);
+    if (fast_gates()) {
+        if (p.bf) return cluster_launch(lstmp_bwd_pair_kernel<NBP, 1, 1>, groups, G, GM::THREADS, smem, (cudaStream_t)stream, p);
+        return cluster_launch(lstmp_bwd_pair_kernel<NBP, 0, 1>, groups, G, GM::THREADS, smem, (cudaStream_t)stream, p);
     }
-    if (p.bf) return cluster_launch(lstmp_bwd_pair_kernel<1, 0>, groups, G, PAIR_THREADS, smem, (cudaStream_t)stream, p);
-    return cluster_launch(lstmp_bwd_pair_kernel<0, 0>, groups, G, PAIR_THREADS, smem, (cudaStream_t)stream, p);
+    if (p.bf) return cluster_launch(lstmp_bwd_pair_kernel<NBP, 1, 0>, groups, G, GM::THREADS, smem, (cudaStream_t)stream, p);
+    return cluster_launch(lstmp_bwd_pair_kernel<NBP, 0, 0>, groups, G, GM::THREADS, smem, (cudaStream_t)stream, p);
+}
+
+// Backward of two stacked LSTMP layers of equal cell count as one wavefront launch (see lstmp_wave_bwd_kernel).
+extern "C" int rsr_lstmp_wave_bwd(rsr_handle* h, void* stream, const rsr_wave_bwd_args* a) {
+    if (!h || !a) return RSR_E_ARG;
+    const int B = a->B, T = a->T, Cp = a->Cp;
+    if (!a->lengths || !a->dmt2 || !a->wc2 || !a->w_i2 || !a->w_f2 || !a->w_o2 || !a->save2 || !a->dz2 || !a->dbias2 || !a->dw_i2 ||
+        !a->dw_f2 || !a->dw_o2 || !a->fT || !a->part || !a->wc1 || !a->w_i1 || !a->w_f1 || !a->w_o1 || !a->save1 || !a->dz1 ||
+        !a->dbias1 || !a->dw_i1 || !a->dw_f1 || !a->dw_o1)
+        return RSR_E_ARG;
+    if (B <= 0 || T <= 0 || Cp <= 0 || (Cp & 255)) return RSR_E_SHAPE;
+    if (((uintptr_t)a->dmt2 | (uintptr_t)a->wc2 | (uintptr_t)a->save2 | (uintptr_t)a->dz2 | (uintptr_t)a->fT | (uintptr_t)a->part |
+         (uintptr_t)a->wc1 | (uintptr_t)a->save1 | (uintptr_t)a->dz1) & 15)
+        return RSR_E_ARG;
+    if (getenv("RSR_NO_CLUSTER") || getenv("RSR_NO_PAIR") || getenv("RSR_NO_WAVE") || getenv("RSR_NO_WAVE_BWD") || Cp > 512)
+        return RSR_E_RESIDENT;
+    const int G = Cp / 32;
+    const int bf = h->dtype == RSR_DTYPE_BF16, fast = fast_gates();
+    auto run = [&](auto kernel, auto nbp_tag) -> int {
+        constexpr int NBP = decltype(nbp_tag)::value;
+        using GM = PairGeomB<NBP>;
+        const int groups = (B + NBP - 1) / NBP;
+        if (groups > 8) return RSR_E_RESIDENT;
+        size_t smem = pbwd_smem(Cp, NBP);
+        if (wproj_smem(Cp, NBP, 4) + 128 * (NBP + 4) * 4 > smem) smem = wproj_smem(Cp, NBP, 4) + 128 * (NBP + 4) * 4;
+        if (smem > (size_t)h->max_smem) return RSR_E_RESIDENT;
+        int cap;
+        {
+            std::lock_guard<std::mutex> g(h->mu);
+            int& c = h->wave_cap[2 + (NBP == 32 ? 0 : 1)][Cp / 256 - 1];
+            const int key = bf * 2 + fast;
+            if (c < 0 || h->wave_key[2 + (NBP == 32 ? 0 : 1)][Cp / 256 - 1] != key) {
+                c = cluster_capacity(kernel, G, GM::THREADS, smem);
+                h->wave_key[2 + (NBP == 32 ? 0 : 1)][Cp / 256 - 1] = key;
+                if (getenv("RSR_DEBUG")) fprintf(stderr, "[rsr] wave bwd kernel Cp=%d NBP=%d: %d-CTA clusters co-resident: %d\n", Cp, NBP, G, c);
+            }
+            cap = c;
+        }
+        if (cap < 2 * groups + 1) return RSR_E_RESIDENT;
+        CUtensorMap tmZ;
+        int rc = rsr_get_tmap(h, a->dz2, (uint64_t)4 * Cp, (uint64_t)T * B, (uint64_t)4 * Cp, 64, (uint32_t)NBP, &tmZ);
+        if (rc) return rc;
+        unsigned int* flags = rsr_take_flags(h, 2 * groups);
+        RSR_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * 2 * groups, (cudaStream_t)stream));
+        PBwdParams p2, p1;
+        fill_bwd_params(p2, h, B, T, Cp, a->dmt2, a->wc2, a->w_i2, a->w_f2, a->w_o2, a->lengths, a->save2, a->dz2, a->dbias2,
+                        a->dw_i2, a->dw_f2, a->dw_o2);
+        fill_bwd_params(p1, h, B, T, Cp, a->part, a->wc1, a->w_i1, a->w_f1, a->w_o1, a->lengths, a->save1, a->dz1, a->dbias1,
+                        a->dw_i1, a->dw_f1, a->dw_o1);
+        p2.post = flags;
+        p1.grouped = 1; p1.groups = groups;
+        p1.wait = flags + groups; p1.wait_per_step = (unsigned int)G;
+        WaveProjB w;
+        w.groups = groups; w.fT = (const uint16_t*)a->fT; w.part = a->part;
+        w.flagA = flags; w.flagB = flags + groups;
+        return cluster_launch(kernel, 2 * groups + 1, G, GM::THREADS, smem, (cudaStream_t)stream, tmZ, p2, p1, w);
+    };
+    auto pick = [&](auto nbp_tag) -> int {
+        constexpr int NBP = decltype(nbp_tag)::value;
+        if (fast) return bf ? run(lstmp_wave_bwd_kernel<NBP, 1, 1>, nbp_tag) : run(lstmp_wave_bwd_kernel<NBP, 0, 1>, nbp_tag);
+        return bf ? run(lstmp_wave_bwd_kernel<NBP, 1, 0>, nbp_tag) : run(lstmp_wave_bwd_kernel<NBP, 0, 0>, nbp_tag);
+    };
+    // 32 utterances per cluster only: the 48-utterance variant (RSR_WAVE_NBP=48) has 14 warps, i.e. four on one SM
+    // sub-partition and 128 registers per thread, spills, and runs 5.9 us per step against 2.7 -- slower than the two
+    // launches one after the other (profiles/r2_wave_steps_v5.txt, r2_wave_trace_bwd_v0.txt).  So a batch of more than
+    // 96 utterances at Cp = 512 (7 clusters placeable: 3 + 3 + 1) declines here.
+    const int force = getenv("RSR_WAVE_NBP") ? atoi(getenv("RSR_WAVE_NBP")) : 0;
+    if (force == 48) return pick(std::integral_constant<int, 48>());
+    return pick(std::integral_constant<int, 32>());
 }
 
 // debug: copies the phase-timing trace of the pair kernels (all zeros unless built with -DRSR_TRACE) to the host

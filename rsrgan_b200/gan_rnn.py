@@ -537,9 +537,7 @@ class GAN_RNN(Model):
             lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=n_rl, cat_src=self._cat(x))
             h.lsgan_mse_losses(self._losses, rl=lg_rl, ld_logit=lg_rl.stride(0), d_rl_grad=d_rl16, **kw)
             D.bwd("rl", d_rl16)
-        # (the layer-wavefront launch would take the SMs D(labels) is using on the side stream: measured no faster here)
-        wave = serial or not h.overlap or os.environ.get("RSR_WAVE_DSTEP") == "1"
-        g32 = _g32 if _g32 is not None else G.fwd(x, B, T, ln, train=_g_train, wave=wave)
+        g32 = _g32 if _g32 is not None else G.fwd(x, B, T, ln, train=_g_train)
         self._last_g32 = g32
         lg_fk = D.fwd("fk", g32, B, T, ln, noise=n_fk, cat_src=self._cat(x))
         h.lsgan_mse_losses(self._losses, fk=lg_fk, ld_logit=lg_fk.stride(0), g=g32, y=y_tm, n_frames=rows,

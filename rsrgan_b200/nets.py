@@ -230,8 +230,10 @@ class LSTMP(object):
         self.kxT16 = torch.zeros(4 * self.Cp, self.Ik, dtype=h.h16, device=h.device)   # K_x^T (fused forward operand)
         self.fused = True            # cleared the first time the library says the fused variant does not apply
         self.wpT16 = torch.zeros(self.Pp, self.Cp, dtype=h.h16, device=h.device)       # W_p^T (layer-wavefront operand)
-        self.wave = False            # set by the network on the first layer of a stacked pair (fwd_wave)
-        self.wave_declined = set()   # batch sizes the library declined the wavefront launch for
+        self.wave = False            # set by the network on the first layer of a stacked pair (fwd_wave / bwd_wave) ...
+        self.wave_next = None        # ... together with the layer stacked on it
+        self.wave_declined = set()   # batch sizes the library declined the wavefront launch for: ("f" | "b", B)
+        self.fT16 = None             # F = W_p K_x(next layer) [Cp, 4Cp]: operand of the backward wavefront
         if self.Cp > 512 and hasattr(h, "overlap"):
             # L2-exchange recurrence kernels (Cp > 512) spin on counters of co-resident CTAs: nothing else
             # may take SMs while they run, so the side stream is switched off for this model
@@ -262,6 +264,10 @@ class LSTMP(object):
             h.transpose16(Kx16, self.Ip, 4 * self.Cp, self.kxT16)
             if self.wave:
                 h.transpose16(Wp16, self.Cp, self.Pp, self.wpT16)
+                if self.wave_next is not None:
+                    if self.fT16 is None:
+                        self.fT16 = torch.zeros(self.Cp, 4 * self.Cp, dtype=h.h16, device=h.device)
+                    h.gemm(Wp16, self.wave_next._w()[0], self.Cp, 4 * self.Cp, self.Pp, b_mn=True, out16=self.fT16)
 
     def fwd(self, ctx, x16, B, T, lengths, save=True, want32=False):
         """x16 [T*B, Ip] -> out_seq16 [(T+1)*B, Pp] (slot 0 = zero initial state; rows B.. are
@@ -300,7 +306,7 @@ class LSTMP(object):
         nxt or None) -- or None when the launch does not apply (the caller then runs the two layers one by one)."""
         net, h = self.net, self.net.h
         if not (self.wave and self.fused and nxt.fused and self.Cp == nxt.Cp and nxt.I == self.P and nxt.Ip == self.Pp) \
-                or B in self.wave_declined:
+                or ("f", B) in self.wave_declined:
             return None
         rows, Cp = T * B, self.Cp
         k1, k2 = (ctx, self.prefix, B), (ctx, nxt.prefix, B)
@@ -314,10 +320,53 @@ class LSTMP(object):
         work = (self.rec_flops(B, T) + nxt.rec_flops(B, T) + 2.0 * rows * (self.I + nxt.I) * 4 * self.C)
         if not h.lstmp_wave_fwd(B, T, Cp, self.I, self.P, lengths, x16, self._fused_operands(), mt1, sv1, self.wpT16, out1,
                                 nxt._fused_operands(), mt2, sv2, work=work):
-            self.wave_declined.add(B)
+            self.wave_declined.add(("f", B))
             return None
         h.gemm(mt2[B:], nxt._w()[2], rows, nxt.Pp, Cp, b_mn=True, out16=out2[B:], out32=o32)
         return out1, out2, o32
+
+    def _peep(self):
+        P = self.net.P
+        return tuple(P.view(self.prefix + n) for n in ("w_i_diag", "w_f_diag", "w_o_diag"))
+
+    def _rec_grads(self):
+        P = self.net.P
+        return tuple(P.view(self.prefix + n, "grad") for n in ("bias", "w_i_diag", "w_f_diag", "w_o_diag"))
+
+    def bwd_wave(self, upper, ctx, x16, x16_upper, dout32_upper, B, T, lengths, prev_y16=None, prev_act=ACT_NONE,
+                 want32=False):
+        """Backward of this layer and the one stacked on it (`upper`, whose bwd_pre has run) as ONE wavefront launch
+        (rsr_lstmp_wave_bwd), then this layer's data gradient on the calling stream and both layers' weight gradients
+        on the side stream.  Returns (dx16, dx32) of this layer -- or None when the launch does not apply."""
+        net, h = self.net, self.net.h
+        if not (self.wave and self.wave_next is upper and self.fT16 is not None and self.Cp == upper.Cp
+                and upper.Ip == self.Pp) or ("b", B) in self.wave_declined:
+            return None
+        rows, Cp = T * B, self.Cp
+        k1, k2 = (ctx, self.prefix, B), (ctx, upper.prefix, B)
+        sv1 = net.ws.get(k1 + ("save",), rows, 5 * Cp, F32)
+        sv2 = net.ws.get(k2 + ("save",), rows, 5 * Cp, F32)
+        dz1 = net.ws.get(k1 + ("dz",), rows + B, 4 * Cp, h.h16)
+        dz2 = net.ws.get(k2 + ("dz",), rows + B, 4 * Cp, h.h16)
+        dmt2 = net.ws.get((ctx, "dmt", Cp, B), rows, Cp, F32)
+        part = net.ws.get((ctx, "wave_part", Cp, B), T * (B + 48), Cp, F32)   # zero at allocation and after every launch
+        dz1[rows:].zero_()
+        dz2[rows:].zero_()
+        if not h.lstmp_wave_bwd(B, T, Cp, lengths, dmt2, (upper.wc16,) + upper._peep(), sv2, dz2, upper._rec_grads(),
+                                self.fT16, part, (self.wc16,) + self._peep(), sv1, dz1, self._rec_grads(),
+                                work=self.rec_flops(B, T) + upper.rec_flops(B, T)):
+            self.wave_declined.add(("b", B))
+            return None
+        dx16 = net.ws.get(k1 + ("dx16",), rows, self.Ip, h.h16)
+        dx32 = net.ws.get(k1 + ("dx32",), rows, self.Ip, F32) if want32 else None
+        h.gemm(dz1, self._w()[0], rows, self.Ip, 4 * Cp, dact_src=prev_y16, dact=prev_act, out16=dx16, out32=dx32)
+        upper.bwd_side(ctx, x16_upper, dout32_upper, B, T)
+        with h.side_stream():      # gradient wrt this layer's output, for its projection's weight gradient only
+            du16 = net.ws.get(k2 + ("dx16",), rows, upper.Ip, h.h16)
+            du32 = net.ws.get(k2 + ("dx32",), rows, upper.Ip, F32)
+            h.gemm(dz2, upper._w()[0], rows, upper.Ip, 4 * Cp, out16=du16, out32=du32)
+        self.bwd_side(ctx, x16, du32, B, T)
+        return dx16, dx32
 
     def bwd(self, ctx, x16, dout16, dout32, B, T, lengths, want_dw=True, want_dx=True, prev_y16=None,
             prev_act=ACT_NONE, resid32=None, want32=False):
@@ -749,8 +798,9 @@ class Generator(Net):
                       FC(net, "g_model/fully_connected", in_dim, proj, ACT_LRELU)]
                 ls += [LSTMP(net, "g_model/rnn/multi_rnn_cell/cell_%d/lstm_cell/" % i, proj, cell, proj)
                        for i in range(L)]
-                for i in range(0, L - 1, 2):      # stacked pairs run as one wavefront launch (LSTMP.fwd_wave)
+                for i in range(0, L - 1, 2):      # stacked pairs run as one wavefront launch (LSTMP.fwd_wave / bwd_wave)
                     ls[1 + i].wave = ls[1 + i].Cp <= 512 and float(keep_prob) >= 1.0
+                    ls[1 + i].wave_next = ls[2 + i]
                 return ls + [FC(net, "g_model/fully_connected_1", proj, out_dim, ACT_NONE)]
         elif g_type in ("res_lstm_l", "res_lstm_base"):
             # models/res_lstm_l.py:101-138: four LSTMP(760 -> in_dim) layers (the `lstm_num_layer = 3` at :45 is unused)
@@ -820,8 +870,8 @@ class Generator(Net):
         """x fp32 (B, T, in_dim) batch-major on the device -> y32 [T*B, out_pad] time-major fp32.
         reuse_staged: the 16-bit time-major copy of this same x from the previous call is still valid (the second
         generator forward of a batch schedule sees the same minibatch).
-        wave: stacked LSTMP pairs may run as one layer-wavefront launch.  It takes 7 sixteen-CTA clusters (112 SMs) where
-        the layer-by-layer kernels take 4, so a caller that has other work for those SMs on the side stream says no."""
+        wave: stacked LSTMP pairs may run as one layer-wavefront launch (7 sixteen-CTA clusters instead of 4; measured
+        faster even while D(labels) runs beside it on the side stream: 3.157 vs 3.175 ms per cfg-2 schedule)."""
         h, ws, rows = self.h, self.ws, T * B
         if self.g_type == "rced":
             self._B, self._T, self._len = B, T, lengths
@@ -926,15 +976,28 @@ class Generator(Net):
         if self.g_type == "lstm":
             d16, d32 = Ls[-1].bwd("g", acts[-1], dy16, rows, want32=True)
             Ls[-2].bwd_pre("g", d16, B, T)
-            for i in range(len(Ls) - 2, 0, -1):
-                first = i == 1
+            i = len(Ls) - 2
+            while i >= 1:
                 dout32 = d32
+                if i >= 2 and Ls[i - 1].wave:     # this layer and the one below it as one wavefront launch
+                    mask = i - 1 == 1 and not self.fcbn
+                    w = Ls[i - 1].bwd_wave(Ls[i], "g", acts[i - 1], acts[i], dout32, B, T, lengths,
+                                           prev_y16=acts[1] if mask else None, prev_act=ACT_LRELU if mask else ACT_NONE,
+                                           want32=i - 1 > 1)
+                    if w is not None:
+                        d16, d32 = w
+                        i -= 2
+                        if i >= 1:
+                            Ls[i].bwd_pre("g", d16, B, T)
+                        continue
+                first = i == 1
                 mask = first and not self.fcbn      # an FCBN first layer applies its own activation gradient
                 d16, d32 = Ls[i].bwd_main("g", d16, B, T, lengths, prev_y16=acts[1] if mask else None,
                                           prev_act=ACT_LRELU if mask else ACT_NONE, want32=not first)
                 if not first:
                     Ls[i - 1].bwd_pre("g", d16, B, T)     # critical path first, then this layer's weight gradients
                 Ls[i].bwd_side("g", acts[i], dout32, B, T)
+                i -= 1
             Ls[0].bwd("g", acts[0], d16, rows, want_dx=False, dw_side=False)
             return
         d16, d32 = Ls[-1].bwd("g", acts[-1], dy16, rows, want32=True)

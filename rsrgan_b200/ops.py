@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT_CLIP, ACT_LRELU, ACT_NONE, ACT_RELU, GemmArgs, WaveArgs, check  # noqa: F401
+from ._lib import ACT_CLIP, ACT_LRELU, ACT_NONE, ACT_RELU, GemmArgs, WaveArgs, WaveBwdArgs, check  # noqa: F401
 
 H16 = {0: torch.float16, 1: torch.bfloat16}
 
@@ -214,6 +214,38 @@ class Handle(object):
         if rc == _lib.RSR_E_RESIDENT:
             return False
         check(rc, "rsr_lstmp_wave_fwd")
+        self.launches += 1
+        return True
+
+    def lstmp_wave_bwd(self, B, T, Cp, lengths, dmt2, l2, save2, dz2, g2, fT, part, l1, save1, dz1, g1, work=0.0):
+        """Backward of two stacked LSTMP layers as one wavefront launch (rsr_lstmp_wave_bwd).  l = (wc, w_i, w_f, w_o),
+        g = (dbias, dw_i, dw_f, dw_o) per layer; part fp32 [T*(B+48), Cp], all zeros (and all zeros again afterwards).  Returns
+        False when the shape does not apply."""
+        a = WaveBwdArgs()
+        a.B, a.T, a.Cp, a.lengths = B, T, Cp, _p(lengths)
+        a.dmt2, a.save2, a.dz2 = _p(dmt2), _p(save2), _p(dz2)
+        a.wc2, a.w_i2, a.w_f2, a.w_o2 = (_p(t) for t in l2)
+        a.dbias2, a.dw_i2, a.dw_f2, a.dw_o2 = (_p(t) for t in g2)
+        a.fT, a.part = _p(fT), _p(part)
+        a.save1, a.dz1 = _p(save1), _p(dz1)
+        a.wc1, a.w_i1, a.w_f1, a.w_o1 = (_p(t) for t in l1)
+        a.dbias1, a.dw_i1, a.dw_f1, a.dw_o1 = (_p(t) for t in g1)
+        fn = self.lib.rsr_lstmp_wave_bwd
+        timed = self.timing is not None or self.timeline is not None
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        rc = fn(self.h, _stream(), C.byref(a))
+        if timed:
+            e1.record()
+            if rc == 0 and self.timing is not None:
+                self.timing.append(("rsr_lstmp_wave_bwd", e0, e1, work))
+            if rc == 0 and self.timeline is not None:
+                cur = torch.cuda.current_stream()
+                self.timeline.append(("rsr_lstmp_wave_bwd", "side" if cur == self._side else "main", e0, e1, work))
+        if rc == _lib.RSR_E_RESIDENT:
+            return False
+        check(rc, "rsr_lstmp_wave_bwd")
         self.launches += 1
         return True
 

@@ -61,3 +61,29 @@ for (B, T, I, Cp, P, nbp) in [(128, 100, 256, 512, 256, 0), (96, 100, 256, 512, 
     ts = timeit(serial)
     tw = timeit(wave)
     print("%5d %5d %5d %5d | %10.1f %8.2f | %10.1f %8.2f | %s" % (B, T, Cp, nbp, ts, ts / (2 * T), tw, tw / T, ok[0]))
+    # backward
+    wc1, wc2 = d1[2].t().contiguous(), d2[2].t().contiguous()
+    kx2 = d2[0].t().contiguous()[:Pp]
+    wp1 = wpT1.t().contiguous()
+    fT = (wp1.float() @ kx2.float()).to(h.h16).contiguous()
+    dmt2 = torch.tensor(rng.standard_normal((T * B, Cp)).astype(np.float32) * 0.01, device=dev)
+    dmt1 = torch.zeros(T * B, Cp, dtype=torch.float32, device=dev)
+    dz1, dz2 = (torch.zeros((T + 1) * B, 4 * Cp, dtype=h.h16, device=dev) for _ in range(2))
+    dx2 = torch.zeros(T * B, Pp, dtype=h.h16, device=dev)
+    part = torch.zeros(T * (B + 48), Cp, dtype=torch.float32, device=dev)
+    z = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
+    g1, g2 = (z(4 * Cp), z(Cp), z(Cp), z(Cp)), (z(4 * Cp), z(Cp), z(Cp), z(Cp))
+
+    def serial_b():
+        h.lstmp_rec_bwd(B, T, Cp, dmt2, wc2, *d2[3:6], d_len, sv2, dz2, *g2)
+        h.gemm(dz2, kx2, T * B, Pp, 4 * Cp, out16=dx2)
+        h.gemm(dx2, wp1, T * B, Cp, Pp, out32=dmt1)
+        h.lstmp_rec_bwd(B, T, Cp, dmt1, wc1, *d1[3:6], d_len, sv1, dz1, *g1)
+
+    def wave_b():
+        ok[0] = h.lstmp_wave_bwd(B, T, Cp, d_len, dmt2, (wc2,) + tuple(d2[3:6]), sv2, dz2, g2, fT, part,
+                                 (wc1,) + tuple(d1[3:6]), sv1, dz1, g1) and ok[0]
+
+    ts = timeit(serial_b)
+    tw = timeit(wave_b)
+    print("%5s %5s %5s %5s | %10.1f %8.2f | %10.1f %8.2f | %s  (backward)" % ("", "", "", "", ts, ts / (2 * T), tw, tw / T, ok[0]))

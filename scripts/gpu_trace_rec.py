@@ -40,6 +40,16 @@ elif which == "wave":    # two stacked layers as one wavefront launch; the trace
     l1, l2 = mk(), mk()
     for _ in range(3):
         assert h.lstmp_wave_fwd(B, T, Cp, I, I, ln, x16, l1, mt, save, wpT, out1, l2, mt2, save2)
+elif which == "wavebwd":  # backward wavefront; the trace is layer 2's first cluster
+    I = 256
+    wc = wcT.t().contiguous()
+    fT = (torch.randn(Cp, 4 * Cp, device=dev) * 0.03).to(h.h16)
+    dmt = torch.randn(rows, Cp, device=dev) * 0.01
+    dz1, dz2 = (torch.zeros(rows + B, 4 * Cp, dtype=h.h16, device=dev) for _ in range(2))
+    part = torch.zeros(T * (B + 48), Cp, device=dev)
+    g = lambda: (torch.zeros(4 * Cp, device=dev), torch.zeros(Cp, device=dev), torch.zeros(Cp, device=dev), torch.zeros(Cp, device=dev))
+    for _ in range(3):
+        assert h.lstmp_wave_bwd(B, T, Cp, ln, dmt, (wc, w[0], w[1], w[2]), save, dz2, g(), fT, part, (wc, w[0], w[1], w[2]), save, dz1, g())
 elif which == "bwd":
     wc = wcT.t().contiguous()
     dmt = torch.randn(rows, Cp, device=dev) * 0.01
@@ -53,7 +63,7 @@ else:
         h.lstmp_rec_fwd(B, T, Cp, zx, wcT, w[0], w[1], w[2], ln, mt, save)
 torch.cuda.synchronize()
 buf = (C.c_ulonglong * (64 * 8))()
-fn = h.lib.rsr_debug_trace_pair if (which.startswith("p") or which == "wave" or (which == "bwd" and B > 16 and not os.environ.get("RSR_NO_PAIR"))) else h.lib.rsr_debug_trace
+fn = h.lib.rsr_debug_trace_pair if (which.startswith("p") or which.startswith("wave") or (which == "bwd" and B > 16 and not os.environ.get("RSR_NO_PAIR"))) else h.lib.rsr_debug_trace
 fn.argtypes = [C.c_void_p, C.c_int]
 rc = fn(buf, 64 * 8)
 tr = np.array(buf[:], dtype=np.int64).reshape(64, 8)[:T]

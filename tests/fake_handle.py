@@ -58,6 +58,9 @@ class FakeHandle(object):
     def lstmp_wave_fwd(self, *a, **k):       # ... and no layer-wavefront launch: the layers run one after the other
         return False
 
+    def lstmp_wave_bwd(self, *a, **k):
+        return False
+
     def transpose16(self, src, rows, cols, dst):
         self.launches += 1
         dst[:cols, :rows] = src[:rows, :cols].t()

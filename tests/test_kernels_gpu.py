@@ -276,6 +276,80 @@ def test_lstmp_wave_forward(h, monkeypatch, B, T, I, C, P, ragged, nbp):
     assert rel(got2, s_mt2[B:].float().cpu().numpy().reshape(T, B, Cp)) < 2e-3
 
 
+@pytest.mark.parametrize("B,T,I,C,P,ragged,nbp", [
+    (40, 10, 256, 512, 256, True, 0),       # BASELINE cfg-2 stack: 32 utterances per cluster
+    (128, 12, 256, 512, 256, True, 0),      # ... at the benchmarked batch: 48 per cluster, all 7 placeable clusters
+    (100, 7, 256, 512, 256, False, 48),     # last group partial
+    (8, 12, 40, 256, 40, True, 0),          # discriminator_lstm stack: 8-CTA clusters
+    (3, 1, 40, 256, 40, False, 32),         # a single frame
+])
+def test_lstmp_wave_backward(h, monkeypatch, B, T, I, C, P, ragged, nbp):
+    """rsr_lstmp_wave_bwd (reversed recurrences of two stacked layers in one launch, dmt1_t = dz2_t (W_p1 K_x2)^T formed
+    between them) == the oracle's gradients of the two dynamic_rnn layers, and ~= the one-after-the-other kernels."""
+    if nbp:
+        monkeypatch.setenv("RSR_WAVE_NBP", str(nbp))
+    dev, rng = h.device, np.random.default_rng(B + I + T)
+    Cp, Ip, Pp = packing.cell_pad(C), packing.round_up(I, 8), packing.round_up(P, 8)
+    x = rng.standard_normal((B, T, I))
+    lengths = rng.integers(max(T // 2, 1), T + 1, size=B) if ragged else np.full(B, T)
+    (w1, d1, wpT1), (w2, d2, wpT2) = _fused_operands(h, rng, I, C, P, Cp), _fused_operands(h, rng, P, C, P, Cp)
+    out1_ref, c1 = O.lstmp_fwd(x, lengths, *w1)
+    out2_ref, c2 = O.lstmp_fwd(out1_ref, lengths, *w2)
+    dout2 = rng.standard_normal((B, T, P)) * 0.1
+    dx2_ref, g2 = O.lstmp_bwd(dout2, c2)
+    dx1_ref, g1 = O.lstmp_bwd(dx2_ref, c1)
+    x16 = torch.zeros(T * B, Ip, dtype=h.h16, device=dev)
+    x16[:, :I] = torch.tensor(x.transpose(1, 0, 2).reshape(T * B, I), device=dev).to(h.h16)
+    d_len = torch.tensor(lengths.astype(np.int32), device=dev)
+    mk = lambda cols, dt: torch.zeros((T + 1) * B, cols, dtype=dt, device=dev)
+    mt1, mt2, out1 = mk(Cp, h.h16), mk(Cp, h.h16), mk(Pp, h.h16)
+    sv1, sv2 = (torch.zeros(T * B, 5 * Cp, dtype=torch.float32, device=dev) for _ in range(2))
+    assert h.lstmp_wave_fwd(B, T, Cp, I, P, d_len, x16, d1, mt1, sv1, wpT1, out1, d2, mt2, sv2)
+    # operands of the backward: Wc (untransposed), dmt2 = dOut2 W_p2^T, F = W_p1 K_x2 (16-bit operands, rounded once)
+    wc1, wc2 = d1[2].t().contiguous(), d2[2].t().contiguous()
+    dmt2 = torch.tensor(packing.pad_last(np.einsum("btp,cp->tbc", dout2, w2[5]).reshape(T * B, C), Cp).astype(np.float32), device=dev)
+    kx2 = torch.zeros(Pp, 4 * Cp, dtype=h.h16, device=dev)
+    kx2[:P] = torch.tensor(packing.pack_cols(w2[0][:P], C), device=dev).to(h.h16)
+    fT = (wpT1.float().t() @ kx2.float()).to(h.h16).contiguous()
+    z = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
+    grads = lambda: (z(4 * Cp), z(Cp), z(Cp), z(Cp))
+    dz1, dz2 = mk(4 * Cp, h.h16), mk(4 * Cp, h.h16)
+    gw1, gw2 = grads(), grads()
+    part = torch.zeros(T * (B + 48), Cp, dtype=torch.float32, device=dev)
+    ok = h.lstmp_wave_bwd(B, T, Cp, d_len, dmt2, (wc2,) + tuple(d2[3:6]), sv2, dz2, gw2, fT, part,
+                          (wc1,) + tuple(d1[3:6]), sv1, dz1, gw1)
+    torch.cuda.synchronize()
+    assert ok
+    t16 = tol(h, 3e-3, 2e-2)
+
+    def check(dz, gw, w, xin, dx_ref, g_ref, Iw, t):
+        dzu = packing.unpack_cols(dz[:T * B].float().cpu().numpy(), C).reshape(T, B, 4 * C)
+        assert rel(packing.unpack_cols(gw[0].cpu().numpy(), C), g_ref["bias"]) < t
+        for k, n in ((1, "w_i_diag"), (2, "w_f_diag"), (3, "w_o_diag")):
+            assert rel(gw[k].cpu().numpy()[:C], g_ref[n]) < t, n
+        assert rel(np.einsum("tbg,ig->bti", dzu, w[0][:Iw]), dx_ref) < t
+        assert rel(np.einsum("tbi,tbg->ig", xin, dzu), g_ref["kernel"]) < t
+
+    prev = lambda o: np.concatenate([np.zeros((1, B, P)), o.transpose(1, 0, 2)[:-1]], 0)
+    check(dz2, gw2, w2, np.concatenate([out1_ref.transpose(1, 0, 2), prev(out2_ref)], 2), dx2_ref, g2, P, t16)
+    check(dz1, gw1, w1, np.concatenate([x.transpose(1, 0, 2), prev(out1_ref)], 2), dx1_ref, g1, I, 2 * t16)
+    # the same two layers one after the other
+    s_dz1, s_dz2 = mk(4 * Cp, h.h16), mk(4 * Cp, h.h16)
+    s_gw1, s_gw2 = grads(), grads()
+    h.lstmp_rec_bwd(B, T, Cp, dmt2, wc2, *d2[3:6], d_len, sv2, s_dz2, *s_gw2)
+    dx2_16 = torch.zeros(T * B, Pp, dtype=h.h16, device=dev)
+    h.gemm(s_dz2, kx2, T * B, Pp, 4 * Cp, out16=dx2_16)
+    dmt1 = torch.zeros(T * B, Cp, dtype=torch.float32, device=dev)
+    h.gemm(dx2_16, wpT1.t().contiguous(), T * B, Cp, Pp, out32=dmt1)
+    h.lstmp_rec_bwd(B, T, Cp, dmt1, wc1, *d1[3:6], d_len, sv1, s_dz1, *s_gw1)
+    torch.cuda.synchronize()
+    if B > 16:        # (B <= 16: rsr_lstmp_rec_bwd runs the single-CTA cluster kernel, another summation order)
+        assert torch.equal(dz2, s_dz2)
+    assert rel(dz2.float().cpu().numpy(), s_dz2.float().cpu().numpy()) < tol(h, 1e-3, 8e-3)
+    assert rel(dz1.float().cpu().numpy(), s_dz1.float().cpu().numpy()) < tol(h, 4e-3, 3e-2)
+    assert float(part.abs().max()) == 0.0        # the scratch is handed back zeroed
+
+
 def test_lstmp_shape_errors(h):
     z = torch.zeros(8, device=h.device)
     from rsrgan_b200 import _lib
