@@ -334,7 +334,7 @@ class LSTMP(object):
         return tuple(P.view(self.prefix + n, "grad") for n in ("bias", "w_i_diag", "w_f_diag", "w_o_diag"))
 
     def bwd_wave(self, upper, ctx, x16, x16_upper, dout32_upper, B, T, lengths, prev_y16=None, prev_act=ACT_NONE,
-                 want32=False):
+                 want32=False, want_dw=True, want_dx=True, resid32=None):
         """Backward of this layer and the one stacked on it (`upper`, whose bwd_pre has run) as ONE wavefront launch
         (rsr_lstmp_wave_bwd), then this layer's data gradient on the calling stream and both layers' weight gradients
         on the side stream.  Returns (dx16, dx32) of this layer -- or None when the launch does not apply."""
@@ -352,20 +352,29 @@ class LSTMP(object):
         part = net.ws.get((ctx, "wave_part", Cp, B), T * (B + 48), Cp, F32)   # zero at allocation and after every launch
         dz1[rows:].zero_()
         dz2[rows:].zero_()
-        if not h.lstmp_wave_bwd(B, T, Cp, lengths, dmt2, (upper.wc16,) + upper._peep(), sv2, dz2, upper._rec_grads(),
-                                self.fT16, part, (self.wc16,) + self._peep(), sv1, dz1, self._rec_grads(),
+
+        def sink(l):
+            s = l.scratch
+            return (s[:4 * Cp], s[4 * Cp:5 * Cp], s[5 * Cp:6 * Cp], s[6 * Cp:])
+        g1, g2 = (self._rec_grads(), upper._rec_grads()) if want_dw else (sink(self), sink(upper))
+        if not h.lstmp_wave_bwd(B, T, Cp, lengths, dmt2, (upper.wc16,) + upper._peep(), sv2, dz2, g2,
+                                self.fT16, part, (self.wc16,) + self._peep(), sv1, dz1, g1,
                                 work=self.rec_flops(B, T) + upper.rec_flops(B, T)):
             self.wave_declined.add(("b", B))
             return None
-        dx16 = net.ws.get(k1 + ("dx16",), rows, self.Ip, h.h16)
-        dx32 = net.ws.get(k1 + ("dx32",), rows, self.Ip, F32) if want32 else None
-        h.gemm(dz1, self._w()[0], rows, self.Ip, 4 * Cp, dact_src=prev_y16, dact=prev_act, out16=dx16, out32=dx32)
-        upper.bwd_side(ctx, x16_upper, dout32_upper, B, T)
-        with h.side_stream():      # gradient wrt this layer's output, for its projection's weight gradient only
-            du16 = net.ws.get(k2 + ("dx16",), rows, upper.Ip, h.h16)
-            du32 = net.ws.get(k2 + ("dx32",), rows, upper.Ip, F32)
-            h.gemm(dz2, upper._w()[0], rows, upper.Ip, 4 * Cp, out16=du16, out32=du32)
-        self.bwd_side(ctx, x16, du32, B, T)
+        dx16 = dx32 = None
+        if want_dx:
+            dx16 = net.ws.get(k1 + ("dx16",), rows, self.Ip, h.h16)
+            dx32 = net.ws.get(k1 + ("dx32",), rows, self.Ip, F32) if want32 else None
+            h.gemm(dz1, self._w()[0], rows, self.Ip, 4 * Cp, resid=resid32, dact_src=prev_y16, dact=prev_act,
+                   out16=dx16, out32=dx32)
+        if want_dw:
+            upper.bwd_side(ctx, x16_upper, dout32_upper, B, T)
+            with h.side_stream():      # gradient wrt this layer's output, for its projection's weight gradient only
+                du16 = net.ws.get(k2 + ("dx16",), rows, upper.Ip, h.h16)
+                du32 = net.ws.get(k2 + ("dx32",), rows, upper.Ip, F32)
+                h.gemm(dz2, upper._w()[0], rows, upper.Ip, 4 * Cp, out16=du16, out32=du32)
+            self.bwd_side(ctx, x16, du32, B, T)
         return dx16, dx32
 
     def bwd(self, ctx, x16, dout16, dout32, B, T, lengths, want_dw=True, want_dx=True, prev_y16=None,
@@ -1028,6 +1037,9 @@ class Discriminator(Net):
             def mk(net):
                 ls = [LSTMP(net, "d_model/rnn/multi_rnn_cell/cell_%d/lstm_cell/" % i, in_dim if i == 0 else proj,
                             cell, proj) for i in range(L)]
+                for i in range(0, L - 1, 2):      # stacked pairs run as one wavefront launch (LSTMP.fwd_wave / bwd_wave)
+                    ls[i].wave = ls[i].Cp <= 512
+                    ls[i].wave_next = ls[i + 1]
                 return ls + [FC(net, "d_model/fully_connected", proj, 1, ACT_NONE)]
         elif d_type == "dnn":
             # models/discriminator_dnn.py:23-24,61-93: 1024 x (1+3) ReLU -> 1, clip_by_value(-0.5, 1.5)
@@ -1064,10 +1076,18 @@ class Discriminator(Net):
         acts = [x16]
         a = x16
         if self.d_type == "lstm":
-            for l in self.layers[:-1]:
-                seq, _ = l.fwd(ctx, a, B, T, lengths, save=train)
+            rec, li = self.layers[:-1], 0
+            while li < len(rec):
+                w = rec[li].fwd_wave(rec[li + 1], ctx, a, B, T, lengths, save=train) if li + 1 < len(rec) else None
+                if w is not None:
+                    acts += [w[0][B:], w[1][B:]]
+                    a = w[1][B:]
+                    li += 2
+                    continue
+                seq, _ = rec[li].fwd(ctx, a, B, T, lengths, save=train)
                 a = seq[B:]
                 acts.append(a)
+                li += 1
         else:
             for l in self.layers[:-1]:
                 a, _ = l.fwd(ctx, a, rows)
@@ -1082,11 +1102,29 @@ class Discriminator(Net):
         rows, Ls = T * B, self.layers
         if self.d_type == "lstm":
             d16, d32 = Ls[-1].bwd(ctx, acts[-1], dlogit16, rows, want_dw=want_dw, want32=want_dw)
-            for i in range(len(Ls) - 2, -1, -1):
-                last = i == 0
+            i = len(Ls) - 2
+            while i >= 0:
+                last, dout32 = i == 0, d32
+                if i >= 1 and Ls[i - 1].wave:     # this layer and the one below it as one wavefront launch
+                    low = i - 1 == 0
+                    Ls[i].bwd_pre(ctx, d16, B, T)
+                    w = Ls[i - 1].bwd_wave(Ls[i], ctx, acts[i - 1], acts[i], dout32, B, T, lengths,
+                                           want32=want_dw and not low, want_dw=want_dw, want_dx=(not low) or want_dx,
+                                           resid32=resid32 if low else None)
+                    if w is not None:
+                        d16, d32 = w
+                        i -= 2
+                        continue
+                    # declined (bwd_pre has run): finish this layer the usual way
+                    d16, d32 = Ls[i].bwd_main(ctx, d16, B, T, lengths, want_dw=want_dw, want_dx=True, want32=want_dw)
+                    if want_dw:
+                        Ls[i].bwd_side(ctx, acts[i], dout32, B, T)
+                    i -= 1
+                    continue
                 d16, d32 = Ls[i].bwd(ctx, acts[i], d16, d32, B, T, lengths, want_dw=want_dw,
                                      want_dx=(not last) or want_dx, resid32=resid32 if last else None,
                                      want32=want_dw and not last)
+                i -= 1
             return d16
         d = dlogit16
         plain = not self.fcbn
