@@ -1300,10 +1300,14 @@ extern "C" int rsr_lstmp_wave_bwd(rsr_handle* h, void* stream, const rsr_wave_bw
         if (fast) return bf ? run(lstmp_wave_bwd_kernel<NBP, 1, 1>, nbp_tag) : run(lstmp_wave_bwd_kernel<NBP, 0, 1>, nbp_tag);
         return bf ? run(lstmp_wave_bwd_kernel<NBP, 1, 0>, nbp_tag) : run(lstmp_wave_bwd_kernel<NBP, 0, 0>, nbp_tag);
     };
-    // 32 utterances per cluster only: the 48-utterance variant (RSR_WAVE_NBP=48) has 14 warps, i.e. four on one SM
-    // sub-partition and 128 registers per thread, spills, and runs 5.9 us per step against 2.7 -- slower than the two
-    // launches one after the other (profiles/r2_wave_steps_v5.txt, r2_wave_trace_bwd_v0.txt).  So a batch of more than
-    // 96 utterances at Cp = 512 (7 clusters placeable: 3 + 3 + 1) declines here.
+    // 32 utterances per cluster only.  The 48-utterance variant (RSR_WAVE_NBP=48, kept for experiments) has 14 warps, i.e.
+    // four on one SM sub-partition and at most 128 registers per thread: the gate math spills and a step takes 5.9 us
+    // against 2.7 -- slower than the two launches one after the other (profiles/r2_wave_steps_v5.txt,
+    // r2_wave_trace_bwd_v0.txt).  Tried on top of it, both worse: moving registers from an auxiliary warpgroup to the gate
+    // warpgroups with setmaxnreg (ptxas kept allocating for 128 and spilled 2.4 KB per thread); dropping the one-step-ahead
+    // operand prefetch to fit 128 registers (8.5 us per step: the saved activations stream from HBM, their latency does
+    // not hide behind the wait for the partial rows, profiles/r2_wave_steps_v6.txt).  So a batch of more than 96
+    // utterances at Cp = 512 (7 clusters placeable: 3 + 3 + 1) declines here.
     const int force = getenv("RSR_WAVE_NBP") ? atoi(getenv("RSR_WAVE_NBP")) : 0;
     if (force == 48) return pick(std::integral_constant<int, 48>());
     return pick(std::integral_constant<int, 32>());
