@@ -385,6 +385,12 @@ int rsr_bn_bwd(rsr_handle* h, void* stream, const void* da16, int ldda, const fl
                int bn, float* coef, const float* bias, float* dgamma, float* dbeta, void* dz16, int lddz,
                float* dz32, int lddz32, float* scratch);
 int rsr_rng_tick(rsr_handle* h, void* stream, unsigned long long* rng);
+/* The discriminator's input noise, tf.random_normal(shape = (B, 1, D), stddev) broadcast over time (utils/ops.py:19-30,
+ * models/discriminator_lstm.py:54-60): out[i] = stddev * sqrt(-2 ln u1) cos(2 pi u2), i < n, with u1 = (h >> 40 + 1) /
+ * 2^24 and u2 = ((h >> 16) & 0xffffff) / 2^24 of h = splitmix64(key ^ i), key as for the dropout mask above (TensorFlow's
+ * random stream cannot be reproduced; parity tests feed the noise explicitly).  The caller ticks rng after each draw. */
+int rsr_gauss_noise(rsr_handle* h, void* stream, const unsigned long long* rng, unsigned salt, float* out,
+                    long long n, float stddev);
 
 /* batch_norm behind the convolutions -- tf.contrib.layers.conv2d(..., normalizer_fn=batch_norm, normalizer_params=
  * {is_training, scale=True, renorm=True}), models/rced.py:63-71,94-97: no bias, the normalised axis is the conv2d

@@ -184,6 +184,17 @@ def dropout_mask(seed, tick, salt, rows, n, keep_prob):
     return bits.reshape(rows, n) < np.uint32(int(float(np.float32(keep_prob)) * 16777216.0))
 
 
+def gauss_noise(seed, tick, salt, n, stddev):
+    """rsr_gauss_noise (include/rsrgan_b200.h): the discriminator's input noise (utils/ops.py:19-30) drawn from the same
+    counter-based stream as the dropout mask -- Box-Muller of the two 24-bit fields of splitmix64(key ^ i)."""
+    with np.errstate(over="ignore"):
+        key = _splitmix64(_U64(seed) + _U64(0x9E3779B97F4A7C15) * (_U64(tick) * _U64(65536) + _U64(salt)))
+        hsh = _splitmix64(key ^ np.arange(n, dtype=np.uint64))
+    u1 = ((hsh >> _U64(40)).astype(np.float64) + 1.0) / 16777216.0
+    u2 = ((hsh >> _U64(16)) & _U64(0xffffff)).astype(np.float64) / 16777216.0
+    return (stddev * np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)).astype(np.float32)
+
+
 def fc_block_fwd(p, name, h, act, opts, salt):
     """One fully_connected call site with its optional normalizer and dropout.  opts (all optional):
     bn_state {name/BatchNorm/<key>}, train (True), update (False), keep_prob (1.0), rng (seed, tick)."""

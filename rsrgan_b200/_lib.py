@@ -115,6 +115,7 @@ SIGNATURES = {
     "rsr_affine_act_drop": [vp, vp, vp, ci, cll, ci, vp, vp, ci, cf, vp, C.c_uint, vp, ci, vp, ci],
     "rsr_bn_bwd": [vp, vp, vp, ci, vp, ci, cll, ci, ci, cf, vp, C.c_uint, ci, vp, vp, vp, vp, vp, ci, vp, ci, vp],
     "rsr_rng_tick": [vp, vp, vp],
+    "rsr_gauss_noise": [vp, vp, vp, C.c_uint, vp, cll, cf],
     "rsr_ark_decompress": [vp, vp, vp, vp, cf, cf, ci, ci, vp, ci, vp, vp, vp, ci],
     "rsr_crc32c_host": [vp, C.c_ulonglong, C.c_uint],
 }

@@ -780,6 +780,29 @@ extern "C" int rsr_vbn_bwd(rsr_handle* h, void* stream, const void* da16, int ld
                        lddz, dz32, lddz32, scratch, batch_weight);
 }
 
+// Gaussian draws from the same counter-based stream (the discriminator's input noise, utils/ops.py:19-30): element i of
+// the draw named (seed, tick, salt) is Box-Muller of the two 24-bit fields of splitmix64(key ^ i)
+__global__ void __launch_bounds__(256) gauss_noise_kernel(const unsigned long long* __restrict__ rng, unsigned salt,
+                                                          float* __restrict__ out, long long n, float stddev) {
+    const uint64_t key = drop_key(rng, salt);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint64_t hsh = splitmix64(key ^ (uint64_t)i);
+        const float u1 = ((float)(uint32_t)(hsh >> 40) + 1.0f) * (1.0f / 16777216.0f);          // (0, 1]
+        const float u2 = (float)((uint32_t)(hsh >> 16) & 0xffffffu) * (1.0f / 16777216.0f);     // [0, 1)
+        out[i] = stddev * sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    }
+}
+
+extern "C" int rsr_gauss_noise(rsr_handle* h, void* stream, const unsigned long long* rng, unsigned salt, float* out,
+                               long long n, float stddev) {
+    if (!h || !rng || !out || n <= 0) return RSR_E_ARG;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 4LL * h->num_sms) blocks = 4LL * h->num_sms;
+    gauss_noise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rng, salt, out, n, stddev);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int rsr_rng_tick(rsr_handle* h, void* stream, unsigned long long* rng) {
     if (!h || !rng) return RSR_E_ARG;
     rng_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rng);

@@ -70,6 +70,10 @@ inline unsigned int* rsr_take_flags(rsr_handle* h, int n) {
     return f;
 }
 
+// zeroes `n` counters with a one-block kernel (lstmp_sm100.cu).  A cudaMemsetAsync node in front of a kernel costs ~13 us of
+// dependency latency inside a captured graph (profiles/r2_timeline_graph_cfg2_v2.txt), a kernel node ~0.5 us.
+int rsr_zero_u32(unsigned int* p, int n, cudaStream_t stream);
+
 // Dynamic shared memory floors that keep TMEM owners apart when kernels of different streams overlap:
 // two recurrence CTAs (each allocates up to all 512 TMEM columns and waits on its cluster) must never share
 // an SM (cross-cluster alloc waits could deadlock), and a GEMM CTA must not share one with either.

@@ -635,7 +635,7 @@ extern "C" int rsr_lstmp_wave_fwd(rsr_handle* h, void* stream, const rsr_wave_ar
         rc = rsr_get_tmap(h, a->mt1, (uint64_t)Cp, (uint64_t)(T + 1) * B, (uint64_t)Cp, 64, (uint32_t)NBP, &tmM);
         if (rc) return rc;
         unsigned int* flags = rsr_take_flags(h, 2 * groups);
-        RSR_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * 2 * groups, (cudaStream_t)stream));
+        { const int rz = rsr_zero_u32(flags, 2 * groups, (cudaStream_t)stream); if (rz) return rz; }
         PFwdParams p1, p2;
         fill_fwd_params(p1, h, B, T, Cp, Ik1, a->kxT1, a->bias1, a->wcT1, a->w_i1, a->w_f1, a->w_o1, a->forget_bias, a->lengths, a->mt1, a->save1);
         fill_fwd_params(p2, h, B, T, Cp, Ik2, a->kxT2, a->bias2, a->wcT2, a->w_i2, a->w_f2, a->w_o2, a->forget_bias, a->lengths, a->mt2, a->save2);
@@ -1281,7 +1281,7 @@ extern "C" int rsr_lstmp_wave_bwd(rsr_handle* h, void* stream, const rsr_wave_bw
         int rc = rsr_get_tmap(h, a->dz2, (uint64_t)4 * Cp, (uint64_t)T * B, (uint64_t)4 * Cp, 64, (uint32_t)NBP, &tmZ);
         if (rc) return rc;
         unsigned int* flags = rsr_take_flags(h, 2 * groups);
-        RSR_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * 2 * groups, (cudaStream_t)stream));
+        { const int rz = rsr_zero_u32(flags, 2 * groups, (cudaStream_t)stream); if (rz) return rz; }
         PBwdParams p2, p1;
         fill_bwd_params(p2, h, B, T, Cp, a->dmt2, a->wc2, a->w_i2, a->w_f2, a->w_o2, a->lengths, a->save2, a->dz2, a->dbias2,
                         a->dw_i2, a->dw_f2, a->dw_o2);

@@ -417,7 +417,17 @@ int pick_nb(int B, int ctas_per_group, int num_sms, int max_smem, int Cp, bool f
 
 unsigned int* take_flags(rsr_handle* h, int n) { return rsr_take_flags(h, n); }
 
+__global__ void zero_u32_kernel(unsigned int* p, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0u;
+}
+
 }  // namespace
+
+int rsr_zero_u32(unsigned int* p, int n, cudaStream_t stream) {
+    zero_u32_kernel<<<1, 128, 0, stream>>>(p, n);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int rsr_lstmp_rec_fwd(rsr_handle* h, void* stream, int B, int T, int Cp, const float* zx,
                                  const void* wcT, const float* w_i, const float* w_f, const float* w_o,
@@ -447,7 +457,7 @@ extern "C" int rsr_lstmp_rec_fwd(rsr_handle* h, void* stream, int B, int T, int 
     p.mt_seq = (uint16_t*)mt_seq; p.save = save;
     p.kb_smem = fwd_kb_smem(Cp); p.wcT = (const uint16_t*)wcT;
     p.flags = take_flags(h, groups);
-    RSR_CHECK_CUDA(cudaMemsetAsync(p.flags, 0, sizeof(unsigned int) * groups, (cudaStream_t)stream));
+    { const int rz = rsr_zero_u32(p.flags, groups, (cudaStream_t)stream); if (rz) return rz; }
     if (nb == 16) {
         RSR_CHECK_CUDA(cudaFuncSetAttribute(lstmp_rec_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
         lstmp_rec_fwd_kernel<16><<<groups * G, 128, smem, (cudaStream_t)stream>>>(tmW, tmM, p);
@@ -509,7 +519,7 @@ extern "C" int rsr_lstmp_rec_bwd(rsr_handle* h, void* stream, int B, int T, int 
     p.dmt = dmt; p.w_i = w_i; p.w_f = w_f; p.w_o = w_o; p.lengths = lengths; p.save = save;
     p.dz16 = (uint16_t*)dz16; p.dbias = dbias; p.dw_i = dw_i; p.dw_f = dw_f; p.dw_o = dw_o;
     p.flags = take_flags(h, groups);
-    RSR_CHECK_CUDA(cudaMemsetAsync(p.flags, 0, sizeof(unsigned int) * groups, (cudaStream_t)stream));
+    { const int rz = rsr_zero_u32(p.flags, groups, (cudaStream_t)stream); if (rz) return rz; }
     if (nb == 16) {
         RSR_CHECK_CUDA(cudaFuncSetAttribute(lstmp_rec_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
         lstmp_rec_bwd_kernel<16><<<groups * per_grp, 128, smem, (cudaStream_t)stream>>>(tmW, p);

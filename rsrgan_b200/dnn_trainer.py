@@ -66,7 +66,7 @@ class DNNTrainer(GAN_RNN):
         gs = self._gscale(rows) if want_grad else 1.0
         g32 = G.fwd(x, B, T, ln, train=train)
         dg32 = G.ws.get(("loss", "dg32"), rows, g32.shape[1], F32) if want_grad else None
-        self._losses.zero_()
+        h.fill32(self._losses, 0.0)
         # g_mse = 0.5 * output_dim * mean((g - y)^2)   (dnn_trainer_single_gpu.py:109-110)
         h.lsgan_mse_losses(self._losses, g=g32, y=y_tm, n_frames=rows, d_out=self.output_dim, lam=1.0, gscale=gs,
                            dg_mse=dg32)

@@ -166,6 +166,10 @@ class GAN_RNN(Model):
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.dist = torch.distributed
             self.world = torch.distributed.get_world_size()
+        # the discriminator's input noise: one counter-based stream per rank (every tower of the reference owns its
+        # random_normal op), state {seed, draws so far} on the device
+        self._noise_seed = int(_arg(args, "seed", 1234)) * 7919 + 17 + (self.dist.get_rank() if self.dist else 0)
+        self._noise_rng = None
 
         if share is not None:
             # train and CV models share weights (scripts/train_gan_rnn_placeholder.py:431-437) but own their
@@ -418,8 +422,14 @@ class GAN_RNN(Model):
             return self._to_dev("noise_" + slot, np.asarray(given, np.float32).reshape(B, -1), F32)
         if self.disc_noise_std <= 0.0:
             return None
-        # utils/ops.py:19-30: tf.random_normal of shape (B, 1, D) -- one draw per utterance
-        return torch.randn(B, self.output_dim, dtype=F32, device=self.h.device) * self.disc_noise_std
+        # utils/ops.py:19-30: tf.random_normal of shape (B, 1, D) -- one draw per utterance, from the library's
+        # counter-based stream (the tick advances with every draw, on the device: CUDA-graph safe)
+        if self._noise_rng is None:
+            self._noise_rng = torch.tensor([self._noise_seed, 0], dtype=torch.int64, device=self.h.device)
+        out = self.D.ws.get(("noise", slot), B, self.output_dim, F32)
+        self.h.gauss_noise(self._noise_rng, 0x4e01 if slot == "rl" else 0x4e02, out, self.disc_noise_std)
+        self.h.rng_tick(self._noise_rng)
+        return out
 
     def _gscale(self, rows):
         """Loss scale keeping the 16-bit gradient tensors of the backward pass in range (fp16 operands): the gradients
@@ -505,7 +515,7 @@ class GAN_RNN(Model):
     def _l2_loss(self):
         """l2_scale * sum_{non-bias} 0.5 ||v||^2   (gan_rnn_placeholder.py:253-258)"""
         if self.l2_scale <= 0.0 or self.cross_validation:
-            self._losses[4:5].zero_()
+            self.h.fill32(self._losses[4:5], 0.0)
             return
         P = self.G.P
         self.h.seg_sumsq(P.theta, 1.0, P.seg_id, len(P.segs), P.sumsq)
@@ -524,7 +534,7 @@ class GAN_RNN(Model):
         d_rl16 = D.ws.get(("loss", "d_rl16"), rows, 8, h.h16)
         d_fk16 = D.ws.get(("loss", "d_fk16"), rows, 8, h.h16)
         n_rl, n_fk = self._noise(B, noise_rl), self._noise(B, noise_fk, "fk")
-        self._losses.zero_()
+        h.fill32(self._losses, 0.0)
         h.fill32(D.P.grad, 0.0)
         kw = dict(n_logit=rows, clip=D.clip, d_real=self.d_real, d_fake=self.d_fake, lam=self.mse_lambda, gscale=gs,
                   ld_grad=8)
@@ -564,7 +574,7 @@ class GAN_RNN(Model):
         # that input -- the generator's columns come first, the conditioning columns of a conditioned D stay zero
         dw = g32.shape[1] if not D.cat_dim else (D.in_dim + D.cat_dim + 7) // 8 * 8
         dg32 = D.ws.get(("loss", "dg32"), rows, dw, F32)
-        self._losses.zero_()
+        h.fill32(self._losses, 0.0)
         h.lsgan_mse_losses(self._losses, fk=lg_fk, ld_logit=lg_fk.stride(0), n_logit=rows, clip=D.clip,
                            g=g32, y=y_tm, n_frames=rows, d_out=self.output_dim, d_real=self.d_real,
                            d_fake=self.d_fake, lam=self.mse_lambda, gscale=gs, g_adv_grad=g_adv16,
@@ -779,7 +789,7 @@ class GAN_RNN(Model):
         g32 = G.fwd(x, B, T, ln, train=False)
         lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=self._noise(B, noise_rl), train=False, cat_src=self._cat(x))
         lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"), train=False, cat_src=self._cat(x))
-        self._losses.zero_()
+        h.fill32(self._losses, 0.0)
         h.lsgan_mse_losses(self._losses, rl=lg_rl, fk=lg_fk, ld_logit=lg_rl.stride(0), n_logit=rows, clip=D.clip,
                            g=g32, y=y_tm, n_frames=rows, d_out=self.output_dim, d_real=self.d_real,
                            d_fake=self.d_fake, lam=self.mse_lambda, gscale=1.0)

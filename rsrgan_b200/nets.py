@@ -350,8 +350,8 @@ class LSTMP(object):
         dz2 = net.ws.get(k2 + ("dz",), rows + B, 4 * Cp, h.h16)
         dmt2 = net.ws.get((ctx, "dmt", Cp, B), rows, Cp, F32)
         part = net.ws.get((ctx, "wave_part", Cp, B), T * (B + 48), Cp, F32)   # zero at allocation and after every launch
-        dz1[rows:].zero_()
-        dz2[rows:].zero_()
+        h.fill32(dz1[rows:].view(F32), 0.0)                # dz_{T} = 0 (no step after the last one; T varies per batch)
+        h.fill32(dz2[rows:].view(F32), 0.0)
 
         def sink(l):
             s = l.scratch
@@ -397,7 +397,9 @@ class LSTMP(object):
         h.gemm(dout16, self._w()[2], rows, Cp, self.Pp, out32=dmt)
 
     def bwd_main(self, ctx, dout16, B, T, lengths, want_dw=True, want_dx=True, prev_y16=None, prev_act=ACT_NONE,
-                 resid32=None, want32=False):
+                 resid32=None, want32=False, after_rec=None):
+        """after_rec: called right behind the launch of the recurrence kernel -- the place to enqueue side-stream work
+        that should take the SMs the recurrence leaves free rather than the ones it is about to need."""
         net, h, P = self.net, self.net.h, self.net.P
         rows, Cp = T * B, self.Cp
         key = (ctx, self.prefix, B)
@@ -405,7 +407,7 @@ class LSTMP(object):
         sv = net.ws.get(key + ("save",), rows, 5 * Cp, F32)
         dmt = net.ws.get((ctx, "dmt", Cp, B), rows, Cp, F32)
         dz = net.ws.get(key + ("dz",), rows + B, 4 * Cp, h.h16)       # per layer: the side stream reads it after we return
-        dz[rows:].zero_()                                  # dz_{T} = 0 (no step after the last one; T varies per batch)
+        h.fill32(dz[rows:].view(F32), 0.0)                 # dz_{T} = 0 (no step after the last one; T varies per batch)
         if want_dw:
             gb = P.view(self.prefix + "bias", "grad")
             gi, gf, go = (P.view(self.prefix + n, "grad") for n in ("w_i_diag", "w_f_diag", "w_o_diag"))
@@ -415,6 +417,8 @@ class LSTMP(object):
         h.lstmp_rec_bwd(B, T, Cp, dmt, self.wc16, P.view(self.prefix + "w_i_diag"),
                         P.view(self.prefix + "w_f_diag"), P.view(self.prefix + "w_o_diag"), lengths, sv,
                         dz, gb, gi, gf, go, work=self.rec_flops(B, T))
+        if after_rec is not None:
+            after_rec()
         dx16 = dx32 = None
         if want_dx:    # the next (earlier) layer waits for this: main stream, before the weight gradients
             dx16 = net.ws.get(key + ("dx16",), rows, self.Ip, h.h16)
@@ -423,8 +427,9 @@ class LSTMP(object):
                    out16=dx16, out32=dx32)
         return dx16, dx32
 
-    def bwd_side(self, ctx, x16, dout32, B, T):
-        """weight gradients, on the side stream: they overlap the next layer's recurrence"""
+    def bwd_side(self, ctx, x16, dout32, B, T, after=None):
+        """weight gradients, on the side stream: they overlap the next layer's recurrence.  after: a Handle.mark() the
+        side stream waits for instead of the calling stream's tail."""
         net, h, P = self.net, self.net.h, self.net.P
         rows, Cp = T * B, self.Cp
         key = (ctx, self.prefix, B)
@@ -432,7 +437,7 @@ class LSTMP(object):
         mt = net.ws.get(key + ("mt",), rows + B, Cp, h.h16)
         out = net.ws.get(key + ("out",), rows + B, self.Pp, h.h16)
         dz = net.ws.get(key + ("dz",), rows + B, 4 * Cp, h.h16)
-        with h.side_stream():
+        with h.side_stream(after=after):
             gK = P.view(self.prefix + "kernel", "grad")
             # dK = [x_t , m_{t-1}]^T dz_t  (two row blocks of the TF kernel)
             h.gemm(x16, dz, self.Ip, 4 * Cp, rows, a_mn=True, b_mn=True, beta=1.0, out32=gK[:self.Ip])
@@ -985,11 +990,18 @@ class Generator(Net):
         if self.g_type == "lstm":
             d16, d32 = Ls[-1].bwd("g", acts[-1], dy16, rows, want32=True)
             Ls[-2].bwd_pre("g", d16, B, T)
+            pending = []
+
+            def flush():
+                while pending:
+                    l, a, d, ev = pending.pop(0)
+                    l.bwd_side("g", a, d, B, T, after=ev)
             i = len(Ls) - 2
             while i >= 1:
                 dout32 = d32
                 if i >= 2 and Ls[i - 1].wave:     # this layer and the one below it as one wavefront launch
                     mask = i - 1 == 1 and not self.fcbn
+                    flush()
                     w = Ls[i - 1].bwd_wave(Ls[i], "g", acts[i - 1], acts[i], dout32, B, T, lengths,
                                            prev_y16=acts[1] if mask else None, prev_act=ACT_LRELU if mask else ACT_NONE,
                                            want32=i - 1 > 1)
@@ -1001,12 +1013,16 @@ class Generator(Net):
                         continue
                 first = i == 1
                 mask = first and not self.fcbn      # an FCBN first layer applies its own activation gradient
+                # the weight gradients of the layer above are enqueued BEHIND this layer's recurrence kernel (the side
+                # stream itself only waits for the point where their operands were complete): launched in front of it,
+                # their persistent 148-CTA GEMM held the recurrence's cluster slots for ~20 us
                 d16, d32 = Ls[i].bwd_main("g", d16, B, T, lengths, prev_y16=acts[1] if mask else None,
-                                          prev_act=ACT_LRELU if mask else ACT_NONE, want32=not first)
+                                          prev_act=ACT_LRELU if mask else ACT_NONE, want32=not first, after_rec=flush)
                 if not first:
                     Ls[i - 1].bwd_pre("g", d16, B, T)     # critical path first, then this layer's weight gradients
-                Ls[i].bwd_side("g", acts[i], dout32, B, T)
+                pending.append((Ls[i], acts[i], dout32, self.h.mark()))
                 i -= 1
+            flush()
             Ls[0].bwd("g", acts[0], d16, rows, want_dx=False, dw_side=False)
             return
         d16, d32 = Ls[-1].bwd("g", acts[-1], dy16, rows, want32=True)

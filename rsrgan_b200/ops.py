@@ -52,15 +52,26 @@ class Handle(object):
         self._side = torch.cuda.Stream(device=self.device)
         self._side_dirty = False
 
+    def mark(self):
+        """An event at the current tail of the current stream (None when the side stream is off): `side_stream(after=...)`
+        orders side work behind this point instead of behind whatever has been enqueued by then."""
+        if not self.overlap or self.timing is not None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return ev
+
     @contextlib.contextmanager
-    def side_stream(self):
+    def side_stream(self, after=None):
         """Calls made inside run on the side stream, ordered after everything enqueued so far on the
-        current stream; `join()` makes the current stream wait for them."""
+        current stream (or after the `mark()` passed as `after`); `join()` makes the current stream wait for them."""
         if not self.overlap or self.timing is not None:
             yield
             return
-        main = torch.cuda.current_stream()
-        self._side.wait_stream(main)
+        if after is not None:
+            self._side.wait_event(after)
+        else:
+            self._side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
             yield
         self._side_dirty = True
@@ -433,6 +444,10 @@ class Handle(object):
 
     def rng_tick(self, rng):
         self._call("rsr_rng_tick", 1, self.h, _stream(), _p(rng))
+
+    def gauss_noise(self, rng, salt, out, stddev):
+        """out (fp32, contiguous) = stddev * N(0, 1) from the counter-based stream {seed, tick} (rsr_gauss_noise)."""
+        self._call("rsr_gauss_noise", 1, self.h, _stream(), _p(rng), salt, _p(out), out.numel(), float(stddev))
 
     # ------------------------------------------------------ Kaldi compressed-matrix decode
     def ark_decompress(self, col_hdr, data, min_value, rng, rows, cols, out64=None, out32=None, mean=None, std=None):

@@ -46,8 +46,11 @@ class FakeHandle(object):
         pass
 
     @contextlib.contextmanager
-    def side_stream(self):     # no streams on the CPU double: everything is serial
+    def side_stream(self, after=None):     # no streams on the CPU double: everything is serial
         yield
+
+    def mark(self):
+        return None
 
     def join(self):
         pass
@@ -464,6 +467,11 @@ class FakeHandle(object):
     def rng_tick(self, rng):
         self.launches += 1
         rng[1] += 1
+
+    def gauss_noise(self, rng, salt, out, stddev):
+        from oracle import rsr_oracle as O
+        self.launches += 1
+        out.copy_(torch.tensor(O.gauss_noise(int(rng[0]), int(rng[1]), salt, out.numel(), stddev)).reshape(out.shape))
 
     # ------------------------------------------------------ Kaldi compressed-matrix decode
     def ark_decompress(self, col_hdr, data, min_value, rng, rows, cols, out64=None, out32=None, mean=None, std=None):

@@ -350,6 +350,23 @@ def test_lstmp_wave_backward(h, monkeypatch, B, T, I, C, P, ragged, nbp):
     assert float(part.abs().max()) == 0.0        # the scratch is handed back zeroed
 
 
+def test_gauss_noise_stream(h):
+    """rsr_gauss_noise == the oracle's restatement of the counter-based stream; draws differ by tick and salt."""
+    dev = h.device
+    rng = torch.tensor([4242, 7], dtype=torch.int64, device=dev)
+    out = torch.zeros(64, 40, dtype=torch.float32, device=dev)
+    h.gauss_noise(rng, 0x4e01, out, 0.05)
+    ref = O.gauss_noise(4242, 7, 0x4e01, 64 * 40, 0.05).reshape(64, 40)
+    got = out.cpu().numpy()
+    assert np.abs(got - ref).max() < 2e-6
+    h.rng_tick(rng)
+    out2 = torch.zeros_like(out)
+    h.gauss_noise(rng, 0x4e01, out2, 0.05)
+    torch.cuda.synchronize()
+    assert int(rng[1]) == 8 and np.abs(out2.cpu().numpy() - O.gauss_noise(4242, 8, 0x4e01, 64 * 40, 0.05).reshape(64, 40)).max() < 2e-6
+    assert np.abs(out2.cpu().numpy() - got).max() > 0.01
+
+
 def test_lstmp_shape_errors(h):
     z = torch.zeros(8, device=h.device)
     from rsrgan_b200 import _lib

@@ -309,3 +309,16 @@ def test_virtual_batch_norm_against_autograd():
     yt.backward(torch.tensor(dy))
     for a, r in ((y, yt.detach()), (dx, xt.grad), (dg, gt.grad), (db, bt.grad)):
         assert np.abs(a - r.numpy()).max() < 1e-11
+
+
+def test_gauss_noise_moments():
+    """The counter-based Gaussian stream of rsr_gauss_noise (discriminator input noise, utils/ops.py:19-30): unit
+    moments, no correlation between draws that differ by tick or salt."""
+    a = O.gauss_noise(1234, 0, 0x4e01, 200000, 1.0).astype(np.float64)
+    b = O.gauss_noise(1234, 1, 0x4e01, 200000, 1.0).astype(np.float64)
+    c = O.gauss_noise(1234, 0, 0x4e02, 200000, 1.0).astype(np.float64)
+    for v in (a, b, c):
+        assert abs(v.mean()) < 0.01 and abs(v.std() - 1.0) < 0.01
+        assert abs((v ** 3).mean()) < 0.03 and abs((v ** 4).mean() - 3.0) < 0.1
+    assert abs((a * b).mean()) < 0.01 and abs((a * c).mean()) < 0.01
+    assert np.abs(O.gauss_noise(1234, 0, 0x4e01, 16, 0.5) * 2 - a[:16]).max() < 1e-6
