@@ -139,6 +139,9 @@ lstmp_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             }
             fence_proxy_async_all();
             if (elect_one_sync()) {
+                // (measured and not kept, profiles/r2_rec_steps_big_v2.txt / _v3.txt: one barrier per K sub-tile so that its
+                //  MMAs start as soon as it lands -- 5.5 instead of 4.6 us per step at Cp = 1024, sixteen try_wait round
+                //  trips cost more than the overlap gains; the saved activations stored behind the release -- no change)
                 mbar_expect_tx(barB, (uint32_t)KB * NB * 128u);
                 for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * NB * 128u, &tmM, barB, kb * 64, t * p.B + b0);
                 if (t == 0) mbar_wait(barA, 0);
