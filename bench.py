@@ -125,10 +125,12 @@ def peaks():
 
 
 NCU_SUMMARY = {   # C-ABI call -> committed `ncu --set full` summary of its kernel (profiles/, made by scripts in DESIGN.md 6)
-    "rsr_gemm": "r1_gemm_full_summary.csv",
-    "rsr_lstmp_rec_bwd": "r2_recbwd_pair_full_summary.csv",       # CTA-pair kernels (cfg-2: Cp = 512)
+    "rsr_gemm": "r2_gemm_full_summary.csv",                        # 90 launches of one cfg-2 schedule, final tree
+    "rsr_lstmp_rec_bwd": "r2_recbwd_pair_v2_full_summary.csv",     # CTA-pair kernels (cfg-2: Cp = 512)
     "rsr_lstmp_rec_fwd": "r1_recfwd_full_summary.csv",
     "rsr_lstmp_fused_fwd": "r2_recfwd_pair_full_summary.csv",
+    "rsr_lstmp_wave_fwd": "r2_wave_fwd_full_summary.csv",          # layer-wavefront launches (cfg-2 forward, cfg-P backward)
+    "rsr_lstmp_wave_bwd": "r2_wave_bwd_full_summary.csv",
 }
 
 
@@ -147,7 +149,10 @@ def ncu_traffic(call):
         try:
             b = sum(float(r[hdr.index(k)]) * mult[units[hdr.index(k)]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         except (ValueError, KeyError):
-            continue
+            try:        # section captures carry the total only (dram__bytes.sum.per_second x duration, see profiles/README.md)
+                b = float(r[hdr.index("dram__bytes.sum")]) * mult[units[hdr.index("dram__bytes.sum")]]
+            except (ValueError, KeyError):
+                continue
         tot, n = tot + b, n + 1
     return tot / n if n else None
 

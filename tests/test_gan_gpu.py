@@ -381,3 +381,37 @@ def test_graph_replay_survives_workspace_growth():
     assert any(st["graph"] is not None for st in ma._graphs.values())      # ... and they were captured again
     for na, nb in ((ma.G, mb.G), (ma.D, mb.D)):
         assert rms(na.P.theta.cpu().numpy(), nb.P.theta.cpu().numpy())[1] < 1e-4
+
+
+@pytest.mark.parametrize("g_type,d_type,B,T,kw", [
+    ("lstm", "dnn", 96, 24, dict(g_cell=512, g_proj=256, g_layers=2)),      # cfg-2 generator: forward AND backward wavefront
+    ("lstm", "dnn", 128, 16, dict(g_cell=512, g_proj=256, g_layers=2)),     # ... benchmarked batch: forward only (48 per cluster)
+    ("lstm", "lstm", 40, 20, dict(g_cell=256, g_proj=64, g_layers=3)),      # three layers (pair + single), LSTM discriminator
+])
+def test_layer_wavefront_matches_layer_by_layer(monkeypatch, g_type, d_type, B, T, kw):
+    """One whole schedule (1 D + 2 G updates) with the wavefront launches == the same schedule with every LSTMP layer
+    launched on its own (RSR_NO_WAVE=1): same losses, same generator afterwards.  The two paths differ only in where 16-bit
+    roundings fall (the projection stage against the projection GEMM; dz2 (W_p1 K_x2)^T folded against two GEMMs)."""
+    rng = np.random.default_rng(B + T)
+    x = rng.standard_normal((B, T, 257)).astype(np.float32)
+    y = rng.standard_normal((B, T, 40)).astype(np.float32)
+    lengths = rng.integers(T // 2, T + 1, size=B)
+    nz = {}
+    outs = []
+    for no_wave in (False, True):
+        if no_wave:
+            monkeypatch.setenv("RSR_NO_WAVE", "1")
+        m = make_model(g_type, d_type, B, use_graph=False, init_disc_noise_std=0.0, **kw)
+        n0 = m.h.launches
+        losses = m.train_batch(x, y, lengths)
+        g = m.generate(x, lengths).cpu().numpy()
+        grads = m.G.P.grad.clone().cpu().numpy()
+        outs.append((losses, g, grads, m.h.launches - n0))
+    (l_w, g_w, gr_w, n_w), (l_s, g_s, gr_s, n_s) = outs
+    assert n_w < n_s                                   # the wavefront path really ran (fewer launches)
+    for k in l_s:
+        assert l_w[k] == pytest.approx(l_s[k], rel=2e-3, abs=1e-6), k
+    a, r = rms(g_w, g_s)
+    assert r < 2e-3, (a, r)
+    a, r = rms(gr_w, gr_s)
+    assert r < 1e-2, (a, r)
