@@ -82,6 +82,19 @@ int rsr_fc1_fwd(rsr_handle* h, void* stream, const void* x16, int ldx, long long
                 const void* w16, int ldw, const float* bias, float* out32, int ldo);
 int rsr_fc1_bwd_dx(rsr_handle* h, void* stream, const void* dy16, int ldy, long long rows, int K,
                    const void* w16, int ldw, const void* dact_src, int ldd, int dact, void* dx16, int ldo);
+/* The whole discriminator head in one pass over the last hidden activation x16 (models/discriminator_dnn.py:90-93 +
+ * the logit terms of models/gan_rnn_placeholder.py:244-252): rsr_fc1_fwd, the logit half of rsr_lsgan_mse_losses and
+ * rsr_fc1_bwd_dx with identical arithmetic, three launches and two passes over the activation fewer.
+ *   which = 0  D(labels):  losses[0] += mean((l - d_real)^2),                         gradient target d_real
+ *   which = 1  D(G(x)):    losses[1] += mean((l - d_fake)^2), losses[2] += mean((l - d_real)^2), gradient target
+ *              grad_target (d_fake in the discriminator update, d_real in the generator update)
+ *   l = clip ? clip_by_value(logit, -0.5, 1.5) : logit (gradient zero outside the range);
+ *   dlogit16[r * ldg] = h16(gscale * 2 (l - target) / rows);  dx16[r, k] = h16(dlogit16[r] * w16[k] * act'(x16[r, k])) with
+ *   act = dact (the activation that produced x16; RSR_ACT_NONE: no mask).  logit32 / dlogit16 / dx16 / losses may be NULL. */
+int rsr_fc1_head(rsr_handle* h, void* stream, const void* x16, int ldx, long long rows, int K,
+                 const void* w16, int ldw, const float* bias, int which, int clip, float d_real, float d_fake,
+                 float grad_target, float gscale, float* losses, float* logit32, int ldl, void* dlogit16, int ldg,
+                 int dact, void* dx16, int ldo);
 
 /* input staging ---------------------------------------------------------------------- */
 /* x fp32 batch-major (B, T, D) -> h16 time-major [T*B, ld16] (and optional fp32 copy [T*B, ld32]):

@@ -95,6 +95,7 @@ SIGNATURES = {
     "rsr_fill32": [vp, vp, vp, cll, cf],
     "rsr_fc1_fwd": [vp, vp, vp, ci, cll, ci, vp, ci, vp, vp, ci],
     "rsr_fc1_bwd_dx": [vp, vp, vp, ci, cll, ci, vp, ci, vp, ci, ci, vp, ci],
+    "rsr_fc1_head": [vp, vp, vp, ci, cll, ci, vp, ci, vp, ci, ci, cf, cf, cf, cf, vp, vp, ci, vp, ci, ci, vp, ci],
     "rsr_conv_stage_frames": [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp],
     "rsr_conv_mask_rows": [vp, vp, vp, cll, ci, ci, ci],
     "rsr_conv_w_flip": [vp, vp, vp, ci, ci, ci, vp],

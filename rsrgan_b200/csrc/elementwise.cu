@@ -684,6 +684,82 @@ __global__ void __launch_bounds__(256) fc1_bwd_dx_kernel(const uint16_t* __restr
     }
 }
 
+// The discriminator head in ONE pass over the last hidden activation: logit = x . w + b (models/discriminator_dnn.py:90-93),
+// the LSGAN loss terms and their gradient at the logit (models/gan_rnn_placeholder.py:244-252, the same arithmetic as
+// lsgan_mse_kernel, clip_by_value mask included), and the head's data gradient dx = dlogit w (.) act'(x) -- what
+// fc1_fwd + lsgan_mse + fc1_bwd_dx do in three launches and two more passes over the activation.  One warp per row; the
+// row is read twice back to back (second time from L1).  which = 0: D(labels) pass, target d_real; which = 1: D(G(x))
+// pass, losses against d_fake and d_real, gradient against grad_target (d_fake in the D update, d_real in the G update).
+struct HeadParams {
+    const uint16_t* x; int ldx; long long rows; int K;
+    const uint16_t* w; int ldw; const float* bias;
+    int which, clip; float d_real, d_fake, grad_target, gscale;
+    float* losses;
+    float* logit; int ldl;
+    uint16_t* dlogit; int ldg;
+    int dact;                   // RSR_ACT_*: the activation that produced x (mask of the data gradient), NONE = no mask
+    uint16_t* dx; int ldo;
+    int bf;
+};
+
+__global__ void __launch_bounds__(256) fc1_head_kernel(const HeadParams p) {
+    extern __shared__ float fc1_w[];
+    __shared__ float sh[8];
+    for (int k = threadIdx.x; k < p.K; k += blockDim.x) fc1_w[k] = h2f(p.w[(size_t)k * p.ldw], p.bf);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float b0 = p.bias ? p.bias[0] : 0.f;
+    const float inv_nl = 1.0f / (float)p.rows;
+    const float neg = p.dact == RSR_ACT_LRELU ? 0.3f : 0.0f;
+    const bool mask = p.dact != RSR_ACT_NONE;
+    float s_a = 0.f, s_b = 0.f;
+    for (long long r = warp0; r < p.rows; r += nwarps) {
+        const uint16_t* xr = p.x + r * p.ldx;
+        float acc = 0.f;
+        for (int k0 = lane * 8; k0 < p.K; k0 += 256) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(xr + k0));
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc = fmaf(h2f((uint16_t)(u[i] & 0xFFFFu), p.bf), fc1_w[k0 + 2 * i], acc);
+                acc = fmaf(h2f((uint16_t)(u[i] >> 16), p.bf), fc1_w[k0 + 2 * i + 1], acc);
+            }
+        }
+        const float uu = warp_sum(acc) + b0;
+        const float l = p.clip ? fminf(fmaxf(uu, -0.5f), 1.5f) : uu;
+        const float in = (!p.clip || (uu >= -0.5f && uu <= 1.5f)) ? 1.f : 0.f;
+        const float e_real = l - p.d_real, e_fake = l - p.d_fake;
+        float e_grad;
+        if (p.which == 0) { e_grad = e_real; if (lane == 0) s_a += e_real * e_real; }
+        else { e_grad = l - p.grad_target; if (lane == 0) { s_a += e_fake * e_fake; s_b += e_real * e_real; } }
+        const uint16_t g16 = f2h(p.gscale * 2.f * e_grad * inv_nl * in, p.bf);
+        if (lane == 0) {
+            if (p.logit) p.logit[r * p.ldl] = uu;
+            if (p.dlogit) p.dlogit[r * p.ldg] = g16;
+        }
+        if (p.dx) {
+            const float g = h2f(g16, p.bf);
+            for (int k0 = lane * 8; k0 < p.K; k0 += 256) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(xr + k0));
+                const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool pos_lo = !mask || (int16_t)(u[i] & 0xFFFFu) > 0, pos_hi = !mask || (int32_t)u[i] >= 0x10000;
+                    o[i] = pack2(g * fc1_w[k0 + 2 * i] * (pos_lo ? 1.0f : neg), g * fc1_w[k0 + 2 * i + 1] * (pos_hi ? 1.0f : neg), p.bf);
+                }
+                *reinterpret_cast<uint4*>(p.dx + r * p.ldo + k0) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+    if (p.losses) {
+        block_atomic_add(s_a * inv_nl, p.losses + (p.which == 0 ? 0 : 1), sh);
+        if (p.which != 0) block_atomic_add(s_b * inv_nl, p.losses + 2, sh);
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
@@ -972,6 +1048,24 @@ extern "C" int rsr_fc1_fwd(rsr_handle* h, void* stream, const void* x16, int ldx
     // few, long-lived blocks: every block stages the strided weight column once
     fc1_fwd_kernel<<<grid_for(rows * 16, 256, h->num_sms, 4), 256, (size_t)K * 4, (cudaStream_t)stream>>>(
         (const uint16_t*)x16, ldx, rows, K, (const uint16_t*)w16, ldw, bias, out32, ldo, h->dtype == RSR_DTYPE_BF16);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rsr_fc1_head(rsr_handle* h, void* stream, const void* x16, int ldx, long long rows, int K,
+                            const void* w16, int ldw, const float* bias, int which, int clip, float d_real, float d_fake,
+                            float grad_target, float gscale, float* losses, float* logit32, int ldl, void* dlogit16, int ldg,
+                            int dact, void* dx16, int ldo) {
+    if (!h || !x16 || !w16 || rows <= 0 || K <= 0 || ldw <= 0 || (which != 0 && which != 1)) return RSR_E_ARG;
+    if ((K & 7) || (ldx & 7) || ldx < K || ((uintptr_t)x16 & 15) || K > 8192) return RSR_E_SHAPE;
+    if (dx16 && ((ldo & 7) || ldo < K || ((uintptr_t)dx16 & 15))) return RSR_E_SHAPE;
+    if ((logit32 && ldl <= 0) || (dlogit16 && ldg <= 0)) return RSR_E_ARG;
+    HeadParams p;
+    p.x = (const uint16_t*)x16; p.ldx = ldx; p.rows = rows; p.K = K; p.w = (const uint16_t*)w16; p.ldw = ldw; p.bias = bias;
+    p.which = which; p.clip = clip; p.d_real = d_real; p.d_fake = d_fake; p.grad_target = grad_target; p.gscale = gscale;
+    p.losses = losses; p.logit = logit32; p.ldl = ldl; p.dlogit = (uint16_t*)dlogit16; p.ldg = ldg;
+    p.dact = dact; p.dx = (uint16_t*)dx16; p.ldo = ldo; p.bf = h->dtype == RSR_DTYPE_BF16;
+    fc1_head_kernel<<<grid_for(rows * 32, 256, h->num_sms, 2), 256, (size_t)K * 4, (cudaStream_t)stream>>>(p);
     RSR_LAUNCH_CHECK();
     return 0;
 }

@@ -543,15 +543,25 @@ class GAN_RNN(Model):
         # (a batch-normalised D assigns its moving averages in both passes: those two then stay on one stream,
         # D(labels) first, so that neither read-modify-write is lost)
         serial = D.fcbn and D.bn_update
+        # (D.fwd(head=...): where the discriminator's head qualifies, logits, loss terms, d loss / d logit and the head's
+        #  data gradient come out of one kernel -- rsr_fc1_head -- and only the MSE term is left for rsr_lsgan_mse_losses)
+        hd = dict(clip=D.clip, d_real=self.d_real, d_fake=self.d_fake, gscale=gs, losses=self._losses)
         with (contextlib.nullcontext() if serial else h.side_stream()):
-            lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=n_rl, cat_src=self._cat(x))
-            h.lsgan_mse_losses(self._losses, rl=lg_rl, ld_logit=lg_rl.stride(0), d_rl_grad=d_rl16, **kw)
+            lg_rl = D.fwd("rl", y_tm, B, T, ln, noise=n_rl, cat_src=self._cat(x),
+                          head=dict(hd, which=0, grad_target=self.d_real, dlogit16=d_rl16))
+            if not D.head_fused["rl"]:
+                h.lsgan_mse_losses(self._losses, rl=lg_rl, ld_logit=lg_rl.stride(0), d_rl_grad=d_rl16, **kw)
             D.bwd("rl", d_rl16)
         g32 = _g32 if _g32 is not None else G.fwd(x, B, T, ln, train=_g_train)
         self._last_g32 = g32
-        lg_fk = D.fwd("fk", g32, B, T, ln, noise=n_fk, cat_src=self._cat(x))
-        h.lsgan_mse_losses(self._losses, fk=lg_fk, ld_logit=lg_fk.stride(0), g=g32, y=y_tm, n_frames=rows,
-                           d_out=self.output_dim, d_fk_grad=d_fk16, **kw)
+        lg_fk = D.fwd("fk", g32, B, T, ln, noise=n_fk, cat_src=self._cat(x),
+                      head=dict(hd, which=1, grad_target=self.d_fake, dlogit16=d_fk16))
+        if D.head_fused["fk"]:
+            mse = dict(kw, n_logit=0)
+            h.lsgan_mse_losses(self._losses, g=g32, y=y_tm, n_frames=rows, d_out=self.output_dim, **mse)
+        else:
+            h.lsgan_mse_losses(self._losses, fk=lg_fk, ld_logit=lg_fk.stride(0), g=g32, y=y_tm, n_frames=rows,
+                               d_out=self.output_dim, d_fk_grad=d_fk16, **kw)
         D.bwd("fk", d_fk16)
         self._update(D, gs, adam=D.P.adam)
         return self._loss_dict(self._losses.tolist(), "d") if sync else self._losses
@@ -568,18 +578,28 @@ class GAN_RNN(Model):
             # frame-level GAN: g_opt depends on the whole UPDATE_OPS collection (models/gan.py:139-143), which holds the
             # assignments of the D(labels) pass too -- run that pass for its statistics (its output is not needed)
             D.fwd("rl", y_tm, B, T, ln, noise=self._noise(B, None), cat_src=self._cat(x))
-        lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"), cat_src=self._cat(x))
         g_adv16 = D.ws.get(("loss", "g_adv16"), rows, 8, h.h16)
         # d(lambda g_mse)/dg is added to the discriminator's input gradient by its last GEMM (resid): same width as
         # that input -- the generator's columns come first, the conditioning columns of a conditioned D stay zero
         dw = g32.shape[1] if not D.cat_dim else (D.in_dim + D.cat_dim + 7) // 8 * 8
         dg32 = D.ws.get(("loss", "dg32"), rows, dw, F32)
         h.fill32(self._losses, 0.0)
-        h.lsgan_mse_losses(self._losses, fk=lg_fk, ld_logit=lg_fk.stride(0), n_logit=rows, clip=D.clip,
-                           g=g32, y=y_tm, n_frames=rows, d_out=self.output_dim, d_real=self.d_real,
-                           d_fake=self.d_fake, lam=self.mse_lambda, gscale=gs, g_adv_grad=g_adv16,
-                           ld_grad=8, dg_mse=dg32)
-        dg16 = D.bwd("fk", g_adv16, want_dw=False, want_dx=True, resid32=dg32)
+        lg_fk = D.fwd("fk", g32, B, T, ln, noise=self._noise(B, noise_fk, "fk"), cat_src=self._cat(x),
+                      head=dict(clip=D.clip, d_real=self.d_real, d_fake=self.d_fake, gscale=gs, losses=self._losses,
+                                which=1, grad_target=self.d_real, dlogit16=g_adv16))
+        if D.head_fused["fk"]:
+            # only the MSE term and its gradient are left; nothing reads them before the discriminator's LAST data-gradient
+            # GEMM (resid), so they leave the critical chain: side stream, joined in front of that GEMM
+            with h.side_stream():
+                h.lsgan_mse_losses(self._losses, n_logit=0, clip=D.clip, g=g32, y=y_tm, n_frames=rows, d_out=self.output_dim,
+                                   d_real=self.d_real, d_fake=self.d_fake, lam=self.mse_lambda, gscale=gs, ld_grad=8,
+                                   dg_mse=dg32)
+        else:
+            h.lsgan_mse_losses(self._losses, fk=lg_fk, ld_logit=lg_fk.stride(0), n_logit=rows, clip=D.clip,
+                               g=g32, y=y_tm, n_frames=rows, d_out=self.output_dim, d_real=self.d_real,
+                               d_fake=self.d_fake, lam=self.mse_lambda, gscale=gs, g_adv_grad=g_adv16,
+                               ld_grad=8, dg_mse=dg32)
+        dg16 = D.bwd("fk", g_adv16, want_dw=False, want_dx=True, resid32=dg32, pre_last=h.join)
         h.fill32(G.P.grad, 0.0)
         G.bwd(dg16[:, :g32.shape[1]] if D.cat_dim else dg16)
         self._l2_loss()

@@ -16,6 +16,7 @@ arithmetic is done by librsrgan_sm100.so (ops.Handle).  No function here has a C
 from __future__ import annotations
 
 import contextlib
+import os
 
 import torch
 
@@ -87,15 +88,34 @@ class FC(object):
                bias=net.P.view(self.bname), act=self.act, out16=y16, out32=y32)
         return y16, y32
 
+    def head_ok(self):
+        """this layer is a one-unit head the fused head kernel applies to (rsr_fc1_head)"""
+        return self.n_out == 1 and self.act == ACT_NONE and self.inp >= 64
+
+    def head(self, ctx, x16, rows, spec, want_dx, x_act):
+        """Forward, LSGAN loss terms, d loss / d logit and (want_dx) this layer's data gradient in one kernel.
+        spec: dict(which, clip, d_real, d_fake, grad_target, gscale, losses, dlogit16); x_act: the activation that
+        produced x16 when its derivative belongs to this layer's data gradient (plain FC producer), else ACT_NONE.
+        Returns the fp32 logits; the data gradient is left where bwd(dx_done=True) expects it."""
+        net, h = self.net, self.net.h
+        y32 = net.ws.get((ctx, self.scope, "y32"), rows, self.outp, F32)
+        dx16 = net.ws.get((ctx, self.scope, "dx16"), rows, self.inp, h.h16) if want_dx else None
+        h.fc1_head(x16, rows, self.inp, net.P.view(self.wname, "theta16"), net.P.view(self.bname), spec["which"],
+                   spec["clip"], spec["d_real"], spec["d_fake"], spec["grad_target"], spec["gscale"], spec["losses"], y32,
+                   dlogit16=spec["dlogit16"], dact=x_act, dx16=dx16)
+        return y32
+
     def bwd(self, ctx, x16, dy16, rows, want_dw=True, want_dx=True, prev_y16=None, prev_act=ACT_NONE,
-            resid32=None, want32=False, dw_side=True):
+            resid32=None, want32=False, dw_side=True, dx_done=False):
         """dy16: gradient wrt this layer's PRE-activation.  Returns the gradient wrt the input,
         multiplied by prev_act'(prev_y16) when the producer of x16 was an activated FC.
         dw_side=False keeps the weight gradient on the calling stream (last layer of a backward pass: the side stream
         still holds the previous layer's weight-gradient GEMMs and nothing else is left for the main stream to do)."""
         net, h = self.net, self.net.h
         dx16 = dx32 = None
-        if want_dx:    # the producer layer waits for this: main stream first
+        if want_dx and dx_done:      # the fused head kernel has written it (FC.head)
+            dx16 = net.ws.get((ctx, self.scope, "dx16"), rows, self.inp, h.h16)
+        elif want_dx:    # the producer layer waits for this: main stream first
             dx16 = net.ws.get((ctx, self.scope, "dx16"), rows, self.inp, h.h16)
             dx32 = net.ws.get((ctx, self.scope, "dx32"), rows, self.inp, F32) if want32 else None
             if self.n_out == 1 and resid32 is None and not want32 and self.inp >= 64:
@@ -398,8 +418,9 @@ class LSTMP(object):
 
     def bwd_main(self, ctx, dout16, B, T, lengths, want_dw=True, want_dx=True, prev_y16=None, prev_act=ACT_NONE,
                  resid32=None, want32=False, after_rec=None):
-        """after_rec: called right behind the launch of the recurrence kernel -- the place to enqueue side-stream work
-        that should take the SMs the recurrence leaves free rather than the ones it is about to need."""
+        """after_rec(mark): called just in front of the launch of the recurrence kernel with a mark of that point -- the
+        place to enqueue side-stream work that should take the SMs the recurrence leaves free rather than the ones it is
+        about to need."""
         net, h, P = self.net, self.net.h, self.net.P
         rows, Cp = T * B, self.Cp
         key = (ctx, self.prefix, B)
@@ -408,6 +429,12 @@ class LSTMP(object):
         dmt = net.ws.get((ctx, "dmt", Cp, B), rows, Cp, F32)
         dz = net.ws.get(key + ("dz",), rows + B, 4 * Cp, h.h16)       # per layer: the side stream reads it after we return
         h.fill32(dz[rows:].view(F32), 0.0)                 # dz_{T} = 0 (no step after the last one; T varies per batch)
+        if after_rec is not None:
+            # In a captured graph only dependencies order kernels: side work that became ready a microsecond before this
+            # recurrence (a persistent 148-CTA GEMM) held its cluster slots for the whole GEMM (~22 us).  So the side
+            # stream is made to wait for THIS point and to start with a one-block spacer kernel: the recurrence's CTAs
+            # are placed first, the GEMM takes the SMs it leaves free.
+            after_rec(h.mark())
         if want_dw:
             gb = P.view(self.prefix + "bias", "grad")
             gi, gf, go = (P.view(self.prefix + n, "grad") for n in ("w_i_diag", "w_f_diag", "w_o_diag"))
@@ -417,8 +444,6 @@ class LSTMP(object):
         h.lstmp_rec_bwd(B, T, Cp, dmt, self.wc16, P.view(self.prefix + "w_i_diag"),
                         P.view(self.prefix + "w_f_diag"), P.view(self.prefix + "w_o_diag"), lengths, sv,
                         dz, gb, gi, gf, go, work=self.rec_flops(B, T))
-        if after_rec is not None:
-            after_rec()
         dx16 = dx32 = None
         if want_dx:    # the next (earlier) layer waits for this: main stream, before the weight gradients
             dx16 = net.ws.get(key + ("dx16",), rows, self.Ip, h.h16)
@@ -992,10 +1017,13 @@ class Generator(Net):
             Ls[-2].bwd_pre("g", d16, B, T)
             pending = []
 
-            def flush():
+            def flush(ev=None):
+                if pending and ev is not None:
+                    with self.h.side_stream(after=ev):
+                        self.h.fill32(self.ws.get(("g", "spacer"), 1, 256, F32), 0.0)
                 while pending:
-                    l, a, d, ev = pending.pop(0)
-                    l.bwd_side("g", a, d, B, T, after=ev)
+                    l, a, d, ev0 = pending.pop(0)
+                    l.bwd_side("g", a, d, B, T, after=False if ev is not None else ev0)
             i = len(Ls) - 2
             while i >= 1:
                 dout32 = d32
@@ -1077,9 +1105,13 @@ class Discriminator(Net):
         super(Discriminator, self).__init__(handle, mk, adam=adam)
         self.clip = d_type == "dnn"
         self._ctx = {}
+        self.head_fused = {}
 
-    def fwd(self, ctx, x32_tm, B, T, lengths, noise=None, train=True, cat_src=None):
-        """x32_tm fp32 [T*B, ld] time-major (labels or generator output); noise fp32 (B, in_dim) or None
+    def fwd(self, ctx, x32_tm, B, T, lengths, noise=None, train=True, cat_src=None, head=None):
+        """head: a loss specification for FC.head -- when the last layer qualifies (one-unit head of the plain DNN
+        discriminator with more than one layer below it), logits, LSGAN loss terms, d loss / d logit and the head's data
+        gradient come out of ONE kernel and `self.head_fused[ctx]` is set; otherwise the caller runs rsr_lsgan_mse_losses.
+        x32_tm fp32 [T*B, ld] time-major (labels or generator output); noise fp32 (B, in_dim) or None
         (utils/ops.py:19-30: ONE draw per utterance broadcast over time).  cat_src: the conditioning block of a
         conditioned discriminator, an fp32 batch-major (B, T, cat_dim) VIEW of the generator's input (row pitch = its
         stride).  Returns logits32 [T*B, 8] (column 0; pre-clip for the DNN discriminator)."""
@@ -1108,15 +1140,26 @@ class Discriminator(Net):
             for l in self.layers[:-1]:
                 a, _ = l.fwd(ctx, a, rows)
                 acts.append(a)
-        _, logits = self.layers[-1].fwd(ctx, a, rows, want16=False, want32=True)
+        last = self.layers[-1]
+        fused = (head is not None and self.d_type == "dnn" and len(self.layers) > 1 and last.head_ok()
+                 and os.environ.get("RSR_NO_HEAD_FUSION") != "1")
+        self.head_fused[ctx] = fused
+        if fused:      # (the head always produces its data gradient: every caller of bwd below a fused forward wants it)
+            logits = last.head(ctx, a, rows, head, True, ACT_RELU if not self.fcbn else ACT_NONE)
+        else:
+            _, logits = last.fwd(ctx, a, rows, want16=False, want32=True)
         self._ctx[ctx] = (acts, B, T, lengths)
         return logits
 
-    def bwd(self, ctx, dlogit16, want_dw=True, want_dx=False, resid32=None):
-        """dlogit16 [T*B, 8] (column 0).  want_dx: returns d/d(input) (+ resid32) as 16-bit [T*B, in_pad]."""
+    def bwd(self, ctx, dlogit16, want_dw=True, want_dx=False, resid32=None, pre_last=None):
+        """dlogit16 [T*B, 8] (column 0).  want_dx: returns d/d(input) (+ resid32) as 16-bit [T*B, in_pad].
+        pre_last: called in front of the first layer's backward (the consumer of resid32): where a caller that computed
+        resid32 on the side stream joins it."""
         acts, B, T, lengths = self._ctx[ctx]
         rows, Ls = T * B, self.layers
         if self.d_type == "lstm":
+            if pre_last is not None:
+                pre_last()
             d16, d32 = Ls[-1].bwd(ctx, acts[-1], dlogit16, rows, want_dw=want_dw, want32=want_dw)
             i = len(Ls) - 2
             while i >= 0:
@@ -1146,7 +1189,10 @@ class Discriminator(Net):
         plain = not self.fcbn
         for i in range(len(Ls) - 1, -1, -1):
             last = i == 0
+            kw = dict(dx_done=True) if (i == len(Ls) - 1 and self.head_fused.get(ctx)) else {}
+            if last and pre_last is not None:
+                pre_last()
             d, _ = Ls[i].bwd(ctx, acts[i], d, rows, want_dw=want_dw, want_dx=(not last) or want_dx,
                              prev_y16=None if last or not plain else acts[i], prev_act=ACT_RELU if plain else ACT_NONE,
-                             resid32=resid32 if last else None)
+                             resid32=resid32 if last else None, **kw)
         return d

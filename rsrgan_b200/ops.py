@@ -64,11 +64,14 @@ class Handle(object):
     @contextlib.contextmanager
     def side_stream(self, after=None):
         """Calls made inside run on the side stream, ordered after everything enqueued so far on the
-        current stream (or after the `mark()` passed as `after`); `join()` makes the current stream wait for them."""
+        current stream (or after the `mark()` passed as `after`; `after=False`: no new dependency); `join()` makes the
+        current stream wait for them."""
         if not self.overlap or self.timing is not None:
             yield
             return
-        if after is not None:
+        if after is False:
+            pass                                   # already ordered: continues the side stream's own queue
+        elif after is not None:
             self._side.wait_event(after)
         else:
             self._side.wait_stream(torch.cuda.current_stream())
@@ -368,6 +371,15 @@ class Handle(object):
         self._call("rsr_fc1_bwd_dx", 1, self.h, _stream(), _p(dy16), dy16.stride(0), rows, K, _p(w16), w16.stride(0),
                    _p(dact_src), dact_src.stride(0) if dact_src is not None else 0, dact, _p(dx16), dx16.stride(0),
                    work=2.0 * rows * K)
+
+    def fc1_head(self, x16, rows, K, w16, bias, which, clip, d_real, d_fake, grad_target, gscale, losses, logit32,
+                 dlogit16=None, dact=ACT_NONE, dx16=None):
+        """The discriminator head in one pass (rsr_fc1_head): logits, LSGAN loss terms, d loss / d logit, head data gradient."""
+        self._call("rsr_fc1_head", 1, self.h, _stream(), _p(x16), x16.stride(0), rows, K, _p(w16), w16.stride(0), _p(bias),
+                   int(which), int(clip), float(d_real), float(d_fake), float(grad_target), float(gscale), _p(losses),
+                   _p(logit32), logit32.stride(0) if logit32 is not None else 0,
+                   _p(dlogit16), dlogit16.stride(0) if dlogit16 is not None else 0, dact,
+                   _p(dx16), dx16.stride(0) if dx16 is not None else 0, work=4.0 * rows * K)
 
     # ------------------------------------------------------ gradient all-reduce over peer memory (rsrgan_b200/peer.py)
     PEER_HEADER_BYTES, PEER_IPC_HANDLE_BYTES = 16384, 64

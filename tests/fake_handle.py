@@ -99,6 +99,29 @@ class FakeHandle(object):
             v = v * _dact(dact_src[:rows, :K].float(), dact)
         dx16[:rows, :K] = v.to(self.h16)
 
+    def fc1_head(self, x16, rows, K, w16, bias, which, clip, d_real, d_fake, grad_target, gscale, losses, logit32,
+                 dlogit16=None, dact=ACT_NONE, dx16=None):
+        self.launches += 1
+        u = x16[:rows, :K].float() @ w16[:K, 0].float() + (bias[0] if bias is not None else 0.0)
+        l = torch.clamp(u, -0.5, 1.5) if clip else u
+        m = ((u >= -0.5) & (u <= 1.5)).float() if clip else torch.ones_like(u)
+        if logit32 is not None:
+            logit32[:rows, 0] = u
+        if losses is not None:
+            if which == 0:
+                losses[0] += ((l - d_real) ** 2).mean()
+            else:
+                losses[1] += ((l - d_fake) ** 2).mean()
+                losses[2] += ((l - d_real) ** 2).mean()
+        g16 = (gscale * 2 * (l - (d_real if which == 0 else grad_target)) / rows * m).to(self.h16)
+        if dlogit16 is not None:
+            dlogit16[:rows, 0] = g16
+        if dx16 is not None:
+            v = g16.float().reshape(rows, 1) * w16[:K, 0].float().reshape(1, K)
+            if dact != ACT_NONE:
+                v = v * _dact(x16[:rows, :K].float(), dact)
+            dx16[:rows, :K] = v.to(self.h16)
+
     # ------------------------------------------------------------- 1-D conv glue
     def conv_stage_frames(self, x, B, T, L, S, Cp, out16, mean=None, istd=None, time_major_in=False, ldx=None):
         self.launches += 1

@@ -633,6 +633,52 @@ def test_fc1_forward_and_data_gradient(h, rows, K):
         assert rel(dx.float().cpu().numpy(), r) < tol(h, 5e-4, 4e-3)
 
 
+@pytest.mark.parametrize("rows,K,which,clip", [(12800, 1024, 1, True), (12800, 1024, 0, True), (333, 64, 1, False), (1000, 264, 0, True)])
+def test_fc1_head_equals_the_three_kernels_it_replaces(h, rows, K, which, clip):
+    """rsr_fc1_head == rsr_fc1_fwd -> rsr_lsgan_mse_losses (logit terms) -> rsr_fc1_bwd_dx: same logits, same 16-bit
+    d loss / d logit, same head data gradient (bit for bit), same loss sums; and the losses against the float64 formula."""
+    from rsrgan_b200 import ops
+    dev, rng = h.device, np.random.default_rng(rows + K + which)
+    x16 = torch.tensor(np.maximum(rng.standard_normal((rows, K)), 0).astype(np.float32), device=dev).to(h.h16)
+    w16 = torch.zeros(K, 8, dtype=h.h16, device=dev)
+    w16[:, 0] = torch.tensor((rng.standard_normal(K) * 0.08).astype(np.float32), device=dev).to(h.h16)
+    bias = torch.tensor([0.4] + [0.0] * 7, device=dev)
+    d_real, d_fake, gs = 1.0, 0.0, 4096.0
+    target = d_real if which == 0 else d_fake
+    # the three kernels
+    lg = torch.zeros(rows, 8, device=dev)
+    g16 = torch.zeros(rows, 8, dtype=h.h16, device=dev)
+    dx = torch.zeros(rows, K, dtype=h.h16, device=dev)
+    losses = torch.zeros(8, device=dev)
+    h.fc1_fwd(x16, rows, K, w16, bias, lg)
+    kw = dict(ld_logit=8, n_logit=rows, clip=clip, d_real=d_real, d_fake=d_fake, gscale=gs, ld_grad=8)
+    if which == 0:
+        h.lsgan_mse_losses(losses, rl=lg, d_rl_grad=g16, **kw)
+    else:
+        h.lsgan_mse_losses(losses, fk=lg, d_fk_grad=g16, **kw)
+    h.fc1_bwd_dx(g16, rows, K, w16, dx, dact_src=x16, dact=ops.ACT_RELU)
+    # the fused head
+    lg2 = torch.zeros(rows, 8, device=dev)
+    g2 = torch.zeros(rows, 8, dtype=h.h16, device=dev)
+    dx2 = torch.zeros(rows, K, dtype=h.h16, device=dev)
+    losses2 = torch.zeros(8, device=dev)
+    h.fc1_head(x16, rows, K, w16, bias, which, clip, d_real, d_fake, target, gs, losses2, lg2, dlogit16=g2, dact=ops.ACT_RELU,
+               dx16=dx2)
+    torch.cuda.synchronize()
+    assert rel(lg2[:, 0].cpu().numpy(), lg[:, 0].cpu().numpy()) < 1e-6
+    # (the two dot products sum in a different order: a logit may differ in its last bits, and with it -- rarely -- the
+    #  rounding of its 16-bit gradient)
+    gd = (g2[:, 0].float() - g16[:, 0].float()).abs().cpu().numpy()
+    assert rel(g2[:, 0].float().cpu().numpy(), g16[:, 0].float().cpu().numpy()) < 1e-3 and (gd > 0).mean() < 0.02
+    assert rel(dx2.float().cpu().numpy(), dx.float().cpu().numpy()) < 2e-3
+    u = x16.double().cpu().numpy() @ w16[:, 0].double().cpu().numpy() + 0.4
+    l = np.clip(u, -0.5, 1.5) if clip else u
+    ref = [((l - d_real) ** 2).mean(), 0.0, 0.0] if which == 0 else [0.0, ((l - d_fake) ** 2).mean(), ((l - d_real) ** 2).mean()]
+    got, got3 = losses2.cpu().numpy(), losses.cpu().numpy()
+    for k in range(3):
+        assert got[k] == pytest.approx(ref[k], rel=1e-4, abs=1e-7) and got[k] == pytest.approx(got3[k], rel=1e-5, abs=1e-7)
+
+
 def test_ark_decompress_bit_exact(h):
     """rsr_ark_decompress == the reference's compressed-matrix reader, bit for bit: (i) the `CM` entry of the golden
     archive, whose expected float64 matrix was produced by the REFERENCE's io_funcs/kaldi_io.py (tests/golden/
