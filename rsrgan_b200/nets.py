@@ -444,6 +444,7 @@ class LSTMP(object):
         h.lstmp_rec_bwd(B, T, Cp, dmt, self.wc16, P.view(self.prefix + "w_i_diag"),
                         P.view(self.prefix + "w_f_diag"), P.view(self.prefix + "w_o_diag"), lengths, sv,
                         dz, gb, gi, gf, go, work=self.rec_flops(B, T))
+        self.rec_mark = h.mark()       # dz is complete here: all the weight gradients of this layer need
         dx16 = dx32 = None
         if want_dx:    # the next (earlier) layer waits for this: main stream, before the weight gradients
             dx16 = net.ws.get(key + ("dx16",), rows, self.Ip, h.h16)
@@ -1048,7 +1049,9 @@ class Generator(Net):
                                           prev_act=ACT_LRELU if mask else ACT_NONE, want32=not first, after_rec=flush)
                 if not first:
                     Ls[i - 1].bwd_pre("g", d16, B, T)     # critical path first, then this layer's weight gradients
-                pending.append((Ls[i], acts[i], dout32, self.h.mark()))
+                # (first LSTMP layer: nothing is launched behind it that its weight gradients should yield to -- they start
+                #  as soon as its recurrence is done, beside its data-gradient GEMM)
+                pending.append((Ls[i], acts[i], dout32, Ls[i].rec_mark if first else self.h.mark()))
                 i -= 1
             flush()
             Ls[0].bwd("g", acts[0], d16, rows, want_dx=False, dw_side=False)
