@@ -195,9 +195,13 @@ int rsr_lstmp_wave_fwd(rsr_handle* h, void* stream, const rsr_wave_args* a);
  *                                 resets every element as it reads it)
  * Outputs as two rsr_lstmp_rec_bwd calls: dz2, dz1 (h16 [T*B, 4Cp]) and the bias / peephole gradients (accumulated).
  * The gradient wrt layer 1's OUTPUT (dz2 K_x2^T), which the weight gradients of layer 1 need, stays an rsr_gemm.
- * Returns RSR_E_RESIDENT (nothing launched) when the shape does not apply, as rsr_lstmp_wave_fwd. */
+ * Returns RSR_E_RESIDENT (nothing launched) when the shape does not apply, as rsr_lstmp_wave_fwd.
+ * max_nbp = 32: a caller that hides weight-gradient GEMMs behind the per-layer launches (which leave 84 SMs free) says so
+ * -- the 48-utterance launch (B = 128 at Cp = 512: all 7 placeable clusters) is 19 % faster than the two launches it
+ * replaces but leaves 36 SMs, and the un-hidden GEMMs cost what it gains. */
 typedef struct rsr_wave_bwd_args {
     int B, T, Cp;
+    int max_nbp;                  /* 0: any; 32: decline rather than seat 48 utterances per cluster (see below) */
     const int* lengths;
     const float* dmt2; const void* wc2; const float* w_i2; const float* w_f2; const float* w_o2; const float* save2;
     void* dz2; float* dbias2; float* dw_i2; float* dw_f2; float* dw_o2;

@@ -49,7 +49,7 @@ class WaveArgs(C.Structure):
 
 class WaveBwdArgs(C.Structure):
     """rsr_wave_bwd_args (include/rsrgan_b200.h)."""
-    _fields_ = [("B", ci), ("T", ci), ("Cp", ci),
+    _fields_ = [("B", ci), ("T", ci), ("Cp", ci), ("max_nbp", ci),
                 ("lengths", vp),
                 ("dmt2", vp), ("wc2", vp), ("w_i2", vp), ("w_f2", vp), ("w_o2", vp), ("save2", vp),
                 ("dz2", vp), ("dbias2", vp), ("dw_i2", vp), ("dw_f2", vp), ("dw_o2", vp),

@@ -72,6 +72,21 @@ __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads)
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// 4-byte / 16-byte asynchronous global -> shared copies (LDGSTS): a prefetch that holds no registers.  src_bytes = 0
+// zero-fills the destination without touching the source.
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ float ld_shared_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+
 // named barrier the gate threads ARRIVE at and the poster warp syncs on, step by step: four ids in rotation, so that
 // arrivals of a later step can only collide with an unconsumed earlier one if the poster fell four steps behind
 __device__ __forceinline__ uint32_t post_bar_id(int step) { return 2u + (uint32_t)(step & 3) + ((step & 3) ? 2u : 0u); }   // 2, 5, 6, 7
@@ -721,6 +736,9 @@ __device__ __forceinline__ void pair_bwd_body(const PBwdParams& p, const int grp
     const uint32_t sBar = sR0 + 2u * sR_bytes;
     const uint32_t barM = sBar, full0 = sBar + 8, full1 = sBar + 16, dzr = sBar + 24;
     const uint32_t tslot = sBar + 32;
+    // 48 utterances per cluster: the operands of the next step are prefetched into shared memory, not registers (below)
+    const uint32_t sPre = sBar + 64;                                 // float pre[20][GT] | float4 predm[GT]
+    const uint32_t sPreDm = sPre + 20u * GT * 4u;
     uint8_t* sB_ptr = base_ptr + (sBt - base);
 
     // TMEM: tile mt of the A operand (rows = output cells 256 mt + 128 e + lane, K = the pair's 256 gate columns) at columns
@@ -857,8 +875,15 @@ __device__ __forceinline__ void pair_bwd_body(const PBwdParams& p, const int grp
         };
 
         // saved activations / dmt of step t-1 are loaded one step ahead (see lstmp_bwd_cluster_kernel)
+        // 48 utterances per cluster = 14 warps, four of them on one SM sub-partition, i.e. at most 128 registers per thread
+        // where this loop wants 168: there (SPRE) the one-step-ahead prefetch goes to shared memory with cp.async -- no
+        // registers -- and is picked up at the end of the step, the two output tiles are drained one after the other and
+        // the 16-bit dz values stay packed.
+        constexpr bool SPRE = NBP > 32;
         float s_i[UPT], s_f[UPT], s_o[UPT], s_j[UPT], s_c[UPT], s_cp[UPT], dm[UPT];
-        float n_i[UPT], n_f[UPT], n_o[UPT], n_j[UPT], n_cp[UPT], n_dm[UPT];
+        float n_i[SPRE ? 1 : UPT], n_f[SPRE ? 1 : UPT], n_o[SPRE ? 1 : UPT], n_j[SPRE ? 1 : UPT], n_cp[SPRE ? 1 : UPT],
+              n_dm[SPRE ? 1 : UPT];
+        const uint32_t pre_me = sPre + (uint32_t)tid * 4u, predm_me = sPreDm + (uint32_t)tid * 16u;
         dm_ready(0);
 #pragma unroll
         for (int u = 0; u < UPT; ++u) {
@@ -879,18 +904,39 @@ __device__ __forceinline__ void pair_bwd_body(const PBwdParams& p, const int grp
             const int buf = step & 1;
             PTRACE(tid == 0, step, 0);
             if (t > 0) dm_ready(step + 1);
+            if constexpr (SPRE) {
+                if (t > 0) {
 #pragma unroll
-            for (int u = 0; u < UPT; ++u) {            // operands of step t-1 (and c_{t-2}): in flight during this step
-                const int b = b0 + UPT * uq + u;
-                n_i[u] = n_f[u] = n_o[u] = n_j[u] = n_cp[u] = n_dm[u] = 0.f;
-                if (b < p.B && t > 0) {
-                    const size_t row = (size_t)(t - 1) * p.B + b;
-                    const float* s = p.save + row * 5 * Cp + cell;
-                    n_i[u] = __ldg(s); n_f[u] = __ldg(s + Cp); n_o[u] = __ldg(s + 2 * Cp); n_j[u] = __ldg(s + 3 * Cp);
-                    if (t > 1) n_cp[u] = __ldg(s - (size_t)p.B * 5 * Cp + 4 * Cp);
+                    for (int u = 0; u < UPT; ++u) {        // operands of step t-1 (and c_{t-2}) -> shared memory, asynchronously
+                        const int b = b0 + UPT * uq + u;
+                        const bool ok = b < p.B;
+                        const float* s = p.save + ((size_t)(t - 1) * p.B + (ok ? b : 0)) * 5 * Cp + cell;
+                        const uint32_t d = pre_me + (uint32_t)(5 * u) * (GT * 4u);
+                        cp_async4(d, s, ok ? 4u : 0u);
+                        cp_async4(d + GT * 4u, s + Cp, ok ? 4u : 0u);
+                        cp_async4(d + 2u * GT * 4u, s + 2 * Cp, ok ? 4u : 0u);
+                        cp_async4(d + 3u * GT * 4u, s + 3 * Cp, ok ? 4u : 0u);
+                        cp_async4(d + 4u * GT * 4u, t > 1 ? s - (size_t)p.B * 5 * Cp + 4 * Cp : s, (ok && t > 1) ? 4u : 0u);
+                        if (!p.grouped)
+                            cp_async4(predm_me + 4u * u, p.dmt + ((size_t)(t - 1) * p.B + (ok ? b : 0)) * Cp + cell, ok ? 4u : 0u);
+                    }
+                    if (p.grouped)
+                        cp_async16_cg(predm_me, p.dmt + ((((size_t)(t - 1) * p.groups + grp) * Cp + cell) * NBP + e * NBR + UPT * uq));
                 }
+            } else {
+#pragma unroll
+                for (int u = 0; u < UPT; ++u) {            // operands of step t-1 (and c_{t-2}): in flight during this step
+                    const int b = b0 + UPT * uq + u;
+                    n_i[u] = n_f[u] = n_o[u] = n_j[u] = n_cp[u] = n_dm[u] = 0.f;
+                    if (b < p.B && t > 0) {
+                        const size_t row = (size_t)(t - 1) * p.B + b;
+                        const float* s = p.save + row * 5 * Cp + cell;
+                        n_i[u] = __ldg(s); n_f[u] = __ldg(s + Cp); n_o[u] = __ldg(s + 2 * Cp); n_j[u] = __ldg(s + 3 * Cp);
+                        if (t > 1) n_cp[u] = __ldg(s - (size_t)p.B * 5 * Cp + 4 * Cp);
+                    }
+                }
+                if (t > 0) load_dm4(t - 1, n_dm);
             }
-            if (t > 0) load_dm4(t - 1, n_dm);
             if (step > 0) {
                 const uint32_t fb = buf ? full1 : full0;
                 mbar_wait(fb, (uint32_t)(((step - 1) >> 1) & 1));   // partial rows of dz_{t+1} Wc^T from all NP pairs
@@ -918,7 +964,12 @@ __device__ __forceinline__ void pair_bwd_body(const PBwdParams& p, const int grp
                 if (tid == 0 && step + 2 < p.T) mbar_expect_tx(fb, sR_bytes);   // re-arm for step + 2
             }
             PTRACE(tid == 0, step, 2);
-            uint16_t hz[UPT][4];
+            // dz of (utterance, gate): 16-bit values, one per register -- or (SPRE) packed in pairs (i, j), (f, o)
+            uint32_t hz[UPT][SPRE ? 2 : 4];
+            auto hz_get = [&](int u, int g) -> uint16_t {
+                if constexpr (SPRE) return (uint16_t)((g & 1) ? (hz[u][g >> 1] >> 16) : (hz[u][g >> 1] & 0xFFFFu));
+                else return (uint16_t)hz[u][g];
+            };
 #pragma unroll
             for (int u = 0; u < UPT; ++u) {
                 const int b = b0 + UPT * uq + u;
@@ -933,7 +984,8 @@ __device__ __forceinline__ void pair_bwd_body(const PBwdParams& p, const int grp
                 dcar[u] = m * (dc * s_f[u] + dz_f * wf + dz_i * wi);
                 a_dwo += dz_o * s_c[u]; a_dwf += dz_f * s_cp[u]; a_dwi += dz_i * s_cp[u];
                 a_db[0] += dz_i; a_db[1] += dz_j; a_db[2] += dz_f; a_db[3] += dz_o;
-                hz[u][0] = f2h(dz_i, BF); hz[u][1] = f2h(dz_j, BF); hz[u][2] = f2h(dz_f, BF); hz[u][3] = f2h(dz_o, BF);
+                if constexpr (SPRE) { hz[u][0] = pack2(dz_i, dz_j, BF); hz[u][1] = pack2(dz_f, dz_o, BF); }
+                else { hz[u][0] = f2h(dz_i, BF); hz[u][1] = f2h(dz_j, BF); hz[u][2] = f2h(dz_f, BF); hz[u][3] = f2h(dz_o, BF); }
             }
             PTRACE(tid == 0, step, 3);
             if (t > 0) {
@@ -941,10 +993,10 @@ __device__ __forceinline__ void pair_bwd_body(const PBwdParams& p, const int grp
 #pragma unroll
                 for (int u = 0; u < UPT; ++u) {
                     const int n = UPT * uq + u;
-                    *reinterpret_cast<uint16_t*>(sB_ptr + zoff + sw128_off(n, cl)) = hz[u][0];                        // g = 0
-                    *reinterpret_cast<uint16_t*>(sB_ptr + zoff + sw128_off(n, 32 + cl)) = hz[u][1];                   // g = 1
-                    *reinterpret_cast<uint16_t*>(sB_ptr + zoff + NBR * 128 + sw128_off(n, cl)) = hz[u][2];            // g = 2
-                    *reinterpret_cast<uint16_t*>(sB_ptr + zoff + NBR * 128 + sw128_off(n, 32 + cl)) = hz[u][3];       // g = 3
+                    *reinterpret_cast<uint16_t*>(sB_ptr + zoff + sw128_off(n, cl)) = hz_get(u, 0);
+                    *reinterpret_cast<uint16_t*>(sB_ptr + zoff + sw128_off(n, 32 + cl)) = hz_get(u, 1);
+                    *reinterpret_cast<uint16_t*>(sB_ptr + zoff + NBR * 128 + sw128_off(n, cl)) = hz_get(u, 2);
+                    *reinterpret_cast<uint16_t*>(sB_ptr + zoff + NBR * 128 + sw128_off(n, 32 + cl)) = hz_get(u, 3);
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1, GT);
@@ -957,7 +1009,7 @@ __device__ __forceinline__ void pair_bwd_body(const PBwdParams& p, const int grp
                 const int b = b0 + UPT * uq + u;
                 if (b < p.B) {
                     uint16_t* d = dzg + ((size_t)t * p.B + b) * 4 * Cp;
-                    d[0] = hz[u][0]; d[32] = hz[u][1]; d[64] = hz[u][2]; d[96] = hz[u][3];
+                    d[0] = hz_get(u, 0); d[32] = hz_get(u, 1); d[64] = hz_get(u, 2); d[96] = hz_get(u, 3);
                 }
             }
             if (p.post) named_bar_arrive(post_bar_id(step), GT + 32);
@@ -967,17 +1019,23 @@ __device__ __forceinline__ void pair_bwd_body(const PBwdParams& p, const int grp
             PTRACE(tid == 0, step, 6);
             const uint32_t dst0 = sR0 + (uint32_t)(buf ^ 1) * sR_bytes;
             const uint32_t dbar = buf ? full0 : full1;
-            uint32_t acc[2][16];                   // both tiles in flight, one wait
+            uint32_t acc[SPRE ? 1 : 2][16];        // both tiles in flight, one wait (SPRE: one after the other)
+            if constexpr (!SPRE) {
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-                if (mt < MT2) tmem_ld16_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * ACCS + piece * 16), acc[mt]);
-            tmem_ld_wait();
+                for (int mt = 0; mt < 2; ++mt)
+                    if (mt < MT2) tmem_ld16_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * ACCS + piece * 16), acc[mt]);
+                tmem_ld_wait();
+            }
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
                 if (mt < MT2) {
+                    if constexpr (SPRE) {
+                        tmem_ld16_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * ACCS + piece * 16), acc[0]);
+                        tmem_ld_wait();
+                    }
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
-                        const uint32_t* a = acc[mt] + 8 * c;
+                        const uint32_t* a = acc[SPRE ? 0 : mt] + 8 * c;
                         st_async_v4(dst0 + soff[c] + rd[mt][c],
                                     pack2(__uint_as_float(a[0]), __uint_as_float(a[1]), BF),
                                     pack2(__uint_as_float(a[2]), __uint_as_float(a[3]), BF),
@@ -987,10 +1045,26 @@ __device__ __forceinline__ void pair_bwd_body(const PBwdParams& p, const int grp
                 }
             }
             tc_fence_before();
+            if constexpr (SPRE) {
+                cp_async_wait_all();                   // (each thread reads only what it copied itself)
 #pragma unroll
-            for (int u = 0; u < UPT; ++u) {
-                s_c[u] = s_cp[u]; s_cp[u] = n_cp[u];
-                s_i[u] = n_i[u]; s_f[u] = n_f[u]; s_o[u] = n_o[u]; s_j[u] = n_j[u]; dm[u] = n_dm[u];
+                for (int u = 0; u < UPT; ++u) {
+                    const uint32_t d = pre_me + (uint32_t)(5 * u) * (GT * 4u);
+                    s_c[u] = s_cp[u];
+                    s_i[u] = ld_shared_f32(d); s_f[u] = ld_shared_f32(d + GT * 4u); s_o[u] = ld_shared_f32(d + 2u * GT * 4u);
+                    s_j[u] = ld_shared_f32(d + 3u * GT * 4u); s_cp[u] = ld_shared_f32(d + 4u * GT * 4u);
+                    dm[u] = ld_shared_f32(predm_me + 4u * u);
+                }
+                if (p.grouped)
+                    __stcg(reinterpret_cast<float4*>(const_cast<float*>(p.dmt)) +
+                               ((((size_t)(t - 1) * p.groups + grp) * Cp + cell) * NBP + e * NBR + UPT * uq) / 4,
+                           make_float4(0.f, 0.f, 0.f, 0.f));
+            } else {
+#pragma unroll
+                for (int u = 0; u < UPT; ++u) {
+                    s_c[u] = s_cp[u]; s_cp[u] = n_cp[u];
+                    s_i[u] = n_i[u]; s_f[u] = n_f[u]; s_o[u] = n_o[u]; s_j[u] = n_j[u]; dm[u] = n_dm[u];
+                }
             }
             PTRACE(tid == 0, step, 7);
         }
@@ -1192,7 +1266,9 @@ lstmp_wave_bwd_kernel(const __grid_constant__ CUtensorMap tmZ, const PBwdParams 
 }
 
 size_t pbwd_smem(int Cp, int nbp) {
-    const size_t need = 1024 + 4 * (size_t)(nbp / 2) * 128 + 2 * (size_t)(Cp / 64) * (nbp / 2) * 128 + 64;
+    const size_t gt = 16 * (size_t)(nbp / 2);       // gate threads
+    const size_t need = 1024 + 4 * (size_t)(nbp / 2) * 128 + 2 * (size_t)(Cp / 64) * (nbp / 2) * 128 + 64 +
+                        (nbp > 32 ? 20 * gt * 4 + gt * 16 : 0);
     return need < RSR_EXCLUSIVE_SMEM_REC ? RSR_EXCLUSIVE_SMEM_REC : need;
 }
 
@@ -1300,17 +1376,20 @@ extern "C" int rsr_lstmp_wave_bwd(rsr_handle* h, void* stream, const rsr_wave_bw
         if (fast) return bf ? run(lstmp_wave_bwd_kernel<NBP, 1, 1>, nbp_tag) : run(lstmp_wave_bwd_kernel<NBP, 0, 1>, nbp_tag);
         return bf ? run(lstmp_wave_bwd_kernel<NBP, 1, 0>, nbp_tag) : run(lstmp_wave_bwd_kernel<NBP, 0, 0>, nbp_tag);
     };
-    // 32 utterances per cluster only.  The 48-utterance variant (RSR_WAVE_NBP=48, kept for experiments) has 14 warps, i.e.
-    // four on one SM sub-partition and at most 128 registers per thread: the gate math spills and a step takes 5.9 us
-    // against 2.7 -- slower than the two launches one after the other (profiles/r2_wave_steps_v5.txt,
-    // r2_wave_trace_bwd_v0.txt).  Tried on top of it, both worse: moving registers from an auxiliary warpgroup to the gate
-    // warpgroups with setmaxnreg (ptxas kept allocating for 128 and spilled 2.4 KB per thread); dropping the one-step-ahead
-    // operand prefetch to fit 128 registers (8.5 us per step: the saved activations stream from HBM, their latency does
-    // not hide behind the wait for the partial rows, profiles/r2_wave_steps_v6.txt).  So a batch of more than 96
-    // utterances at Cp = 512 (7 clusters placeable: 3 + 3 + 1) declines here.
+    // 32 utterances per cluster when the batch seats that way (2.7 us per step), else 48 (3.9 us; B = 128 at Cp = 512: the 7
+    // placeable clusters are 3 + 3 + 1).  The 48-utterance variant has 14 warps, i.e. four on one SM sub-partition and at
+    // most 128 registers per thread where the gate-backward loop wants 168: with the operand prefetch in registers it
+    // spilled and took 5.9 us per step, slower than the two launches one after the other (2 x 2.4 + two GEMMs;
+    // profiles/r2_wave_steps_v5.txt, r2_wave_trace_bwd_v0.txt).  Tried and worse: setmaxnreg (ptxas kept allocating for 128
+    // and spilled 2.4 KB per thread); no prefetch at all (8.5 us: the saved activations stream from HBM, their latency does
+    // not hide behind the wait for the partial rows, r2_wave_steps_v6.txt).  What works is the prefetch through shared
+    // memory with cp.async (no registers), tiles drained one after the other, packed dz: r2_wave_steps_v7.txt.
     const int force = getenv("RSR_WAVE_NBP") ? atoi(getenv("RSR_WAVE_NBP")) : 0;
-    if (force == 48) return pick(std::integral_constant<int, 48>());
-    return pick(std::integral_constant<int, 32>());
+    if (force != 48) {
+        const int rc = pick(std::integral_constant<int, 32>());
+        if (rc != RSR_E_RESIDENT || force == 32 || (a->max_nbp > 0 && a->max_nbp < 48)) return rc;
+    }
+    return pick(std::integral_constant<int, 48>());
 }
 
 // debug: copies the phase-timing trace of the pair kernels (all zeros unless built with -DRSR_TRACE) to the host

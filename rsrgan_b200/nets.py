@@ -379,7 +379,11 @@ class LSTMP(object):
         g1, g2 = (self._rec_grads(), upper._rec_grads()) if want_dw else (sink(self), sink(upper))
         if not h.lstmp_wave_bwd(B, T, Cp, lengths, dmt2, (upper.wc16,) + upper._peep(), sv2, dz2, g2,
                                 self.fT16, part, (self.wc16,) + self._peep(), sv1, dz1, g1,
-                                work=self.rec_flops(B, T) + upper.rec_flops(B, T)):
+                                work=self.rec_flops(B, T) + upper.rec_flops(B, T),
+                                # weight gradients that hide behind the per-layer launches on the side stream: only the
+                                # 32-utterance launch pays (cfg-2, B = 128: 3.089 ms per schedule with the 48-utterance
+                                # launch against 3.057 without)
+                                max_nbp=32 if (want_dw and getattr(h, "overlap", False)) else 0):
             self.wave_declined.add(("b", B))
             return None
         dx16 = dx32 = None

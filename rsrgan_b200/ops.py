@@ -231,12 +231,13 @@ class Handle(object):
         self.launches += 1
         return True
 
-    def lstmp_wave_bwd(self, B, T, Cp, lengths, dmt2, l2, save2, dz2, g2, fT, part, l1, save1, dz1, g1, work=0.0):
+    def lstmp_wave_bwd(self, B, T, Cp, lengths, dmt2, l2, save2, dz2, g2, fT, part, l1, save1, dz1, g1, work=0.0,
+                       max_nbp=0):
         """Backward of two stacked LSTMP layers as one wavefront launch (rsr_lstmp_wave_bwd).  l = (wc, w_i, w_f, w_o),
         g = (dbias, dw_i, dw_f, dw_o) per layer; part fp32 [T*(B+48), Cp], all zeros (and all zeros again afterwards).  Returns
         False when the shape does not apply."""
         a = WaveBwdArgs()
-        a.B, a.T, a.Cp, a.lengths = B, T, Cp, _p(lengths)
+        a.B, a.T, a.Cp, a.max_nbp, a.lengths = B, T, Cp, int(max_nbp), _p(lengths)
         a.dmt2, a.save2, a.dz2 = _p(dmt2), _p(save2), _p(dz2)
         a.wc2, a.w_i2, a.w_f2, a.w_o2 = (_p(t) for t in l2)
         a.dbias2, a.dw_i2, a.dw_f2, a.dw_o2 = (_p(t) for t in g2)

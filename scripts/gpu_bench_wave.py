@@ -33,8 +33,8 @@ def timeit(fn, n=10):
 
 
 print("%5s %5s %5s %5s | %10s %8s | %10s %8s | %s" % ("B", "T", "Cp", "nbp", "serial us", "us/step", "wave us", "us/step", "ok"))
-for (B, T, I, Cp, P, nbp) in [(128, 100, 256, 512, 256, 0), (96, 100, 256, 512, 256, 32), (96, 100, 256, 512, 256, 48),
-                              (64, 100, 256, 512, 256, 32), (128, 200, 256, 512, 256, 0), (64, 100, 40, 256, 40, 0)]:
+for (B, T, I, Cp, P, nbp) in [(128, 100, 256, 512, 256, 48), (96, 100, 256, 512, 256, 32), (96, 100, 256, 512, 256, 48),
+                              (64, 100, 256, 512, 256, 32), (128, 200, 256, 512, 256, 48), (64, 100, 40, 256, 40, 0)]:
     if nbp:
         os.environ["RSR_WAVE_NBP"] = str(nbp)
     else:
