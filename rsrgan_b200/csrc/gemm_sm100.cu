@@ -228,6 +228,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
 // iteration with BOTH tcgen05.ld in flight before a single wait, the bias as uniform 16-byte loads (no shuffles), one
 // proxy fence and one TMA store per span -- half the fixed per-chunk cost of the general path below, which was the
 // pacing stage of these GEMMs (ncu: epilogue warps busy 2/3 of the kernel, tensor pipe 41 %).
+// (Measured and not kept: loading the activation-gradient source of a warp's first span before it waits for the
+//  accumulator, and the next span's while the current one is drained -- 32 more live registers at the 168-register cap of
+//  this 320-thread kernel: 180 instead of 44 bytes of spills in EVERY instance, cfg-2 3.101 against 3.057 ms per schedule.)
 template <bool HAS_D>
 __device__ __forceinline__ void epilogue_fast16(const GemmKParams& p, const CUtensorMap* tmC16, uint32_t taddr, int row0,
                                                 int n0, int lane, int ew, uint32_t st16, bool leader) {
