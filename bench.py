@@ -304,7 +304,7 @@ def main():
         ach = work / (tms * 1e-3) / 1e12 if tms > 0 else 0.0
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": sus, "unit": "TFLOP/s",
                 "frac": ach / sus, "traffic": ncu_traffic(name),
-                "traffic_source": "profiles/" + NCU_SUMMARY[name] + " (ncu --set full, mean over captured launches)"
+                "traffic_source": "profiles/" + NCU_SUMMARY[name] + " (ncu capture of one schedule, mean over the captured launches)"
                 if name in NCU_SUMMARY else None,
                 "peak_source": how + " (bf16 sustained; fp16 runs at the same rate)",
                 "launches_per_step": cnt / nprof, "avg_launch_ms": tms / cnt, "share_of_step": tms / tot,
