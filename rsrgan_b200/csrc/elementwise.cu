@@ -1065,7 +1065,7 @@ extern "C" int rsr_fc1_head(rsr_handle* h, void* stream, const void* x16, int ld
     p.which = which; p.clip = clip; p.d_real = d_real; p.d_fake = d_fake; p.grad_target = grad_target; p.gscale = gscale;
     p.losses = losses; p.logit = logit32; p.ldl = ldl; p.dlogit = (uint16_t*)dlogit16; p.ldg = ldg;
     p.dact = dact; p.dx = (uint16_t*)dx16; p.ldo = ldo; p.bf = h->dtype == RSR_DTYPE_BF16;
-    fc1_head_kernel<<<grid_for(rows * 32, 256, h->num_sms, 2), 256, (size_t)K * 4, (cudaStream_t)stream>>>(p);
+    fc1_head_kernel<<<grid_for(rows * 32, 256, h->num_sms, 8), 256, (size_t)K * 4, (cudaStream_t)stream>>>(p);
     RSR_LAUNCH_CHECK();
     return 0;
 }
