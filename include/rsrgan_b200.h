@@ -68,6 +68,11 @@ typedef struct rsr_gemm_args {
     int tile_n;                   /* 0 = auto */
     int split_k;                  /* 0 = auto; > 1 only for "out32 += alpha A B" (beta = 1, no other epilogue term):
                                      partial sums are added into out32 with fp32 atomics */
+    float* stats;                 /* NULL, or batch_norm statistics out of the epilogue (models/dnn.py:56-62,
+                                     models/discriminator_dnn.py:36-46): for every block of 128 output rows and every
+                                     column the (count, mean, M2) of out32, laid out [ceil(M / 128)][3][N] -- the partials
+                                     rsr_bn_train_finish merges.  Only for a plain fp32 output (no bias / activation /
+                                     16-bit copy, alpha = 1, beta = 0), N a multiple of 32, M <= 32768; else RSR_E_SHAPE */
 } rsr_gemm_args;
 int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a);
 
@@ -392,6 +397,11 @@ int rsr_vbn_bwd(rsr_handle* h, void* stream, const void* da16, int ldda, const f
 int rsr_bn_train_stats(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,
                        const float* gamma, const float* beta, float eps, float* state, float momentum,
                        float renorm_momentum, int update_state, float* coef, float* scratch);
+/* rsr_bn_train_stats without its first pass: `scratch` already holds `splits` row-block partials [split][3][N] of
+ * (count, mean, M2), written by the epilogue of the rsr_gemm that produced z (rsr_gemm_args.stats) */
+int rsr_bn_train_finish(rsr_handle* h, void* stream, int splits, long long rows, int N, const float* gamma,
+                        const float* beta, float eps, float* state, float momentum, float renorm_momentum,
+                        int update_state, float* coef, const float* scratch);
 int rsr_bn_eval_coef(rsr_handle* h, void* stream, int N, const float* gamma, const float* beta, float eps,
                      const float* state, float* coef);
 int rsr_affine_act_drop(rsr_handle* h, void* stream, const float* z, int ldz, long long rows, int N,

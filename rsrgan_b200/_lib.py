@@ -31,7 +31,8 @@ class GemmArgs(C.Structure):
                 ("dact_src", vp), ("ldd", ci), ("dact", ci),
                 ("out32", vp), ("ldc32", ci),
                 ("out16", vp), ("ldc16", ci),
-                ("tile_n", ci), ("split_k", ci)]
+                ("tile_n", ci), ("split_k", ci),
+                ("stats", vp)]
 
 
 class WaveArgs(C.Structure):
@@ -108,6 +109,7 @@ SIGNATURES = {
     "rsr_vbn_stats": [vp, vp, vp, ci, cll, ci, vp, vp, cf, cf, vp, vp, vp, vp],
     "rsr_vbn_bwd": [vp, vp, vp, ci, vp, ci, cll, ci, ci, cf, vp, vp, vp, vp, ci, vp, ci, vp],
     "rsr_bn_train_stats": [vp, vp, vp, ci, cll, ci, vp, vp, cf, vp, cf, cf, ci, vp, vp],
+    "rsr_bn_train_finish": [vp, vp, ci, cll, ci, vp, vp, cf, vp, cf, cf, ci, vp, vp],
     "rsr_bn_eval_coef": [vp, vp, ci, vp, vp, cf, vp, vp],
     "rsr_bn_train_stats_lines": [vp, vp, vp, ci, cll, ci, ci, ci, ci, ci, vp, vp, cf, vp, ci, cf, cf, ci, vp, vp],
     "rsr_bn_eval_coef_lines": [vp, vp, ci, ci, ci, vp, vp, cf, vp, ci, vp],

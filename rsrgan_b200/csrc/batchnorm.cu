@@ -617,6 +617,17 @@ extern "C" int rsr_bn_train_stats(rsr_handle* h, void* stream, const float* z, i
     return 0;
 }
 
+extern "C" int rsr_bn_train_finish(rsr_handle* h, void* stream, int splits, long long rows, int N, const float* gamma,
+                                   const float* beta, float eps, float* state, float momentum, float renorm_momentum,
+                                   int update_state, float* coef, const float* scratch) {
+    if (!h || !gamma || !beta || !state || !coef || !scratch || rows <= 0 || N <= 0) return RSR_E_ARG;
+    if ((N & 3) || splits <= 0 || splits > BN_MAX_SPLITS) return RSR_E_SHAPE;
+    bn_finish_train_kernel<<<(N + FIN_COLS - 1) / FIN_COLS, dim3(FIN_COLS, FIN_LANES), 0, (cudaStream_t)stream>>>(
+        scratch, splits, rows, N, gamma, beta, eps, state, momentum, renorm_momentum, update_state, coef);
+    RSR_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int rsr_bn_eval_coef(rsr_handle* h, void* stream, int N, const float* gamma, const float* beta, float eps,
                                 const float* state, float* coef) {
     if (!h || !gamma || !beta || !state || !coef || N <= 0) return RSR_E_ARG;

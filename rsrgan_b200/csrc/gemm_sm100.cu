@@ -47,6 +47,7 @@ struct GemmKParams {
     uint16_t* out16; int ldc16;
     int has32, has16;
     int fast16;               // 16-bit-only output in 64-column boxes, no residual / alpha: epilogue_fast16
+    float* stats;             // STATS instances: per 128-row block (count, mean, M2) of every output column, [block][3][N]
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -69,9 +70,15 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
 // Epilogue of ONE 128 x bn accumulator tile, executed by one epilogue warp: thread <-> accumulator row
 // (TMEM lane), 32 columns per tcgen05.ld; bias / residual / activation / activation-gradient in registers;
 // results go through a swizzled per-warp staging box and leave with one TMA store (or reduce-add) per box.
+// STATS (batch_norm statistics in the epilogue, models/dnn.py:56-62, models/discriminator_dnn.py:36-46): the fp32 chunk that
+// is about to leave through the staging box is read back column-wise -- lane <-> column, 32 conflict-free shared loads --
+// and its (mean, M2) over the live rows of this warp's 32-row quadrant go to sstat[quadrant][column]; the kernel merges the
+// four quadrants of a tile in a fixed order (Chan) and writes one (count, mean, M2) partial per 128-row block and column,
+// the layout rsr_bn_train_stats' finish kernel merges -- so the statistics kernel never re-reads the pre-activation.
+template <bool STATS>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtensorMap* tmC32, const CUtensorMap* tmC16,
                                               uint32_t taddr, int row0, int n0, int lane, int ew, uint32_t st32,
-                                              uint32_t st16, bool leader) {
+                                              uint32_t st16, bool leader, uint32_t sstat) {
     const int span = (p.has16 && p.w16 == 64) ? 64 : 32;   // the two warps of a quadrant interleave column spans
     const uint32_t sw32 = (uint32_t)(lane & 7), sw16 = (uint32_t)((lane >> 1) & 3);
     const bool general_beta = p.has32 && !p.reduce32 && p.beta != 0.0f;
@@ -215,6 +222,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
             }
             tma_commit_group();
         }
+        if constexpr (STATS) {
+            int live = p.M - row0;
+            live = live < 0 ? 0 : (live > 32 ? 32 : live);
+            float sh = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                float x;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x)
+                             : "r"(st32 + (uint32_t)r * 128u + ((((uint32_t)(lane >> 2)) ^ (uint32_t)(r & 7)) << 4) + (uint32_t)(lane & 3) * 4u));
+                if (r == 0) sh = x;
+                if (r < live) { const float d = x - sh; a0 += d; a1 = fmaf(d, d, a1); }
+            }
+            float mean = 0.f, m2 = 0.f;
+            if (live > 0) {
+                const float inv = 1.0f / (float)live;
+                mean = sh + a0 * inv;
+                m2 = fmaxf(a1 - a0 * a0 * inv, 0.0f);
+            }
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sstat + (uint32_t)(c0 + lane) * 8u), "f"(mean), "f"(m2) : "memory");
+        }
       }
       if (wrote16 && p.w16 == 64 && leader && row0 < p.M) {   // one 64-column (128-byte rows) box per span
           tma_store_2d(tmC16, st16, n0 + s0, row0);
@@ -317,6 +344,26 @@ __device__ __forceinline__ void epilogue_fast16(const GemmKParams& p, const CUte
     }
 }
 
+// STATS: column `col` (< bn) of a finished tile -- the four quadrants' (mean, M2) merged in a fixed order
+__device__ __forceinline__ void stats_merge_tile(const GemmKParams& p, uint32_t sstat_tile, int m0, int n0, int col) {
+    if (col >= p.bn || n0 + col >= p.N) return;
+    float na = 0.f, ma = 0.f, qa = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int live = p.M - (m0 + 32 * q);
+        live = live < 0 ? 0 : (live > 32 ? 32 : live);
+        if (live == 0) continue;
+        float mb, qb;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(mb), "=f"(qb) : "r"(sstat_tile + (uint32_t)(q * p.bn + col) * 8u));
+        const float nb = (float)live, nab = na + nb, d = mb - ma;
+        ma += d * (nb / nab);
+        qa += qb + d * d * (na * nb / nab);
+        na = nab;
+    }
+    float* o = p.stats + (size_t)(m0 / BM) * 3 * p.N + n0 + col;
+    o[0] = na; o[p.N] = ma; o[2 * (size_t)p.N] = qa;
+}
+
 // Persistent, warp-specialised GEMM.  Each CTA (one per SM) walks tiles tile = blockIdx.x + i*gridDim.x of
 // the (k-split, m, n) tile space.  Three pipelines run concurrently: TMA -> smem ring (full/empty
 // mbarriers), tcgen05.mma -> double-buffered TMEM accumulator (tfull/tempty), and the epilogue warps,
@@ -326,6 +373,7 @@ __device__ __forceinline__ void epilogue_fast16(const GemmKParams& p, const CUte
 // swizzled per-warp staging box and leave with ONE TMA store per box (cp.async.bulk.tensor, or
 // cp.reduce...add for accumulated fp32 outputs), so HBM sees full 128-byte lines and the M / N edges are
 // clipped by the tensor map.
+template <bool STATS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC32, const __grid_constant__ CUtensorMap tmC16,
@@ -345,6 +393,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     auto tfull_bar = [&](int a) { return bars + 16u * p.stages + 8u * a; };
     auto tempty_bar = [&](int a) { return bars + 16u * p.stages + 16u + 8u * a; };
     const uint32_t tmem_slot = bars + 16u * p.stages + 32u;
+    const uint32_t sstat0 = (tmem_slot + 16u + 15u) & ~15u;           // STATS: float2 [2 accumulators][4 quadrants][bn]
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -452,11 +501,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (p.dsrc) epilogue_fast16<true>(p, &tmC16, taddr, row0, n0, lane, ew, st16, leader);
                 else epilogue_fast16<false>(p, &tmC16, taddr, row0, n0, lane, ew, st16, leader);
             } else {
-                epilogue_tile(p, &tmC32, &tmC16, taddr, row0, n0, lane, ew, st32, st16, leader);
+                epilogue_tile<STATS>(p, &tmC32, &tmC16, taddr, row0, n0, lane, ew, st32, st16, leader,
+                                     sstat0 + (uint32_t)((acc * 4 + q) * p.bn) * 8u);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));       // accumulator may be overwritten
+            if constexpr (STATS) {      // all eight epilogue warps have written their quadrant / column spans of this tile
+                named_bar_sync(1u, 32 * EPI_WARPS);
+                stats_merge_tile(p, sstat0 + (uint32_t)(acc * 4 * p.bn) * 8u, m0, n0, ew * 32 + lane);
+            }
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
         if (leader) tma_wait_group<0>();                    // stores complete before the CTA retires
@@ -474,6 +528,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // the one-CTA kernel on the large products (L2 -> SM operand bandwidth).  Barriers: TMA loads of both CTAs
 // complete on the LEADER's full barrier; the leader's commits are multicast to both CTAs' empty / tfull
 // barriers; both CTAs' epilogue warps arrive on the leader's tempty barrier.
+template <bool STATS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC32, const __grid_constant__ CUtensorMap tmC16,
@@ -496,6 +551,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     auto tfull_bar = [&](int a) { return bars + 16u * p.stages + 8u * a; };
     auto tempty_bar = [&](int a) { return bars + 16u * p.stages + 16u + 8u * a; };
     const uint32_t tmem_slot = bars + 16u * p.stages + 32u;
+    const uint32_t sstat0 = (tmem_slot + 16u + 15u) & ~15u;           // STATS: float2 [2 accumulators][4 quadrants][bn]
     const uint32_t to_leader = mapa_u32(smem_base, 0u) - smem_base;  // shared::cta -> shared::cluster address in the leader
 
     if (threadIdx.x == 0) {
@@ -605,11 +661,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (p.dsrc) epilogue_fast16<true>(p, &tmC16, taddr, m0 + q * 32, n0, lane, ew, st16, leader);
                 else epilogue_fast16<false>(p, &tmC16, taddr, m0 + q * 32, n0, lane, ew, st16, leader);
             } else {
-                epilogue_tile(p, &tmC32, &tmC16, taddr, m0 + q * 32, n0, lane, ew, st32, st16, leader);
+                epilogue_tile<STATS>(p, &tmC32, &tmC16, taddr, m0 + q * 32, n0, lane, ew, st32, st16, leader,
+                                     sstat0 + (uint32_t)((acc * 4 + q) * p.bn) * 8u);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) + to_leader);
+            if constexpr (STATS) {
+                named_bar_sync(1u, 32 * EPI_WARPS);
+                stats_merge_tile(p, sstat0 + (uint32_t)(acc * 4 * p.bn) * 8u, m0, n0, ew * 32 + lane);
+            }
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
         if (leader) tma_wait_group<0>();
@@ -721,7 +782,7 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     //  cluster barriers cost more than the saved operand traffic)
     if (a->tile_n <= 0 && bn2 && a->M >= 512 && a->K >= 512 && 2.0 * a->M * a->N * a->K >= 1.0e10 && !getenv("RSR_NO_2CTA")) {
         if (h->gemm2_pairs < 0) {   // co-resident CTA pairs, queried once
-            cudaFuncSetAttribute(gemm2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+            cudaFuncSetAttribute(gemm2_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(2, 1, 1); cfg.blockDim = dim3(GEMM_THREADS, 1, 1); cfg.dynamicSmemBytes = h->max_smem;
             cudaLaunchAttribute at[1];
@@ -729,7 +790,7 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, gemm2_tcgen05_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+            if (cudaOccupancyMaxActiveClusters(&n, gemm2_tcgen05_kernel<false>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
             h->gemm2_pairs = n;
         }
         const long long pair_tiles = (long long)((a->M + 2 * BM - 1) / (2 * BM)) * (a->N / bn2);
@@ -753,6 +814,12 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     p.dsrc = (const uint16_t*)a->dact_src; p.ldd = a->ldd; p.dact = a->dact;
     p.out32 = a->out32; p.ldc32 = a->ldc32; p.out16 = (uint16_t*)a->out16; p.ldc16 = a->ldc16;
     p.has32 = a->out32 ? 1 : 0; p.has16 = a->out16 ? 1 : 0;
+    p.stats = a->stats;
+    // statistics in the epilogue: plain fp32 pre-activation output, whole 32-column chunks, at most 256 row blocks (the
+    // partial buffer of rsr_bn_train_stats); anything else -> RSR_E_SHAPE, the caller runs the statistics kernel instead
+    if (a->stats && (!a->out32 || a->out16 || a->bias || a->resid || a->act != RSR_ACT_NONE || a->dact_src || a->beta != 0.0f ||
+                     a->alpha != 1.0f || (a->N & 31) || (a->M + BM - 1) / BM > 256 || a->split_k > 1))
+        return RSR_E_SHAPE;
     p.st_stride = (p.has32 ? 4096 : 0) + (p.has16 ? 4096 : 0);
     p.m_tiles = m_tiles;
     p.n_tiles = (a->N + bn - 1) / bn;
@@ -792,7 +859,7 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     p.w16 = (a->out16 && (a->N & 7) == 0 && (p.n_tiles == 1 || (bn & 63) == 0)) ? 64 : 32;
     p.fast16 = (p.w16 == 64 && !a->out32 && !a->resid && a->alpha == 1.0f && (bn & 63) == 0 &&
                 (!a->bias || ((uintptr_t)a->bias & 15) == 0) && !getenv("RSR_NO_FAST_EPI")) ? 1 : 0;
-    const int fixed = 1024 /*align slack*/ + EPI_WARPS * p.st_stride + 64 + 16 * 8;
+    const int fixed = 1024 /*align slack*/ + EPI_WARPS * p.st_stride + 64 + 16 * 8 + (a->stats ? 2 * 4 * 256 * 8 + 32 : 0);
     int stages = (h->max_smem - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
     const int kb_per_tile = (nkb + splits - 1) / splits;
@@ -830,8 +897,10 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        RSR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
-        RSR_CHECK_CUDA(cudaFuncSetAttribute(gemm2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        RSR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        RSR_CHECK_CUDA(cudaFuncSetAttribute(gemm2_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        RSR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        RSR_CHECK_CUDA(cudaFuncSetAttribute(gemm2_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
         attr_set = true;
     }
     // One CTA per SM, and never next to a CTA of a recurrence kernel (those hold the whole TMEM of their SM for
@@ -859,10 +928,12 @@ extern "C" int rsr_gemm(rsr_handle* h, void* stream, const rsr_gemm_args* a) {
     cfg.attrs = at; cfg.numAttrs = na;
     if (two) {
         cfg.gridDim = dim3(2 * grid, 1, 1);
-        RSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tcgen05_kernel, tmA, tmB, tmC32, tmC16, p));
+        if (p.stats) RSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tcgen05_kernel<true>, tmA, tmB, tmC32, tmC16, p));
+        else RSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tcgen05_kernel<false>, tmA, tmB, tmC32, tmC16, p));
         return 0;
     }
     cfg.gridDim = dim3(grid, 1, 1);
-    RSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, tmA, tmB, tmC32, tmC16, p));
+    if (p.stats) RSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, tmA, tmB, tmC32, tmC16, p));
+    else RSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<false>, tmA, tmB, tmC32, tmC16, p));
     return 0;
 }

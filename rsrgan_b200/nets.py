@@ -173,10 +173,19 @@ class FCBN(FC):
         net, h = self.net, self.net.h
         z32, coef, scratch = self._bufs(ctx, rows)
         y16 = net.ws.get((ctx, self.scope, "y16"), rows, self.outp, h.h16)
-        h.gemm(x16, net.P.view(self.wname, "theta16"), rows, self.outp, self.inp, b_mn=True, out32=z32)
+        # training-mode batch_norm: the GEMM's epilogue leaves the (count, mean, M2) of every 128-row block and column in
+        # `scratch` (rsr_gemm_args.stats), so the statistics need only the fixed-order merge of those partials -- the
+        # pre-activation is not read a second time (models/dnn.py:56-62, models/discriminator_dnn.py:36-46)
+        epi_stats = (self.bn and net.training and hasattr(h, "bn_train_finish") and self.outp % 32 == 0
+                     and rows <= h.BN_STATS_ROWS_MAX and os.environ.get("RSR_NO_EPILOGUE_STATS") != "1")
+        h.gemm(x16, net.P.view(self.wname, "theta16"), rows, self.outp, self.inp, b_mn=True, out32=z32,
+               **(dict(stats=scratch) if epi_stats else {}))
         keep = net.keep_prob if net.training and self.drop else 1.0
         if self.bn:
-            if net.training:
+            if epi_stats:
+                h.bn_train_finish((rows + 127) // 128, rows, self.outp, net.P.view(self.gname), net.P.view(self.betaname),
+                                  self.state, coef, scratch, update_state=net.bn_update)
+            elif net.training:
                 h.bn_train_stats(z32, rows, self.outp, net.P.view(self.gname), net.P.view(self.betaname), self.state,
                                  coef, scratch, update_state=net.bn_update)
             else:

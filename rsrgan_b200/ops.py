@@ -127,7 +127,7 @@ class Handle(object):
     # ------------------------------------------------------------------ GEMM
     def gemm(self, A, B, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, bias=None,
              resid=None, act=ACT_NONE, dact_src=None, dact=ACT_NONE, out32=None, out16=None,
-             tile_n=0, lda=None, ldb=None, split_k=0):
+             tile_n=0, lda=None, ldb=None, split_k=0, stats=None):
         """D[M,N] = epi(alpha * A B).  A/B are 2-D h16 tensors (or views with a row stride);
         see rsr_gemm in the header for operand major-ness."""
         a = GemmArgs()
@@ -142,6 +142,7 @@ class Handle(object):
         a.out32, a.ldc32 = _p(out32), (out32.stride(0) if out32 is not None else 0)
         a.out16, a.ldc16 = _p(out16), (out16.stride(0) if out16 is not None else 0)
         a.tile_n, a.split_k = tile_n, split_k
+        a.stats = _p(stats)       # batch_norm statistics out of the epilogue: (count, mean, M2) per 128-row block and column
         self._call("rsr_gemm", 1, self.h, _stream(), C.byref(a), work=2.0 * M * N * K)
 
     # --------------------------------------------------------------- staging
@@ -420,6 +421,14 @@ class Handle(object):
         self._call("rsr_bn_train_stats", 2, self.h, _stream(), _p(z32), z32.stride(0), rows, N, _p(gamma), _p(beta),
                    self.BN_EPS, _p(state), self.BN_DECAY, self.BN_RENORM_DECAY, int(update_state), _p(coef),
                    _p(scratch))
+
+    BN_STATS_ROWS_MAX = 256 * 128       # row blocks the partial buffer of rsr_bn_train_stats holds
+
+    def bn_train_finish(self, splits, rows, N, gamma, beta, state, coef, scratch, update_state=False):
+        """rsr_bn_train_stats without its first pass: `scratch` holds `splits` row-block partials written by the epilogue of
+        the GEMM that produced the pre-activation (gemm(..., stats=scratch))."""
+        self._call("rsr_bn_train_finish", 1, self.h, _stream(), int(splits), rows, N, _p(gamma), _p(beta), self.BN_EPS,
+                   _p(state), self.BN_DECAY, self.BN_RENORM_DECAY, int(update_state), _p(coef), _p(scratch))
 
     def bn_eval_coef(self, N, gamma, beta, state, coef):
         self._call("rsr_bn_eval_coef", 1, self.h, _stream(), N, _p(gamma), _p(beta), self.BN_EPS, _p(state), _p(coef))

@@ -74,3 +74,36 @@ for name, fn, nbytes in cases:
     print(json.dumps({"call": name, "rows": rows, "N": N, "us": round(ms * 1e3, 2), "algorithmic_bytes": nbytes,
                       "achieved_GBps": round(gbs, 1), "peak_GBps": peak, "frac": round(gbs / peak, 3),
                       "buffers": "%d rotating sets (%.0f MB) > 126 MB L2" % (SETS, SETS * E * 10 / 1e6)}), flush=True)
+
+# batch_norm statistics in the GEMM epilogue (rsr_gemm_args.stats + rsr_bn_train_finish) against the two-pass form
+# (GEMM writes the pre-activation, rsr_bn_train_stats reads it back): the cfg-2 discriminator's two hidden layers
+for K in (1024, 40):
+    x16 = [(0.5 * torch.randn(rows, K, device=dev, generator=g)).half() for _ in range(SETS)]
+    w16 = (0.05 * torch.randn(K, N, device=dev, generator=g)).half()
+
+    def two_pass(i):
+        s = sets[i]
+        h.gemm(x16[i], w16, rows, N, K, b_mn=True, out32=s["z"])
+        h.bn_train_stats(s["z"], rows, N, gamma, beta, s["state"], s["coef"], s["scratch"], update_state=True)
+
+    def fused(i):
+        s = sets[i]
+        h.gemm(x16[i], w16, rows, N, K, b_mn=True, out32=s["z"], stats=s["scratch"])
+        h.bn_train_finish((rows + 127) // 128, rows, N, gamma, beta, s["state"], s["coef"], s["scratch"], update_state=True)
+
+    def gemm_only(i):
+        h.gemm(x16[i], w16, rows, N, K, b_mn=True, out32=sets[i]["z"])
+
+    for name, fn in (("gemm", gemm_only), ("gemm + rsr_bn_train_stats", two_pass),
+                     ("gemm(stats) + rsr_bn_train_finish", fused)):
+        for i in range(SETS):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(ITERS):
+            fn(i % SETS)
+        e1.record()
+        torch.cuda.synchronize()
+        print(json.dumps({"call": name, "rows": rows, "N": N, "K": K, "us": round(e0.elapsed_time(e1) / ITERS * 1e3, 2)}),
+              flush=True)

@@ -184,6 +184,48 @@ def test_bn_backward(h, rows, N, bn, act, keep):
         assert np.abs((got * xh).sum(0) / scale).max() < tol(h, 2e-3, 2e-2)
 
 
+@pytest.mark.parametrize("M,N,K,update", [(12800, 1024, 1024, True),     # cfg-2 discriminator layer: two-CTA GEMM
+                                          (12800, 1024, 40, False),      # its first layer: one-CTA GEMM, K = 40
+                                          (1000, 96, 64, True),          # ragged last row block, N = 3 chunks
+                                          (130, 32, 264, False)])        # two row blocks, the second with 2 rows
+def test_gemm_epilogue_batch_norm_statistics(h, M, N, K, update):
+    """rsr_gemm(stats=...) leaves the (count, mean, M2) of every 128-row block and column of its fp32 output in the partial
+    buffer, and rsr_bn_train_finish on those partials == rsr_bn_train_stats on the output (coefficients and UPDATE_OPS)."""
+    dev, rng = h.device, np.random.default_rng(M + N + K)
+    Kp = (K + 7) // 8 * 8
+    A = torch.zeros(M, Kp, dtype=h.h16, device=dev)
+    A[:, :K] = torch.tensor(rng.standard_normal((M, K)).astype(np.float32), device=dev).to(h.h16)
+    W = torch.zeros(Kp, N, dtype=h.h16, device=dev)
+    W[:K] = torch.tensor((rng.standard_normal((K, N)) * (0.05 + 0.1 * rng.random(N))).astype(np.float32), device=dev).to(h.h16)
+    z = torch.zeros(M, N, dtype=F32, device=dev)
+    scratch = torch.zeros(768, N, dtype=F32, device=dev)
+    h.gemm(A, W, M, N, Kp, b_mn=True, out32=z, stats=scratch)
+    torch.cuda.synchronize()
+    zz = z.double().cpu().numpy()
+    assert rel(zz, A.double().cpu().numpy() @ W.double().cpu().numpy()) < 1e-5
+    nb = (M + 127) // 128
+    part = scratch[:3 * nb].cpu().numpy().reshape(nb, 3, N).astype(np.float64)
+    for b in range(nb):
+        blk = zz[128 * b:128 * b + 128]
+        assert np.all(part[b, 0] == blk.shape[0])
+        assert np.abs(part[b, 1] - blk.mean(0)).max() < 1e-5 * (np.abs(blk).max() + 1)
+        m2 = ((blk - blk.mean(0)) ** 2).sum(0)
+        assert np.abs(part[b, 2] - m2).max() < 1e-4 * (m2.max() + 1e-6)
+    gamma, beta = (1 + 0.2 * rng.standard_normal(N)).astype(np.float32), rng.standard_normal(N).astype(np.float32)
+    st = warm(O.bn_init_state(N), rng)
+    gam_t, bet_t = torch.tensor(gamma, device=dev), torch.tensor(beta, device=dev)
+    state_a, state_b = (torch.tensor(state_arrays(st, N), device=dev) for _ in range(2))
+    coef_a, coef_b = (torch.zeros(8, N, dtype=F32, device=dev) for _ in range(2))
+    h.bn_train_finish(nb, M, N, gam_t, bet_t, state_a, coef_a, scratch, update_state=update)
+    h.bn_train_stats(z, M, N, gam_t, bet_t, state_b, coef_b, torch.zeros(768, N, dtype=F32, device=dev), update_state=update)
+    torch.cuda.synchronize()
+    assert rel(coef_a[:6].cpu().numpy(), coef_b[:6].cpu().numpy()) < 1e-5
+    assert rel(state_a.cpu().numpy(), state_b.cpu().numpy()) < 1e-5
+    from rsrgan_b200._lib import RsrError
+    with pytest.raises(RsrError, match="RSR_E_SHAPE"):           # statistics want a plain fp32 output
+        h.gemm(A, W, M, N, Kp, b_mn=True, out32=z, bias=bet_t, stats=scratch)
+
+
 def test_bn_shape_errors(h):
     from rsrgan_b200._lib import RsrError
     dev = h.device

@@ -134,7 +134,11 @@ def test_frame_gan_gpu(bn, keep, l2):
     """The same on the kernels, at the reference's layer width (1024 units, 2827-d spliced input, 297-d D input)."""
     m = build(None, bn=bn, keep=keep, l2=l2, B=256, units=1024, input_dim=257, output_dim=40, left_context=5,
               right_context=5)
-    rng = np.random.default_rng(6)
+    # seed chosen with the oracle (float64, here on the CPU) so that no pre-clip logit of either discriminator pass lies
+    # within 2.5e-3 of the clip_by_value edges -0.5 / 1.5 (models/discriminator_dnn.py:93): a row on an edge flips its whole
+    # gradient (2 (l - target) / N, the largest in the batch) on the last 16-bit rounding and the comparison below would
+    # measure that coin toss, not the kernels (seed 6 has a row at 1.49993).  The margin is asserted below.
+    rng = np.random.default_rng(25)
     N, I = 256, 257 * 11
     assert m.D.cat_dim == 257 and m.D.layers[0].inp == 304
     gp = O.init_g_dnn(rng, in_dim=I, out_dim=40, units=1024, hidden=1, batch_norm=bn)
@@ -149,9 +153,14 @@ def test_frame_gan_gpu(bn, keep, l2):
     for tick, which in enumerate("dg"):
         go = dict(bn_state=copy.deepcopy(gbs), keep_prob=keep if l2 > 0 else 1.0, rng=(4, tick))
         do = dict(bn_state=copy.deepcopy(dbs), keep_prob=keep, rng=(4, tick))
-        L, G, _ = O.tower_losses_and_grads(st, x[:, None].astype(np.float64), y[:, None].astype(np.float64),
-                                           np.ones(N, int), which, mse_lambda=10.0, l2_scale=l2, g_opts=go, d_opts=do,
-                                           d_cat=(257 * 5, 257 * 6), l2_weights_only=True)
+        L, G, g_ref = O.tower_losses_and_grads(st, x[:, None].astype(np.float64), y[:, None].astype(np.float64),
+                                               np.ones(N, int), which, mse_lambda=10.0, l2_scale=l2, g_opts=go, d_opts=do,
+                                               d_cat=(257 * 5, 257 * 6), l2_weights_only=True)
+        xx = x[:, None].astype(np.float64)
+        for v, salt in ((y[:, None].astype(np.float64), 256), (g_ref, 512)):
+            u = O.d_dnn_fwd(st.d, np.concatenate([xx[..., 257 * 5:257 * 6], v], -1), None, None,
+                            opts=dict(do, bn_state=copy.deepcopy(dbs)), salt0=salt)[1][-1][2]
+            assert min(np.abs(u + 0.5).min(), np.abs(u - 1.5).min()) > 2.5e-3
         m.update_bn_stats = False
         out = (m.d_step if which == "d" else m.g_step)(x, y)
         net, keys = (m.D, ("d_rl_loss", "d_fk_loss")) if which == "d" else (m.G, ("g_adv_loss", "g_mse_loss"))
