@@ -138,6 +138,24 @@ def test_lstmp_recurrence_fwd_bwd(h, B, T, I, C, P, ragged):
             assert v < t, (k, v, r)
 
 
+@pytest.mark.parametrize("B,T,I,C,P,ragged", [
+    (2, 1000, 40, 256, 40, True),        # discriminator_lstm layer, two long ragged utterances
+    (1, 1200, 257, 760, 257, False),     # decode of ONE whole utterance (batch_size = 1) through a res_lstm_l layer
+    (8, 800, 256, 512, 256, True),       # cfg-2 layer at the reference driver's batch of 8
+])
+def test_lstmp_recurrence_long_utterances(h, B, T, I, C, P, ragged):
+    """Utterance-scale lengths (the reference trains on and decodes whole utterances of up to ~1000 frames,
+    scripts/train_gan_rnn_placeholder.py:262-300): forward states and every gradient against the float64 oracle after
+    800-1200 dependent steps.  Bars = 2x the measured deviation (profiles/r2_long_T_v0.jsonl: fp16 <= 9.7e-4, bf16 <= 7.4e-3,
+    relative RMS)."""
+    r = _rec_case(h, B, T, I, C, P, ragged, seed=B + T)
+    t = tol(h, 2e-3, 1.5e-2)
+    assert r["pad"] == 0.0
+    for k, v in r.items():
+        if k != "pad":
+            assert v < t, (k, v, r)
+
+
 @pytest.mark.parametrize("B,T,I,C,P", [(40, 10, 256, 512, 256), (8, 12, 40, 256, 40)])
 def test_lstmp_recurrence_l2_exchange_variant(h, monkeypatch, B, T, I, C, P):
     """Cp <= 512 normally runs the cluster/DSMEM kernels; RSR_NO_CLUSTER forces the L2-exchange kernels
