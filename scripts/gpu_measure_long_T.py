@@ -20,3 +20,12 @@ for dt in ("f16", "bf16"):
         r = TK._rec_case(h, B, T, I, C, P, ragged, seed=B + T)
         print(json.dumps(dict(dtype=dt, B=B, T=T, I=I, C=C, P=P, ragged=ragged, **{k: float("%.3g" % v) for k, v in r.items()})), flush=True)
     h.close()
+
+# model level: decode of ONE whole utterance (GAN_RNN.generate, batch_size = 1) -- absolute and relative RMS of the
+# generator output against the float64 oracle
+import test_gan_gpu as TG              # noqa: E402
+for dt in ("f16", "bf16"):
+    for name, g_type, d_type, T, kw in (("cfg2 lstm 2x512", "lstm", "dnn", 1000, TG.CFG2),
+                                        ("reference driver res_lstm_l 4x760", "res_lstm_l", "lstm", 400, {})):
+        a, r = TG._g_slice(g_type, d_type, 1, T, [0], dt, kw)
+        print(json.dumps(dict(dtype=dt, model=name, B=1, T=T, g_out_rms=float("%.3g" % a), g_out_rel=float("%.3g" % r))), flush=True)

@@ -350,6 +350,17 @@ def test_cfg5_T200_against_oracle(dtype):
                      "(fp16 is the product dtype; DESIGN.md section 2)" % a)
 
 
+@pytest.mark.parametrize("g_type,d_type,T,kw,bar", [("lstm", "dnn", 1000, CFG2, 1.5e-4),
+                                                    ("res_lstm_l", "lstm", 400, {}, 9.5e-4)])
+def test_decode_of_one_long_utterance_against_oracle(g_type, d_type, T, kw, bar):
+    """The reference decodes whole utterances one at a time (batch_size = 1, scripts/train_gan_rnn_placeholder.py:262-300):
+    generator output of one 1000-frame utterance through the cfg-2 generator, and of a 400-frame one through the network
+    the shipped driver trains (res_lstm_l 4 x 760, the L2-exchange kernels), against the float64 oracle.  fp16, the
+    product dtype; bars = 2x the measured RMS (7.0e-5 / 4.6e-4, profiles/r2_long_T_v1.jsonl), both inside 1e-3."""
+    a, r = _g_slice(g_type, d_type, 1, T, [0], "f16", kw)
+    assert a < bar <= 1e-3, (a, r)
+
+
 def test_graph_replay_survives_workspace_growth():
     """A captured schedule holds raw workspace addresses.  A longer batch (train_batch) or a longer cross-validation
     utterance (eval_losses on the model that shares the workspace) replaces workspace buffers: the graphs captured

@@ -146,7 +146,7 @@ def test_lstmp_recurrence_fwd_bwd(h, B, T, I, C, P, ragged):
 def test_lstmp_recurrence_long_utterances(h, B, T, I, C, P, ragged):
     """Utterance-scale lengths (the reference trains on and decodes whole utterances of up to ~1000 frames,
     scripts/train_gan_rnn_placeholder.py:262-300): forward states and every gradient against the float64 oracle after
-    800-1200 dependent steps.  Bars = 2x the measured deviation (profiles/r2_long_T_v0.jsonl: fp16 <= 9.7e-4, bf16 <= 7.4e-3,
+    800-1200 dependent steps.  Bars = 2x the measured deviation (profiles/r2_long_T_v1.jsonl: fp16 <= 9.7e-4, bf16 <= 7.4e-3,
     relative RMS)."""
     r = _rec_case(h, B, T, I, C, P, ragged, seed=B + T)
     t = tol(h, 2e-3, 1.5e-2)
