@@ -74,7 +74,7 @@ def test_gemm_fused_epilogue(h):
     assert rel(o16.float().cpu().numpy(), v) < tol(h, 5e-4, 4e-3)
 
 
-def _rec_case(h, B, T, I, C, P, ragged, seed):
+def _rec_case(h, B, T, I, C, P, ragged, seed, lengths=None):
     dev, rng = h.device, np.random.default_rng(seed)
     Cp = packing.cell_pad(C)
     x = rng.standard_normal((B, T, I))
@@ -82,7 +82,8 @@ def _rec_case(h, B, T, I, C, P, ragged, seed):
     b = rng.standard_normal(4 * C) * 0.1
     wi, wf, wo = (O.xavier(rng, (C,)) for _ in range(3))
     Wp = O.xavier(rng, (C, P)) * 2.0
-    lengths = rng.integers(max(T // 2, 1), T + 1, size=B) if ragged else np.full(B, T)
+    drawn = rng.integers(max(T // 2, 1), T + 1, size=B) if ragged else np.full(B, T)
+    lengths = drawn if lengths is None else np.asarray(lengths)
     out_ref, cache = O.lstmp_fwd(x, lengths, K, b, wi, wf, wo, Wp)
     steps = cache[-1]
     zx = np.einsum("bti,ig->tbg", x, K[:I]) + b
@@ -150,6 +151,22 @@ def test_lstmp_recurrence_long_utterances(h, B, T, I, C, P, ragged):
     relative RMS)."""
     r = _rec_case(h, B, T, I, C, P, ragged, seed=B + T)
     t = tol(h, 2e-3, 1.5e-2)
+    assert r["pad"] == 0.0
+    for k, v in r.items():
+        if k != "pad":
+            assert v < t, (k, v, r)
+
+
+@pytest.mark.parametrize("B,T,I,C,P,lengths", [
+    (4, 6, 40, 256, 40, [0, 6, 3, 0]),                     # cluster / pair kernels: first and last utterance empty
+    (3, 5, 257, 760, 257, [5, 0, 1]),                      # L2-exchange kernels (Cp = 768)
+    (40, 8, 256, 512, 256, [0] * 32 + [8, 0, 3, 8, 0, 1, 2, 8]),   # a whole utterance group of empty rows
+])
+def test_lstmp_recurrence_empty_utterances(h, B, T, I, C, P, lengths):
+    """sequence_length = 0 (tf.nn.dynamic_rnn copies zero state through and emits zeros, models/lstm.py:104-112): the rows
+    of an empty utterance stay exactly zero, it contributes nothing to any gradient, and its neighbours are unaffected."""
+    r = _rec_case(h, B, T, I, C, P, True, seed=B + T, lengths=lengths)
+    t = tol(h, 1.5e-3, 1e-2)
     assert r["pad"] == 0.0
     for k, v in r.items():
         if k != "pad":
