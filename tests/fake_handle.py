@@ -70,7 +70,8 @@ class FakeHandle(object):
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, A, B, M, N, K, a_mn=False, b_mn=False, alpha=1.0, beta=0.0, bias=None, resid=None,
-             act=ACT_NONE, dact_src=None, dact=ACT_NONE, out32=None, out16=None, tile_n=0, lda=None, ldb=None):
+             act=ACT_NONE, dact_src=None, dact=ACT_NONE, out32=None, out16=None, tile_n=0, lda=None, ldb=None, split_k=0,
+             stats=None):
         self.launches += 1
         Ae = (A[:K, :M].t() if a_mn else A[:M, :K]).float()
         Be = (B[:K, :N] if b_mn else B[:N, :K].t()).float()
@@ -86,6 +87,14 @@ class FakeHandle(object):
             out16[:M, :N] = v.to(self.h16)
         if out32 is not None:
             out32[:M, :N] = v + (beta * out32[:M, :N] if beta != 0.0 else 0.0)
+        if stats is not None:       # rsr_gemm_args.stats: (count, mean, M2) of every 128-row block and column, [block][3][N]
+            assert out32 is not None and out16 is None and bias is None and resid is None and act == ACT_NONE \
+                and dact_src is None and alpha == 1.0 and beta == 0.0 and N % 32 == 0 and M <= self.BN_STATS_ROWS_MAX
+            for blk in range((M + 127) // 128):
+                z = v[128 * blk:128 * blk + 128]
+                stats[3 * blk, :N] = float(z.shape[0])
+                stats[3 * blk + 1, :N] = z.mean(0)
+                stats[3 * blk + 2, :N] = ((z - z.mean(0)) ** 2).sum(0)
 
     # ------------------------------------------------- one-output fully_connected
     def fc1_fwd(self, x16, rows, K, w16, bias, out32):
@@ -354,7 +363,9 @@ class FakeHandle(object):
         self.launches += 2
         z = z32[:rows, :N]
         mean = z.mean(0)
-        var = ((z - mean) ** 2).mean(0)
+        self._bn_from_moments(mean, ((z - mean) ** 2).mean(0), N, gamma, beta, state, coef, update_state)
+
+    def _bn_from_moments(self, mean, var, N, gamma, beta, state, coef, update_state):
         std = torch.sqrt(var + self.BN_EPS)
         mm, mv, rm, rs, rmw, rsw = (state[i, :N] for i in range(6))
         denom = rs + (1 - rsw) * std
@@ -370,6 +381,24 @@ class FakeHandle(object):
             rsw -= (rsw - 1) * k
             mm -= (mm - rm / rmw) * (1 - self.BN_DECAY)
             mv -= (mv - ((rs / rsw) ** 2 - self.BN_EPS)) * (1 - self.BN_DECAY)
+
+    BN_STATS_ROWS_MAX = 256 * 128
+
+    def bn_train_finish(self, splits, rows, N, gamma, beta, state, coef, scratch, update_state=False):
+        """rsr_bn_train_finish: the partials the GEMM epilogue left in `scratch`, merged in block order (Chan), then the same
+        coefficients and UPDATE_OPS as bn_train_stats."""
+        self.launches += 1
+        n = torch.zeros(N)
+        mean, m2 = torch.zeros(N), torch.zeros(N)
+        for blk in range(splits):
+            nb, mb, qb = scratch[3 * blk, :N], scratch[3 * blk + 1, :N], scratch[3 * blk + 2, :N]
+            tot = n + nb
+            d = mb - mean
+            mean = mean + d * nb / tot
+            m2 = m2 + qb + d * d * n * nb / tot
+            n = tot
+        assert float(n[0]) == rows
+        self._bn_from_moments(mean, m2 / rows, N, gamma, beta, state, coef, update_state)
 
     def bn_eval_coef(self, N, gamma, beta, state, coef):
         self.launches += 1

@@ -195,6 +195,43 @@ def test_dnn_trainer_batch_norm_steps_match_oracle():
     assert int(m2.G.rng[1]) == 2
 
 
+def test_fcbn_statistics_epilogue_and_two_pass_forms_agree(monkeypatch):
+    """nets.FCBN in training mode asks the GEMM for the batch_norm partials (rsr_gemm_args.stats) and finishes them
+    (rsr_bn_train_finish); RSR_NO_EPILOGUE_STATS=1, a width that is not a multiple of 32, or the inference graph keep the
+    two-pass / moving-average forms.  Same numbers either way."""
+    def run(units, no_epi):
+        if no_epi:
+            monkeypatch.setenv("RSR_NO_EPILOGUE_STATS", "1")
+        else:
+            monkeypatch.delenv("RSR_NO_EPILOGUE_STATS", raising=False)
+        h = FakeHandle("f16")
+        calls = {"finish": 0, "two_pass": 0}
+        fin, two = h.bn_train_finish, h.bn_train_stats
+        h.bn_train_finish = lambda *a, **k: (calls.__setitem__("finish", calls["finish"] + 1), fin(*a, **k))[1]
+        h.bn_train_stats = lambda *a, **k: (calls.__setitem__("two_pass", calls["two_pass"] + 1), two(*a, **k))[1]
+        args = Namespace(g_type="dnn", batch_size=300, input_dim=40, output_dim=8, g_units=units, g_layers=2, batch_norm=True,
+                         keep_prob=1.0, l2_scale=0.0, g_learning_rate=1e-3, seed=11)
+        m = DNNTrainer(None, args, ["/gpu:0"], handle=h)
+        rng = np.random.default_rng(3)
+        outs = [m.train_step(rng.standard_normal((300, 40)).astype(np.float32),
+                             rng.standard_normal((300, 8)).astype(np.float32)) for _ in range(2)]
+        return calls, outs, m.G.bn_state_tf(), m.G.P.export_tf()
+    ca, oa, sa, ta = run(64, False)
+    cb, ob, sb, tb = run(64, True)
+    n = 2 * sum(1 for l in DNNTrainer(None, Namespace(g_type="dnn", batch_size=300, input_dim=40, output_dim=8, g_units=64,
+                                                     g_layers=2, batch_norm=True, seed=11), ["/gpu:0"],
+                                      handle=FakeHandle("f16")).G.layers if getattr(l, "bn", False))
+    assert n > 0 and ca == {"finish": n, "two_pass": 0} and cb == {"finish": 0, "two_pass": n}   # every layer, both steps
+    for a, b in zip(oa, ob):
+        assert a["g_mse_loss"] == pytest.approx(b["g_mse_loss"], rel=1e-5)
+    for k in sa:
+        assert rel(sa[k], sb[k]) < 1e-5, k
+    for k in ta:          # two Adam steps from zero-initialised betas are all update: rounding of the moments shows there
+        assert rel(ta[k], tb[k]) < 1e-3, k
+    cc, _, _, _ = run(40, False)                                   # 40 units: not whole 32-column chunks -> two-pass form
+    assert cc == {"finish": 0, "two_pass": n}
+
+
 def test_gan_with_batch_norm_discriminator_matches_oracle():
     """dnn generator + discriminator_dnn, both batch-normalised, dropout in D: gradients of one D and one G update.
     UPDATE_OPS as models/gan_rnn_placeholder.py:163-175 wires them: the D update assigns the discriminator's statistics
