@@ -65,6 +65,8 @@ def flops_per_frame(cfg):
         fd = 2 * 40 * 1024 + 3 * 2 * 1024 * 1024 + 2 * 1024
     else:
         fd = lstmp(40, 256, 40) + lstmp(40, 256, 40) + 2 * 40
+    if cfg.get("_parts"):
+        return fg, fd
     return 7 * fg + 10 * fd
 
 
@@ -316,6 +318,11 @@ def main():
                   if k in shares]
     fpf = flops_per_frame(cfg)
     step_tflops = value / world * fpf / 1e12
+    # what the schedule EXECUTES: G(x) of the D update is the forward the first G update reuses when the generator has no
+    # dropout (same weights, same minibatch, same numbers: GAN_RNN._schedule), i.e. 6 F_G instead of the reference's 7
+    fg1, fd1 = flops_per_frame(dict(cfg, _parts=True))
+    shared = getattr(model, "G", None) is not None and model.G.keep_prob >= 1.0 and getattr(model, "gen_updates", 0) > 0
+    fpf_exec = (6 if shared else 7) * fg1 + 10 * fd1
 
     out = {
         "metric": "gan_train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -332,7 +339,11 @@ def main():
         "roofline": roofline,
         "roofline_lstm_kernels": lstm_roofs,
         "step_roofline": {"algorithmic_mflop_per_frame": fpf / 1e6, "achieved_tflops_per_gpu": step_tflops,
-                          "frac_of_sustained_bf16": step_tflops / sus, "frac_of_burst_bf16": step_tflops / burst},
+                          "frac_of_sustained_bf16": step_tflops / sus, "frac_of_burst_bf16": step_tflops / burst,
+                          "executed_mflop_per_frame": fpf_exec / 1e6,
+                          "executed_tflops_per_gpu": value / world * fpf_exec / 1e12,
+                          "note": "algorithmic = 7 F_G + 10 F_D of the reference schedule (SURVEY 8d); executed = with the generator "
+                                  "forward shared between the D update and the first G update (identical numbers)"},
         "kernel_shares": {k: {"calls_per_step": v[0] / nprof, "ms_per_step": v[1] / nprof, "share": v[1] / tot}
                           for k, v in sorted(shares.items(), key=lambda kv: -kv[1][1])},
     }
