@@ -1,0 +1,96 @@
+"""The oracle against the reference's OWN graph-building code.
+
+tests/golden/ref_graph_*.npz were produced in the build container by tests/golden/make_reference_graph_golden.py, which
+imports /root/reference/models/gan_rnn_placeholder.py (and with it lstm.py, res_lstm_l.py, res_lstm_base.py,
+discriminator_lstm.py, utils/ops.py) plus models/BNLSTMCell.py, and executes them over an eager float64 stand-in for the
+TensorFlow-1.4 calls they make (tests/golden/tf_standin.py: TensorFlow itself cannot be installed here).  So the variable
+names and shapes, the layer wiring, the (B, 1, 40) discriminator noise, the loss formulas, tower slicing,
+average_gradients, clip_by_norm 15, which optimizer updates which network and the EMA are the REFERENCE's statements;
+only TensorFlow's library layers and op kernels are restated (and the LSTM step of that restatement is checked against
+models/BNLSTMCell.py:176-213).  Here the oracle replays the same seeded parameters and feeds and must agree to 1e-9."""
+import copy
+import os
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+sys.path.insert(0, GOLD)
+import ref_graph_common as C  # noqa: E402
+from oracle import rsr_oracle as O  # noqa: E402
+
+LOSS_KEYS = [("d_rl_losses", "d_rl_loss"), ("d_fk_losses", "d_fk_loss"), ("d_losses", "d_loss"), ("g_adv_losses", "g_adv_loss"),
+             ("g_mse_losses", "g_mse_loss"), ("g_l2_losses", "g_l2_loss"), ("g_losses", "g_loss")]
+
+
+def close(a, b, rtol=1e-9):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return a.shape == b.shape and np.allclose(a, b, rtol=rtol, atol=rtol * (float(np.abs(b).max()) if b.size else 0.0) + 1e-13)
+
+
+@pytest.mark.parametrize("case", list(C.GAN_RNN_CASES))
+def test_gan_rnn_graph_of_the_reference(case):
+    fix = np.load(os.path.join(GOLD, "ref_graph_gan_rnn_%s.npz" % case))
+    c, gp, dp, x, y, lengths, noise = C.gan_rnn_setup(case)
+    B = c["B"]
+    # 1. the variables models/gan_rnn_placeholder.py creates are exactly the ones the oracle names, with these shapes
+    mine = {"%s %s" % (k, list(v.shape)) for p in (gp, dp) for k, v in p.items()}
+    assert set(fix["variables"].tolist()) == mine
+    kw = dict(mse_lambda=C.MSE_LAMBDA, l2_scale=c["l2_scale"])
+    towers = []
+    for i in range(c["towers"]):
+        sl = slice(B * i, B * (i + 1))                                   # gan_rnn_placeholder.py:157-159
+        towers.append(dict(x=x[sl], y=y[sl], lengths=lengths[sl], noise_rl=C.NOISE_STD * noise[1 + 2 * i],
+                           noise_fk=C.NOISE_STD * noise[2 + 2 * i]))
+    st = O.GanState(copy.deepcopy(gp), copy.deepcopy(dp), c["g_type"], "lstm")
+    for i, t in enumerate(towers):
+        # 2. forward values and the seven losses of every tower (:191-260)
+        Ld, Gd, g_out = O.tower_losses_and_grads(st, t["x"], t["y"], t["lengths"], "d", t["noise_rl"], t["noise_fk"], **kw)
+        Lg, Gg, _ = O.tower_losses_and_grads(st, t["x"], t["y"], t["lengths"], "g", t["noise_rl"], t["noise_fk"], **kw)
+        assert close(g_out, fix["fwd|tower%d/g_clean|full" % i])
+        assert close(O.d_lstm_fwd(st.d, t["y"], t["lengths"], t["noise_rl"])[0], fix["fwd|tower%d/d_real|full" % i])
+        assert close(O.d_lstm_fwd(st.d, g_out, t["lengths"], t["noise_fk"])[0], fix["fwd|tower%d/d_fake|full" % i])
+        for fk, ok in LOSS_KEYS:
+            assert Lg.get(ok, 0.0) == pytest.approx(float(fix["loss|" + fk][i]), rel=1e-10, abs=1e-14), (fk, i)
+        assert Ld["d_loss"] == pytest.approx(float(fix["loss|d_losses"][i]), rel=1e-10)
+        # 3. raw gradients of d_loss wrt the d_ variables and of g_loss wrt the g_ variables (:169-175)
+        assert C.check(fix, "grad_d_tower%d" % i, Gd) == len(dp)
+        assert C.check(fix, "grad_g_tower%d" % i, Gg) == len(gp)
+    # 4. average over towers, clip each tensor to norm 15, SGD on D / Adam on G, EMA 0.9999 (:177-189)
+    sd = O.GanState(copy.deepcopy(gp), copy.deepcopy(dp), c["g_type"], "lstm")
+    _, clipped_d = O.d_step(sd, towers, C.LR_D, **kw)
+    C.check(fix, "applied_d", clipped_d)
+    C.check(fix, "theta_d_after_d_opt", sd.d, rtol=1e-10)
+    C.check(fix, "ema_d_after_d_opt", sd.d_ema, rtol=1e-10)
+    sg = O.GanState(copy.deepcopy(gp), copy.deepcopy(dp), c["g_type"], "lstm")
+    _, clipped_g = O.g_step(sg, towers, C.LR_G, **kw)
+    C.check(fix, "applied_g", clipped_g)
+    C.check(fix, "theta_g_after_g_opt", sg.g, rtol=1e-10)
+    C.check(fix, "ema_g_after_g_opt", sg.g_ema, rtol=1e-10)
+    # the clip bites in these cases (the generator's loss is large), so its order -- after the tower mean -- is exercised
+    raw = O.average_gradients([O.tower_losses_and_grads(st, t["x"], t["y"], t["lengths"], "g", t["noise_rl"], t["noise_fk"], **kw)[1]
+                               for t in towers])
+    assert max(float(np.sqrt((v ** 2).sum())) for v in raw.values()) > 15.0
+
+
+def test_lstm_step_of_the_reference():
+    """models/BNLSTMCell.py:176-213 (the reference's statement of the peephole LSTMP step; batch norms replaced by the
+    identity) == oracle lstmp_fwd, state and projected output, over four steps."""
+    f = np.load(os.path.join(GOLD, "ref_graph_lstm_cell.npz"))
+    out, cache = O.lstmp_fwd(f["x"], np.full(f["x"].shape[0], f["x"].shape[1]), f["K"], f["b"], f["w_i"], f["w_f"], f["w_o"], f["Wp"])
+    assert close(out, f["m"], 1e-12)
+
+
+def test_exponential_decay_of_the_reference():
+    """utils/ops.py:378-391 called directly == the oracle's and the trainer CLI's restatements."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "rsr_cli", os.path.join(os.path.dirname(GOLD), os.pardir, "scripts", "train_gan_rnn_placeholder.py"))
+    rows = np.load(os.path.join(GOLD, "ref_graph_schedules.npz"))["exponential_decay"]
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    for it, jobs, iters, init, mult, want in rows:
+        for fn in (O.exponential_decay, cli.exponential_decay):
+            assert fn(int(it), int(jobs), int(iters), float(init), bool(mult)) == pytest.approx(want, rel=1e-13)
