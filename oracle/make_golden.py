@@ -2,9 +2,10 @@
 (oracle/rsr_oracle.py) computes for them -- generator output, the seven losses, raw D / G
 gradients and the generator output after one batch schedule (1 D + 2 G updates).
 
-PARITY UNPINNED (see rsr_oracle.py header): the reference's TF-1.4 graph cannot be executed here,
-so these vectors pin the *oracle*; they are cross-checked by the independent torch-autograd
-statement (oracle/torch_ref.py) in tests/test_oracle.py.
+These vectors are the ORACLE's outputs (they pin the product to the oracle).  What pins the oracle to the reference is
+tests/golden/make_reference_graph_golden.py -> tests/test_reference_graph.py (the reference's model files executed over a
+TensorFlow stand-in; rsr_oracle.py header) and the independent torch-autograd statement (oracle/torch_ref.py) in
+tests/test_oracle.py; TensorFlow 1.4 itself cannot be run here.
 
     python -m oracle.make_golden
 """

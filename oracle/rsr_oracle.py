@@ -6,15 +6,21 @@ the path `models/gan_rnn_placeholder.py` drives.  It is the *checker*: only
 leg may import it.  Nothing under `rsrgan_b200/` imports it and the product has
 no CPU fallback.
 
-PARITY UNPINNED: all arithmetic of the reference lives in TensorFlow 1.4.0
-(unvendored, not installable here: no python2, no `tensorflow`, no network), and
-the reference ships no golden vectors for this path.  The
-oracle is therefore pinned only by (i) an independent torch-autograd float64
-implementation of the same forward (`oracle/torch_ref.py`; must agree to
-1e-9), (ii) finite-difference gradient checks, (iii) torch.nn.LSTM(proj_size)
-cross-check with peepholes zeroed and gates re-ordered, and (iv) for the Kaldi
-ark reader the reference's own `io_funcs/kaldi_io.py`, which does import here
-(fixtures under tests/golden/ made by `oracle/make_golden.py`).
+PARITY PINNED TO THE REFERENCE'S SOURCE, NOT TO TENSORFLOW'S KERNELS.  TensorFlow 1.4.0 (unvendored, not
+installable here: no python2, no `tensorflow`, no network) cannot be run and the reference ships no golden vectors
+for this path.  What CAN be run is everything the reference itself wrote:
+`tests/golden/make_reference_graph_golden.py` imports models/gan_rnn_placeholder.py, lstm.py, res_lstm_l.py,
+res_lstm_base.py, discriminator_lstm.py, discriminator_dnn.py, dnn.py, rced.py, gan.py, dnn_trainer*.py, BNLSTMCell.py,
+utils/ops.py and utils/bnorm.py from /root/reference and executes them over an eager float64 stand-in for the
+TensorFlow calls they make (tests/golden/tf_standin.py); the fixtures it wrote (tests/golden/ref_graph_*.npz: variable
+names and shapes, forward values, losses, per-tower gradients, averaged + clipped gradients, SGD / Adam / EMA results)
+are what tests/test_reference_graph.py holds this oracle to, at 1e-9.  That pins the wiring, the formulas and the LSTM
+step (against models/BNLSTMCell.py:176-213) to reference code; TensorFlow's own library layers and op kernels (contrib
+fully_connected / conv2d / LSTMCell / dynamic_rnn / batch_norm(renorm), Adam) remain restatements, cross-checked by
+(i) an independent torch-autograd float64 implementation of the same forward (`oracle/torch_ref.py`; must agree to
+1e-9), (ii) finite-difference gradient checks, (iii) torch.nn.LSTM(proj_size) with peepholes zeroed and gates
+re-ordered, torch conv / conv_transpose / batch_norm.  The Kaldi ark reader is pinned bit for bit to the reference's own
+`io_funcs/kaldi_io.py`, which imports here (tests/golden/make_kaldi_golden.py).
 
 Every function cites the reference file:line it follows (paths relative to the
 reference root).  Default dtype is float64; pass float32 arrays to get a

@@ -90,6 +90,173 @@ def gan_rnn_case(case):
           % (case, len(out["variables"]), out["loss|d_losses"], out["loss|g_losses"], raw_norm))
 
 
+def frame_gan_case():
+    """models/gan.py: DNN generator on the spliced frame, discriminator_dnn on concat(centre LPS frame, MFCC), LSGAN + MSE +
+    REGULARIZATION_LOSSES of g_model, Adam for D and for G, gradients applied unclipped."""
+    import models.gan as ref_frame_gan
+    c, gp, dp, x, y = C.frame_setup("gan_dnn")
+    S.reset()
+    S.unknown_time = False
+    S.init = dict(gp, **dp)
+    args = Namespace(keep_prob=1.0, batch_norm=False, batch_size=c["N"], save_dir="/tmp/ref_graph", l2_scale=c["l2_scale"],
+                     input_dim=257, output_dim=40, left_context=C.LEFT, right_context=C.RIGHT, disc_updates=1, gen_updates=2,
+                     init_mse_weight=C.MSE_LAMBDA, init_disc_noise_std=C.NOISE_STD, d_learning_rate=c["lr_d"],
+                     g_learning_rate=c["lr_g"], g_type="dnn")
+    with redirect_stdout(io.StringIO()):
+        m = ref_frame_gan.GAN(Sess(), args, ["gpu:0"], tf_standin.TT(torch.tensor(x)), tf_standin.TT(torch.tensor(y)))
+    assert S.init_used == set(S.init), sorted(set(S.init) - S.init_used)
+    out = {"variables": np.array(["%s %s" % (k, list(v.v.shape)) for k, v in S.vars.items() if not k.startswith("__anon__/")])}
+    for n, t in S.summaries:
+        if n in ("d_real", "d_fake", "g_clean"):
+            out["fwd|%s|full" % n] = t.numpy()
+    for k in ("d_rl_losses", "d_fk_losses", "d_losses", "g_adv_losses", "g_mse_losses", "g_l2_losses", "g_losses"):
+        out["loss|" + k] = np.array([float(tf_standin._raw(t).detach()) for t in getattr(m, k)])
+    assert len(S.grad_log) == 2 and len(S.apply_log) == 2
+    C.pack(out, "grad_d", named(S.grad_log[0][1]))
+    C.pack(out, "grad_g", named(S.grad_log[1][1]))
+    C.pack(out, "applied_d", named(S.apply_log[0][1]))
+    C.pack(out, "applied_g", named(S.apply_log[1][1]))
+    ema = S.emas[0]
+    m.d_opt()
+    C.pack(out, "theta_d_after_d_opt", OrderedDict((k, S.vars[k].numpy()) for k in dp))
+    C.pack(out, "ema_d_after_d_opt", OrderedDict((k, ema.shadow[S.vars[k]].numpy().copy()) for k in dp))
+    m.g_opt()
+    C.pack(out, "theta_g_after_g_opt", OrderedDict((k, S.vars[k].numpy()) for k in gp))
+    C.pack(out, "ema_g_after_g_opt", OrderedDict((k, ema.shadow[S.vars[k]].numpy().copy()) for k in gp))
+    np.savez_compressed(os.path.join(HERE, "ref_graph_frame_gan_dnn.npz"), **out)
+    print("frame gan (models/gan.py) %d variables, d_loss %s g_loss %s g_l2 %s" % (len(out["variables"]), out["loss|d_losses"],
+                                                                               out["loss|g_losses"], out["loss|g_l2_losses"]))
+
+
+def dnn_trainer_case():
+    """models/dnn_trainer_single_gpu.py: 0.5 * 40 * mse + REGULARIZATION_LOSSES, Adam.minimize on the g_ variables; two steps
+    are not possible in an eagerly built graph, so: losses, gradients and the weights after the one `g_opt`."""
+    import models.dnn_trainer_single_gpu as ref_trainer
+    c, gp, _, x, y = C.frame_setup("dnn_trainer")
+    S.reset()
+    S.unknown_time = False
+    S.init = dict(gp)
+    args = Namespace(keep_prob=1.0, batch_norm=False, batch_size=c["N"], save_dir="/tmp/ref_graph", l2_scale=c["l2_scale"],
+                     input_dim=257, output_dim=40, left_context=C.LEFT, right_context=C.RIGHT, g_learning_rate=c["lr_g"],
+                     g_type="dnn")
+    with redirect_stdout(io.StringIO()):
+        m = ref_trainer.DNNTrainer(Sess(), args, ["gpu:0"], tf_standin.TT(torch.tensor(x)), tf_standin.TT(torch.tensor(y)))
+    assert S.init_used == set(S.init)
+    out = {"variables": np.array(["%s %s" % (k, list(v.v.shape)) for k, v in S.vars.items() if not k.startswith("__anon__/")])}
+    for k in ("g_mse_losses", "g_l2_losses", "g_losses"):
+        out["loss|" + k] = np.array([float(tf_standin._raw(getattr(m, k)).detach())])
+    assert len(S.grad_log) == 1 and len(S.apply_log) == 1
+    C.pack(out, "grad_g", named(S.grad_log[0][1]))
+    m.g_opt()
+    C.pack(out, "theta_g_after_g_opt", OrderedDict((k, S.vars[k].numpy()) for k in gp))
+    np.savez_compressed(os.path.join(HERE, "ref_graph_dnn_trainer.npz"), **out)
+    print("dnn trainer            %d variables, g_mse %s g_l2 %s" % (len(out["variables"]), out["loss|g_mse_losses"], out["loss|g_l2_losses"]))
+
+
+def rced_case(case):
+    """models/rced.py under models/dnn_trainer.py (the multi-tower MSE trainer: average_gradients, Adam, EMA over
+    tf.trainable_variables()): nine [splice, w] SAME convolutions on (N, splice, 257, 1), NHWC flatten, linear output."""
+    import models.dnn_trainer as ref_mt
+    c, gp, x, y = C.rced_setup(case)
+    S.reset()
+    S.unknown_time = False
+    S.init = dict(gp)
+    args = Namespace(keep_prob=1.0, batch_norm=False, batch_size=c["N"], save_dir="/tmp/ref_graph", l2_scale=c["l2_scale"],
+                     input_dim=257, output_dim=40, left_context=c["ctx"], right_context=c["ctx"], g_learning_rate=c["lr_g"],
+                     g_type="rced")
+    with redirect_stdout(io.StringIO()):
+        m = ref_mt.DNNTrainer(Sess(), args, ["gpu:0"], tf_standin.TT(torch.tensor(x)), tf_standin.TT(torch.tensor(y)))
+    assert S.init_used == set(S.init), sorted(set(S.init) - S.init_used)
+    out = {"variables": np.array(["%s %s" % (k, list(v.v.shape)) for k, v in S.vars.items() if not k.startswith("__anon__/")])}
+    for k in ("g_mse_losses", "g_l2_losses", "g_losses"):
+        out["loss|" + k] = np.array([float(tf_standin._raw(t).detach()) for t in getattr(m, k)])
+    assert len(S.grad_log) == 1 and len(S.apply_log) == 1
+    C.pack(out, "grad_g", named(S.grad_log[0][1]))
+    ema = S.emas[0]
+    m.g_opt()
+    C.pack(out, "theta_g_after_g_opt", OrderedDict((k, S.vars[k].numpy()) for k in gp))
+    C.pack(out, "ema_g_after_g_opt", OrderedDict((k, ema.shadow[S.vars[k]].numpy().copy()) for k in gp))
+    np.savez_compressed(os.path.join(HERE, "ref_graph_%s.npz" % case), **out)
+    print("%-22s %d variables, g_mse %s g_l2 %s" % (case, len(out["variables"]), out["loss|g_mse_losses"], out["loss|g_l2_losses"]))
+
+
+def vbn_case():
+    """utils/bnorm.py:11-69 (virtual batch norm): the reference pass and a live pass, outputs and -- by autograd through the
+    reference's own expressions -- the gradients of a weighted sum of the outputs wrt the input, gamma and beta."""
+    import utils.bnorm as ref_bnorm
+    rng = np.random.default_rng(11)
+    B, L, Cn = 3, 5, 4
+    x_ref, x = 1.5 * rng.standard_normal((B, L, Cn)) + 0.3, 0.8 * rng.standard_normal((B, L, Cn)) - 0.2
+    gamma, beta = 1.0 + 0.2 * rng.standard_normal(Cn), 0.1 * rng.standard_normal(Cn)
+    r_ref, r_live = rng.standard_normal((B, L, Cn)), rng.standard_normal((B, L, Cn))
+    S.reset()
+    S.unknown_time = False
+    S.init = {"d_vbn/gamma": gamma, "d_vbn/beta": beta}
+    xr = tf_standin.TT(torch.tensor(x_ref, requires_grad=True))
+    xl = tf_standin.TT(torch.tensor(x, requires_grad=True))
+    vb = ref_bnorm.VBN(xr, "d_vbn")
+    with tf.variable_scope(tf.get_variable_scope(), reuse=True):
+        live = vb(xl)
+    g, b = S.vars["d_vbn/gamma"], S.vars["d_vbn/beta"]
+    gr = torch.autograd.grad((vb.reference_output.v * torch.tensor(r_ref)).sum(), [xr.v, g.v, b.v], retain_graph=True)
+    # live pass: the reference batch's statistics are constants of this pass (they belong to the reference pass)
+    vb.mean, vb.mean_sq = tf_standin.TT(vb.mean.v.detach()), tf_standin.TT(vb.mean_sq.v.detach())
+    with tf.variable_scope(tf.get_variable_scope(), reuse=True):
+        live = vb(xl)
+    gl = torch.autograd.grad((live.v * torch.tensor(r_live)).sum(), [xl.v, g.v, b.v])
+    np.savez_compressed(os.path.join(HERE, "ref_graph_vbn.npz"), x_ref=x_ref, x=x, gamma=gamma, beta=beta, r_ref=r_ref, r_live=r_live,
+                        out_ref=vb.reference_output.numpy(), out_live=live.numpy(),
+                        dx_ref=gr[0].numpy(), dgamma_ref=gr[1].numpy(), dbeta_ref=gr[2].numpy(),
+                        dx_live=gl[0].numpy(), dgamma_live=gl[1].numpy(), dbeta_live=gl[2].numpy())
+    print("vbn                    utils/bnorm.py reference + live pass, outputs and gradients")
+
+
+def conv_family_case():
+    """utils/ops.py:78-98 downconv (k = 31, stride 2, bias), :138-156 conv1d (k = 31), :277-310 deconv (k = 31, dilation 2,
+    bias): outputs and the autograd gradients of a weighted sum of the outputs wrt the input, filter and bias."""
+    rng = np.random.default_rng(13)
+    out = {}
+    B, L, Ci, Co, k = 2, 14, 3, 5, 31
+    for name, odd in (("even", 0), ("odd", 1)):
+        Lx = L + odd
+        x = rng.standard_normal((B, Lx, Ci))
+        # downconv
+        S.reset(); S.unknown_time = False
+        W, b = 0.2 * rng.standard_normal((k, 1, Ci, Co)), 0.1 * rng.standard_normal(Co)
+        S.init = {"dc/W": W, "dc/b": b}
+        xt = tf_standin.TT(torch.tensor(x, requires_grad=True))
+        y = ref_ops.downconv(xt, Co, kwidth=k, pool=2, bias_init=tf.constant_initializer(0.), name="dc")
+        r = rng.standard_normal(tuple(y.v.shape))
+        g = torch.autograd.grad((y.v * torch.tensor(r)).sum(), [xt.v, S.vars["dc/W"].v, S.vars["dc/b"].v])
+        out.update({"down_%s|%s" % (name, kk): v for kk, v in dict(x=x, W=W, b=b, r=r, y=y.numpy(), dx=g[0].numpy(), dW=g[1].numpy(),
+                                                                  db=g[2].numpy()).items()})
+        # deconv: (B, Lx, Ci) -> (B, 2 Lx, Co)
+        S.reset(); S.unknown_time = False
+        W, b = 0.2 * rng.standard_normal((k, 1, Co, Ci)), 0.1 * rng.standard_normal(Co)
+        S.init = {"de/W": W, "de/b": b}
+        xt = tf_standin.TT(torch.tensor(x, requires_grad=True))
+        y = ref_ops.deconv(xt, [B, 2 * Lx, Co], kwidth=k, dilation=2, bias_init=0.0, name="de")
+        r = rng.standard_normal(tuple(y.v.shape))
+        g = torch.autograd.grad((y.v * torch.tensor(r)).sum(), [xt.v, S.vars["de/W"].v, S.vars["de/b"].v])
+        out.update({"de_%s|%s" % (name, kk): v for kk, v in dict(x=x, W=W, b=b, r=r, y=y.numpy(), dx=g[0].numpy(), dW=g[1].numpy(),
+                                                                db=g[2].numpy()).items()})
+    # conv1d k = 31, stride 1
+    S.reset(); S.unknown_time = False
+    x = rng.standard_normal((B, L, Ci))
+    W, b = 0.2 * rng.standard_normal((k, Ci, 1)), np.array([0.3])
+    S.init = {"c1/W": W, "c1/b": b}
+    xt = tf_standin.TT(torch.tensor(x, requires_grad=True))
+    y = ref_ops.conv1d(xt, kwidth=k, num_kernels=1, bias_init=0.3, name="c1")
+    r = rng.standard_normal(tuple(y.v.shape))
+    g = torch.autograd.grad((y.v * torch.tensor(r)).sum(), [xt.v, S.vars["c1/W"].v, S.vars["c1/b"].v])
+    out.update({"conv1d|%s" % kk: v for kk, v in dict(x=x, W=W, b=b, r=r, y=y.numpy(), dx=g[0].numpy(), dW=g[1].numpy(),
+                                                      db=g[2].numpy()).items()})
+    lr = ref_ops.leakyrelu(tf_standin.TT(torch.tensor(x)))
+    out["leakyrelu|x"], out["leakyrelu|y"] = x, lr.numpy()
+    np.savez_compressed(os.path.join(HERE, "ref_graph_conv_family.npz"), **out)
+    print("conv family            utils/ops.py downconv / deconv (even and odd lengths), conv1d, leakyrelu")
+
+
 def lstm_cell_case():
     """models/BNLSTMCell.py:176-213 -- the reference's own statement of the peephole LSTMP step -- with its three
     batch_norm calls replaced by the identity, over a few steps; against it: the stand-in's LSTMCell (checked here) and the
@@ -146,5 +313,11 @@ def schedules_case():
 if __name__ == "__main__":
     lstm_cell_case()
     schedules_case()
+    vbn_case()
+    conv_family_case()
     for case in C.GAN_RNN_CASES:
         gan_rnn_case(case)
+    frame_gan_case()
+    dnn_trainer_case()
+    for case in C.RCED_CASES:
+        rced_case(case)

@@ -65,3 +65,48 @@ def check(fix, prefix, tensors, rtol=1e-9, atol=1e-12):
                 scale = float(np.abs(ref).max()) if np.size(ref) else 0.0
                 assert np.allclose(a, ref, rtol=rtol, atol=atol + rtol * scale), (prefix, k, f, float(np.abs(a - ref).max()), scale)
     return len(names)
+
+
+# frame-level trainers: models/gan.py (DNN generator + conditioned discriminator_dnn, Adam for both, no clipping) and
+# models/dnn_trainer_single_gpu.py (MSE + l2, Adam) at the reference's layer sizes, splice 5 + 1 + 5
+FRAME_CASES = OrderedDict([
+    ("gan_dnn", dict(N=6, l2_scale=1e-4, scale=2.0, seed=201, lr_d=1e-3, lr_g=8e-5)),
+    ("dnn_trainer", dict(N=5, l2_scale=1e-3, scale=2.0, seed=202, lr_g=1e-3)),
+])
+LEFT = RIGHT = 5
+
+
+def frame_setup(case):
+    c = FRAME_CASES[case]
+    rng = np.random.default_rng(c["seed"])
+    in_dim = 257 * (LEFT + 1 + RIGHT)
+    gp = O.init_g_dnn(rng, in_dim=in_dim, out_dim=40, units=1024, hidden=3)
+    dp = O.init_d_dnn(rng, in_dim=257 + 40, units=1024, hidden=3) if case == "gan_dnn" else OrderedDict()
+    for p in (gp, dp):
+        for k in p:
+            if k.endswith("biases"):
+                p[k] = p[k] + 0.1 * rng.standard_normal(p[k].shape)
+    x = c["scale"] * rng.standard_normal((c["N"], in_dim))
+    y = c["scale"] * rng.standard_normal((c["N"], 40))
+    return c, gp, dp, x, y
+
+
+# the convolutional generator (models/rced.py) under the reference's multi-tower MSE trainer (models/dnn_trainer.py):
+# splice 1 (BASELINE configs[3]) and a [3, w] case of the 2-D convolutions run_dnn.sh trains with splice 11
+RCED_CASES = OrderedDict([
+    ("rced_splice1", dict(N=4, ctx=0, l2_scale=1e-3, scale=1.5, seed=301, lr_g=1e-3)),
+    ("rced_splice3", dict(N=3, ctx=1, l2_scale=0.0, scale=1.5, seed=302, lr_g=1e-3)),
+])
+
+
+def rced_setup(case):
+    c = RCED_CASES[case]
+    rng = np.random.default_rng(c["seed"])
+    splice = 2 * c["ctx"] + 1
+    gp = O.init_g_rced(rng, in_dim=257, out_dim=40, splice=splice)
+    for k in gp:
+        if k.endswith("biases"):
+            gp[k] = gp[k] + 0.1 * rng.standard_normal(gp[k].shape)
+    x = c["scale"] * rng.standard_normal((c["N"], splice * 257))
+    y = c["scale"] * rng.standard_normal((c["N"], 40))
+    return c, gp, x, y

@@ -313,6 +313,10 @@ def truncated_normal_initializer(mean=0.0, stddev=1.0, **_):
     return lambda shape, **__: mean + stddev * np.clip(STATE.rng.standard_normal(shape), -2, 2)
 
 
+def random_normal_initializer(mean=0.0, stddev=1.0, **_):
+    return lambda shape, **__: mean + stddev * STATE.rng.standard_normal(shape)
+
+
 def l2_regularizer(scale, scope=None):
     def f(w):
         t = TT(scale * 0.5 * (w.v ** 2).sum())
@@ -418,6 +422,69 @@ def fully_connected(inputs, num_outputs, activation_fn=relu, normalizer_fn=None,
         if activation_fn is not None:
             out = activation_fn(out)
         return out
+
+
+def conv2d(inputs, num_outputs, kernel_size, stride=1, padding="SAME", activation_fn=relu, normalizer_fn=None,
+           normalizer_params=None, weights_initializer=None, weights_regularizer=None, biases_initializer=zeros_initializer(),
+           reuse=None, trainable=True, scope=None, **_):
+    """tf.contrib.layers.conv2d (contrib/layers/python/layers/layers.py `convolution`): scope "Conv" made unique, variables
+    "weights" [kh, kw, C_in, C_out] and "biases" [C_out], NHWC, stride 1, SAME (odd kernels: k // 2 zeros per side)."""
+    assert stride == 1 and padding == "SAME"
+    kh, kw = (int(k) for k in kernel_size)
+    assert kh % 2 == 1 and kw % 2 == 1
+    with variable_scope(scope, "Conv", [inputs], reuse=reuse):
+        x = _raw(inputs)                                                   # N, H, W, C
+        w = _get_variable("weights", [kh, kw, x.shape[-1], int(num_outputs)], initializer=weights_initializer or xavier_initializer(),
+                          regularizer=weights_regularizer, trainable=trainable)
+        out = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.v.permute(3, 2, 0, 1), padding=(kh // 2, kw // 2))
+        out = TT(out.permute(0, 2, 3, 1))
+        if normalizer_fn is not None:
+            out = normalizer_fn(out, **(normalizer_params or {}))
+        elif biases_initializer is not None:
+            b = _get_variable("biases", [int(num_outputs)], initializer=biases_initializer, trainable=trainable)
+            out = TT(out.v + b.v)
+        if activation_fn is not None:
+            out = activation_fn(out)
+        return out
+
+
+def _same(L, k, s):
+    """TensorFlow SAME padding along one axis (core/framework/common_shape_fns.cc GetWindowedOutputSize): output length
+    ceil(L / s), total padding max((out - 1) s + k - L, 0), the odd element after."""
+    out = -(-L // s)
+    total = max((out - 1) * s + k - L, 0)
+    return out, total // 2, total - total // 2
+
+
+def _conv2d_raw(x, w, strides):
+    sh, sw = int(strides[1]), int(strides[2])
+    _, pt, pb = _same(x.shape[1], w.shape[0], sh)
+    _, pl, pr = _same(x.shape[2], w.shape[1], sw)
+    xp = torch.nn.functional.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb))
+    return torch.nn.functional.conv2d(xp.contiguous(), w.permute(3, 2, 0, 1).contiguous(), stride=(sh, sw)).permute(0, 2, 3, 1)
+
+
+def nn_conv2d(input, filter, strides, padding, **_):
+    """tf.nn.conv2d, NHWC, filter [kh, kw, C_in, C_out]."""
+    assert padding == "SAME" and strides[0] == 1 and strides[3] == 1
+    return TT(_conv2d_raw(_raw(input), _raw(filter), strides))
+
+
+def nn_conv1d(value, filters, stride, padding, **_):
+    """tf.nn.conv1d: conv2d on [B, 1, L, C] with filter [1, k, C_in, C_out] (python/ops/nn_ops.py conv1d)."""
+    assert padding == "SAME"
+    return TT(_conv2d_raw(_raw(value).unsqueeze(1), _raw(filters).unsqueeze(0), [1, 1, int(stride), 1]).squeeze(1))
+
+
+def nn_conv2d_transpose(value, filter, output_shape, strides, padding="SAME", **_):
+    """tf.nn.conv2d_transpose is, by definition, conv2d_backprop_input: the gradient of conv2d(z, filter) wrt z (z of
+    output_shape, filter [kh, kw, C_out, C_in]) contracted with `value` -- taken here literally, by autograd."""
+    assert padding == "SAME"
+    z = torch.zeros([int(s) for s in output_shape], dtype=F64, requires_grad=True)
+    y = _conv2d_raw(z, _raw(filter), strides)
+    v = _raw(value)
+    assert list(y.shape) == list(v.shape), (list(y.shape), list(v.shape))
+    return TT(torch.autograd.grad(y, z, grad_outputs=v, create_graph=True)[0])
 
 
 def batch_norm(*a, **k):
@@ -580,6 +647,10 @@ class _Optimizer(object):
         return Op([lambda: self._apply(gv)])
 
 
+    def minimize(self, loss, global_step=None, var_list=None, **_):
+        return self.apply_gradients(self.compute_gradients(loss, var_list=var_list))
+
+
 class GradientDescentOptimizer(_Optimizer):
     def _apply(self, gv):
         lr = float(_raw(self.lr))
@@ -660,7 +731,7 @@ def install():
     me = sys.modules[__name__]
     for n in ("variable_scope get_variable_scope name_scope device control_dependencies get_variable Variable "
               "trainable_variables get_collection placeholder assign zeros_initializer ones_initializer constant_initializer "
-              "truncated_normal_initializer tanh sigmoid square sqrt ones_like zeros_like maximum add matmul squared_difference "
+              "truncated_normal_initializer random_normal_initializer tanh sigmoid square sqrt ones_like zeros_like maximum add matmul squared_difference "
               "clip_by_value constant expand_dims squeeze reshape concat split reduce_mean reduce_sum random_normal clip_by_norm "
               "group GraphKeys").split():
         setattr(tf, n, getattr(me, n))
@@ -668,6 +739,7 @@ def install():
     tf.float32 = "float32"
     tf.int32 = "int32"
     tf.nn = types.SimpleNamespace(relu=relu, dynamic_rnn=dynamic_rnn, dropout=dropout, moments=moments, l2_loss=l2_loss,
+                                  conv2d=nn_conv2d, conv1d=nn_conv1d, conv2d_transpose=nn_conv2d_transpose,
                                   batch_normalization=batch_normalization, bias_add=bias_add, tanh=tanh, sigmoid=sigmoid)
     tf.train = types.SimpleNamespace(GradientDescentOptimizer=GradientDescentOptimizer, AdamOptimizer=AdamOptimizer,
                                      RMSPropOptimizer=RMSPropOptimizer, ExponentialMovingAverage=ExponentialMovingAverage,
@@ -680,7 +752,7 @@ def install():
     tf.losses = types.SimpleNamespace(mean_squared_error=mean_squared_error)
     tf.logging = types.SimpleNamespace(WARN=30, log_first_n=lambda *a, **k: None)
     layers = types.ModuleType("tensorflow.contrib.layers")
-    for n in "fully_connected batch_norm xavier_initializer l2_regularizer flatten".split():
+    for n in "fully_connected conv2d batch_norm xavier_initializer l2_regularizer flatten".split():
         setattr(layers, n, getattr(me, n))
     rnn = types.ModuleType("tensorflow.contrib.rnn")
     for n in "LSTMCell MultiRNNCell DropoutWrapper RNNCell LSTMStateTuple".split():

@@ -1,6 +1,6 @@
 """Pins the CPU oracle (oracle/rsr_oracle.py): against the independent torch-autograd statement,
-finite differences, torch.nn.LSTM(proj_size) and the committed golden vectors.  PARITY UNPINNED
-against TF-1.4 itself (not runnable here) -- see the oracle header."""
+finite differences, torch.nn.LSTM(proj_size) and the committed golden vectors.  (The oracle against the reference's own
+model code: tests/test_reference_graph.py.  TF-1.4 itself is not runnable here -- see the oracle header.)"""
 import os
 from collections import OrderedDict
 

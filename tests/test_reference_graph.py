@@ -94,3 +94,106 @@ def test_exponential_decay_of_the_reference():
     for it, jobs, iters, init, mult, want in rows:
         for fn in (O.exponential_decay, cli.exponential_decay):
             assert fn(int(it), int(jobs), int(iters), float(init), bool(mult)) == pytest.approx(want, rel=1e-13)
+
+
+def test_frame_gan_graph_of_the_reference():
+    """models/gan.py (+ dnn.py, discriminator_dnn.py) executed over the stand-in: conditioned discriminator input
+    concat(centre LPS frame, MFCC) (:159-174), clip_by_value(-0.5, 1.5) on the logits, g_l2 from the REGULARIZATION_LOSSES of
+    g_model only (:209-214), Adam for both networks, no gradient clipping (:139-153)."""
+    fix = np.load(os.path.join(GOLD, "ref_graph_frame_gan_dnn.npz"))
+    c, gp, dp, x, y = C.frame_setup("gan_dnn")
+    assert set(fix["variables"].tolist()) == {"%s %s" % (k, list(v.shape)) for p in (gp, dp) for k, v in p.items()}
+    N = c["N"]
+    x3, y3, ones = x[:, None], y[:, None], np.ones(N, int)
+    kw = dict(mse_lambda=C.MSE_LAMBDA, l2_scale=c["l2_scale"], d_cat=(257 * C.LEFT, 257 * (C.LEFT + 1)), l2_weights_only=True)
+    st = O.GanState(copy.deepcopy(gp), copy.deepcopy(dp), "dnn", "dnn")
+    Ld, Gd, g_out = O.tower_losses_and_grads(st, x3, y3, ones, "d", **kw)
+    Lg, Gg, _ = O.tower_losses_and_grads(st, x3, y3, ones, "g", **kw)
+    assert close(g_out[:, 0], fix["fwd|g_clean|full"])
+    centre = x3[..., 257 * C.LEFT:257 * (C.LEFT + 1)]
+    assert close(O.d_dnn_fwd(st.d, np.concatenate([centre, y3], -1))[0][:, 0], fix["fwd|d_real|full"])
+    assert close(O.d_dnn_fwd(st.d, np.concatenate([centre, g_out], -1))[0][:, 0], fix["fwd|d_fake|full"])
+    for fk, ok in LOSS_KEYS:
+        assert Lg.get(ok, 0.0) == pytest.approx(float(fix["loss|" + fk][0]), rel=1e-10, abs=1e-14), fk
+    assert C.check(fix, "grad_d", Gd) == len(dp)
+    assert C.check(fix, "grad_g", Gg) == len(gp)
+    tower = dict(x=x3, y=y3, lengths=ones)
+    sd = O.GanState(copy.deepcopy(gp), copy.deepcopy(dp), "dnn", "dnn")
+    _, applied = O.d_step(sd, [tower], c["lr_d"], max_norm=1e30, adam=True, **kw)
+    C.check(fix, "applied_d", applied)
+    C.check(fix, "theta_d_after_d_opt", sd.d, rtol=1e-10)
+    C.check(fix, "ema_d_after_d_opt", sd.d_ema, rtol=1e-10)
+    sg = O.GanState(copy.deepcopy(gp), copy.deepcopy(dp), "dnn", "dnn")
+    _, applied = O.g_step(sg, [tower], c["lr_g"], max_norm=1e30, **kw)
+    C.check(fix, "applied_g", applied)
+    C.check(fix, "theta_g_after_g_opt", sg.g, rtol=1e-10)
+    C.check(fix, "ema_g_after_g_opt", sg.g_ema, rtol=1e-10)
+
+
+def test_dnn_trainer_graph_of_the_reference():
+    """models/dnn_trainer_single_gpu.py:93-133 (+ dnn.py) executed over the stand-in: 0.5 * 40 * mse + the weights-only l2
+    of the contrib regularizer, Adam.minimize."""
+    fix = np.load(os.path.join(GOLD, "ref_graph_dnn_trainer.npz"))
+    c, gp, _, x, y = C.frame_setup("dnn_trainer")
+    assert set(fix["variables"].tolist()) == {"%s %s" % (k, list(v.shape)) for k, v in gp.items()}
+    st = O.MseState(copy.deepcopy(gp), "dnn")
+    losses, grads = O.mse_step(st, x, y, c["lr_g"], l2_scale=c["l2_scale"])
+    for fk, ok in (("g_mse_losses", "g_mse_loss"), ("g_l2_losses", "g_l2_loss"), ("g_losses", "g_loss")):
+        assert losses[ok] == pytest.approx(float(fix["loss|" + fk][0]), rel=1e-10), fk
+    assert C.check(fix, "grad_g", grads) == len(gp)
+    C.check(fix, "theta_g_after_g_opt", st.g, rtol=1e-10)
+
+
+@pytest.mark.parametrize("case", list(C.RCED_CASES))
+def test_rced_graph_of_the_reference(case):
+    """models/rced.py under models/dnn_trainer.py executed over the stand-in: (N, splice * 257) frames reshaped to
+    (N, splice, 257, 1) (:46-57), nine SAME [splice, w] convolutions with ReLU (:90-101), NHWC flatten into the linear output
+    layer with bias 0.1 (:106-113); 0.5 * 40 * mse + weights-only l2, Adam, EMA over all trainable variables."""
+    fix = np.load(os.path.join(GOLD, "ref_graph_%s.npz" % case))
+    c, gp, x, y = C.rced_setup(case)
+    assert set(fix["variables"].tolist()) == {"%s %s" % (k, list(v.shape)) for k, v in gp.items()}
+    st = O.MseState(copy.deepcopy(gp), "rced")
+    losses, grads = O.mse_step(st, x, y, c["lr_g"], l2_scale=c["l2_scale"])
+    for fk, ok in (("g_mse_losses", "g_mse_loss"), ("g_l2_losses", "g_l2_loss"), ("g_losses", "g_loss")):
+        assert losses[ok] == pytest.approx(float(fix["loss|" + fk][0]), rel=1e-10, abs=1e-14), fk
+    assert C.check(fix, "grad_g", grads) == len(gp)
+    C.check(fix, "theta_g_after_g_opt", st.g, rtol=1e-10)
+    C.check(fix, "ema_g_after_g_opt", O.ema_update(copy.deepcopy(gp), st.g, 0.9999), rtol=1e-10)
+
+
+def test_virtual_batch_norm_of_the_reference():
+    """utils/bnorm.py:11-69 executed over the stand-in (reference pass, then a live pass blended with weight 1 / (B + 1)):
+    outputs, and the gradients autograd takes through the reference's expressions, against vbn_fwd / vbn_bwd."""
+    f = np.load(os.path.join(GOLD, "ref_graph_vbn.npz"))
+    out, cache = O.vbn_fwd(f["x_ref"], f["gamma"], f["beta"])
+    assert close(out, f["out_ref"], 1e-12)
+    dx, dg, db = O.vbn_bwd(f["r_ref"], cache)
+    assert close(dx, f["dx_ref"], 1e-11) and close(dg, f["dgamma_ref"], 1e-11) and close(db, f["dbeta_ref"], 1e-11)
+    out, cache = O.vbn_fwd(f["x"], f["gamma"], f["beta"], ref=O.vbn_reference(f["x_ref"]))
+    assert close(out, f["out_live"], 1e-12)
+    dx, dg, db = O.vbn_bwd(f["r_live"], cache)
+    assert close(dx, f["dx_live"], 1e-11) and close(dg, f["dgamma_live"], 1e-11) and close(db, f["dbeta_live"], 1e-11)
+
+
+def test_conv_family_of_the_reference():
+    """utils/ops.py downconv (:78-98), deconv (:277-310), conv1d (:138-156) and leakyrelu (:120-121) executed over the stand-in
+    (tf.nn.conv2d with TensorFlow's SAME rule; conv2d_transpose literally as the gradient of conv2d), even and odd lengths:
+    outputs and autograd gradients against the oracle's forward / backward statements."""
+    f = np.load(os.path.join(GOLD, "ref_graph_conv_family.npz"))
+    for par in ("even", "odd"):
+        g = lambda k: f["down_%s|%s" % (par, k)]
+        y, cache = O.downconv_fwd(g("x"), g("W")[:, 0], g("b"), pool=2)
+        assert close(y, g("y"), 1e-12)
+        dx, dW, db = O.downconv_bwd(g("r"), cache)
+        assert close(dx, g("dx"), 1e-11) and close(dW, g("dW")[:, 0], 1e-11) and close(db, g("db"), 1e-11)
+        g = lambda k: f["de_%s|%s" % (par, k)]
+        y, cache = O.deconv_fwd(g("x"), g("W")[:, 0], g("b"), dilation=2)
+        assert close(y, g("y"), 1e-12)
+        dx, dW, db = O.deconv_bwd(g("r"), cache)
+        assert close(dx, g("dx"), 1e-11) and close(dW, g("dW")[:, 0], 1e-11) and close(db, g("db"), 1e-11)
+    g = lambda k: f["conv1d|" + k]
+    y, cache = O.conv1d_same_fwd(g("x"), g("W")[None], g("b"), O.ACT_NONE)
+    assert close(y, g("y"), 1e-12)
+    dx, dW, db = O.conv1d_same_bwd(g("r"), cache)
+    assert close(dx, g("dx"), 1e-11) and close(dW[0], g("dW"), 1e-11) and close(db, g("db"), 1e-11)
+    assert close(O.act_fwd(f["leakyrelu|x"], O.ACT_LRELU), f["leakyrelu|y"], 1e-15)
