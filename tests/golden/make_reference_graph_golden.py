@@ -257,6 +257,19 @@ def conv_family_case():
     print("conv family            utils/ops.py downconv / deconv (even and odd lengths), conv1d, leakyrelu")
 
 
+def splice_case():
+    """io_funcs/tfrecords_io.py:177-204 splice_feats (slice + one-row SYMMETRIC pads), the loader's context splicing."""
+    import io_funcs.tfrecords_io as ref_io
+    rng = np.random.default_rng(17)
+    out = {}
+    for i, (rows, cols, left, right) in enumerate([(9, 4, 5, 5), (6, 3, 2, 0), (6, 3, 0, 3), (7, 2, 1, 1), (12, 257, 5, 5)]):
+        feats = rng.standard_normal((rows, cols))
+        out["case%d|feats" % i], out["case%d|ctx" % i] = feats, np.array([left, right])
+        out["case%d|spliced" % i] = ref_io.splice_feats(tf_standin.TT(torch.tensor(feats)), left, right).numpy()
+    np.savez_compressed(os.path.join(HERE, "ref_graph_splice.npz"), **out)
+    print("splice                 io_funcs/tfrecords_io.py splice_feats, %d cases" % (i + 1))
+
+
 def lstm_cell_case():
     """models/BNLSTMCell.py:176-213 -- the reference's own statement of the peephole LSTMP step -- with its three
     batch_norm calls replaced by the identity, over a few steps; against it: the stand-in's LSTMCell (checked here) and the
@@ -315,6 +328,7 @@ if __name__ == "__main__":
     schedules_case()
     vbn_case()
     conv_family_case()
+    splice_case()
     for case in C.GAN_RNN_CASES:
         gan_rnn_case(case)
     frame_gan_case()

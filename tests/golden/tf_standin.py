@@ -358,6 +358,17 @@ def slice_(x, begin, size, name=None):
     return TT(r[tuple(slice(b, None if s == -1 else b + s) for b, s in zip(begin, size))])
 
 
+def shape(x, **_):
+    return [int(d) for d in _raw(x).shape]
+
+
+def pad(tensor, paddings, mode="CONSTANT", **_):
+    """tf.pad; SYMMETRIC mirrors INCLUDING the edge element (numpy 'symmetric')."""
+    r = _raw(tensor).detach().numpy()
+    return TT(torch.tensor(np.pad(r, [tuple(int(q) for q in pr) for pr in paddings], mode={"CONSTANT": "constant", "SYMMETRIC": "symmetric",
+                                                                                     "REFLECT": "reflect"}[mode])))
+
+
 def _reduce(f):
     def g(x, axis=None, keep_dims=False, name=None, **_):
         r = _raw(x)
@@ -732,7 +743,7 @@ def install():
     for n in ("variable_scope get_variable_scope name_scope device control_dependencies get_variable Variable "
               "trainable_variables get_collection placeholder assign zeros_initializer ones_initializer constant_initializer "
               "truncated_normal_initializer random_normal_initializer tanh sigmoid square sqrt ones_like zeros_like maximum add matmul squared_difference "
-              "clip_by_value constant expand_dims squeeze reshape concat split reduce_mean reduce_sum random_normal clip_by_norm "
+              "clip_by_value shape pad constant expand_dims squeeze reshape concat split reduce_mean reduce_sum random_normal clip_by_norm "
               "group GraphKeys").split():
         setattr(tf, n, getattr(me, n))
     tf.slice = slice_

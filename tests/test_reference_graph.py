@@ -197,3 +197,14 @@ def test_conv_family_of_the_reference():
     dx, dW, db = O.conv1d_same_bwd(g("r"), cache)
     assert close(dx, g("dx"), 1e-11) and close(dW[0], g("dW"), 1e-11) and close(db, g("db"), 1e-11)
     assert close(O.act_fwd(f["leakyrelu|x"], O.ACT_LRELU), f["leakyrelu|y"], 1e-15)
+
+
+def test_splice_feats_of_the_reference():
+    """io_funcs/tfrecords_io.py:177-204 executed over the stand-in == the loader's splice_feats (edge replication)."""
+    from rsrgan_b200.dataset import splice_feats
+    f = np.load(os.path.join(GOLD, "ref_graph_splice.npz"))
+    n = len([k for k in f.files if k.endswith("|feats")])
+    assert n >= 5
+    for i in range(n):
+        left, right = (int(v) for v in f["case%d|ctx" % i])
+        assert np.array_equal(splice_feats(f["case%d|feats" % i], left, right), f["case%d|spliced" % i]), i
