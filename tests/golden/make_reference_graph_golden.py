@@ -270,6 +270,58 @@ def splice_case():
     print("splice                 io_funcs/tfrecords_io.py splice_feats, %d cases" % (i + 1))
 
 
+def schedule_case():
+    """scripts/train_gan_rnn_placeholder.py:48-133 train_one_iteration -- the reference's own loop -- over a queue of three
+    minibatches (the second one ragged: skipped): per minibatch one sess.run of d_opt, then two of g_opt, each re-executing
+    the reference's graph code on the current variables (tf_standin.Session)."""
+    import importlib.util
+    import queue
+    spec = importlib.util.spec_from_file_location("ref_train_script", os.path.join(REF, "scripts", "train_gan_rnn_placeholder.py"))
+    ref_script = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_script)
+    c, gp, dp, batches = C.schedule_setup()
+    B = c["B"]
+    S.reset()
+    S.init = dict(gp, **dp)
+    S.noise_fn = lambda shape: np.zeros(shape) if shape == [B, 1, 40] else None        # std 0; the SHAPE is still checked
+    args = Namespace(keep_prob=1.0, batch_norm=False, batch_size=B, num_gpu=1, save_dir="/tmp/ref_graph", l2_scale=c["l2_scale"],
+                     input_dim=257, output_dim=40, left_context=0, right_context=0, disc_updates=1, gen_updates=2,
+                     init_mse_weight=C.MSE_LAMBDA, init_disc_noise_std=0.0, d_learning_rate=C.LR_D, g_learning_rate=C.LR_G,
+                     g_type=c["g_type"])
+
+    def rebuild(feeds):
+        S.begin_retrace(feeds)
+        with redirect_stdout(io.StringIO()):
+            return ref_gan.GAN_RNN(sess, args, ["gpu:0"])
+    sess = tf_standin.Session(rebuild)
+    x0, y0, l0 = batches[0]
+    S.feeds = {"inputs": x0, "labels": y0, "lengths": l0.astype(np.float64)}
+    with redirect_stdout(io.StringIO()):
+        model = ref_gan.GAN_RNN(sess, args, ["gpu:0"])
+    assert S.init_used == set(S.init)
+    sess.bind(model)
+    ref_script.FLAGS = Namespace(num_gpu=1, batch_size=B)
+    q = queue.Queue()
+    for i, (x, y, ln) in enumerate(batches):
+        q.put(["utt%d" % i, x, y, ln.astype(np.float64)])
+    means = ref_script.train_one_iteration(sess, model, len(batches), 0, q)
+    assert sess.log == [["d_opt", "d_rl_losses", "d_fk_losses", "d_losses"]] + 2 * [["g_opt", "g_adv_losses", "g_mse_losses",
+                                                                               "g_l2_losses", "g_losses"]] + \
+        [["summaries"]] * 0 + [["d_opt", "d_rl_losses", "d_fk_losses", "d_losses"]] + 2 * [["g_opt", "g_adv_losses", "g_mse_losses",
+                                                                                        "g_l2_losses", "g_losses"]], sess.log
+    out = {"means": np.array(means, np.float64), "adam_t": np.array(S.persist[("adam", 0)]["t"])}
+    ema = S.persist[("ema", 0)]
+    C.pack(out, "theta_g", OrderedDict((k, S.vars[k].numpy()) for k in gp))
+    C.pack(out, "theta_d", OrderedDict((k, S.vars[k].numpy()) for k in dp))
+    C.pack(out, "ema_g", OrderedDict((k, ema[S.vars[k]].numpy().copy()) for k in gp))
+    C.pack(out, "ema_d", OrderedDict((k, ema[S.vars[k]].numpy().copy()) for k in dp))
+    sess.run([model.d_losses], feed_dict={model.inputs: x0, model.labels: y0, model.lengths: l0.astype(np.float64)})
+    out["g_after"] = [t for n, t in S.summaries if n == "g_clean"][0].numpy()
+    np.savez_compressed(os.path.join(HERE, "ref_graph_schedule.npz"), **out)
+    print("schedule               train_one_iteration over %d queued minibatches (%d sess.run of d_opt / g_opt), mean losses %s"
+          % (len(batches), len(sess.log) - 1, np.round(out["means"], 4)))
+
+
 def lstm_cell_case():
     """models/BNLSTMCell.py:176-213 -- the reference's own statement of the peephole LSTMP step -- with its three
     batch_norm calls replaced by the identity, over a few steps; against it: the stand-in's LSTMCell (checked here) and the
@@ -333,5 +385,6 @@ if __name__ == "__main__":
         gan_rnn_case(case)
     frame_gan_case()
     dnn_trainer_case()
+    schedule_case()
     for case in C.RCED_CASES:
         rced_case(case)

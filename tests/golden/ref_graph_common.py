@@ -110,3 +110,24 @@ def rced_setup(case):
     x = c["scale"] * rng.standard_normal((c["N"], splice * 257))
     y = c["scale"] * rng.standard_normal((c["N"], 40))
     return c, gp, x, y
+
+
+# the reference's own training loop (scripts/train_gan_rnn_placeholder.py train_one_iteration) over three queued
+# minibatches, the second one short of an utterance (skipped, :69-70); discriminator noise off
+SCHEDULE = dict(g_type="lstm", B=2, T=5, l2_scale=1e-4, scale=2.0, seed=401, batches=(2, 1, 2))
+
+
+def schedule_setup():
+    c = SCHEDULE
+    rng = np.random.default_rng(c["seed"])
+    gp, dp = O.init_g_lstm(rng), O.init_d_lstm(rng)
+    for p in (gp, dp):
+        for k in p:
+            if k.endswith("bias") or k.endswith("biases"):
+                p[k] = p[k] + 0.1 * rng.standard_normal(p[k].shape)
+    batches = []
+    for n in c["batches"]:
+        lengths = rng.integers(max(c["T"] // 2, 1), c["T"] + 1, size=n)
+        lengths[0] = c["T"]
+        batches.append((c["scale"] * rng.standard_normal((n, c["T"], 257)), c["scale"] * rng.standard_normal((n, c["T"], 40)), lengths))
+    return c, gp, dp, batches

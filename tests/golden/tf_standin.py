@@ -54,6 +54,25 @@ class _State(object):
         self.apply_log = []            # (optimizer, [(grad, var)]) per apply_gradients call
         self.emas = []                 # ExponentialMovingAverage objects, creation order
         self.summaries = []            # (name, tensor) per tf.summary.histogram / scalar call
+        self.retrace = False           # Session.run re-executes the reference's graph-building code on the CURRENT variables
+        self.anon_list, self.anon_i = [], 0
+        self.persist = {}              # (kind, creation index within one build) -> optimizer slots / EMA shadows
+        self.created = {}              # kind -> objects created in the current build
+        self.noise_fn = None           # fallback for tf.random_normal when the queue is empty
+
+    def begin_retrace(self, feeds):
+        """One sess.run(fetches, feed_dict): the graph code runs again, on the same variable objects (current values), the
+        same optimizer slots and EMA shadows; nothing may be created."""
+        self.retrace = True
+        self.feeds = dict(feeds)
+        self.scope = [VariableScope("", False)]
+        self.scope_counts, self.created, self.anon_i = {}, {}, 0
+        self.grad_log, self.apply_log, self.emas, self.summaries = [], [], [], []
+
+    def slots(self, kind, make):
+        i = self.created.get(kind, 0)
+        self.created[kind] = i + 1
+        return self.persist.setdefault((kind, i), make())
 
 
 class VariableScope(object):
@@ -225,6 +244,12 @@ name_scope = device = control_dependencies = _noop
 def _get_variable(name, shape=None, dtype=None, initializer=None, trainable=True, regularizer=None, **_):
     sc = STATE.scope[-1]
     full = _join(sc.name, name)
+    if STATE.retrace:
+        if full not in STATE.vars:
+            raise ValueError("re-executed graph code asks for a new variable %s" % full)
+        if regularizer is not None:
+            _add_reg(STATE.vars[full], regularizer)
+        return STATE.vars[full]
     if full in STATE.vars:
         if not sc.reuse:
             raise ValueError("Variable %s already exists, disallowed (reuse not set)" % full)
@@ -245,8 +270,21 @@ def _get_variable(name, shape=None, dtype=None, initializer=None, trainable=True
     v = TT(t, name=full + ":0", trainable=bool(trainable))
     STATE.vars[full] = v
     if regularizer is not None:
-        STATE.collections.setdefault(GraphKeys.REGULARIZATION_LOSSES, []).append(regularizer(v))
+        _add_reg(v, regularizer)
     return v
+
+
+def _add_reg(v, regularizer):
+    """one REGULARIZATION_LOSSES entry per variable (added where TensorFlow adds it: at creation), re-evaluated on the
+    variable's current value when the graph code is re-executed"""
+    items = STATE.collections.setdefault(GraphKeys.REGULARIZATION_LOSSES, [])
+    t = regularizer(v)
+    t.var = v
+    for i, old in enumerate(items):
+        if getattr(old, "var", None) is v:
+            items[i] = t
+            return
+    items.append(t)
 
 
 def get_variable(*a, **k):
@@ -254,12 +292,17 @@ def get_variable(*a, **k):
 
 
 def Variable(value, trainable=True, name=None, **_):
+    if STATE.retrace:
+        v = STATE.anon_list[STATE.anon_i]
+        STATE.anon_i += 1
+        return v
     n = "Variable" if STATE.anon == 0 else "Variable_%d" % STATE.anon
     STATE.anon += 1
     full = _join(STATE.scope[-1].name, name or n)
     v = TT(torch.tensor(np.asarray(value, np.float64), dtype=F64, requires_grad=bool(trainable)), name=full + ":0",
            trainable=bool(trainable))
     STATE.vars.setdefault("__anon__/" + full, v)
+    STATE.anon_list.append(v)
     return v
 
 
@@ -392,7 +435,7 @@ def batch_normalization(x, mean, variance, offset, scale, variance_epsilon, name
 def random_normal(shape, mean=0.0, stddev=1.0, dtype=None, seed=None, name=None):
     """Unit-variance draws come from STATE.noise (queued by the caller, one array per call, shape checked): the
     generator script decides the numbers, the reference decides the SHAPE."""
-    unit = np.asarray(STATE.noise.pop(0), np.float64)
+    unit = np.asarray(STATE.noise.pop(0) if STATE.noise else STATE.noise_fn([int(q) for q in shape]), np.float64)
     assert list(unit.shape) == [int(s) for s in shape], ("tf.random_normal asked for", list(shape), "queued", unit.shape)
     return TT(mean + _raw(stddev) * torch.tensor(unit, dtype=F64))
 
@@ -673,15 +716,17 @@ class GradientDescentOptimizer(_Optimizer):
 class AdamOptimizer(_Optimizer):
     def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8, **_):
         super(AdamOptimizer, self).__init__(learning_rate)
-        self.b1, self.b2, self.eps, self.t, self.m, self.vv = beta1, beta2, epsilon, 0, {}, {}
+        self.b1, self.b2, self.eps = beta1, beta2, epsilon
+        self.st = STATE.slots("adam", lambda: {"t": 0, "m": {}, "v": {}})      # beta powers and slots outlive a re-execution
 
     def _apply(self, gv):
-        self.t += 1
-        lr_t = float(_raw(self.lr)) * np.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        self.st["t"] += 1
+        t = self.st["t"]
+        lr_t = float(_raw(self.lr)) * np.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
         with torch.no_grad():
             for g, v in gv:
-                m = self.m.setdefault(v, torch.zeros_like(v.v))
-                s = self.vv.setdefault(v, torch.zeros_like(v.v))
+                m = self.st["m"].setdefault(v, torch.zeros_like(v.v))
+                s = self.st["v"].setdefault(v, torch.zeros_like(v.v))
                 m.mul_(self.b1).add_((1.0 - self.b1) * g.v)
                 s.mul_(self.b2).add_((1.0 - self.b2) * g.v * g.v)
                 v.v -= lr_t * m / (torch.sqrt(s) + self.eps)
@@ -694,7 +739,8 @@ class RMSPropOptimizer(_Optimizer):
 
 class ExponentialMovingAverage(object):
     def __init__(self, decay, num_updates=None, **_):
-        self.decay, self.shadow = float(decay), {}
+        self.decay = float(decay)
+        self.shadow = STATE.slots("ema", dict)
         STATE.emas.append(self)
 
     def apply(self, var_list=None):
@@ -714,6 +760,46 @@ class ExponentialMovingAverage(object):
 
 def group(*ops, **_):
     return Op(ops)
+
+
+class Session(object):
+    """sess.run for the eager stand-in.  Without a feed_dict: reads / eager assigns.  With one: `rebuild(feeds)` re-executes
+    the reference's graph-building code on the current variables (STATE.begin_retrace) and returns the new model object; the
+    fetches -- attributes of the ORIGINAL model object, as the reference's scripts pass them -- are looked up by attribute
+    name on it.  Fetched tensors are evaluated on the pre-update state, then the fetched ops run (one run = one forward)."""
+    graph = None
+
+    def __init__(self, rebuild=None):
+        self.rebuild, self.names, self.log = rebuild, {}, []
+
+    def bind(self, model):
+        self.names = {id(v): k for k, v in vars(model).items() if v is not None}
+
+    @staticmethod
+    def _value(o):
+        if isinstance(o, (list, tuple)):
+            return [Session._value(e) for e in o]
+        if isinstance(o, TT):
+            return o.numpy()
+        return o
+
+    def run(self, fetches, feed_dict=None):
+        if fetches is None:
+            return None
+        single = not isinstance(fetches, (list, tuple))
+        fl = [fetches] if single else list(fetches)
+        if feed_dict is None:
+            out = [self._value(f) for f in fl]
+        else:
+            new = self.rebuild({k.name[:-2]: np.asarray(v, np.float64) for k, v in feed_dict.items()})
+            names = [self.names[id(f)] for f in fl]
+            self.log.append(names)
+            objs = [getattr(new, n) for n in names]
+            out = [None if isinstance(o, Op) else self._value(o) for o in objs]
+            for o in objs:
+                if isinstance(o, Op):
+                    o()
+        return out[0] if single else out
 
 
 class _Dummy(object):
@@ -761,7 +847,9 @@ def install():
                                        tensor_summary=lambda *a, **k: None, audio=lambda *a, **k: None,
                                        merge=lambda *a, **k: None, FileWriter=_Dummy)
     tf.losses = types.SimpleNamespace(mean_squared_error=mean_squared_error)
-    tf.logging = types.SimpleNamespace(WARN=30, log_first_n=lambda *a, **k: None)
+    tf.logging = types.SimpleNamespace(WARN=30, log_first_n=lambda *a, **k: None, info=lambda *a, **k: None)
+    tf.Session = Session
+    tf.errors = types.SimpleNamespace(OutOfRangeError=type("OutOfRangeError", (Exception,), {}))
     layers = types.ModuleType("tensorflow.contrib.layers")
     for n in "fully_connected conv2d batch_norm xavier_initializer l2_regularizer flatten".split():
         setattr(layers, n, getattr(me, n))
@@ -769,8 +857,11 @@ def install():
     for n in "LSTMCell MultiRNNCell DropoutWrapper RNNCell LSTMStateTuple".split():
         setattr(rnn, n, getattr(me, n))
     contrib = types.ModuleType("tensorflow.contrib")
-    contrib.layers, contrib.rnn = layers, rnn
+    slim = types.ModuleType("tensorflow.contrib.slim")          # utils/misc.py imports it; nothing on these paths calls it
+    contrib.layers, contrib.rnn, contrib.slim = layers, rnn, slim
     tf.contrib = contrib
+    import queue
     sys.modules.update({"tensorflow": tf, "tensorflow.contrib": contrib, "tensorflow.contrib.layers": layers,
-                        "tensorflow.contrib.rnn": rnn})
+                        "tensorflow.contrib.rnn": rnn, "tensorflow.contrib.slim": slim,
+                        "Queue": queue})                          # the reference's scripts are Python 2: `import Queue`
     return tf, STATE

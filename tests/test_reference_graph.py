@@ -208,3 +208,36 @@ def test_splice_feats_of_the_reference():
     for i in range(n):
         left, right = (int(v) for v in f["case%d|ctx" % i])
         assert np.array_equal(splice_feats(f["case%d|feats" % i], left, right), f["case%d|spliced" % i]), i
+
+
+def test_training_loop_of_the_reference():
+    """scripts/train_gan_rnn_placeholder.py:48-133 `train_one_iteration`, the reference's own loop, was run over a queue of
+    three minibatches (the second one an utterance short: skipped, :69-70), every sess.run re-executing the reference's graph
+    code on the current variables: per minibatch one d_opt, then two g_opt -- each g_opt seeing the discriminator the d_opt
+    before it produced, the second g_opt the generator the first one produced.  The oracle replays d_step, g_step, g_step per
+    full minibatch: returned mean losses (over update counts, :124-130), weights, EMA shadows, Adam step count, and the
+    generator output afterwards."""
+    fix = np.load(os.path.join(GOLD, "ref_graph_schedule.npz"))
+    c, gp, dp, batches = C.schedule_setup()
+    st = O.GanState(copy.deepcopy(gp), copy.deepcopy(dp), c["g_type"], "lstm")
+    kw = dict(mse_lambda=C.MSE_LAMBDA, l2_scale=c["l2_scale"])
+    acc = OrderedDict((k, []) for k in ("d_rl_loss", "d_fk_loss", "d_loss", "g_adv_loss", "g_mse_loss", "g_l2_loss", "g_loss"))
+    for x, y, ln in batches:
+        if x.shape[0] != c["B"]:
+            continue
+        tower = dict(x=x, y=y, lengths=ln)
+        Ld, _ = O.d_step(st, [tower], C.LR_D, **kw)
+        for k in ("d_rl_loss", "d_fk_loss", "d_loss"):
+            acc[k].append(Ld[0][k])
+        for _ in range(2):
+            Lg, _ = O.g_step(st, [tower], C.LR_G, **kw)
+            for k in ("g_adv_loss", "g_mse_loss", "g_l2_loss", "g_loss"):
+                acc[k].append(Lg[0][k])
+    assert np.allclose([np.mean(v) for v in acc.values()], fix["means"], rtol=1e-10)
+    assert st.adam_t == int(fix["adam_t"]) == 4
+    C.check(fix, "theta_g", st.g, rtol=1e-10)
+    C.check(fix, "theta_d", st.d, rtol=1e-10)
+    C.check(fix, "ema_g", st.g_ema, rtol=1e-10)
+    C.check(fix, "ema_d", st.d_ema, rtol=1e-10)
+    x0, _, l0 = batches[0]
+    assert close(O.g_lstm_fwd(st.g, x0, l0)[0], fix["g_after"], 1e-9)
