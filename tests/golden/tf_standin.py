@@ -6,7 +6,10 @@ here, where /root/reference exists) to produce tests/golden/ref_graph_*.npz; not
 
 What this is and is not.  Everything the reference WRITES is executed from its own source files: models/lstm.py,
 models/res_lstm_l.py, models/res_lstm_base.py, models/discriminator_lstm.py, models/discriminator_dnn.py, models/dnn.py,
-models/gan_rnn_placeholder.py, models/gan.py, models/BNLSTMCell.py, utils/ops.py.  What TensorFlow itself provides -- the
+models/rced.py, models/gan_rnn_placeholder.py, models/gan.py, models/dnn_trainer.py, models/dnn_trainer_single_gpu.py,
+models/BNLSTMCell.py, utils/ops.py, utils/bnorm.py, io_funcs/tfrecords_io.py (splice_feats) and the training loop
+`train_one_iteration` of scripts/train_gan_rnn_placeholder.py (its sess.run calls go to `Session`, which re-executes the
+reference's graph-building code on the current variables for every run).  What TensorFlow itself provides -- the
 op kernels and the library layers -- is restated here on torch float64 tensors (derivatives by torch autograd):
   * elementwise / reduction / shape ops: one line of torch each;
   * tf.contrib.layers.fully_connected (TF r1.4 contrib/layers/python/layers/layers.py): variable scope
@@ -16,6 +19,8 @@ op kernels and the library layers -- is restated here on torch float64 tensors (
     "bias" [4C] (zeros), "w_f_diag" / "w_i_diag" / "w_o_diag" [C], "projection/kernel" [C, P]; gate order i, j, f, o.
     The generator script checks this restatement against the reference's OWN statement of the same equations
     (models/BNLSTMCell.py:176-213, its three batch_norm calls replaced by the identity);
+  * tf.contrib.layers.conv2d (scope "Conv", NHWC, SAME), tf.nn.conv2d / conv1d with TensorFlow's SAME rule for strides,
+    tf.nn.conv2d_transpose taken literally as the gradient of conv2d (autograd), tf.pad SYMMETRIC;
   * MultiRNNCell ("multi_rnn_cell/cell_%d"), tf.nn.dynamic_rnn (scope "rnn"; past sequence_length: zero output, state
     copied through -- python/ops/rnn.py _rnn_step), GradientDescentOptimizer, AdamOptimizer (python/training/adam.py:
     lr_t = lr sqrt(1 - b2^t) / (1 - b1^t), var -= lr_t m / (sqrt(v) + eps)), ExponentialMovingAverage, clip_by_norm.
