@@ -322,6 +322,54 @@ def schedule_case():
           % (len(batches), len(sess.log) - 1, np.round(out["means"], 4)))
 
 
+def update_ops_case():
+    """WIRING ONLY (tf_standin.batch_norm): with batch_norm = True, which batch_norm UPDATE_OPS exist in the reference's graphs
+    -- one per graph COPY of a batch-normalised layer -- and which of them each optimizer's train op runs."""
+    import json
+    import models.gan as ref_frame_gan
+    import models.dnn_trainer as ref_mt
+    import models.dnn_trainer_single_gpu as ref_st
+    rng = np.random.default_rng(23)
+    res = OrderedDict()
+
+    def record(tag, opt_names):
+        ops = [o.name for o in S.collections.get(tf.GraphKeys.UPDATE_OPS, [])]
+        entry = OrderedDict(update_ops=ops)
+        for (opt, _), nm in zip(S.grad_log, opt_names):
+            entry[nm + "_runs"] = [o.name for o in opt.deps]
+        res[tag] = entry
+
+    base = dict(keep_prob=1.0, batch_norm=True, save_dir="/tmp/ref_graph", l2_scale=0.0, input_dim=257, output_dim=40,
+                disc_updates=1, gen_updates=2, init_mse_weight=10.0, init_disc_noise_std=0.0, d_learning_rate=1e-3,
+                g_learning_rate=8e-5)
+    # recurrent GAN: batch_norm sits on the lstm generator's first fully_connected only (models/lstm.py:61-67,84-85)
+    S.reset(); S.allow_bn = True
+    S.noise_fn = lambda shape: np.zeros(shape)
+    B, T = 2, 3
+    S.feeds = {"inputs": rng.standard_normal((B, T, 257)), "labels": rng.standard_normal((B, T, 40)), "lengths": np.full(B, float(T))}
+    with redirect_stdout(io.StringIO()):
+        ref_gan.GAN_RNN(Sess(), Namespace(batch_size=B, num_gpu=1, left_context=0, right_context=0, g_type="lstm", **base), ["gpu:0"])
+    record("gan_rnn_placeholder lstm, 1 tower", ["d_opt", "g_opt"])
+    # frame-level GAN: batch_norm on every hidden layer of the DNN generator and of discriminator_dnn
+    S.reset(); S.allow_bn = True; S.unknown_time = False
+    N = 4
+    x, y = rng.standard_normal((N, 257 * 11)), rng.standard_normal((N, 40))
+    with redirect_stdout(io.StringIO()):
+        ref_frame_gan.GAN(Sess(), Namespace(batch_size=N, left_context=5, right_context=5, g_type="dnn", **base), ["gpu:0"],
+                          tf_standin.TT(torch.tensor(x)), tf_standin.TT(torch.tensor(y)))
+    record("gan (frame level) dnn + discriminator_dnn, 1 tower", ["d_opt", "g_opt"])
+    for tag, mod in (("dnn_trainer_single_gpu dnn", ref_st), ("dnn_trainer (multi-tower trainer) dnn, 1 tower", ref_mt)):
+        S.reset(); S.allow_bn = True; S.unknown_time = False
+        with redirect_stdout(io.StringIO()):
+            mod.DNNTrainer(Sess(), Namespace(batch_size=N, left_context=5, right_context=5, g_type="dnn", **base), ["gpu:0"],
+                           tf_standin.TT(torch.tensor(x)), tf_standin.TT(torch.tensor(y)))
+        record(tag, ["g_opt"])
+    with open(os.path.join(HERE, "ref_graph_update_ops.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    for k, v in res.items():
+        print("update ops  %-50s %d in the graph; %s" % (k, len(v["update_ops"]), {n: len(o) for n, o in v.items() if n != "update_ops"}))
+
+
 def lstm_cell_case():
     """models/BNLSTMCell.py:176-213 -- the reference's own statement of the peephole LSTMP step -- with its three
     batch_norm calls replaced by the identity, over a few steps; against it: the stand-in's LSTMCell (checked here) and the
@@ -386,5 +434,6 @@ if __name__ == "__main__":
     frame_gan_case()
     dnn_trainer_case()
     schedule_case()
+    update_ops_case()
     for case in C.RCED_CASES:
         rced_case(case)

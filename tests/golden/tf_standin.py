@@ -64,6 +64,9 @@ class _State(object):
         self.persist = {}              # (kind, creation index within one build) -> optimizer slots / EMA shadows
         self.created = {}              # kind -> objects created in the current build
         self.noise_fn = None           # fallback for tf.random_normal when the queue is empty
+        self.allow_bn = False          # batch_norm stand-in (wiring only) enabled
+        self.ctrl = []                 # stack of control_dependencies op lists
+        self.ran_updates = []          # names of UPDATE_OPS executed, in order
 
     def begin_retrace(self, feeds):
         """One sess.run(fetches, feed_dict): the graph code runs again, on the same variable objects (current values), the
@@ -243,7 +246,19 @@ def _noop(*a, **k):
     yield
 
 
-name_scope = device = control_dependencies = _noop
+name_scope = device = _noop
+
+
+@contextlib.contextmanager
+def control_dependencies(ops):
+    """What is created inside depends on `ops`.  The one use in the reference's graph code is around compute_gradients
+    (gan_rnn_placeholder.py:163-175, gan.py:139-143, dnn_trainer*.py): the stand-in records the ops on the optimizer whose
+    compute_gradients runs inside, and that optimizer's apply op runs them first."""
+    STATE.ctrl.append([o for o in (ops or []) if isinstance(o, Op)])
+    try:
+        yield
+    finally:
+        STATE.ctrl.pop()
 
 
 def _get_variable(name, shape=None, dtype=None, initializer=None, trainable=True, regularizer=None, **_):
@@ -546,9 +561,37 @@ def nn_conv2d_transpose(value, filter, output_shape, strides, padding="SAME", **
     return TT(torch.autograd.grad(y, z, grad_outputs=v, create_graph=True)[0])
 
 
-def batch_norm(*a, **k):
-    raise NotImplementedError("contrib batch_norm is outside the fixtures (batch_norm = False, as in the shipped drivers "
-                              "of the recurrent GAN)")
+def batch_norm(inputs, is_training=True, scale=False, renorm=False, decay=0.999, epsilon=0.001, scope=None, reuse=None, **_):
+    """WIRING ONLY.  contrib batch_norm's arithmetic (renorm corrections, zero-debiased renorm averages) is TensorFlow library
+    code and is NOT restated here: this stand-in normalises with the plain batch moments and exists so that the reference's
+    graph code can be executed with batch_norm = True and the UPDATE_OPS it collects -- which copies of which network, run by
+    which optimizer -- can be recorded.  Per call (= per graph copy) it registers one update op in GraphKeys.UPDATE_OPS,
+    named after the variable scope like TensorFlow's (`<scope>/BatchNorm/AssignMovingAvg`), plus a serial number."""
+    if not STATE.allow_bn:
+        raise NotImplementedError("contrib batch_norm arithmetic is outside the numeric fixtures (tf_standin.batch_norm docstring)")
+    with variable_scope(scope, "BatchNorm", [inputs], reuse=reuse) as sc:
+        x = _raw(inputs)
+        n = x.shape[-1]
+        beta = _get_variable("beta", [n], initializer=zeros_initializer())
+        gamma = _get_variable("gamma", [n], initializer=ones_initializer()) if scale else None
+        mm = _get_variable("moving_mean", [n], initializer=zeros_initializer(), trainable=False)
+        mv = _get_variable("moving_variance", [n], initializer=ones_initializer(), trainable=False)
+        red = list(range(x.dim() - 1))
+        if is_training:
+            mean, var = x.mean(dim=red), x.var(dim=red, unbiased=False)
+            def update(mean=mean.detach(), var=var.detach()):
+                with torch.no_grad():
+                    mm.v -= (1.0 - decay) * (mm.v - mean)
+                    mv.v -= (1.0 - decay) * (mv.v - var)
+            op = Op([update])
+            op.name = "%s/AssignMovingAvg#%d" % (sc.name, len(STATE.collections.setdefault(GraphKeys.UPDATE_OPS, [])))
+            STATE.collections[GraphKeys.UPDATE_OPS].append(op)
+        else:
+            mean, var = mm.v, mv.v
+        y = (x - mean) * torch.rsqrt(var + epsilon)
+        if gamma is not None:
+            y = y * gamma.v
+        return TT(y + beta.v)
 
 
 def flatten(x, **_):
@@ -692,18 +735,28 @@ def dynamic_rnn(cell, inputs, sequence_length=None, initial_state=None, dtype=No
 class _Optimizer(object):
     def __init__(self, learning_rate):
         self.lr = learning_rate
+        self.deps = []                 # ops its compute_gradients calls were made to depend on (control_dependencies)
+
+    def _run_deps(self):
+        for o in self.deps:
+            STATE.ran_updates.append(getattr(o, "name", "?"))
+            o()
 
     def compute_gradients(self, loss, var_list=None):
         vs_ = list(var_list)
         g = torch.autograd.grad(_raw(loss), [v.v for v in vs_], retain_graph=True, allow_unused=True)
         gv = [(None if gi is None else TT(gi.detach().clone()), v) for gi, v in zip(g, vs_)]
         STATE.grad_log.append((self, gv))
+        for ops in STATE.ctrl:
+            for o in ops:
+                if o not in self.deps:
+                    self.deps.append(o)
         return gv
 
     def apply_gradients(self, grads_and_vars, global_step=None, name=None):
         gv = list(grads_and_vars)
         STATE.apply_log.append((self, gv))
-        return Op([lambda: self._apply(gv)])
+        return Op([self._run_deps, lambda: self._apply(gv)])
 
 
     def minimize(self, loss, global_step=None, var_list=None, **_):

@@ -241,3 +241,32 @@ def test_training_loop_of_the_reference():
     C.check(fix, "ema_d", st.d_ema, rtol=1e-10)
     x0, _, l0 = batches[0]
     assert close(O.g_lstm_fwd(st.g, x0, l0)[0], fix["g_after"], 1e-9)
+
+
+def test_update_ops_wiring_of_the_reference():
+    """Which batch_norm UPDATE_OPS the reference's graphs hold and which train op runs them (wiring only: the stand-in's
+    batch_norm does not restate contrib's arithmetic).  gan_rnn_placeholder.py:163-175: g_opt runs the g_model updates, d_opt
+    the d_model ones (none: discriminator_lstm has no normalised layer); gan.py:139-143 and dnn_trainer*.py: every train op
+    runs the whole collection.  One update op exists per graph COPY of a layer: tower 0 builds the generator twice (reuse=False,
+    then reuse=True, :196-205) and the discriminator three times (dummy, labels, G(x)), so the reference assigns the same
+    moving averages two / three times per run, unlocked and in no defined order -- between one and two (three) effective
+    updates.  The oracle and the product apply one per pass the loss uses (G once; D on labels, then on G(x)): inside that
+    envelope, recorded in DESIGN.md section 2.  dnn_trainer_single_gpu.py builds one copy: no ambiguity there."""
+    import json
+    with open(os.path.join(GOLD, "ref_graph_update_ops.json")) as f:
+        w = json.load(f)
+    net = lambda names: sorted({n.split("/")[0] for n in names})
+    copies = lambda names, layer: sum(1 for n in names if n.split("#")[0] == layer + "/BatchNorm/AssignMovingAvg")
+    r = w["gan_rnn_placeholder lstm, 1 tower"]
+    assert r["d_opt_runs"] == [] and net(r["g_opt_runs"]) == ["g_model"] and copies(r["update_ops"], "g_model/fully_connected") == 2
+    r = w["gan (frame level) dnn + discriminator_dnn, 1 tower"]
+    assert r["d_opt_runs"] == r["g_opt_runs"] == r["update_ops"] and net(r["update_ops"]) == ["d_model", "g_model"]
+    assert copies(r["update_ops"], "g_model/fully_connected_1") == 2 and copies(r["update_ops"], "d_model/fully_connected_1") == 3
+    r = w["dnn_trainer_single_gpu dnn"]
+    assert r["g_opt_runs"] == r["update_ops"] and copies(r["update_ops"], "g_model/fully_connected") == 1
+    r = w["dnn_trainer (multi-tower trainer) dnn, 1 tower"]
+    assert r["g_opt_runs"] == r["update_ops"] and copies(r["update_ops"], "g_model/fully_connected") == 2
+    # the product's association of networks to updates is the reference's (rsrgan_b200/gan_rnn.py::_mode, gan.py, dnn_trainer.py)
+    from rsrgan_b200 import gan_rnn, gan as frame_gan
+    src = open(gan_rnn.__file__).read() + open(frame_gan.__file__).read()
+    assert "g_update" in src and "d_update" in src
