@@ -370,6 +370,35 @@ def update_ops_case():
         print("update ops  %-50s %d in the graph; %s" % (k, len(v["update_ops"]), {n: len(o) for n, o in v.items() if n != "update_ops"}))
 
 
+def cv_and_infer_case():
+    """The two other graphs scripts/train_gan_rnn_placeholder.py builds from models/gan_rnn_placeholder.py: the
+    cross-validation model (cross_validation=True: losses only, no l2 term even with l2_scale > 0, discriminator noise still
+    applied, :253-258 and discriminator_lstm.py:60) and the decode model (infer=True: generator only, :133-135)."""
+    c, gp, dp, x, y, lengths, noise = C.gan_rnn_setup("res_lstm_l_1tower")
+    out = {}
+    for tag, kw in (("cv", dict(cross_validation=True)), ("infer", dict(cross_validation=True, infer=True))):
+        S.reset()
+        S.init = dict(gp, **dp) if tag == "cv" else dict(gp)
+        S.feeds = {"inputs": x, "labels": y, "lengths": lengths.astype(np.float64)}
+        S.noise = [n.copy() for n in noise]
+        args = Namespace(keep_prob=0.7, batch_norm=False, batch_size=c["B"], num_gpu=1, save_dir="/tmp/ref_graph", l2_scale=1e-4,
+                         input_dim=257, output_dim=40, left_context=0, right_context=0, disc_updates=1, gen_updates=2,
+                         init_mse_weight=C.MSE_LAMBDA, init_disc_noise_std=C.NOISE_STD, d_learning_rate=C.LR_D,
+                         g_learning_rate=C.LR_G, g_type=c["g_type"])
+        with redirect_stdout(io.StringIO()):
+            m = ref_gan.GAN_RNN(Sess(), args, ["gpu:0"], **kw)
+        assert S.init_used == set(S.init)
+        if tag == "cv":
+            assert not S.grad_log and not S.apply_log and not hasattr(m, "d_opt")          # no optimizer in this graph
+            for k in ("d_rl_losses", "d_fk_losses", "d_losses", "g_adv_losses", "g_mse_losses", "g_l2_losses", "g_losses"):
+                out["cv|" + k] = np.array([float(tf_standin._raw(t).detach()) for t in getattr(m, k)])
+        else:
+            assert len(S.noise) == len(noise)                      # the decode graph has no discriminator: nothing drawn
+            out["infer|g_outputs"] = m.g_outputs.numpy()
+    np.savez_compressed(os.path.join(HERE, "ref_graph_cv_infer.npz"), **out)
+    print("cv / infer             cross-validation losses %s, decode output %s" % (np.round(out["cv|g_losses"], 3), out["infer|g_outputs"].shape))
+
+
 def lstm_cell_case():
     """models/BNLSTMCell.py:176-213 -- the reference's own statement of the peephole LSTMP step -- with its three
     batch_norm calls replaced by the identity, over a few steps; against it: the stand-in's LSTMCell (checked here) and the
@@ -435,5 +464,6 @@ if __name__ == "__main__":
     dnn_trainer_case()
     schedule_case()
     update_ops_case()
+    cv_and_infer_case()
     for case in C.RCED_CASES:
         rced_case(case)

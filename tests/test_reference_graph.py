@@ -270,3 +270,18 @@ def test_update_ops_wiring_of_the_reference():
     from rsrgan_b200 import gan_rnn, gan as frame_gan
     src = open(gan_rnn.__file__).read() + open(frame_gan.__file__).read()
     assert "g_update" in src and "d_update" in src
+
+
+def test_cross_validation_and_decode_graphs_of_the_reference():
+    """GAN_RNN(cross_validation=True) and GAN_RNN(infer=True) of models/gan_rnn_placeholder.py executed over the stand-in
+    (res_lstm_l): the cross-validation losses carry no l2 term although l2_scale > 0 (:253-258), keep_prob is forced to 1
+    (:72-75), the discriminator noise is still applied (discriminator_lstm.py:60); the decode graph is the generator alone."""
+    f = np.load(os.path.join(GOLD, "ref_graph_cv_infer.npz"))
+    c, gp, dp, x, y, lengths, noise = C.gan_rnn_setup("res_lstm_l_1tower")
+    st = O.GanState(copy.deepcopy(gp), copy.deepcopy(dp), c["g_type"], "lstm")
+    L, _, g_out = O.tower_losses_and_grads(st, x, y, lengths, "g", C.NOISE_STD * noise[1], C.NOISE_STD * noise[2],
+                                           mse_lambda=C.MSE_LAMBDA, l2_scale=0.0)
+    for fk, ok in LOSS_KEYS:
+        assert L.get(ok, 0.0) == pytest.approx(float(f["cv|" + fk][0]), rel=1e-10, abs=1e-14), fk
+    assert float(f["cv|g_l2_losses"][0]) == 0.0
+    assert close(g_out, f["infer|g_outputs"])
