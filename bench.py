@@ -159,14 +159,31 @@ def ncu_traffic(call):
     return tot / n if n else None
 
 
+def cpu_sample_utterances(cfg, cb):
+    """Utterances per CPU schedule: the WHOLE minibatch of the config when one schedule of it takes about four seconds or
+    less on this host (probed with one schedule of ~3200 frames), else as many utterances as fit that time, never fewer than
+    the ~3200-frame probe.  (cfg-2 on the 16-core GPU box: 128 of 128 utterances, ~2 s per schedule.)"""
+    B, T = cfg["B"], cfg["T"]
+    Bs0 = max(1, min(B, 3200 // T))
+    if Bs0 >= B:
+        return B
+    v, _, _ = cb.time_schedule(cfg, Bs0, T, steps=1, warmup=1)
+    return int(min(B, max(Bs0, v * 4.0 / T)))
+
+
+def sample_text(Bs, cfg):
+    if Bs == cfg["B"]:
+        return "the whole minibatch: %d utterances x %d frames per step" % (Bs, cfg["T"])
+    return "%d of %d utterances x %d frames per step" % (Bs, cfg["B"], cfg["T"])
+
+
 def run_reference(a, cfg):
     """CPU arm: oracle/cpu_baseline.py (port of the reference schedule) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import cpu_baseline as cb
-    Bs = max(1, min(cfg["B"], 3200 // cfg["T"]))   # bounded sample of ~3200 frames per step (cfg-2: 32 utterances x 100;
-                                                   # the CPU port runs 1.7x more frames/s on 32 utterances than on 8)
+    Bs = cpu_sample_utterances(cfg, cb)            # the whole minibatch when the host is fast enough, else a bounded sample
     gan = cb.CpuGan(cfg, 1234)
     import torch
     g = torch.Generator().manual_seed(1234)
@@ -180,12 +197,12 @@ def run_reference(a, cfg):
         gan.schedule(x, y, ln)
     dt = (time.perf_counter() - t0) / max(a.steps, 1)
     v = Bs * cfg["T"] / dt
-    sample = "%d of %d utterances x %d frames per step (same networks, same schedule), torch-CPU fp32" % (Bs, cfg["B"], cfg["T"])
+    sample = sample_text(Bs, cfg) + " (same networks, same schedule), torch-CPU fp32"
     print(json.dumps({
         "impl": "reference", "metric": "gan_train_frames_per_sec", "value": v, "unit": "frames/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["name"], "sample": sample},
+        "config": {"workload": cfg["name"], "sample": sample, "same_config": bool(Bs == cfg["B"])},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -362,11 +379,11 @@ def main():
         out["clocks"] = sampler.summary()
         if world == 1 and not a.no_cpu_baseline:
             from oracle import cpu_baseline as cb
-            Bs = max(1, min(B, 3200 // T))
+            Bs = cpu_sample_utterances(cfg, cb)
             v, dt, cores = cb.time_schedule(cfg, Bs, T, steps=2, warmup=0)
             out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                                   "sample": "%d of %d utterances x %d frames, 2 schedules (median), torch-CPU fp32 restatement "
-                                             "of the reference (TF-1.4 unavailable)" % (Bs, B, T)}
+                                   "sample": sample_text(Bs, cfg) + ", 2 schedules (median), torch-CPU fp32 restatement "
+                                                                    "of the reference (TF-1.4 unavailable)"}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(out), flush=True)
