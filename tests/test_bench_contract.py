@@ -51,3 +51,25 @@ def test_committed_gpu_line_has_the_contract_keys():
     assert 0 < e["value"] <= d["value"] * 1.02
     assert d["clocks"]["sm_mhz"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_cpu_sample_is_the_whole_minibatch_when_the_host_is_fast_enough():
+    """bench.cpu_sample_utterances: the CPU arm runs the config's whole minibatch when one schedule of it fits ~4 s (probed on
+    ~3200 frames), else a bounded sample, never fewer utterances than the probe."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class Fake(object):
+        def __init__(self, rate):
+            self.rate, self.calls = rate, []
+
+        def time_schedule(self, cfg, B, T, steps=1, warmup=0):
+            self.calls.append((B, T))
+            return self.rate, B * T / self.rate, 16
+    cfg = dict(B=128, T=100)
+    fast, slow, mid = Fake(7000.0), Fake(500.0), Fake(2000.0)
+    assert bench.cpu_sample_utterances(cfg, fast) == 128 and fast.calls == [(32, 100)]
+    assert bench.cpu_sample_utterances(cfg, slow) == 32
+    assert bench.cpu_sample_utterances(cfg, mid) == 80
+    assert bench.cpu_sample_utterances(dict(B=8, T=100), Fake(1.0)) == 8            # already the whole minibatch: no probe
+    assert bench.sample_text(128, cfg).startswith("the whole minibatch") and bench.sample_text(32, cfg).startswith("32 of 128")
